@@ -1,0 +1,178 @@
+/* mishagpu.h -- C ABI of the B200-native track-extraction / aggregation path (libmishagpu.so).
+ *
+ * This is boundary B2 of SURVEY.md 8(b): what misha's host C++ (the .Call entry points, TrackExprScanner,
+ * TrackExpressionVars) calls INSTEAD of its per-row CPU arithmetic. Plain C: opaque handles, pointers and
+ * sizes; no SEXP, no C++ types, no torch types. Every function returns 0 on success and a non-zero status on
+ * failure (message via mg_last_error); nothing throws or longjmps across the boundary. There is no CPU
+ * fallback behind any entry point.
+ *
+ * Reference interfaces replaced (paths under the misha checkout, v5.11.20):
+ *   staging      GenomeTrackFixedBin::init_read        src/GenomeTrackFixedBin.cpp:1129   -> mg_dense_stage
+ *                GenomeTrackSparse::read_file_into_mem src/GenomeTrackSparse.cpp:162-235  -> mg_sparse_stage
+ *                add_vtrack_var_src_interv             src/TrackExpressionVars.cpp:1292-1301 -> mg_ivset_stage
+ *                GenomeSeqFetch::read_interval         src/GenomeSeqFetch.cpp:50-175      -> mg_seq_stage
+ *   rows         TrackExpressionFixedBinIterator::next src/TrackExpressionFixedBinIterator.cpp:29-62 -> mg_rows_fixedbin
+ *                TrackExpressionIntervals1DIterator    src/TrackExpressionIntervals1DIterator.cpp:21-85 -> mg_rows_intervals
+ *   per-row work TrackExpressionVars::set_vars         src/TrackExpressionVars.cpp:2080-2150:
+ *                  Iterator_modifier1D::transform      src/TrackExpressionVars.h:395-402  (sshift/eshift clamp)
+ *                  GenomeTrackFixedBin::read_interval  src/GenomeTrackFixedBin.cpp:607-1016 -> mg_dense_window
+ *                  GenomeTrackSparse::read_interval    src/GenomeTrackSparse.cpp:237-340  -> mg_sparse_window
+ *                  IntervVarProcessor::process_coverage src/IntervVarProcessor.cpp:242-325 -> mg_coverage
+ *                  PWMScorer::score_interval           src/PWMScorer.cpp:742-861          -> mg_pwm
+ *   consumers    IntervalSummary::update/merge         src/GenomeTrackSummary.cpp:22-69   -> mg_summary*, mg_summary_finalize
+ *                BinsManager::vals2idx + counters      src/BinsManager.h:53-72, src/GenomeTrackDistribution.cpp:121-141 -> mg_hist*
+ *                C_gscreen run merge                   src/GenomeTrackScreener.cpp:195-220 -> mg_screen_merge
+ *
+ * Conventions
+ *   - One mg_ctx per process and GPU; calls on one ctx are serialised by the caller (R is single-threaded).
+ *   - "d_" pointers are device memory on the ctx's GPU, "h_" pointers host memory (pinned recommended).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). Device entry points only
+ *     enqueue work; the caller synchronises (mg_sync) before reading results.
+ *   - Value columns are double (R numeric) holding float32-rounded values exactly as the reference's float
+ *     members widened to double (src/GenomeTrack1D.h:58-103).
+ */
+#ifndef MISHAGPU_H_
+#define MISHAGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+typedef struct mg_ctx mg_ctx;
+typedef struct mg_dense mg_dense;   /* dense fixed-bin track staged in HBM (all chromosomes) */
+typedef struct mg_sparse mg_sparse; /* sparse track staged in HBM */
+typedef struct mg_ivset mg_ivset;   /* sorted, overlap-unified interval set (coverage source) */
+typedef struct mg_seq mg_seq;       /* 2-bit packed genome sequence + validity mask */
+typedef struct mg_rows mg_rows;     /* iterator rows resident on the device (explicit, or implicit fixed-bin) */
+
+/* Virtual-track functions (gvtrack.create `func`, R/vtrack.R; Track_var::Val_func src/TrackExpressionVars.h:118-163). */
+enum mg_func {
+	MG_AVG = 0,      /* "avg"; a bare dense track name */
+	MG_SUM = 1,      /* "sum" */
+	MG_MIN = 2,      /* "min" */
+	MG_MAX = 3,      /* "max" */
+	MG_STDDEV = 4,   /* "stddev" */
+	MG_QUANTILE = 5, /* "quantile", param = percentile */
+	MG_NEAREST = 6,  /* "nearest" (dense: == avg) */
+	MG_SIZE = 7,     /* "size": number of non-NaN values */
+	MG_EXISTS = 8,   /* "exists" */
+	MG_NUM_FUNCS = 9
+};
+
+/* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */
+enum mg_pwm_mode { MG_PWM_TOTAL = 0 /* "pwm" */, MG_PWM_MAX = 1 /* "pwm.max" */, MG_PWM_COUNT = 3 /* "pwm.count" */ };
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int mg_abi_version(void);
+/* chrom_sizes[chromid] as GenomeChromKey (src/GenomeChromKey.h) holds them; fixed for the ctx lifetime. */
+int mg_init(int device, int nchroms, const int64_t *chrom_sizes, mg_ctx **out);
+void mg_shutdown(mg_ctx *ctx);
+const char *mg_last_error(const mg_ctx *ctx); /* ctx may be NULL: error of the last failed mg_init in this thread */
+int mg_sync(mg_ctx *ctx, void *stream);
+/* number of kernels this ctx has launched since mg_init (bench.py's gpu_launches claim) */
+int64_t mg_launch_count(const mg_ctx *ctx);
+/* device properties of the ctx's GPU: SM count, bytes of HBM, compute capability major*10+minor */
+int mg_device_info(const mg_ctx *ctx, int *sm_count, int64_t *hbm_bytes, int *cc);
+
+/* plumbing for hosts that have no other CUDA binding (the Python mirror uses these; R/C++ hosts may too) */
+int mg_dev_alloc(mg_ctx *ctx, int64_t bytes, void **d_ptr);
+int mg_dev_free(mg_ctx *ctx, void *d_ptr);
+int mg_host_alloc(mg_ctx *ctx, int64_t bytes, void **h_ptr); /* pinned */
+int mg_host_free(mg_ctx *ctx, void *h_ptr);
+int mg_copy_h2d(mg_ctx *ctx, void *d_dst, const void *h_src, int64_t bytes, void *stream);
+int mg_copy_d2h(mg_ctx *ctx, void *h_dst, const void *d_src, int64_t bytes, void *stream);
+int mg_dev_memset(mg_ctx *ctx, void *d_ptr, int value, int64_t bytes, void *stream);
+
+/* ---- staging ("stages chromosome track blocks into HBM once") ------------------------------------------ */
+/* Dense: h_bins = payload of the per-chromosome file after the 4-byte bin-size header (may hold +-inf, which */
+/* become NaN on load as in read_bins_bulk). Builds the per-chromosome prefix sums used by avg/sum.           */
+int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out);
+int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float *h_bins, int64_t nbins);
+void mg_dense_free(mg_ctx *ctx, mg_dense *t);
+int64_t mg_dense_bytes(const mg_dense *t); /* HBM bytes held */
+
+/* Sparse: records sorted by start, non-overlapping, 0 <= start < end (validated; error otherwise).          */
+int mg_sparse_create(mg_ctx *ctx, mg_sparse **out);
+int mg_sparse_stage(mg_ctx *ctx, mg_sparse *t, int chromid, const int64_t *h_start, const int64_t *h_end, const float *h_val, int64_t n);
+void mg_sparse_free(mg_ctx *ctx, mg_sparse *t);
+
+/* Interval set for `coverage`: per chromosome, sorted by start and overlap-unified by the caller.           */
+int mg_ivset_create(mg_ctx *ctx, mg_ivset **out);
+int mg_ivset_stage(mg_ctx *ctx, mg_ivset *s, int chromid, const int64_t *h_start, const int64_t *h_end, int64_t n);
+void mg_ivset_free(mg_ctx *ctx, mg_ivset *s);
+
+/* Sequence: h_ascii = seq/<chrom>.seq bytes (1 per base, mixed case, N = unknown). Packed on the device.    */
+int mg_seq_create(mg_ctx *ctx, mg_seq **out);
+int mg_seq_stage(mg_ctx *ctx, mg_seq *s, int chromid, const char *h_ascii, int64_t len);
+void mg_seq_free(mg_ctx *ctx, mg_seq *s);
+
+/* ---- iterator rows --------------------------------------------------------------------------------------- */
+/* Explicit rows uploaded from the host (already in output order). */
+int mg_rows_upload(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, void *stream, mg_rows **out);
+/* Explicit rows over caller-owned device arrays (not copied, not freed). */
+int mg_rows_wrap(mg_ctx *ctx, int64_t n, const int32_t *d_chrom, const int64_t *d_start, const int64_t *d_end, mg_rows **out);
+/* Implicit fixed-bin iterator over a scope sorted by (chromid,start): rows are never materialised. */
+int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, mg_rows **out);
+/* Intervals iterator: iterator intervals (sorted, unified with touching kept apart) x sorted scope, computed on */
+/* the device; h_ arrays are host memory. */
+int mg_rows_intervals(mg_ctx *ctx, int64_t niter, const int32_t *h_ichrom, const int64_t *h_istart, const int64_t *h_iend, int64_t nscope,
+					  const int32_t *h_schrom, const int64_t *h_sstart, const int64_t *h_send, void *stream, mg_rows **out);
+int64_t mg_rows_count(const mg_rows *r);
+/* Coordinates (and the scope index each row came from, -1 for uploaded rows) of rows [first, first+count) into */
+/* device arrays; any output may be NULL. */
+int mg_rows_coords(mg_ctx *ctx, const mg_rows *r, int64_t first, int64_t count, int32_t *d_chrom, int64_t *d_start, int64_t *d_end,
+				   int64_t *d_scope_idx, void *stream);
+void mg_rows_free(mg_ctx *ctx, mg_rows *r);
+
+/* ---- per-row vtrack values (device in, device out) --------------------------------------------------------- */
+/* For rows [first, first+count): window = clamp(row +- shift); d_out[k][i] = funcs[k] of row first+i.         */
+int mg_dense_window(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+					int nfuncs, const int *funcs, const double *params, double *const *d_out, void *stream);
+int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+					 int nfuncs, const int *funcs, const double *params, double *const *d_out, void *stream);
+int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+				double *d_out, void *stream);
+/* h_logp: L x 4 float log-probabilities (A,C,G,T) after normalisation and prior (mg_pssm_logp). strand: 1 / -1. */
+int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
+		   const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream);
+/* PSSM rows (L x 4 probabilities, A,C,G,T) -> the float log table the reference scores with                    */
+/* (src/PWMScorer.cpp:1452-1459, src/DnaPSSM.cpp:77-106,703-719). Host arithmetic, float, bit-exact.            */
+int mg_pssm_logp(const double *h_pssm, int L, double prior, float *h_logp);
+
+/* ---- consumers: gsummary / gdist / gscreen ------------------------------------------------------------------ */
+/* Partial summary = {num_bins, num_non_nan, sum, min, max, sum_sq} (IntervalSummary's six doubles), ACCUMULATED  */
+/* into d_partial (initialise with mg_summary_init). Sums are order-dependent to ~1 ulp; counts/min/max exact.   */
+int mg_summary_init(mg_ctx *ctx, double *d_partial, void *stream);
+int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *d_partial, void *stream);
+/* fused: summary of one dense-track function over rows, values never leave the chip */
+int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+					 int func, double param, double *d_partial, void *stream);
+/* host arithmetic of gtracksummary's result vector (src/GenomeTrackSummary.cpp:148-155): 6 partials -> 7 outputs */
+void mg_summary_finalize(const double partial[6], double out[7]);
+
+/* N-D histogram (gdist). h_breaks = concatenated break vectors, nbreaks[d] each; d_counts has prod(nbreaks[d]-1)  */
+/* uint64 cells, first dimension fastest; counts are ACCUMULATED (zero them first). Bit-exact bins.               */
+int mg_hist(mg_ctx *ctx, int ndim, const double *const *d_cols, int64_t n, const double *h_breaks, const int *nbreaks, int include_lowest,
+			uint64_t *d_counts, void *stream);
+int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+				  int func, double param, const double *h_breaks, int nbreaks, int include_lowest, uint64_t *d_counts, void *stream);
+
+/* gscreen: merge consecutive TRUE rows (d_flag[i] == 1) of rows [first, first+count) into intervals. Outputs are   */
+/* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */
+int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
+					int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream);
+
+/* ---- host-buffer convenience: what a .Call entry point does per vtrack group --------------------------------- */
+/* Host arrays in, host columns out; uploads, kernels and downloads are chunked and overlapped on internal        */
+/* streams. This is the end-to-end path bench.py times as `e2e`.                                                  */
+int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+					  int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISHAGPU_H_ */

@@ -1,0 +1,128 @@
+// common.cuh -- context, error plumbing and small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/mishagpu.h"
+
+#define MG_SM_COUNT_B200 148
+
+struct mg_ctx {
+	int device = 0;
+	int sm_count = MG_SM_COUNT_B200;
+	int cc = 0;
+	int64_t hbm_bytes = 0;
+	int nchroms = 0;
+	std::vector<int64_t> chrom_sizes;
+	int64_t *d_chrom_sizes = nullptr;
+	int64_t launches = 0;
+	std::string err;
+	// internal streams + staging buffers of the host-buffer entry points (lazily created)
+	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+	void *pipe_dev[3] = {nullptr, nullptr, nullptr};
+	int64_t pipe_dev_bytes[3] = {0, 0, 0};
+};
+
+extern thread_local std::string g_mg_init_err;
+
+static inline int mg_fail(mg_ctx *ctx, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx)
+		ctx->err = buf;
+	else
+		g_mg_init_err = buf;
+	return 1;
+}
+
+#define MG_CUDA(ctx, call)                                                                                             \
+	do {                                                                                                               \
+		cudaError_t e__ = (call);                                                                                      \
+		if (e__ != cudaSuccess)                                                                                        \
+			return mg_fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);          \
+	} while (0)
+
+#define MG_LAUNCH_CHECK(ctx)                                                                                           \
+	do {                                                                                                               \
+		(ctx)->launches++;                                                                                             \
+		cudaError_t e__ = cudaGetLastError();                                                                          \
+		if (e__ != cudaSuccess)                                                                                        \
+			return mg_fail(ctx, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__);      \
+	} while (0)
+
+#define MG_REQUIRE(ctx, cond, ...)                                                                                     \
+	do {                                                                                                               \
+		if (!(cond))                                                                                                   \
+			return mg_fail(ctx, __VA_ARGS__);                                                                          \
+	} while (0)
+
+static inline cudaStream_t mg_stream(void *s) { return (cudaStream_t)s; }
+
+static inline int64_t mg_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mg_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ float mg_nanf() { return __int_as_float(0x7fc00000); }
+
+// float member widened to double, as the reference's last_*() accessors feed var[idx] (src/TrackVarProcessor.cpp:113-173)
+__device__ __forceinline__ double mg_f2d(double x) { return (double)__double2float_rn(x); }
+
+// streaming loads/stores: data touched once should not displace the reused working set in L1
+__device__ __forceinline__ float mg_ldg_f(const float *p) { return __ldg(p); }
+
+__device__ __forceinline__ void mg_st_stream(double *p, double v) { __stcs(p, v); }
+
+// Window transform, src/TrackExpressionVars.h:395-402. Returns false when out of range.
+__device__ __forceinline__ bool mg_window(int64_t start, int64_t end, int64_t sshift, int64_t eshift, int64_t chromsize, int64_t &ws,
+										  int64_t &we)
+{
+	ws = start + sshift;
+	we = end + eshift;
+	if (ws < 0)
+		ws = 0;
+	if (we > chromsize)
+		we = chromsize;
+	return ws < we;
+}
+
+// floor(a / b), ceil(a / b) for 0 <= a, 0 < b < 2^32 with a 32-bit fast path (genomic coordinates fit in 31 bits
+// for every genome misha ships; the 64-bit path keeps it general). Identical to the reference's
+// (int64_t)(a / b) and (int64_t)ceil(a / (double)b) for a < 2^53.
+__device__ __forceinline__ int64_t mg_floordiv(int64_t a, uint32_t b)
+{
+	if ((uint64_t)a <= 0xffffffffull)
+		return (int64_t)((uint32_t)a / b);
+	return a / (int64_t)b;
+}
+__device__ __forceinline__ int64_t mg_ceildiv(int64_t a, uint32_t b)
+{
+	if ((uint64_t)a <= 0xffffffffull) {
+		uint32_t q = (uint32_t)a / b;
+		return (int64_t)q + ((uint32_t)a - q * b != 0);
+	}
+	int64_t q = a / (int64_t)b;
+	return q + (a - q * (int64_t)b != 0);
+}
+
+__device__ __forceinline__ double mg_shfl_xor_d(double v, int m)
+{
+	return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ double mg_warp_sum_d(double v)
+{
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, m);
+	return v;
+}

@@ -1,0 +1,487 @@
+// dense.cuh -- dense fixed-bin tracks: staging (clean + prefix build) and per-row window functions.
+//
+// HBM layout per chromosome:
+//   vals[nbins (+pad)]  float32, +-inf already turned into NaN (read_bins_bulk, src/GenomeTrackFixedBin.cpp:1066-1069)
+//   pref[nbins + 1]     16-byte entries {double sum of non-NaN vals[0..i), int64 count of non-NaN vals[0..i)}
+// avg / sum / size / exists of any window are two 16-byte lookups (kernel k_dense_prefix); min / max / stddev /
+// quantile sweep the window with one warp per row (kernel k_dense_sweep).
+#pragma once
+#include "common.cuh"
+#include "rows.cuh"
+
+struct __align__(16) Pref {
+	double sum;
+	long long cnt;
+};
+
+struct DenseChrom {
+	const float *vals;
+	const Pref *pref;
+	int64_t nbins;
+	double abs_sum; // sum |v| over the chromosome: scale of the prefix rounding error (cancellation guard)
+};
+
+struct mg_dense {
+	uint32_t bin_size = 0;
+	int nchroms = 0;
+	std::vector<DenseChrom> h_table;
+	DenseChrom *d_table = nullptr;
+	std::vector<void *> allocs;
+	int64_t bytes = 0;
+};
+
+#define MG_MAX_Q 8
+
+struct DenseQuery {
+	RowSrc rows;
+	int64_t first, count;
+	int64_t sshift, eshift;
+	const DenseChrom *table;
+	const int64_t *chrom_sizes;
+	uint32_t bin_size;
+	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
+	int nq;
+	double q_pct[MG_MAX_Q];
+	double *q_out[MG_MAX_Q];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Staging. Tile = 256 threads x 8 bins.
+#define MG_ST_THREADS 256
+#define MG_ST_PER_THREAD 8
+#define MG_ST_TILE (MG_ST_THREADS * MG_ST_PER_THREAD)
+
+template <typename T>
+__device__ __forceinline__ T mg_block_excl_scan(T v, T *smem /* >= 32 entries */, T &block_total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	T incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		T o = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d)
+			incl += o;
+	}
+	if (lane == 31)
+		smem[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		T w = lane < nwarps ? smem[lane] : T(0);
+		T wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			T o = __shfl_up_sync(0xffffffffu, wi, d);
+			if (lane >= d)
+				wi += o;
+		}
+		smem[lane] = wi - w; // exclusive warp offsets
+		if (lane == 31)
+			smem[32] = wi; // grand total (nwarps <= 32, upper lanes carry zeros)
+	}
+	__syncthreads();
+	T res = smem[warp] + (incl - v);
+	block_total = smem[32];
+	__syncthreads();
+	return res;
+}
+
+// pass 1: +-inf -> NaN in place, per-tile {sum, count, abs sum}
+__global__ void __launch_bounds__(MG_ST_THREADS) k_dense_clean_reduce(float *vals, int64_t nbins, double *tile_sum, long long *tile_cnt,
+																	   double *tile_abs)
+{
+	__shared__ double sd[33];
+	__shared__ long long sc[33];
+	const int64_t base = (int64_t)blockIdx.x * MG_ST_TILE + (int64_t)threadIdx.x * MG_ST_PER_THREAD;
+	double s = 0, a = 0;
+	long long c = 0;
+#pragma unroll
+	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
+		int64_t i = base + j;
+		if (i < nbins) {
+			float v = vals[i];
+			if (isinf(v)) {
+				v = mg_nanf();
+				vals[i] = v;
+			}
+			if (!isnan(v)) {
+				s += (double)v;
+				a += fabs((double)v);
+				++c;
+			}
+		}
+	}
+	double ts, ta;
+	long long tc;
+	mg_block_excl_scan<double>(s, sd, ts);
+	mg_block_excl_scan<double>(a, sd, ta);
+	mg_block_excl_scan<long long>(c, sc, tc);
+	if (threadIdx.x == 0) {
+		tile_sum[blockIdx.x] = ts;
+		tile_cnt[blockIdx.x] = tc;
+		tile_abs[blockIdx.x] = ta;
+	}
+}
+
+// pass 2 (one block): exclusive scan of the tile totals in place; total abs sum -> *abs_total
+__global__ void __launch_bounds__(1024) k_dense_tile_scan(double *tile_sum, long long *tile_cnt, const double *tile_abs, int64_t ntiles,
+														  double *abs_total)
+{
+	__shared__ double sd[33];
+	__shared__ long long sc[33];
+	const int64_t chunk = (ntiles + blockDim.x - 1) / blockDim.x;
+	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, ntiles);
+	double s = 0, a = 0;
+	long long c = 0;
+	for (int64_t i = lo; i < hi; ++i) {
+		s += tile_sum[i];
+		c += tile_cnt[i];
+		a += tile_abs[i];
+	}
+	double ts, ta;
+	long long tc;
+	double s0 = mg_block_excl_scan<double>(s, sd, ts);
+	mg_block_excl_scan<double>(a, sd, ta);
+	long long c0 = mg_block_excl_scan<long long>(c, sc, tc);
+	for (int64_t i = lo; i < hi; ++i) {
+		double vs = tile_sum[i];
+		long long vc = tile_cnt[i];
+		tile_sum[i] = s0;
+		tile_cnt[i] = c0;
+		s0 += vs;
+		c0 += vc;
+	}
+	if (threadIdx.x == 0)
+		*abs_total = ta;
+}
+
+// pass 3: per-bin prefix entries. pref[i] = totals over vals[0..i); pref[nbins] is the chromosome total.
+__global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const float *vals, int64_t nbins, const double *tile_sum,
+																	   const long long *tile_cnt, Pref *pref)
+{
+	__shared__ double sd[33];
+	__shared__ long long sc[33];
+	const int64_t base = (int64_t)blockIdx.x * MG_ST_TILE + (int64_t)threadIdx.x * MG_ST_PER_THREAD;
+	float v[MG_ST_PER_THREAD];
+	double s = 0;
+	long long c = 0;
+#pragma unroll
+	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
+		int64_t i = base + j;
+		v[j] = i < nbins ? vals[i] : mg_nanf();
+		if (!isnan(v[j])) {
+			s += (double)v[j];
+			++c;
+		}
+	}
+	double ts;
+	long long tc;
+	double s0 = tile_sum[blockIdx.x] + mg_block_excl_scan<double>(s, sd, ts);
+	long long c0 = tile_cnt[blockIdx.x] + mg_block_excl_scan<long long>(c, sc, tc);
+#pragma unroll
+	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
+		int64_t i = base + j;
+		if (i <= nbins) {
+			Pref p;
+			p.sum = s0;
+			p.cnt = c0;
+			pref[i] = p;
+		}
+		if (!isnan(v[j])) {
+			s0 += (double)v[j];
+			++c0;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Window geometry shared by the row kernels. false => every function is NaN for this row.
+struct DenseWin {
+	const DenseChrom *ch;
+	int64_t sbin, ebin;
+};
+
+__device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, DenseWin &w)
+{
+	int chrom;
+	int64_t s, e, scope;
+	mg_get_row(q.rows, row, chrom, s, e, scope);
+	int64_t ws, we;
+	if (!mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we))
+		return false;
+	w.ch = q.table + chrom;
+	w.sbin = mg_floordiv(ws, q.bin_size);                 // src/GenomeTrackFixedBin.cpp:675
+	int64_t eb = mg_ceildiv(we, q.bin_size);              // :676
+	int64_t nb = w.ch->nbins;
+	w.ebin = eb < nb ? eb : nb;                           // read_bins_bulk clamp :1036-1041
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_dense_prefix: one thread per row; avg / sum / nearest / size / exists from two 16-byte prefix entries.
+// Windows of <= 4 bins, and windows whose prefix difference is small against the accumulated rounding scale
+// (catastrophic cancellation), are summed directly in bin order, which reproduces the reference bit for bit.
+#define MG_PREFIX_DIRECT_BINS 4
+
+__device__ __forceinline__ Pref mg_ld_pref(const Pref *p)
+{
+	const int4 r = __ldg(reinterpret_cast<const int4 *>(p)); // one 16-byte read-only load
+	Pref o;
+	o.sum = __hiloint2double(r.y, r.x);
+	o.cnt = (long long)(((unsigned long long)(unsigned)r.w << 32) | (unsigned)r.z);
+	return o;
+}
+
+__global__ void __launch_bounds__(256) k_dense_prefix(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan();
+	if (mg_dense_win(q, q.first + i, w)) {
+		long long n = 0;
+		double S = 0;
+		const int64_t nb = w.ebin - w.sbin;
+		bool direct = nb <= MG_PREFIX_DIRECT_BINS;
+		if (!direct && nb > 0) {
+			const Pref a = mg_ld_pref(w.ch->pref + w.sbin);
+			const Pref b = mg_ld_pref(w.ch->pref + w.ebin);
+			n = b.cnt - a.cnt;
+			S = b.sum - a.sum;
+			// rounding of each prefix entry is O(2^-53 * abs_sum); demand >= ~2^-27 relative accuracy of S
+			if (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */)
+				direct = true;
+		}
+		if (direct) {
+			n = 0;
+			S = 0;
+			for (int64_t b = w.sbin; b < w.ebin; ++b) {
+				float v = __ldg(w.ch->vals + b);
+				if (!isnan(v)) {
+					S += (double)v;
+					++n;
+				}
+			}
+		}
+		size = (double)n;
+		exists = n > 0 ? 1. : 0.;
+		if (n > 0) {
+			avg = mg_f2d(S / (double)n);
+			sum = mg_f2d(S);
+		}
+	}
+	if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
+	if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+	if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
+	if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
+	if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_dense_sweep: one warp per row, any function set. Lanes stride the window (coalesced 128-byte requests);
+// count / sum / min / max / Welford (mean, M2) are merged with shuffles. For quantiles the non-NaN values are
+// compacted into a per-warp shared-memory buffer and sorted there (bitonic); windows that do not fit are
+// selected by an 8-bit radix select that re-reads the window from L2/HBM.
+#define MG_SW_WARPS 8
+#define MG_SW_CAP 1024 // floats per warp buffer (4 KB); covers +-10 kb at 20 bp
+
+__device__ __forceinline__ uint32_t mg_fkey(float v)
+{
+	uint32_t b = __float_as_uint(v);
+	return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float mg_fkey_inv(uint32_t k)
+{
+	uint32_t b = k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu);
+	return __uint_as_float(b);
+}
+
+// bitonic sort of buf[0..P) (P power of two, padded with +inf) by one warp
+__device__ __forceinline__ void mg_warp_bitonic(float *buf, int P, int lane)
+{
+	for (int k = 2; k <= P; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = lane; t < (P >> 1); t += 32) {
+				int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+				int ixj = i | j;
+				float a = buf[i], b = buf[ixj];
+				bool up = (i & k) == 0;
+				if ((a > b) == up) {
+					buf[i] = b;
+					buf[ixj] = a;
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// k-th smallest (0-based) non-NaN value of vals[sbin..ebin) by MSD radix select, 8 bits per pass; hist = 256 uint32 in smem.
+__device__ float mg_warp_radix_select(const float *vals, int64_t sbin, int64_t ebin, long long k, uint32_t *hist, int lane)
+{
+	uint32_t prefix = 0, mask = 0;
+	for (int shift = 24; shift >= 0; shift -= 8) {
+		for (int b = lane; b < 256; b += 32)
+			hist[b] = 0;
+		__syncwarp();
+		for (int64_t i = sbin + lane; i < ebin; i += 32) {
+			float v = __ldg(vals + i);
+			if (!isnan(v)) {
+				uint32_t key = mg_fkey(v);
+				if ((key & mask) == prefix)
+					atomicAdd(&hist[(key >> shift) & 0xff], 1u);
+			}
+		}
+		__syncwarp();
+		// find the digit whose cumulative count passes k (serial over 256 bins on all lanes; rare path)
+		uint32_t digit = 0;
+		long long acc = 0;
+		for (int b = 0; b < 256; ++b) {
+			uint32_t c = hist[b];
+			if (acc + c > k) {
+				digit = b;
+				break;
+			}
+			acc += c;
+		}
+		k -= acc;
+		prefix |= digit << shift;
+		mask |= 0xffu << shift;
+		__syncwarp();
+	}
+	return mg_fkey_inv(prefix);
+}
+
+// src/StreamPercentiler.h:210-217, operands kept un-fused so the double rounding matches the host compiler's
+__device__ __forceinline__ double mg_interp(float x1, float x2, double wgt)
+{
+	return mg_f2d(__dadd_rn(__dmul_rn((double)x1, __dsub_rn(1., wgt)), __dmul_rn((double)x2, wgt)));
+}
+
+__global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQuery q)
+{
+	__shared__ float sbuf[MG_SW_WARPS][MG_SW_CAP];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	float *buf = sbuf[warp];
+	const int64_t nwarps_total = (int64_t)gridDim.x * MG_SW_WARPS;
+	for (int64_t i = (int64_t)blockIdx.x * MG_SW_WARPS + warp; i < q.count; i += nwarps_total) {
+		DenseWin w;
+		const bool ok = mg_dense_win(q, q.first + i, w);
+		long long n = 0;
+		double S = 0, mean = 0, m2 = 0;
+		float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
+		const bool want_q = q.nq > 0;
+		bool in_smem = true;
+		if (ok) {
+			const float *vals = w.ch->vals;
+			for (int64_t b0 = w.sbin; b0 < w.ebin; b0 += 32) {
+				const int64_t b = b0 + lane;
+				float v = b < w.ebin ? __ldg(vals + b) : mg_nanf();
+				const bool valid = !isnan(v);
+				if (valid) {
+					S += (double)v;
+					fmin = fminf(fmin, v);
+					fmax = fmaxf(fmax, v);
+					++n;
+					const double d = (double)v - mean;
+					mean += d / (double)n;
+					m2 += d * ((double)v - mean);
+				}
+			}
+		}
+		// merge lanes: counts, sums, extrema, Welford pairs (Chan et al.)
+#pragma unroll
+		for (int m = 16; m > 0; m >>= 1) {
+			const long long on = __shfl_xor_sync(0xffffffffu, n, m);
+			const double oS = __shfl_xor_sync(0xffffffffu, S, m);
+			const double omean = __shfl_xor_sync(0xffffffffu, mean, m);
+			const double om2 = __shfl_xor_sync(0xffffffffu, m2, m);
+			const float omin = __shfl_xor_sync(0xffffffffu, fmin, m);
+			const float omax = __shfl_xor_sync(0xffffffffu, fmax, m);
+			const long long tn = n + on;
+			if (tn > 0) {
+				// symmetric form so both partners compute identical results
+				const double d = omean - mean;
+				const double nm = ((double)n * mean + (double)on * omean) / (double)tn;
+				m2 = m2 + om2 + d * d * ((double)n * (double)on / (double)tn);
+				mean = nm;
+			}
+			n = tn;
+			S += oS;
+			fmin = fminf(fmin, omin);
+			fmax = fmaxf(fmax, omax);
+		}
+		// quantiles
+		double qv[MG_MAX_Q];
+#pragma unroll
+		for (int k = 0; k < MG_MAX_Q; ++k)
+			qv[k] = mg_nan();
+		if (want_q && ok && n > 0) {
+			in_smem = n <= MG_SW_CAP;
+			if (in_smem) {
+				// compact non-NaN values into the warp buffer (second pass over the window: L1/L2 hits)
+				const float *vals = w.ch->vals;
+				int fill = 0;
+				for (int64_t b0 = w.sbin; b0 < w.ebin; b0 += 32) {
+					const int64_t b = b0 + lane;
+					float v = b < w.ebin ? __ldg(vals + b) : mg_nanf();
+					const bool valid = !isnan(v);
+					const unsigned m = __ballot_sync(0xffffffffu, valid);
+					if (valid)
+						buf[fill + __popc(m & ((1u << lane) - 1))] = v;
+					fill += __popc(m);
+				}
+				int P = 1;
+				while (P < (int)n)
+					P <<= 1;
+				for (int t = (int)n + lane; t < P; t += 32)
+					buf[t] = __int_as_float(0x7f800000);
+				__syncwarp();
+				mg_warp_bitonic(buf, P, lane);
+			}
+			for (int k = 0; k < q.nq; ++k) {
+				double pct = q.q_pct[k];
+				pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
+				const double index = __dmul_rn((double)(n - 1), pct);
+				const long long i1 = (long long)floor(index), i2 = (long long)ceil(index);
+				const double wgt = __dsub_rn(index, (double)i1);
+				float x1, x2;
+				if (in_smem) {
+					x1 = buf[i1];
+					x2 = buf[i2];
+				} else {
+					uint32_t *hist = reinterpret_cast<uint32_t *>(buf);
+					x1 = mg_warp_radix_select(w.ch->vals, w.sbin, w.ebin, i1, hist, lane);
+					x2 = i2 == i1 ? x1 : mg_warp_radix_select(w.ch->vals, w.sbin, w.ebin, i2, hist, lane);
+				}
+				qv[k] = mg_interp(x1, x2, wgt);
+			}
+			__syncwarp();
+		}
+		if (lane == 0) {
+			double avg = mg_nan(), sum = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan(), size = mg_nan(), exists = mg_nan();
+			if (ok) {
+				size = (double)n;
+				exists = n > 0 ? 1. : 0.;
+				if (n > 0) {
+					avg = mg_f2d(S / (double)n);
+					sum = mg_f2d(S);
+					mn = (double)fmin;
+					mx = (double)fmax;
+					if (n > 1)
+						sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
+				}
+			}
+			if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
+			if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+			if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
+			if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
+			if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, mx);
+			if (q.out[MG_STDDEV]) mg_st_stream(q.out[MG_STDDEV] + i, sd);
+			if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
+			if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+			for (int k = 0; k < q.nq; ++k)
+				mg_st_stream(q.q_out[k] + i, qv[k]);
+		}
+	}
+}

@@ -1,0 +1,116 @@
+"""Parity of the CUDA dense-track window functions (mg_dense_window / mg_h_dense_window) with the reference.
+
+Bar: bit-exact for min / max / quantile / size, <= 1e-6 relative for avg / sum / stddev (north_star); the golden
+vectors come from the reference's own compiled GenomeTrackFixedBin (tests/golden/make_fixtures.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import CHROMS, assert_close, assert_same, read_dense
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+def test_golden_all_functions(gpu_ctx, dense_testdb, golden):
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = golden[f"dense_{c}_start"], golden[f"dense_{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        funcs = ["avg", "sum", "min", "max", "stddev", ("quantile", 0.9), ("quantile", 0.5), ("quantile", 0.0), ("quantile", 1.0)]
+        out = dense_testdb.window(rows, funcs)
+        assert_close(out[0], golden[f"dense_{c}_avg"], RTOL, f"{c} avg")
+        assert_close(out[1], golden[f"dense_{c}_sum"], RTOL, f"{c} sum")
+        assert_same(out[2], golden[f"dense_{c}_min"], f"{c} min")
+        assert_same(out[3], golden[f"dense_{c}_max"], f"{c} max")
+        assert_close(out[4], golden[f"dense_{c}_stddev"], RTOL, f"{c} stddev")
+        assert_same(out[5], golden[f"dense_{c}_quantile"], f"{c} q0.9")
+        assert_same(out[6], golden[f"dense_{c}_quantile_0.5"], f"{c} q0.5")
+        assert_same(out[7], golden[f"dense_{c}_quantile_0.0"], f"{c} q0")
+        assert_same(out[8], golden[f"dense_{c}_quantile_1.0"], f"{c} q1")
+
+
+def test_prefix_path_avg_sum(gpu_ctx, dense_testdb, golden):
+    """avg/sum alone go through the O(1) prefix kernel; also the reference's sliding (Kahan) scan."""
+    for cid, (c, size) in enumerate(CHROMS):
+        for key in ("", "slide_"):
+            s, e = golden[f"dense_{c}_{key}start"], golden[f"dense_{c}_{key}end"]
+            rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+            avg, sm = dense_testdb.window(rows, ["avg", "sum"])
+            assert_close(avg, golden[f"dense_{c}_{key}avg"], RTOL, f"{c} {key}avg")
+            assert_close(sm, golden[f"dense_{c}_{key}sum"], RTOL, f"{c} {key}sum")
+
+
+def test_shifts_and_clamp_vs_oracle(gpu_ctx, dense_testdb):
+    rng = np.random.default_rng(7)
+    for cid, (c, size) in enumerate(CHROMS):
+        bs, bins = read_dense("dense_track", c)
+        s = np.sort(rng.integers(0, size - 1, 3000))
+        e = np.minimum(s + rng.integers(1, 400, 3000), size)
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        for sshift, eshift in ((-5000, 5000), (-100, -50), (300, 100), (0, 0), (-10**7, 10**7), (2000, -2000)):
+            funcs = ["avg", "sum", "min", "max", "stddev", ("quantile", 0.9), "size"]
+            got = dense_testdb.window(rows, funcs, sshift, eshift)
+            exp = port.dense_window(bins, bs, size, s, e, sshift, eshift, 0.9)
+            for k, name in enumerate(("avg", "sum", "min", "max", "stddev", "quantile", "size")):
+                if name in ("avg", "sum", "stddev"):
+                    assert_close(got[k], exp[name], RTOL, f"{c} {name} shift {sshift},{eshift}")
+                else:
+                    assert_same(got[k], exp[name], f"{c} {name} shift {sshift},{eshift}")
+
+
+def test_host_entry_point_matches_device_path(gpu_ctx, dense_testdb):
+    rng = np.random.default_rng(11)
+    chrom = np.sort(rng.integers(0, 3, 5000)).astype(np.int32)
+    sizes = np.array([z for _, z in CHROMS])[chrom]
+    start = (rng.random(5000) * (sizes - 2)).astype(np.int64)
+    end = np.minimum(start + rng.integers(1, 3000, 5000), sizes)
+    funcs = ["avg", "max", ("quantile", 0.9)]
+    host = dense_testdb.window_host(chrom, start, end, funcs, -500, 500)
+    rows = gpu_ctx.rows_upload(chrom, start, end)
+    dev = dense_testdb.window(rows, funcs, -500, 500)
+    for a, b in zip(host, dev):
+        assert_same(a, b, "host vs device path")
+
+
+def test_empty_and_ragged(gpu_ctx, dense_testdb):
+    rows = gpu_ctx.rows_upload(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    out = dense_testdb.window(rows, ["avg", "max"])
+    assert len(out[0]) == 0 and len(out[1]) == 0
+    # one row; windows wider than the warp buffer (quantile radix-select path); whole chromosome
+    bs, bins = read_dense("dense_track", "chr1")
+    s = np.array([0, 100, 250000, 0]); e = np.array([500000, 400100, 250001, 1])
+    rows = gpu_ctx.rows_upload(np.zeros(4, np.int32), s, e)
+    got = dense_testdb.window(rows, ["avg", "min", "max", ("quantile", 0.9), ("quantile", 0.123), "stddev"])
+    exp = port.dense_window(bins, bs, 500000, s, e, 0, 0, 0.9)
+    exp2 = port.dense_window(bins, bs, 500000, s, e, 0, 0, 0.123, ("quantile",))
+    assert_close(got[0], exp["avg"], RTOL, "avg")
+    assert_same(got[1], exp["min"], "min")
+    assert_same(got[2], exp["max"], "max")
+    assert_same(got[3], exp["quantile"], "q.9 wide")
+    assert_same(got[4], exp2["quantile"], "q.123 wide")
+    assert_close(got[5], exp["stddev"], RTOL, "stddev")
+
+
+def test_cancellation_guard(gpu_ctx):
+    """A huge value early in the chromosome must not poison windows after it (prefix cancellation guard)."""
+    from misha_b200 import gpu
+    size = 200000
+    ctx2 = gpu.Context([size])
+    try:
+        rng = np.random.default_rng(3)
+        bins = rng.random(size // 20).astype(np.float32) * 1e-3
+        bins[10] = 1e30
+        bins[500:600] = 0
+        t = gpu.DenseTrack(ctx2, 20)
+        t.stage(0, bins)
+        s = np.arange(0, size - 4000, 777, dtype=np.int64)
+        e = s + 4000
+        rows = ctx2.rows_upload(np.zeros(len(s), np.int32), s, e)
+        avg, sm = t.window(rows, ["avg", "sum"])
+        exp = port.dense_window(bins, 20, size, s, e, 0, 0, 0.5, ("avg", "sum"))
+        assert_close(avg, exp["avg"], RTOL, "avg")
+        assert_close(sm, exp["sum"], RTOL, "sum")
+    finally:
+        ctx2.close()
