@@ -463,3 +463,725 @@ extern "C" int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, cons
 		MG_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]));
 	return 0;
 }
+
+// ---- generic device exclusive scan of int64 (tile reduce -> one-block scan -> tile write) -------------------------
+#define MG_SCAN_THREADS 256
+#define MG_SCAN_PER_THREAD 8
+#define MG_SCAN_TILE (MG_SCAN_THREADS * MG_SCAN_PER_THREAD)
+
+__global__ void __launch_bounds__(MG_SCAN_THREADS) k_scan_tile_reduce(const long long *in, int64_t n, long long *tile_tot)
+{
+	__shared__ long long sc[33];
+	const int64_t base = (int64_t)blockIdx.x * MG_SCAN_TILE + (int64_t)threadIdx.x * MG_SCAN_PER_THREAD;
+	long long s = 0;
+#pragma unroll
+	for (int j = 0; j < MG_SCAN_PER_THREAD; ++j)
+		if (base + j < n)
+			s += in[base + j];
+	long long tot;
+	mg_block_excl_scan<long long>(s, sc, tot);
+	if (threadIdx.x == 0)
+		tile_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(long long *tile_tot, int64_t ntiles, long long *total)
+{
+	__shared__ long long sc[33];
+	const int64_t chunk = (ntiles + blockDim.x - 1) / blockDim.x;
+	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, ntiles);
+	long long s = 0;
+	for (int64_t i = lo; i < hi; ++i)
+		s += tile_tot[i];
+	long long tot;
+	long long s0 = mg_block_excl_scan<long long>(s, sc, tot);
+	for (int64_t i = lo; i < hi; ++i) {
+		const long long v = tile_tot[i];
+		tile_tot[i] = s0;
+		s0 += v;
+	}
+	if (threadIdx.x == 0)
+		*total = tot;
+}
+
+// out[i] = sum in[0..i), out[n] = total (out has n + 1 entries; may alias nothing)
+__global__ void __launch_bounds__(MG_SCAN_THREADS) k_scan_write(const long long *in, int64_t n, const long long *tile_tot, long long *out)
+{
+	__shared__ long long sc[33];
+	const int64_t base = (int64_t)blockIdx.x * MG_SCAN_TILE + (int64_t)threadIdx.x * MG_SCAN_PER_THREAD;
+	long long v[MG_SCAN_PER_THREAD], s = 0;
+#pragma unroll
+	for (int j = 0; j < MG_SCAN_PER_THREAD; ++j) {
+		v[j] = base + j < n ? in[base + j] : 0;
+		s += v[j];
+	}
+	long long tot;
+	long long s0 = tile_tot[blockIdx.x] + mg_block_excl_scan<long long>(s, sc, tot);
+#pragma unroll
+	for (int j = 0; j < MG_SCAN_PER_THREAD; ++j) {
+		if (base + j <= n)
+			out[base + j] = s0;
+		s0 += v[j];
+	}
+}
+
+// d_out[0..n] = exclusive prefix of d_in[0..n); *h_total = d_out[n]. Synchronises the stream.
+static int mg_excl_scan_i64(mg_ctx *ctx, const long long *d_in, int64_t n, long long *d_out, long long *h_total, cudaStream_t st)
+{
+	const int64_t ntiles = mg_div_up(n + 1, MG_SCAN_TILE);
+	long long *tile_tot = nullptr, *d_total = nullptr;
+	MG_CUDA(ctx, cudaMalloc(&tile_tot, sizeof(long long) * (ntiles + 1)));
+	d_total = tile_tot + ntiles;
+	k_scan_tile_reduce<<<(unsigned)ntiles, MG_SCAN_THREADS, 0, st>>>(d_in, n, tile_tot);
+	MG_LAUNCH_CHECK(ctx);
+	k_scan_tiles<<<1, 1024, 0, st>>>(tile_tot, ntiles, d_total);
+	MG_LAUNCH_CHECK(ctx);
+	k_scan_write<<<(unsigned)ntiles, MG_SCAN_THREADS, 0, st>>>(d_in, n, tile_tot, d_out);
+	MG_LAUNCH_CHECK(ctx);
+	MG_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	cudaFree(tile_tot);
+	return 0;
+}
+
+// ---- intervals iterator rows (src/TrackExpressionIntervals1DIterator.cpp:21-85) ------------------------------------
+// For scope interval k the overlapping iterator intervals are the contiguous range [lo_k, hi_k): the iterator set is
+// sorted and disjoint, so lo_k = first interval with (chrom, end) > (chrom_k, start_k) and hi_k = first with
+// (chrom, start) >= (chrom_k, end_k).
+struct IvIterArgs {
+	int64_t niter, nscope;
+	const int32_t *ichrom;
+	const int64_t *istart, *iend;
+	const int32_t *schrom;
+	const int64_t *sstart, *send;
+};
+
+__global__ void __launch_bounds__(256) k_ivrows_range(const IvIterArgs a, long long *lo_out, long long *cnt_out)
+{
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= a.nscope)
+		return;
+	const int32_t c = a.schrom[k];
+	const int64_t s = a.sstart[k], e = a.send[k];
+	int64_t lo = 0, hi = a.niter;
+	while (lo < hi) {
+		const int64_t mid = lo + ((hi - lo) >> 1);
+		const int32_t mc = __ldg(a.ichrom + mid);
+		if (mc < c || (mc == c && __ldg(a.iend + mid) <= s))
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	const int64_t first = lo;
+	hi = a.niter;
+	while (lo < hi) {
+		const int64_t mid = lo + ((hi - lo) >> 1);
+		const int32_t mc = __ldg(a.ichrom + mid);
+		if (mc < c || (mc == c && __ldg(a.istart + mid) < e))
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	lo_out[k] = first;
+	cnt_out[k] = lo - first;
+}
+
+__global__ void __launch_bounds__(256) k_ivrows_write(const IvIterArgs a, const long long *lo, const long long *off, int64_t nrows, int32_t *ochrom,
+													   int64_t *ostart, int64_t *oend, int64_t *oscope)
+{
+	const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows)
+		return;
+	int64_t klo = 0, khi = a.nscope; // last k with off[k] <= r
+	while (khi - klo > 1) {
+		const int64_t mid = (klo + khi) >> 1;
+		if (__ldg(off + mid) <= r)
+			klo = mid;
+		else
+			khi = mid;
+	}
+	const int64_t k = klo, j = lo[k] + (r - off[k]);
+	const int64_t s = a.sstart[k], e = a.send[k], is = a.istart[j], ie = a.iend[j];
+	ochrom[r] = a.schrom[k];
+	ostart[r] = s > is ? s : is;
+	oend[r] = e < ie ? e : ie;
+	oscope[r] = k;
+}
+
+extern "C" int mg_rows_intervals(mg_ctx *ctx, int64_t niter, const int32_t *h_ichrom, const int64_t *h_istart, const int64_t *h_iend,
+								 int64_t nscope, const int32_t *h_schrom, const int64_t *h_sstart, const int64_t *h_send, void *stream,
+								 mg_rows **out)
+{
+	MG_REQUIRE(ctx, niter >= 0 && nscope >= 0, "mg_rows_intervals: negative sizes");
+	cudaStream_t st = mg_stream(stream);
+	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t ni = (size_t)(niter > 0 ? niter : 1), ns = (size_t)(nscope > 0 ? nscope : 1);
+	char *tmp = nullptr;
+	const size_t tmp_bytes = ni * 20 + ns * 20 + ns * 8 * 2 + (ns + 1) * 8;
+	MG_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+	IvIterArgs a;
+	a.niter = niter;
+	a.nscope = nscope;
+	char *p = tmp;
+	a.istart = (int64_t *)p; p += ni * 8;
+	a.iend = (int64_t *)p; p += ni * 8;
+	a.sstart = (int64_t *)p; p += ns * 8;
+	a.send = (int64_t *)p; p += ns * 8;
+	long long *lo = (long long *)p; p += ns * 8;
+	long long *cnt = (long long *)p; p += ns * 8;
+	long long *off = (long long *)p; p += (ns + 1) * 8;
+	a.ichrom = (int32_t *)p; p += ni * 4;
+	a.schrom = (int32_t *)p;
+	if (niter) {
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.istart, h_istart, niter * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.iend, h_iend, niter * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.ichrom, h_ichrom, niter * 4, cudaMemcpyHostToDevice, st));
+	}
+	if (nscope) {
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.sstart, h_sstart, nscope * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.send, h_send, nscope * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync((void *)a.schrom, h_schrom, nscope * 4, cudaMemcpyHostToDevice, st));
+	}
+	long long nrows = 0;
+	if (nscope && niter) {
+		k_ivrows_range<<<(unsigned)mg_div_up(nscope, 256), 256, 0, st>>>(a, lo, cnt);
+		MG_LAUNCH_CHECK(ctx);
+		if (mg_excl_scan_i64(ctx, cnt, nscope, off, &nrows, st))
+			return 1;
+	}
+	mg_rows *r = new (std::nothrow) mg_rows();
+	MG_REQUIRE(ctx, r, "out of memory");
+	const size_t nr = (size_t)(nrows > 0 ? nrows : 1);
+	cudaError_t e = cudaMalloc(&r->d_block, nr * 28);
+	if (e != cudaSuccess) {
+		delete r;
+		cudaFree(tmp);
+		return mg_fail(ctx, "mg_rows_intervals: %s", cudaGetErrorString(e));
+	}
+	char *base = (char *)r->d_block;
+	r->owns = true;
+	r->src.kind = 0;
+	r->src.n = nrows;
+	r->src.start = (const int64_t *)base;
+	r->src.end = (const int64_t *)(base + nr * 8);
+	r->src.scope_idx = (const int64_t *)(base + nr * 16);
+	r->src.chrom = (const int32_t *)(base + nr * 24);
+	if (nrows) {
+		k_ivrows_write<<<(unsigned)mg_div_up(nrows, 256), 256, 0, st>>>(a, lo, off, nrows, (int32_t *)r->src.chrom, (int64_t *)r->src.start,
+																		 (int64_t *)r->src.end, (int64_t *)r->src.scope_idx);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	cudaFree(tmp);
+	*out = r;
+	return 0;
+}
+
+// ---- sparse tracks and interval sets -----------------------------------------------------------------------------
+template <typename H>
+static int mg_sparse_like_create(mg_ctx *ctx, H **out)
+{
+	H *t = new (std::nothrow) H();
+	MG_REQUIRE(ctx, t, "out of memory");
+	t->nchroms = ctx->nchroms;
+	t->h_table.assign(ctx->nchroms, SparseChrom{nullptr, nullptr, nullptr, 0});
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ctx->nchroms, &t->d_table))
+		return 1;
+	MG_CUDA(ctx, cudaMemcpy(t->d_table, t->h_table.data(), sizeof(SparseChrom) * ctx->nchroms, cudaMemcpyHostToDevice));
+	*out = t;
+	return 0;
+}
+
+template <typename H>
+static int mg_sparse_like_stage(mg_ctx *ctx, H *t, int chromid, const int64_t *h_start, const int64_t *h_end, const float *h_val, int64_t n,
+								const char *what)
+{
+	MG_REQUIRE(ctx, chromid >= 0 && chromid < t->nchroms, "%s: chromid %d out of range", what, chromid);
+	MG_REQUIRE(ctx, n >= 0, "%s: negative record count", what);
+	MG_REQUIRE(ctx, t->h_table[chromid].start == nullptr, "%s: chromosome %d already staged", what, chromid);
+	// the reference's load-time validation (src/GenomeTrackSparse.cpp:209-222)
+	for (int64_t i = 0; i < n; ++i) {
+		MG_REQUIRE(ctx, h_start[i] >= 0, "%s: interval %lld has negative start (%lld)", what, (long long)i, (long long)h_start[i]);
+		MG_REQUIRE(ctx, h_start[i] < h_end[i], "%s: interval %lld has start (%lld) >= end (%lld)", what, (long long)i, (long long)h_start[i],
+				   (long long)h_end[i]);
+		MG_REQUIRE(ctx, i == 0 || h_start[i] >= h_end[i - 1], "%s: interval %lld [%lld, %lld) overlaps with previous interval [%lld, %lld)",
+				   what, (long long)i, (long long)h_start[i], (long long)h_end[i], (long long)h_start[i - 1], (long long)h_end[i - 1]);
+	}
+	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	SparseChrom sc{nullptr, nullptr, nullptr, n};
+	int64_t *ds = nullptr, *de = nullptr;
+	float *dv = nullptr;
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, n, &ds) || mg_alloc_tracked(ctx, t->allocs, t->bytes, n, &de))
+		return 1;
+	if (n) {
+		MG_CUDA(ctx, cudaMemcpy(ds, h_start, sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+		MG_CUDA(ctx, cudaMemcpy(de, h_end, sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+	}
+	if (h_val) {
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, n, &dv))
+			return 1;
+		std::vector<float> clean(h_val, h_val + n);
+		for (auto &v : clean)
+			if (std::isinf(v))
+				v = std::numeric_limits<float>::quiet_NaN(); // src/GenomeTrackSparse.cpp:205-206
+		if (n)
+			MG_CUDA(ctx, cudaMemcpy(dv, clean.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+	}
+	sc.start = ds;
+	sc.end = de;
+	sc.val = dv;
+	t->h_table[chromid] = sc;
+	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &sc, sizeof(SparseChrom), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" int mg_sparse_create(mg_ctx *ctx, mg_sparse **out) { return mg_sparse_like_create(ctx, out); }
+extern "C" int mg_sparse_stage(mg_ctx *ctx, mg_sparse *t, int chromid, const int64_t *h_start, const int64_t *h_end, const float *h_val, int64_t n)
+{
+	MG_REQUIRE(ctx, h_val || n == 0, "mg_sparse_stage: values are NULL");
+	static const float dummy = 0;
+	return mg_sparse_like_stage(ctx, t, chromid, h_start, h_end, h_val ? h_val : &dummy, n, "Invalid sparse track");
+}
+extern "C" void mg_sparse_free(mg_ctx *ctx, mg_sparse *t)
+{
+	if (!t)
+		return;
+	for (void *p : t->allocs)
+		cudaFree(p);
+	delete t;
+}
+extern "C" int mg_ivset_create(mg_ctx *ctx, mg_ivset **out) { return mg_sparse_like_create(ctx, out); }
+extern "C" int mg_ivset_stage(mg_ctx *ctx, mg_ivset *s, int chromid, const int64_t *h_start, const int64_t *h_end, int64_t n)
+{
+	return mg_sparse_like_stage(ctx, s, chromid, h_start, h_end, nullptr, n, "Invalid interval set");
+}
+extern "C" void mg_ivset_free(mg_ctx *ctx, mg_ivset *s)
+{
+	if (!s)
+		return;
+	for (void *p : s->allocs)
+		cudaFree(p);
+	delete s;
+}
+
+extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift,
+								int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *d_out, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, nfuncs > 0, "no functions requested");
+	SparseQuery q;
+	memset(&q, 0, sizeof(q));
+	q.rows = rows->src;
+	q.first = first;
+	q.count = count;
+	q.sshift = sshift;
+	q.eshift = eshift;
+	q.table = t->d_table;
+	q.chrom_sizes = ctx->d_chrom_sizes;
+	for (int k = 0; k < nfuncs; ++k) {
+		const int f = funcs[k];
+		MG_REQUIRE(ctx, f >= 0 && f < MG_NUM_FUNCS, "unknown function id %d", f);
+		MG_REQUIRE(ctx, d_out[k], "output column %d is NULL", k);
+		if (f == MG_QUANTILE) {
+			MG_REQUIRE(ctx, q.nq < MG_MAX_Q && params, "bad quantile request");
+			q.q_pct[q.nq] = params[k];
+			q.q_out[q.nq++] = d_out[k];
+		} else {
+			MG_REQUIRE(ctx, !q.out[f], "function %d requested twice in one call", f);
+			q.out[f] = d_out[k];
+		}
+	}
+	if (!count)
+		return 0;
+	k_sparse_window<<<(unsigned)mg_div_up(count, 256), 256, 0, mg_stream(stream)>>>(q);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
+extern "C" int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+						   double *d_out, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, d_out, "output column is NULL");
+	if (!count)
+		return 0;
+	CoverageQuery q;
+	q.rows = rows->src;
+	q.first = first;
+	q.count = count;
+	q.sshift = sshift;
+	q.eshift = eshift;
+	q.table = s->d_table;
+	q.chrom_sizes = ctx->d_chrom_sizes;
+	q.out = d_out;
+	k_coverage<<<(unsigned)mg_div_up(count, 256), 256, 0, mg_stream(stream)>>>(q);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
+// ---- sequence + PWM -----------------------------------------------------------------------------------------------
+extern "C" int mg_seq_create(mg_ctx *ctx, mg_seq **out)
+{
+	mg_seq *s = new (std::nothrow) mg_seq();
+	MG_REQUIRE(ctx, s, "out of memory");
+	s->nchroms = ctx->nchroms;
+	s->h_table.assign(ctx->nchroms, SeqChrom{nullptr, nullptr, 0});
+	if (mg_alloc_tracked(ctx, s->allocs, s->bytes, ctx->nchroms, &s->d_table))
+		return 1;
+	MG_CUDA(ctx, cudaMemcpy(s->d_table, s->h_table.data(), sizeof(SeqChrom) * ctx->nchroms, cudaMemcpyHostToDevice));
+	*out = s;
+	return 0;
+}
+
+extern "C" int mg_seq_stage(mg_ctx *ctx, mg_seq *s, int chromid, const char *h_ascii, int64_t len)
+{
+	MG_REQUIRE(ctx, chromid >= 0 && chromid < s->nchroms, "mg_seq_stage: chromid %d out of range", chromid);
+	MG_REQUIRE(ctx, len == ctx->chrom_sizes[chromid], "mg_seq_stage: chromosome %d has %lld bases, expected %lld", chromid, (long long)len,
+			   (long long)ctx->chrom_sizes[chromid]);
+	MG_REQUIRE(ctx, s->h_table[chromid].codes == nullptr, "mg_seq_stage: chromosome %d already staged", chromid);
+	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int64_t nthreads = mg_div_up(len, 32);
+	uint32_t *codes = nullptr, *inval = nullptr;
+	if (mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads * 2 + 8, &codes) || mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads + 8, &inval))
+		return 1;
+	MG_CUDA(ctx, cudaMemset(codes, 0, sizeof(uint32_t) * (nthreads * 2 + 8)));
+	MG_CUDA(ctx, cudaMemset(inval, 0xff, sizeof(uint32_t) * (nthreads + 8)));
+	uint8_t *d_ascii = nullptr;
+	MG_CUDA(ctx, cudaMalloc(&d_ascii, (size_t)(len > 0 ? len : 1)));
+	if (len) {
+		MG_CUDA(ctx, cudaMemcpy(d_ascii, h_ascii, (size_t)len, cudaMemcpyHostToDevice));
+		k_seq_pack<<<(unsigned)mg_div_up(nthreads, 256), 256>>>(d_ascii, len, codes, inval);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaDeviceSynchronize());
+	}
+	cudaFree(d_ascii);
+	SeqChrom sc{codes, inval, len};
+	s->h_table[chromid] = sc;
+	MG_CUDA(ctx, cudaMemcpy(s->d_table + chromid, &sc, sizeof(SeqChrom), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" void mg_seq_free(mg_ctx *ctx, mg_seq *s)
+{
+	if (!s)
+		return;
+	for (void *p : s->allocs)
+		cudaFree(p);
+	delete s;
+}
+
+// src/PWMScorer.cpp:1452-1459 (double -> float), src/DnaPSSM.cpp:77-106 (normalize), :703-719 (prior)
+extern "C" int mg_pssm_logp(const double *h_pssm, int L, double prior, float *h_logp)
+{
+	if (!h_pssm || !h_logp || L <= 0)
+		return 1;
+	for (int i = 0; i < L; ++i) {
+		float p[4];
+		for (int c = 0; c < 4; ++c)
+			p[c] = (float)h_pssm[i * 4 + c];
+		for (int pass = 0; pass < 2; ++pass) {
+			const float sum = p[0] + p[1] + p[2] + p[3];
+			for (int c = 0; c < 4; ++c) {
+				p[c] /= sum;
+				h_logp[i * 4 + c] = p[c] != 0 ? logf(p[c]) : -INFINITY;
+			}
+			if (pass == 1 || prior <= 0)
+				break;
+			for (int c = 0; c < 4; ++c)
+				p[c] = p[c] + (float)prior;
+		}
+	}
+	return 0;
+}
+
+extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand,
+					  float score_thresh, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out,
+					  void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, L >= 1 && L <= MG_PWM_MAXL, "PSSM length %d not in [1, %d]", L, MG_PWM_MAXL);
+	MG_REQUIRE(ctx, mode == MG_PWM_TOTAL || mode == MG_PWM_MAX || mode == MG_PWM_COUNT, "unsupported pwm mode %d", mode);
+	MG_REQUIRE(ctx, strand == 1 || strand == -1, "strand must be 1 or -1");
+	if (!count)
+		return 0;
+	cudaStream_t st = mg_stream(stream);
+	std::vector<float2> tab((size_t)L * 5);
+	for (int j = 0; j < L; ++j) {
+		for (int c = 0; c < 4; ++c)
+			tab[j * 5 + c] = make_float2(h_logp[j * 4 + c], h_logp[(L - 1 - j) * 4 + (3 - c)]);
+		tab[j * 5 + 4] = make_float2(-INFINITY, -INFINITY);
+	}
+	float2 *d_tab = nullptr;
+	MG_CUDA(ctx, cudaMallocAsync(&d_tab, sizeof(float2) * tab.size(), st));
+	MG_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st)); // tab is a stack-lifetime host buffer
+	PwmQuery q;
+	q.rows = rows->src;
+	q.first = first;
+	q.count = count;
+	q.sshift = sshift;
+	q.eshift = eshift;
+	q.table = s->d_table;
+	q.chrom_sizes = ctx->d_chrom_sizes;
+	q.tab = d_tab;
+	q.L = L;
+	q.bidirect = bidirect;
+	q.extend = extend;
+	q.mode = mode;
+	q.strand = strand;
+	q.thresh = score_thresh;
+	q.out = d_out;
+	const int64_t blocks_needed = mg_div_up(count, MG_PWM_WARPS);
+	const int64_t cap = (int64_t)ctx->sm_count * 16;
+	k_pwm<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), MG_PWM_WARPS * 32, 0, st>>>(q);
+	MG_LAUNCH_CHECK(ctx);
+	MG_CUDA(ctx, cudaFreeAsync(d_tab, st));
+	return 0;
+}
+
+// ---- gsummary ------------------------------------------------------------------------------------------------------
+extern "C" int mg_summary_init(mg_ctx *ctx, double *d_partial, void *stream)
+{
+	k_summary_init<<<1, 1, 0, mg_stream(stream)>>>(d_partial);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
+static int mg_summary_blocks(mg_ctx *ctx, int64_t n)
+{
+	int64_t b = mg_div_up(n, MG_SUM_THREADS);
+	const int64_t cap = (int64_t)ctx->sm_count * 8;
+	if (b > cap) b = cap;
+	if (b > MG_SUM_MAX_BLOCKS) b = MG_SUM_MAX_BLOCKS;
+	return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *d_partial, void *stream)
+{
+	if (n <= 0)
+		return 0;
+	cudaStream_t st = mg_stream(stream);
+	const int nb = mg_summary_blocks(ctx, n);
+	Moments *scratch = nullptr;
+	MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * nb, st));
+	k_summary_values<<<nb, MG_SUM_THREADS, 0, st>>>(d_vals, n, scratch);
+	MG_LAUNCH_CHECK(ctx);
+	k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, nb, d_partial);
+	MG_LAUNCH_CHECK(ctx);
+	MG_CUDA(ctx, cudaFreeAsync(scratch, st));
+	return 0;
+}
+
+static bool mg_is_prefix_func(int f) { return f == MG_AVG || f == MG_SUM || f == MG_NEAREST || f == MG_SIZE || f == MG_EXISTS; }
+
+// implicit fixed-bin rows at the track's own resolution with no shifts: each row is exactly one bin
+static bool mg_is_stream_case(const mg_dense *t, const mg_rows *rows, int64_t sshift, int64_t eshift, int func)
+{
+	return rows->src.kind == 1 && rows->src.binsize == (int64_t)t->bin_size && sshift == 0 && eshift == 0 &&
+		   (func == MG_AVG || func == MG_NEAREST || func == MG_SUM || func == MG_MIN || func == MG_MAX);
+}
+
+extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift,
+								int64_t eshift, int func, double param, double *d_partial, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	if (!count)
+		return 0;
+	cudaStream_t st = mg_stream(stream);
+	if (mg_is_stream_case(t, rows, sshift, eshift, func) || mg_is_prefix_func(func)) {
+		const int nb = mg_summary_blocks(ctx, count);
+		Moments *scratch = nullptr;
+		MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * nb, st));
+		if (mg_is_stream_case(t, rows, sshift, eshift, func)) {
+			k_dense_stream_summary<<<nb, MG_SUM_THREADS, 0, st>>>(rows->src, t->d_table, first, count, scratch);
+		} else {
+			DenseQuery q;
+			bool need_sweep;
+			double *dummy = (double *)d_partial; // mg_fill_dense_query wants a non-null column; never written by k_dense_summary
+			if (mg_fill_dense_query(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &dummy, q, need_sweep))
+				return 1;
+			k_dense_summary<<<nb, MG_SUM_THREADS, 0, st>>>(q, func, scratch);
+		}
+		MG_LAUNCH_CHECK(ctx);
+		k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, nb, d_partial);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaFreeAsync(scratch, st));
+		return 0;
+	}
+	// any other function: materialise the column on the device, then reduce it (values never leave HBM)
+	double *col = nullptr;
+	MG_CUDA(ctx, cudaMallocAsync(&col, sizeof(double) * count, st));
+	if (mg_dense_window(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &col, stream) || mg_summary(ctx, col, count, d_partial, stream))
+		return 1;
+	MG_CUDA(ctx, cudaFreeAsync(col, st));
+	return 0;
+}
+
+// src/GenomeTrackSummary.cpp:148-155 with get_mean / get_stdev :30-40
+extern "C" void mg_summary_finalize(const double p[6], double out[7])
+{
+	const double n = p[0], nn = p[1], total = p[2], mn = p[3], mx = p[4], ssq = p[5];
+	const double nan = std::numeric_limits<double>::quiet_NaN();
+	out[0] = n;
+	out[1] = n - nn;
+	out[2] = nn ? mn : nan;
+	out[3] = nn ? mx : nan;
+	out[4] = nn ? total : nan;
+	out[5] = nn ? total / nn : nan;
+	if (nn > 1) {
+		const double mean = total / nn;
+		const double var = ssq / (nn - 1) - (mean * mean) * (nn / (nn - 1));
+		out[6] = var > 0 ? sqrt(var) : 0;
+	} else
+		out[6] = nan;
+}
+
+// ---- gdist -----------------------------------------------------------------------------------------------------------
+static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, const int *nbreaks, int include_lowest, HistSpec &hs, double **d_breaks,
+							 cudaStream_t st)
+{
+	MG_REQUIRE(ctx, ndim >= 1 && ndim <= MG_HIST_MAX_DIMS, "histogram dimension %d not in [1, %d]", ndim, MG_HIST_MAX_DIMS);
+	memset(&hs, 0, sizeof(hs));
+	hs.ndim = ndim;
+	hs.include_lowest = include_lowest;
+	long long total = 1;
+	int off = 0;
+	for (int d = 0; d < ndim; ++d) {
+		// BinFinder::init (src/BinFinder.cpp:10-43)
+		MG_REQUIRE(ctx, nbreaks[d] >= 2, "Invalid number of breaks %d", nbreaks[d]);
+		const double *b = h_breaks + off;
+		double binsize = b[1] - b[0];
+		for (int i = 1; i < nbreaks[d]; ++i) {
+			MG_REQUIRE(ctx, b[i] != b[i - 1], "Breaks are not unique (break[%d]=break[%d]=%g)", i - 1, i, b[i]);
+			MG_REQUIRE(ctx, b[i] > b[i - 1], "Breaks are not sorted (break[%d]=%g, break[%d]=%g)", i - 1, b[i - 1], i, b[i]);
+			if ((float)(b[i] - b[i - 1]) != (float)binsize)
+				binsize = 0;
+		}
+		if (!std::isfinite(binsize))
+			binsize = 0;
+		hs.nbreaks[d] = nbreaks[d];
+		hs.boff[d] = off;
+		hs.mult[d] = total;
+		hs.binsize[d] = binsize;
+		total *= nbreaks[d] - 1;
+		off += nbreaks[d];
+	}
+	hs.total = total;
+	MG_CUDA(ctx, cudaMallocAsync(d_breaks, sizeof(double) * off, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(*d_breaks, h_breaks, sizeof(double) * off, cudaMemcpyHostToDevice, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	hs.breaks = *d_breaks;
+	return 0;
+}
+
+static size_t mg_hist_private_smem(const HistSpec &hs)
+{
+	const int nb = hs.nbreaks[0] - 1;
+	return (size_t)(2 * hs.nbreaks[0]) * 4 + (size_t)(MG_HIST_THREADS / 32) * nb * 32 * 4;
+}
+
+static int mg_hist_blocks(mg_ctx *ctx, int64_t n)
+{
+	int64_t b = mg_div_up(n, MG_HIST_THREADS * 8);
+	const int64_t cap = (int64_t)ctx->sm_count * 2;
+	if (b > cap) b = cap;
+	return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int mg_hist(mg_ctx *ctx, int ndim, const double *const *d_cols, int64_t n, const double *h_breaks, const int *nbreaks,
+					   int include_lowest, uint64_t *d_counts, void *stream)
+{
+	cudaStream_t st = mg_stream(stream);
+	HistSpec hs;
+	double *d_breaks = nullptr;
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
+	if (n > 0) {
+		if (ndim == 1 && hs.nbreaks[0] - 1 <= MG_HIST_PRIVATE_MAX) {
+			const size_t smem = mg_hist_private_smem(hs);
+			MG_CUDA(ctx, cudaFuncSetAttribute(k_values_hist_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			k_values_hist_private<<<mg_hist_blocks(ctx, n), MG_HIST_THREADS, smem, st>>>(d_cols[0], n, hs, (unsigned long long *)d_counts);
+		} else {
+			HistCols cols;
+			for (int d = 0; d < ndim; ++d)
+				cols.col[d] = d_cols[d];
+			k_hist_nd<<<(unsigned)mg_div_up(n, MG_HIST_THREADS * 4), MG_HIST_THREADS, 0, st>>>(cols, n, hs, (unsigned long long *)d_counts);
+		}
+		MG_LAUNCH_CHECK(ctx);
+	}
+	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+	return 0;
+}
+
+extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+							 int func, double param, const double *h_breaks, int nbreaks, int include_lowest, uint64_t *d_counts, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	cudaStream_t st = mg_stream(stream);
+	const bool stream_case = mg_is_stream_case(t, rows, sshift, eshift, func);
+	if (!stream_case && !mg_is_prefix_func(func)) {
+		if (!count)
+			return 0;
+		double *col = nullptr;
+		MG_CUDA(ctx, cudaMallocAsync(&col, sizeof(double) * count, st));
+		const double *cols[1] = {col};
+		if (mg_dense_window(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &col, stream) ||
+			mg_hist(ctx, 1, cols, count, h_breaks, &nbreaks, include_lowest, d_counts, stream))
+			return 1;
+		MG_CUDA(ctx, cudaFreeAsync(col, st));
+		return 0;
+	}
+	HistSpec hs;
+	double *d_breaks = nullptr;
+	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
+	if (count > 0) {
+		const bool priv = nbreaks - 1 <= MG_HIST_PRIVATE_MAX;
+		DenseQuery q;
+		bool need_sweep;
+		double *dummy = (double *)d_counts;
+		if (mg_fill_dense_query(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &dummy, q, need_sweep))
+			return 1;
+		if (priv) {
+			const size_t smem = mg_hist_private_smem(hs);
+			const int nb = mg_hist_blocks(ctx, count);
+			if (stream_case) {
+				MG_CUDA(ctx, cudaFuncSetAttribute(k_dense_stream_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				k_dense_stream_hist<<<nb, MG_HIST_THREADS, smem, st>>>(rows->src, t->d_table, first, count, hs, (unsigned long long *)d_counts);
+			} else {
+				MG_CUDA(ctx, cudaFuncSetAttribute(k_dense_hist_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				k_dense_hist_private<<<nb, MG_HIST_THREADS, smem, st>>>(q, func, hs, (unsigned long long *)d_counts);
+			}
+		} else
+			k_dense_hist_global<<<(unsigned)mg_div_up(count, MG_HIST_THREADS * 4), MG_HIST_THREADS, 0, st>>>(q, func, hs, (unsigned long long *)d_counts);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+	return 0;
+}
+
+// ---- gscreen -----------------------------------------------------------------------------------------------------------
+extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
+							   int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	*h_nout = 0;
+	if (!count)
+		return 0;
+	cudaStream_t st = mg_stream(stream);
+	const int64_t nblocks = mg_div_up(count, MG_SCR_THREADS);
+	long long *blk = nullptr;
+	MG_CUDA(ctx, cudaMallocAsync(&blk, sizeof(long long) * (2 * nblocks + 1), st));
+	long long *heads = blk, *tails = blk + nblocks, *total = blk + 2 * nblocks;
+	k_screen_count<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails);
+	MG_LAUNCH_CHECK(ctx);
+	k_screen_scan<<<1, 1024, 0, st>>>(heads, tails, nblocks, total);
+	MG_LAUNCH_CHECK(ctx);
+	k_screen_write<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails, d_chrom, d_start, d_end);
+	MG_LAUNCH_CHECK(ctx);
+	long long n = 0;
+	MG_CUDA(ctx, cudaMemcpyAsync(&n, total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	MG_CUDA(ctx, cudaFreeAsync(blk, st));
+	*h_nout = n;
+	return 0;
+}

@@ -1,3 +1,445 @@
+// stats.cuh -- the consumers of a scan: gsummary moments, gdist histograms, gscreen run merging.
+//
+// gsummary : IntervalSummary's six doubles {num_bins, num_non_nan, sum, min, max, sum_sq}
+//            (src/GenomeTrackSummary.cpp:22-69). Fixed-shape two-stage reduction (grid partials -> one block), so a
+//            given input always reduces in the same order; results are accumulated into a 6-double device record
+//            that the host reduces across GPUs (NCCL sum / min / max) and finalises with mg_summary_finalize.
+// gdist    : BinFinder::val2bin (src/BinFinder.h:55-108) in double, BinsManager::vals2idx (src/BinsManager.h:53-72).
+//            Small histograms use per-lane private columns in shared memory (no atomics, no bank conflicts);
+//            larger ones shared-memory or global atomics.
+// gscreen  : run-length merge of consecutive TRUE rows (src/GenomeTrackScreener.cpp:195-220).
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
+#include "dense.cuh"
+
+struct Moments {
+	double n, nn, sum, mn, mx, ssq;
+};
+
+__device__ __forceinline__ void mom_init(Moments &m)
+{
+	m.n = 0;
+	m.nn = 0;
+	m.sum = 0;
+	m.mn = 1.7976931348623157e308;
+	m.mx = -1.7976931348623157e308;
+	m.ssq = 0;
+}
+__device__ __forceinline__ void mom_add(Moments &m, double v)
+{
+	m.n += 1;
+	if (!isnan(v)) {
+		m.nn += 1;
+		m.sum += v;
+		m.mn = fmin(m.mn, v);
+		m.mx = fmax(m.mx, v);
+		m.ssq += __dmul_rn(v, v);
+	}
+}
+__device__ __forceinline__ void mom_merge(Moments &a, const Moments &b)
+{
+	a.n += b.n;
+	a.nn += b.nn;
+	a.sum += b.sum;
+	a.mn = fmin(a.mn, b.mn);
+	a.mx = fmax(a.mx, b.mx);
+	a.ssq += b.ssq;
+}
+__device__ __forceinline__ Moments mom_shfl_xor(const Moments &m, int mask)
+{
+	Moments o;
+	o.n = __shfl_xor_sync(0xffffffffu, m.n, mask);
+	o.nn = __shfl_xor_sync(0xffffffffu, m.nn, mask);
+	o.sum = __shfl_xor_sync(0xffffffffu, m.sum, mask);
+	o.mn = __shfl_xor_sync(0xffffffffu, m.mn, mask);
+	o.mx = __shfl_xor_sync(0xffffffffu, m.mx, mask);
+	o.ssq = __shfl_xor_sync(0xffffffffu, m.ssq, mask);
+	return o;
+}
+
+#define MG_SUM_THREADS 256
+#define MG_SUM_MAX_BLOCKS 1184 // 148 SMs x 8
+
+// block-level merge; result valid in thread 0
+__device__ __forceinline__ void mom_block_reduce(Moments &m, Moments *smem /* >= 8 */)
+{
+#pragma unroll
+	for (int k = 16; k > 0; k >>= 1) {
+		Moments o = mom_shfl_xor(m, k);
+		mom_merge(m, o);
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0)
+		smem[warp] = m;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+			mom_merge(m, smem[w]);
+	}
+}
+
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_summary_values(const double *__restrict__ vals, int64_t n, Moments *block_out)
+{
+	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	Moments m;
+	mom_init(m);
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		mom_add(m, __ldcs(vals + i));
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0)
+		block_out[blockIdx.x] = m;
+}
+
+// one block: merge the per-block partials in index order and accumulate into the caller's 6-double record
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_summary_final(const Moments *block_in, int nblocks, double *partial)
+{
+	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	Moments m;
+	mom_init(m);
+	for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+		mom_merge(m, block_in[i]);
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0) {
+		partial[0] += m.n;
+		partial[1] += m.nn;
+		partial[2] += m.sum;
+		partial[3] = fmin(partial[3], m.mn);
+		partial[4] = fmax(partial[4], m.mx);
+		partial[5] += m.ssq;
+	}
+}
+
+__global__ void k_summary_init(double *partial)
+{
+	partial[0] = 0;
+	partial[1] = 0;
+	partial[2] = 0;
+	partial[3] = 1.7976931348623157e308;
+	partial[4] = -1.7976931348623157e308;
+	partial[5] = 0;
+}
+
+// ---- values of one prefix-able dense function for a row (avg / sum / nearest / size / exists), as k_dense_prefix ------
+__device__ __forceinline__ double mg_dense_row_value(const DenseQuery &q, int64_t row, int func)
+{
+	DenseWin w;
+	if (!mg_dense_win(q, row, w))
+		return mg_nan();
+	long long n = 0;
+	double S = 0;
+	const int64_t nb = w.ebin - w.sbin;
+	bool direct = nb <= MG_PREFIX_DIRECT_BINS;
+	if (!direct) {
+		const Pref a = mg_ld_pref(w.ch->pref + w.sbin), b = mg_ld_pref(w.ch->pref + w.ebin);
+		n = b.cnt - a.cnt;
+		S = b.sum - a.sum;
+		if (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)
+			direct = true;
+	}
+	if (direct) {
+		n = 0;
+		S = 0;
+		for (int64_t b = w.sbin; b < w.ebin; ++b) {
+			const float v = __ldg(w.ch->vals + b);
+			if (!isnan(v)) {
+				S += (double)v;
+				++n;
+			}
+		}
+	}
+	if (func == MG_SIZE)
+		return (double)n;
+	if (func == MG_EXISTS)
+		return n > 0 ? 1. : 0.;
+	if (n == 0)
+		return mg_nan();
+	return func == MG_SUM ? mg_f2d(S) : mg_f2d(S / (double)n);
+}
+
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_dense_summary(const DenseQuery q, int func, Moments *block_out)
+{
+	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	Moments m;
+	mom_init(m);
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.count; i += stride)
+		mom_add(m, mg_dense_row_value(q, q.first + i, func));
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0)
+		block_out[blockIdx.x] = m;
+}
+
+// ---- streaming fast path: fixed-bin iterator at the track's own bin size, no shifts => row value == bin value ----------
+// Grid-stride over the implicit rows: a warp reads 128 contiguous bytes of the track per request. Each thread keeps
+// the scope interval it is in and only steps forward (rows grow monotonically along its stride).
+template <typename F>
+__device__ __forceinline__ void mg_stream_rows(const RowSrc &rs, const DenseChrom *table, int64_t first, int64_t count, F &&f)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	int64_t k = -1, row0 = 0, row1 = 0, bin0 = 0, nbins = 0;
+	const float *vals = nullptr;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+		const int64_t r = first + i;
+		if (k < 0 || r >= row1) {
+			k = k < 0 ? mg_scope_of_row(rs, r) : k + 1;
+			while (r >= __ldg(rs.srow0 + k + 1))
+				++k;
+			row0 = __ldg(rs.srow0 + k);
+			row1 = __ldg(rs.srow0 + k + 1);
+			const DenseChrom *ch = table + __ldg(rs.schrom + k);
+			vals = ch->vals;
+			nbins = ch->nbins;
+			bin0 = __ldg(rs.sstart + k) / rs.binsize;
+		}
+		const int64_t b = bin0 + (r - row0);
+		f((double)(b < nbins ? __ldcs(vals + b) : mg_nanf()));
+	}
+}
+
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_dense_stream_summary(const RowSrc rs, const DenseChrom *table, int64_t first,
+																		  int64_t count, Moments *block_out)
+{
+	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	Moments m;
+	mom_init(m);
+	mg_stream_rows(rs, table, first, count, [&](double v) { mom_add(m, v); });
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0)
+		block_out[blockIdx.x] = m;
+}
+
+// ---- histogram -----------------------------------------------------------------------------------------------------------
+#define MG_HIST_MAX_DIMS 8
+#define MG_HIST_MAX_BREAKS 1024 // per call, all dimensions together (constant-bank resident)
+
+struct HistSpec {
+	int ndim;
+	int include_lowest;
+	int nbreaks[MG_HIST_MAX_DIMS];
+	int boff[MG_HIST_MAX_DIMS];      // offset of the dimension's breaks in `breaks`
+	long long mult[MG_HIST_MAX_DIMS]; // first dimension fastest
+	double binsize[MG_HIST_MAX_DIMS]; // BinFinder::m_binsize (0 => binary search)
+	long long total;
+	const double *breaks; // device copy, concatenated
+};
+
+// BinFinder::val2bin, right-closed intervals (src/BinFinder.h:55-81)
+__device__ __forceinline__ int mg_val2bin(const double *br, int nbreaks, double binsize, int include_lowest, double val)
+{
+	const double b0 = br[0];
+	if (include_lowest && val == b0)
+		return 0;
+	if (isnan(val) || val <= b0 || val > br[nbreaks - 1])
+		return -1;
+	const int numbins = nbreaks - 1;
+	if (binsize != 0.) {
+		const int b = (int)ceil(__ddiv_rn(__dsub_rn(val, b0), binsize)) - 1;
+		return b < numbins - 1 ? b : numbins - 1;
+	}
+	unsigned s = 0, e = (unsigned)numbins;
+	while (e - s > 1) {
+		const unsigned mid = (s + e) >> 1;
+		if (val <= br[mid])
+			e = mid;
+		else
+			s = mid;
+	}
+	return (int)s;
+}
+
+#define MG_HIST_THREADS 256
+#define MG_HIST_PRIVATE_MAX 160 // bins: 160 x 32 lanes x 4 B = 20 KB per warp, 8 warps = 160 KB dynamic smem
+
+// 1-D histogram with per-lane private columns: hist[warp][bin][lane]; no atomics in the hot loop.
+template <typename Gen>
+__device__ __forceinline__ void mg_hist1d_private(const HistSpec &hs, uint32_t *smem, unsigned long long *counts, Gen &&gen)
+{
+	const int nb = hs.nbreaks[0] - 1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	double *sbr = reinterpret_cast<double *>(smem);                       // breaks first (8-byte aligned)
+	uint32_t *h = smem + 2 * hs.nbreaks[0] + warp * nb * 32;              // then the per-warp columns
+	for (int t = threadIdx.x; t < hs.nbreaks[0]; t += blockDim.x)
+		sbr[t] = hs.breaks[t];
+	for (int t = lane; t < nb * 32; t += 32)
+		h[t] = 0;
+	__syncthreads();
+	const double binsize = hs.binsize[0];
+	gen([&](double v) {
+		const int b = mg_val2bin(sbr, nb + 1, binsize, hs.include_lowest, v);
+		if (b >= 0)
+			h[b * 32 + lane]++;
+	});
+	__syncthreads();
+	uint32_t *hall = smem + 2 * hs.nbreaks[0];
+	for (int b = warp; b < nb; b += nwarps) { // one warp sums the 32 x nwarps replicas of a bin
+		unsigned long long c = 0;
+		for (int w = 0; w < nwarps; ++w)
+			c += hall[(w * nb + b) * 32 + lane];
+#pragma unroll
+		for (int k = 16; k > 0; k >>= 1)
+			c += __shfl_xor_sync(0xffffffffu, c, k);
+		if (lane == 0 && c)
+			atomicAdd(counts + b, c);
+	}
+}
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_dense_stream_hist(const RowSrc rs, const DenseChrom *table, int64_t first, int64_t count,
+																		const HistSpec hs, unsigned long long *counts)
+{
+	extern __shared__ __align__(16) uint32_t hsmem[];
+	mg_hist1d_private(hs, hsmem, counts, [&](auto &&emit) { mg_stream_rows(rs, table, first, count, emit); });
+}
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_dense_hist_private(const DenseQuery q, int func, const HistSpec hs, unsigned long long *counts)
+{
+	extern __shared__ __align__(16) uint32_t hsmem[];
+	mg_hist1d_private(hs, hsmem, counts, [&](auto &&emit) {
+		const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+		for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.count; i += stride)
+			emit(mg_dense_row_value(q, q.first + i, func));
+	});
+}
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_values_hist_private(const double *__restrict__ vals, int64_t n, const HistSpec hs,
+																		  unsigned long long *counts)
+{
+	extern __shared__ __align__(16) uint32_t hsmem[];
+	mg_hist1d_private(hs, hsmem, counts, [&](auto &&emit) {
+		const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+		for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+			emit(__ldcs(vals + i));
+	});
+}
+
+// general N-D histogram over device columns: global atomics (one per surviving row)
+struct HistCols {
+	const double *col[MG_HIST_MAX_DIMS];
+};
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_hist_nd(const HistCols cols, int64_t n, const HistSpec hs, unsigned long long *counts)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		long long idx = 0;
+		bool ok = true;
+		for (int d = 0; d < hs.ndim && ok; ++d) {
+			const double v = __ldcs(cols.col[d] + i);
+			const int b = mg_val2bin(hs.breaks + hs.boff[d], hs.nbreaks[d], hs.binsize[d], hs.include_lowest, v);
+			if (b < 0)
+				ok = false;
+			else
+				idx += b * hs.mult[d];
+		}
+		if (ok)
+			atomicAdd(counts + idx, 1ull);
+	}
+}
+
+// general 1-D histogram of a dense function that is too wide for private columns
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_dense_hist_global(const DenseQuery q, int func, const HistSpec hs, unsigned long long *counts)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.count; i += stride) {
+		const int b = mg_val2bin(hs.breaks, hs.nbreaks[0], hs.binsize[0], hs.include_lowest, mg_dense_row_value(q, q.first + i, func));
+		if (b >= 0)
+			atomicAdd(counts + b, 1ull);
+	}
+}
+
+// ---- gscreen run merge ---------------------------------------------------------------------------------------------------
+// A TRUE row continues the current output interval iff the previous row is TRUE, on the same chromosome, and ends where
+// this one starts (src/GenomeTrackScreener.cpp:203-211); otherwise it is a run HEAD. A TRUE row whose successor does not
+// continue it is a run TAIL. The k-th head and the k-th tail delimit the k-th output interval, so the merge is two
+// order-preserving compactions (start/chrom from heads, end from tails) over one block-scan.
+#define MG_SCR_THREADS 256
+
+__device__ __forceinline__ void mg_screen_classify(const RowSrc &rs, int64_t first, int64_t count, const int8_t *flag, int64_t i, bool &head,
+												   bool &tail, int &c, int64_t &s, int64_t &e)
+{
+	int64_t k;
+	head = tail = false;
+	if (flag[i] != 1)
+		return;
+	mg_get_row(rs, first + i, c, s, e, k);
+	head = true;
+	if (i > 0 && flag[i - 1] == 1) {
+		int pc;
+		int64_t ps, pe;
+		mg_get_row(rs, first + i - 1, pc, ps, pe, k);
+		head = !(pc == c && pe == s);
+	}
+	tail = true;
+	if (i + 1 < count && flag[i + 1] == 1) {
+		int nc;
+		int64_t ns, ne;
+		mg_get_row(rs, first + i + 1, nc, ns, ne, k);
+		tail = !(nc == c && ns == e);
+	}
+}
+
+__global__ void __launch_bounds__(MG_SCR_THREADS) k_screen_count(const RowSrc rs, int64_t first, int64_t count, const int8_t *flag,
+																  long long *block_heads, long long *block_tails)
+{
+	__shared__ long long sc[33];
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool head = false, tail = false;
+	int c;
+	int64_t s, e;
+	if (i < count)
+		mg_screen_classify(rs, first, count, flag, i, head, tail, c, s, e);
+	long long th, tt;
+	mg_block_excl_scan<long long>(head ? 1 : 0, sc, th);
+	mg_block_excl_scan<long long>(tail ? 1 : 0, sc, tt);
+	if (threadIdx.x == 0) {
+		block_heads[blockIdx.x] = th;
+		block_tails[blockIdx.x] = tt;
+	}
+}
+
+__global__ void __launch_bounds__(1024) k_screen_scan(long long *block_heads, long long *block_tails, int64_t nblocks, long long *total_out)
+{
+	__shared__ long long sc[33];
+	const int64_t chunk = (nblocks + blockDim.x - 1) / blockDim.x;
+	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, nblocks);
+	long long sh = 0, st = 0;
+	for (int64_t i = lo; i < hi; ++i) {
+		sh += block_heads[i];
+		st += block_tails[i];
+	}
+	long long total_h, total_t;
+	long long h0 = mg_block_excl_scan<long long>(sh, sc, total_h);
+	long long t0 = mg_block_excl_scan<long long>(st, sc, total_t);
+	for (int64_t i = lo; i < hi; ++i) {
+		const long long vh = block_heads[i], vt = block_tails[i];
+		block_heads[i] = h0;
+		block_tails[i] = t0;
+		h0 += vh;
+		t0 += vt;
+	}
+	if (threadIdx.x == 0)
+		*total_out = total_h;
+}
+
+__global__ void __launch_bounds__(MG_SCR_THREADS) k_screen_write(const RowSrc rs, int64_t first, int64_t count, const int8_t *flag,
+																  const long long *block_heads, const long long *block_tails, int32_t *ochrom,
+																  int64_t *ostart, int64_t *oend)
+{
+	__shared__ long long sc[33];
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool head = false, tail = false;
+	int c = 0;
+	int64_t s = 0, e = 0;
+	if (i < count)
+		mg_screen_classify(rs, first, count, flag, i, head, tail, c, s, e);
+	long long th, tt;
+	const long long hoff = block_heads[blockIdx.x] + mg_block_excl_scan<long long>(head ? 1 : 0, sc, th);
+	const long long toff = block_tails[blockIdx.x] + mg_block_excl_scan<long long>(tail ? 1 : 0, sc, tt);
+	if (head) {
+		ochrom[hoff] = c;
+		ostart[hoff] = s;
+	}
+	if (tail)
+		oend[toff] = e;
+}

@@ -1,0 +1,185 @@
+"""Parity of the sparse-track, coverage, PWM and iterator-row kernels with the reference's compiled objects
+(golden vectors) and with the oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import CHROMS, assert_close, assert_same, read_seq, read_sparse
+from misha_b200 import gpu
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def sparse_testdb(gpu_ctx):
+    t = gpu.SparseTrack(gpu_ctx)
+    for cid, (c, _) in enumerate(CHROMS):
+        t.stage(cid, *read_sparse("sparse_track", c))
+    return t
+
+
+@pytest.fixture(scope="module")
+def seq_testdb(gpu_ctx):
+    s = gpu.Sequence(gpu_ctx)
+    for cid, (c, _) in enumerate(CHROMS):
+        s.stage(cid, read_seq(c))
+    return s
+
+
+def test_sparse_golden(gpu_ctx, sparse_testdb, golden):
+    names = ("avg", "min", "max", "stddev", "sum", "nearest")
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = golden[f"sparse_{c}_start"], golden[f"sparse_{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        out = sparse_testdb.window(rows, list(names) + [("quantile", 0.9)])
+        for k, name in enumerate(names):
+            # record-order accumulation == the reference's order: everything is bit-exact, including avg/sum/stddev
+            assert_same(out[k], golden[f"sparse_{c}_{name}"], f"{c} {name}")
+        assert_same(out[6], golden[f"sparse_{c}_quantile"], f"{c} quantile")
+
+
+def test_sparse_shifts_vs_oracle(gpu_ctx, sparse_testdb):
+    rng = np.random.default_rng(5)
+    for cid, (c, size) in enumerate(CHROMS):
+        rs, re, rv = read_sparse("sparse_track", c)
+        s = np.sort(rng.integers(0, size - 1, 4000))
+        e = np.minimum(s + rng.integers(1, 300, 4000), size)
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        for sshift, eshift in ((0, 0), (-3000, 3000), (500, -100), (-10**7, 10**7)):
+            names = ("avg", "sum", "min", "max", "stddev", "nearest", "size")
+            got = sparse_testdb.window(rows, list(names) + [("quantile", 0.5)], sshift, eshift)
+            exp = port.sparse_window(rs, re, rv, size, s, e, sshift, eshift, 0.5)
+            for k, name in enumerate(names):
+                assert_same(got[k], exp[name], f"{c} {name} {sshift},{eshift}")
+            assert_same(got[7], exp["quantile"], f"{c} quantile {sshift},{eshift}")
+
+
+def test_sparse_nan_inf_and_empty(gpu_ctx):
+    size = 100000
+    ctx2 = gpu.Context([size, size])
+    try:
+        rs = np.array([100, 300, 500, 700, 900]); re = rs + 100
+        rv = np.array([1.0, np.nan, np.inf, -np.inf, 2.0], dtype=np.float32)
+        t = gpu.SparseTrack(ctx2)
+        t.stage(0, rs, re, rv)
+        t.stage(1, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32))  # empty chromosome
+        s = np.array([0, 150, 250, 350, 450, 0, 650, 950, 2000]); e = np.array([50, 260, 300, 460, 1000, 100000, 700, 960, 3000])
+        for chrom in (0, 1):
+            rows = ctx2.rows_upload(np.full(len(s), chrom), s, e)
+            got = t.window(rows, ["avg", "nearest", "max", "size"])
+            if chrom == 0:
+                exp = port.sparse_window(rs, re, rv, size, s, e, funcs=("avg", "nearest", "max", "size"))
+            else:
+                exp = port.sparse_window(rs[:0], re[:0], rv[:0], size, s, e, funcs=("avg", "nearest", "max", "size"))
+            for k, name in enumerate(("avg", "nearest", "max", "size")):
+                assert_same(got[k], exp[name], f"chrom{chrom} {name}")
+        with pytest.raises(gpu.MishaGpuError):
+            t2 = gpu.SparseTrack(ctx2)
+            t2.stage(0, [10, 5], [20, 8], [1, 2])  # unsorted / overlapping -> reference's load-time error
+    finally:
+        ctx2.close()
+
+
+def test_coverage_known_answers(gpu_ctx):
+    """tests/testthat/test-vtrack-coverage.R:5-29,48-69 (DB-independent)."""
+    iv = gpu.IntervalSet(gpu_ctx)
+    # source chr1: [100,200) and [300,400) (already unified)
+    iv.stage(0, [100, 300], [200, 400])
+    iv.stage(1, [], [])
+    iv.stage(2, [], [])
+
+    def cov(starts, ends, chrom=0, **kw):
+        rows = gpu_ctx.rows_upload(np.full(len(starts), chrom), starts, ends)
+        return iv.coverage(rows, **kw)
+
+    assert_same(cov([0, 100], [100, 200]), [0.0, 1.0], "c(0,1)")
+    assert_same(cov([0, 100, 200, 250, 400], [100, 300, 250, 500, 500]), port.coverage([100, 300], [200, 400], 500000, [0, 100, 200, 250, 400], [100, 300, 250, 500, 500]), "mixed")
+    assert_same(cov([0, 150, 350], [50, 250, 450]), [0.0, 0.5, 0.5], "half")
+    assert_same(cov([0], [500]), [0.4], "0.4")
+    assert_same(cov([0], [10], chrom=1), [0.0], "empty chrom")
+    # out-of-range shifted window -> NaN (src/IntervVarProcessor.cpp:249-252)
+    out = cov([100], [110], sshift=50, eshift=-50)
+    assert np.isnan(out[0])
+
+
+def test_coverage_random_vs_oracle(gpu_ctx):
+    rng = np.random.default_rng(9)
+    iv = gpu.IntervalSet(gpu_ctx)
+    srcs = []
+    for cid, (c, size) in enumerate(CHROMS):
+        st = rng.integers(0, size - 2000, 3000)
+        en = st + rng.integers(1, 1500, 3000)
+        _, us, ue = port.unify(np.zeros(3000), st, en, True)
+        iv.stage(cid, us, ue)
+        srcs.append((us, ue))
+    for cid, (c, size) in enumerate(CHROMS):
+        s = np.sort(rng.integers(0, size - 1, 5000))
+        e = np.minimum(s + rng.integers(1, 5000, 5000), size)
+        rows = gpu_ctx.rows_upload(np.full(5000, cid), s, e)
+        for sshift, eshift in ((0, 0), (-700, 900), (100, -100)):
+            got = iv.coverage(rows, sshift, eshift)
+            assert_same(got, port.coverage(srcs[cid][0], srcs[cid][1], size, s, e, sshift, eshift), f"{c} {sshift}")
+
+
+def test_pwm_golden(gpu_ctx, seq_testdb, golden):
+    logp = gpu.pssm_logp(golden["pwm_pssm20"], 0.01)
+    assert np.array_equal(logp, golden["pwm_logp20"])  # bit-exact table
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = golden[f"pwm_{c}_start"], golden[f"pwm_{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        for bid in (True, False):
+            for ext in (True, False):
+                for mode in ("pwm", "pwm.max", "pwm.count"):
+                    for strand in (1, -1):
+                        if mode == "pwm.max" and strand == -1:
+                            continue
+                        exp = golden[f"pwm_{c}_{mode}_bid{int(bid)}_ext{int(ext)}_str{strand}"]
+                        got = seq_testdb.pwm(rows, logp, bidirect=bid, extend=ext, mode=mode, strand=strand, score_thresh=-25.0)
+                        what = f"{c} {mode} bid={bid} ext={ext} strand={strand}"
+                        if mode == "pwm.count":
+                            # a hit count can move by one when an anchor score sits within 1 ulp of the threshold
+                            assert np.array_equal(np.isnan(got), np.isnan(exp)), what
+                            d = np.abs(got - exp)[~np.isnan(exp)]
+                            assert d.max() <= 1 and (d > 0).mean() < 1e-3, what
+                        elif not bid and mode == "pwm.max":
+                            assert_same(got, exp, what)  # pure float adds in the reference's order
+                        else:
+                            assert_close(got, exp, RTOL, what)
+
+
+def test_pwm_long_rows_and_shift_vs_oracle(gpu_ctx, seq_testdb, golden):
+    logp = gpu.pssm_logp(golden["pwm_pssm20"], 0.01)
+    seq = read_seq("chr2")
+    s = np.array([0, 1000, 250000, 299000, 299990]); e = np.array([5000, 1300, 251000, 300000, 300000])
+    rows = gpu_ctx.rows_upload(np.full(len(s), 1), s, e)
+    for sshift, eshift in ((0, 0), (-200, 300), (10, -5)):
+        for mode in ("pwm", "pwm.max"):
+            got = seq_testdb.pwm(rows, logp, mode=mode, sshift=sshift, eshift=eshift)
+            exp = port.pwm(seq, logp, s, e, True, True, mode, 1, 0.0, sshift, eshift)
+            assert_close(got, exp, RTOL, f"{mode} {sshift},{eshift}")
+
+
+def test_rows_fixedbin_and_intervals_golden(gpu_ctx, golden):
+    # scope is sorted by the entry points before it reaches the iterator
+    sc, ss, se = golden["it_scope_chrom"], golden["it_scope_start"], golden["it_scope_end"]
+    perm = port.sort_perm(sc, ss)
+    for b in (500, 50, 333):
+        rows = gpu_ctx.rows_fixedbin(b, sc[perm], ss[perm], se[perm])
+        c, s, e, k = rows.coords()
+        assert np.array_equal(c, golden[f"it_fixed{b}_chrom"])
+        assert np.array_equal(s, golden[f"it_fixed{b}_start"])
+        assert np.array_equal(e, golden[f"it_fixed{b}_end"])
+        assert np.array_equal(perm[k], golden[f"it_fixed{b}_scope"])  # scope idx = original row (udata)
+    ic, is_, ie = port.unify(golden["it_iv_chrom"], golden["it_iv_start"], golden["it_iv_end"], False)
+    assert np.array_equal(ic, golden["unify0_chrom"]) and np.array_equal(is_, golden["unify0_start"]) and np.array_equal(ie, golden["unify0_end"])
+    sc, ss, se = golden["it_scope2_chrom"], golden["it_scope2_start"], golden["it_scope2_end"]
+    perm = port.sort_perm(sc, ss)
+    rows = gpu_ctx.rows_intervals(ic, is_, ie, sc[perm], ss[perm], se[perm])
+    c, s, e, k = rows.coords()
+    assert np.array_equal(c, golden["it_iv_rows_chrom"])
+    assert np.array_equal(s, golden["it_iv_rows_start"])
+    assert np.array_equal(e, golden["it_iv_rows_end"])
+    assert np.array_equal(perm[k], golden["it_iv_rows_scope"])
+    # known answer: tests/testthat/test-iterator-overlaps.R:444 -- 2 rows for gintervals(1, 0, 1000) at iterator 500
+    assert gpu_ctx.rows_fixedbin(500, [0], [0], [1000]).n == 2

@@ -1,0 +1,163 @@
+"""gsummary / gdist / gscreen kernels against the oracle and the reference's known answers."""
+import numpy as np
+import pytest
+
+from conftest import CHROMS, assert_close, assert_same, read_dense
+from misha_b200 import gpu
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _scope_all():
+    return np.arange(3, dtype=np.int32), np.zeros(3, np.int64), np.array([z for _, z in CHROMS], dtype=np.int64)
+
+
+def _all_bins():
+    return np.concatenate([read_dense("dense_track", c)[1] for c, _ in CHROMS])
+
+
+def _clean(v):
+    v = v.astype(np.float64)
+    v[np.isinf(v)] = np.nan
+    return v
+
+
+def test_gdist_known_answers(gpu_ctx, dense_testdb):
+    """tests/testthat/test-gdist.R:69-72: sum(gdist(dense_track, c(0,.2,.5,1))) == 6546 over chr1, 901 over chr1:0-50000."""
+    for end, expect in ((500000, 6546), (50000, 901)):
+        rows = gpu_ctx.rows_fixedbin(50, [0], [0], [end])
+        counts = gpu_ctx.alloc(3, np.uint64).zero()
+        dense_testdb.hist_dev(rows, "avg", [0, 0.2, 0.5, 1.0], counts)
+        got = counts.to_host()
+        assert int(got.sum()) == expect
+        bins = _clean(read_dense("dense_track", "chr1")[1][: end // 50])
+        assert np.array_equal(got, port.hist(bins, [[0, 0.2, 0.5, 1.0]]))
+
+
+def test_summary_stream_and_generic(gpu_ctx, dense_testdb):
+    sc, ss, se = _scope_all()
+    vals = _clean(_all_bins())
+    exp = port.summary(vals)
+    for binsize in (50,):  # track resolution: streaming kernel
+        rows = gpu_ctx.rows_fixedbin(binsize, sc, ss, se)
+        part = gpu.summary_init(gpu_ctx)
+        dense_testdb.summary_dev(rows, "avg", part)
+        got = gpu.summary_finalize(part.to_host())
+        assert_same(got[:4], exp[:4], "counts/min/max")
+        assert_close(got[4:], exp[4:], 1e-9, "sum/mean/sd")
+    # coarser iterator: prefix path, then sweep path (max) through a device column
+    for func in ("avg", "sum", "max", ("quantile", 0.5)):
+        rows = gpu_ctx.rows_fixedbin(1000, sc, ss, se)
+        part = gpu.summary_init(gpu_ctx)
+        dense_testdb.summary_dev(rows, func, part)
+        got = gpu.summary_finalize(part.to_host())
+        c, s, e, _ = rows.coords()
+        name = func if isinstance(func, str) else func[0]
+        cols = []
+        for cid, (cn, size) in enumerate(CHROMS):
+            bs, bins = read_dense("dense_track", cn)
+            m = c == cid
+            cols.append(port.dense_window(bins, bs, size, s[m], e[m], 0, 0, 0.5, (name,))[name])
+        exp2 = port.summary(np.concatenate(cols))
+        assert_same(got[:2], exp2[:2], f"{name} counts")
+        assert_close(got[2:], exp2[2:], 1e-6, f"{name} moments")
+
+
+def test_summary_values_and_accumulate(gpu_ctx):
+    rng = np.random.default_rng(2)
+    v = rng.lognormal(size=300001)
+    v[rng.random(v.size) < 0.05] = np.nan
+    d = gpu_ctx.alloc(v.size, np.float64).from_host(v)
+    part = gpu.summary_init(gpu_ctx)
+    half = 150000
+    gpu.summary_add(gpu_ctx, d.ptr, half, part)
+    gpu.summary_add(gpu_ctx, d.ptr + 8 * half, v.size - half, part)  # accumulation across calls (chromosome shards)
+    got = gpu.summary_finalize(part.to_host())
+    exp = port.summary(v)
+    assert_same(got[:4], exp[:4], "counts/min/max")
+    assert_close(got[4:], exp[4:], 1e-12, "moments")
+    # all-NaN and empty
+    d2 = gpu_ctx.alloc(10, np.float64).from_host(np.full(10, np.nan))
+    part = gpu.summary_init(gpu_ctx)
+    gpu.summary_add(gpu_ctx, d2.ptr, 10, part)
+    got = gpu.summary_finalize(part.to_host())
+    assert got[0] == 10 and got[1] == 10 and np.all(np.isnan(got[2:]))
+
+
+def test_hist_bins_golden(gpu_ctx, golden):
+    vals = golden["bins_vals"]
+    d = gpu_ctx.alloc(vals.size, np.float64).from_host(vals)
+    for name in ("uniform", "ragged", "uniform_f32"):
+        br = golden[f"bins_{name}_breaks"]
+        for il in (0, 1):
+            ref_bins = golden[f"bins_{name}_il{il}"]
+            exp = np.bincount(ref_bins[ref_bins >= 0], minlength=len(br) - 1).astype(np.uint64)
+            counts = gpu_ctx.alloc(len(br) - 1, np.uint64).zero()
+            gpu.hist_dev(gpu_ctx, [d], vals.size, [br], counts, include_lowest=bool(il))
+            assert np.array_equal(counts.to_host(), exp), f"{name} il={il}"
+
+
+def test_hist_2d_and_wide(gpu_ctx):
+    rng = np.random.default_rng(4)
+    n = 200000
+    a, b = rng.normal(size=n), rng.random(n)
+    a[::97] = np.nan
+    da, db = gpu_ctx.alloc(n, np.float64).from_host(a), gpu_ctx.alloc(n, np.float64).from_host(b)
+    br = [np.linspace(-3, 3, 13), np.array([0, 0.1, 0.5, 0.9, 1.0])]
+    counts = gpu_ctx.alloc(12 * 4, np.uint64).zero()
+    gpu.hist_dev(gpu_ctx, [da, db], n, br, counts, include_lowest=True)
+    exp = port.hist(np.stack([a, b], axis=1), br, True)
+    assert np.array_equal(counts.to_host().reshape(exp.shape, order="F"), exp)
+    # 1-D, more bins than the private-column kernel takes
+    br1 = np.linspace(-4, 4, 1001)
+    counts = gpu_ctx.alloc(1000, np.uint64).zero()
+    gpu.hist_dev(gpu_ctx, [da], n, [br1], counts)
+    assert np.array_equal(counts.to_host(), port.hist(a, [br1]))
+
+
+def test_dense_hist_paths(gpu_ctx, dense_testdb):
+    sc, ss, se = _scope_all()
+    br = np.linspace(0, 1, 101)
+    exp = port.hist(_clean(_all_bins()), [br])
+    rows = gpu_ctx.rows_fixedbin(50, sc, ss, se)
+    counts = gpu_ctx.alloc(100, np.uint64).zero()
+    dense_testdb.hist_dev(rows, "avg", br, counts)
+    assert np.array_equal(counts.to_host(), exp)
+    # windowed avg over a coarser iterator (prefix kernel + private histogram) and max (column + histogram)
+    for func in ("avg", "max"):
+        rows = gpu_ctx.rows_fixedbin(300, sc, ss, se)
+        counts = gpu_ctx.alloc(100, np.uint64).zero()
+        dense_testdb.hist_dev(rows, func, br, counts, sshift=-200, eshift=200)
+        c, s, e, _ = rows.coords()
+        cols = []
+        for cid, (cn, size) in enumerate(CHROMS):
+            bs, bins = read_dense("dense_track", cn)
+            m = c == cid
+            cols.append(port.dense_window(bins, bs, size, s[m], e[m], -200, 200, 0.5, (func,))[func])
+        col = np.concatenate(cols)
+        got, exp2 = counts.to_host(), port.hist(col, [br])
+        if func == "max":
+            assert np.array_equal(got, exp2)
+        else:  # avg is within 1 float ulp of the reference: a value sitting on a break may move one bin
+            assert got.sum() == exp2.sum() and np.abs(got.astype(np.int64) - exp2.astype(np.int64)).sum() <= 4
+
+
+def test_screen_merge(gpu_ctx):
+    rng = np.random.default_rng(8)
+    sc, ss, se = _scope_all()
+    rows = gpu_ctx.rows_fixedbin(20, sc, ss, se)
+    c, s, e, _ = rows.coords()
+    for p in (0.5, 0.95, 0.02, 1.0, 0.0):
+        flag = (rng.random(rows.n) < p).astype(np.int8)
+        flag[rng.random(rows.n) < 0.01] = -128  # NA rows end a run like FALSE
+        dflag = gpu_ctx.alloc(rows.n, np.int8).from_host(flag)
+        gc, gs, ge = gpu.screen_merge(gpu_ctx, rows, dflag)
+        ec, es, ee = port.screen_merge(c, s, e, flag)
+        assert np.array_equal(gc, ec) and np.array_equal(gs, es) and np.array_equal(ge, ee), f"p={p}"
+    # explicit rows with gaps: touching rows merge, gapped rows do not, chromosome change splits
+    ch = np.array([0, 0, 0, 0, 1, 1]); st = np.array([0, 10, 30, 40, 40, 50]); en = np.array([10, 20, 40, 50, 50, 60])
+    rows = gpu_ctx.rows_upload(ch, st, en)
+    dflag = gpu_ctx.alloc(6, np.int8).from_host(np.ones(6, np.int8))
+    gc, gs, ge = gpu.screen_merge(gpu_ctx, rows, dflag)
+    assert gc.tolist() == [0, 0, 1] and gs.tolist() == [0, 30, 40] and ge.tolist() == [20, 50, 60]
