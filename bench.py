@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- iterator intervals/sec of gextract over dense-track window vtracks at hg38 scale (BASELINE.json metric).
+
+Workload (configs[2] of BASELINE.json, the one the metric is quoted on; SURVEY.md 8(d) "C3"): synthetic 3.1 Gbp genome
+(24 hg38-length chromosomes), 20 bp dense track (155 M float32, log-normal, 5 % NaN runs, 0.01 % inf), 10 M sorted
+non-overlapping intervals (100-300 bp), three vtracks avg / max / quantile(0.9) with sshift = -5000, eshift = +5000.
+One "step" = one gextract pass producing the three value columns for every interval.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path (libmishagpu.so)
+  python bench.py --impl reference ...                           the reference's own CPU arithmetic (oracle/_ref),
+                                                                 all host threads it would use, bounded sample per step
+
+N > 1 is launched by torch.distributed.run, one rank per GPU; chromosomes are sharded over ranks (whole chromosomes,
+LPT), there is no data-path collective (each rank owns a disjoint row range) and scaling is weak in the per-GPU sense
+of "the same total job split N ways" -> reported as "strong" (total work fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from misha_b200 import synth  # noqa: E402
+
+BIN = 20
+SSHIFT, ESHIFT = -5000, 5000
+FUNCS = ["avg", "max", ("quantile", 0.9)]
+N_INTERVALS = 10_000_000
+METRIC = "iterator intervals/sec (gextract vtrack avg, hg38-scale)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--intervals", type=int, default=N_INTERVALS, help=argparse.SUPPRESS)  # smaller = NOT the named config
+    ap.add_argument("--scale", type=float, default=1.0, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.lines = []
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        # "under load" = samples at or above the median (idle samples between regions pull the raw median down)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(args, rank, world):
+    chroms = synth.genome(args.scale)
+    owner = synth.lpt_shards(chroms, world)
+    counts = synth.interval_counts(chroms, args.intervals)
+    mine = [i for i in range(len(chroms)) if owner[i] == rank]
+    return chroms, counts, mine
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from misha_b200 import gpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    chroms, counts, mine = build_workload(args, rank, world)
+    sizes = [s for _, s in chroms]
+    ctx = gpu.Context(sizes, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- stage the track once (one-time cost, reported separately) ----
+    t0 = time.perf_counter()
+    dense = gpu.DenseTrack(ctx, BIN)
+    nbins_mine = 0
+    host_bins = {}
+    for i in mine:
+        b = synth.dense_bins(i, sizes[i], BIN)
+        nbins_mine += len(b)
+        dense.stage(i, b)
+        if rank == 0 and world == 1:
+            host_bins[i] = b  # the CPU baseline reads the same data
+    ctx.sync()
+    stage_s = time.perf_counter() - t0
+
+    # ---- intervals in pinned host memory ----
+    n_mine = int(sum(counts[i] for i in mine))
+    h_chrom, h_start, h_end = ctx.pinned(n_mine, np.int32), ctx.pinned(n_mine, np.int64), ctx.pinned(n_mine, np.int64)
+    off = 0
+    iv = {}
+    for i in mine:
+        s, e = synth.intervals(i, sizes[i], int(counts[i]))
+        h_chrom[off:off + len(s)] = i
+        h_start[off:off + len(s)] = s
+        h_end[off:off + len(s)] = e
+        iv[i] = (off, len(s))
+        off += len(s)
+    h_out = [ctx.pinned(n_mine, np.float64) for _ in FUNCS]
+
+    rows = ctx.rows_upload(h_chrom, h_start, h_end)
+    d_out = [ctx.alloc(n_mine, np.float64) for _ in FUNCS]
+
+    def step():
+        dense.window_dev(rows, FUNCS, SSHIFT, ESHIFT, out=d_out, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- kernel-resident throughput: inputs already in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    launches = ctx.launch_count() - launches0
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host arrays in, host columns out ----
+    for _ in range(2):
+        dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    launches += ctx.launch_count() - launches0 - launches
+
+    # ---- per-kernel timing for the roofline (each function group alone, same stream, CUDA events) ----
+    kernels = []
+    for name, funcs in (("k_dense_prefix[avg]", ["avg"]), ("k_dense_sweep[max]", ["max"]), ("k_dense_sweep[quantile]", [("quantile", 0.9)]),
+                        ("k_dense_sweep[avg+max+quantile]", FUNCS)):
+        outs = d_out[:len(funcs)]
+        for _ in range(3):
+            dense.window_dev(rows, funcs, SSHIFT, ESHIFT, out=outs, stream=stream)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            dense.window_dev(rows, funcs, SSHIFT, ESHIFT, out=outs, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        alg = 4 * nbins_mine + n_mine * (20 + 8 * len(funcs))  # unique track bytes + interval in + value columns out
+        kernels.append({"kernel": name, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6})
+    clocks = sampler.stop() if sampler else None
+
+    # parity spot check of what was just timed (size-independent property: host path == device path, bitwise)
+    dev_cols = [d.to_host() for d in d_out]
+    dense.window_dev(rows, FUNCS, SSHIFT, ESHIFT, out=d_out, stream=stream)
+    torch.cuda.synchronize()
+    dev_cols = [d.to_host() for d in d_out]
+    for a, b in zip(dev_cols, h_out):
+        if not np.array_equal(a, b, equal_nan=True):
+            raise SystemExit("bench: host-buffer path and device path disagree")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    n_total = args.intervals
+    # the step is one fused launch today; the dominant kernel is the step's kernel
+    dom = kernels[-1]
+    alg_total_launch = dom["alg_bytes"]
+    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": None,
+                "kernel": dom["kernel"], "alg_bytes_per_launch": alg_total_launch, "peak_source": peak_src,
+                "per_kernel": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(chroms, counts, host_bins, sizes)
+
+    line = {
+        "metric": METRIC, "value": n_total / (ms_step / 1e3), "unit": "intervals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 data / f64 accumulate", "data": "synthetic",
+        "config": {"workload": "C3: gextract avg/max/quantile(0.9) vtracks, sshift/eshift +-5kb, %d sorted intervals (100-300 bp), "
+                               "20 bp dense track on a synthetic %.2f Gbp genome (24 hg38-length chromosomes)" % (n_total, sum(sizes) / 1e9),
+                   "intervals": n_total, "bin_size": BIN, "funcs": ["avg", "max", "quantile(0.9)"], "sharding": "chromosomes, LPT over ranks",
+                   "l2_policy": "inputs larger than L2 (track 0.62 GB + prefix 2.5 GB + intervals 0.2 GB vs 126 MB L2)",
+                   "staging_s_one_time": round(stage_s, 3), "hbm_bytes_staged_rank0": dense.bytes()},
+        "e2e": {"value": n_total / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n_mine * 20), "d2h_bytes_per_step": int(n_mine * 8 * len(FUNCS)),
+                "ms_per_step": e2e_s * 1e3, "api": "mg_h_dense_window (pinned host arrays in, host columns out)"},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def make_cpu_sample(chroms, counts, host_bins, sizes, n_sample, procs):
+    from oracle.cpu_baseline import DenseSample
+    sample = DenseSample(BIN, SSHIFT, ESHIFT, ("avg", "max", "quantile"), 0.9)
+    # the reference shards by chromosome: take the first intervals of `procs` chromosomes
+    ids = sorted(host_bins)[:max(procs, 1)] if host_bins else list(range(min(procs, len(chroms))))
+    per = max(1, n_sample // len(ids))
+    for i in ids:
+        bins = host_bins[i] if i in host_bins else synth.dense_bins(i, sizes[i], BIN)
+        s, e = synth.intervals(i, sizes[i], int(counts[i]))
+        sample.add(i, chroms[i][0], sizes[i], bins, s[:per], e[:per])
+    return sample
+
+
+def cpu_baseline(chroms, counts, host_bins, sizes, target_cpu_s=20.0):
+    from oracle.cpu_baseline import default_procs
+    procs = default_procs()
+    pilot = make_cpu_sample(chroms, counts, host_bins, sizes, 20000, 1)
+    dt, n, kind, _ = pilot.run(1)
+    pilot.close()
+    per_row = dt / max(n, 1)
+    n_sample = int(min(max(target_cpu_s / per_row, 100000), 4_000_000))
+    sample = make_cpu_sample(chroms, counts, host_bins, sizes, n_sample, procs)
+    dt, n, kind, used = sample.run(procs)
+    sample.close()
+    return {"value": n / dt, "unit": "intervals/s", "cores": used, "kind": kind,
+            "sample": "%d of the 10 M intervals (first %d of each of %d chromosomes), same track; forked workers sharded by chromosome as "
+                      "gextract_multitask does, floor(0.7 x %d cores) = %d processes; single-thread cost %.2f us/interval; R assembly omitted"
+                      % (n, n // max(used, 1), used, os.cpu_count() or 1, procs, per_row * 1e6)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import default_procs
+    chroms = synth.genome(args.scale)
+    counts = synth.interval_counts(chroms, args.intervals)
+    sizes = [s for _, s in chroms]
+    procs = default_procs()
+    pilot = make_cpu_sample(chroms, counts, {}, sizes, 20000, 1)
+    dt, n, kind, _ = pilot.run(1)
+    pilot.close()
+    per_row = dt / max(n, 1)
+    steps, warm = args.steps, max(args.warmup, 1)
+    budget_s = 150.0  # whole run
+    n_sample = int(min(max(budget_s / (steps + warm) * procs / per_row * 0.8, 50000), 3_000_000))
+    sample = make_cpu_sample(chroms, counts, {}, sizes, n_sample, procs)
+    for _ in range(warm):
+        sample.run(procs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, n, kind, used = sample.run(procs)
+    dt = (time.perf_counter() - t0) / steps
+    sample.close()
+    val = n / dt
+    desc = ("%d of the 10 M intervals per step (first %d of each of %d chromosomes); forked workers sharded by chromosome, "
+            "floor(0.7 x %d cores) = %d processes; R data-frame assembly omitted (optimistic for the CPU)" % (n, n // used, used, os.cpu_count() or 1, procs))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "intervals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 data / f64 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "C3: gextract avg/max/quantile(0.9) vtracks, sshift/eshift +-5kb, sorted intervals (100-300 bp), 20 bp dense "
+                               "track on a synthetic %.2f Gbp genome; bounded sample per step" % (sum(sizes) / 1e9),
+                   "intervals": args.intervals, "bin_size": BIN, "funcs": ["avg", "max", "quantile(0.9)"]},
+        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": used, "kind": kind, "sample": desc},
+        "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

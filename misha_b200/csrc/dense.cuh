@@ -358,6 +358,9 @@ __device__ __forceinline__ double mg_interp(float x1, float x2, double wgt)
 	return mg_f2d(__dadd_rn(__dmul_rn((double)x1, __dsub_rn(1., wgt)), __dmul_rn((double)x2, wgt)));
 }
 
+// Specialised on what the requested function set needs, so that e.g. a max-only query does not pay for the
+// double-precision Welford update: SUM (avg/sum/nearest), MM (min/max), SD (stddev), Q (quantiles).
+template <bool SUM, bool MM, bool SD, bool Q>
 __global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQuery q)
 {
 	__shared__ float sbuf[MG_SW_WARPS][MG_SW_CAP];
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQue
 		long long n = 0;
 		double S = 0, mean = 0, m2 = 0;
 		float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
-		const bool want_q = q.nq > 0;
+		const bool want_q = Q;
 		bool in_smem = true;
 		if (ok) {
 			const float *vals = w.ch->vals;
@@ -379,13 +382,18 @@ __global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQue
 				float v = b < w.ebin ? __ldg(vals + b) : mg_nanf();
 				const bool valid = !isnan(v);
 				if (valid) {
-					S += (double)v;
-					fmin = fminf(fmin, v);
-					fmax = fmaxf(fmax, v);
 					++n;
-					const double d = (double)v - mean;
-					mean += d / (double)n;
-					m2 += d * ((double)v - mean);
+					if (SUM)
+						S += (double)v;
+					if (MM) {
+						fmin = fminf(fmin, v);
+						fmax = fmaxf(fmax, v);
+					}
+					if (SD) {
+						const double d = (double)v - mean;
+						mean += d / (double)n;
+						m2 += d * ((double)v - mean);
+					}
 				}
 			}
 		}
@@ -393,23 +401,25 @@ __global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQue
 #pragma unroll
 		for (int m = 16; m > 0; m >>= 1) {
 			const long long on = __shfl_xor_sync(0xffffffffu, n, m);
-			const double oS = __shfl_xor_sync(0xffffffffu, S, m);
-			const double omean = __shfl_xor_sync(0xffffffffu, mean, m);
-			const double om2 = __shfl_xor_sync(0xffffffffu, m2, m);
-			const float omin = __shfl_xor_sync(0xffffffffu, fmin, m);
-			const float omax = __shfl_xor_sync(0xffffffffu, fmax, m);
 			const long long tn = n + on;
-			if (tn > 0) {
-				// symmetric form so both partners compute identical results
-				const double d = omean - mean;
-				const double nm = ((double)n * mean + (double)on * omean) / (double)tn;
-				m2 = m2 + om2 + d * d * ((double)n * (double)on / (double)tn);
-				mean = nm;
+			if (SD) {
+				const double omean = __shfl_xor_sync(0xffffffffu, mean, m);
+				const double om2 = __shfl_xor_sync(0xffffffffu, m2, m);
+				if (tn > 0) {
+					// symmetric form so both partners compute identical results
+					const double d = omean - mean;
+					const double nm = ((double)n * mean + (double)on * omean) / (double)tn;
+					m2 = m2 + om2 + d * d * ((double)n * (double)on / (double)tn);
+					mean = nm;
+				}
 			}
 			n = tn;
-			S += oS;
-			fmin = fminf(fmin, omin);
-			fmax = fmaxf(fmax, omax);
+			if (SUM)
+				S += __shfl_xor_sync(0xffffffffu, S, m);
+			if (MM) {
+				fmin = fminf(fmin, __shfl_xor_sync(0xffffffffu, fmin, m));
+				fmax = fmaxf(fmax, __shfl_xor_sync(0xffffffffu, fmax, m));
+			}
 		}
 		// quantiles
 		double qv[MG_MAX_Q];

@@ -387,7 +387,19 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 	} else {
 		const int64_t blocks_needed = mg_div_up(q.count, MG_SW_WARPS);
 		const int64_t cap = (int64_t)ctx->sm_count * 32; // grid-stride beyond that
-		k_dense_sweep<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), MG_SW_WARPS * 32, 0, st>>>(q);
+		const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
+		const bool sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST], mm = q.out[MG_MIN] || q.out[MG_MAX], sd = q.out[MG_STDDEV] != nullptr,
+				   qq = q.nq > 0;
+		const int key = (sum ? 1 : 0) | (mm ? 2 : 0) | (sd ? 4 : 0) | (qq ? 8 : 0);
+#define MG_SWEEP_CASE(K)                                                                                                \
+	case K:                                                                                                             \
+		k_dense_sweep<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, MG_SW_WARPS * 32, 0, st>>>(q);   \
+		break;
+		switch (key) {
+			MG_SWEEP_CASE(0) MG_SWEEP_CASE(1) MG_SWEEP_CASE(2) MG_SWEEP_CASE(3) MG_SWEEP_CASE(4) MG_SWEEP_CASE(5) MG_SWEEP_CASE(6) MG_SWEEP_CASE(7)
+			MG_SWEEP_CASE(8) MG_SWEEP_CASE(9) MG_SWEEP_CASE(10) MG_SWEEP_CASE(11) MG_SWEEP_CASE(12) MG_SWEEP_CASE(13) MG_SWEEP_CASE(14) MG_SWEEP_CASE(15)
+		}
+#undef MG_SWEEP_CASE
 	}
 	MG_LAUNCH_CHECK(ctx);
 	return 0;

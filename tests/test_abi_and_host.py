@@ -1,0 +1,132 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports every declared symbol, the product
+never touches the oracle, the synthetic writers speak the reference's on-disk formats, multi-rank reductions work (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from misha_b200 import _lib, build
+    so = build.build()
+    lib = ctypes.CDLL(so)
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 40
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.mg_abi_version.restype = ctypes.c_int
+    assert lib.mg_abi_version() == 1
+
+
+def test_built_for_sm_100a():
+    from misha_b200 import build
+    so = build.build()
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback_init_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    from misha_b200 import gpu
+    try:
+        gpu.Context([1000])
+    except gpu.MishaGpuError as e:
+        assert "no CUDA device" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("Context() must fail without a GPU")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "misha_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "libmisha_ref" not in txt, f
+
+
+def test_synth_formats_roundtrip(tmp_path):
+    from misha_b200 import synth
+    from oracle import ref
+    chroms = [("chr1", 100000), ("chr2", 60000)]
+    synth.write_chrom_sizes(str(tmp_path), chroms)
+    assert open(tmp_path / "chrom_sizes.txt").read() == "1\t100000\n2\t60000\n"
+    bins = synth.dense_bins(0, 100000, 20)
+    assert len(bins) == 5000 and np.isnan(bins).any()
+    synth.write_dense_chrom(str(tmp_path), "d", "chr1", bins, 20)
+    f = str(tmp_path / "tracks" / "d.track" / "chr1")
+    assert os.path.getsize(f) == 4 + 4 * 5000
+    s, e, v = synth.sparse_records(0, 100000, 150)
+    assert np.all(s[1:] >= e[:-1]) and np.all(s < e) and e[-1] <= 100000
+    synth.write_sparse_chrom(str(tmp_path), "s", "chr1", s, e, v)
+    assert os.path.getsize(tmp_path / "tracks" / "s.track" / "chr1") == 4 + 20 * 150
+    if ref.available():  # the reference's own readers accept the files
+        r = ref.dense_eval(f, 0, [0], [100000], ("avg",))
+        assert np.isfinite(r["avg"][0])
+        r = ref.sparse_eval(str(tmp_path / "tracks" / "s.track" / "chr1"), 0, [0], [100000], ("avg",))
+        assert np.isfinite(r["avg"][0])
+    a, b = synth.intervals(1, 60000, 100)
+    assert np.all(a[1:] > b[:-1]) and b[-1] <= 60000 and np.all((b - a >= 100) & (b - a <= 300))
+    assert np.array_equal(synth.dense_bins(0, 100000, 20), bins, equal_nan=True)  # seeded
+
+
+def test_lpt_sharding_and_counts():
+    from misha_b200 import synth
+    chroms = synth.genome()
+    assert len(chroms) == 24 and chroms[0][0] == "chr1" and chroms[1][0] == "chr10"
+    cnt = synth.interval_counts(chroms, 10_000_000)
+    assert cnt.sum() == 10_000_000
+    for w in (1, 2, 4, 8):
+        owner = synth.lpt_shards(chroms, w)
+        load = np.zeros(w)
+        for i, (_, s) in enumerate(chroms):
+            load[owner[i]] += s
+        assert load.max() / load.mean() < 1.12
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from misha_b200 import dist as mdist
+from oracle import port
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+rng = np.random.default_rng(5)
+v = rng.lognormal(size=20001); v[::13] = np.nan
+halves = [v[:9000], v[9000:]]
+mine = halves[rank]
+fin = mine[~np.isnan(mine)]
+part = np.array([len(mine), len(fin), fin.sum(), fin.min(), fin.max(), (fin * fin).sum()])
+tot = mdist.reduce_summary(part)
+exp = port.summary(v)
+assert tot[0] == exp[0] and tot[0] - tot[1] == exp[1] and tot[3] == exp[2] and tot[4] == exp[3]
+assert abs(tot[2] - exp[4]) <= 1e-12 * abs(exp[4])
+br = np.linspace(0, 10, 41)
+h = mdist.reduce_hist(port.hist(mine, [br]))
+assert np.array_equal(h, port.hist(v, [br]))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_reductions_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o

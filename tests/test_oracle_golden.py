@@ -1,0 +1,159 @@
+"""CPU tests: the oracle (oracle/oracle.c) is pinned against
+  (a) tests/golden/ref_vectors.npz -- outputs of the reference's OWN compiled objects (make_fixtures.py),
+  (b) the known answers the reference's tests hold for this path,
+  (c) the compiled reference live, when oracle/_ref/libmisha_ref.so is present (build container and GPU box)."""
+import numpy as np
+import pytest
+
+from conftest import CHROMS, TESTDB, assert_same, read_dense, read_seq, read_sparse
+from oracle import port, ref
+
+DENSE_FUNCS = ("avg", "min", "max", "stddev", "sum", "quantile")
+
+
+def test_dense_matches_reference_golden(golden):
+    for c, size in CHROMS:
+        bs, bins = read_dense("dense_track", c)
+        s, e = golden[f"dense_{c}_start"], golden[f"dense_{c}_end"]
+        out = port.dense_window(bins, bs, size, s, e, 0, 0, 0.9, DENSE_FUNCS)
+        for k in DENSE_FUNCS:
+            assert_same(out[k], golden[f"dense_{c}_{k}"], f"{c} {k}")
+        for q in (0.5, 0.0, 1.0):
+            out = port.dense_window(bins, bs, size, s, e, 0, 0, q, ("quantile",))
+            assert_same(out["quantile"], golden[f"dense_{c}_quantile_{q}"], f"{c} q{q}")
+        # the reference's single-function and Kahan sliding fast paths give the same floats on this data
+        s, e = golden[f"dense_{c}_slide_start"], golden[f"dense_{c}_slide_end"]
+        out = port.dense_window(bins, bs, size, s, e, 0, 0, 0.5, ("avg", "sum"))
+        assert_same(out["avg"], golden[f"dense_{c}_slide_avg"], f"{c} slide avg")
+        assert_same(out["sum"], golden[f"dense_{c}_slide_sum"], f"{c} slide sum")
+
+
+def test_dense_survey_known_values():
+    """chr1 [0,1000) of the bundled dense_track."""
+    bs, bins = read_dense("dense_track", "chr1")
+    out = port.dense_window(bins, bs, 500000, [0], [1000], 0, 0, 0.9, DENSE_FUNCS)
+    assert np.float32(out["avg"][0]) == np.float32(0.0898888856)
+    assert np.float32(out["sum"][0]) == np.float32(1.79777777)
+    assert np.float32(out["stddev"][0]) == np.float32(0.075674057)
+    assert np.float32(out["quantile"][0]) == np.float32(0.178000003)
+
+
+def test_sparse_matches_reference_golden(golden):
+    funcs = ("avg", "min", "max", "stddev", "sum", "nearest", "quantile")
+    for c, size in CHROMS:
+        rs, re, rv = read_sparse("sparse_track", c)
+        s, e = golden[f"sparse_{c}_start"], golden[f"sparse_{c}_end"]
+        out = port.sparse_window(rs, re, rv, size, s, e, 0, 0, 0.9, funcs)
+        for k in funcs:
+            assert_same(out[k], golden[f"sparse_{c}_{k}"], f"{c} {k}")
+
+
+def test_sparse_survey_known_values():
+    """nearest between records (0,50) and (100,150) ties to the earlier record."""
+    rs, re, rv = read_sparse("sparse_track", "chr1")
+    out = port.sparse_window(rs, re, rv, 500000, [50, 200, 0], [100, 250, 400], funcs=("avg", "nearest", "max"))
+    assert np.isnan(out["avg"][0]) and np.float32(out["nearest"][0]) == np.float32(0.355555564)
+    assert np.float32(out["nearest"][1]) == np.float32(0.4)
+    assert np.float32(out["avg"][2]) == np.float32(0.371851861) and np.float32(out["max"][2]) == np.float32(0.4)
+
+
+def test_gdist_known_answers():
+    """tests/testthat/test-gdist.R:69-72."""
+    _, bins = read_dense("dense_track", "chr1")
+    v = bins.astype(np.float64)
+    v[np.isinf(v)] = np.nan
+    assert int(port.hist(v, [[0, 0.2, 0.5, 1.0]]).sum()) == 6546
+    assert int(port.hist(v[:1000], [[0, 0.2, 0.5, 1.0]]).sum()) == 901
+
+
+def test_val2bin_matches_reference_golden(golden):
+    vals = golden["bins_vals"]
+    for name in ("uniform", "ragged", "uniform_f32"):
+        br = golden[f"bins_{name}_breaks"]
+        for il in (0, 1):
+            assert np.array_equal(port.val2bin(br, vals, bool(il)), golden[f"bins_{name}_il{il}"]), f"{name} il={il}"
+
+
+def test_coverage_known_answers():
+    """tests/testthat/test-vtrack-coverage.R:5-29,48-69 (source [100,200),[300,400) on chr1)."""
+    cs, ce = [100, 300], [200, 400]
+    assert_same(port.coverage(cs, ce, 500000, [0, 100], [100, 200]), [0.0, 1.0])
+    assert_same(port.coverage(cs, ce, 500000, [0, 150, 350], [50, 250, 450]), [0.0, 0.5, 0.5])
+    assert_same(port.coverage(cs, ce, 500000, [0, 100, 200, 300, 400], [100, 200, 300, 400, 500]), [0, 1, 0, 1, 0])
+    assert_same(port.coverage(cs, ce, 500000, [0], [500]), [0.4])
+    assert np.isnan(port.coverage(cs, ce, 500000, [100], [110], 50, -50)[0])
+
+
+def test_iterators_match_reference_golden(golden):
+    sc, ss, se = golden["it_scope_chrom"], golden["it_scope_start"], golden["it_scope_end"]
+    perm = port.sort_perm(sc, ss)
+    for b in (500, 50, 333):
+        c, s, e, k = port.fixedbin_rows(b, sc[perm], ss[perm], se[perm])
+        assert np.array_equal(c, golden[f"it_fixed{b}_chrom"]) and np.array_equal(s, golden[f"it_fixed{b}_start"])
+        assert np.array_equal(e, golden[f"it_fixed{b}_end"]) and np.array_equal(perm[k], golden[f"it_fixed{b}_scope"])
+    for touch in (0, 1):
+        u = port.unify(golden["it_iv_chrom"], golden["it_iv_start"], golden["it_iv_end"], bool(touch))
+        for a, key in zip(u, ("chrom", "start", "end")):
+            assert np.array_equal(a, golden[f"unify{touch}_{key}"])
+    ic, is_, ie = port.unify(golden["it_iv_chrom"], golden["it_iv_start"], golden["it_iv_end"], False)
+    sc, ss, se = golden["it_scope2_chrom"], golden["it_scope2_start"], golden["it_scope2_end"]
+    perm = port.sort_perm(sc, ss)
+    c, s, e, k = port.intervals_rows(ic, is_, ie, sc[perm], ss[perm], se[perm])
+    assert np.array_equal(c, golden["it_iv_rows_chrom"]) and np.array_equal(s, golden["it_iv_rows_start"])
+    assert np.array_equal(e, golden["it_iv_rows_end"]) and np.array_equal(perm[k], golden["it_iv_rows_scope"])
+    # tests/testthat/test-iterator-overlaps.R:444: 2 rows for gintervals(1, 0, 1000) at iterator 500
+    assert len(port.fixedbin_rows(500, [0], [0], [1000])[0]) == 2
+
+
+def test_percentile_matches_reference_golden(golden):
+    for n in (1, 2, 3, 10, 511, 512, 525):
+        v = golden[f"pct_vals_{n}"]
+        got = [port.percentile(v, p) for p in (0.0, 0.1, 0.5, 0.9, 0.999, 1.0)]
+        assert_same(np.array(got), golden[f"pct_out_{n}"], f"n={n}")
+
+
+def test_pwm_matches_reference_golden(golden):
+    logp = port.pssm_logp(golden["pwm_pssm20"], 0.01)
+    assert np.array_equal(logp, golden["pwm_logp20"])
+    for c, size in CHROMS:
+        seq = read_seq(c)
+        s, e = golden[f"pwm_{c}_start"], golden[f"pwm_{c}_end"]
+        for bid in (True, False):
+            for ext in (True, False):
+                for mode in ("pwm", "pwm.max", "pwm.count"):
+                    for strand in (1, -1):
+                        if mode == "pwm.max" and strand == -1:
+                            continue
+                        got = port.pwm(seq, logp, s, e, bid, ext, mode, strand, -25.0)
+                        assert_same(got, golden[f"pwm_{c}_{mode}_bid{int(bid)}_ext{int(ext)}_str{strand}"], f"{c} {mode} {bid} {ext} {strand}")
+
+
+def test_summary_and_screen_merge():
+    v = np.array([1.0, np.nan, 3.0, 2.0])
+    out = port.summary(v)
+    assert out[0] == 4 and out[1] == 1 and out[2] == 1 and out[3] == 3 and out[4] == 6 and out[5] == 2
+    assert abs(out[6] - 1.0) < 1e-15
+    assert np.all(np.isnan(port.summary([np.nan])[2:]))
+    c, s, e = port.screen_merge([0, 0, 0, 1], [0, 10, 30, 30], [10, 20, 40, 40], [1, 1, 1, 1])
+    assert c.tolist() == [0, 0, 1] and s.tolist() == [0, 30, 30] and e.tolist() == [20, 40, 40]
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libmisha_ref.so not built")
+def test_port_matches_compiled_reference_live():
+    """Seeded cross-check against the reference's own objects (sorted rows, as the scanner feeds them)."""
+    import os
+    rng = np.random.default_rng(123)
+    for cid, (c, size) in enumerate(CHROMS):
+        s = np.sort(rng.integers(0, size - 1, 3000))
+        e = np.minimum(s + rng.choice([1, 20, 50, 777, 10000], 3000), size)
+        bs, bins = read_dense("dense_track", c)
+        r = ref.dense_eval(os.path.join(TESTDB, "tracks", "dense_track.track", c), cid, s, e, DENSE_FUNCS, 0.37)
+        o = port.dense_window(bins, bs, size, s, e, 0, 0, 0.37, DENSE_FUNCS)
+        for k in DENSE_FUNCS:
+            assert_same(o[k], r[k], f"dense {c} {k}")
+        rs, re, rv = read_sparse("sparse_track", c)
+        funcs = ("avg", "min", "max", "stddev", "sum", "nearest", "quantile")
+        r = ref.sparse_eval(os.path.join(TESTDB, "tracks", "sparse_track.track", c), cid, s, e, funcs, 0.37)
+        o = port.sparse_window(rs, re, rv, size, s, e, 0, 0, 0.37, funcs)
+        for k in funcs:
+            assert_same(o[k], r[k], f"sparse {c} {k}")
