@@ -73,6 +73,9 @@ int mg_init(int device, int nchroms, const int64_t *chrom_sizes, mg_ctx **out);
 void mg_shutdown(mg_ctx *ctx);
 const char *mg_last_error(const mg_ctx *ctx); /* ctx may be NULL: error of the last failed mg_init in this thread */
 int mg_sync(mg_ctx *ctx, void *stream);
+/* Tuning / ablation switches. "force_sweep" = 1 routes min / max / quantile through the warp-per-row sweep kernel
+ * instead of the per-chromosome index structures (same results; used by tests and profiling). */
+int mg_set_option(mg_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this ctx has launched since mg_init (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const mg_ctx *ctx);
 /* device properties of the ctx's GPU: SM count, bytes of HBM, compute capability major*10+minor */

@@ -23,6 +23,7 @@ struct mg_ctx {
 	std::vector<int64_t> chrom_sizes;
 	int64_t *d_chrom_sizes = nullptr;
 	int64_t launches = 0;
+	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;
 	// internal streams + staging buffers of the host-buffer entry points (lazily created)
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};

@@ -14,11 +14,20 @@ struct __align__(16) Pref {
 	long long cnt;
 };
 
+#define MG_PYR_MAX 14 // fan-out 8 levels above the raw bins: enough for 2^45 bins
+
 struct DenseChrom {
 	const float *vals;
 	const Pref *pref;
 	int64_t nbins;
 	double abs_sum; // sum |v| over the chromosome: scale of the prefix rounding error (cancellation guard)
+	// index structures (dense_index.cuh)
+	const float *pmax[MG_PYR_MAX];
+	const float *pmin[MG_PYR_MAX];
+	const uint32_t *wm;       // wavelet matrix, 32 levels x wm_blocks x 8 uint32
+	const uint32_t *wm_zeros; // zeros per level (32)
+	int64_t wm_blocks;
+	int64_t wm_m;             // number of non-NaN bins
 };
 
 struct mg_dense {

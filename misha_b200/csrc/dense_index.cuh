@@ -1,0 +1,329 @@
+// dense_index.cuh -- per-chromosome index structures built once at staging so that EVERY dense window function of an
+// arbitrary row is O(1) or O(log) lookups from one thread (no per-row sweep of the window):
+//
+//   prefix sums (dense.cuh)      avg / sum / nearest / size / exists      2 x 16-byte entries
+//   min / max pyramids           fan-out 8; level j entry i = extremum of level j-1 entries [8i, 8i+8)
+//                                a window decomposes into <= 7 head + <= 7 tail entries per level: 2 sectors per level
+//   wavelet matrix               over the order-preserving uint32 keys of the non-NaN values (compacted in bin order;
+//                                a window maps to [cnt[sbin], cnt[ebin]) through the prefix counts). Level L holds bit
+//                                31-L of every key after the stable partitions of levels 0..L-1, in 32-byte blocks
+//                                {uint32 ones before the block, 7 x uint32 bits} so one sector answers a rank query.
+//                                k-th smallest of a window = 32 dependent rank pairs (fewer: constant levels are
+//                                skipped and a singleton range needs one rank per level). Exact for any window size.
+#pragma once
+#include "common.cuh"
+#include "dense.cuh"
+
+// ------------------------------------------------------------------------------------------------------------------
+// pyramids
+__global__ void __launch_bounds__(256) k_pyr_build(const float *__restrict__ child_max, const float *__restrict__ child_min, int64_t nchild,
+													float *pmax, float *pmin, int64_t nparent_padded)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nparent_padded)
+		return;
+	float mx = __int_as_float(0xff800000), mn = __int_as_float(0x7f800000);
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const int64_t c = i * 8 + j;
+		if (c < nchild) {
+			mx = fmaxf(mx, child_max[c]); // fmaxf/fminf return the non-NaN operand: NaN bins are skipped
+			mn = fminf(mn, child_min[c]);
+		}
+	}
+	pmax[i] = mx;
+	pmin[i] = mn;
+}
+
+// extremum over entries [lo, hi) of one aligned group of 8 (lo, hi within [g, g+8]); two 16-byte loads = one sector
+template <bool IS_MAX>
+__device__ __forceinline__ float mg_group_ext(const float *__restrict__ p, int64_t g, int lo, int hi, float acc)
+{
+	const float4 a = __ldg(reinterpret_cast<const float4 *>(p + g));
+	const float4 b = __ldg(reinterpret_cast<const float4 *>(p + g + 4));
+	const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		if (j >= lo && j < hi)
+			acc = IS_MAX ? fmaxf(acc, v[j]) : fminf(acc, v[j]);
+	return acc;
+}
+
+// extremum of bins [s, e), s < e. Returns -inf (max) / +inf (min) when every bin is NaN.
+template <bool IS_MAX>
+__device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, int64_t e)
+{
+	float acc = IS_MAX ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+	int64_t lo = s, hi = e;
+	for (int level = 0; lo < hi; ++level) {
+		const float *p = level == 0 ? ch->vals : (IS_MAX ? ch->pmax[level - 1] : ch->pmin[level - 1]);
+		const int64_t glo = lo & ~7ll, ghi = hi & ~7ll;
+		if (glo == ghi || (glo + 8 == hi)) { // the whole range sits in one group
+			acc = mg_group_ext<IS_MAX>(p, glo, (int)(lo - glo), (int)(hi - glo), acc);
+			break;
+		}
+		int64_t nlo = lo;
+		if (lo != glo) { // partial head group
+			acc = mg_group_ext<IS_MAX>(p, glo, (int)(lo - glo), 8, acc);
+			nlo = glo + 8;
+		}
+		if (hi != ghi) // partial tail group
+			acc = mg_group_ext<IS_MAX>(p, ghi, 0, (int)(hi - ghi), acc);
+		lo = nlo >> 3;
+		hi = ghi >> 3;
+	}
+	return acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wavelet matrix
+#define MG_WM_BLOCK_BITS 224
+#define MG_WM_LEVELS 32
+
+// compact the non-NaN values' keys in bin order: keys[cnt[i]] = fkey(vals[i])
+__global__ void __launch_bounds__(256) k_wm_compact(const float *__restrict__ vals, const Pref *__restrict__ pref, int64_t nbins, uint32_t *keys)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nbins)
+		return;
+	const float v = vals[i];
+	if (!isnan(v))
+		keys[pref[i].cnt] = mg_fkey(v);
+}
+
+// one thread per 32 positions: the level's bit words + per-block popcounts. blocks[b] = {ones (later: ones before), 7 words}
+__global__ void __launch_bounds__(256) k_wm_bits(const uint32_t *__restrict__ keys, int64_t m, int shift, uint32_t *blocks, int64_t nblocks)
+{
+	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // word index, 7 words per block
+	if (w >= nblocks * 7)
+		return;
+	const int64_t p0 = w * 32;
+	uint32_t bits = 0;
+#pragma unroll 8
+	for (int j = 0; j < 32; ++j) {
+		const int64_t p = p0 + j;
+		if (p < m)
+			bits |= ((keys[p] >> shift) & 1u) << j;
+	}
+	const int64_t b = w / 7;
+	blocks[b * 8 + 1 + (w - b * 7)] = bits;
+}
+
+// one block: per-block popcounts -> exclusive "ones before" headers; zeros[level] = m - total ones
+__global__ void __launch_bounds__(1024) k_wm_scan(uint32_t *blocks, int64_t nblocks, int64_t m, uint32_t *zeros_out)
+{
+	__shared__ long long sc[33];
+	const int64_t chunk = (nblocks + blockDim.x - 1) / blockDim.x;
+	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, nblocks);
+	long long s = 0;
+	for (int64_t b = lo; b < hi; ++b) {
+		const uint32_t *w = blocks + b * 8;
+		s += __popc(w[1]) + __popc(w[2]) + __popc(w[3]) + __popc(w[4]) + __popc(w[5]) + __popc(w[6]) + __popc(w[7]);
+	}
+	long long total;
+	long long s0 = mg_block_excl_scan<long long>(s, sc, total);
+	for (int64_t b = lo; b < hi; ++b) {
+		uint32_t *w = blocks + b * 8;
+		w[0] = (uint32_t)s0;
+		s0 += __popc(w[1]) + __popc(w[2]) + __popc(w[3]) + __popc(w[4]) + __popc(w[5]) + __popc(w[6]) + __popc(w[7]);
+	}
+	if (threadIdx.x == 0)
+		*zeros_out = (uint32_t)(m - total);
+}
+
+// ones among positions [0, i) of a level
+__device__ __forceinline__ uint32_t mg_wm_rank1(const uint32_t *__restrict__ level, uint32_t i, uint32_t &bit_at_i)
+{
+	const uint32_t b = i / MG_WM_BLOCK_BITS, off = i - b * MG_WM_BLOCK_BITS;
+	const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(level + (size_t)b * 8));
+	const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(level + (size_t)b * 8 + 4));
+	const uint32_t w[7] = {h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+	uint32_t r = h0.x;
+	const uint32_t wi = off >> 5, bi = off & 31;
+	uint32_t cur = 0;
+#pragma unroll
+	for (int j = 0; j < 7; ++j) {
+		r += j < (int)wi ? __popc(w[j]) : 0;
+		cur = j == (int)wi ? w[j] : cur;
+	}
+	r += __popc(cur & ((1u << bi) - 1u));
+	bit_at_i = (cur >> bi) & 1u;
+	return r;
+}
+
+// stable partition of the keys by the level's bit
+__global__ void __launch_bounds__(256) k_wm_scatter(const uint32_t *__restrict__ keys, int64_t m, const uint32_t *__restrict__ level, uint32_t zeros,
+													 uint32_t *keys_out)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m)
+		return;
+	uint32_t bit;
+	const uint32_t r1 = mg_wm_rank1(level, (uint32_t)i, bit);
+	keys_out[bit ? zeros + r1 : (uint32_t)i - r1] = keys[i];
+}
+
+struct WmState {
+	uint32_t l, r, k;
+};
+
+// advance one order statistic by one level; returns the bit it takes
+__device__ __forceinline__ bool mg_wm_step(const uint32_t *__restrict__ lv, uint32_t zeros, WmState &st)
+{
+	uint32_t bit_l, bit_r;
+	const uint32_t ol = mg_wm_rank1(lv, st.l, bit_l);
+	if (st.r - st.l == 1) { // singleton range: its own bit decides, one rank query is enough
+		st.l = bit_l ? zeros + ol : st.l - ol;
+		st.r = st.l + 1;
+		st.k = 0;
+		return bit_l != 0;
+	}
+	const uint32_t orr = mg_wm_rank1(lv, st.r, bit_r);
+	const uint32_t nz = (st.r - st.l) - (orr - ol);
+	if (st.k < nz) {
+		st.l -= ol;
+		st.r -= orr;
+		return false;
+	}
+	st.k -= nz;
+	st.l = zeros + ol;
+	st.r = zeros + orr;
+	return true;
+}
+
+// k-th smallest key (0-based) among compacted positions [l, r), r > l, k < r - l; with want2 (requires k + 1 < r - l)
+// also the (k+1)-th. The two order statistics share one walk until the level where they part.
+__device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, uint32_t &key1, uint32_t &key2)
+{
+	const uint32_t m = (uint32_t)ch->wm_m;
+	const size_t stride = (size_t)ch->wm_blocks * 8;
+	WmState a{l, r, k}, b{0, 0, 0};
+	bool joint = want2, split = false;
+	uint32_t v1 = 0, v2 = 0;
+	for (int level = 0; level < MG_WM_LEVELS; ++level) {
+		const uint32_t zeros = __ldg(ch->wm_zeros + level);
+		const uint32_t bitmask = 1u << (31 - level);
+		if (zeros == m)
+			continue; // every key has a 0 here: positions and values unchanged
+		if (zeros == 0) {
+			v1 |= bitmask; // every key has a 1 here: Z = 0, positions unchanged
+			v2 |= bitmask;
+			continue;
+		}
+		const uint32_t *lv = ch->wm + (size_t)level * stride;
+		if (joint) { // both statistics still in one range (which therefore holds >= 2 elements)
+			uint32_t bit_l, bit_r;
+			const uint32_t ol = mg_wm_rank1(lv, a.l, bit_l), orr = mg_wm_rank1(lv, a.r, bit_r);
+			const uint32_t nz = (a.r - a.l) - (orr - ol);
+			if (a.k + 1 < nz) {
+				a.l -= ol;
+				a.r -= orr;
+			} else if (a.k >= nz) {
+				a.k -= nz;
+				a.l = zeros + ol;
+				a.r = zeros + orr;
+				v1 |= bitmask;
+				v2 |= bitmask;
+			} else { // k is the last zero, k + 1 the first one: they part here
+				b.l = zeros + ol;
+				b.r = zeros + orr;
+				b.k = 0;
+				v2 |= bitmask;
+				a.l -= ol;
+				a.r -= orr;
+				joint = false;
+				split = true;
+			}
+		} else {
+			if (mg_wm_step(lv, zeros, a))
+				v1 |= bitmask;
+			if (split && mg_wm_step(lv, zeros, b))
+				v2 |= bitmask;
+		}
+	}
+	key1 = v1;
+	key2 = want2 ? v2 : v1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_dense_rowquery: one thread per row, every function from the index structures.
+//   SUM: avg / sum / nearest / size / exists   MM: min / max   Q: quantiles
+template <bool SUM, bool MM, bool Q>
+__global__ void __launch_bounds__(256) k_dense_rowquery(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan();
+	double qv[MG_MAX_Q];
+#pragma unroll
+	for (int k = 0; k < MG_MAX_Q; ++k)
+		qv[k] = mg_nan();
+	if (mg_dense_win(q, q.first + i, w)) {
+		const int64_t nb = w.ebin - w.sbin;
+		long long n = 0;
+		if (nb > 0) {
+			Pref a, b;
+			if (SUM || Q) {
+				a = mg_ld_pref(w.ch->pref + w.sbin);
+				b = mg_ld_pref(w.ch->pref + w.ebin);
+				n = b.cnt - a.cnt;
+			}
+			if (SUM) {
+				double S = b.sum - a.sum;
+				if (nb <= MG_PREFIX_DIRECT_BINS || (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)) {
+					S = 0;
+					for (int64_t t = w.sbin; t < w.ebin; ++t) {
+						const float v = __ldg(w.ch->vals + t);
+						if (!isnan(v))
+							S += (double)v;
+					}
+				}
+				if (n > 0) {
+					avg = mg_f2d(S / (double)n);
+					sum = mg_f2d(S);
+				}
+			}
+			if (MM) {
+				if (q.out[MG_MAX]) {
+					const float v = mg_pyr_query<true>(w.ch, w.sbin, w.ebin);
+					if (v != __int_as_float(0xff800000))
+						mx = (double)v;
+				}
+				if (q.out[MG_MIN]) {
+					const float v = mg_pyr_query<false>(w.ch, w.sbin, w.ebin);
+					if (v != __int_as_float(0x7f800000))
+						mn = (double)v;
+				}
+			}
+			if (Q && n > 0) {
+				for (int k = 0; k < q.nq; ++k) {
+					double pct = q.q_pct[k];
+					pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
+					const double index = __dmul_rn((double)(n - 1), pct);
+					const long long i1 = (long long)floor(index), i2 = (long long)ceil(index);
+					uint32_t k1, k2;
+					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, i2 != i1, k1, k2);
+					qv[k] = mg_interp(mg_fkey_inv(k1), mg_fkey_inv(k2), __dsub_rn(index, (double)i1));
+				}
+			}
+		}
+		size = (double)n;
+		exists = n > 0 ? 1. : 0.;
+	}
+	if (SUM) {
+		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
+		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
+		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
+		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+	}
+	if (MM) {
+		if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
+		if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, mx);
+	}
+	if (Q)
+		for (int k = 0; k < q.nq; ++k)
+			mg_st_stream(q.q_out[k] + i, qv[k]);
+}

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "rows.cuh"
 #include "dense.cuh"
+#include "dense_index.cuh"
 #include "sparse.cuh"
 #include "stats.cuh"
 #include "pwm.cuh"
@@ -70,6 +71,15 @@ extern "C" int mg_sync(mg_ctx *ctx, void *stream)
 {
 	MG_CUDA(ctx, cudaStreamSynchronize(mg_stream(stream)));
 	return 0;
+}
+
+extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
+{
+	if (name && !strcmp(name, "force_sweep")) {
+		ctx->force_sweep = value != 0;
+		return 0;
+	}
+	return mg_fail(ctx, "mg_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
 extern "C" int64_t mg_launch_count(const mg_ctx *ctx) { return ctx->launches; }
@@ -153,6 +163,65 @@ extern "C" int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out)
 	return 0;
 }
 
+// min/max pyramids + wavelet matrix of one staged chromosome (dense_index.cuh)
+static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
+{
+	const int64_t nbins = dc.nbins;
+	// pyramids: level j+1 exists while level j has more than one group of 8
+	{
+		const float *cmax = dc.vals, *cmin = dc.vals;
+		int64_t nchild = nbins;
+		for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
+			const int64_t nparent = mg_div_up(nchild, 8), padded = (nparent + 7) / 8 * 8 + 8;
+			float *pmax = nullptr, *pmin = nullptr;
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmin))
+				return 1;
+			k_pyr_build<<<(unsigned)mg_div_up(padded, 256), 256>>>(cmax, cmin, nchild, pmax, pmin, padded);
+			MG_LAUNCH_CHECK(ctx);
+			dc.pmax[lv] = pmax;
+			dc.pmin[lv] = pmin;
+			cmax = pmax;
+			cmin = pmin;
+			nchild = nparent;
+		}
+	}
+	// wavelet matrix over the non-NaN values
+	long long m = 0;
+	MG_CUDA(ctx, cudaMemcpy(&m, &dc.pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
+	dc.wm_m = m;
+	dc.wm_blocks = m / MG_WM_BLOCK_BITS + 1; // position m itself must be addressable
+	uint32_t *wm = nullptr, *zeros = nullptr;
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * 8 * MG_WM_LEVELS, &wm) || mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros))
+		return 1;
+	dc.wm = wm;
+	dc.wm_zeros = zeros;
+	uint32_t *keys[2] = {nullptr, nullptr};
+	MG_CUDA(ctx, cudaMalloc(&keys[0], sizeof(uint32_t) * (size_t)(m > 0 ? m : 1)));
+	MG_CUDA(ctx, cudaMalloc(&keys[1], sizeof(uint32_t) * (size_t)(m > 0 ? m : 1)));
+	if (nbins) {
+		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, dc.pref, nbins, keys[0]);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	std::vector<uint32_t> h_zeros(MG_WM_LEVELS);
+	for (int lv = 0; lv < MG_WM_LEVELS; ++lv) {
+		uint32_t *level = wm + (size_t)lv * dc.wm_blocks * 8;
+		const uint32_t *src = keys[lv & 1];
+		k_wm_bits<<<(unsigned)mg_div_up(dc.wm_blocks * 7, 256), 256>>>(src, m, 31 - lv, level, dc.wm_blocks);
+		MG_LAUNCH_CHECK(ctx);
+		k_wm_scan<<<1, 1024>>>(level, dc.wm_blocks, m, zeros + lv);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaMemcpy(&h_zeros[lv], zeros + lv, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		if (m) {
+			k_wm_scatter<<<(unsigned)mg_div_up(m, 256), 256>>>(src, m, level, h_zeros[lv], keys[(lv + 1) & 1]);
+			MG_LAUNCH_CHECK(ctx);
+		}
+	}
+	MG_CUDA(ctx, cudaDeviceSynchronize());
+	cudaFree(keys[0]);
+	cudaFree(keys[1]);
+	return 0;
+}
+
 extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float *h_bins, int64_t nbins)
 {
 	MG_REQUIRE(ctx, chromid >= 0 && chromid < t->nchroms, "mg_dense_stage: chromid %d out of range", chromid);
@@ -165,7 +234,7 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
 	float *vals = nullptr;
 	Pref *pref = nullptr;
-	const int64_t padded = (nbins + 3) / 4 * 4 + 4; // float4-safe tail, NaN filled
+	const int64_t padded = (nbins + 7) / 8 * 8 + 8; // group-of-8 / float4-safe tail, NaN filled
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals) || mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref))
 		return 1;
 	MG_CUDA(ctx, cudaMemset(vals, 0xff, sizeof(float) * padded)); // 0xffffffff is a NaN
@@ -184,8 +253,14 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	MG_LAUNCH_CHECK(ctx);
 	k_dense_prefix_write<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, pref);
 	MG_LAUNCH_CHECK(ctx);
-	DenseChrom dc{vals, pref, nbins, 0.};
+	DenseChrom dc;
+	memset(&dc, 0, sizeof(dc));
+	dc.vals = vals;
+	dc.pref = pref;
+	dc.nbins = nbins;
 	MG_CUDA(ctx, cudaMemcpy(&dc.abs_sum, abs_total, sizeof(double), cudaMemcpyDeviceToHost));
+	if (mg_dense_build_index(ctx, t, dc))
+		return 1;
 	t->h_table[chromid] = dc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &dc, sizeof(DenseChrom), cudaMemcpyHostToDevice));
 	cudaFree(tile_sum);
@@ -382,8 +457,22 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 {
 	if (!q.count)
 		return 0;
+	const bool want_sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST] || q.out[MG_SIZE] || q.out[MG_EXISTS];
+	const bool want_mm = q.out[MG_MIN] || q.out[MG_MAX];
 	if (!need_sweep) {
 		k_dense_prefix<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
+	} else if (!q.out[MG_STDDEV] && !ctx->force_sweep) {
+		// everything else comes from the index structures, one thread per row
+		const unsigned grid = (unsigned)mg_div_up(q.count, 256);
+		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0);
+		switch (key) {
+		case 2: k_dense_rowquery<false, true, false><<<grid, 256, 0, st>>>(q); break;
+		case 3: k_dense_rowquery<true, true, false><<<grid, 256, 0, st>>>(q); break;
+		case 4: k_dense_rowquery<false, false, true><<<grid, 256, 0, st>>>(q); break;
+		case 5: k_dense_rowquery<true, false, true><<<grid, 256, 0, st>>>(q); break;
+		case 6: k_dense_rowquery<false, true, true><<<grid, 256, 0, st>>>(q); break;
+		default: k_dense_rowquery<true, true, true><<<grid, 256, 0, st>>>(q); break;
+		}
 	} else {
 		const int64_t blocks_needed = mg_div_up(q.count, MG_SW_WARPS);
 		const int64_t cap = (int64_t)ctx->sm_count * 32; // grid-stride beyond that

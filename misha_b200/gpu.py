@@ -86,6 +86,9 @@ class Context:
     def sync(self, stream=None):
         self._check(self.lib.mg_sync(self.h, c_vp(stream)))
 
+    def set_option(self, name, value):
+        self._check(self.lib.mg_set_option(self.h, name.encode(), c_i64(int(value))))
+
     def launch_count(self):
         return int(self.lib.mg_launch_count(self.h))
 

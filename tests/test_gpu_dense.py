@@ -114,3 +114,22 @@ def test_cancellation_guard(gpu_ctx):
         assert_close(sm, exp["sum"], RTOL, "sum")
     finally:
         ctx2.close()
+
+
+def test_sweep_and_index_paths_agree(gpu_ctx, dense_testdb):
+    """min / max / quantile through the index structures (pyramids, wavelet matrix) == the warp-per-row sweep, bitwise."""
+    rng = np.random.default_rng(21)
+    for cid, (c, size) in enumerate(CHROMS):
+        s = rng.integers(0, size - 1, 4000)  # unsorted on purpose
+        e = np.minimum(s + rng.choice([1, 19, 20, 21, 160, 161, 1000, 9999, 123456], 4000), size)
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        funcs = ["avg", "min", "max", ("quantile", 0.9), ("quantile", 0.5), ("quantile", 0.0), ("quantile", 1.0), ("quantile", 0.3333)]
+        idx = dense_testdb.window(rows, funcs, -300, 700)
+        gpu_ctx.set_option("force_sweep", 1)
+        try:
+            swp = dense_testdb.window(rows, funcs, -300, 700)
+        finally:
+            gpu_ctx.set_option("force_sweep", 0)
+        assert_close(idx[0], swp[0], RTOL, f"{c} avg")
+        for k in range(1, len(funcs)):
+            assert_same(idx[k], swp[k], f"{c} {funcs[k]}")
