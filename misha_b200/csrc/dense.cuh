@@ -24,7 +24,7 @@ struct DenseChrom {
 	// index structures (dense_index.cuh)
 	const float *pmax[MG_PYR_MAX];
 	const float *pmin[MG_PYR_MAX];
-	const uint32_t *wm;       // wavelet matrix, 32 levels x wm_blocks x 8 uint32
+	const uint2 *wm;          // wavelet matrix, 32 levels x wm_blocks units {ones before, 32 bits}
 	const uint32_t *wm_zeros; // zeros per level (32)
 	int64_t wm_blocks;
 	int64_t wm_m;             // number of non-NaN bins

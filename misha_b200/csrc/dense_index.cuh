@@ -6,8 +6,8 @@
 //                                a window decomposes into <= 7 head + <= 7 tail entries per level: 2 sectors per level
 //   wavelet matrix               over the order-preserving uint32 keys of the non-NaN values (compacted in bin order;
 //                                a window maps to [cnt[sbin], cnt[ebin]) through the prefix counts). Level L holds bit
-//                                31-L of every key after the stable partitions of levels 0..L-1, in 32-byte blocks
-//                                {uint32 ones before the block, 7 x uint32 bits} so one sector answers a rank query.
+//                                31-L of every key after the stable partitions of levels 0..L-1, in 8-byte units
+//                                {uint32 ones before the unit, uint32 bits}: a rank query = one 8-byte load + popc.
 //                                k-th smallest of a window = 32 dependent rank pairs (fewer: constant levels are
 //                                skipped and a singleton range needs one rank per level). Exact for any window size.
 #pragma once
@@ -77,7 +77,6 @@ __device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, i
 
 // ------------------------------------------------------------------------------------------------------------------
 // wavelet matrix
-#define MG_WM_BLOCK_BITS 224
 #define MG_WM_LEVELS 32
 
 // compact the non-NaN values' keys in bin order: keys[cnt[i]] = fkey(vals[i])
@@ -91,13 +90,14 @@ __global__ void __launch_bounds__(256) k_wm_compact(const float *__restrict__ va
 		keys[pref[i].cnt] = mg_fkey(v);
 }
 
-// one thread per 32 positions: the level's bit words + per-block popcounts. blocks[b] = {ones (later: ones before), 7 words}
-__global__ void __launch_bounds__(256) k_wm_bits(const uint32_t *__restrict__ keys, int64_t m, int shift, uint32_t *blocks, int64_t nblocks)
+// A level is an array of 8-byte units {uint32 ones before the unit, uint32 bits of 32 positions}: a rank query is one
+// 8-byte load, a shift and a popcount. One thread per unit builds the bit word.
+__global__ void __launch_bounds__(256) k_wm_bits(const uint32_t *__restrict__ keys, int64_t m, int shift, uint2 *units, int64_t nunits)
 {
-	const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // word index, 7 words per block
-	if (w >= nblocks * 7)
+	const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= nunits)
 		return;
-	const int64_t p0 = w * 32;
+	const int64_t p0 = u * 32;
 	uint32_t bits = 0;
 #pragma unroll 8
 	for (int j = 0; j < 32; ++j) {
@@ -105,54 +105,40 @@ __global__ void __launch_bounds__(256) k_wm_bits(const uint32_t *__restrict__ ke
 		if (p < m)
 			bits |= ((keys[p] >> shift) & 1u) << j;
 	}
-	const int64_t b = w / 7;
-	blocks[b * 8 + 1 + (w - b * 7)] = bits;
+	units[u] = make_uint2(0u, bits);
 }
 
-// one block: per-block popcounts -> exclusive "ones before" headers; zeros[level] = m - total ones
-__global__ void __launch_bounds__(1024) k_wm_scan(uint32_t *blocks, int64_t nblocks, int64_t m, uint32_t *zeros_out)
+// one block: exclusive scan of the units' popcounts into their headers; zeros[level] = m - total ones
+__global__ void __launch_bounds__(1024) k_wm_scan(uint2 *units, int64_t nunits, int64_t m, uint32_t *zeros_out)
 {
 	__shared__ long long sc[33];
-	const int64_t chunk = (nblocks + blockDim.x - 1) / blockDim.x;
-	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, nblocks);
+	const int64_t chunk = (nunits + blockDim.x - 1) / blockDim.x;
+	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, nunits);
 	long long s = 0;
-	for (int64_t b = lo; b < hi; ++b) {
-		const uint32_t *w = blocks + b * 8;
-		s += __popc(w[1]) + __popc(w[2]) + __popc(w[3]) + __popc(w[4]) + __popc(w[5]) + __popc(w[6]) + __popc(w[7]);
-	}
+	for (int64_t u = lo; u < hi; ++u)
+		s += __popc(units[u].y);
 	long long total;
 	long long s0 = mg_block_excl_scan<long long>(s, sc, total);
-	for (int64_t b = lo; b < hi; ++b) {
-		uint32_t *w = blocks + b * 8;
-		w[0] = (uint32_t)s0;
-		s0 += __popc(w[1]) + __popc(w[2]) + __popc(w[3]) + __popc(w[4]) + __popc(w[5]) + __popc(w[6]) + __popc(w[7]);
+	for (int64_t u = lo; u < hi; ++u) {
+		const uint32_t bits = units[u].y;
+		units[u].x = (uint32_t)s0;
+		s0 += __popc(bits);
 	}
 	if (threadIdx.x == 0)
 		*zeros_out = (uint32_t)(m - total);
 }
 
-// ones among positions [0, i) of a level
-__device__ __forceinline__ uint32_t mg_wm_rank1(const uint32_t *__restrict__ level, uint32_t i, uint32_t &bit_at_i)
+// ones among positions [0, i) of a level; also the bit AT position i
+__device__ __forceinline__ uint32_t mg_wm_rank1(const uint2 *__restrict__ level, uint32_t i, uint32_t &bit_at_i)
 {
-	const uint32_t b = i / MG_WM_BLOCK_BITS, off = i - b * MG_WM_BLOCK_BITS;
-	const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(level + (size_t)b * 8));
-	const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(level + (size_t)b * 8 + 4));
-	const uint32_t w[7] = {h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-	uint32_t r = h0.x;
-	const uint32_t wi = off >> 5, bi = off & 31;
-	uint32_t cur = 0;
-#pragma unroll
-	for (int j = 0; j < 7; ++j) {
-		r += j < (int)wi ? __popc(w[j]) : 0;
-		cur = j == (int)wi ? w[j] : cur;
-	}
-	r += __popc(cur & ((1u << bi) - 1u));
-	bit_at_i = (cur >> bi) & 1u;
-	return r;
+	const uint2 u = __ldg(level + (i >> 5));
+	const uint32_t bi = i & 31u;
+	bit_at_i = (u.y >> bi) & 1u;
+	return u.x + __popc(u.y & ((1u << bi) - 1u));
 }
 
 // stable partition of the keys by the level's bit
-__global__ void __launch_bounds__(256) k_wm_scatter(const uint32_t *__restrict__ keys, int64_t m, const uint32_t *__restrict__ level, uint32_t zeros,
+__global__ void __launch_bounds__(256) k_wm_scatter(const uint32_t *__restrict__ keys, int64_t m, const uint2 *__restrict__ level, uint32_t zeros,
 													 uint32_t *keys_out)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,7 +154,7 @@ struct WmState {
 };
 
 // advance one order statistic by one level; returns the bit it takes
-__device__ __forceinline__ bool mg_wm_step(const uint32_t *__restrict__ lv, uint32_t zeros, WmState &st)
+__device__ __forceinline__ bool mg_wm_step(const uint2 *__restrict__ lv, uint32_t zeros, WmState &st)
 {
 	uint32_t bit_l, bit_r;
 	const uint32_t ol = mg_wm_rank1(lv, st.l, bit_l);
@@ -196,7 +182,7 @@ __device__ __forceinline__ bool mg_wm_step(const uint32_t *__restrict__ lv, uint
 __device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, uint32_t &key1, uint32_t &key2)
 {
 	const uint32_t m = (uint32_t)ch->wm_m;
-	const size_t stride = (size_t)ch->wm_blocks * 8;
+	const size_t stride = (size_t)ch->wm_blocks;
 	WmState a{l, r, k}, b{0, 0, 0};
 	bool joint = want2, split = false;
 	uint32_t v1 = 0, v2 = 0;
@@ -210,7 +196,7 @@ __device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, u
 			v2 |= bitmask;
 			continue;
 		}
-		const uint32_t *lv = ch->wm + (size_t)level * stride;
+		const uint2 *lv = ch->wm + (size_t)level * stride;
 		if (joint) { // both statistics still in one range (which therefore holds >= 2 elements)
 			uint32_t bit_l, bit_r;
 			const uint32_t ol = mg_wm_rank1(lv, a.l, bit_l), orr = mg_wm_rank1(lv, a.r, bit_r);

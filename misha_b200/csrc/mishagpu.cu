@@ -189,9 +189,10 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 	long long m = 0;
 	MG_CUDA(ctx, cudaMemcpy(&m, &dc.pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
 	dc.wm_m = m;
-	dc.wm_blocks = m / MG_WM_BLOCK_BITS + 1; // position m itself must be addressable
-	uint32_t *wm = nullptr, *zeros = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * 8 * MG_WM_LEVELS, &wm) || mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros))
+	dc.wm_blocks = m / 32 + 1; // position m itself must be addressable
+	uint2 *wm = nullptr;
+	uint32_t *zeros = nullptr;
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * MG_WM_LEVELS, &wm) || mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros))
 		return 1;
 	dc.wm = wm;
 	dc.wm_zeros = zeros;
@@ -204,9 +205,9 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 	}
 	std::vector<uint32_t> h_zeros(MG_WM_LEVELS);
 	for (int lv = 0; lv < MG_WM_LEVELS; ++lv) {
-		uint32_t *level = wm + (size_t)lv * dc.wm_blocks * 8;
+		uint2 *level = wm + (size_t)lv * dc.wm_blocks;
 		const uint32_t *src = keys[lv & 1];
-		k_wm_bits<<<(unsigned)mg_div_up(dc.wm_blocks * 7, 256), 256>>>(src, m, 31 - lv, level, dc.wm_blocks);
+		k_wm_bits<<<(unsigned)mg_div_up(dc.wm_blocks, 256), 256>>>(src, m, 31 - lv, level, dc.wm_blocks);
 		MG_LAUNCH_CHECK(ctx);
 		k_wm_scan<<<1, 1024>>>(level, dc.wm_blocks, m, zeros + lv);
 		MG_LAUNCH_CHECK(ctx);
