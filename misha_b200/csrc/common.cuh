@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <algorithm>
+#include <limits>
 
 #include "../../include/mishagpu.h"
 

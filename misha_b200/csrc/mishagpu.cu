@@ -363,6 +363,10 @@ extern "C" int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, co
 	r->src.send = (const int64_t *)(base + ns * 8);
 	r->src.srow0 = (const int64_t *)(base + ns * 16);
 	r->src.schrom = (const int32_t *)(base + ns * 16 + (ns + 1) * 8);
+	r->h_schrom.assign(h_chrom, h_chrom + nscope);
+	r->h_sstart.assign(h_start, h_start + nscope);
+	r->h_send.assign(h_end, h_end + nscope);
+	r->h_srow0 = row0;
 	if (nscope) {
 		if ((e = cudaMemcpy((void *)r->src.sstart, h_start, (size_t)nscope * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
 			(e = cudaMemcpy((void *)r->src.send, h_end, (size_t)nscope * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -894,7 +898,7 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 	}
 	if (!count)
 		return 0;
-	k_sparse_window<<<(unsigned)mg_div_up(count, 256), 256, 0, mg_stream(stream)>>>(q);
+	k_sparse_window<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
 }
@@ -915,7 +919,7 @@ extern "C" int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, 
 	q.table = s->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.out = d_out;
-	k_coverage<<<(unsigned)mg_div_up(count, 256), 256, 0, mg_stream(stream)>>>(q);
+	k_coverage<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
 }
@@ -1082,6 +1086,38 @@ static bool mg_is_stream_case(const mg_dense *t, const mg_rows *rows, int64_t ss
 		   (func == MG_AVG || func == MG_NEAREST || func == MG_SUM || func == MG_MIN || func == MG_MAX);
 }
 
+// Stream case over few scope intervals: contiguous bin segments of rows [first, first + count)
+struct StreamSeg {
+	const float *p;
+	int64_t n;
+};
+#define MG_MAX_STREAM_SEGS 64
+static bool mg_stream_segments(const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, std::vector<StreamSeg> &segs)
+{
+	segs.clear();
+	const int64_t last = first + count;
+	const size_t ns = rows->h_schrom.size();
+	// first scope interval that holds row `first`
+	size_t k = std::upper_bound(rows->h_srow0.begin(), rows->h_srow0.end(), first) - rows->h_srow0.begin();
+	k = k ? k - 1 : 0;
+	for (; k < ns && rows->h_srow0[k] < last; ++k) {
+		const int64_t r0 = std::max(first, rows->h_srow0[k]), r1 = std::min(last, rows->h_srow0[k + 1]);
+		if (r1 <= r0)
+			continue;
+		const DenseChrom &ch = t->h_table[rows->h_schrom[k]];
+		if (!ch.vals)
+			return false;
+		const int64_t b0 = rows->h_sstart[k] / rows->src.binsize + (r0 - rows->h_srow0[k]);
+		int64_t n = r1 - r0;
+		if (b0 + n > ch.nbins) // rows past the last stored bin read as NaN in the generic path: keep that path
+			return false;
+		segs.push_back(StreamSeg{ch.vals + b0, n});
+		if (segs.size() > MG_MAX_STREAM_SEGS)
+			return false;
+	}
+	return true;
+}
+
 extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift,
 								int64_t eshift, int func, double param, double *d_partial, void *stream)
 {
@@ -1089,6 +1125,30 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 	if (!count)
 		return 0;
 	cudaStream_t st = mg_stream(stream);
+	std::vector<StreamSeg> segs;
+	if (mg_is_stream_case(t, rows, sshift, eshift, func) && mg_stream_segments(t, rows, first, count, segs)) {
+		// one pure-streaming launch per contiguous segment, partials side by side, one final reduction
+		std::vector<int> nbs(segs.size());
+		int total_blocks = 0;
+		for (size_t i = 0; i < segs.size(); ++i) {
+			int64_t b = mg_div_up(segs[i].n, (int64_t)MG_SUM_THREADS * 16);
+			const int64_t cap = (int64_t)ctx->sm_count * 8;
+			nbs[i] = (int)std::max<int64_t>(1, std::min(b, cap));
+			total_blocks += nbs[i];
+		}
+		Moments *scratch = nullptr;
+		MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * total_blocks, st));
+		int off = 0;
+		for (size_t i = 0; i < segs.size(); ++i) {
+			k_seg_summary<<<nbs[i], MG_SUM_THREADS, 0, st>>>(segs[i].p, segs[i].n, scratch + off);
+			MG_LAUNCH_CHECK(ctx);
+			off += nbs[i];
+		}
+		k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, total_blocks, d_partial);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaFreeAsync(scratch, st));
+		return 0;
+	}
 	if (mg_is_stream_case(t, rows, sshift, eshift, func) || mg_is_prefix_func(func)) {
 		const int nb = mg_summary_blocks(ctx, count);
 		Moments *scratch = nullptr;
@@ -1175,6 +1235,66 @@ static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, cons
 	return 0;
 }
 
+// BinFinder::val2bin on the host (src/BinFinder.h:55-81), extended monotonically: -1 below the first break, nbins above the last
+static int mg_host_bin_monotone(const double *br, int nbreaks, double binsize, int include_lowest, double val)
+{
+	const int numbins = nbreaks - 1;
+	if (include_lowest && val == br[0])
+		return 0;
+	if (val <= br[0])
+		return -1;
+	if (val > br[nbreaks - 1])
+		return numbins;
+	if (binsize != 0.) {
+		const int b = (int)ceil((val - br[0]) / binsize) - 1;
+		return b < numbins - 1 ? b : numbins - 1;
+	}
+	unsigned s = 0, e = (unsigned)numbins;
+	while (e - s > 1) {
+		const unsigned mid = (s + e) / 2;
+		if (val <= br[mid])
+			e = mid;
+		else
+			s = mid;
+	}
+	return (int)s;
+}
+
+static inline uint32_t mg_host_fkey(float v)
+{
+	uint32_t b;
+	memcpy(&b, &v, 4);
+	return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+static inline float mg_host_fkey_inv(uint32_t k)
+{
+	const uint32_t b = k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu);
+	float v;
+	memcpy(&v, &b, 4);
+	return v;
+}
+
+// thr[j], j = 0..nb: the largest float whose (monotone) bin is < j. Exact: bisection over the float order with the
+// double formula the reference uses.
+static void mg_float_thresholds(const double *br, int nbreaks, double binsize, int include_lowest, std::vector<float> &thr)
+{
+	const int nb = nbreaks - 1;
+	thr.resize(nb + 1);
+	const uint32_t kmin = mg_host_fkey(-INFINITY), kmax = mg_host_fkey(INFINITY);
+	for (int j = 0; j <= nb; ++j) {
+		// smallest key in [kmin, kmax] whose bin >= j (kmax + 1 if none)
+		uint64_t lo = kmin, hi = (uint64_t)kmax + 1;
+		while (lo < hi) {
+			const uint64_t mid = (lo + hi) >> 1;
+			if (mg_host_bin_monotone(br, nbreaks, binsize, include_lowest, (double)mg_host_fkey_inv((uint32_t)mid)) >= j)
+				hi = mid;
+			else
+				lo = mid + 1;
+		}
+		thr[j] = lo > kmax ? INFINITY : (lo == kmin ? -INFINITY : mg_host_fkey_inv((uint32_t)lo - 1));
+	}
+}
+
 static size_t mg_hist_private_smem(const HistSpec &hs)
 {
 	const int nb = hs.nbreaks[0] - 1;
@@ -1236,6 +1356,28 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 	double *d_breaks = nullptr;
 	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
 		return 1;
+	std::vector<StreamSeg> segs;
+	if (count > 0 && stream_case && nbreaks - 1 <= MG_HIST_PRIVATE_MAX && mg_stream_segments(t, rows, first, count, segs)) {
+		// pure streaming per contiguous segment with exact float thresholds
+		const int nb = nbreaks - 1;
+		std::vector<float> thr;
+		mg_float_thresholds(h_breaks, nbreaks, hs.binsize[0], include_lowest, thr);
+		float *d_thr = nullptr;
+		MG_CUDA(ctx, cudaMallocAsync(&d_thr, sizeof(float) * thr.size(), st));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaStreamSynchronize(st));
+		const size_t smem = ((size_t)((nb + 1 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
+		MG_CUDA(ctx, cudaFuncSetAttribute(k_seg_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		for (const StreamSeg &sg : segs) {
+			int64_t b = mg_div_up(sg.n, (int64_t)MG_HIST_THREADS * 64);
+			const int64_t cap = (int64_t)ctx->sm_count * 2;
+			k_seg_hist<<<(unsigned)std::max<int64_t>(1, std::min(b, cap)), MG_HIST_THREADS, smem, st>>>(sg.p, sg.n, d_thr, nb, (unsigned long long *)d_counts);
+			MG_LAUNCH_CHECK(ctx);
+		}
+		MG_CUDA(ctx, cudaFreeAsync(d_thr, st));
+		MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+		return 0;
+	}
 	if (count > 0) {
 		const bool priv = nbreaks - 1 <= MG_HIST_PRIVATE_MAX;
 		DenseQuery q;

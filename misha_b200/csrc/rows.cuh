@@ -27,6 +27,9 @@ struct mg_rows {
 	RowSrc src{};
 	bool owns = false;
 	void *d_block = nullptr; // one allocation backing every owned array
+	// host copy of a fixed-bin scope (few entries): lets the host split a scan into contiguous per-chromosome segments
+	std::vector<int32_t> h_schrom;
+	std::vector<int64_t> h_sstart, h_send, h_srow0;
 };
 
 // scope interval of implicit row r: last k with srow0[k] <= r
@@ -43,21 +46,52 @@ __device__ __forceinline__ int64_t mg_scope_of_row(const RowSrc &rs, int64_t r)
 	return lo;
 }
 
-__device__ __forceinline__ void mg_get_row(const RowSrc &rs, int64_t r, int &chrom, int64_t &s, int64_t &e, int64_t &scope)
+// floor(a / b) for a >= 0, b > 0 with a 32-bit fast path (a 64-bit division is ~100 instructions on the GPU)
+__device__ __forceinline__ int64_t mg_div_pos(int64_t a, int64_t b)
+{
+	if (((uint64_t)a | (uint64_t)b) <= 0xffffffffull)
+		return (int64_t)((uint32_t)a / (uint32_t)b);
+	return a / b;
+}
+
+// scope interval cache of a thread that walks several implicit rows: the search and the division are paid once per
+// scope interval, not once per row
+struct RowCache {
+	int64_t k = -1, row0 = 0, row1 = 0, bin_base = 0, sstart = 0, send = 0;
+	int chrom = 0;
+};
+
+__device__ __forceinline__ void mg_rowcache_load(const RowSrc &rs, int64_t r, RowCache &c)
+{
+	c.k = mg_scope_of_row(rs, r);
+	c.row0 = __ldg(rs.srow0 + c.k);
+	c.row1 = __ldg(rs.srow0 + c.k + 1);
+	c.sstart = __ldg(rs.sstart + c.k);
+	c.send = __ldg(rs.send + c.k);
+	c.chrom = __ldg(rs.schrom + c.k);
+	c.bin_base = mg_div_pos(c.sstart, rs.binsize) - c.row0;
+}
+
+__device__ __forceinline__ void mg_get_row_cached(const RowSrc &rs, int64_t r, RowCache &c, int &chrom, int64_t &s, int64_t &e, int64_t &scope)
 {
 	if (rs.kind == 0) {
 		chrom = __ldg(rs.chrom + r);
 		s = __ldg(rs.start + r);
 		e = __ldg(rs.end + r);
 		scope = rs.scope_idx ? __ldg(rs.scope_idx + r) : -1;
-	} else {
-		int64_t k = mg_scope_of_row(rs, r);
-		int64_t ss = __ldg(rs.sstart + k), se = __ldg(rs.send + k);
-		int64_t bin = ss / rs.binsize + (r - __ldg(rs.srow0 + k));
-		int64_t coord = bin * rs.binsize;
-		chrom = __ldg(rs.schrom + k);
-		s = coord > ss ? coord : ss;
-		e = coord + rs.binsize < se ? coord + rs.binsize : se;
-		scope = k;
+		return;
 	}
+	if (c.k < 0 || r < c.row0 || r >= c.row1)
+		mg_rowcache_load(rs, r, c);
+	const int64_t coord = (c.bin_base + r) * rs.binsize;
+	chrom = c.chrom;
+	s = coord > c.sstart ? coord : c.sstart;
+	e = coord + rs.binsize < c.send ? coord + rs.binsize : c.send;
+	scope = c.k;
+}
+
+__device__ __forceinline__ void mg_get_row(const RowSrc &rs, int64_t r, int &chrom, int64_t &s, int64_t &e, int64_t &scope)
+{
+	RowCache c;
+	mg_get_row_cached(rs, r, c, chrom, s, e, scope);
 }

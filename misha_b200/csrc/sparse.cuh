@@ -63,7 +63,7 @@ __device__ float mg_thread_radix_select(const float *val, int64_t r0, int64_t r1
 		for (int b = 0; b < 16; ++b)
 			hist[b] = 0;
 		for (int64_t r = r0; r < r1; ++r) {
-			const float v = __ldg(val + r);
+			const float v = val[r];
 			if (!isnan(v)) {
 				const uint32_t key = mg_fkey(v);
 				if ((key & mask) == prefix)
@@ -86,50 +86,176 @@ __device__ float mg_thread_radix_select(const float *val, int64_t r0, int64_t r1
 	return mg_fkey_inv(prefix);
 }
 
-// One thread per row. read_interval: src/GenomeTrackSparse.cpp:237-340; calc_vals: src/GenomeTrackSparse.h:143-259.
-// Sums and Welford updates run in record order, exactly the reference's order => avg / sum / stddev are bit-exact.
-__global__ void __launch_bounds__(256) k_sparse_window(const SparseQuery q)
-{
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= q.count)
-		return;
+// ------------------------------------------------------------------------------------------------------------------
+// Block-level narrowing. The rows of a block are (nearly always) neighbours on one chromosome, so the records any of
+// them can touch form one short contiguous range: two binary searches per BLOCK find it, the range is staged in shared
+// memory with coalesced loads, and each thread then searches ~log2(range) shared-memory entries instead of
+// ~log2(n) dependent global loads. Exactness: for a row window [ws, we) inside the block hull [WS, WE), the first record
+// with end > ws and the last one with start < we both lie in [lo, hi] where lo = first record with end > WS and
+// hi = first record with start >= WE; one extra record on each side keeps the nearest-neighbour cases local.
+#define MG_SP_THREADS 256
+#define MG_SP_ROWS 8   // rows per thread: one block narrows for 2048 rows
+#define MG_SP_CAP 1024 // records staged per block (20 KB)
+
+struct SpLocal {
+	const int64_t *start;
+	const int64_t *end;
+	const float *val;
+	int64_t n;
+};
+
+struct SpSmem {
+	int64_t start[MG_SP_CAP];
+	int64_t end[MG_SP_CAP];
+	float val[MG_SP_CAP];
+	int64_t red_min[MG_SP_THREADS / 32], red_max[MG_SP_THREADS / 32];
+	int red_chrom_lo[MG_SP_THREADS / 32], red_chrom_hi[MG_SP_THREADS / 32];
+	int64_t hull_min, hull_max;
+	int64_t s_lo[2], s_hi[2]; // the two cooperative searches
+	int s_first[2];
+	int64_t lo, n;
 	int chrom;
-	int64_t s, e, scope;
-	mg_get_row(q.rows, q.first + i, chrom, s, e, scope);
-	int64_t ws, we;
+	int mode; // 0 = per-thread global search over the whole chromosome, 1 = staged in smem, 2 = narrowed global range
+};
+
+// Two 128-ary searches run side by side by the 256 threads of a block: half 0 finds the first record with end > WS,
+// half 1 the first record with start >= WE (both predicates are monotone over the sorted, disjoint records).
+// Each round is ONE global load per thread, so a block resolves n = 10^6 records in 3 rounds.
+__device__ __forceinline__ void mg_sp_block_search(SpSmem &sm, const SparseChrom &ch)
+{
+	const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
+	if (t == 0) {
+		sm.s_lo[half] = 0;
+		sm.s_hi[half] = ch.n;
+	}
+	__syncthreads();
+	for (;;) {
+		const int64_t lo = sm.s_lo[half], hi = sm.s_hi[half];
+		const int64_t span0 = sm.s_hi[0] - sm.s_lo[0], span1 = sm.s_hi[1] - sm.s_lo[1];
+		const bool last_round = span0 <= 128 && span1 <= 128;
+		const int64_t span = hi - lo;
+		const int64_t step = span <= 128 ? 1 : (span + 127) / 128;
+		const int64_t p = lo + (int64_t)(t + 1) * step - 1; // probe; the answer is the first index whose predicate holds
+		bool pred = true; // a probe at or past hi is past the answer by definition (the answer is <= hi)
+		if (p < hi)
+			pred = half == 0 ? (__ldg(ch.end + p) > sm.hull_min) : (__ldg(ch.start + p) >= sm.hull_max);
+		if (t == 0)
+			sm.s_first[half] = 128;
+		__syncthreads();
+		if (pred)
+			atomicMin(&sm.s_first[half], t);
+		__syncthreads();
+		const int T = sm.s_first[half];
+		__syncthreads();
+		if (t == 0) {
+			// probes t < T are false, probe T (if any) is true: answer in (p_{T-1}, p_T]
+			const int64_t nlo = T > 0 ? min(hi, lo + (int64_t)T * step) : lo;
+			const int64_t nhi = T < 128 ? min(hi, lo + (int64_t)(T + 1) * step - 1) : hi;
+			sm.s_lo[half] = step == 1 ? nhi : nlo; // with step == 1 the first true probe IS the answer
+			sm.s_hi[half] = nhi;
+		}
+		__syncthreads();
+		if (last_round)
+			break;
+	}
+}
+
+// Computes the block's record view. `ok/chrom/ws/we` describe up to MG_SP_ROWS rows of this thread.
+// (mn, mx, clo, chi) = this thread's hull over its valid rows (INT64_MAX / INT64_MIN / INT_MAX / INT_MIN when none)
+__device__ __forceinline__ SpLocal mg_sp_narrow(SpSmem &sm, const SparseChrom *table, int64_t mn, int64_t mx, int clo, int chi, bool want_val,
+												int &mode_out)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 16; k > 0; k >>= 1) {
+		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, k));
+		mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+		clo = min(clo, __shfl_xor_sync(0xffffffffu, clo, k));
+		chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, k));
+	}
+	if (lane == 0) {
+		sm.red_min[warp] = mn;
+		sm.red_max[warp] = mx;
+		sm.red_chrom_lo[warp] = clo;
+		sm.red_chrom_hi[warp] = chi;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < MG_SP_THREADS / 32; ++w) {
+			mn = min(mn, sm.red_min[w]);
+			mx = max(mx, sm.red_max[w]);
+			clo = min(clo, sm.red_chrom_lo[w]);
+			chi = max(chi, sm.red_chrom_hi[w]);
+		}
+		sm.hull_min = mn;
+		sm.hull_max = mx;
+		sm.chrom = clo == INT_MAX ? 0 : clo;
+		sm.mode = (clo == chi && clo != INT_MAX) ? 1 : 0; // one chromosome for every valid row of the block?
+	}
+	__syncthreads();
+	if (sm.mode == 0) {
+		mode_out = 0;
+		return SpLocal{nullptr, nullptr, nullptr, 0};
+	}
+	const SparseChrom ch = table[sm.chrom];
+	mg_sp_block_search(sm, ch);
+	if (threadIdx.x == 0) {
+		const int64_t lo = sm.s_lo[0], l2 = sm.s_lo[1];
+		const int64_t a = lo > 0 ? lo - 1 : 0, b = l2 < ch.n ? l2 + 1 : ch.n; // one neighbour on each side
+		sm.lo = a;
+		sm.n = b > a ? b - a : 0;
+		sm.mode = sm.n <= MG_SP_CAP ? 1 : 2;
+	}
+	__syncthreads();
+	mode_out = sm.mode;
+	if (sm.mode == 2) // range too long for shared memory: search the narrowed global range
+		return SpLocal{ch.start + sm.lo, ch.end + sm.lo, ch.val ? ch.val + sm.lo : nullptr, sm.n};
+	for (int64_t t = threadIdx.x; t < sm.n; t += MG_SP_THREADS) { // stage [lo, lo + n) (coalesced)
+		sm.start[t] = __ldg(ch.start + sm.lo + t);
+		sm.end[t] = __ldg(ch.end + sm.lo + t);
+		if (want_val)
+			sm.val[t] = __ldg(ch.val + sm.lo + t);
+	}
+	__syncthreads();
+	return SpLocal{sm.start, sm.end, sm.val, sm.n};
+}
+
+// Per-row arithmetic. read_interval: src/GenomeTrackSparse.cpp:237-340; calc_vals: src/GenomeTrackSparse.h:143-259.
+// Sums and Welford updates run in record order, exactly the reference's order => avg / sum / stddev are bit-exact.
+__device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLocal &ch, bool ok, int64_t ws, int64_t we, int64_t i)
+{
 	double avg = mg_nan(), sum = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan(), nearest = mg_nan(), size = mg_nan(),
 		   exists = mg_nan();
 	double qv[MG_MAX_Q];
 #pragma unroll
 	for (int k = 0; k < MG_MAX_Q; ++k)
 		qv[k] = mg_nan();
-	if (mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we)) {
-		const SparseChrom ch = q.table[chrom];
+	if (ok) {
 		size = 0;
 		exists = 0;
 		if (ch.n > 0) {
-			if (__ldg(ch.start) >= we)
-				nearest = (double)__ldg(ch.val); // before the first record (:281-284)
-			else if (__ldg(ch.end + ch.n - 1) <= ws)
-				nearest = (double)__ldg(ch.val + ch.n - 1); // after the last record (:286-289)
+			if (ch.start[0] >= we)
+				nearest = (double)ch.val[0]; // before the first record (:281-284)
+			else if (ch.end[ch.n - 1] <= ws)
+				nearest = (double)ch.val[ch.n - 1]; // after the last record (:286-289)
 			else {
 				// first record whose end > ws (ends are sorted because records are disjoint)
 				int64_t lo = 0, hi = ch.n;
 				while (lo < hi) {
 					const int64_t mid = lo + ((hi - lo) >> 1);
-					if (__ldg(ch.end + mid) > ws)
+					if (ch.end[mid] > ws)
 						hi = mid;
 					else
 						lo = mid + 1;
 				}
 				const int64_t first = lo;
-				if (__ldg(ch.start + first) < we) {
+				if (ch.start[first] < we) {
 					long long n = 0;
 					double S = 0, mean = 0, m2 = 0;
 					float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
 					int64_t r = first;
-					for (; r < ch.n && __ldg(ch.start + r) < we; ++r) {
-						const float v = __ldg(ch.val + r);
+					for (; r < ch.n && ch.start[r] < we; ++r) {
+						const float v = ch.val[r];
 						if (isnan(v))
 							continue;
 						S += (double)v;
@@ -162,9 +288,9 @@ __global__ void __launch_bounds__(256) k_sparse_window(const SparseQuery q)
 				} else {
 					// no overlap: closer neighbour, ties to the earlier record (:336-338)
 					const int64_t prv = first - 1;
-					const int64_t dp = mg_dist(ws, we, __ldg(ch.start + prv), __ldg(ch.end + prv));
-					const int64_t dn = mg_dist(ws, we, __ldg(ch.start + first), __ldg(ch.end + first));
-					nearest = (double)__ldg(ch.val + (dp <= dn ? prv : first));
+					const int64_t dp = mg_dist(ws, we, ch.start[prv], ch.end[prv]);
+					const int64_t dn = mg_dist(ws, we, ch.start[first], ch.end[first]);
+					nearest = (double)ch.val[dp <= dn ? prv : first];
 				}
 			}
 		}
@@ -181,6 +307,64 @@ __global__ void __launch_bounds__(256) k_sparse_window(const SparseQuery q)
 		mg_st_stream(q.q_out[k] + i, qv[k]);
 }
 
+template <typename Q>
+__device__ __forceinline__ bool mg_sp_row_window(const Q &q, int64_t i, RowCache &rc, int &chrom, int64_t &ws, int64_t &we)
+{
+	int64_t s, e, scope;
+	mg_get_row_cached(q.rows, q.first + i, rc, chrom, s, e, scope);
+	return mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we);
+}
+
+template <typename Q>
+__device__ __forceinline__ void mg_sp_thread_hull(const Q &q, int64_t base, int64_t &mn, int64_t &mx, int &clo, int &chi)
+{
+	mn = INT64_MAX;
+	mx = INT64_MIN;
+	clo = INT_MAX;
+	chi = INT_MIN;
+	RowCache rc;
+#pragma unroll
+	for (int j = 0; j < MG_SP_ROWS; ++j) {
+		const int64_t i = base + (int64_t)j * MG_SP_THREADS;
+		if (i < q.count) {
+			int chrom;
+			int64_t ws, we;
+			if (mg_sp_row_window(q, i, rc, chrom, ws, we)) {
+				mn = min(mn, ws);
+				mx = max(mx, we);
+				clo = min(clo, chrom);
+				chi = max(chi, chrom);
+			}
+		}
+	}
+}
+
+// A block handles MG_SP_THREADS x MG_SP_ROWS consecutive rows; thread t takes rows base + j * MG_SP_THREADS + t (coalesced).
+__global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_window(const SparseQuery q)
+{
+	__shared__ SpSmem sm;
+	const int64_t base = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SP_ROWS) + threadIdx.x;
+	int64_t mn, mx;
+	int clo, chi, mode;
+	mg_sp_thread_hull(q, base, mn, mx, clo, chi);
+	const SpLocal blk = mg_sp_narrow(sm, q.table, mn, mx, clo, chi, true, mode);
+	RowCache rc;
+	for (int j = 0; j < MG_SP_ROWS; ++j) {
+		const int64_t i = base + (int64_t)j * MG_SP_THREADS;
+		if (i >= q.count)
+			break;
+		int chrom;
+		int64_t ws, we;
+		const bool ok = mg_sp_row_window(q, i, rc, chrom, ws, we);
+		SpLocal ch = blk;
+		if (mode == 0 && ok) {
+			const SparseChrom c = q.table[chrom];
+			ch = SpLocal{c.start, c.end, c.val, c.n};
+		}
+		mg_sparse_row(q, ch, ok, ws, we, i);
+	}
+}
+
 // coverage = sum of overlaps with the unified source intervals / window length. src/IntervVarProcessor.cpp:242-325.
 struct CoverageQuery {
 	RowSrc rows;
@@ -191,36 +375,48 @@ struct CoverageQuery {
 	double *out;
 };
 
-__global__ void __launch_bounds__(256) k_coverage(const CoverageQuery q)
+__global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery q)
 {
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= q.count)
-		return;
-	int chrom;
-	int64_t s, e, scope;
-	mg_get_row(q.rows, q.first + i, chrom, s, e, scope);
-	int64_t ws, we;
-	double cov = mg_nan();
-	if (mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we)) {
-		const SparseChrom ch = q.table[chrom];
-		// first source interval with end > ws (== lower_bound by start, minus one when the previous one still overlaps)
-		int64_t lo = 0, hi = ch.n;
-		while (lo < hi) {
-			const int64_t mid = lo + ((hi - lo) >> 1);
-			if (__ldg(ch.end + mid) > ws)
-				hi = mid;
-			else
-				lo = mid + 1;
+	__shared__ SpSmem sm;
+	const int64_t base = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SP_ROWS) + threadIdx.x;
+	int64_t mn, mx;
+	int clo, chi, mode;
+	mg_sp_thread_hull(q, base, mn, mx, clo, chi);
+	const SpLocal blk = mg_sp_narrow(sm, q.table, mn, mx, clo, chi, false, mode);
+	RowCache rc;
+	for (int j = 0; j < MG_SP_ROWS; ++j) {
+		const int64_t i = base + (int64_t)j * MG_SP_THREADS;
+		if (i >= q.count)
+			break;
+		int chrom;
+		int64_t ws, we;
+		const bool ok = mg_sp_row_window(q, i, rc, chrom, ws, we);
+		SpLocal ch = blk;
+		if (mode == 0 && ok) {
+			const SparseChrom c = q.table[chrom];
+			ch = SpLocal{c.start, c.end, c.val, c.n};
 		}
-		int64_t total = 0;
-		for (int64_t r = lo; r < ch.n; ++r) {
-			const int64_t rs = __ldg(ch.start + r);
-			if (rs >= we)
-				break;
-			const int64_t re = __ldg(ch.end + r);
-			total += (we < re ? we : re) - (ws > rs ? ws : rs);
+		double cov = mg_nan();
+		if (ok) {
+			// first source interval with end > ws (== lower_bound by start, minus one when the previous one still overlaps)
+			int64_t lo = 0, hi = ch.n;
+			while (lo < hi) {
+				const int64_t mid = lo + ((hi - lo) >> 1);
+				if (ch.end[mid] > ws)
+					hi = mid;
+				else
+					lo = mid + 1;
+			}
+			int64_t total = 0;
+			for (int64_t r = lo; r < ch.n; ++r) {
+				const int64_t rs = ch.start[r];
+				if (rs >= we)
+					break;
+				const int64_t re = ch.end[r];
+				total += (we < re ? we : re) - (ws > rs ? ws : rs);
+			}
+			cov = (double)total / (double)(we - ws);
 		}
-		cov = (double)total / (double)(we - ws);
+		mg_st_stream(q.out + i, cov);
 	}
-	mg_st_stream(q.out + i, cov);
 }

@@ -210,6 +210,74 @@ __global__ void __launch_bounds__(MG_SUM_THREADS) k_dense_stream_summary(const R
 		block_out[blockIdx.x] = m;
 }
 
+// ---- contiguous-segment streaming kernels (fixed-bin iterator at track resolution over few scope intervals) ---------------
+// One launch per scope interval: a pure stream over vals[b0, b0 + n) with aligned 16-byte loads, 4 independent loads in
+// flight per thread. FP64 work per bin is one DADD (sum) and one DFMA (sum of squares: the product of two floats is exact
+// in double, so fma(v, v, acc) rounds exactly like acc + v * v); counts are integers, min / max stay in float.
+struct MomF {
+	unsigned long long nn;
+	double sum, ssq;
+	float mn, mx;
+};
+__device__ __forceinline__ void momf_add(MomF &m, float v)
+{
+	if (!isnan(v)) {
+		const double d = (double)v;
+		m.nn++;
+		m.sum += d;
+		m.ssq = fma(d, d, m.ssq);
+		m.mn = fminf(m.mn, v);
+		m.mx = fmaxf(m.mx, v);
+	}
+}
+
+template <typename F>
+__device__ __forceinline__ void mg_stream_segment(const float *__restrict__ p, int64_t n, F &&f)
+{
+	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+	int64_t head = (4 - (int64_t)((reinterpret_cast<uintptr_t>(p) >> 2) & 3)) & 3;
+	if (head > n)
+		head = n;
+	const int64_t nv4 = (n - head) >> 2;
+	const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+	int64_t i = tid;
+	for (; i + 3 * nthreads < nv4; i += 4 * nthreads) {
+		const float4 a = __ldcs(p4 + i), b = __ldcs(p4 + i + nthreads), c = __ldcs(p4 + i + 2 * nthreads), d = __ldcs(p4 + i + 3 * nthreads);
+		f(a.x); f(a.y); f(a.z); f(a.w);
+		f(b.x); f(b.y); f(b.z); f(b.w);
+		f(c.x); f(c.y); f(c.z); f(c.w);
+		f(d.x); f(d.y); f(d.z); f(d.w);
+	}
+	for (; i < nv4; i += nthreads) {
+		const float4 a = __ldcs(p4 + i);
+		f(a.x); f(a.y); f(a.z); f(a.w);
+	}
+	if (tid < head)
+		f(p[tid]);
+	const int64_t tail0 = head + (nv4 << 2);
+	if (tid < n - tail0)
+		f(p[tail0 + tid]);
+}
+
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_seg_summary(const float *__restrict__ p, int64_t n, Moments *block_out)
+{
+	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	MomF mf{0ull, 0., 0., __int_as_float(0x7f800000), __int_as_float(0xff800000)};
+	mg_stream_segment(p, n, [&](float v) { momf_add(mf, v); });
+	Moments m;
+	m.n = 0; // the row count of the segment is added by the host-side launch (thread 0 of block 0 below)
+	m.nn = (double)mf.nn;
+	m.sum = mf.sum;
+	m.ssq = mf.ssq;
+	m.mn = mf.nn ? (double)mf.mn : 1.7976931348623157e308;
+	m.mx = mf.nn ? (double)mf.mx : -1.7976931348623157e308;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		m.n = (double)n;
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0)
+		block_out[blockIdx.x] = m;
+}
+
 // ---- histogram -----------------------------------------------------------------------------------------------------------
 #define MG_HIST_MAX_DIMS 8
 #define MG_HIST_MAX_BREAKS 1024 // per call, all dimensions together (constant-bank resident)
@@ -311,6 +379,55 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_values_hist_private(const d
 		for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
 			emit(__ldcs(vals + i));
 	});
+}
+
+// Float inputs (dense-track values are float32 widened to double): val2bin is monotone in the value, so the bin of a
+// float is the number of float thresholds below it. thr[j], j = 0..nb, = the largest float whose bin is < j (bin -1 =
+// below the first break, nb = above the last); computed on the host by bisection with the double formula, hence exact.
+__device__ __forceinline__ int mg_float_bin(const float *__restrict__ thr, int nb, float v)
+{
+	if (isnan(v))
+		return -1;
+	int lo = 0, hi = nb + 1; // count of thresholds < v lies in [lo, hi]
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (thr[mid] < v)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo == nb + 1 ? -1 : lo - 1; // lo thresholds are below v: bin = lo - 1 (-1: too low); all nb+1 below: too high
+}
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_seg_hist(const float *__restrict__ p, int64_t n, const float *__restrict__ thr_g, int nb,
+															   unsigned long long *counts)
+{
+	extern __shared__ __align__(16) uint32_t hsmem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	float *thr = reinterpret_cast<float *>(hsmem);
+	const int thr_words = (nb + 1 + 3) & ~3;
+	uint32_t *hall = hsmem + thr_words, *h = hall + warp * nb * 32;
+	for (int t = threadIdx.x; t <= nb; t += blockDim.x)
+		thr[t] = thr_g[t];
+	for (int t = lane; t < nb * 32; t += 32)
+		h[t] = 0;
+	__syncthreads();
+	mg_stream_segment(p, n, [&](float v) {
+		const int b = mg_float_bin(thr, nb, v);
+		if (b >= 0)
+			h[b * 32 + lane]++;
+	});
+	__syncthreads();
+	for (int b = warp; b < nb; b += nwarps) {
+		unsigned long long c = 0;
+		for (int w = 0; w < nwarps; ++w)
+			c += hall[(w * nb + b) * 32 + lane];
+#pragma unroll
+		for (int k = 16; k > 0; k >>= 1)
+			c += __shfl_xor_sync(0xffffffffu, c, k);
+		if (lane == 0 && c)
+			atomicAdd(counts + b, c);
+	}
 }
 
 // general N-D histogram over device columns: global atomics (one per surviving row)

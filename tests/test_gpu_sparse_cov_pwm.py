@@ -183,3 +183,46 @@ def test_rows_fixedbin_and_intervals_golden(gpu_ctx, golden):
     assert np.array_equal(perm[k], golden["it_iv_rows_scope"])
     # known answer: tests/testthat/test-iterator-overlaps.R:444 -- 2 rows for gintervals(1, 0, 1000) at iterator 500
     assert gpu_ctx.rows_fixedbin(500, [0], [0], [1000]).n == 2
+
+
+def test_sparse_and_coverage_block_narrowing_modes():
+    """Rows of mixed chromosomes in one block (per-thread global search), hulls wider than the shared-memory stage
+    (narrowed global range) and ordinary neighbouring rows (staged range) must all agree with the oracle."""
+    from misha_b200 import synth
+    sizes = [3_000_000, 2_000_000]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(17)
+        sp, iv = gpu.SparseTrack(ctx2), gpu.IntervalSet(ctx2)
+        recs = []
+        for cid in range(2):
+            s, e, v = synth.sparse_records(cid, sizes[cid], 6000)
+            sp.stage(cid, s, e, v)
+            iv.stage(cid, s, e)
+            recs.append((s, e, v))
+        n = 6000
+        chrom = rng.integers(0, 2, n).astype(np.int32)  # interleaved chromosomes, unsorted positions
+        start = (rng.random(n) * (np.array(sizes)[chrom] - 10)).astype(np.int64)
+        end = np.minimum(start + rng.choice([1, 30, 500, 40000, 2_500_000], n), np.array(sizes)[chrom])
+        cases = [(chrom, start, end)]
+        for cid in range(2):  # sorted single-chromosome rows: staged path; with huge shifts: narrowed-global path
+            s = np.sort(rng.integers(0, sizes[cid] - 10, n))
+            cases.append((np.full(n, cid, np.int32), s, np.minimum(s + rng.integers(1, 3000, n), sizes[cid])))
+        for ch, s, e in cases:
+            rows = ctx2.rows_upload(ch, s, e)
+            for sshift, eshift in ((0, 0), (-2000, 2000), (-1_500_000, 1_500_000)):
+                names = ("avg", "sum", "min", "max", "stddev", "nearest", "size")
+                got = sp.window(rows, list(names) + [("quantile", 0.25)], sshift, eshift)
+                cov = iv.coverage(rows, sshift, eshift)
+                for cid in range(2):
+                    m = ch == cid
+                    if not m.any():
+                        continue
+                    rs, re, rv = recs[cid]
+                    exp = port.sparse_window(rs, re, rv, sizes[cid], s[m], e[m], sshift, eshift, 0.25)
+                    for k, name in enumerate(names):
+                        assert_same(got[k][m], exp[name], f"{name} chrom{cid} {sshift}")
+                    assert_same(got[7][m], exp["quantile"], f"quantile chrom{cid} {sshift}")
+                    assert_same(cov[m], port.coverage(rs, re, sizes[cid], s[m], e[m], sshift, eshift), f"coverage chrom{cid} {sshift}")
+    finally:
+        ctx2.close()

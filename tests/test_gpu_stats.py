@@ -161,3 +161,34 @@ def test_screen_merge(gpu_ctx):
     dflag = gpu_ctx.alloc(6, np.int8).from_host(np.ones(6, np.int8))
     gc, gs, ge = gpu.screen_merge(gpu_ctx, rows, dflag)
     assert gc.tolist() == [0, 0, 1] and gs.tolist() == [0, 30, 40] and ge.tolist() == [20, 50, 60]
+
+
+def test_stream_hist_values_on_breaks():
+    """Exact float thresholds of the streaming gdist kernel: values sitting exactly on breaks, one ulp either side,
+    include.lowest on and off, uniform (ceil formula) and ragged (binary search) breaks."""
+    size = 20 * 40000
+    ctx2 = gpu.Context([size])
+    try:
+        rng = np.random.default_rng(6)
+        brs = [np.linspace(0, 1, 101), np.arange(11) * 0.1, np.array([0, 0.2, 0.5, 1.0]), np.linspace(-2, 7, 38)]
+        pool = np.concatenate([b.astype(np.float32) for b in brs] + [np.nextafter(b.astype(np.float32), np.float32(9)) for b in brs] +
+                              [np.nextafter(b.astype(np.float32), np.float32(-9)) for b in brs] + [rng.normal(0.5, 1, 5000).astype(np.float32)])
+        bins = rng.choice(pool, size // 20).astype(np.float32)
+        bins[::101] = np.nan
+        t = gpu.DenseTrack(ctx2, 20)
+        t.stage(0, bins)
+        rows = ctx2.rows_fixedbin(20, [0], [0], [size])
+        v = bins.astype(np.float64)
+        for br in brs:
+            for il in (False, True):
+                counts = ctx2.alloc(len(br) - 1, np.uint64).zero()
+                t.hist_dev(rows, "avg", br, counts, include_lowest=il)
+                assert np.array_equal(counts.to_host(), port.hist(v, [br], il)), (len(br), il)
+        part = gpu.summary_init(ctx2)
+        t.summary_dev(rows, "avg", part)
+        got = gpu.summary_finalize(part.to_host())
+        exp = port.summary(v)
+        assert_same(got[:4], exp[:4], "counts/min/max")
+        assert_close(got[4:], exp[4:], 1e-12, "moments")
+    finally:
+        ctx2.close()

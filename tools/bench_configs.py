@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Kernel timings of the other BASELINE.json configs (C2, C4, C5) at full size -- not the driver's bench line, but the
+numbers DESIGN.md / profiles quote for those rows. CUDA events on the launching stream, inputs resident in HBM.
+
+    python tools/bench_configs.py [--configs C2,C4,C5] [--steps 5] [--scale 1.0]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from misha_b200 import gpu, synth  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(torch, fn, steps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def report(name, ms, alg_bytes, rows, extra=None):
+    d = {"config": name, "ms": round(ms, 4), "rows": int(rows), "rows_per_s": rows / ms * 1e3, "alg_bytes": int(alg_bytes),
+         "alg_gbs": alg_bytes / ms / 1e6, "frac_of_measured_hbm_peak": alg_bytes / ms / 1e6 / PEAK}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="C2,C4,C5")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    import torch
+    torch.cuda.set_device(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    chroms = synth.genome(args.scale)
+    sizes = [s for _, s in chroms]
+    ctx = gpu.Context(sizes)
+    want = args.configs.split(",")
+    sc = np.arange(len(chroms), dtype=np.int32)
+    ss, se = np.zeros(len(chroms), np.int64), np.array(sizes, np.int64)
+
+    if "C2" in want:
+        dense = gpu.DenseTrack(ctx, 20)
+        nb = 0
+        for i in range(len(chroms)):
+            b = synth.dense_bins(i, sizes[i], 20)
+            nb += len(b)
+            dense.stage(i, b)
+        rows = ctx.rows_fixedbin(20, sc, ss, se)
+        part = gpu.summary_init(ctx)
+        ms = timed(torch, lambda: dense.summary_dev(rows, "avg", part, stream=stream), args.steps)
+        report("C2 gsummary (dense 20bp, whole genome, track-resolution iterator)", ms, 4 * nb, rows.n)
+        counts = ctx.alloc(100, np.uint64).zero()
+        br = np.linspace(0, 100, 101)
+        ms = timed(torch, lambda: dense.hist_dev(rows, "avg", br, counts, stream=stream), args.steps)
+        report("C2 gdist 100 bins (dense 20bp, whole genome)", ms, 4 * nb, rows.n)
+        # generic (non-streaming) path: iterator 200 bp = 10 bins per row through the prefix sums
+        rows2 = ctx.rows_fixedbin(200, sc, ss, se)
+        ms = timed(torch, lambda: dense.summary_dev(rows2, "avg", part, stream=stream), args.steps)
+        report("C2b gsummary iterator=200 (prefix path)", ms, 4 * nb, rows2.n)
+        dense.free()
+
+    if "C4" in want:
+        sp = gpu.SparseTrack(ctx)
+        iv = gpu.IntervalSet(ctx)
+        cnt = synth.interval_counts(chroms, int(5_000_000 * args.scale))
+        nrec = 0
+        for i in range(len(chroms)):
+            s, e, v = synth.sparse_records(i, sizes[i], int(cnt[i]))
+            sp.stage(i, s, e, v)
+            iv.stage(i, s, e)
+            nrec += len(s)
+        rows = ctx.rows_fixedbin(20, sc, ss, se)
+        out = [ctx.alloc(rows.n, np.float64)]
+        ms1 = timed(torch, lambda: sp.window_dev(rows, ["nearest"], out=out, stream=stream), args.steps)
+        report("C4 sparse nearest @ 20bp iterator", ms1, 20 * nrec + 8 * rows.n, rows.n)
+        out2 = ctx.alloc(rows.n, np.float64)
+        ms2 = timed(torch, lambda: iv.coverage_dev(rows, out=out2, stream=stream), args.steps)
+        report("C4 coverage @ 20bp iterator", ms2, 16 * nrec + 8 * rows.n, rows.n)
+        report("C4 nearest + coverage (two launches)", ms1 + ms2, 20 * nrec + 16 * rows.n, rows.n)
+        sp.free(); iv.free()
+
+    if "C5" in want:
+        seq = gpu.Sequence(ctx)
+        t0 = time.perf_counter()
+        for i in range(len(chroms)):
+            seq.stage(i, synth.sequence(i, sizes[i]))
+        stage_s = time.perf_counter() - t0
+        n = int(1_000_000 * args.scale)
+        cnt = synth.interval_counts(chroms, n)
+        ch, st, en = [], [], []
+        for i in range(len(chroms)):
+            s, e = synth.intervals(i, sizes[i], int(cnt[i]), 500, 500)
+            ch.append(np.full(len(s), i, np.int32)); st.append(s); en.append(e)
+        rows = ctx.rows_upload(np.concatenate(ch), np.concatenate(st), np.concatenate(en))
+        logp = gpu.pssm_logp(synth.pssm(20), 0.01)
+        out = ctx.alloc(rows.n, np.float64)
+        for mode in ("pwm", "pwm.max"):
+            ms = timed(torch, lambda: seq.pwm_dev(rows, logp, bidirect=True, extend=True, mode=mode, out=out, stream=stream), args.steps)
+            anchors = rows.n * 500
+            report("C5 %s 20-mer bidirect, 1M x 500bp" % mode, ms, rows.n * (130 + 8), rows.n,
+                   {"anchors_per_s": anchors / ms * 1e3, "strand_scores_per_s": 2 * anchors / ms * 1e3, "seq_staging_s": round(stage_s, 2)})
+        seq.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
