@@ -1,0 +1,504 @@
+"""Host-side mirror of misha's R interface for the hot path -- same names, argument meaning and error behaviour
+(`gextract`, `gscreen`, `gsummary`, `gdist`, `gvtrack.create`, `gvtrack.iterator`, `gintervals`), so the parity tests read
+like the reference's own tests. It holds NO arithmetic: it reads the reference's on-disk formats,
+stages tracks once, turns scope + iterator into device rows and calls the C ABI (include/mishagpu.h). Track expressions
+other than a bare (virtual) track name are evaluated on the returned vectors with numpy, as R evaluates them on the
+1000-row batches (src/TrackExpressionScanner.cpp:352-368).
+
+R reference points: gextract R/compute-core.R:77, gsummary :286, gscreen R/compute-utils.R:216, gdist
+R/compute-distribution.R:152, gvtrack.create R/vtrack.R:1204, gvtrack.iterator :1370; C++ entry points
+src/GenomeTrackExtract.cpp:518, src/GenomeTrackScreener.cpp:167, src/GenomeTrackSummary.cpp:119,
+src/GenomeTrackDistribution.cpp:19.
+"""
+import os
+import re
+
+import numpy as np
+
+from . import gpu
+
+TRACK_FUNCS = ("avg", "sum", "min", "max", "stddev", "quantile", "nearest", "size", "exists")
+PWM_FUNCS = ("pwm", "pwm.max", "pwm.count")
+
+
+# What rerror()/verror() raise in R (src/rdbutils.cpp:708-733): host-side validation and C-ABI failures are one error type.
+MishaError = gpu.MishaGpuError
+
+
+def _split_top(expr, ops):
+    """Split at the top-level (parenthesis depth 0) occurrences of the one-character operators in `ops`."""
+    parts, depth, cur = [], 0, []
+    i = 0
+    while i < len(expr):
+        ch = expr[i]
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if depth == 0 and ch in ops:
+            parts.append("".join(cur))
+            cur = []
+            if i + 1 < len(expr) and expr[i + 1] == ch:  # && and || behave like & and | on the vectors we hold
+                i += 1
+        else:
+            cur.append(ch)
+        i += 1
+    parts.append("".join(cur))
+    return parts
+
+
+def _r_logic_to_python(expr):
+    """R gives comparison operators higher precedence than !, & and |; Python's ~, & and | bind tighter than comparisons.
+    Re-parenthesise so that numpy evaluates what R would: a > 1 & !b < 2  ->  ((a > 1)) & (~(b < 2))."""
+    out, i, n = [], 0, len(expr)
+    while i < n:  # first rewrite the inside of every parenthesised group
+        if expr[i] == "(":
+            depth, j = 1, i + 1
+            while j < n and depth:
+                depth += expr[j] == "("
+                depth -= expr[j] == ")"
+                j += 1
+            out.append("(" + _r_logic_to_python(expr[i + 1:j - 1]) + ")")
+            i = j
+        else:
+            out.append(expr[i])
+            i += 1
+    expr = "".join(out)
+    ors = _split_top(expr, "|")
+    if len(ors) > 1:
+        return " | ".join("(" + _r_logic_to_python(o) + ")" for o in ors)
+    ands = _split_top(expr, "&")
+    if len(ands) > 1:
+        return " & ".join("(" + _r_logic_to_python(a) + ")" for a in ands)
+    t = expr.strip()
+    if t.startswith("!") and not t.startswith("!="):
+        return "~(" + _r_logic_to_python(t[1:]) + ")"
+    return expr
+
+
+class Intervals(dict):
+    """A 1-D intervals set: columns chrom (names), start, end (+ anything else). Mirrors the R data frame."""
+
+    def __init__(self, chrom, start, end, **extra):
+        super().__init__(chrom=np.asarray(chrom, dtype=object), start=np.asarray(start, dtype=np.int64), end=np.asarray(end, dtype=np.int64))
+        for k, v in extra.items():
+            self[k] = np.asarray(v)
+
+    def __len__(self):
+        return len(self["start"])
+
+
+class _VTrack:
+    def __init__(self, name, src, func, params):
+        self.name, self.src, self.func, self.params = name, src, func, params
+        self.sshift = self.eshift = 0
+
+
+class MishaDB:
+    """One genome database root + one GPU context (the `.misha` environment of an R session)."""
+
+    def __init__(self, groot, device=0):
+        self.groot = groot
+        path = os.path.join(groot, "chrom_sizes.txt")
+        if not os.path.exists(path):
+            raise MishaError("%s is not a misha database root (no chrom_sizes.txt)" % groot)
+        chroms = []
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 2:
+                name = f[0] if f[0].startswith("chr") else "chr" + f[0]  # R/db-root.R:86-105
+                chroms.append((name, int(f[1])))
+        chroms.sort(key=lambda c: c[0])  # per-chromosome DB: alphabetical order (R/db-root.R:157-162)
+        self.chroms = chroms
+        self.chrom_names = [c for c, _ in chroms]
+        self.chrom_sizes = np.array([s for _, s in chroms], dtype=np.int64)
+        self.chrom_id = {c: i for i, c in enumerate(self.chrom_names)}
+        for c, i in list(self.chrom_id.items()):
+            self.chrom_id[c[3:]] = i  # un-prefixed aliases
+        self.ctx = gpu.Context(self.chrom_sizes, device)
+        self.vtracks = {}
+        self._dense, self._sparse, self._ivsets, self._seq = {}, {}, {}, None
+
+    def close(self):
+        self.ctx.close()
+
+    # ---- intervals ----------------------------------------------------------------------------------------
+    def gintervals(self, chroms, starts=0, ends=-1):
+        chroms = np.atleast_1d(np.asarray(chroms, dtype=object))
+        starts = np.broadcast_to(np.atleast_1d(starts), chroms.shape).astype(np.int64)
+        ends = np.broadcast_to(np.atleast_1d(ends), chroms.shape).astype(np.int64).copy()
+        names = []
+        for k, c in enumerate(chroms):
+            key = str(c)
+            if key not in self.chrom_id:
+                raise MishaError("Chromosome %s does not exist" % key)
+            cid = self.chrom_id[key]
+            names.append(self.chrom_names[cid])
+            if ends[k] == -1:
+                ends[k] = self.chrom_sizes[cid]
+        iv = Intervals(names, starts, ends)
+        self._validate(iv)
+        return iv
+
+    def gintervals_all(self):
+        return Intervals(self.chrom_names, np.zeros(len(self.chroms), np.int64), self.chrom_sizes.copy())
+
+    def _validate(self, iv):
+        cid = self._cids(iv)
+        s, e = iv["start"], iv["end"]
+        bad = (s < 0) | (s >= e) | (e > self.chrom_sizes[cid])
+        if bad.any():
+            k = int(np.flatnonzero(bad)[0])
+            raise MishaError("Invalid interval (%s, %d, %d)" % (iv["chrom"][k], s[k], e[k]))  # src/IntervalConverter.cpp:200-360
+
+    def _cids(self, iv):
+        try:
+            return np.array([self.chrom_id[str(c)] for c in iv["chrom"]], dtype=np.int32)
+        except KeyError as e:
+            raise MishaError("Chromosome %s does not exist" % e.args[0])
+
+    # ---- tracks -------------------------------------------------------------------------------------------
+    def _track_dir(self, track):
+        return os.path.join(self.groot, "tracks", track.replace(".", "/") + ".track")
+
+    def gtrack_exists(self, track):
+        return os.path.isdir(self._track_dir(track))
+
+    def gtrack_ls(self):
+        out = []
+        root = os.path.join(self.groot, "tracks")
+        for dp, dn, _ in os.walk(root):
+            for d in dn:
+                if d.endswith(".track"):
+                    out.append(os.path.relpath(os.path.join(dp, d), root)[:-6].replace(os.sep, "."))
+        return sorted(out)
+
+    def _track_type(self, track):
+        d = self._track_dir(track)
+        for c in self.chrom_names:
+            f = os.path.join(d, c)
+            if os.path.exists(f) and os.path.getsize(f) >= 4:
+                sig = int(np.fromfile(f, dtype=np.int32, count=1)[0])  # src/GenomeTrack.cpp:227-250
+                if sig >= 1:
+                    return "dense"
+                if sig == -1:
+                    return "sparse"
+                raise MishaError("Track %s: unsupported track type (signature %d)" % (track, sig))
+        raise MishaError("Track %s does not exist" % track)
+
+    def _dense_track(self, track):
+        if track not in self._dense:
+            d = self._track_dir(track)
+            t = None
+            for cid, c in enumerate(self.chrom_names):
+                f = os.path.join(d, c)
+                if not os.path.exists(f):
+                    raise MishaError("Track %s: missing chromosome file %s" % (track, c))
+                raw = np.fromfile(f, dtype=np.uint8)
+                bin_size = int(raw[:4].view(np.uint32)[0])
+                if t is None:
+                    t = gpu.DenseTrack(self.ctx, bin_size)
+                elif t.bin_size != bin_size:
+                    raise MishaError("Track %s: inconsistent bin size" % track)
+                t.stage(cid, raw[4:].view(np.float32))
+            self._dense[track] = t
+        return self._dense[track]
+
+    def _sparse_records(self, track, cid):
+        f = os.path.join(self._track_dir(track), self.chrom_names[cid])
+        if not os.path.exists(f):
+            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32)
+        raw = np.fromfile(f, dtype=np.uint8)
+        rec = raw[4:].view(np.dtype([("s", "<i8"), ("e", "<i8"), ("v", "<f4")]))
+        return rec["s"].copy(), rec["e"].copy(), rec["v"].copy()
+
+    def _sparse_track(self, track):
+        if track not in self._sparse:
+            t = gpu.SparseTrack(self.ctx)
+            for cid in range(len(self.chroms)):
+                t.stage(cid, *self._sparse_records(track, cid))
+            self._sparse[track] = t
+        return self._sparse[track]
+
+    def _sequence(self):
+        if self._seq is None:
+            s = gpu.Sequence(self.ctx)
+            for cid, c in enumerate(self.chrom_names):
+                s.stage(cid, np.fromfile(os.path.join(self.groot, "seq", c + ".seq"), dtype=np.uint8))
+            self._seq = s
+        return self._seq
+
+    def _ivset(self, vt):
+        if vt.name not in self._ivsets:
+            iv = vt.src
+            cid = self._cids(iv)
+            s = gpu.IntervalSet(self.ctx)
+            for c in range(len(self.chroms)):
+                m = cid == c
+                st, en = iv["start"][m], iv["end"][m]
+                order = np.argsort(st, kind="stable")
+                st, en = st[order], en[order]
+                # sort + unify_overlaps (src/TrackExpressionVars.cpp:1299-1301, src/GIntervals.cpp:59-74)
+                us, ue = [], []
+                for a, b in zip(st, en):
+                    if us and a <= ue[-1]:
+                        ue[-1] = max(ue[-1], b)
+                    else:
+                        us.append(a)
+                        ue.append(b)
+                s.stage(c, np.array(us, np.int64), np.array(ue, np.int64))
+            self._ivsets[vt.name] = s
+        return self._ivsets[vt.name]
+
+    # ---- virtual tracks -----------------------------------------------------------------------------------
+    def gvtrack_create(self, vtrack, src=None, func=None, params=None):
+        """R/vtrack.R:1204. src: track name, Intervals (for 'coverage'), or None for sequence functions (pwm*)."""
+        if not re.match(r"^[A-Za-z][A-Za-z0-9_.]*$", vtrack):
+            raise MishaError("Invalid virtual track name %s" % vtrack)
+        if isinstance(src, str):
+            if not self.gtrack_exists(src):
+                raise MishaError("Track %s does not exist" % src)
+            func = func or "avg"
+            if func not in TRACK_FUNCS:
+                raise MishaError("Virtual track %s: function %s is not supported by this build" % (vtrack, func))
+            if func == "quantile":
+                if params is None or not (0 <= float(params) <= 1):
+                    raise MishaError("Virtual track %s: function quantile requires a percentile in [0, 1]" % vtrack)
+        elif isinstance(src, Intervals):
+            func = func or "coverage"
+            if func != "coverage":
+                raise MishaError("Virtual track %s: function %s is not supported for interval sources by this build" % (vtrack, func))
+        elif src is None:
+            if func not in PWM_FUNCS:
+                raise MishaError("Virtual track %s: a NULL source requires a sequence function (pwm, pwm.max, pwm.count)" % vtrack)
+            p = dict(params) if isinstance(params, dict) else {"pssm": params}
+            pssm = np.asarray(p.get("pssm"), dtype=np.float64)
+            if pssm.ndim != 2 or pssm.shape[1] != 4:
+                raise MishaError("Virtual track %s: PWM functions require a matrix with columns A, C, G, T" % vtrack)
+            prior = float(p.get("prior", 0.01))  # defaults: R/vtrack.R:179-290
+            if not (0 <= prior <= 1):
+                raise MishaError("Virtual track %s: prior must be between 0 and 1" % vtrack)
+            params = dict(pssm=pssm, bidirect=bool(p.get("bidirect", True)), prior=prior, extend=bool(p.get("extend", True)),
+                          strand=int(p.get("strand", 1)), score_thresh=float(p.get("score.thresh", p.get("score_thresh", 0.0))))
+        else:
+            raise MishaError("Virtual track %s: unsupported source" % vtrack)
+        self.vtracks[vtrack] = _VTrack(vtrack, src, func, params)
+        self._ivsets.pop(vtrack, None)
+
+    def gvtrack_iterator(self, vtrack, sshift=0, eshift=0):
+        """R/vtrack.R:1370 (1-D form)."""
+        if vtrack not in self.vtracks:
+            raise MishaError("Virtual track %s does not exist" % vtrack)
+        self.vtracks[vtrack].sshift, self.vtracks[vtrack].eshift = int(sshift), int(eshift)
+
+    def gvtrack_rm(self, vtrack):
+        self.vtracks.pop(vtrack, None)
+        self._ivsets.pop(vtrack, None)
+
+    def gvtrack_ls(self):
+        return sorted(self.vtracks)
+
+    # ---- scanner ------------------------------------------------------------------------------------------
+    def _expr_vars(self, expr):
+        """Names of tracks / virtual tracks an expression mentions (longest match first, as identifiers)."""
+        names = sorted(set(self.gtrack_ls()) | set(self.vtracks), key=len, reverse=True)
+        found = []
+        for n in names:
+            if re.search(r"(?<![A-Za-z0-9_.])" + re.escape(n) + r"(?![A-Za-z0-9_.])", expr):
+                found.append(n)
+        return found
+
+    def _var_track(self, name):
+        vt = self.vtracks.get(name)
+        return vt.src if vt is not None and isinstance(vt.src, str) else (name if vt is None else None)
+
+    def _rows(self, exprs, intervals, iterator, unify_scope):
+        self._validate(intervals)
+        cid = self._cids(intervals)
+        order = np.lexsort((intervals["start"], cid))  # stable sort by (chromid, start), src/GenomeTrackExtract.cpp:557-562
+        sc, ss, se = cid[order], intervals["start"][order], intervals["end"][order]
+        if unify_scope and len(sc):  # gsummary / gdist / gscreen: sort + unify_overlaps
+            keep_c, keep_s, keep_e = [sc[0]], [ss[0]], [se[0]]
+            for c, a, b in zip(sc[1:], ss[1:], se[1:]):
+                if c != keep_c[-1] or keep_e[-1] < a:
+                    keep_c.append(c); keep_s.append(a); keep_e.append(b)
+                elif keep_e[-1] < b:
+                    keep_e[-1] = b
+            sc, ss, se = np.array(keep_c, np.int32), np.array(keep_s, np.int64), np.array(keep_e, np.int64)
+            order = np.arange(len(sc))
+        if iterator is None:
+            tracks = []
+            for e in exprs:
+                for v in self._expr_vars(e):
+                    t = self._var_track(v)
+                    if t is not None:
+                        tracks.append(t)
+            if not tracks:
+                raise MishaError("Cannot implicitly determine iterator policy: track expressions do not contain any tracks.")
+            types = {self._track_type(t) for t in tracks}
+            if types == {"dense"}:
+                sizes = {self._dense_track(t).bin_size for t in tracks}
+                if len(sizes) != 1:
+                    raise MishaError("Cannot implicitly determine iterator policy: track expressions contain tracks with different bin sizes.")
+                iterator = sizes.pop()
+            elif types == {"sparse"} and len(set(tracks)) == 1:
+                chroms, st, en = [], [], []
+                for c in range(len(self.chroms)):
+                    a, b, _ = self._sparse_records(tracks[0], c)
+                    chroms.append(np.full(len(a), c, np.int32)); st.append(a); en.append(b)
+                iterator = ("records", np.concatenate(chroms), np.concatenate(st), np.concatenate(en))
+            else:
+                raise MishaError("Cannot implicitly determine iterator policy")
+        if isinstance(iterator, (int, np.integer)):
+            if iterator <= 0:
+                raise MishaError("Bin size of a fixed bin iterator (%d) must be positive" % iterator)
+            rows = self.ctx.rows_fixedbin(int(iterator), sc, ss, se)
+        else:
+            if isinstance(iterator, Intervals):
+                self._validate(iterator)
+                ic, is_, ie = self._cids(iterator), iterator["start"], iterator["end"]
+            else:
+                _, ic, is_, ie = iterator
+            o = np.lexsort((is_, ic))
+            ic, is_, ie = ic[o], is_[o], ie[o]
+            if len(ic):  # unify_overlaps(false): touching intervals stay apart (src/TrackExpressionScanner.cpp:948)
+                kc, ks, ke = [ic[0]], [is_[0]], [ie[0]]
+                for c, a, b in zip(ic[1:], is_[1:], ie[1:]):
+                    if c != kc[-1] or ke[-1] <= a:
+                        kc.append(c); ks.append(a); ke.append(b)
+                    elif ke[-1] < b:
+                        ke[-1] = b
+                ic, is_, ie = np.array(kc, np.int32), np.array(ks, np.int64), np.array(ke, np.int64)
+            rows = self.ctx.rows_intervals(ic, is_, ie, sc, ss, se)
+        return rows, order
+
+    def _var_column(self, name, rows):
+        """Device column (DevBuf) of one track / vtrack variable over the rows."""
+        vt = self.vtracks.get(name)
+        if vt is None:  # a bare track name: avg (src/TrackExpressionVars.cpp:1543-1546)
+            vt = _VTrack(name, name, "avg", None)
+        if isinstance(vt.src, str):
+            f = vt.func if vt.func != "quantile" else ("quantile", float(vt.params))
+            kind = self._track_type(vt.src)
+            t = self._dense_track(vt.src) if kind == "dense" else self._sparse_track(vt.src)
+            return t.window_dev(rows, [f], vt.sshift, vt.eshift)[0]
+        if isinstance(vt.src, Intervals):
+            return self._ivset(vt).coverage_dev(rows, vt.sshift, vt.eshift)
+        p = vt.params
+        logp = gpu.pssm_logp(p["pssm"], p["prior"])
+        return self._sequence().pwm_dev(rows, logp, bidirect=p["bidirect"], extend=p["extend"], mode=vt.func, strand=p["strand"],
+                                        score_thresh=p["score_thresh"], sshift=vt.sshift, eshift=vt.eshift)
+
+    def _eval(self, expr, rows, cache):
+        """Host value vector of a track expression over the rows."""
+        expr = expr.strip()
+        names = self._expr_vars(expr)
+        if not names:
+            raise MishaError("Track expression \"%s\" does not contain any tracks or virtual tracks" % expr)
+        env = {}
+        for n in names:
+            if n not in cache:
+                cache[n] = self._var_column(n, rows).to_host()
+            env[n] = cache[n]
+        if expr in env:
+            return env[expr]
+        py = expr
+        alias = {}
+        for k, n in enumerate(names):  # names may contain dots: substitute safe identifiers
+            a = "__v%d" % k
+            py = re.sub(r"(?<![A-Za-z0-9_.])" + re.escape(n) + r"(?![A-Za-z0-9_.])", a, py)
+            alias[a] = env[n]
+        py = _r_logic_to_python(py).replace("^", "**")
+        py = re.sub(r"\bTRUE\b", "True", re.sub(r"\bFALSE\b", "False", py))
+        fns = {"log": np.log, "log2": np.log2, "log10": np.log10, "exp": np.exp, "sqrt": np.sqrt, "abs": np.abs, "pmin": np.minimum,
+               "pmax": np.maximum, "is_na": np.isnan, "floor": np.floor, "ceiling": np.ceil, "NaN": np.nan}
+        py = py.replace("is.na(", "is_na(")
+        try:
+            with np.errstate(all="ignore"):
+                out = eval(py, {"__builtins__": {}}, {**fns, **alias})  # noqa: S307 - the expression language of the host
+        except Exception as e:  # noqa: BLE001
+            raise MishaError("Evaluation of track expression \"%s\" failed: %s" % (expr, e))
+        out = np.asarray(out)
+        if out.shape == ():
+            out = np.full(rows.n, out)
+        return out
+
+    # ---- entry points -------------------------------------------------------------------------------------
+    def gextract(self, *exprs, intervals=None, iterator=None, colnames=None):
+        """R/compute-core.R:77. Returns a dict of columns: chrom, start, end, one per expression, intervalID."""
+        if not exprs:
+            raise MishaError("Usage: gextract([expr]+, intervals, colnames = NULL, iterator = NULL)")
+        intervals = self.gintervals_all() if intervals is None else intervals
+        if colnames is not None and len(colnames) != len(exprs):
+            raise MishaError("Number of column names must match the number of track expressions")
+        rows, order = self._rows(exprs, intervals, iterator, unify_scope=False)
+        if rows.n == 0:
+            return None  # R returns NULL
+        c, s, e, k = rows.coords()
+        res = {"chrom": np.array(self.chrom_names, dtype=object)[c], "start": s, "end": e}
+        cache = {}
+        for j, ex in enumerate(exprs):
+            res[colnames[j] if colnames else ex] = np.asarray(self._eval(ex, rows, cache), dtype=np.float64)
+        res["intervalID"] = (order[k] + 1).astype(np.int32)  # 1-based row of the scope data frame (src/IntervalConverter.cpp:357)
+        return res
+
+    def gscreen(self, expr, intervals=None, iterator=None):
+        """R/compute-utils.R:216. Returns Intervals of merged TRUE runs (or None)."""
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows([expr], intervals, iterator, unify_scope=True)
+        if rows.n == 0:
+            return None
+        v = self._eval(expr, rows, {})
+        if v.dtype != np.bool_:
+            raise MishaError("Expression \"%s\" does not produce a logical result" % expr)  # src/TrackExpressionScanner.h:158-173
+        flag = self.ctx.alloc(rows.n, np.int8).from_host(v.astype(np.int8))
+        c, s, e = gpu.screen_merge(self.ctx, rows, flag)
+        if len(c) == 0:
+            return None
+        return Intervals(np.array(self.chrom_names, dtype=object)[c], s, e)
+
+    def gsummary(self, expr, intervals=None, iterator=None):
+        """R/compute-core.R:286. Returns the named 7-vector as a dict."""
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows([expr], intervals, iterator, unify_scope=True)
+        part = gpu.summary_init(self.ctx)
+        expr = expr.strip()
+        vt = self.vtracks.get(expr)
+        bare_dense = (vt is None and self.gtrack_exists(expr) and self._track_type(expr) == "dense") or \
+                     (vt is not None and isinstance(vt.src, str) and self._track_type(vt.src) == "dense")
+        if rows.n:
+            if bare_dense:  # fused on the device: values never leave the chip
+                if vt is None:
+                    self._dense_track(expr).summary_dev(rows, "avg", part)
+                else:
+                    f = vt.func if vt.func != "quantile" else ("quantile", float(vt.params))
+                    self._dense_track(vt.src).summary_dev(rows, f, part, vt.sshift, vt.eshift)
+            else:
+                v = np.asarray(self._eval(expr, rows, {}), dtype=np.float64)
+                d = self.ctx.alloc(len(v), np.float64).from_host(v)
+                gpu.summary_add(self.ctx, d, len(v), part)
+        out = gpu.summary_finalize(part.to_host())
+        return dict(zip(gpu.SUMMARY_NAMES, out))
+
+    def gdist(self, *args, intervals=None, iterator=None, include_lowest=False):
+        """R/compute-distribution.R:152: gdist(expr1, breaks1, [expr2, breaks2, ...]). Returns counts, one axis per expression."""
+        if len(args) < 2 or len(args) % 2:
+            raise MishaError("Usage: gdist([expr, breaks]+, intervals = ALLGENOME, include.lowest = FALSE, iterator = NULL)")
+        exprs, breaks = [a.strip() for a in args[0::2]], [np.asarray(b, dtype=np.float64) for b in args[1::2]]
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows(exprs, intervals, iterator, unify_scope=True)
+        shape = tuple(len(b) - 1 for b in breaks)
+        counts = self.ctx.alloc(int(np.prod(shape)), np.uint64).zero()
+        if rows.n:
+            e0 = exprs[0]
+            if len(exprs) == 1 and e0 not in self.vtracks and self.gtrack_exists(e0) and self._track_type(e0) == "dense":
+                self._dense_track(e0).hist_dev(rows, "avg", breaks[0], counts, include_lowest)
+            else:
+                cache = {}
+                cols = [self.ctx.alloc(rows.n, np.float64).from_host(np.asarray(self._eval(e, rows, cache), dtype=np.float64)) for e in exprs]
+                gpu.hist_dev(self.ctx, cols, rows.n, breaks, counts, include_lowest)
+        return counts.to_host().astype(np.float64).reshape(shape, order="F")
+
+
+def gdb_init(groot, device=0):
+    return MishaDB(groot, device)

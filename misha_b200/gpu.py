@@ -7,7 +7,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import MishaGpuError, c_dbl, c_i64, c_int, c_vp, load
+from ._lib import MishaGpuError, c_dbl, c_i64, c_int, c_vp, load  # noqa: F401 (MishaGpuError re-exported)
 
 FUNC_IDS = {"avg": 0, "sum": 1, "min": 2, "max": 3, "stddev": 4, "quantile": 5, "nearest": 6, "size": 7, "exists": 8}
 PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.count": 3}

@@ -130,3 +130,16 @@ def test_two_rank_reductions_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_r_expression_precedence_rewrite():
+    """R: comparison binds tighter than ! & |; the host rewrites before numpy evaluates (misha_b200/api.py)."""
+    from misha_b200.api import _r_logic_to_python
+    a, b, c = np.array([0.5, 0.1, 0.9, np.nan]), np.array([0.3, 0.3, 0.1, 0.3]), np.array([1.0, 5.0, 2.0, 3.0])
+    env = {"a": a, "b": b, "c": c}
+    with np.errstate(invalid="ignore"):
+        assert eval(_r_logic_to_python("a > 0.4 & b > 0.25"), {}, env).tolist() == [True, False, False, False]
+        assert eval(_r_logic_to_python("a > 0.4 | (b < 0.2 & !c >= 3)"), {}, env).tolist() == [True, False, True, False]
+        assert eval(_r_logic_to_python("!a > 0.4"), {}, env).tolist() == [False, True, False, True]
+        assert eval(_r_logic_to_python("a != b && c > 1.5"), {}, env).tolist() == [False, True, True, True]
+        assert np.allclose(eval(_r_logic_to_python("a*2+c"), {}, env)[:3], [2.0, 5.2, 3.8])

@@ -1,0 +1,191 @@
+"""The R-interface mirror (misha_b200.api) on the reference's bundled example DB: these read like the reference's own
+testthat files (test-gdist.R, test-vtrack-coverage.R, test-iterator-overlaps.R, test-vtrack.R, test-pwm.R) and check
+against the known answers they hold and against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import CHROMS, TESTDB, assert_close, assert_same, read_dense, read_seq, read_sparse
+from misha_b200 import api
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def db():
+    d = api.gdb_init(TESTDB)
+    yield d
+    d.close()
+
+
+def test_gdb_init_and_chromosomes(db):
+    assert db.chrom_names == ["chr1", "chr2", "chrX"] and db.chrom_sizes.tolist() == [500000, 300000, 200000]
+    assert set(db.gtrack_ls()) >= {"dense_track", "sparse_track"}
+    all_iv = db.gintervals_all()
+    assert all_iv["end"].tolist() == [500000, 300000, 200000]
+    with pytest.raises(api.MishaError):
+        db.gintervals(7, 0, 100)
+    with pytest.raises(api.MishaError):
+        db.gintervals(1, 100, 50)
+
+
+def test_config_c1_gextract_dense_iterator_1000(db):
+    """BASELINE.json configs[0]: gextract("dense_track", gintervals.all(), iterator = 1000) -> 1000 rows."""
+    r = db.gextract("dense_track", intervals=db.gintervals_all(), iterator=1000)
+    assert len(r["start"]) == 1000 and list(r) == ["chrom", "start", "end", "dense_track", "intervalID"]
+    assert r["intervalID"].tolist() == [1] * 500 + [2] * 300 + [3] * 200
+    off = 0
+    for cid, (c, size) in enumerate(CHROMS):
+        bs, bins = read_dense("dense_track", c)
+        n = size // 1000
+        assert np.array_equal(r["start"][off:off + n], np.arange(n) * 1000) and np.all(r["chrom"][off:off + n] == c)
+        exp = port.dense_window(bins, bs, size, r["start"][off:off + n], r["end"][off:off + n], funcs=("avg",))["avg"]
+        assert_close(r["dense_track"][off:off + n], exp, 1e-6, c)
+        off += n
+
+
+def test_gdist_known_answers(db):
+    """tests/testthat/test-gdist.R:69-72."""
+    d = db.gdist("dense_track", [0, 0.2, 0.5, 1], intervals=db.gintervals(1, 0, 500000))
+    assert d.sum() == 6546
+    d = db.gdist("dense_track", [0, 0.2, 0.5, 1], intervals=db.gintervals(1, 0, 50000))
+    assert d.sum() == 901
+    with pytest.raises(api.MishaError, match="not sorted|not unique"):
+        db.gdist("dense_track", [0, 0.5, 0.2], intervals=db.gintervals(1, 0, 50000))
+    # 2-D: dense x sparse over a 200 bp iterator
+    d2 = db.gdist("dense_track", [0, 0.1, 0.2, 1], "sparse_track", [0, 0.3, 0.5, 1], intervals=db.gintervals(1), iterator=200)
+    r = db.gextract("dense_track", "sparse_track", intervals=db.gintervals(1), iterator=200)
+    exp = port.hist(np.stack([r["dense_track"], r["sparse_track"]], axis=1), [[0, 0.1, 0.2, 1], [0, 0.3, 0.5, 1]])
+    assert np.array_equal(d2, exp.astype(np.float64))
+
+
+def test_vtrack_coverage_known_answers(db):
+    """tests/testthat/test-vtrack-coverage.R:5-29,48-69."""
+    src = db.gintervals([1, 1], [100, 300], [200, 400])
+    db.gvtrack_create("cov", src, "coverage")
+    r = db.gextract("cov", intervals=db.gintervals([1, 1], [0, 100], [100, 200]), iterator=db.gintervals([1, 1], [0, 100], [100, 200]))
+    assert r["cov"].tolist() == [0.0, 1.0]
+    it = db.gintervals([1] * 5, [0, 100, 200, 300, 400], [100, 200, 300, 400, 500])
+    assert db.gextract("cov", intervals=it, iterator=it)["cov"].tolist() == [0, 1, 0, 1, 0]
+    it = db.gintervals([1] * 3, [0, 150, 350], [50, 250, 450])
+    assert db.gextract("cov", intervals=it, iterator=it)["cov"].tolist() == [0.0, 0.5, 0.5]
+    # overlapping sources are unified before coverage is computed
+    db.gvtrack_create("cov2", db.gintervals([1, 1, 1], [100, 150, 300], [200, 250, 400]), "coverage")
+    it = db.gintervals(1, 0, 500)
+    assert db.gextract("cov2", intervals=it, iterator=it)["cov2"].tolist() == [0.5]
+    db.gvtrack_rm("cov"); db.gvtrack_rm("cov2")
+
+
+def test_iterator_overlaps_and_interval_ids(db):
+    """tests/testthat/test-iterator-overlaps.R:444 and the intervalID contract (1-based row of the scope data frame)."""
+    r = db.gextract("dense_track", intervals=db.gintervals(1, 0, 1000), iterator=500)
+    assert len(r["start"]) == 2 and r["start"].tolist() == [0, 500] and r["end"].tolist() == [500, 1000]
+    scope = db.gintervals(["X", 1, 2, 1], [100, 5000, 30, 120], [260, 5100, 75, 4990])  # unsorted, overlapping scope rows
+    r = db.gextract("dense_track", intervals=scope, iterator=50)
+    c, s, e, k = port.fixedbin_rows(50, *[a[np.lexsort((scope["start"], db._cids(scope)))] for a in (db._cids(scope), scope["start"], scope["end"])])
+    order = np.lexsort((scope["start"], db._cids(scope)))
+    assert np.array_equal(r["start"], s) and np.array_equal(r["end"], e) and np.array_equal(r["intervalID"], order[k] + 1)
+
+
+def test_vtracks_on_dense_with_shifts(db):
+    """tests/testthat/test-vtrack.R style: min / max / stddev / quantile / sum with an iterator modifier."""
+    for func, prm in (("avg", None), ("max", None), ("min", None), ("sum", None), ("stddev", None), ("quantile", 0.9), ("quantile", 0.5)):
+        db.gvtrack_create("v", "dense_track", func, prm)
+        db.gvtrack_iterator("v", sshift=-130, eshift=220)
+        iv = db.gintervals([1, 1, 2, "X"], [0, 250000, 1000, 199000], [2000, 253000, 9000, 200000])
+        r = db.gextract("v", intervals=iv, iterator=100)
+        off = 0
+        for cid, (c, size) in enumerate(CHROMS):
+            m = r["chrom"] == c
+            bs, bins = read_dense("dense_track", c)
+            exp = port.dense_window(bins, bs, size, r["start"][m], r["end"][m], -130, 220, prm or 0.5, (func,))[func]
+            if func in ("avg", "sum", "stddev"):
+                assert_close(r["v"][m], exp, 1e-6, f"{func} {c}")
+            else:
+                assert_same(r["v"][m], exp, f"{func} {c}")
+    db.gvtrack_rm("v")
+    with pytest.raises(api.MishaError):
+        db.gvtrack_create("q", "dense_track", "quantile")  # percentile missing
+    with pytest.raises(api.MishaError):
+        db.gvtrack_create("q", "no_such_track", "avg")
+
+
+def test_sparse_track_implicit_iterator_and_nearest(db):
+    r = db.gextract("sparse_track", intervals=db.gintervals(1, 0, 10000))  # iterator = the track's own records
+    rs, re, rv = read_sparse("sparse_track", "chr1")
+    m = rs < 10000
+    assert np.array_equal(r["start"], rs[m]) and np.array_equal(r["end"], np.minimum(re[m], 10000))
+    assert_same(r["sparse_track"], rv[m].astype(np.float64), "values")
+    db.gvtrack_create("near", "sparse_track", "nearest")
+    r = db.gextract("near", intervals=db.gintervals(1, 0, 20000), iterator=20)
+    exp = port.sparse_window(rs, re, rv, 500000, r["start"], r["end"], funcs=("nearest",))["nearest"]
+    assert_same(r["near"], exp, "nearest")
+    db.gvtrack_rm("near")
+
+
+def test_gscreen_and_expressions(db):
+    scr = db.gscreen("dense_track > 0.2", intervals=db.gintervals(1), iterator=None)
+    bs, bins = read_dense("dense_track", "chr1")
+    c, s, e, _ = port.fixedbin_rows(50, [0], [0], [500000])
+    v = bins.astype(np.float64); v[np.isinf(v)] = np.nan
+    ec, es, ee = port.screen_merge(c, s, e, (v > 0.2).astype(np.int8))
+    assert np.array_equal(scr["start"], es) and np.array_equal(scr["end"], ee) and np.all(scr["chrom"] == "chr1")
+    # config C4 shape: nearest + coverage predicate over a 20 bp iterator
+    rs, re, rv = read_sparse("sparse_track", "chrX")
+    db.gvtrack_create("near", "sparse_track", "nearest")
+    db.gvtrack_create("cov", api.Intervals(["chrX"] * len(rs), rs, re), "coverage")
+    scr = db.gscreen("near > 0.4 & cov > 0.25", intervals=db.gintervals("X"), iterator=20)
+    c, s, e, _ = port.fixedbin_rows(20, [2], [0], [200000])
+    near = port.sparse_window(rs, re, rv, 200000, s, e, funcs=("nearest",))["nearest"]
+    _, us, ue = port.unify(np.zeros(len(rs)), rs, re, True)
+    cov = port.coverage(us, ue, 200000, s, e)
+    with np.errstate(invalid="ignore"):
+        ec, es, ee = port.screen_merge(c, s, e, ((near > 0.4) & (cov > 0.25)).astype(np.int8))
+    assert np.array_equal(scr["start"], es) and np.array_equal(scr["end"], ee)
+    # arithmetic expression over two variables
+    r = db.gextract("dense_track * 2 + near", intervals=db.gintervals("X", 0, 5000), iterator=50, colnames=["x"])
+    r2 = db.gextract("dense_track", "near", intervals=db.gintervals("X", 0, 5000), iterator=50)
+    assert_same(r["x"], r2["dense_track"] * 2 + r2["near"], "expression")
+    with pytest.raises(api.MishaError, match="logical"):
+        db.gscreen("dense_track", intervals=db.gintervals(1))
+    db.gvtrack_rm("near"); db.gvtrack_rm("cov")
+
+
+def test_gsummary(db):
+    out = db.gsummary("dense_track")
+    v = np.concatenate([read_dense("dense_track", c)[1] for c, _ in CHROMS]).astype(np.float64)
+    v[np.isinf(v)] = np.nan
+    exp = port.summary(v)
+    assert list(out) == ["Total intervals", "NaN intervals", "Min", "Max", "Sum", "Mean", "Std dev"]
+    got = np.array(list(out.values()))
+    assert_same(got[:4], exp[:4], "counts/min/max")
+    assert_close(got[4:], exp[4:], 1e-9, "moments")
+    db.gvtrack_create("mx", "dense_track", "max")
+    db.gvtrack_iterator("mx", -500, 500)
+    out = db.gsummary("mx", intervals=db.gintervals([1, 2], [0, 0], [100000, 100000]), iterator=300)
+    r = db.gextract("mx", intervals=db.gintervals([1, 2], [0, 0], [100000, 100000]), iterator=300)
+    exp = port.summary(r["mx"])
+    got = np.array(list(out.values()))
+    assert_same(got[:4], exp[:4], "vtrack counts/min/max")
+    assert_close(got[4:], exp[4:], 1e-9, "vtrack moments")
+    db.gvtrack_rm("mx")
+
+
+def test_pwm_vtrack(db, golden):
+    """tests/testthat/test-pwm.R style: pwm / pwm.max vtracks against the independent oracle, tolerance 1e-6."""
+    pssm = golden["pwm_pssm20"]
+    iv = db.gintervals([1, 1, 2, "X"], [1000, 200000, 50000, 199500], [1500, 200200, 50020, 200000])
+    for func in ("pwm", "pwm.max", "pwm.count"):
+        db.gvtrack_create("motif", None, func, dict(pssm=pssm, bidirect=True, prior=0.01, extend=True, **({"score.thresh": -22.0} if func == "pwm.count" else {})))
+        r = db.gextract("motif", intervals=iv, iterator=iv)
+        logp = port.pssm_logp(pssm, 0.01)
+        for cid, (c, size) in enumerate(CHROMS):
+            m = r["chrom"] == c
+            exp = port.pwm(read_seq(c), logp, r["start"][m], r["end"][m], True, True, func, 1, -22.0)
+            if func == "pwm.count":
+                assert np.abs(r["motif"][m] - exp).max() <= 1
+            else:
+                assert_close(r["motif"][m], exp, 1e-6, f"{func} {c}")
+    db.gvtrack_rm("motif")
+    with pytest.raises(api.MishaError):
+        db.gvtrack_create("motif", None, "pwm", dict(pssm=np.ones((5, 3))))
