@@ -24,10 +24,13 @@ struct DenseChrom {
 	// index structures (dense_index.cuh)
 	const float *pmax[MG_PYR_MAX];
 	const float *pmin[MG_PYR_MAX];
-	const uint2 *wm;          // wavelet matrix, 32 levels x wm_blocks units {ones before, 32 bits}
-	const uint32_t *wm_zeros; // zeros per level (32)
+	const uint2 *wm;          // wavelet matrix over RANK keys, wm_levels x wm_blocks units {ones before, 32 bits}
+	const uint32_t *wm_zeros; // zeros per level
 	int64_t wm_blocks;
 	int64_t wm_m;             // number of non-NaN bins
+	int wm_levels;            // ceil(log2(wm_m)): rank keys are balanced, every level halves a range
+	const float *wm_sorted;   // the non-NaN values in ascending order: value of rank r
+	const uint32_t *wm_ckpt[7]; // rank keys in the order ENTERING levels 4, 8, ..., 28: a walk whose range shrank to <= 8 finishes here
 };
 
 struct mg_dense {

@@ -4,12 +4,14 @@
 //   prefix sums (dense.cuh)      avg / sum / nearest / size / exists      2 x 16-byte entries
 //   min / max pyramids           fan-out 8; level j entry i = extremum of level j-1 entries [8i, 8i+8)
 //                                a window decomposes into <= 7 head + <= 7 tail entries per level: 2 sectors per level
-//   wavelet matrix               over the order-preserving uint32 keys of the non-NaN values (compacted in bin order;
-//                                a window maps to [cnt[sbin], cnt[ebin]) through the prefix counts). Level L holds bit
-//                                31-L of every key after the stable partitions of levels 0..L-1, in 8-byte units
-//                                {uint32 ones before the unit, uint32 bits}: a rank query = one 8-byte load + popc.
-//                                k-th smallest of a window = 32 dependent rank pairs (fewer: constant levels are
-//                                skipped and a singleton range needs one rank per level). Exact for any window size.
+//   wavelet matrix               over the DENSE RANKS of the non-NaN values (rank = position in the chromosome's sorted
+//                                order, ties by position; compacted in bin order, a window maps to
+//                                [cnt[sbin], cnt[ebin]) through the prefix counts). Ranks make every level split any
+//                                range in half whatever the value distribution, so a window of n values is down to
+//                                <= 8 candidates after log2(n/8) levels and finishes from a checkpoint. Level L holds
+//                                bit (levels-1-L) of every rank after the stable partitions of levels 0..L-1, in 8-byte
+//                                units {uint32 ones before the unit, uint32 bits}: a rank query = one 8-byte load + popc.
+//                                Exact for any window size; value of rank r = wm_sorted[r].
 #pragma once
 #include "common.cuh"
 #include "dense.cuh"
@@ -77,17 +79,21 @@ __device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, i
 
 // ------------------------------------------------------------------------------------------------------------------
 // wavelet matrix
-#define MG_WM_LEVELS 32
+#define MG_WM_LEVELS 32 // upper bound; a chromosome uses ceil(log2(#values)) levels
 
-// compact the non-NaN values' keys in bin order: keys[cnt[i]] = fkey(vals[i])
-__global__ void __launch_bounds__(256) k_wm_compact(const float *__restrict__ vals, const Pref *__restrict__ pref, int64_t nbins, uint32_t *keys)
+// compact the non-NaN values' keys in bin order: keys[j] = fkey(vals[i]), pos[j] = j with j = cnt[i]
+__global__ void __launch_bounds__(256) k_wm_compact(const float *__restrict__ vals, const Pref *__restrict__ pref, int64_t nbins, uint32_t *keys,
+													 uint32_t *pos)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nbins)
 		return;
 	const float v = vals[i];
-	if (!isnan(v))
-		keys[pref[i].cnt] = mg_fkey(v);
+	if (!isnan(v)) {
+		const long long j = pref[i].cnt;
+		keys[j] = mg_fkey(v);
+		pos[j] = (uint32_t)j;
+	}
 }
 
 // A level is an array of 8-byte units {uint32 ones before the unit, uint32 bits of 32 positions}: a rank query is one
@@ -149,6 +155,40 @@ __global__ void __launch_bounds__(256) k_wm_scatter(const uint32_t *__restrict__
 	keys_out[bit ? zeros + r1 : (uint32_t)i - r1] = keys[i];
 }
 
+// one pass of the LSD bit sort that ranks the values: stable partition of (key, pos) pairs by the pass's bit
+__global__ void __launch_bounds__(256) k_wm_sort_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pos, int64_t m,
+														  const uint2 *__restrict__ level, uint32_t zeros, uint32_t *keys_out, uint32_t *pos_out)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m)
+		return;
+	uint32_t bit;
+	const uint32_t r1 = mg_wm_rank1(level, (uint32_t)i, bit);
+	const uint32_t dst = bit ? zeros + r1 : (uint32_t)i - r1;
+	keys_out[dst] = keys[i];
+	pos_out[dst] = pos[i];
+}
+
+// after the sort: sorted[j] = value of rank j; rank_of[pos[j]] = j
+__global__ void __launch_bounds__(256) k_wm_assign_ranks(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pos, int64_t m, float *sorted,
+														  uint32_t *rank_of)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m)
+		return;
+	sorted[j] = mg_fkey_inv(keys[j]);
+	rank_of[pos[j]] = (uint32_t)j;
+}
+
+// checkpoint content: the VALUE key of every element in the order entering a level (ordering by value key == ordering by
+// rank), so a finished walk needs no rank -> value lookup
+__global__ void __launch_bounds__(256) k_wm_ckpt(const uint32_t *__restrict__ rank_keys, int64_t m, const float *__restrict__ sorted, uint32_t *ck)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < m)
+		ck[i] = mg_fkey(sorted[rank_keys[i]]);
+}
+
 struct WmState {
 	uint32_t l, r, k;
 };
@@ -177,26 +217,99 @@ __device__ __forceinline__ bool mg_wm_step(const uint2 *__restrict__ lv, uint32_
 	return true;
 }
 
-// k-th smallest key (0-based) among compacted positions [l, r), r > l, k < r - l; with want2 (requires k + 1 < r - l)
-// also the (k+1)-th. The two order statistics share one walk until the level where they part.
-__device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, uint32_t &key1, uint32_t &key2)
+// ---- finishing a walk from a checkpoint ------------------------------------------------------------------------------
+// wm_ckpt[c] holds the full keys in the order entering level 4 (c + 1). Once a range holds <= MG_WM_FINISH keys, the
+// order statistics are read off directly: three 16-byte loads cover any 8 consecutive keys, an 8-input sorting network
+// (19 compare-exchanges) orders them.
+#define MG_WM_FINISH 8
+
+__device__ __forceinline__ void mg_cswap(uint32_t &a, uint32_t &b)
 {
-	const uint32_t m = (uint32_t)ch->wm_m;
+	const uint32_t lo = min(a, b), hi = max(a, b);
+	a = lo;
+	b = hi;
+}
+
+__device__ __forceinline__ uint32_t mg_pick8(const uint32_t (&v)[8], uint32_t k)
+{
+	uint32_t r = v[0];
+#pragma unroll
+	for (int j = 1; j < 8; ++j)
+		r = k == (uint32_t)j ? v[j] : r;
+	return r;
+}
+
+// k-th (and optionally (k+1)-th) smallest of ckpt[l, r), r - l <= 8
+__device__ __forceinline__ void mg_wm_finish(const uint32_t *__restrict__ ckpt, uint32_t l, uint32_t r, uint32_t k, bool want2, uint32_t &key1,
+											 uint32_t &key2)
+{
+	const uint32_t base = l & ~3u;
+	const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(ckpt + base));
+	const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(ckpt + base + 4));
+	const uint4 q2 = __ldg(reinterpret_cast<const uint4 *>(ckpt + base + 8));
+	const uint32_t c[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+	const uint32_t off = l - base, n = r - l;
+	uint32_t v[8];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) { // v[j] = c[off + j] for j < n, else +inf padding
+		uint32_t x = c[j];
+		x = off == 1 ? c[j + 1] : x;
+		x = off == 2 ? c[j + 2] : x;
+		x = off == 3 ? c[j + 3] : x;
+		v[j] = (uint32_t)j < n ? x : 0xffffffffu;
+	}
+	mg_cswap(v[0], v[1]); mg_cswap(v[2], v[3]); mg_cswap(v[4], v[5]); mg_cswap(v[6], v[7]);
+	mg_cswap(v[0], v[2]); mg_cswap(v[1], v[3]); mg_cswap(v[4], v[6]); mg_cswap(v[5], v[7]);
+	mg_cswap(v[1], v[2]); mg_cswap(v[5], v[6]);
+	mg_cswap(v[0], v[4]); mg_cswap(v[1], v[5]); mg_cswap(v[2], v[6]); mg_cswap(v[3], v[7]);
+	mg_cswap(v[2], v[4]); mg_cswap(v[3], v[5]);
+	mg_cswap(v[1], v[2]); mg_cswap(v[3], v[4]); mg_cswap(v[5], v[6]);
+	key1 = mg_pick8(v, k);
+	key2 = want2 ? mg_pick8(v, k + 1) : key1;
+}
+
+// RANK of the k-th smallest value (0-based) among compacted positions [l, r), r > l, k < r - l; with want2 (requires
+// k + 1 < r - l) also of the (k+1)-th. The two order statistics share one walk until the level where they part; every walk stops at the
+// first checkpoint level (4, 8, ..., 28) where its range holds <= 8 keys.
+__device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
+{
+	uint32_t key1, key2;
 	const size_t stride = (size_t)ch->wm_blocks;
+	const uint2 *lv = ch->wm;
+	const uint32_t *zp = ch->wm_zeros;
 	WmState a{l, r, k}, b{0, 0, 0};
-	bool joint = want2, split = false;
+	bool joint = want2, split = false, a_done = false, b_done = false;
 	uint32_t v1 = 0, v2 = 0;
-	for (int level = 0; level < MG_WM_LEVELS; ++level) {
-		const uint32_t zeros = __ldg(ch->wm_zeros + level);
-		const uint32_t bitmask = 1u << (31 - level);
-		if (zeros == m)
-			continue; // every key has a 0 here: positions and values unchanged
-		if (zeros == 0) {
-			v1 |= bitmask; // every key has a 1 here: Z = 0, positions unchanged
-			v2 |= bitmask;
-			continue;
+	const int nlevels = ch->wm_levels;
+	uint32_t bitmask = nlevels ? 1u << (nlevels - 1) : 0u;
+	// rank keys: no level is constant (rank 0 has every bit clear, rank m-1 has the top bit set), so every level is walked
+	for (int level = 0; level < nlevels; ++level, lv += stride, bitmask >>= 1) {
+		if (level >= 4 && (level & 3) == 0) { // a checkpoint: finish whatever has become small
+			const uint32_t *ck = ch->wm_ckpt[(level >> 2) - 1];
+			if (joint) {
+				if (a.r - a.l <= MG_WM_FINISH) {
+					mg_wm_finish(ck, a.l, a.r, a.k, true, key1, key2);
+					x1 = mg_fkey_inv(key1);
+					x2 = mg_fkey_inv(key2);
+					return;
+				}
+			} else {
+				uint32_t dummy;
+				if (!a_done && a.r - a.l <= MG_WM_FINISH) {
+					mg_wm_finish(ck, a.l, a.r, a.k, false, key1, dummy);
+					x1 = mg_fkey_inv(key1);
+					a_done = true;
+				}
+				if (split && !b_done && b.r - b.l <= MG_WM_FINISH) {
+					mg_wm_finish(ck, b.l, b.r, b.k, false, key2, dummy);
+					x2 = mg_fkey_inv(key2);
+					b_done = true;
+				}
+				if (a_done && (b_done || !split))
+					break;
+			}
 		}
-		const uint2 *lv = ch->wm + (size_t)level * stride;
+		const uint32_t zeros = __ldg(zp + level);
 		if (joint) { // both statistics still in one range (which therefore holds >= 2 elements)
 			uint32_t bit_l, bit_r;
 			const uint32_t ol = mg_wm_rank1(lv, a.l, bit_l), orr = mg_wm_rank1(lv, a.r, bit_r);
@@ -221,21 +334,26 @@ __device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, u
 				split = true;
 			}
 		} else {
-			if (mg_wm_step(lv, zeros, a))
+			if (!a_done && mg_wm_step(lv, zeros, a))
 				v1 |= bitmask;
-			if (split && mg_wm_step(lv, zeros, b))
+			if (split && !b_done && mg_wm_step(lv, zeros, b))
 				v2 |= bitmask;
 		}
 	}
-	key1 = v1;
-	key2 = want2 ? v2 : v1;
+	// whatever walked all the way down holds a rank: look its value up
+	if (!a_done)
+		x1 = __ldg(ch->wm_sorted + v1);
+	if (!want2)
+		x2 = x1;
+	else if (!b_done)
+		x2 = __ldg(ch->wm_sorted + v2);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_dense_rowquery: one thread per row, every function from the index structures.
 //   SUM: avg / sum / nearest / size / exists   MM: min / max   Q: quantiles
 template <bool SUM, bool MM, bool Q>
-__global__ void __launch_bounds__(256) k_dense_rowquery(const DenseQuery q)
+__global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.count)
@@ -289,9 +407,9 @@ __global__ void __launch_bounds__(256) k_dense_rowquery(const DenseQuery q)
 					pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
 					const double index = __dmul_rn((double)(n - 1), pct);
 					const long long i1 = (long long)floor(index), i2 = (long long)ceil(index);
-					uint32_t k1, k2;
-					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, i2 != i1, k1, k2);
-					qv[k] = mg_interp(mg_fkey_inv(k1), mg_fkey_inv(k2), __dsub_rn(index, (double)i1));
+					float x1, x2;
+					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, i2 != i1, x1, x2);
+					qv[k] = mg_interp(x1, x2, __dsub_rn(index, (double)i1));
 				}
 			}
 		}

@@ -185,41 +185,88 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 			nchild = nparent;
 		}
 	}
-	// wavelet matrix over the non-NaN values
+	// wavelet matrix over the dense ranks of the non-NaN values
 	long long m = 0;
 	MG_CUDA(ctx, cudaMemcpy(&m, &dc.pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
 	dc.wm_m = m;
 	dc.wm_blocks = m / 32 + 1; // position m itself must be addressable
+	int nlevels = 0;
+	while (nlevels < 32 && (1ll << nlevels) < m)
+		++nlevels;
+	dc.wm_levels = nlevels;
 	uint2 *wm = nullptr;
 	uint32_t *zeros = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * MG_WM_LEVELS, &wm) || mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros))
+	float *sorted = nullptr;
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * (nlevels > 0 ? nlevels : 1), &wm) ||
+		mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros) || mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &sorted))
 		return 1;
 	dc.wm = wm;
 	dc.wm_zeros = zeros;
-	uint32_t *keys[2] = {nullptr, nullptr};
-	MG_CUDA(ctx, cudaMalloc(&keys[0], sizeof(uint32_t) * (size_t)(m > 0 ? m : 1)));
-	MG_CUDA(ctx, cudaMalloc(&keys[1], sizeof(uint32_t) * (size_t)(m > 0 ? m : 1)));
+	dc.wm_sorted = sorted;
+	const size_t mm = (size_t)(m > 0 ? m : 1);
+	uint32_t *keys[2] = {nullptr, nullptr}, *pos[2] = {nullptr, nullptr}, *d_zero = nullptr;
+	uint2 *scratch = nullptr;
+	MG_CUDA(ctx, cudaMalloc(&keys[0], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, cudaMalloc(&keys[1], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, cudaMalloc(&pos[0], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, cudaMalloc(&pos[1], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, cudaMalloc(&scratch, sizeof(uint2) * dc.wm_blocks));
+	MG_CUDA(ctx, cudaMalloc(&d_zero, sizeof(uint32_t)));
 	if (nbins) {
-		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, dc.pref, nbins, keys[0]);
+		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, dc.pref, nbins, keys[0], pos[0]);
 		MG_LAUNCH_CHECK(ctx);
 	}
-	std::vector<uint32_t> h_zeros(MG_WM_LEVELS);
-	for (int lv = 0; lv < MG_WM_LEVELS; ++lv) {
+	const unsigned gm = (unsigned)mg_div_up(m > 0 ? m : 1, 256), gb = (unsigned)mg_div_up(dc.wm_blocks, 256);
+	// (1) rank the values: LSD bit sort of (key, position) pairs, one stable partition per non-constant bit
+	int cur = 0;
+	for (int bit = 0; bit < 32 && m > 1; ++bit) {
+		uint32_t z = 0;
+		k_wm_bits<<<gb, 256>>>(keys[cur], m, bit, scratch, dc.wm_blocks);
+		MG_LAUNCH_CHECK(ctx);
+		k_wm_scan<<<1, 1024>>>(scratch, dc.wm_blocks, m, d_zero);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaMemcpy(&z, d_zero, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		if (z == 0 || z == (uint32_t)m)
+			continue; // constant bit: the partition is the identity
+		k_wm_sort_scatter<<<gm, 256>>>(keys[cur], pos[cur], m, scratch, z, keys[cur ^ 1], pos[cur ^ 1]);
+		MG_LAUNCH_CHECK(ctx);
+		cur ^= 1;
+	}
+	uint32_t *rank_of = keys[cur ^ 1]; // reuse: rank key of every compacted position, in bin order
+	if (m) {
+		k_wm_assign_ranks<<<gm, 256>>>(keys[cur], pos[cur], m, sorted, rank_of);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	// (2) the matrix: level lv partitions by bit (nlevels - 1 - lv) of the rank
+	uint32_t *wk[2] = {rank_of, keys[cur]};
+	std::vector<uint32_t> h_zeros(MG_WM_LEVELS, 0);
+	for (int lv = 0; lv < nlevels; ++lv) {
 		uint2 *level = wm + (size_t)lv * dc.wm_blocks;
-		const uint32_t *src = keys[lv & 1];
-		k_wm_bits<<<(unsigned)mg_div_up(dc.wm_blocks, 256), 256>>>(src, m, 31 - lv, level, dc.wm_blocks);
+		const uint32_t *src = wk[lv & 1];
+		if (lv >= 4 && (lv & 3) == 0) { // checkpoint: the rank keys in the order entering this level
+			uint32_t *ck = nullptr;
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &ck))
+				return 1;
+			MG_CUDA(ctx, cudaMemset(ck + m, 0xff, sizeof(uint32_t) * 16));
+			k_wm_ckpt<<<gm, 256>>>(src, m, sorted, ck);
+			MG_LAUNCH_CHECK(ctx);
+			dc.wm_ckpt[(lv >> 2) - 1] = ck;
+		}
+		k_wm_bits<<<gb, 256>>>(src, m, nlevels - 1 - lv, level, dc.wm_blocks);
 		MG_LAUNCH_CHECK(ctx);
 		k_wm_scan<<<1, 1024>>>(level, dc.wm_blocks, m, zeros + lv);
 		MG_LAUNCH_CHECK(ctx);
 		MG_CUDA(ctx, cudaMemcpy(&h_zeros[lv], zeros + lv, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-		if (m) {
-			k_wm_scatter<<<(unsigned)mg_div_up(m, 256), 256>>>(src, m, level, h_zeros[lv], keys[(lv + 1) & 1]);
-			MG_LAUNCH_CHECK(ctx);
-		}
+		k_wm_scatter<<<gm, 256>>>(src, m, level, h_zeros[lv], wk[(lv + 1) & 1]);
+		MG_LAUNCH_CHECK(ctx);
 	}
 	MG_CUDA(ctx, cudaDeviceSynchronize());
 	cudaFree(keys[0]);
 	cudaFree(keys[1]);
+	cudaFree(pos[0]);
+	cudaFree(pos[1]);
+	cudaFree(scratch);
+	cudaFree(d_zero);
 	return 0;
 }
 
