@@ -21,6 +21,8 @@ struct DenseChrom {
 	const Pref *pref;
 	int64_t nbins;
 	double abs_sum; // sum |v| over the chromosome: scale of the prefix rounding error (cancellation guard)
+	const double *pref2; // pref2[i] = sum of squares of the non-NaN vals[0..i) (stddev)
+	double sq_sum;       // sum v^2 over the chromosome
 	// index structures (dense_index.cuh)
 	const float *pmax[MG_PYR_MAX];
 	const float *pmin[MG_PYR_MAX];
@@ -99,12 +101,12 @@ __device__ __forceinline__ T mg_block_excl_scan(T v, T *smem /* >= 32 entries */
 
 // pass 1: +-inf -> NaN in place, per-tile {sum, count, abs sum}
 __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_clean_reduce(float *vals, int64_t nbins, double *tile_sum, long long *tile_cnt,
-																	   double *tile_abs)
+																	   double *tile_abs, double *tile_sq)
 {
 	__shared__ double sd[33];
 	__shared__ long long sc[33];
 	const int64_t base = (int64_t)blockIdx.x * MG_ST_TILE + (int64_t)threadIdx.x * MG_ST_PER_THREAD;
-	double s = 0, a = 0;
+	double s = 0, a = 0, q = 0;
 	long long c = 0;
 #pragma unroll
 	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
@@ -118,63 +120,72 @@ __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_clean_reduce(float *val
 			if (!isnan(v)) {
 				s += (double)v;
 				a += fabs((double)v);
+				q = fma((double)v, (double)v, q);
 				++c;
 			}
 		}
 	}
-	double ts, ta;
+	double ts, ta, tq;
 	long long tc;
 	mg_block_excl_scan<double>(s, sd, ts);
 	mg_block_excl_scan<double>(a, sd, ta);
+	mg_block_excl_scan<double>(q, sd, tq);
 	mg_block_excl_scan<long long>(c, sc, tc);
 	if (threadIdx.x == 0) {
 		tile_sum[blockIdx.x] = ts;
 		tile_cnt[blockIdx.x] = tc;
 		tile_abs[blockIdx.x] = ta;
+		tile_sq[blockIdx.x] = tq;
 	}
 }
 
 // pass 2 (one block): exclusive scan of the tile totals in place; total abs sum -> *abs_total
-__global__ void __launch_bounds__(1024) k_dense_tile_scan(double *tile_sum, long long *tile_cnt, const double *tile_abs, int64_t ntiles,
-														  double *abs_total)
+__global__ void __launch_bounds__(1024) k_dense_tile_scan(double *tile_sum, long long *tile_cnt, const double *tile_abs, double *tile_sq,
+														  int64_t ntiles, double *abs_total /* [0] = sum |v|, [1] = sum v^2 */)
 {
 	__shared__ double sd[33];
 	__shared__ long long sc[33];
 	const int64_t chunk = (ntiles + blockDim.x - 1) / blockDim.x;
 	const int64_t lo = (int64_t)threadIdx.x * chunk, hi = min(lo + chunk, ntiles);
-	double s = 0, a = 0;
+	double s = 0, a = 0, q = 0;
 	long long c = 0;
 	for (int64_t i = lo; i < hi; ++i) {
 		s += tile_sum[i];
 		c += tile_cnt[i];
 		a += tile_abs[i];
+		q += tile_sq[i];
 	}
-	double ts, ta;
+	double ts, ta, tq;
 	long long tc;
 	double s0 = mg_block_excl_scan<double>(s, sd, ts);
 	mg_block_excl_scan<double>(a, sd, ta);
+	double q0 = mg_block_excl_scan<double>(q, sd, tq);
 	long long c0 = mg_block_excl_scan<long long>(c, sc, tc);
 	for (int64_t i = lo; i < hi; ++i) {
-		double vs = tile_sum[i];
+		double vs = tile_sum[i], vq = tile_sq[i];
 		long long vc = tile_cnt[i];
 		tile_sum[i] = s0;
 		tile_cnt[i] = c0;
+		tile_sq[i] = q0;
 		s0 += vs;
 		c0 += vc;
+		q0 += vq;
 	}
-	if (threadIdx.x == 0)
-		*abs_total = ta;
+	if (threadIdx.x == 0) {
+		abs_total[0] = ta;
+		abs_total[1] = tq;
+	}
 }
 
 // pass 3: per-bin prefix entries. pref[i] = totals over vals[0..i); pref[nbins] is the chromosome total.
 __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const float *vals, int64_t nbins, const double *tile_sum,
-																	   const long long *tile_cnt, Pref *pref)
+																	   const long long *tile_cnt, const double *tile_sq, Pref *pref, double *pref2)
 {
 	__shared__ double sd[33];
 	__shared__ long long sc[33];
 	const int64_t base = (int64_t)blockIdx.x * MG_ST_TILE + (int64_t)threadIdx.x * MG_ST_PER_THREAD;
 	float v[MG_ST_PER_THREAD];
-	double s = 0;
+	double s = 0, q = 0;
 	long long c = 0;
 #pragma unroll
 	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
@@ -182,12 +193,14 @@ __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const floa
 		v[j] = i < nbins ? vals[i] : mg_nanf();
 		if (!isnan(v[j])) {
 			s += (double)v[j];
+			q = fma((double)v[j], (double)v[j], q);
 			++c;
 		}
 	}
-	double ts;
+	double ts, tq;
 	long long tc;
 	double s0 = tile_sum[blockIdx.x] + mg_block_excl_scan<double>(s, sd, ts);
+	double q0 = tile_sq[blockIdx.x] + mg_block_excl_scan<double>(q, sd, tq);
 	long long c0 = tile_cnt[blockIdx.x] + mg_block_excl_scan<long long>(c, sc, tc);
 #pragma unroll
 	for (int j = 0; j < MG_ST_PER_THREAD; ++j) {
@@ -197,9 +210,11 @@ __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const floa
 			p.sum = s0;
 			p.cnt = c0;
 			pref[i] = p;
+			pref2[i] = q0;
 		}
 		if (!isnan(v[j])) {
 			s0 += (double)v[j];
+			q0 = fma((double)v[j], (double)v[j], q0);
 			++c0;
 		}
 	}

@@ -352,14 +352,18 @@ __device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, u
 // ------------------------------------------------------------------------------------------------------------------
 // k_dense_rowquery: one thread per row, every function from the index structures.
 //   SUM: avg / sum / nearest / size / exists   MM: min / max   Q: quantiles
-template <bool SUM, bool MM, bool Q>
+//   SD: stddev = sqrt(M2 / (n - 1)) with M2 = S2 - S1^2 / n from the prefix sums of v and v^2. When that difference has
+//       lost too many digits (low variance against the mean, or a window that is tiny against the chromosome's running
+//       sum of squares) the window is re-read and Welford's update is run in bin order, i.e. the reference's arithmetic.
+#define MG_SD_DIRECT_BINS 8
+template <bool SUM, bool MM, bool Q, bool SD>
 __global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.count)
 		return;
 	DenseWin w;
-	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan();
+	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan();
 	double qv[MG_MAX_Q];
 #pragma unroll
 	for (int k = 0; k < MG_MAX_Q; ++k)
@@ -369,10 +373,30 @@ __global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
 		long long n = 0;
 		if (nb > 0) {
 			Pref a, b;
-			if (SUM || Q) {
+			if (SUM || Q || SD) {
 				a = mg_ld_pref(w.ch->pref + w.sbin);
 				b = mg_ld_pref(w.ch->pref + w.ebin);
 				n = b.cnt - a.cnt;
+			}
+			if (SD && n > 1) {
+				const double S1 = b.sum - a.sum, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
+				double m2 = S2 - S1 * S1 / (double)n;
+				// trust the difference only while it keeps ~9 significant digits
+				if (nb <= MG_SD_DIRECT_BINS || !(m2 > S2 * 1e-7) || !(m2 > w.ch->sq_sum * 1e-7)) {
+					long long c = 0;
+					double mean = 0;
+					m2 = 0;
+					for (int64_t t = w.sbin; t < w.ebin; ++t) { // src/GenomeTrackFixedBin.cpp:912-917
+						const float v = __ldg(w.ch->vals + t);
+						if (!isnan(v)) {
+							++c;
+							const double d = (double)v - mean;
+							mean += d / (double)c;
+							m2 += d * ((double)v - mean);
+						}
+					}
+				}
+				sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
 			}
 			if (SUM) {
 				double S = b.sum - a.sum;
@@ -427,6 +451,8 @@ __global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
 		if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
 		if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, mx);
 	}
+	if (SD)
+		mg_st_stream(q.out[MG_STDDEV] + i, sd);
 	if (Q)
 		for (int k = 0; k < q.nq; ++k)
 			mg_st_stream(q.q_out[k] + i, qv[k]);

@@ -149,7 +149,11 @@ extern "C" int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out)
 	MG_REQUIRE(ctx, t, "out of memory");
 	t->bin_size = bin_size;
 	t->nchroms = ctx->nchroms;
-	t->h_table.assign(ctx->nchroms, DenseChrom{nullptr, nullptr, 0, 0.});
+	{
+		DenseChrom z;
+		memset(&z, 0, sizeof(z));
+		t->h_table.assign(ctx->nchroms, z);
+	}
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ctx->nchroms, &t->d_table)) {
 		delete t;
 		return 1;
@@ -289,30 +293,40 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	if (nbins)
 		MG_CUDA(ctx, cudaMemcpy(vals, h_bins, sizeof(float) * nbins, cudaMemcpyHostToDevice));
 	const int64_t ntiles = mg_div_up(nbins + 1, MG_ST_TILE); // +1: the closing entry pref[nbins]
-	double *tile_sum = nullptr, *tile_abs = nullptr, *abs_total = nullptr;
+	double *tile_sum = nullptr, *tile_abs = nullptr, *tile_sq = nullptr, *abs_total = nullptr, *pref2 = nullptr;
 	long long *tile_cnt = nullptr;
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref2))
+		return 1;
 	MG_CUDA(ctx, cudaMalloc(&tile_sum, sizeof(double) * ntiles));
 	MG_CUDA(ctx, cudaMalloc(&tile_abs, sizeof(double) * ntiles));
+	MG_CUDA(ctx, cudaMalloc(&tile_sq, sizeof(double) * ntiles));
 	MG_CUDA(ctx, cudaMalloc(&tile_cnt, sizeof(long long) * ntiles));
-	MG_CUDA(ctx, cudaMalloc(&abs_total, sizeof(double)));
-	k_dense_clean_reduce<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_abs);
+	MG_CUDA(ctx, cudaMalloc(&abs_total, sizeof(double) * 2));
+	k_dense_clean_reduce<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_abs, tile_sq);
 	MG_LAUNCH_CHECK(ctx);
-	k_dense_tile_scan<<<1, 1024>>>(tile_sum, tile_cnt, tile_abs, ntiles, abs_total);
+	k_dense_tile_scan<<<1, 1024>>>(tile_sum, tile_cnt, tile_abs, tile_sq, ntiles, abs_total);
 	MG_LAUNCH_CHECK(ctx);
-	k_dense_prefix_write<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, pref);
+	k_dense_prefix_write<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_sq, pref, pref2);
 	MG_LAUNCH_CHECK(ctx);
 	DenseChrom dc;
 	memset(&dc, 0, sizeof(dc));
 	dc.vals = vals;
 	dc.pref = pref;
 	dc.nbins = nbins;
-	MG_CUDA(ctx, cudaMemcpy(&dc.abs_sum, abs_total, sizeof(double), cudaMemcpyDeviceToHost));
+	dc.pref2 = pref2;
+	{
+		double tot[2] = {0, 0};
+		MG_CUDA(ctx, cudaMemcpy(tot, abs_total, sizeof(tot), cudaMemcpyDeviceToHost));
+		dc.abs_sum = tot[0];
+		dc.sq_sum = tot[1];
+	}
 	if (mg_dense_build_index(ctx, t, dc))
 		return 1;
 	t->h_table[chromid] = dc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &dc, sizeof(DenseChrom), cudaMemcpyHostToDevice));
 	cudaFree(tile_sum);
 	cudaFree(tile_abs);
+	cudaFree(tile_sq);
 	cudaFree(tile_cnt);
 	cudaFree(abs_total);
 	return 0;
@@ -513,18 +527,21 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 	const bool want_mm = q.out[MG_MIN] || q.out[MG_MAX];
 	if (!need_sweep) {
 		k_dense_prefix<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
-	} else if (!q.out[MG_STDDEV] && !ctx->force_sweep) {
+	} else if (!ctx->force_sweep) {
 		// everything else comes from the index structures, one thread per row
 		const unsigned grid = (unsigned)mg_div_up(q.count, 256);
-		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0);
+		const bool want_sd = q.out[MG_STDDEV] != nullptr;
+		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0) | (want_sd ? 8 : 0);
+#define MG_RQ_CASE(K)                                                                                                    \
+	case K:                                                                                                             \
+		k_dense_rowquery<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, 256, 0, st>>>(q);           \
+		break;
 		switch (key) {
-		case 2: k_dense_rowquery<false, true, false><<<grid, 256, 0, st>>>(q); break;
-		case 3: k_dense_rowquery<true, true, false><<<grid, 256, 0, st>>>(q); break;
-		case 4: k_dense_rowquery<false, false, true><<<grid, 256, 0, st>>>(q); break;
-		case 5: k_dense_rowquery<true, false, true><<<grid, 256, 0, st>>>(q); break;
-		case 6: k_dense_rowquery<false, true, true><<<grid, 256, 0, st>>>(q); break;
-		default: k_dense_rowquery<true, true, true><<<grid, 256, 0, st>>>(q); break;
+			MG_RQ_CASE(1) MG_RQ_CASE(2) MG_RQ_CASE(3) MG_RQ_CASE(4) MG_RQ_CASE(5) MG_RQ_CASE(6) MG_RQ_CASE(7) MG_RQ_CASE(8) MG_RQ_CASE(9)
+			MG_RQ_CASE(10) MG_RQ_CASE(11) MG_RQ_CASE(12) MG_RQ_CASE(13) MG_RQ_CASE(14) MG_RQ_CASE(15)
+		default: break;
 		}
+#undef MG_RQ_CASE
 	} else {
 		const int64_t blocks_needed = mg_div_up(q.count, MG_SW_WARPS);
 		const int64_t cap = (int64_t)ctx->sm_count * 32; // grid-stride beyond that

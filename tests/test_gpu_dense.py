@@ -133,3 +133,31 @@ def test_sweep_and_index_paths_agree(gpu_ctx, dense_testdb):
         assert_close(idx[0], swp[0], RTOL, f"{c} avg")
         for k in range(1, len(funcs)):
             assert_same(idx[k], swp[k], f"{c} {funcs[k]}")
+
+
+def test_stddev_prefix_squares_guard():
+    """stddev comes from prefix sums of v and v^2; low-variance / constant / tiny windows must fall back to the exact
+    in-order Welford update instead of returning a cancelled difference."""
+    from misha_b200 import gpu
+    size = 20 * 60000
+    ctx2 = gpu.Context([size])
+    try:
+        rng = np.random.default_rng(12)
+        bins = (1000 + rng.normal(0, 1e-3, size // 20)).astype(np.float32)  # mean / sd = 1e6
+        bins[20000:30000] = 7.25                                              # constant stretch: sd == 0 exactly
+        bins[30000:40000] = rng.lognormal(size=10000).astype(np.float32)      # ordinary data
+        bins[35000:35100] = np.nan
+        bins[50000] = 3e18                                                    # one huge value poisons the running sum of squares
+        t = gpu.DenseTrack(ctx2, 20)
+        t.stage(0, bins)
+        s = np.sort(rng.integers(0, size - 20, 6000))
+        e = np.minimum(s + rng.choice([20, 40, 200, 2000, 20000, 400000], 6000), size)
+        rows = ctx2.rows_upload(np.zeros(len(s), np.int32), s, e)
+        got = t.window(rows, ["stddev", "avg"])
+        exp = port.dense_window(bins, 20, size, s, e, 0, 0, 0.5, ("stddev", "avg"))
+        assert_close(got[0], exp["stddev"], RTOL, "stddev")
+        assert_close(got[1], exp["avg"], RTOL, "avg")
+        const = (s >= 20000 * 20) & (e <= 30000 * 20) & (e - s > 20)
+        assert const.any() and np.all(got[0][const] == 0.0)
+    finally:
+        ctx2.close()
