@@ -74,7 +74,9 @@ void mg_shutdown(mg_ctx *ctx);
 const char *mg_last_error(const mg_ctx *ctx); /* ctx may be NULL: error of the last failed mg_init in this thread */
 int mg_sync(mg_ctx *ctx, void *stream);
 /* Tuning / ablation switches. "force_sweep" = 1 routes min / max / quantile through the warp-per-row sweep kernel
- * instead of the per-chromosome index structures (same results; used by tests and profiling). */
+ * instead of the per-chromosome index structures (same results; used by tests and profiling). "pipe_chunk_rows" = rows per
+ * slot of the host-buffer pipeline (default 2^19). "zero_copy" = 1 lets mg_h_* kernels read / write pinned host buffers
+ * directly instead of staging them through the DMA pipeline (default 0: measured slower on B200). */
 int mg_set_option(mg_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this ctx has launched since mg_init (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const mg_ctx *ctx);

@@ -79,6 +79,16 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->force_sweep = value != 0;
 		return 0;
 	}
+	if (name && !strcmp(name, "zero_copy")) {
+		ctx->zero_copy = value != 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "pipe_chunk_rows")) {
+		if (value < 1024)
+			return mg_fail(ctx, "mg_set_option: pipe_chunk_rows must be >= 1024");
+		ctx->pipe_chunk_rows = value;
+		return 0;
+	}
 	return mg_fail(ctx, "mg_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
@@ -597,7 +607,47 @@ extern "C" int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, cons
 								 double *const *h_out)
 {
 	MG_REQUIRE(ctx, n >= 0 && nfuncs > 0 && nfuncs <= 32, "mg_h_dense_window: bad arguments");
-	const int64_t CHUNK = 1 << 20; // rows per pipeline slot
+	if (ctx->zero_copy && n > 0) {
+		// Every buffer pinned (cudaMallocHost / cudaHostRegister / torch pin_memory)? Then the kernel reads the rows and
+		// writes the result columns directly over PCIe: reads and posted writes overlap in both directions and there is no
+		// staging copy at all. Otherwise fall through to the chunked copy pipeline.
+		const void *hp[3 + 32] = {h_chrom, h_start, h_end};
+		for (int k = 0; k < nfuncs; ++k)
+			hp[3 + k] = h_out[k];
+		void *dp[3 + 32];
+		bool pinned = true;
+		for (int k = 0; k < 3 + nfuncs && pinned; ++k) {
+			cudaPointerAttributes at;
+			if (cudaPointerGetAttributes(&at, hp[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+				cudaGetLastError();
+				pinned = false;
+			} else
+				dp[k] = at.devicePointer;
+		}
+		if (pinned) {
+			MG_CUDA(ctx, cudaSetDevice(ctx->device));
+			if (mg_pipe_prepare(ctx, 1))
+				return 1;
+			cudaStream_t st = ctx->pipe_stream[0];
+			mg_rows rows;
+			rows.src.kind = 0;
+			rows.src.n = n;
+			rows.src.chrom = (const int32_t *)dp[0];
+			rows.src.start = (const int64_t *)dp[1];
+			rows.src.end = (const int64_t *)dp[2];
+			double *d_cols[32];
+			for (int k = 0; k < nfuncs; ++k)
+				d_cols[k] = (double *)dp[3 + k];
+			DenseQuery q;
+			bool need_sweep;
+			if (mg_fill_dense_query(ctx, t, &rows, 0, n, sshift, eshift, nfuncs, funcs, params, d_cols, q, need_sweep) ||
+				mg_launch_dense(ctx, q, need_sweep, st))
+				return 1;
+			MG_CUDA(ctx, cudaStreamSynchronize(st));
+			return 0;
+		}
+	}
+	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows per pipeline slot
 	const int64_t slot_bytes = CHUNK * (20 + 8 * (int64_t)nfuncs);
 	if (mg_pipe_prepare(ctx, slot_bytes))
 		return 1;
