@@ -123,6 +123,9 @@ def run_ours(args):
     sizes = [s for _, s in chroms]
     ctx = gpu.Context(sizes, device=local)
     stream = torch.cuda.current_stream().cuda_stream
+    for opt in os.environ.get("MG_OPTIONS", "").split(","):  # experiments: MG_OPTIONS=name=value,...
+        if "=" in opt:
+            ctx.set_option(opt.split("=")[0], int(opt.split("=")[1]))
 
     # ---- stage the track once (one-time cost, reported separately) ----
     t0 = time.perf_counter()

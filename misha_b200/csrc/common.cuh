@@ -28,6 +28,8 @@ struct mg_ctx {
 	int64_t pipe_chunk_rows = 1 << 19; // rows per slot of the host-buffer pipeline (measured best of 2^17..2^22 on B200 / PCIe Gen5)
 	bool zero_copy = false; // host-buffer entry points: kernels read rows / write columns straight in pinned host memory.
 	                        // Measured SLOWER than the 3-slot DMA pipeline on B200 (5.9 vs 5.3 ms for C3), hence off by default.
+	bool block_wm = true;    // quantiles of windows <= MG_BW_S bins walk the block-local wavelet matrices (off: ablation / tests of the
+	                         // chromosome-wide matrix)
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;
 	// internal streams + staging buffers of the host-buffer entry points (lazily created)

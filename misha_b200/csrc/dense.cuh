@@ -33,6 +33,7 @@ struct DenseChrom {
 	int wm_levels;            // ceil(log2(wm_m)): rank keys are balanced, every level halves a range
 	const float *wm_sorted;   // the non-NaN values in ascending order: value of rank r
 	const uint32_t *wm_ckpt[7]; // rank keys in the order ENTERING levels 4, 8, ..., 28: a walk whose range shrank to <= 8 finishes here
+	const uint8_t *bw;        // block-local wavelet matrices (dense_blockwm.cuh), one record per half-overlapping block
 };
 
 struct mg_dense {
@@ -55,6 +56,7 @@ struct DenseQuery {
 	uint32_t bin_size;
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
 	int nq;
+	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
 };

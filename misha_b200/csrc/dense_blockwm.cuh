@@ -1,0 +1,171 @@
+// dense_blockwm.cuh -- block-local wavelet matrices: the quantile index for windows of up to MG_BW_S bins.
+//
+// The chromosome is cut into blocks of B = 2^LB bins that overlap by half (block b covers bins [b*S, b*S + B), S = B/2),
+// so every window of <= S bins lies inside block floor(sbin / S). Inside a block the bins are ranked 0..B-1 by
+// (value, position) with NaN (and the padding past the chromosome end) ranked last; the ranks are a permutation of
+// [0, B), therefore
+//   * a wavelet matrix over the ranks has LB levels and every level has exactly B/2 zeros -- no per-level constant;
+//   * the k-th smallest non-NaN value of a window is the k-th smallest RANK of the window's positions (k < n, n = the
+//     window's non-NaN count from the prefix entries) -- NaNs never need compacting;
+//   * the (k+1)-th is the next larger rank whose position lies in the window: a short scan of pos_of_rank.
+// A block record is LB levels x B/32 units {uint32 ones before the unit, uint32 bits} followed by pos_of_rank[B] (uint16).
+// Rows sorted by position walk the same 5.6 KB of levels as their neighbours: the walk runs out of L1 instead of paying
+// one L2/HBM round trip per level as the chromosome-wide matrix (dense_index.cuh) does. The value of a rank is read from
+// the track itself: vals[b*S + pos_of_rank[rank]].
+#pragma once
+#include "common.cuh"
+#include "dense.cuh"
+
+#define MG_BW_LB 11
+#define MG_BW_B (1 << MG_BW_LB)
+#define MG_BW_S (MG_BW_B / 2)
+#define MG_BW_UNITS (MG_BW_B / 32)
+#define MG_BW_LEVEL_BYTES (MG_BW_UNITS * 8)
+#define MG_BW_RECORD_BYTES (MG_BW_LB * MG_BW_LEVEL_BYTES + MG_BW_B * 2)
+#define MG_BW_BUILD_THREADS 1024
+#define MG_BW_PER_THREAD (MG_BW_B / MG_BW_BUILD_THREADS)
+
+__device__ __forceinline__ uint32_t mg_bw_key(float v)
+{
+	if (isnan(v))
+		return 0xffffffffu;
+	const uint32_t b = __float_as_uint(v);
+	return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+// one CTA per block: rank the block's bins (bitonic sort of (key, position)), then build the LB levels in shared memory
+__global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *__restrict__ vals, int64_t nbins, uint8_t *__restrict__ records)
+{
+	__shared__ unsigned long long skey[MG_BW_B];
+	__shared__ uint16_t sa[MG_BW_B], sb[MG_BW_B];
+	__shared__ uint32_t sbits[MG_BW_UNITS], scnt[MG_BW_UNITS];
+	const int t = threadIdx.x;
+	const int64_t base = (int64_t)blockIdx.x * MG_BW_S;
+	uint8_t *rec = records + (size_t)blockIdx.x * MG_BW_RECORD_BYTES;
+#pragma unroll
+	for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
+		const int e = t + j * MG_BW_BUILD_THREADS;
+		const int64_t i = base + e;
+		const float v = i < nbins ? vals[i] : mg_nanf();
+		skey[e] = ((unsigned long long)mg_bw_key(v) << 32) | (unsigned)e;
+	}
+	__syncthreads();
+	for (int k = 2; k <= MG_BW_B; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int p = t; p < MG_BW_B / 2; p += MG_BW_BUILD_THREADS) {
+				const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), ixj = i | j;
+				const unsigned long long a = skey[i], b = skey[ixj];
+				if ((a > b) == ((i & k) == 0)) {
+					skey[i] = b;
+					skey[ixj] = a;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	uint16_t *pos_of_rank = reinterpret_cast<uint16_t *>(rec + MG_BW_LB * MG_BW_LEVEL_BYTES);
+	uint16_t *cur = sa, *nxt = sb;
+#pragma unroll
+	for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
+		const int r = t + j * MG_BW_BUILD_THREADS;
+		const uint32_t pos = (uint32_t)skey[r];
+		pos_of_rank[r] = (uint16_t)pos;
+		cur[pos] = (uint16_t)r;
+	}
+	__syncthreads();
+	uint2 *level = reinterpret_cast<uint2 *>(rec);
+	for (int lv = 0; lv < MG_BW_LB; ++lv, level += MG_BW_UNITS) {
+		const int shift = MG_BW_LB - 1 - lv;
+		uint32_t myword[MG_BW_PER_THREAD];
+#pragma unroll
+		for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
+			const int e = t + j * MG_BW_BUILD_THREADS;
+			myword[j] = __ballot_sync(0xffffffffu, (cur[e] >> shift) & 1);
+			if ((t & 31) == 0)
+				sbits[e >> 5] = myword[j];
+		}
+		__syncthreads();
+		if (t < 32) { // exclusive scan of the MG_BW_UNITS word popcounts by one warp
+			uint32_t c[MG_BW_UNITS / 32], s = 0;
+#pragma unroll
+			for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
+				c[j] = __popc(sbits[t * (MG_BW_UNITS / 32) + j]);
+				s += c[j];
+			}
+			uint32_t incl = s;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+				if (t >= d)
+					incl += o;
+			}
+			uint32_t run = incl - s;
+#pragma unroll
+			for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
+				scnt[t * (MG_BW_UNITS / 32) + j] = run;
+				run += c[j];
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
+			const int e = t + j * MG_BW_BUILD_THREADS;
+			const uint32_t bits = myword[j], lane = t & 31;
+			const uint32_t ones_before = scnt[e >> 5] + __popc(bits & ((1u << lane) - 1u));
+			const uint16_t v = cur[e];
+			nxt[((bits >> lane) & 1u) ? MG_BW_S + ones_before : (uint32_t)e - ones_before] = v;
+			if (lane == 0)
+				level[e >> 5] = make_uint2(scnt[e >> 5], bits);
+		}
+		__syncthreads();
+		uint16_t *tmp = cur;
+		cur = nxt;
+		nxt = tmp;
+	}
+}
+
+// ones among positions [0, i) of a level, 0 <= i < B
+__device__ __forceinline__ uint32_t mg_bw_rank_lo(const uint2 *__restrict__ lv, uint32_t i)
+{
+	const uint2 u = __ldg(lv + (i >> 5));
+	return u.x + __popc(u.y & ((1u << (i & 31u)) - 1u));
+}
+// ones among positions [0, i) of a level, 1 <= i <= B (looks at the unit of position i - 1, so i == B needs no padding unit)
+__device__ __forceinline__ uint32_t mg_bw_rank_hi(const uint2 *__restrict__ lv, uint32_t i)
+{
+	const uint32_t j = i - 1u;
+	const uint2 u = __ldg(lv + (j >> 5));
+	return u.x + __popc(u.y << (~j & 31u));
+}
+
+// k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l; with want2 (k + 1 < n) also the
+// (k+1)-th. vals_block = the track at the block's first bin.
+__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l, uint32_t r, uint32_t k,
+											 bool want2, float &x1, float &x2)
+{
+	const uint2 *lv = reinterpret_cast<const uint2 *>(rec);
+	const uint32_t l0 = l, len = r - l;
+	uint32_t rank = 0;
+#pragma unroll
+	for (int level = 0; level < MG_BW_LB; ++level, lv += MG_BW_UNITS) {
+		const uint32_t ol = mg_bw_rank_lo(lv, l), orr = mg_bw_rank_hi(lv, r);
+		const uint32_t nz = (r - l) - (orr - ol);
+		const bool one = k >= nz;
+		l = one ? MG_BW_S + ol : l - ol;
+		r = one ? MG_BW_S + orr : r - orr;
+		k = one ? k - nz : k;
+		rank = (rank << 1) | (one ? 1u : 0u);
+	}
+	const uint16_t *pos_of_rank = reinterpret_cast<const uint16_t *>(rec + MG_BW_LB * MG_BW_LEVEL_BYTES);
+	x1 = __ldg(vals_block + __ldg(pos_of_rank + rank));
+	x2 = x1;
+	if (want2) {
+		// the next larger rank whose position lies in the window; exists because k + 1 < n
+		uint32_t p;
+		do {
+			++rank;
+			p = __ldg(pos_of_rank + rank);
+		} while (p - l0 >= len && rank < MG_BW_B - 1);
+		x2 = __ldg(vals_block + p);
+	}
+}

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "dense.cuh"
+#include "dense_blockwm.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // pyramids
@@ -271,7 +272,7 @@ __device__ __forceinline__ void mg_wm_finish(const uint32_t *__restrict__ ckpt, 
 // RANK of the k-th smallest value (0-based) among compacted positions [l, r), r > l, k < r - l; with want2 (requires
 // k + 1 < r - l) also of the (k+1)-th. The two order statistics share one walk until the level where they part; every walk stops at the
 // first checkpoint level (4, 8, ..., 28) where its range holds <= 8 keys.
-__device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
+__device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
 {
 	uint32_t key1, key2;
 	const size_t stride = (size_t)ch->wm_blocks;
@@ -357,86 +358,73 @@ __device__ __forceinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, u
 //       sum of squares) the window is re-read and Welford's update is run in bin order, i.e. the reference's arithmetic.
 #define MG_SD_DIRECT_BINS 8
 template <bool SUM, bool MM, bool Q, bool SD>
-__global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
+__global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.count)
 		return;
 	DenseWin w;
 	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan();
-	double qv[MG_MAX_Q];
-#pragma unroll
-	for (int k = 0; k < MG_MAX_Q; ++k)
-		qv[k] = mg_nan();
-	if (mg_dense_win(q, q.first + i, w)) {
-		const int64_t nb = w.ebin - w.sbin;
-		long long n = 0;
-		if (nb > 0) {
-			Pref a, b;
-			if (SUM || Q || SD) {
-				a = mg_ld_pref(w.ch->pref + w.sbin);
-				b = mg_ld_pref(w.ch->pref + w.ebin);
-				n = b.cnt - a.cnt;
-			}
-			if (SD && n > 1) {
-				const double S1 = b.sum - a.sum, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
-				double m2 = S2 - S1 * S1 / (double)n;
-				// trust the difference only while it keeps ~9 significant digits
-				if (nb <= MG_SD_DIRECT_BINS || !(m2 > S2 * 1e-7) || !(m2 > w.ch->sq_sum * 1e-7)) {
-					long long c = 0;
-					double mean = 0;
-					m2 = 0;
-					for (int64_t t = w.sbin; t < w.ebin; ++t) { // src/GenomeTrackFixedBin.cpp:912-917
-						const float v = __ldg(w.ch->vals + t);
-						if (!isnan(v)) {
-							++c;
-							const double d = (double)v - mean;
-							mean += d / (double)c;
-							m2 += d * ((double)v - mean);
-						}
+	const bool ok = mg_dense_win(q, q.first + i, w);
+	const int64_t nb = ok ? w.ebin - w.sbin : 0;
+	long long n = 0;
+	Pref a, b;
+	a.cnt = b.cnt = 0;
+	if (nb > 0) {
+		if (SUM || Q || SD) {
+			a = mg_ld_pref(w.ch->pref + w.sbin);
+			b = mg_ld_pref(w.ch->pref + w.ebin);
+			n = b.cnt - a.cnt;
+		}
+		if (SD && n > 1) {
+			const double S1 = b.sum - a.sum, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
+			double m2 = S2 - S1 * S1 / (double)n;
+			// trust the difference only while it keeps ~9 significant digits
+			if (nb <= MG_SD_DIRECT_BINS || !(m2 > S2 * 1e-7) || !(m2 > w.ch->sq_sum * 1e-7)) {
+				long long c = 0;
+				double mean = 0;
+				m2 = 0;
+				for (int64_t t = w.sbin; t < w.ebin; ++t) { // src/GenomeTrackFixedBin.cpp:912-917
+					const float v = __ldg(w.ch->vals + t);
+					if (!isnan(v)) {
+						++c;
+						const double d = (double)v - mean;
+						mean += d / (double)c;
+						m2 += d * ((double)v - mean);
 					}
 				}
-				sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
 			}
-			if (SUM) {
-				double S = b.sum - a.sum;
-				if (nb <= MG_PREFIX_DIRECT_BINS || (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)) {
-					S = 0;
-					for (int64_t t = w.sbin; t < w.ebin; ++t) {
-						const float v = __ldg(w.ch->vals + t);
-						if (!isnan(v))
-							S += (double)v;
-					}
-				}
-				if (n > 0) {
-					avg = mg_f2d(S / (double)n);
-					sum = mg_f2d(S);
+			sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
+		}
+		if (SUM) {
+			double S = b.sum - a.sum;
+			if (nb <= MG_PREFIX_DIRECT_BINS || (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)) {
+				S = 0;
+				for (int64_t t = w.sbin; t < w.ebin; ++t) {
+					const float v = __ldg(w.ch->vals + t);
+					if (!isnan(v))
+						S += (double)v;
 				}
 			}
-			if (MM) {
-				if (q.out[MG_MAX]) {
-					const float v = mg_pyr_query<true>(w.ch, w.sbin, w.ebin);
-					if (v != __int_as_float(0xff800000))
-						mx = (double)v;
-				}
-				if (q.out[MG_MIN]) {
-					const float v = mg_pyr_query<false>(w.ch, w.sbin, w.ebin);
-					if (v != __int_as_float(0x7f800000))
-						mn = (double)v;
-				}
-			}
-			if (Q && n > 0) {
-				for (int k = 0; k < q.nq; ++k) {
-					double pct = q.q_pct[k];
-					pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
-					const double index = __dmul_rn((double)(n - 1), pct);
-					const long long i1 = (long long)floor(index), i2 = (long long)ceil(index);
-					float x1, x2;
-					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, i2 != i1, x1, x2);
-					qv[k] = mg_interp(x1, x2, __dsub_rn(index, (double)i1));
-				}
+			if (n > 0) {
+				avg = mg_f2d(S / (double)n);
+				sum = mg_f2d(S);
 			}
 		}
+		if (MM) {
+			if (q.out[MG_MAX]) {
+				const float v = mg_pyr_query<true>(w.ch, w.sbin, w.ebin);
+				if (v != __int_as_float(0xff800000))
+					mx = (double)v;
+			}
+			if (q.out[MG_MIN]) {
+				const float v = mg_pyr_query<false>(w.ch, w.sbin, w.ebin);
+				if (v != __int_as_float(0x7f800000))
+					mn = (double)v;
+			}
+		}
+	}
+	if (ok) {
 		size = (double)n;
 		exists = n > 0 ? 1. : 0.;
 	}
@@ -453,7 +441,29 @@ __global__ void __launch_bounds__(256, 5) k_dense_rowquery(const DenseQuery q)
 	}
 	if (SD)
 		mg_st_stream(q.out[MG_STDDEV] + i, sd);
-	if (Q)
-		for (int k = 0; k < q.nq; ++k)
-			mg_st_stream(q.q_out[k] + i, qv[k]);
+	if (Q) {
+		// every quantile column is stored as soon as it is known (a per-thread array indexed by k would live in local memory)
+		const bool use_bw = q.use_bw && nb <= MG_BW_S;
+		const int64_t blk = w.sbin >> (MG_BW_LB - 1);
+		const uint32_t l = (uint32_t)w.sbin & (MG_BW_S - 1);
+		for (int k = 0; k < q.nq; ++k) {
+			double qv = mg_nan();
+			if (n > 0) {
+				double pct = q.q_pct[k];
+				pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
+				const double index = __dmul_rn((double)(n - 1), pct);
+				const double fl = floor(index);
+				const long long i1 = (long long)fl;
+				const bool want2 = index != fl; // ceil(index) != floor(index)
+				float x1, x2;
+				if (use_bw)
+					mg_bw_select(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, w.ch->vals + blk * MG_BW_S, l, l + (uint32_t)nb, (uint32_t)i1, want2,
+								 x1, x2);
+				else
+					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, want2, x1, x2);
+				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
+			}
+			mg_st_stream(q.q_out[k] + i, qv);
+		}
+	}
 }

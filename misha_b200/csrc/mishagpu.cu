@@ -79,6 +79,14 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->force_sweep = value != 0;
 		return 0;
 	}
+	if (name && !strcmp(name, "block_wm")) {
+		ctx->block_wm = value != 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "l2_fetch_granularity")) { // 32 / 64 / 128 bytes: how much L2 pulls from HBM per missed sector
+		MG_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+		return 0;
+	}
 	if (name && !strcmp(name, "zero_copy")) {
 		ctx->zero_copy = value != 0;
 		return 0;
@@ -198,6 +206,16 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 			cmin = pmin;
 			nchild = nparent;
 		}
+	}
+	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
+	{
+		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_S);
+		uint8_t *bw = nullptr;
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nblk * MG_BW_RECORD_BYTES, &bw))
+			return 1;
+		k_bw_build<<<(unsigned)nblk, MG_BW_BUILD_THREADS>>>(dc.vals, nbins, bw);
+		MG_LAUNCH_CHECK(ctx);
+		dc.bw = bw;
 	}
 	// wavelet matrix over the dense ranks of the non-NaN values
 	long long m = 0;
@@ -507,6 +525,7 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.table = t->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.bin_size = t->bin_size;
+	q.use_bw = ctx->block_wm ? 1 : 0;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {
 		const int f = funcs[k];

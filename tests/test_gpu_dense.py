@@ -161,3 +161,47 @@ def test_stddev_prefix_squares_guard():
         assert const.any() and np.all(got[0][const] == 0.0)
     finally:
         ctx2.close()
+
+
+def test_block_wavelet_matches_global_and_oracle():
+    """Quantiles of windows <= 1024 bins come from the block-local wavelet matrices, larger ones from the chromosome-wide
+    matrix: both must equal the oracle bit for bit -- NaN runs, ties, negative values, block-boundary windows."""
+    from misha_b200 import gpu
+    nb = 2048 * 5 + 777
+    size = nb * 20 - 7
+    ctx2 = gpu.Context([size])
+    try:
+        rng = np.random.default_rng(99)
+        bins = rng.normal(0, 3, nb).astype(np.float32)
+        bins[rng.integers(0, nb, 600)] = np.float32(1.5)           # ties
+        bins[1000:1100] = np.nan
+        bins[2040:2060] = np.nan                                  # a NaN run across a block boundary
+        bins[4096:5200] = np.nan                                  # windows with no values at all
+        bins[rng.integers(0, nb, 300)] = np.nan
+        bins[7000:7300] = np.round(bins[7000:7300])                # many duplicates
+        t = gpu.DenseTrack(ctx2, 20)
+        t.stage(0, bins)
+        n = 20000
+        s = rng.integers(0, size - 1, n)
+        wl = rng.choice([1, 20, 399, 5000, 10240, 20479, 20480, 20481, 20500, 40000], n)
+        # windows that start / end exactly on block (1024-bin) boundaries
+        s[:2000] = (rng.integers(0, nb // 1024, 2000) * 1024 + rng.integers(-1, 2, 2000)).clip(0) * 20
+        e = np.minimum(s + wl, size)
+        rows = ctx2.rows_upload(np.zeros(n, np.int32), s, e)
+        funcs = [("quantile", 0.9), ("quantile", 0.5), ("quantile", 0.0), ("quantile", 1.0), ("quantile", 0.777), "max", "avg"]
+        blk = t.window(rows, funcs)
+        ctx2.set_option("block_wm", 0)
+        try:
+            glb = t.window(rows, funcs)
+        finally:
+            ctx2.set_option("block_wm", 1)
+        for k in range(len(funcs)):
+            if funcs[k] == "avg":
+                assert_close(blk[k], glb[k], RTOL, "avg")
+            else:
+                assert_same(blk[k], glb[k], f"block vs global {funcs[k]}")
+        for k, p in enumerate((0.9, 0.5, 0.0, 1.0, 0.777)):
+            exp = port.dense_window(bins, 20, size, s, e, 0, 0, p, ("quantile",))
+            assert_same(blk[k], exp["quantile"], f"block wavelet q{p} vs oracle")
+    finally:
+        ctx2.close()
