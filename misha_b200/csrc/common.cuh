@@ -32,6 +32,10 @@ struct mg_ctx {
 	                         // chromosome-wide matrix)
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;
+	// exact float thresholds of the last 1-D break set (mg_dense_hist streaming path)
+	std::vector<double> thr_breaks;
+	std::vector<float> thr_values;
+	int thr_include_lowest = -1;
 	// internal streams + staging buffers of the host-buffer entry points (lazily created)
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	void *pipe_dev[3] = {nullptr, nullptr, nullptr};

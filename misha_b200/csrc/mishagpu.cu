@@ -436,7 +436,7 @@ extern "C" int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, co
 	mg_rows *r = new (std::nothrow) mg_rows();
 	MG_REQUIRE(ctx, r, "out of memory");
 	const size_t ns = (size_t)(nscope > 0 ? nscope : 1);
-	const size_t total = ns * 8 * 2 + (ns + 1) * 8 + ns * 4;
+	const size_t total = ns * 8 * 2 + (ns + 1) * 8 * 2 + ns * 4;
 	cudaError_t e = cudaMalloc(&r->d_block, total);
 	if (e != cudaSuccess) {
 		delete r;
@@ -451,7 +451,8 @@ extern "C" int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, co
 	r->src.sstart = (const int64_t *)base;
 	r->src.send = (const int64_t *)(base + ns * 8);
 	r->src.srow0 = (const int64_t *)(base + ns * 16);
-	r->src.schrom = (const int32_t *)(base + ns * 16 + (ns + 1) * 8);
+	r->src.sbin0 = (const int64_t *)(base + ns * 16 + (ns + 1) * 8);
+	r->src.schrom = (const int32_t *)(base + ns * 16 + (ns + 1) * 16);
 	r->h_schrom.assign(h_chrom, h_chrom + nscope);
 	r->h_sstart.assign(h_start, h_start + nscope);
 	r->h_send.assign(h_end, h_end + nscope);
@@ -464,7 +465,11 @@ extern "C" int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, co
 			return mg_fail(ctx, "mg_rows_fixedbin: %s", cudaGetErrorString(e));
 		}
 	}
-	if ((e = cudaMemcpy((void *)r->src.srow0, row0.data(), ((size_t)nscope + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+	std::vector<int64_t> bin0((size_t)nscope + 1, 0);
+	for (int64_t k = 0; k < nscope; ++k)
+		bin0[k] = h_start[k] / binsize; // first bin of the scope interval: no 64-bit division on the device
+	if ((e = cudaMemcpy((void *)r->src.sbin0, bin0.data(), ((size_t)nscope + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+		(e = cudaMemcpy((void *)r->src.srow0, row0.data(), ((size_t)nscope + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
 		mg_rows_free(ctx, r);
 		return mg_fail(ctx, "mg_rows_fixedbin: %s", cudaGetErrorString(e));
 	}
@@ -922,7 +927,7 @@ static int mg_sparse_like_create(mg_ctx *ctx, H **out)
 	H *t = new (std::nothrow) H();
 	MG_REQUIRE(ctx, t, "out of memory");
 	t->nchroms = ctx->nchroms;
-	t->h_table.assign(ctx->nchroms, SparseChrom{nullptr, nullptr, nullptr, 0});
+	t->h_table.assign(ctx->nchroms, SparseChrom{nullptr, nullptr, nullptr, 0, nullptr, 0, 0});
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ctx->nchroms, &t->d_table))
 		return 1;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table, t->h_table.data(), sizeof(SparseChrom) * ctx->nchroms, cudaMemcpyHostToDevice));
@@ -946,7 +951,7 @@ static int mg_sparse_like_stage(mg_ctx *ctx, H *t, int chromid, const int64_t *h
 				   what, (long long)i, (long long)h_start[i], (long long)h_end[i], (long long)h_start[i - 1], (long long)h_end[i - 1]);
 	}
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
-	SparseChrom sc{nullptr, nullptr, nullptr, n};
+	SparseChrom sc{nullptr, nullptr, nullptr, n, nullptr, 0, 0};
 	int64_t *ds = nullptr, *de = nullptr;
 	float *dv = nullptr;
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, n, &ds) || mg_alloc_tracked(ctx, t->allocs, t->bytes, n, &de))
@@ -968,6 +973,29 @@ static int mg_sparse_like_stage(mg_ctx *ctx, H *t, int chromid, const int64_t *h
 	sc.start = ds;
 	sc.end = de;
 	sc.val = dv;
+	{
+		// coarse position index: cells of 2^shift bp holding ~8 records each; coarse[c] = first record with end > c << shift
+		const int64_t csize = ctx->chrom_sizes[chromid];
+		int shift = 8;
+		while (shift < 40 && ((csize >> shift) + 2) > std::max<int64_t>(n / 8, 16))
+			++shift;
+		const int64_t ncoarse = (csize >> shift) + 2;
+		std::vector<uint32_t> coarse((size_t)ncoarse);
+		int64_t r = 0;
+		for (int64_t c = 0; c < ncoarse; ++c) {
+			const int64_t pos = c << shift;
+			while (r < n && h_end[r] <= pos)
+				++r;
+			coarse[(size_t)c] = (uint32_t)r;
+		}
+		uint32_t *dc = nullptr;
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ncoarse, &dc))
+			return 1;
+		MG_CUDA(ctx, cudaMemcpy(dc, coarse.data(), sizeof(uint32_t) * (size_t)ncoarse, cudaMemcpyHostToDevice));
+		sc.coarse = dc;
+		sc.ncoarse = ncoarse;
+		sc.coarse_shift = shift;
+	}
 	t->h_table[chromid] = sc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &sc, sizeof(SparseChrom), cudaMemcpyHostToDevice));
 	return 0;
@@ -1031,7 +1059,18 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 	}
 	if (!count)
 		return 0;
-	k_sparse_window<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+	MG_REQUIRE(ctx, count < (1ll << 31) * (MG_SP_THREADS * MG_SF_ROWS), "row range too long for one launch");
+	if (!q.out[MG_STDDEV] && q.nq == 0 && !ctx->force_sweep) {
+		const bool sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST], mm = q.out[MG_MIN] || q.out[MG_MAX];
+		const unsigned grid = (unsigned)mg_div_up(count, MG_SP_THREADS * MG_SF_ROWS);
+		if (sum && mm)
+			k_sparse_merge<true, true><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+		else if (mm)
+			k_sparse_merge<false, true><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+		else
+			k_sparse_merge<true, false><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+	} else
+		k_sparse_window<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
 }
@@ -1052,7 +1091,10 @@ extern "C" int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, 
 	q.table = s->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.out = d_out;
-	k_coverage<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+	if (ctx->force_sweep)
+		k_coverage<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+	else
+		k_coverage_merge<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SF_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
 }
@@ -1224,7 +1266,21 @@ struct StreamSeg {
 	const float *p;
 	int64_t n;
 };
-#define MG_MAX_STREAM_SEGS 64
+static void mg_make_segtable(const std::vector<StreamSeg> &segs, SegTable &st)
+{
+	memset(&st, 0, sizeof(st));
+	st.nseg = (int)segs.size();
+	int64_t tiles = 0;
+	for (int i = 0; i < st.nseg; ++i) {
+		const int64_t mis = (int64_t)((reinterpret_cast<uintptr_t>(segs[i].p) >> 2) & 3);
+		st.p[i] = segs[i].p;
+		st.n[i] = segs[i].n;
+		st.tile0[i] = tiles;
+		tiles += mg_div_up(mis + segs[i].n, MG_SEG_TILE);
+	}
+	for (int i = st.nseg; i <= MG_MAX_STREAM_SEGS; ++i)
+		st.tile0[i] = tiles;
+}
 static bool mg_stream_segments(const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, std::vector<StreamSeg> &segs)
 {
 	segs.clear();
@@ -1244,9 +1300,9 @@ static bool mg_stream_segments(const mg_dense *t, const mg_rows *rows, int64_t f
 		int64_t n = r1 - r0;
 		if (b0 + n > ch.nbins) // rows past the last stored bin read as NaN in the generic path: keep that path
 			return false;
-		segs.push_back(StreamSeg{ch.vals + b0, n});
-		if (segs.size() > MG_MAX_STREAM_SEGS)
+		if (segs.size() >= MG_MAX_STREAM_SEGS)
 			return false;
+		segs.push_back(StreamSeg{ch.vals + b0, n});
 	}
 	return true;
 }
@@ -1260,23 +1316,14 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 	cudaStream_t st = mg_stream(stream);
 	std::vector<StreamSeg> segs;
 	if (mg_is_stream_case(t, rows, sshift, eshift, func) && mg_stream_segments(t, rows, first, count, segs)) {
-		// one pure-streaming launch per contiguous segment, partials side by side, one final reduction
-		std::vector<int> nbs(segs.size());
-		int total_blocks = 0;
-		for (size_t i = 0; i < segs.size(); ++i) {
-			int64_t b = mg_div_up(segs[i].n, (int64_t)MG_SUM_THREADS * 16);
-			const int64_t cap = (int64_t)ctx->sm_count * 8;
-			nbs[i] = (int)std::max<int64_t>(1, std::min(b, cap));
-			total_blocks += nbs[i];
-		}
+		// one pure-streaming launch over every contiguous segment, then the fixed-order final reduction
+		SegTable tab;
+		mg_make_segtable(segs, tab);
+		const int total_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], (int64_t)ctx->sm_count * 8));
 		Moments *scratch = nullptr;
 		MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * total_blocks, st));
-		int off = 0;
-		for (size_t i = 0; i < segs.size(); ++i) {
-			k_seg_summary<<<nbs[i], MG_SUM_THREADS, 0, st>>>(segs[i].p, segs[i].n, scratch + off);
-			MG_LAUNCH_CHECK(ctx);
-			off += nbs[i];
-		}
+		k_segs_summary<<<total_blocks, MG_SUM_THREADS, 0, st>>>(tab, count, scratch);
+		MG_LAUNCH_CHECK(ctx);
 		k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, total_blocks, d_partial);
 		MG_LAUNCH_CHECK(ctx);
 		MG_CUDA(ctx, cudaFreeAsync(scratch, st));
@@ -1361,6 +1408,8 @@ static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, cons
 		off += nbreaks[d];
 	}
 	hs.total = total;
+	if (!d_breaks) // the caller only wants the validated description (breaks travel another way)
+		return 0;
 	MG_CUDA(ctx, cudaMallocAsync(d_breaks, sizeof(double) * off, st));
 	MG_CUDA(ctx, cudaMemcpyAsync(*d_breaks, h_breaks, sizeof(double) * off, cudaMemcpyHostToDevice, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1487,30 +1536,39 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 	}
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, nullptr, st))
 		return 1;
 	std::vector<StreamSeg> segs;
 	if (count > 0 && stream_case && nbreaks - 1 <= MG_HIST_PRIVATE_MAX && mg_stream_segments(t, rows, first, count, segs)) {
-		// pure streaming per contiguous segment with exact float thresholds
+		// pure streaming over the contiguous segments with exact float thresholds (cached per break set: the bisection
+		// costs more host time than the kernel takes)
 		const int nb = nbreaks - 1;
-		std::vector<float> thr;
-		mg_float_thresholds(h_breaks, nbreaks, hs.binsize[0], include_lowest, thr);
-		float *d_thr = nullptr;
-		MG_CUDA(ctx, cudaMallocAsync(&d_thr, sizeof(float) * thr.size(), st));
-		MG_CUDA(ctx, cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice, st));
-		MG_CUDA(ctx, cudaStreamSynchronize(st));
-		const size_t smem = ((size_t)((nb + 1 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
-		MG_CUDA(ctx, cudaFuncSetAttribute(k_seg_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		for (const StreamSeg &sg : segs) {
-			int64_t b = mg_div_up(sg.n, (int64_t)MG_HIST_THREADS * 64);
-			const int64_t cap = (int64_t)ctx->sm_count * 2;
-			k_seg_hist<<<(unsigned)std::max<int64_t>(1, std::min(b, cap)), MG_HIST_THREADS, smem, st>>>(sg.p, sg.n, d_thr, nb, (unsigned long long *)d_counts);
-			MG_LAUNCH_CHECK(ctx);
+		if (ctx->thr_include_lowest != include_lowest || ctx->thr_breaks.size() != (size_t)nbreaks ||
+			memcmp(ctx->thr_breaks.data(), h_breaks, sizeof(double) * nbreaks)) {
+			mg_float_thresholds(h_breaks, nbreaks, hs.binsize[0], include_lowest, ctx->thr_values);
+			ctx->thr_breaks.assign(h_breaks, h_breaks + nbreaks);
+			ctx->thr_include_lowest = include_lowest;
 		}
-		MG_CUDA(ctx, cudaFreeAsync(d_thr, st));
-		MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+		const std::vector<float> &thr = ctx->thr_values;
+		FloatThr ft;
+		memset(&ft, 0, sizeof(ft));
+		ft.nb = nb;
+		ft.uniform = hs.binsize[0] != 0.;
+		ft.b0 = (float)h_breaks[0];
+		ft.inv_binsize = ft.uniform ? (float)(1. / hs.binsize[0]) : 0.f;
+		memcpy(ft.thr, thr.data(), sizeof(float) * thr.size());
+		SegTable tab;
+		mg_make_segtable(segs, tab);
+		const size_t smem = ((size_t)((nb + 1 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
+		MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)(220 * 1024) / (int64_t)(smem + 1024)));
+		const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], (int64_t)ctx->sm_count * per_sm));
+		k_segs_hist<<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+		MG_LAUNCH_CHECK(ctx);
 		return 0;
 	}
+	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
 	if (count > 0) {
 		const bool priv = nbreaks - 1 <= MG_HIST_PRIVATE_MAX;
 		DenseQuery q;

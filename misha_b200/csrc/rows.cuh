@@ -21,6 +21,7 @@ struct RowSrc {
 	const int64_t *sstart;
 	const int64_t *send;
 	const int64_t *srow0; // nscope + 1 exclusive prefix of rows per scope interval
+	const int64_t *sbin0; // floor(sstart / binsize) per scope interval (host-computed)
 };
 
 struct mg_rows {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mg_rowcache_load(const RowSrc &rs, int64_t r, Ro
 	c.sstart = __ldg(rs.sstart + c.k);
 	c.send = __ldg(rs.send + c.k);
 	c.chrom = __ldg(rs.schrom + c.k);
-	c.bin_base = mg_div_pos(c.sstart, rs.binsize) - c.row0;
+	c.bin_base = __ldg(rs.sbin0 + c.k) - c.row0;
 }
 
 __device__ __forceinline__ void mg_get_row_cached(const RowSrc &rs, int64_t r, RowCache &c, int &chrom, int64_t &s, int64_t &e, int64_t &scope)

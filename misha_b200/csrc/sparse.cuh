@@ -13,6 +13,11 @@ struct SparseChrom {
 	const int64_t *end;
 	const float *val;
 	int64_t n;
+	// coarse position index built at staging: coarse[c] = first record whose end > (c << coarse_shift), c = 0..ncoarse-1.
+	// Two lookups bracket the records any window inside a block's hull can touch (no search).
+	const uint32_t *coarse;
+	int64_t ncoarse;
+	int coarse_shift;
 };
 
 struct mg_sparse {
@@ -416,6 +421,363 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery 
 				total += (we < re ? we : re) - (ws > rs ? ws : rs);
 			}
 			cov = (double)total / (double)(we - ws);
+		}
+		mg_st_stream(q.out + i, cov);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Merge kernels for the common function sets (no stddev / quantile). Per block of 2048 rows:
+//   * the records any of its rows can touch are bracketed by two lookups in the coarse position index (no search) and
+//     staged in shared memory as 32-bit offsets from the block hull's start (12 bytes per record);
+//   * lane l of a warp takes rows w0 + l + 32 k, k = 0..7, so stores stay coalesced and the "first record with
+//     end > ws" of a lane only moves forward by a record or two between its consecutive rows (a restart plus a binary
+//     search covers unsorted rows);
+//   * blocks that span chromosomes, hold more than MG_SF_CAP records or do not fit 32-bit offsets take the per-row
+//     search path (mg_sparse_row / the coverage search) over the row's whole chromosome.
+#define MG_SF_ROWS 8
+#define MG_SF_CAP 2048
+
+struct SfSmem {
+	int start[MG_SF_CAP];
+	int end[MG_SF_CAP];
+	float val[MG_SF_CAP];
+	int64_t red_min[MG_SP_THREADS / 32], red_max[MG_SP_THREADS / 32];
+	int red_clo[MG_SP_THREADS / 32], red_chi[MG_SP_THREADS / 32];
+	int64_t origin; // staged positions are relative to the block hull's start
+	int64_t lo;     // first staged record
+	int n;          // staged records
+	int chrom;
+	int mode;       // 1 = staged, 0 = per-row search over the whole chromosome
+};
+
+// rows of lane l: block_base + warp * 32 * MG_SF_ROWS + l + 32 k
+template <typename Q>
+__device__ __forceinline__ int64_t mg_sf_row(const Q &q, int k)
+{
+	return (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + (int64_t)(threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31) + 32 * k;
+}
+
+// windows of this lane's rows; bit k of the result = row k exists and its window is non-empty
+template <typename Q>
+__device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_SF_ROWS], int64_t (&we)[MG_SF_ROWS], int (&chrom)[MG_SF_ROWS])
+{
+	unsigned ok = 0;
+	const int64_t i0 = mg_sf_row(q, 0);
+	if (q.rows.kind == 0) {
+#pragma unroll
+		for (int k = 0; k < MG_SF_ROWS; ++k) {
+			const int64_t i = i0 + 32 * k;
+			chrom[k] = 0;
+			ws[k] = we[k] = 0;
+			if (i < q.count) {
+				const int64_t r = q.first + i;
+				chrom[k] = __ldg(q.rows.chrom + r);
+				const int64_t s = __ldg(q.rows.start + r), e = __ldg(q.rows.end + r);
+				if (mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom[k]), ws[k], we[k]))
+					ok |= 1u << k;
+			}
+		}
+		return ok;
+	}
+	// implicit fixed-bin rows (src/TrackExpressionFixedBinIterator.cpp:52-60): the scope interval is looked up once and
+	// the bin coordinate advances by 32 bins per row
+	const int64_t binsize = q.rows.binsize, step = 32 * binsize;
+	int64_t r = q.first + i0, kscope = -1, row1 = 0, sstart = 0, send = 0, csize = 0, coord = 0;
+	int c = 0;
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k, r += 32, coord += step) {
+		chrom[k] = c;
+		ws[k] = we[k] = 0;
+		if (i0 + 32 * k >= q.count)
+			continue;
+		if (kscope < 0 || r >= row1) {
+			kscope = kscope < 0 ? mg_scope_of_row(q.rows, r) : kscope + 1;
+			while (r >= __ldg(q.rows.srow0 + kscope + 1))
+				++kscope;
+			row1 = __ldg(q.rows.srow0 + kscope + 1);
+			sstart = __ldg(q.rows.sstart + kscope);
+			send = __ldg(q.rows.send + kscope);
+			c = __ldg(q.rows.schrom + kscope);
+			csize = __ldg(q.chrom_sizes + c);
+			coord = (__ldg(q.rows.sbin0 + kscope) + (r - __ldg(q.rows.srow0 + kscope))) * binsize;
+		}
+		chrom[k] = c;
+		const int64_t s = coord > sstart ? coord : sstart;
+		const int64_t e = coord + binsize < send ? coord + binsize : send;
+		if (mg_window(s, e, q.sshift, q.eshift, csize, ws[k], we[k]))
+			ok |= 1u << k;
+	}
+	return ok;
+}
+
+// block hull -> record slice -> shared memory. Every thread passes the hull of its own valid rows.
+__device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table, unsigned okmask, const int64_t (&ws)[MG_SF_ROWS],
+											 const int64_t (&we)[MG_SF_ROWS], const int (&chrom)[MG_SF_ROWS], bool want_val)
+{
+	int64_t mn = INT64_MAX, mx = INT64_MIN;
+	int clo = INT_MAX, chi = INT_MIN;
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k)
+		if ((okmask >> k) & 1u) {
+			mn = min(mn, ws[k]);
+			mx = max(mx, we[k]);
+			clo = min(clo, chrom[k]);
+			chi = max(chi, chrom[k]);
+		}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 16; k > 0; k >>= 1) {
+		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, k));
+		mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+		clo = min(clo, __shfl_xor_sync(0xffffffffu, clo, k));
+		chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, k));
+	}
+	if (lane == 0) {
+		sm.red_min[warp] = mn;
+		sm.red_max[warp] = mx;
+		sm.red_clo[warp] = clo;
+		sm.red_chi[warp] = chi;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < MG_SP_THREADS / 32; ++w) {
+			mn = min(mn, sm.red_min[w]);
+			mx = max(mx, sm.red_max[w]);
+			clo = min(clo, sm.red_clo[w]);
+			chi = max(chi, sm.red_chi[w]);
+		}
+		int mode = 1, n = 0;
+		int64_t first = 0;
+		sm.chrom = 0;
+		if (clo != INT_MAX) { // the block has at least one valid row
+			mode = clo == chi ? 1 : 0;
+			sm.chrom = clo;
+			if (mode) {
+				const SparseChrom ch = table[clo];
+				if (ch.n > 0) {
+					const int64_t c0 = min(max(mn, (int64_t)0) >> ch.coarse_shift, ch.ncoarse - 1);
+					const int64_t c1 = min((max(mx, (int64_t)0) >> ch.coarse_shift) + 1, ch.ncoarse - 1);
+					// record coarse[c1] ends past a cell start >= the hull's end, so the record after it starts past the hull
+					const int64_t lo = (int64_t)__ldg(ch.coarse + c0), hi = (int64_t)__ldg(ch.coarse + c1) + 1;
+					const int64_t a = lo > 0 ? lo - 1 : 0, b = min(hi + 1, ch.n); // one neighbour on each side
+					first = a;
+					const int64_t cnt = b - a;
+					const int64_t lim = 0x7fffffff;
+					if (cnt > MG_SF_CAP || mx - mn > lim || mn - __ldg(ch.start + a) > lim || __ldg(ch.end + b - 1) - mn > lim)
+						mode = 0;
+					else
+						n = (int)cnt;
+				}
+			}
+		}
+		sm.origin = mn;
+		sm.lo = first;
+		sm.n = n;
+		sm.mode = mode;
+	}
+	__syncthreads();
+	if (sm.mode == 1 && sm.n > 0) {
+		const SparseChrom ch = table[sm.chrom];
+		const int64_t origin = sm.origin, lo = sm.lo;
+		for (int t = threadIdx.x; t < sm.n; t += MG_SP_THREADS) {
+			sm.start[t] = (int)(__ldg(ch.start + lo + t) - origin);
+			sm.end[t] = (int)(__ldg(ch.end + lo + t) - origin);
+			if (want_val)
+				sm.val[t] = __ldg(ch.val + lo + t);
+		}
+	}
+	__syncthreads();
+}
+
+// first staged record with end > a, searching forward from lo (a few linear steps, then a binary search)
+__device__ __forceinline__ int mg_sf_advance(const int *__restrict__ end, int n, int lo, int a)
+{
+	int steps = 0;
+	while (lo < n && end[lo] <= a) {
+		++lo;
+		if (++steps == 4) {
+			int hi = n;
+			while (lo < hi) {
+				const int mid = (lo + hi) >> 1;
+				if (end[mid] > a)
+					hi = mid;
+				else
+					lo = mid + 1;
+			}
+			break;
+		}
+	}
+	return lo;
+}
+
+// the per-row search path of a block the merge kernel cannot stage (windows are recomputed: indexing the caller's ws[] / we[]
+// by a loop counter would put them in local memory)
+__device__ __forceinline__ void mg_sparse_rows_search(const SparseQuery &q)
+{
+	RowCache rc;
+#pragma unroll 1
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		const int64_t i = mg_sf_row(q, k);
+		if (i >= q.count)
+			break;
+		int c;
+		int64_t s, e;
+		const bool ok = mg_sp_row_window(q, i, rc, c, s, e);
+		const SparseChrom ch = q.table[ok ? c : 0];
+		mg_sparse_row(q, SpLocal{ch.start, ch.end, ch.val, ch.n}, ok, s, e, i);
+	}
+}
+
+template <bool SUM, bool MM>
+__global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_merge(const SparseQuery q)
+{
+	__shared__ SfSmem sm;
+	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
+	int chrom[MG_SF_ROWS];
+	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
+	mg_sf_stage(sm, q.table, okmask, ws, we, chrom, true);
+	if (sm.mode == 0) { // rare: per-row search over the row's whole chromosome
+		mg_sparse_rows_search(q);
+		return;
+	}
+	const int64_t origin = sm.origin;
+	const int n = sm.n;
+	int lo = 0, prev = INT_MIN;
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		const int64_t i = mg_sf_row(q, k);
+		if (i >= q.count)
+			break;
+		double avg = mg_nan(), sum = mg_nan(), vmn = mg_nan(), vmx = mg_nan(), nearest = mg_nan(), size = mg_nan(), exists = mg_nan();
+		if ((okmask >> k) & 1u) {
+			const int a = (int)(ws[k] - origin), b = (int)(we[k] - origin);
+			if (a < prev)
+				lo = 0; // unsorted rows: restart
+			prev = a;
+			size = 0;
+			exists = 0;
+			if (n > 0) {
+				lo = mg_sf_advance(sm.end, n, lo, a);
+				if (lo == n)
+					nearest = (double)sm.val[n - 1]; // after the last record (src/GenomeTrackSparse.cpp:286-289)
+				else if (sm.start[lo] < b) {
+					int cnt = 0;
+					double S = 0;
+					float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
+					for (int r = lo; r < n && sm.start[r] < b; ++r) { // record order = the reference's order
+						const float v = sm.val[r];
+						if (isnan(v))
+							continue;
+						if (SUM)
+							S += (double)v;
+						if (MM) {
+							fmin = fminf(fmin, v);
+							fmax = fmaxf(fmax, v);
+						}
+						++cnt;
+					}
+					size = (double)cnt;
+					if (cnt > 0) {
+						exists = 1;
+						if (SUM) {
+							avg = nearest = mg_f2d(cnt == 1 ? S : S / (double)cnt);
+							sum = mg_f2d(S);
+						}
+						if (MM) {
+							vmn = (double)fmin;
+							vmx = (double)fmax;
+						}
+					}
+				} else if (lo == 0)
+					nearest = (double)sm.val[0]; // before the first record (:281-284)
+				else {
+					// no overlap: end[lo-1] <= a < b <= start[lo]; the closer neighbour, ties to the earlier record (:336-338)
+					const int dp = a - sm.end[lo - 1], dn = sm.start[lo] - b;
+					nearest = (double)sm.val[dp <= dn ? lo - 1 : lo];
+				}
+			}
+		}
+		if (SUM) {
+			if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
+			if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, nearest);
+			if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
+		}
+		if (MM) {
+			if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, vmn);
+			if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, vmx);
+		}
+		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
+		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+	}
+}
+
+__global__ void __launch_bounds__(MG_SP_THREADS) k_coverage_merge(const CoverageQuery q)
+{
+	__shared__ SfSmem sm;
+	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
+	int chrom[MG_SF_ROWS];
+	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
+	mg_sf_stage(sm, q.table, okmask, ws, we, chrom, false);
+	if (sm.mode == 0) {
+		RowCache rc;
+#pragma unroll 1
+		for (int k = 0; k < MG_SF_ROWS; ++k) {
+			const int64_t i = mg_sf_row(q, k);
+			if (i >= q.count)
+				break;
+			double cov = mg_nan();
+			int c;
+			int64_t s, e;
+			if (mg_sp_row_window(q, i, rc, c, s, e)) {
+				const SparseChrom ch = q.table[c];
+				int64_t lo = 0, hi = ch.n;
+				while (lo < hi) {
+					const int64_t mid = lo + ((hi - lo) >> 1);
+					if (ch.end[mid] > s)
+						hi = mid;
+					else
+						lo = mid + 1;
+				}
+				int64_t total = 0;
+				for (int64_t r = lo; r < ch.n; ++r) {
+					const int64_t rs = ch.start[r];
+					if (rs >= e)
+						break;
+					const int64_t re = ch.end[r];
+					total += (e < re ? e : re) - (s > rs ? s : rs);
+				}
+				cov = (double)total / (double)(e - s);
+			}
+			mg_st_stream(q.out + i, cov);
+		}
+		return;
+	}
+	const int64_t origin = sm.origin;
+	const int n = sm.n;
+	int lo = 0, prev = INT_MIN;
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		const int64_t i = mg_sf_row(q, k);
+		if (i >= q.count)
+			break;
+		double cov = mg_nan();
+		if ((okmask >> k) & 1u) {
+			const int a = (int)(ws[k] - origin), b = (int)(we[k] - origin);
+			if (a < prev)
+				lo = 0;
+			prev = a;
+			lo = mg_sf_advance(sm.end, n, lo, a);
+			int total = 0;
+			for (int r = lo; r < n; ++r) {
+				const int rs = sm.start[r];
+				if (rs >= b)
+					break;
+				const int re = sm.end[r];
+				total += min(b, re) - max(a, rs);
+			}
+			// 0 / len and len / len need no divide (most rows of a fine iterator are fully outside or inside a source interval)
+			cov = total == 0 ? 0. : (total == b - a ? 1. : (double)total / (double)(b - a));
 		}
 		mg_st_stream(q.out + i, cov);
 	}

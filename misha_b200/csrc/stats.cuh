@@ -191,7 +191,7 @@ __device__ __forceinline__ void mg_stream_rows(const RowSrc &rs, const DenseChro
 			const DenseChrom *ch = table + __ldg(rs.schrom + k);
 			vals = ch->vals;
 			nbins = ch->nbins;
-			bin0 = __ldg(rs.sstart + k) / rs.binsize;
+			bin0 = __ldg(rs.sbin0 + k);
 		}
 		const int64_t b = bin0 + (r - row0);
 		f((double)(b < nbins ? __ldcs(vals + b) : mg_nanf()));
@@ -231,48 +231,65 @@ __device__ __forceinline__ void momf_add(MomF &m, float v)
 	}
 }
 
+// All segments of a scan in ONE launch: the segments are cut into tiles of MG_SEG_TILE floats, aligned to 16 bytes
+// relative to each segment's own aligned-down base, and the tiles are dealt round-robin to a persistent grid. Interior
+// tiles are four unpredicated 16-byte loads per thread; only a segment's first / last tile masks elements.
+#define MG_MAX_STREAM_SEGS 64
+#define MG_SEG_TILE (MG_SUM_THREADS * 16)
+struct SegTable {
+	int nseg;
+	const float *p[MG_MAX_STREAM_SEGS]; // first element of the segment
+	int64_t n[MG_MAX_STREAM_SEGS];
+	int64_t tile0[MG_MAX_STREAM_SEGS + 1]; // exclusive prefix of tiles per segment
+};
+
 template <typename F>
-__device__ __forceinline__ void mg_stream_segment(const float *__restrict__ p, int64_t n, F &&f)
+__device__ __forceinline__ void mg_stream_segtable(const SegTable &st, F &&f)
 {
-	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
-	int64_t head = (4 - (int64_t)((reinterpret_cast<uintptr_t>(p) >> 2) & 3)) & 3;
-	if (head > n)
-		head = n;
-	const int64_t nv4 = (n - head) >> 2;
-	const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
-	int64_t i = tid;
-	for (; i + 3 * nthreads < nv4; i += 4 * nthreads) {
-		const float4 a = __ldcs(p4 + i), b = __ldcs(p4 + i + nthreads), c = __ldcs(p4 + i + 2 * nthreads), d = __ldcs(p4 + i + 3 * nthreads);
-		f(a.x); f(a.y); f(a.z); f(a.w);
-		f(b.x); f(b.y); f(b.z); f(b.w);
-		f(c.x); f(c.y); f(c.z); f(c.w);
-		f(d.x); f(d.y); f(d.z); f(d.w);
+	const int64_t ntiles = st.tile0[st.nseg];
+	int s = 0;
+	for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		while (tile >= st.tile0[s + 1])
+			++s;
+		const float *p = st.p[s];
+		const int64_t mis = (int64_t)((reinterpret_cast<uintptr_t>(p) >> 2) & 3); // floats between the aligned-down base and p
+		const int64_t lo = mis, hi = mis + st.n[s];                                 // valid element range relative to that base
+		const int64_t e0 = (tile - st.tile0[s]) * MG_SEG_TILE;
+		const float4 *q = reinterpret_cast<const float4 *>(p - mis + e0) + threadIdx.x;
+		if (e0 >= lo && e0 + MG_SEG_TILE <= hi) {
+			const float4 a = __ldcs(q), b = __ldcs(q + MG_SUM_THREADS), c = __ldcs(q + 2 * MG_SUM_THREADS), d = __ldcs(q + 3 * MG_SUM_THREADS);
+			f(a.x); f(a.y); f(a.z); f(a.w);
+			f(b.x); f(b.y); f(b.z); f(b.w);
+			f(c.x); f(c.y); f(c.z); f(c.w);
+			f(d.x); f(d.y); f(d.z); f(d.w);
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const int64_t i0 = e0 + ((int64_t)threadIdx.x + k * MG_SUM_THREADS) * 4;
+				if (i0 + 3 < lo || i0 >= hi)
+					continue;
+				const float4 a = __ldcs(q + k * MG_SUM_THREADS); // stays inside the staged array: it is padded past nbins
+				if (i0 >= lo && i0 < hi) f(a.x);
+				if (i0 + 1 >= lo && i0 + 1 < hi) f(a.y);
+				if (i0 + 2 >= lo && i0 + 2 < hi) f(a.z);
+				if (i0 + 3 >= lo && i0 + 3 < hi) f(a.w);
+			}
+		}
 	}
-	for (; i < nv4; i += nthreads) {
-		const float4 a = __ldcs(p4 + i);
-		f(a.x); f(a.y); f(a.z); f(a.w);
-	}
-	if (tid < head)
-		f(p[tid]);
-	const int64_t tail0 = head + (nv4 << 2);
-	if (tid < n - tail0)
-		f(p[tail0 + tid]);
 }
 
-__global__ void __launch_bounds__(MG_SUM_THREADS) k_seg_summary(const float *__restrict__ p, int64_t n, Moments *block_out)
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_segs_summary(const SegTable st, int64_t nrows, Moments *block_out)
 {
 	__shared__ Moments sm[MG_SUM_THREADS / 32];
 	MomF mf{0ull, 0., 0., __int_as_float(0x7f800000), __int_as_float(0xff800000)};
-	mg_stream_segment(p, n, [&](float v) { momf_add(mf, v); });
+	mg_stream_segtable(st, [&](float v) { momf_add(mf, v); });
 	Moments m;
-	m.n = 0; // the row count of the segment is added by the host-side launch (thread 0 of block 0 below)
+	m.n = blockIdx.x == 0 && threadIdx.x == 0 ? (double)nrows : 0.;
 	m.nn = (double)mf.nn;
 	m.sum = mf.sum;
 	m.ssq = mf.ssq;
 	m.mn = mf.nn ? (double)mf.mn : 1.7976931348623157e308;
 	m.mx = mf.nn ? (double)mf.mx : -1.7976931348623157e308;
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		m.n = (double)n;
 	mom_block_reduce(m, sm);
 	if (threadIdx.x == 0)
 		block_out[blockIdx.x] = m;
@@ -399,24 +416,57 @@ __device__ __forceinline__ int mg_float_bin(const float *__restrict__ thr, int n
 	return lo == nb + 1 ? -1 : lo - 1; // lo thresholds are below v: bin = lo - 1 (-1: too low); all nb+1 below: too high
 }
 
-__global__ void __launch_bounds__(MG_HIST_THREADS) k_seg_hist(const float *__restrict__ p, int64_t n, const float *__restrict__ thr_g, int nb,
-															   unsigned long long *counts)
+// Thresholds travel as a kernel parameter (no upload, no synchronisation). With equal-width breaks the bin is guessed with
+// one float multiply and corrected against the exact thresholds (the guess is off by at most one or two).
+struct FloatThr {
+	int nb;
+	int uniform;
+	float b0, inv_binsize;
+	float thr[MG_HIST_PRIVATE_MAX + 1];
+};
+
+__device__ __forceinline__ int mg_float_bin_guess(const float *__restrict__ thr, int nb, float b0, float inv, float v)
+{
+	if (isnan(v))
+		return -1;
+	// c = number of thresholds below v, c in [0, nb + 1]
+	float g = (v - b0) * inv + 1.f;
+	g = fminf(fmaxf(g, 0.f), (float)(nb + 1));
+	int c = (int)g;
+	while (c <= nb && thr[c] < v)
+		++c;
+	while (c > 0 && !(thr[c - 1] < v))
+		--c;
+	return c == nb + 1 ? -1 : c - 1;
+}
+
+__global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st, const FloatThr ft, unsigned long long *counts)
 {
 	extern __shared__ __align__(16) uint32_t hsmem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const int nb = ft.nb;
 	float *thr = reinterpret_cast<float *>(hsmem);
 	const int thr_words = (nb + 1 + 3) & ~3;
 	uint32_t *hall = hsmem + thr_words, *h = hall + warp * nb * 32;
 	for (int t = threadIdx.x; t <= nb; t += blockDim.x)
-		thr[t] = thr_g[t];
+		thr[t] = ft.thr[t];
 	for (int t = lane; t < nb * 32; t += 32)
 		h[t] = 0;
 	__syncthreads();
-	mg_stream_segment(p, n, [&](float v) {
-		const int b = mg_float_bin(thr, nb, v);
-		if (b >= 0)
-			h[b * 32 + lane]++;
-	});
+	if (ft.uniform) {
+		const float b0 = ft.b0, inv = ft.inv_binsize;
+		mg_stream_segtable(st, [&](float v) {
+			const int b = mg_float_bin_guess(thr, nb, b0, inv, v);
+			if (b >= 0)
+				h[b * 32 + lane]++;
+		});
+	} else {
+		mg_stream_segtable(st, [&](float v) {
+			const int b = mg_float_bin(thr, nb, v);
+			if (b >= 0)
+				h[b * 32 + lane]++;
+		});
+	}
 	__syncthreads();
 	for (int b = warp; b < nb; b += nwarps) {
 		unsigned long long c = 0;

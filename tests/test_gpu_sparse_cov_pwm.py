@@ -226,3 +226,71 @@ def test_sparse_and_coverage_block_narrowing_modes():
                     assert_same(cov[m], port.coverage(rs, re, sizes[cid], s[m], e[m], sshift, eshift), f"coverage chrom{cid} {sshift}")
     finally:
         ctx2.close()
+
+
+def test_merge_kernels_vs_search_kernels_and_oracle():
+    """The merge kernels (coarse position index + per-lane forward walk) against the per-row search kernels and the
+    oracle: unsorted rows, blocks that span chromosomes, records far denser and far sparser than the rows, implicit
+    fixed-bin rows."""
+    sizes = [300000, 50000, 200000]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(17)
+        t = gpu.SparseTrack(ctx2)
+        iv = gpu.IntervalSet(ctx2)
+        recs = []
+        for cid, size in enumerate(sizes):
+            n = (20000, 7, 0)[cid]  # dense / very sparse / empty
+            st = np.sort(rng.choice(size // 10 - 2, n, replace=False)) * 10
+            en = st + rng.integers(1, 10, n)
+            v = rng.random(n).astype(np.float32)
+            v[rng.random(n) < 0.05] = np.nan
+            t.stage(cid, st, en, v)
+            iv.stage(cid, st, en)
+            recs.append((st, en, v))
+        n = 30000
+        chrom = rng.integers(0, 3, n).astype(np.int32)
+        chrom[:10000] = np.sort(chrom[:10000])  # first part sorted by chromosome, the rest fully shuffled
+        size_of = np.array(sizes)[chrom]
+        s = (rng.random(n) * (size_of - 2)).astype(np.int64)
+        s[:10000] = np.concatenate([np.sort(s[:10000][chrom[:10000] == c]) for c in range(3)])
+        e = np.minimum(s + rng.choice([1, 5, 20, 300, 5000, 100000], n), size_of)
+        rows = ctx2.rows_upload(chrom, s, e)
+        names = ["avg", "sum", "min", "max", "nearest", "size", "exists"]
+        for sshift, eshift in ((0, 0), (-250, 250)):
+            new = t.window(rows, names, sshift, eshift)
+            newc = iv.coverage(rows, sshift=sshift, eshift=eshift)
+            ctx2.set_option("force_sweep", 1)
+            try:
+                old = t.window(rows, names, sshift, eshift)
+                oldc = iv.coverage(rows, sshift=sshift, eshift=eshift)
+            finally:
+                ctx2.set_option("force_sweep", 0)
+            for k, name in enumerate(names):
+                assert_same(new[k], old[k], f"merge vs search {name} shift {sshift}")
+            assert_same(newc, oldc, f"coverage merge vs search shift {sshift}")
+            for c in range(3):
+                m = chrom == c
+                onames = [x for x in names if x != "exists"]
+                exp = port.sparse_window(*recs[c], sizes[c], s[m], e[m], sshift, eshift, 0.5, funcs=tuple(onames))
+                for k, name in enumerate(names):
+                    if name == "exists":
+                        assert_same(new[k][m], np.where(np.isnan(exp["size"]), np.nan, (exp["size"] > 0).astype(float)), f"chrom{c} exists")
+                    else:
+                        assert_same(new[k][m], exp[name], f"chrom{c} {name} vs oracle")
+                assert_same(newc[m], port.coverage(recs[c][0], recs[c][1], sizes[c], s[m], e[m], sshift, eshift), f"chrom{c} coverage vs oracle")
+        # implicit fixed-bin rows over the whole genome
+        frows = ctx2.rows_fixedbin(20, np.arange(3, dtype=np.int32), np.zeros(3, np.int64), np.array(sizes, np.int64))
+        new = t.window(frows, ["nearest", "avg"])
+        newc = iv.coverage(frows)
+        ctx2.set_option("force_sweep", 1)
+        try:
+            old = t.window(frows, ["nearest", "avg"])
+            oldc = iv.coverage(frows)
+        finally:
+            ctx2.set_option("force_sweep", 0)
+        assert_same(new[0], old[0], "fixed-bin nearest")
+        assert_same(new[1], old[1], "fixed-bin avg")
+        assert_same(newc, oldc, "fixed-bin coverage")
+    finally:
+        ctx2.close()
