@@ -8,6 +8,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <map>
 #include <new>
 #include <algorithm>
 #include <limits>
@@ -36,6 +37,7 @@ struct mg_ctx {
 	std::vector<double> thr_breaks;
 	std::vector<float> thr_values;
 	int thr_include_lowest = -1;
+	std::map<void *, void *> stream_scratch; // per-stream reduction scratch (mishagpu.cu: mg_stream_scratch)
 	// internal streams + staging buffers of the host-buffer entry points (lazily created)
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	void *pipe_dev[3] = {nullptr, nullptr, nullptr};

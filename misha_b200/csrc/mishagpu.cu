@@ -61,6 +61,8 @@ extern "C" void mg_shutdown(mg_ctx *ctx)
 		if (ctx->pipe_stream[i])
 			cudaStreamDestroy(ctx->pipe_stream[i]);
 	}
+	for (auto &kv : ctx->stream_scratch)
+		cudaFree(kv.second);
 	cudaFree(ctx->d_chrom_sizes);
 	delete ctx;
 }
@@ -1061,14 +1063,18 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 		return 0;
 	MG_REQUIRE(ctx, count < (1ll << 31) * (MG_SP_THREADS * MG_SF_ROWS), "row range too long for one launch");
 	if (!q.out[MG_STDDEV] && q.nq == 0 && !ctx->force_sweep) {
-		const bool sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST], mm = q.out[MG_MIN] || q.out[MG_MAX];
 		const unsigned grid = (unsigned)mg_div_up(count, MG_SP_THREADS * MG_SF_ROWS);
-		if (sum && mm)
-			k_sparse_merge<true, true><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
-		else if (mm)
-			k_sparse_merge<false, true><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
-		else
-			k_sparse_merge<true, false><<<grid, MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
+		cudaStream_t st = mg_stream(stream);
+		switch (nfuncs == 1 ? funcs[0] : -1) { // one requested column: the kernel specialised on it
+		case MG_AVG: k_sparse_merge<MG_AVG><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_SUM: k_sparse_merge<MG_SUM><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_MIN: k_sparse_merge<MG_MIN><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_MAX: k_sparse_merge<MG_MAX><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_NEAREST: k_sparse_merge<MG_NEAREST><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_SIZE: k_sparse_merge<MG_SIZE><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		case MG_EXISTS: k_sparse_merge<MG_EXISTS><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		default: k_sparse_merge<-1><<<grid, MG_SP_THREADS, 0, st>>>(q); break;
+		}
 	} else
 		k_sparse_window<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
@@ -1252,6 +1258,22 @@ extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *
 	return 0;
 }
 
+// Per-stream device scratch (a zeroed 256-byte header + MG_SUM_MAX_BLOCKS block partials), allocated on first use and kept:
+// kernels that finish with a "last block reduces" step need it without a malloc / free pair per call.
+static int mg_stream_scratch(mg_ctx *ctx, cudaStream_t st, void **out)
+{
+	auto it = ctx->stream_scratch.find((void *)st);
+	if (it == ctx->stream_scratch.end()) {
+		void *p = nullptr;
+		const size_t bytes = 256 + sizeof(Moments) * MG_SUM_MAX_BLOCKS;
+		MG_CUDA(ctx, cudaMalloc(&p, bytes));
+		MG_CUDA(ctx, cudaMemset(p, 0, bytes));
+		it = ctx->stream_scratch.emplace((void *)st, p).first;
+	}
+	*out = it->second;
+	return 0;
+}
+
 static bool mg_is_prefix_func(int f) { return f == MG_AVG || f == MG_SUM || f == MG_NEAREST || f == MG_SIZE || f == MG_EXISTS; }
 
 // implicit fixed-bin rows at the track's own resolution with no shifts: each row is exactly one bin
@@ -1319,14 +1341,12 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 		// one pure-streaming launch over every contiguous segment, then the fixed-order final reduction
 		SegTable tab;
 		mg_make_segtable(segs, tab);
-		const int total_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], (int64_t)ctx->sm_count * 8));
-		Moments *scratch = nullptr;
-		MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * total_blocks, st));
-		k_segs_summary<<<total_blocks, MG_SUM_THREADS, 0, st>>>(tab, count, scratch);
+		const int total_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], std::min<int64_t>((int64_t)ctx->sm_count * 8, MG_SUM_MAX_BLOCKS)));
+		void *scratch = nullptr;
+		if (mg_stream_scratch(ctx, st, &scratch))
+			return 1;
+		k_segs_summary<<<total_blocks, MG_SUM_THREADS, 0, st>>>(tab, count, (Moments *)((char *)scratch + 256), (unsigned *)scratch, d_partial);
 		MG_LAUNCH_CHECK(ctx);
-		k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, total_blocks, d_partial);
-		MG_LAUNCH_CHECK(ctx);
-		MG_CUDA(ctx, cudaFreeAsync(scratch, st));
 		return 0;
 	}
 	if (mg_is_stream_case(t, rows, sshift, eshift, func) || mg_is_prefix_func(func)) {
@@ -1559,7 +1579,7 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 		memcpy(ft.thr, thr.data(), sizeof(float) * thr.size());
 		SegTable tab;
 		mg_make_segtable(segs, tab);
-		const size_t smem = ((size_t)((nb + 1 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
+		const size_t smem = ((size_t)((nb + 3 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
 		MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)(220 * 1024) / (int64_t)(smem + 1024)));
 		const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], (int64_t)ctx->sm_count * per_sm));

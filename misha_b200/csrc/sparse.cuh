@@ -227,6 +227,7 @@ __device__ __forceinline__ SpLocal mg_sp_narrow(SpSmem &sm, const SparseChrom *t
 
 // Per-row arithmetic. read_interval: src/GenomeTrackSparse.cpp:237-340; calc_vals: src/GenomeTrackSparse.h:143-259.
 // Sums and Welford updates run in record order, exactly the reference's order => avg / sum / stddev are bit-exact.
+template <bool FULL> // FULL = stddev and quantiles too (the merge kernels' fallback never needs them)
 __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLocal &ch, bool ok, int64_t ws, int64_t we, int64_t i)
 {
 	double avg = mg_nan(), sum = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan(), nearest = mg_nan(), size = mg_nan(),
@@ -267,9 +268,11 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 						if (v < fmin) fmin = v;
 						if (v > fmax) fmax = v;
 						++n;
-						const double d = (double)v - mean;
-						mean += d / (double)n;
-						m2 += d * ((double)v - mean);
+						if (FULL) {
+							const double d = (double)v - mean;
+							mean += d / (double)n;
+							m2 += d * ((double)v - mean);
+						}
 					}
 					size = (double)n;
 					if (n > 0) {
@@ -278,9 +281,9 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 						sum = mg_f2d(S);
 						mn = (double)fmin;
 						mx = (double)fmax;
-						if (n > 1)
+						if (FULL && n > 1)
 							sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
-						for (int k = 0; k < q.nq; ++k) {
+						for (int k = 0; FULL && k < q.nq; ++k) {
 							double pct = q.q_pct[k];
 							pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
 							const double index = __dmul_rn((double)(n - 1), pct);
@@ -305,10 +308,10 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 	if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
 	if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
 	if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, mx);
-	if (q.out[MG_STDDEV]) mg_st_stream(q.out[MG_STDDEV] + i, sd);
+	if (FULL && q.out[MG_STDDEV]) mg_st_stream(q.out[MG_STDDEV] + i, sd);
 	if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
 	if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
-	for (int k = 0; k < q.nq; ++k)
+	for (int k = 0; FULL && k < q.nq; ++k)
 		mg_st_stream(q.q_out[k] + i, qv[k]);
 }
 
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_window(const SparseQue
 			const SparseChrom c = q.table[chrom];
 			ch = SpLocal{c.start, c.end, c.val, c.n};
 		}
-		mg_sparse_row(q, ch, ok, ws, we, i);
+		mg_sparse_row<true>(q, ch, ok, ws, we, i);
 	}
 }
 
@@ -436,12 +439,17 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery 
 //   * blocks that span chromosomes, hold more than MG_SF_CAP records or do not fit 32-bit offsets take the per-row
 //     search path (mg_sparse_row / the coverage search) over the row's whole chromosome.
 #define MG_SF_ROWS 8
-#define MG_SF_CAP 2048
+#define MG_SF_CAP 1024
+#define MG_SF_SENT (1 << 30) // sentinel coordinate; real offsets stay within +-MG_SF_RANGE so distances never overflow
+#define MG_SF_RANGE (1 << 28)
 
+// Staged records live at indices 1..n between sentinels: [0] = {-SENT, -SENT}, [n+1] = [n+2] = {+SENT, +SENT}. With them
+// "first record with end > a" always exists, the neighbours lo - 1 / lo + 1 can be read unguarded, and a sentinel never
+// wins the nearest-neighbour comparison against a real record.
 struct SfSmem {
-	int start[MG_SF_CAP];
-	int end[MG_SF_CAP];
-	float val[MG_SF_CAP];
+	int start[MG_SF_CAP + 3];
+	int end[MG_SF_CAP + 3];
+	float val[MG_SF_CAP + 3];
 	int64_t red_min[MG_SP_THREADS / 32], red_max[MG_SP_THREADS / 32];
 	int red_clo[MG_SP_THREADS / 32], red_chi[MG_SP_THREADS / 32];
 	int64_t origin; // staged positions are relative to the block hull's start
@@ -480,32 +488,63 @@ __device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_S
 		}
 		return ok;
 	}
-	// implicit fixed-bin rows (src/TrackExpressionFixedBinIterator.cpp:52-60): the scope interval is looked up once and
-	// the bin coordinate advances by 32 bins per row
+	// implicit fixed-bin rows (src/TrackExpressionFixedBinIterator.cpp:52-60)
 	const int64_t binsize = q.rows.binsize, step = 32 * binsize;
 	int64_t r = q.first + i0, kscope = -1, row1 = 0, sstart = 0, send = 0, csize = 0, coord = 0;
 	int c = 0;
+	if (i0 + 32 * (MG_SF_ROWS - 1) < q.count) {
+		// Regular case: all rows of the lane are interior rows of ONE scope interval and no window is clamped. Then row k's
+		// window is the first row's shifted by k * 32 bins: one scope lookup and two additions per row.
+		kscope = mg_scope_of_row(q.rows, r);
+		const int64_t row0 = __ldg(q.rows.srow0 + kscope);
+		row1 = __ldg(q.rows.srow0 + kscope + 1);
+		sstart = __ldg(q.rows.sstart + kscope);
+		send = __ldg(q.rows.send + kscope);
+		c = __ldg(q.rows.schrom + kscope);
+		csize = __ldg(q.chrom_sizes + c);
+		coord = (__ldg(q.rows.sbin0 + kscope) + (r - row0)) * binsize;
+		const int64_t last = coord + (MG_SF_ROWS - 1) * step;
+		const int64_t w0 = coord + q.sshift, len = binsize + q.eshift - q.sshift;
+		if (r > row0 && r + 32 * (MG_SF_ROWS - 1) < row1 - 1 && w0 >= 0 && last + binsize + q.eshift <= csize && len > 0) {
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k, r += 32, coord += step) {
-		chrom[k] = c;
-		ws[k] = we[k] = 0;
-		if (i0 + 32 * k >= q.count)
-			continue;
-		if (kscope < 0 || r >= row1) {
-			kscope = kscope < 0 ? mg_scope_of_row(q.rows, r) : kscope + 1;
-			while (r >= __ldg(q.rows.srow0 + kscope + 1))
-				++kscope;
-			row1 = __ldg(q.rows.srow0 + kscope + 1);
-			sstart = __ldg(q.rows.sstart + kscope);
-			send = __ldg(q.rows.send + kscope);
-			c = __ldg(q.rows.schrom + kscope);
-			csize = __ldg(q.chrom_sizes + c);
-			coord = (__ldg(q.rows.sbin0 + kscope) + (r - __ldg(q.rows.srow0 + kscope))) * binsize;
+			for (int k = 0; k < MG_SF_ROWS; ++k) {
+				chrom[k] = c;
+				ws[k] = w0 + k * step;
+				we[k] = ws[k] + len;
+			}
+			return (1u << MG_SF_ROWS) - 1u;
 		}
-		chrom[k] = c;
-		const int64_t s = coord > sstart ? coord : sstart;
-		const int64_t e = coord + binsize < send ? coord + binsize : send;
-		if (mg_window(s, e, q.sshift, q.eshift, csize, ws[k], we[k]))
+		kscope = -1; // fall through to the general path
+	}
+#pragma unroll 1
+	for (int k = 0; k < MG_SF_ROWS; ++k, r += 32, coord += step) {
+		int64_t wsk = 0, wek = 0;
+		bool okk = false;
+		if (i0 + 32 * k < q.count) {
+			if (kscope < 0 || r >= row1) {
+				kscope = kscope < 0 ? mg_scope_of_row(q.rows, r) : kscope + 1;
+				while (r >= __ldg(q.rows.srow0 + kscope + 1))
+					++kscope;
+				row1 = __ldg(q.rows.srow0 + kscope + 1);
+				sstart = __ldg(q.rows.sstart + kscope);
+				send = __ldg(q.rows.send + kscope);
+				c = __ldg(q.rows.schrom + kscope);
+				csize = __ldg(q.chrom_sizes + c);
+				coord = (__ldg(q.rows.sbin0 + kscope) + (r - __ldg(q.rows.srow0 + kscope))) * binsize;
+			}
+			const int64_t s = coord > sstart ? coord : sstart;
+			const int64_t e = coord + binsize < send ? coord + binsize : send;
+			okk = mg_window(s, e, q.sshift, q.eshift, csize, wsk, wek);
+		}
+		// ws[] / we[] must stay in registers: write them with compile-time indices
+#pragma unroll
+		for (int j = 0; j < MG_SF_ROWS; ++j)
+			if (j == k) {
+				chrom[j] = c;
+				ws[j] = wsk;
+				we[j] = wek;
+			}
+		if (okk)
 			ok |= 1u << k;
 	}
 	return ok;
@@ -526,12 +565,21 @@ __device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table
 			chi = max(chi, chrom[k]);
 		}
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	clo = __reduce_min_sync(0xffffffffu, clo);
+	chi = __reduce_max_sync(0xffffffffu, chi);
+	// genomic coordinates almost always fit 31 bits: then the hull is two 32-bit warp reductions
+	const bool small = okmask == 0 || (uint64_t)mx < 0x7fffffffull; // windows are clamped to >= 0, so mn <= mx < 2^31 too
+	if (__all_sync(0xffffffffu, small)) {
+		const int m1 = __reduce_min_sync(0xffffffffu, okmask ? (int)mn : INT_MAX);
+		const int m2 = __reduce_max_sync(0xffffffffu, okmask ? (int)mx : INT_MIN);
+		mn = m1 == INT_MAX ? INT64_MAX : (int64_t)m1;
+		mx = m2 == INT_MIN ? INT64_MIN : (int64_t)m2;
+	} else {
 #pragma unroll
-	for (int k = 16; k > 0; k >>= 1) {
-		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, k));
-		mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, k));
-		clo = min(clo, __shfl_xor_sync(0xffffffffu, clo, k));
-		chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, k));
+		for (int k = 16; k > 0; k >>= 1) {
+			mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, k));
+			mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+		}
 	}
 	if (lane == 0) {
 		sm.red_min[warp] = mn;
@@ -563,8 +611,7 @@ __device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table
 					const int64_t a = lo > 0 ? lo - 1 : 0, b = min(hi + 1, ch.n); // one neighbour on each side
 					first = a;
 					const int64_t cnt = b - a;
-					const int64_t lim = 0x7fffffff;
-					if (cnt > MG_SF_CAP || mx - mn > lim || mn - __ldg(ch.start + a) > lim || __ldg(ch.end + b - 1) - mn > lim)
+					if (cnt > MG_SF_CAP || mx - mn > MG_SF_RANGE || mn - __ldg(ch.start + a) > MG_SF_RANGE || __ldg(ch.end + b - 1) - mn > MG_SF_RANGE)
 						mode = 0;
 					else
 						n = (int)cnt;
@@ -580,24 +627,32 @@ __device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table
 	if (sm.mode == 1 && sm.n > 0) {
 		const SparseChrom ch = table[sm.chrom];
 		const int64_t origin = sm.origin, lo = sm.lo;
-		for (int t = threadIdx.x; t < sm.n; t += MG_SP_THREADS) {
-			sm.start[t] = (int)(__ldg(ch.start + lo + t) - origin);
-			sm.end[t] = (int)(__ldg(ch.end + lo + t) - origin);
-			if (want_val)
-				sm.val[t] = __ldg(ch.val + lo + t);
+		const int n = sm.n;
+		for (int t = threadIdx.x; t < n + 3; t += MG_SP_THREADS) {
+			int st = t == 0 ? -MG_SF_SENT : MG_SF_SENT, en = st;
+			float v = mg_nanf();
+			if (t >= 1 && t <= n) {
+				st = (int)(__ldg(ch.start + lo + t - 1) - origin);
+				en = (int)(__ldg(ch.end + lo + t - 1) - origin);
+				if (want_val)
+					v = __ldg(ch.val + lo + t - 1);
+			}
+			sm.start[t] = st;
+			sm.end[t] = en;
+			sm.val[t] = v;
 		}
 	}
 	__syncthreads();
 }
 
-// first staged record with end > a, searching forward from lo (a few linear steps, then a binary search)
+// first staged index >= lo with end > a (the right sentinel always qualifies): a few linear steps, then a binary search
 __device__ __forceinline__ int mg_sf_advance(const int *__restrict__ end, int n, int lo, int a)
 {
 	int steps = 0;
-	while (lo < n && end[lo] <= a) {
+	while (end[lo] <= a) {
 		++lo;
 		if (++steps == 4) {
-			int hi = n;
+			int hi = n + 1;
 			while (lo < hi) {
 				const int mid = (lo + hi) >> 1;
 				if (end[mid] > a)
@@ -625,14 +680,182 @@ __device__ __forceinline__ void mg_sparse_rows_search(const SparseQuery &q)
 		int64_t s, e;
 		const bool ok = mg_sp_row_window(q, i, rc, c, s, e);
 		const SparseChrom ch = q.table[ok ? c : 0];
-		mg_sparse_row(q, SpLocal{ch.start, ch.end, ch.val, ch.n}, ok, s, e, i);
+		mg_sparse_row<false>(q, SpLocal{ch.start, ch.end, ch.val, ch.n}, ok, s, e, i);
 	}
 }
 
+// ---- regular-grid blocks -------------------------------------------------------------------------------------------------
+// A block of implicit fixed-bin rows that lies strictly inside one scope interval with no clamped window is a regular grid:
+// row j's window is [origin + j * binsize, + len). Every thread derives that from blockIdx alone -- no per-row coordinate
+// arithmetic, no hull reduction, no elected thread: the coarse-index lookups are uniform loads and the block stages its
+// records after ONE barrier.
+struct SfGrid {
+	int chrom;
+	int64_t origin; // window start of the block's first row
+	int len;        // window length
+	int nrows;      // rows of this block
+};
+
+template <typename Q>
+__device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
+{
+	if (q.rows.kind != 1)
+		return false;
+	const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS);
+	const int64_t nrows = min((int64_t)(MG_SP_THREADS * MG_SF_ROWS), q.count - i0);
+	const int64_t r0 = q.first + i0, r1 = r0 + nrows - 1;
+	const int64_t k = mg_scope_of_row(q.rows, r0);
+	const int64_t row0 = __ldg(q.rows.srow0 + k), row1 = __ldg(q.rows.srow0 + k + 1);
+	if (!(r0 > row0 && r1 < row1 - 1)) // first / last row of a scope interval may be cut by its ends
+		return false;
+	const int64_t binsize = q.rows.binsize;
+	g.chrom = __ldg(q.rows.schrom + k);
+	const int64_t w0 = (__ldg(q.rows.sbin0 + k) + (r0 - row0)) * binsize + q.sshift, len = binsize + q.eshift - q.sshift;
+	const int64_t span = (nrows - 1) * binsize + len;
+	if (w0 < 0 || len <= 0 || span > MG_SF_RANGE || w0 + span > __ldg(q.chrom_sizes + g.chrom))
+		return false;
+	g.origin = w0;
+	g.len = (int)len;
+	g.nrows = (int)nrows;
+	return true;
+}
+
+// stages the records a regular-grid block can touch; false = does not fit (count or 32-bit range): use the search path
+__device__ __forceinline__ bool mg_sf_stage_grid(SfSmem &sm, const SparseChrom *table, const SfGrid &g, int64_t binsize, bool want_val, int &n_out)
+{
+	const SparseChrom ch = table[g.chrom];
+	int n = 0;
+	int64_t first = 0;
+	bool bad = false;
+	if (ch.n > 0) {
+		const int64_t hull_end = g.origin + (int64_t)(g.nrows - 1) * binsize + g.len;
+		const int64_t c0 = min(g.origin >> ch.coarse_shift, ch.ncoarse - 1), c1 = min((hull_end >> ch.coarse_shift) + 1, ch.ncoarse - 1);
+		const int64_t lo = (int64_t)__ldg(ch.coarse + c0), hi = (int64_t)__ldg(ch.coarse + c1) + 1;
+		first = lo > 0 ? lo - 1 : 0;
+		const int64_t cnt = min(hi + 1, ch.n) - first;
+		bad = cnt > MG_SF_CAP;
+		n = bad ? 0 : (int)cnt;
+		for (int t = threadIdx.x; t < n + 3; t += MG_SP_THREADS) {
+			int st = t == 0 ? -MG_SF_SENT : MG_SF_SENT, en = st;
+			float v = mg_nanf();
+			if (t >= 1 && t <= n) {
+				const int64_t rs = __ldg(ch.start + first + t - 1) - g.origin, re = __ldg(ch.end + first + t - 1) - g.origin;
+				bad |= rs < -MG_SF_RANGE || re > MG_SF_RANGE;
+				st = (int)rs;
+				en = (int)re;
+				if (want_val)
+					v = __ldg(ch.val + first + t - 1);
+			}
+			sm.start[t] = st;
+			sm.end[t] = en;
+			sm.val[t] = v;
+		}
+	}
+	n_out = n;
+	return !__syncthreads_or(bad);
+}
+
+// Statistics of one window [a, b) over the staged records (indices 1..n between sentinels); lo = this lane's cursor.
+struct SpVals {
+	double avg, sum, mn, mx, nearest, size, exists;
+};
+
 template <bool SUM, bool MM>
+__device__ __forceinline__ void mg_sf_eval(const SfSmem &sm, int n, int &lo, int a, int b, SpVals &o)
+{
+	o.avg = o.sum = o.mn = o.mx = o.nearest = mg_nan();
+	o.size = 0;
+	o.exists = 0;
+	if (n <= 0)
+		return;
+	lo = mg_sf_advance(sm.end, n, lo, a);
+	const int s0 = sm.start[lo];
+	if (!(sm.start[lo + 1] < b)) {
+		// at most one record overlaps the window (src/GenomeTrackSparse.cpp:281-338): its value is every statistic;
+		// otherwise the closer neighbour (ties to the earlier record) is `nearest` and nothing else is defined
+		const bool ov = s0 < b;
+		const int dp = a - sm.end[lo - 1], dn = s0 - b; // end[lo-1] <= a < b <= start[lo] when nothing overlaps
+		const float v = sm.val[(ov || dp > dn) ? lo : lo - 1];
+		o.nearest = (double)v;
+		if (ov && !isnan(v)) {
+			o.avg = o.sum = o.mn = o.mx = (double)v;
+			o.size = 1;
+			o.exists = 1;
+		}
+		return;
+	}
+	int cnt = 0;
+	double S = 0;
+	float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
+	for (int r = lo; sm.start[r] < b; ++r) { // record order = the reference's order
+		const float v = sm.val[r];
+		if (isnan(v))
+			continue;
+		if (SUM)
+			S += (double)v;
+		if (MM) {
+			fmin = fminf(fmin, v);
+			fmax = fmaxf(fmax, v);
+		}
+		++cnt;
+	}
+	o.size = (double)cnt;
+	if (cnt > 0) {
+		o.exists = 1;
+		if (SUM) {
+			o.avg = o.nearest = mg_f2d(cnt == 1 ? S : S / (double)cnt);
+			o.sum = mg_f2d(S);
+		}
+		if (MM) {
+			o.mn = (double)fmin;
+			o.mx = (double)fmax;
+		}
+	}
+}
+
+// F = the single requested function (one store per row, everything else compiled out) or -1 = any subset of the basic ones.
+template <int F>
+__device__ __forceinline__ void mg_sf_store(const SparseQuery &q, int64_t i, const SpVals &o)
+{
+	if (F >= 0) {
+		const double v = F == MG_AVG ? o.avg : F == MG_NEAREST ? o.nearest : F == MG_SUM ? o.sum : F == MG_MIN ? o.mn : F == MG_MAX ? o.mx : F == MG_SIZE ? o.size : o.exists;
+		mg_st_stream(q.out[F] + i, v);
+	} else {
+		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, o.avg);
+		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, o.nearest);
+		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, o.sum);
+		if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, o.mn);
+		if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, o.mx);
+		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, o.size);
+		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, o.exists);
+	}
+}
+
+template <int F>
 __global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_merge(const SparseQuery q)
 {
 	__shared__ SfSmem sm;
+	constexpr bool SUM = F < 0 || F == MG_AVG || F == MG_SUM || F == MG_NEAREST, MM = F < 0 || F == MG_MIN || F == MG_MAX;
+	SfGrid g;
+	if (mg_sf_grid_block(q, g)) { // block-uniform
+		int n;
+		if (!mg_sf_stage_grid(sm, q.table, g, q.rows.binsize, true, n)) {
+			mg_sparse_rows_search(q);
+			return;
+		}
+		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
+		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + j0;
+		int a = j0 * (int)q.rows.binsize, lo = 1;
+#pragma unroll
+		for (int k = 0; k < MG_SF_ROWS; ++k, a += step) {
+			if (j0 + 32 * k >= g.nrows)
+				break;
+			SpVals o;
+			mg_sf_eval<SUM, MM>(sm, n, lo, a, a + g.len, o);
+			mg_sf_store<F>(q, i0 + 32 * k, o);
+		}
+		return;
+	}
 	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
 	int chrom[MG_SF_ROWS];
 	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
@@ -643,119 +866,105 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_merge(const SparseQuer
 	}
 	const int64_t origin = sm.origin;
 	const int n = sm.n;
-	int lo = 0, prev = INT_MIN;
+	int lo = 1, prev = INT_MIN;
 #pragma unroll
 	for (int k = 0; k < MG_SF_ROWS; ++k) {
 		const int64_t i = mg_sf_row(q, k);
 		if (i >= q.count)
 			break;
-		double avg = mg_nan(), sum = mg_nan(), vmn = mg_nan(), vmx = mg_nan(), nearest = mg_nan(), size = mg_nan(), exists = mg_nan();
+		SpVals o;
+		o.avg = o.sum = o.mn = o.mx = o.nearest = o.size = o.exists = mg_nan();
 		if ((okmask >> k) & 1u) {
 			const int a = (int)(ws[k] - origin), b = (int)(we[k] - origin);
 			if (a < prev)
-				lo = 0; // unsorted rows: restart
+				lo = 1; // unsorted rows: restart
 			prev = a;
-			size = 0;
-			exists = 0;
-			if (n > 0) {
-				lo = mg_sf_advance(sm.end, n, lo, a);
-				if (lo == n)
-					nearest = (double)sm.val[n - 1]; // after the last record (src/GenomeTrackSparse.cpp:286-289)
-				else if (sm.start[lo] < b) {
-					int cnt = 0;
-					double S = 0;
-					float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
-					for (int r = lo; r < n && sm.start[r] < b; ++r) { // record order = the reference's order
-						const float v = sm.val[r];
-						if (isnan(v))
-							continue;
-						if (SUM)
-							S += (double)v;
-						if (MM) {
-							fmin = fminf(fmin, v);
-							fmax = fmaxf(fmax, v);
-						}
-						++cnt;
-					}
-					size = (double)cnt;
-					if (cnt > 0) {
-						exists = 1;
-						if (SUM) {
-							avg = nearest = mg_f2d(cnt == 1 ? S : S / (double)cnt);
-							sum = mg_f2d(S);
-						}
-						if (MM) {
-							vmn = (double)fmin;
-							vmx = (double)fmax;
-						}
-					}
-				} else if (lo == 0)
-					nearest = (double)sm.val[0]; // before the first record (:281-284)
-				else {
-					// no overlap: end[lo-1] <= a < b <= start[lo]; the closer neighbour, ties to the earlier record (:336-338)
-					const int dp = a - sm.end[lo - 1], dn = sm.start[lo] - b;
-					nearest = (double)sm.val[dp <= dn ? lo - 1 : lo];
-				}
+			mg_sf_eval<SUM, MM>(sm, n, lo, a, b, o);
+		}
+		mg_sf_store<F>(q, i, o);
+	}
+}
+
+// coverage of [a, b) by the staged source intervals: 0 / len and len / len need no divide (most rows of a fine iterator lie
+// fully outside or inside a source interval)
+__device__ __forceinline__ double mg_sf_coverage(const SfSmem &sm, int n, int &lo, int a, int b)
+{
+	int total = 0;
+	if (n > 0) {
+		lo = mg_sf_advance(sm.end, n, lo, a);
+		for (int r = lo; sm.start[r] < b; ++r)
+			total += min(b, sm.end[r]) - max(a, sm.start[r]);
+	}
+	return total == 0 ? 0. : (total == b - a ? 1. : (double)total / (double)(b - a));
+}
+
+__device__ __forceinline__ void mg_coverage_rows_search(const CoverageQuery &q)
+{
+	RowCache rc;
+#pragma unroll 1
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		const int64_t i = mg_sf_row(q, k);
+		if (i >= q.count)
+			break;
+		double cov = mg_nan();
+		int c;
+		int64_t s, e;
+		if (mg_sp_row_window(q, i, rc, c, s, e)) {
+			const SparseChrom ch = q.table[c];
+			int64_t lo = 0, hi = ch.n;
+			while (lo < hi) {
+				const int64_t mid = lo + ((hi - lo) >> 1);
+				if (ch.end[mid] > s)
+					hi = mid;
+				else
+					lo = mid + 1;
 			}
+			int64_t total = 0;
+			for (int64_t r = lo; r < ch.n; ++r) {
+				const int64_t rs = ch.start[r];
+				if (rs >= e)
+					break;
+				const int64_t re = ch.end[r];
+				total += (e < re ? e : re) - (s > rs ? s : rs);
+			}
+			cov = (double)total / (double)(e - s);
 		}
-		if (SUM) {
-			if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
-			if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, nearest);
-			if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
-		}
-		if (MM) {
-			if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, vmn);
-			if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, vmx);
-		}
-		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
-		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+		mg_st_stream(q.out + i, cov);
 	}
 }
 
 __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage_merge(const CoverageQuery q)
 {
 	__shared__ SfSmem sm;
+	SfGrid g;
+	if (mg_sf_grid_block(q, g)) { // block-uniform
+		int n;
+		if (!mg_sf_stage_grid(sm, q.table, g, q.rows.binsize, false, n)) {
+			mg_coverage_rows_search(q);
+			return;
+		}
+		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
+		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + j0;
+		int a = j0 * (int)q.rows.binsize, lo = 1;
+#pragma unroll
+		for (int k = 0; k < MG_SF_ROWS; ++k, a += step) {
+			if (j0 + 32 * k >= g.nrows)
+				break;
+			mg_st_stream(q.out + i0 + 32 * k, mg_sf_coverage(sm, n, lo, a, a + g.len));
+		}
+		return;
+	}
 	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
 	int chrom[MG_SF_ROWS];
 	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
 	mg_sf_stage(sm, q.table, okmask, ws, we, chrom, false);
 	if (sm.mode == 0) {
-		RowCache rc;
-#pragma unroll 1
-		for (int k = 0; k < MG_SF_ROWS; ++k) {
-			const int64_t i = mg_sf_row(q, k);
-			if (i >= q.count)
-				break;
-			double cov = mg_nan();
-			int c;
-			int64_t s, e;
-			if (mg_sp_row_window(q, i, rc, c, s, e)) {
-				const SparseChrom ch = q.table[c];
-				int64_t lo = 0, hi = ch.n;
-				while (lo < hi) {
-					const int64_t mid = lo + ((hi - lo) >> 1);
-					if (ch.end[mid] > s)
-						hi = mid;
-					else
-						lo = mid + 1;
-				}
-				int64_t total = 0;
-				for (int64_t r = lo; r < ch.n; ++r) {
-					const int64_t rs = ch.start[r];
-					if (rs >= e)
-						break;
-					const int64_t re = ch.end[r];
-					total += (e < re ? e : re) - (s > rs ? s : rs);
-				}
-				cov = (double)total / (double)(e - s);
-			}
-			mg_st_stream(q.out + i, cov);
-		}
+		mg_coverage_rows_search(q);
 		return;
 	}
 	const int64_t origin = sm.origin;
 	const int n = sm.n;
-	int lo = 0, prev = INT_MIN;
+	int lo = 1, prev = INT_MIN;
 #pragma unroll
 	for (int k = 0; k < MG_SF_ROWS; ++k) {
 		const int64_t i = mg_sf_row(q, k);
@@ -765,19 +974,9 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage_merge(const Coverage
 		if ((okmask >> k) & 1u) {
 			const int a = (int)(ws[k] - origin), b = (int)(we[k] - origin);
 			if (a < prev)
-				lo = 0;
+				lo = 1;
 			prev = a;
-			lo = mg_sf_advance(sm.end, n, lo, a);
-			int total = 0;
-			for (int r = lo; r < n; ++r) {
-				const int rs = sm.start[r];
-				if (rs >= b)
-					break;
-				const int re = sm.end[r];
-				total += min(b, re) - max(a, rs);
-			}
-			// 0 / len and len / len need no divide (most rows of a fine iterator are fully outside or inside a source interval)
-			cov = total == 0 ? 0. : (total == b - a ? 1. : (double)total / (double)(b - a));
+			cov = mg_sf_coverage(sm, n, lo, a, b);
 		}
 		mg_st_stream(q.out + i, cov);
 	}

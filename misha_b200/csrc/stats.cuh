@@ -278,9 +278,13 @@ __device__ __forceinline__ void mg_stream_segtable(const SegTable &st, F &&f)
 	}
 }
 
-__global__ void __launch_bounds__(MG_SUM_THREADS) k_segs_summary(const SegTable st, int64_t nrows, Moments *block_out)
+// The last block to finish (ticket counter) merges the per-block partials in index order and accumulates them into the
+// caller's 6-double record: one launch per gsummary call, and the reduction order is fixed whatever the block schedule.
+__global__ void __launch_bounds__(MG_SUM_THREADS) k_segs_summary(const SegTable st, int64_t nrows, Moments *block_out, unsigned *ticket,
+																  double *partial)
 {
 	__shared__ Moments sm[MG_SUM_THREADS / 32];
+	__shared__ bool is_last;
 	MomF mf{0ull, 0., 0., __int_as_float(0x7f800000), __int_as_float(0xff800000)};
 	mg_stream_segtable(st, [&](float v) { momf_add(mf, v); });
 	Moments m;
@@ -291,8 +295,38 @@ __global__ void __launch_bounds__(MG_SUM_THREADS) k_segs_summary(const SegTable 
 	m.mn = mf.nn ? (double)mf.mn : 1.7976931348623157e308;
 	m.mx = mf.nn ? (double)mf.mx : -1.7976931348623157e308;
 	mom_block_reduce(m, sm);
-	if (threadIdx.x == 0)
+	if (threadIdx.x == 0) {
 		block_out[blockIdx.x] = m;
+		__threadfence();
+		is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (!is_last)
+		return;
+	__threadfence();
+	mom_init(m);
+	for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+	{
+		const double *p = reinterpret_cast<const double *>(block_out + i); // written by other blocks: read through L2
+		Moments o;
+		o.n = __ldcg(p);
+		o.nn = __ldcg(p + 1);
+		o.sum = __ldcg(p + 2);
+		o.mn = __ldcg(p + 3);
+		o.mx = __ldcg(p + 4);
+		o.ssq = __ldcg(p + 5);
+		mom_merge(m, o);
+	}
+	mom_block_reduce(m, sm);
+	if (threadIdx.x == 0) {
+		partial[0] += m.n;
+		partial[1] += m.nn;
+		partial[2] += m.sum;
+		partial[3] = fmin(partial[3], m.mn);
+		partial[4] = fmax(partial[4], m.mx);
+		partial[5] += m.ssq;
+		*ticket = 0; // ready for the next launch on this stream
+	}
 }
 
 // ---- histogram -----------------------------------------------------------------------------------------------------------
@@ -417,7 +451,7 @@ __device__ __forceinline__ int mg_float_bin(const float *__restrict__ thr, int n
 }
 
 // Thresholds travel as a kernel parameter (no upload, no synchronisation). With equal-width breaks the bin is guessed with
-// one float multiply and corrected against the exact thresholds (the guess is off by at most one or two).
+// one float multiply and checked against the exact thresholds on both sides (two shared-memory loads); a wrong guess walks.
 struct FloatThr {
 	int nb;
 	int uniform;
@@ -425,19 +459,19 @@ struct FloatThr {
 	float thr[MG_HIST_PRIVATE_MAX + 1];
 };
 
-__device__ __forceinline__ int mg_float_bin_guess(const float *__restrict__ thr, int nb, float b0, float inv, float v)
+// shared-memory accesses by 32-bit shared address: keeps the base in a register (the compiler otherwise re-derives the
+// shared window base for every access of an extern __shared__ array reached through a pointer)
+__device__ __forceinline__ float mg_lds_f(uint32_t a)
 {
-	if (isnan(v))
-		return -1;
-	// c = number of thresholds below v, c in [0, nb + 1]
-	float g = (v - b0) * inv + 1.f;
-	g = fminf(fmaxf(g, 0.f), (float)(nb + 1));
-	int c = (int)g;
-	while (c <= nb && thr[c] < v)
-		++c;
-	while (c > 0 && !(thr[c - 1] < v))
-		--c;
-	return c == nb + 1 ? -1 : c - 1;
+	float v;
+	asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void mg_smem_inc(uint32_t a)
+{
+	uint32_t c;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(a) : "memory");
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(c + 1u) : "memory");
 }
 
 __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st, const FloatThr ft, unsigned long long *counts)
@@ -445,26 +479,38 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 	extern __shared__ __align__(16) uint32_t hsmem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int nb = ft.nb;
-	float *thr = reinterpret_cast<float *>(hsmem);
-	const int thr_words = (nb + 1 + 3) & ~3;
+	// P[0] = -inf, P[j] = thr[j-1] (j = 1..nb+1), P[nb+2] = +inf: c = #thresholds below v is right iff P[c] < v <= P[c+1]
+	float *P = reinterpret_cast<float *>(hsmem);
+	const int thr_words = (nb + 3 + 3) & ~3;
 	uint32_t *hall = hsmem + thr_words, *h = hall + warp * nb * 32;
-	for (int t = threadIdx.x; t <= nb; t += blockDim.x)
-		thr[t] = ft.thr[t];
+	for (int t = threadIdx.x; t <= nb + 2; t += blockDim.x)
+		P[t] = t == 0 ? __int_as_float(0xff800000) : (t == nb + 2 ? __int_as_float(0x7f800000) : ft.thr[t - 1]);
 	for (int t = lane; t < nb * 32; t += 32)
 		h[t] = 0;
 	__syncthreads();
+	const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(P);
+	const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(h) + 4u * lane - 128u; // column of bin c - 1 at hbase + 128 c
 	if (ft.uniform) {
-		const float b0 = ft.b0, inv = ft.inv_binsize;
+		const float b0 = ft.b0, inv = ft.inv_binsize, top = (float)(nb + 1);
 		mg_stream_segtable(st, [&](float v) {
-			const int b = mg_float_bin_guess(thr, nb, b0, inv, v);
-			if (b >= 0)
-				h[b * 32 + lane]++;
+			if (v != v)
+				return;
+			int c = (int)fminf(fmaxf((v - b0) * inv + 1.f, 0.f), top);
+			const float t0 = mg_lds_f(pbase + 4u * c), t1 = mg_lds_f(pbase + 4u * c + 4u);
+			if (!(t0 < v) || t1 < v) { // the float guess missed: walk to the right count (sentinels bound both walks)
+				while (mg_lds_f(pbase + 4u * c + 4u) < v)
+					++c;
+				while (!(mg_lds_f(pbase + 4u * c) < v))
+					--c;
+			}
+			if ((unsigned)(c - 1) < (unsigned)nb)
+				mg_smem_inc(hbase + 128u * c);
 		});
 	} else {
 		mg_stream_segtable(st, [&](float v) {
-			const int b = mg_float_bin(thr, nb, v);
+			const int b = mg_float_bin(P + 1, nb, v);
 			if (b >= 0)
-				h[b * 32 + lane]++;
+				mg_smem_inc(hbase + 128u * (b + 1));
 		});
 	}
 	__syncthreads();
