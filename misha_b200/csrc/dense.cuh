@@ -2,9 +2,11 @@
 //
 // HBM layout per chromosome:
 //   vals[nbins (+pad)]  float32, +-inf already turned into NaN (read_bins_bulk, src/GenomeTrackFixedBin.cpp:1066-1069)
-//   pref[nbins + 1]     16-byte entries {double sum of non-NaN vals[0..i), int64 count of non-NaN vals[0..i)}
-// avg / sum / size / exists of any window are two 16-byte lookups (kernel k_dense_prefix); min / max / stddev /
-// quantile sweep the window with one warp per row (kernel k_dense_sweep).
+//   p8[ngroups + 1]     16-byte entries {double sum, int64 count} of the non-NaN vals[0..8g): one entry per group of 8 bins
+//                       (2 bytes per bin: rows that are 15 bins apart stream this array instead of gathering 64-byte
+//                       DRAM granules out of a 16-bytes-per-bin one)
+// avg / sum / size / exists of a window = partial head group + (p8 difference over the full groups) + partial tail group;
+// the two partial groups are the same 32-byte sectors the min / max pyramid reads at level 0 (mg_win_basic).
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
@@ -18,7 +20,7 @@ struct __align__(16) Pref {
 
 struct DenseChrom {
 	const float *vals;
-	const Pref *pref;
+	const Pref *p8;  // per group of 8 bins: totals over vals[0..8g), g = 0..ceil(nbins / 8)
 	int64_t nbins;
 	double abs_sum; // sum |v| over the chromosome: scale of the prefix rounding error (cancellation guard)
 	const double *pref2; // pref2[i] = sum of squares of the non-NaN vals[0..i) (stddev)
@@ -55,6 +57,7 @@ struct DenseQuery {
 	const int64_t *chrom_sizes;
 	uint32_t bin_size;
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
+	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
 	int nq;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
 	double q_pct[MG_MAX_Q];
@@ -238,17 +241,28 @@ __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, D
 	if (!mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we))
 		return false;
 	w.ch = q.table + chrom;
-	w.sbin = mg_floordiv(ws, q.bin_size);                 // src/GenomeTrackFixedBin.cpp:675
-	int64_t eb = mg_ceildiv(we, q.bin_size);              // :676
+	int64_t eb;
+	if ((uint64_t)we <= 0xffffffffull - q.bin_size && q.bin_magic) { // 0 <= ws < we: both fit the magic-number division
+		w.sbin = (int64_t)__umul64hi((uint64_t)ws, q.bin_magic);             // src/GenomeTrackFixedBin.cpp:675
+		eb = (int64_t)__umul64hi((uint64_t)we + q.bin_size - 1, q.bin_magic); // :676
+	} else {
+		w.sbin = mg_floordiv(ws, q.bin_size);
+		eb = mg_ceildiv(we, q.bin_size);
+	}
 	int64_t nb = w.ch->nbins;
 	w.ebin = eb < nb ? eb : nb;                           // read_bins_bulk clamp :1036-1041
 	return true;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_dense_prefix: one thread per row; avg / sum / nearest / size / exists from two 16-byte prefix entries.
-// Windows of <= 4 bins, and windows whose prefix difference is small against the accumulated rounding scale
-// (catastrophic cancellation), are summed directly in bin order, which reproduces the reference bit for bit.
+// p8 entries from the per-bin prefix the staging pass produces (which is then released)
+__global__ void __launch_bounds__(256) k_p8_build(const Pref *__restrict__ pref, int64_t nbins, Pref *__restrict__ p8, int64_t nentries)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < nentries)
+		p8[g] = pref[min(g * 8, nbins)];
+}
+
 #define MG_PREFIX_DIRECT_BINS 4
 
 __device__ __forceinline__ Pref mg_ld_pref(const Pref *p)
@@ -260,50 +274,142 @@ __device__ __forceinline__ Pref mg_ld_pref(const Pref *p)
 	return o;
 }
 
+// bins [lo, hi) of the aligned group of 8 starting at bin 8 g: one 32-byte sector. Sum in bin order (exact for the few
+// floats involved), non-NaN count, extrema.
+template <bool SUM, bool MM>
+__device__ __forceinline__ void mg_part8(const float *__restrict__ vals, int64_t g, int lo, int hi, double &S, int &n, float &mx, float &mn)
+{
+	const float4 a = __ldg(reinterpret_cast<const float4 *>(vals + 8 * g));
+	const float4 b = __ldg(reinterpret_cast<const float4 *>(vals + 8 * g + 4));
+	const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const bool in = j >= lo && j < hi && v[j] == v[j];
+		if (SUM)
+			S += in ? (double)v[j] : 0.;
+		n += in ? 1 : 0;
+		if (MM) {
+			mx = fmaxf(mx, in ? v[j] : __int_as_float(0xff800000));
+			mn = fminf(mn, in ? v[j] : __int_as_float(0x7f800000));
+		}
+	}
+}
+
+// Sum / count / extrema of bins [sbin, ebin), sbin < ebin. The full groups [gs, ge) in between are NOT covered by mx / mn
+// (the caller continues in the pyramid from level 1 with that range); S and n cover the whole window.
+struct WinBasic {
+	double S;
+	long long n;
+	long long before; // non-NaN bins of the chromosome before sbin (the window's start in the compacted order)
+	float mx, mn;     // over the partial head / tail groups only
+	int64_t gs, ge;   // full groups of the window; gs >= ge when there are none
+};
+
+template <bool SUM, bool MM>
+__device__ __forceinline__ void mg_win_basic(const DenseChrom *ch, int64_t sbin, int64_t ebin, WinBasic &w)
+{
+	const float *vals = ch->vals;
+	double S = 0;
+	int n = 0;
+	float mx = __int_as_float(0xff800000), mn = __int_as_float(0x7f800000);
+	const int64_t g0 = sbin >> 3, g1 = (ebin - 1) >> 3;
+	w.gs = 1;
+	w.ge = 0;
+	if (g0 == g1) { // inside one group
+		mg_part8<SUM, MM>(vals, g0, (int)(sbin - 8 * g0), (int)(ebin - 8 * g0), S, n, mx, mn);
+		w.S = S;
+		w.n = n;
+		w.before = -1; // not known without a p8 entry: mg_win_before()
+	} else {
+		int nh = 0;
+		const int64_t gs = (sbin + 7) >> 3, ge = ebin >> 3;
+		if (sbin & 7)
+			mg_part8<SUM, MM>(vals, g0, (int)(sbin & 7), 8, S, nh, mx, mn);
+		const Pref a = mg_ld_pref(ch->p8 + gs), b = mg_ld_pref(ch->p8 + ge); // gs <= ge here
+		double Sm = b.sum - a.sum;
+		int nt = 0;
+		double St = 0;
+		if (ebin & 7)
+			mg_part8<SUM, MM>(vals, ge, 0, (int)(ebin & 7), St, nt, mx, mn);
+		w.S = (S + Sm) + St;
+		w.n = (long long)nh + (b.cnt - a.cnt) + nt;
+		w.before = a.cnt - nh;
+		w.gs = gs;
+		w.ge = ge;
+	}
+	w.mx = mx;
+	w.mn = mn;
+}
+
+// non-NaN bins before sbin for a window that lies inside one group (the chromosome-wide wavelet matrix needs it)
+__device__ __forceinline__ long long mg_win_before(const DenseChrom *ch, int64_t sbin)
+{
+	const int64_t g0 = sbin >> 3;
+	double S = 0;
+	int n = 0;
+	float mx = 0, mn = 0;
+	mg_part8<false, false>(ch->vals, g0, 0, (int)(sbin - 8 * g0), S, n, mx, mn);
+	return mg_ld_pref(ch->p8 + g0).cnt + n;
+}
+
+// sum of the window in bin order, the reference's arithmetic (src/GenomeTrackFixedBin.cpp:476-591)
+__device__ __forceinline__ double mg_win_direct_sum(const DenseChrom *ch, int64_t sbin, int64_t ebin)
+{
+	double S = 0;
+	for (int64_t t = sbin; t < ebin; ++t) {
+		const float v = __ldg(ch->vals + t);
+		if (!isnan(v))
+			S += (double)v;
+	}
+	return S;
+}
+
+// avg / sum / nearest / size / exists of one row. Windows inside two groups are summed in bin order (bit-exact); a
+// window whose sum is small against the accumulated rounding scale of the prefix (catastrophic cancellation) is re-summed
+// directly.
+struct RowSum {
+	double avg, sum, size, exists;
+};
+
+__device__ __forceinline__ void mg_row_sum(const DenseChrom *ch, const WinBasic &w, int64_t sbin, int64_t ebin, RowSum &r)
+{
+	double S = w.S;
+	// rounding of each prefix entry is O(2^-53 * abs_sum); demand >= ~2^-27 relative accuracy of S
+	if (w.gs < w.ge && w.n > 0 && fabs(S) < ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */)
+		S = mg_win_direct_sum(ch, sbin, ebin);
+	r.size = (double)w.n;
+	r.exists = w.n > 0 ? 1. : 0.;
+	r.avg = r.sum = mg_nan();
+	if (w.n > 0) {
+		r.avg = mg_f2d(S / (double)w.n);
+		r.sum = mg_f2d(S);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_dense_prefix: one thread per row; avg / sum / nearest / size / exists.
 __global__ void __launch_bounds__(256) k_dense_prefix(const DenseQuery q)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.count)
 		return;
 	DenseWin w;
-	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan();
+	RowSum r;
+	r.avg = r.sum = r.size = r.exists = mg_nan();
 	if (mg_dense_win(q, q.first + i, w)) {
-		long long n = 0;
-		double S = 0;
-		const int64_t nb = w.ebin - w.sbin;
-		bool direct = nb <= MG_PREFIX_DIRECT_BINS;
-		if (!direct && nb > 0) {
-			const Pref a = mg_ld_pref(w.ch->pref + w.sbin);
-			const Pref b = mg_ld_pref(w.ch->pref + w.ebin);
-			n = b.cnt - a.cnt;
-			S = b.sum - a.sum;
-			// rounding of each prefix entry is O(2^-53 * abs_sum); demand >= ~2^-27 relative accuracy of S
-			if (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */)
-				direct = true;
-		}
-		if (direct) {
-			n = 0;
-			S = 0;
-			for (int64_t b = w.sbin; b < w.ebin; ++b) {
-				float v = __ldg(w.ch->vals + b);
-				if (!isnan(v)) {
-					S += (double)v;
-					++n;
-				}
-			}
-		}
-		size = (double)n;
-		exists = n > 0 ? 1. : 0.;
-		if (n > 0) {
-			avg = mg_f2d(S / (double)n);
-			sum = mg_f2d(S);
+		r.size = 0;
+		r.exists = 0;
+		if (w.ebin > w.sbin) {
+			WinBasic wb;
+			mg_win_basic<true, false>(w.ch, w.sbin, w.ebin, wb);
+			mg_row_sum(w.ch, wb, w.sbin, w.ebin, r);
 		}
 	}
-	if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
-	if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, avg);
-	if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
-	if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
-	if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+	if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, r.avg);
+	if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, r.avg);
+	if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, r.sum);
+	if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, r.size);
+	if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, r.exists);
 }
 
 // ------------------------------------------------------------------------------------------------------------

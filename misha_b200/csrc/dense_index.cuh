@@ -52,13 +52,12 @@ __device__ __forceinline__ float mg_group_ext(const float *__restrict__ p, int64
 	return acc;
 }
 
-// extremum of bins [s, e), s < e. Returns -inf (max) / +inf (min) when every bin is NaN.
+// extremum of entries [lo, hi) of pyramid level `level` (0 = the bins themselves) folded into acc; -inf (max) / +inf (min)
+// when every bin is NaN
 template <bool IS_MAX>
-__device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, int64_t e)
+__device__ __forceinline__ float mg_pyr_query_from(const DenseChrom *ch, int level, int64_t lo, int64_t hi, float acc)
 {
-	float acc = IS_MAX ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
-	int64_t lo = s, hi = e;
-	for (int level = 0; lo < hi; ++level) {
+	for (; lo < hi; ++level) {
 		const float *p = level == 0 ? ch->vals : (IS_MAX ? ch->pmax[level - 1] : ch->pmin[level - 1]);
 		const int64_t glo = lo & ~7ll, ghi = hi & ~7ll;
 		if (glo == ghi || (glo + 8 == hi)) { // the whole range sits in one group
@@ -76,6 +75,12 @@ __device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, i
 		hi = ghi >> 3;
 	}
 	return acc;
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ float mg_pyr_query(const DenseChrom *ch, int64_t s, int64_t e)
+{
+	return mg_pyr_query_from<IS_MAX>(ch, 0, s, e, IS_MAX ? __int_as_float(0xff800000) : __int_as_float(0x7f800000));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -364,21 +369,30 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 	if (i >= q.count)
 		return;
 	DenseWin w;
-	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan(), sd = mg_nan();
+	RowSum rs;
+	rs.avg = rs.sum = rs.size = rs.exists = mg_nan();
+	double mn = mg_nan(), mx = mg_nan(), sd = mg_nan();
 	const bool ok = mg_dense_win(q, q.first + i, w);
 	const int64_t nb = ok ? w.ebin - w.sbin : 0;
-	long long n = 0;
-	Pref a, b;
-	a.cnt = b.cnt = 0;
+	WinBasic wb;
+	wb.n = 0;
+	wb.before = 0;
+	if (ok) {
+		rs.size = 0;
+		rs.exists = 0;
+	}
 	if (nb > 0) {
-		if (SUM || Q || SD) {
-			a = mg_ld_pref(w.ch->pref + w.sbin);
-			b = mg_ld_pref(w.ch->pref + w.ebin);
-			n = b.cnt - a.cnt;
+		// one pass over the window's two partial groups feeds the sum, the count and level 0 of the pyramids
+		mg_win_basic<SUM || SD, MM>(w.ch, w.sbin, w.ebin, wb);
+		if (SUM || SD)
+			mg_row_sum(w.ch, wb, w.sbin, w.ebin, rs);
+		else {
+			rs.size = (double)wb.n;
+			rs.exists = wb.n > 0 ? 1. : 0.;
 		}
-		if (SD && n > 1) {
-			const double S1 = b.sum - a.sum, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
-			double m2 = S2 - S1 * S1 / (double)n;
+		if (SD && wb.n > 1) {
+			const double S1 = wb.S, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
+			double m2 = S2 - S1 * S1 / (double)wb.n;
 			// trust the difference only while it keeps ~9 significant digits
 			if (nb <= MG_SD_DIRECT_BINS || !(m2 > S2 * 1e-7) || !(m2 > w.ch->sq_sum * 1e-7)) {
 				long long c = 0;
@@ -394,46 +408,21 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 					}
 				}
 			}
-			sd = mg_f2d(sqrt(m2 / (double)(n - 1)));
+			sd = mg_f2d(sqrt(m2 / (double)(wb.n - 1)));
 		}
-		if (SUM) {
-			double S = b.sum - a.sum;
-			if (nb <= MG_PREFIX_DIRECT_BINS || (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)) {
-				S = 0;
-				for (int64_t t = w.sbin; t < w.ebin; ++t) {
-					const float v = __ldg(w.ch->vals + t);
-					if (!isnan(v))
-						S += (double)v;
-				}
-			}
-			if (n > 0) {
-				avg = mg_f2d(S / (double)n);
-				sum = mg_f2d(S);
-			}
+		if (MM && wb.n > 0) {
+			if (q.out[MG_MAX])
+				mx = (double)mg_pyr_query_from<true>(w.ch, 1, wb.gs, wb.ge, wb.mx);
+			if (q.out[MG_MIN])
+				mn = (double)mg_pyr_query_from<false>(w.ch, 1, wb.gs, wb.ge, wb.mn);
 		}
-		if (MM) {
-			if (q.out[MG_MAX]) {
-				const float v = mg_pyr_query<true>(w.ch, w.sbin, w.ebin);
-				if (v != __int_as_float(0xff800000))
-					mx = (double)v;
-			}
-			if (q.out[MG_MIN]) {
-				const float v = mg_pyr_query<false>(w.ch, w.sbin, w.ebin);
-				if (v != __int_as_float(0x7f800000))
-					mn = (double)v;
-			}
-		}
-	}
-	if (ok) {
-		size = (double)n;
-		exists = n > 0 ? 1. : 0.;
 	}
 	if (SUM) {
-		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, avg);
-		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, avg);
-		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, sum);
-		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, size);
-		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, rs.avg);
+		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, rs.avg);
+		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, rs.sum);
+		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, rs.size);
+		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, rs.exists);
 	}
 	if (MM) {
 		if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
@@ -443,9 +432,13 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 		mg_st_stream(q.out[MG_STDDEV] + i, sd);
 	if (Q) {
 		// every quantile column is stored as soon as it is known (a per-thread array indexed by k would live in local memory)
+		const long long n = wb.n;
 		const bool use_bw = q.use_bw && nb <= MG_BW_S;
 		const int64_t blk = w.sbin >> (MG_BW_LB - 1);
 		const uint32_t l = (uint32_t)w.sbin & (MG_BW_S - 1);
+		long long before = wb.before;
+		if (!use_bw && n > 0 && before < 0)
+			before = mg_win_before(w.ch, w.sbin);
 		for (int k = 0; k < q.nq; ++k) {
 			double qv = mg_nan();
 			if (n > 0) {
@@ -460,7 +453,7 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 					mg_bw_select(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, w.ch->vals + blk * MG_BW_S, l, l + (uint32_t)nb, (uint32_t)i1, want2,
 								 x1, x2);
 				else
-					mg_wm_select(w.ch, (uint32_t)a.cnt, (uint32_t)b.cnt, (uint32_t)i1, want2, x1, x2);
+					mg_wm_select(w.ch, (uint32_t)before, (uint32_t)(before + n), (uint32_t)i1, want2, x1, x2);
 				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
 			}
 			mg_st_stream(q.q_out[k] + i, qv);

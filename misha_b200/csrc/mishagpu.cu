@@ -188,7 +188,7 @@ extern "C" int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out)
 }
 
 // min/max pyramids + wavelet matrix of one staged chromosome (dense_index.cuh)
-static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
+static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const Pref *pref /* per-bin, staging only */)
 {
 	const int64_t nbins = dc.nbins;
 	// pyramids: level j+1 exists while level j has more than one group of 8
@@ -221,7 +221,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 	}
 	// wavelet matrix over the dense ranks of the non-NaN values
 	long long m = 0;
-	MG_CUDA(ctx, cudaMemcpy(&m, &dc.pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
+	MG_CUDA(ctx, cudaMemcpy(&m, &pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
 	dc.wm_m = m;
 	dc.wm_blocks = m / 32 + 1; // position m itself must be addressable
 	int nlevels = 0;
@@ -247,7 +247,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc)
 	MG_CUDA(ctx, cudaMalloc(&scratch, sizeof(uint2) * dc.wm_blocks));
 	MG_CUDA(ctx, cudaMalloc(&d_zero, sizeof(uint32_t)));
 	if (nbins) {
-		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, dc.pref, nbins, keys[0], pos[0]);
+		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, pref, nbins, keys[0], pos[0]);
 		MG_LAUNCH_CHECK(ctx);
 	}
 	const unsigned gm = (unsigned)mg_div_up(m > 0 ? m : 1, 256), gb = (unsigned)mg_div_up(dc.wm_blocks, 256);
@@ -317,8 +317,9 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	float *vals = nullptr;
 	Pref *pref = nullptr;
 	const int64_t padded = (nbins + 7) / 8 * 8 + 8; // group-of-8 / float4-safe tail, NaN filled
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals) || mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref))
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals))
 		return 1;
+	MG_CUDA(ctx, cudaMalloc(&pref, sizeof(Pref) * (size_t)(nbins + 1))); // per-bin prefix: staging scratch, released below
 	MG_CUDA(ctx, cudaMemset(vals, 0xff, sizeof(float) * padded)); // 0xffffffff is a NaN
 	if (nbins)
 		MG_CUDA(ctx, cudaMemcpy(vals, h_bins, sizeof(float) * nbins, cudaMemcpyHostToDevice));
@@ -341,7 +342,15 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	DenseChrom dc;
 	memset(&dc, 0, sizeof(dc));
 	dc.vals = vals;
-	dc.pref = pref;
+	{
+		const int64_t nent = mg_div_up(nbins, 8) + 1;
+		Pref *p8 = nullptr;
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nent, &p8))
+			return 1;
+		k_p8_build<<<(unsigned)mg_div_up(nent, 256), 256>>>(pref, nbins, p8, nent);
+		MG_LAUNCH_CHECK(ctx);
+		dc.p8 = p8;
+	}
 	dc.nbins = nbins;
 	dc.pref2 = pref2;
 	{
@@ -350,8 +359,9 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 		dc.abs_sum = tot[0];
 		dc.sq_sum = tot[1];
 	}
-	if (mg_dense_build_index(ctx, t, dc))
+	if (mg_dense_build_index(ctx, t, dc, pref))
 		return 1;
+	cudaFree(pref);
 	t->h_table[chromid] = dc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &dc, sizeof(DenseChrom), cudaMemcpyHostToDevice));
 	cudaFree(tile_sum);
@@ -532,6 +542,7 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.table = t->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.bin_size = t->bin_size;
+	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
 	q.use_bw = ctx->block_wm ? 1 : 0;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {

@@ -127,35 +127,20 @@ __device__ __forceinline__ double mg_dense_row_value(const DenseQuery &q, int64_
 	DenseWin w;
 	if (!mg_dense_win(q, row, w))
 		return mg_nan();
-	long long n = 0;
-	double S = 0;
-	const int64_t nb = w.ebin - w.sbin;
-	bool direct = nb <= MG_PREFIX_DIRECT_BINS;
-	if (!direct) {
-		const Pref a = mg_ld_pref(w.ch->pref + w.sbin), b = mg_ld_pref(w.ch->pref + w.ebin);
-		n = b.cnt - a.cnt;
-		S = b.sum - a.sum;
-		if (n > 0 && fabs(S) < w.ch->abs_sum * 1.4901161193847656e-08)
-			direct = true;
-	}
-	if (direct) {
-		n = 0;
-		S = 0;
-		for (int64_t b = w.sbin; b < w.ebin; ++b) {
-			const float v = __ldg(w.ch->vals + b);
-			if (!isnan(v)) {
-				S += (double)v;
-				++n;
-			}
-		}
+	RowSum r;
+	r.avg = r.sum = mg_nan();
+	r.size = 0;
+	r.exists = 0;
+	if (w.ebin > w.sbin) {
+		WinBasic wb;
+		mg_win_basic<true, false>(w.ch, w.sbin, w.ebin, wb);
+		mg_row_sum(w.ch, wb, w.sbin, w.ebin, r);
 	}
 	if (func == MG_SIZE)
-		return (double)n;
+		return r.size;
 	if (func == MG_EXISTS)
-		return n > 0 ? 1. : 0.;
-	if (n == 0)
-		return mg_nan();
-	return func == MG_SUM ? mg_f2d(S) : mg_f2d(S / (double)n);
+		return r.exists;
+	return func == MG_SUM ? r.sum : r.avg;
 }
 
 __global__ void __launch_bounds__(MG_SUM_THREADS) k_dense_summary(const DenseQuery q, int func, Moments *block_out)
