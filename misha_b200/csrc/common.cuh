@@ -29,6 +29,7 @@ struct mg_ctx {
 	int64_t pipe_chunk_rows = 1 << 19; // rows per slot of the host-buffer pipeline (measured best of 2^17..2^22 on B200 / PCIe Gen5)
 	bool zero_copy = false; // host-buffer entry points: kernels read rows / write columns straight in pinned host memory.
 	                        // Measured SLOWER than the 3-slot DMA pipeline on B200 (5.9 vs 5.3 ms for C3), hence off by default.
+	bool prefetch = true;    // row-query kernels prefetch their block record / window lines (off: ablation)
 	bool block_wm = true;    // quantiles of windows <= MG_BW_S bins walk the block-local wavelet matrices (off: ablation / tests of the
 	                         // chromosome-wide matrix)
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
@@ -96,6 +97,8 @@ __device__ __forceinline__ double mg_f2d(double x) { return (double)__double2flo
 __device__ __forceinline__ float mg_ldg_f(const float *p) { return __ldg(p); }
 
 __device__ __forceinline__ void mg_st_stream(double *p, double v) { __stcs(p, v); }
+
+__device__ __forceinline__ void mg_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Window transform, src/TrackExpressionVars.h:395-402. Returns false when out of range.
 __device__ __forceinline__ bool mg_window(int64_t start, int64_t end, int64_t sshift, int64_t eshift, int64_t chromsize, int64_t &ws,

@@ -59,6 +59,7 @@ struct DenseQuery {
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
 	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
 	int nq;
+	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
@@ -305,7 +306,7 @@ struct WinBasic {
 	int64_t gs, ge;   // full groups of the window; gs >= ge when there are none
 };
 
-template <bool SUM, bool MM>
+template <bool SUM, bool MM, bool CNT = true>
 __device__ __forceinline__ void mg_win_basic(const DenseChrom *ch, int64_t sbin, int64_t ebin, WinBasic &w)
 {
 	const float *vals = ch->vals;
@@ -313,29 +314,32 @@ __device__ __forceinline__ void mg_win_basic(const DenseChrom *ch, int64_t sbin,
 	int n = 0;
 	float mx = __int_as_float(0xff800000), mn = __int_as_float(0x7f800000);
 	const int64_t g0 = sbin >> 3, g1 = (ebin - 1) >> 3;
-	w.gs = 1;
-	w.ge = 0;
 	if (g0 == g1) { // inside one group
 		mg_part8<SUM, MM>(vals, g0, (int)(sbin - 8 * g0), (int)(ebin - 8 * g0), S, n, mx, mn);
 		w.S = S;
 		w.n = n;
 		w.before = -1; // not known without a p8 entry: mg_win_before()
+		w.gs = 1;
+		w.ge = 0;
 	} else {
-		int nh = 0;
-		const int64_t gs = (sbin + 7) >> 3, ge = ebin >> 3;
-		if (sbin & 7)
-			mg_part8<SUM, MM>(vals, g0, (int)(sbin & 7), 8, S, nh, mx, mn);
-		const Pref a = mg_ld_pref(ch->p8 + gs), b = mg_ld_pref(ch->p8 + ge); // gs <= ge here
-		double Sm = b.sum - a.sum;
-		int nt = 0;
+		// head group g0 from sbin on, tail group g1 up to ebin, full groups (g0, g1) in between: six independent loads
+		// (2 x 2 x 16 bytes of bins + two p8 entries) issued back to back, one memory round trip
+		Pref a, b;
+		a.sum = b.sum = 0;
+		a.cnt = b.cnt = 0;
+		if (SUM || CNT) {
+			a = mg_ld_pref(ch->p8 + g0 + 1);
+			b = mg_ld_pref(ch->p8 + g1);
+		}
+		int nh = 0, nt = 0;
 		double St = 0;
-		if (ebin & 7)
-			mg_part8<SUM, MM>(vals, ge, 0, (int)(ebin & 7), St, nt, mx, mn);
-		w.S = (S + Sm) + St;
+		mg_part8<SUM, MM>(vals, g0, (int)(sbin & 7), 8, S, nh, mx, mn);
+		mg_part8<SUM, MM>(vals, g1, 0, (int)(ebin - 8 * g1), St, nt, mx, mn);
+		w.S = (S + (b.sum - a.sum)) + St;
 		w.n = (long long)nh + (b.cnt - a.cnt) + nt;
 		w.before = a.cnt - nh;
-		w.gs = gs;
-		w.ge = ge;
+		w.gs = g0 + 1;
+		w.ge = g1;
 	}
 	w.mx = mx;
 	w.mn = mn;

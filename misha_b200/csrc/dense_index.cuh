@@ -381,9 +381,21 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 		rs.size = 0;
 		rs.exists = 0;
 	}
+	if (Q && q.prefetch && nb > 0 && nb <= MG_BW_S && q.use_bw) {
+		// Rows that are neighbours in position share their block record (76 lines of 128 bytes) and most of their window:
+		// every thread asks for two lines of its record and one line of its window, so between them the rows of a block
+		// pull all of it towards L1 / L2 long before the dependent loads of the walk arrive.
+		const uint8_t *rec = w.ch->bw + (size_t)(w.sbin >> (MG_BW_LB - 1)) * MG_BW_RECORD_BYTES;
+		const unsigned t = threadIdx.x;
+		mg_prefetch(rec + ((2 * t) % (MG_BW_RECORD_BYTES / 128)) * 128);
+		mg_prefetch(rec + ((2 * t + 1) % (MG_BW_RECORD_BYTES / 128)) * 128);
+		const int64_t pb = w.sbin + (int64_t)(t & 15) * 32;
+		if (pb < w.ebin)
+			mg_prefetch(w.ch->vals + pb);
+	}
 	if (nb > 0) {
 		// one pass over the window's two partial groups feeds the sum, the count and level 0 of the pyramids
-		mg_win_basic<SUM || SD, MM>(w.ch, w.sbin, w.ebin, wb);
+		mg_win_basic<SUM || SD, MM, SUM || SD || Q>(w.ch, w.sbin, w.ebin, wb);
 		if (SUM || SD)
 			mg_row_sum(w.ch, wb, w.sbin, w.ebin, rs);
 		else {
@@ -410,11 +422,17 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 			}
 			sd = mg_f2d(sqrt(m2 / (double)(wb.n - 1)));
 		}
-		if (MM && wb.n > 0) {
-			if (q.out[MG_MAX])
-				mx = (double)mg_pyr_query_from<true>(w.ch, 1, wb.gs, wb.ge, wb.mx);
-			if (q.out[MG_MIN])
-				mn = (double)mg_pyr_query_from<false>(w.ch, 1, wb.gs, wb.ge, wb.mn);
+		if (MM) { // an extremum still at its -inf / +inf seed means the window holds no value
+			if (q.out[MG_MAX]) {
+				const float v = mg_pyr_query_from<true>(w.ch, 1, wb.gs, wb.ge, wb.mx);
+				if (v != __int_as_float(0xff800000))
+					mx = (double)v;
+			}
+			if (q.out[MG_MIN]) {
+				const float v = mg_pyr_query_from<false>(w.ch, 1, wb.gs, wb.ge, wb.mn);
+				if (v != __int_as_float(0x7f800000))
+					mn = (double)v;
+			}
 		}
 	}
 	if (SUM) {

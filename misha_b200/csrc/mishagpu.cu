@@ -81,6 +81,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->force_sweep = value != 0;
 		return 0;
 	}
+	if (name && !strcmp(name, "prefetch")) {
+		ctx->prefetch = value != 0;
+		return 0;
+	}
 	if (name && !strcmp(name, "block_wm")) {
 		ctx->block_wm = value != 0;
 		return 0;
@@ -544,6 +548,7 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.bin_size = t->bin_size;
 	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
 	q.use_bw = ctx->block_wm ? 1 : 0;
+	q.prefetch = ctx->prefetch ? 1 : 0;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {
 		const int f = funcs[k];
