@@ -16,6 +16,7 @@ struct __align__(16) Pref {
 	long long cnt;
 };
 
+#define MG_ST_LEVELS 12 // sparse-table levels: windows of up to 2^12 groups = 32768 bins without touching the pyramid
 #define MG_PYR_MAX 14 // fan-out 8 levels above the raw bins: enough for 2^45 bins
 
 struct DenseChrom {
@@ -28,6 +29,11 @@ struct DenseChrom {
 	// index structures (dense_index.cuh)
 	const float *pmax[MG_PYR_MAX];
 	const float *pmin[MG_PYR_MAX];
+	// sparse tables over the groups of 8: smax[j][g] = max of groups [g, g + 2^j) (j = 0 is pmax[0]): the extremum of any run of
+	// fewer than 2^MG_ST_LEVELS full groups is two lookups
+	const float *smax[MG_ST_LEVELS];
+	const float *smin[MG_ST_LEVELS];
+	int64_t ngroups;
 	const uint2 *wm;          // wavelet matrix over RANK keys, wm_levels x wm_blocks units {ones before, 32 bits}
 	const uint32_t *wm_zeros; // zeros per level
 	int64_t wm_blocks;

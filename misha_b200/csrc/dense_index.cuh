@@ -38,6 +38,40 @@ __global__ void __launch_bounds__(256) k_pyr_build(const float *__restrict__ chi
 	pmin[i] = mn;
 }
 
+// sparse-table level j from level j - 1: out[g] = ext(in[g], in[g + half]) (the second operand only where it exists)
+__global__ void __launch_bounds__(256) k_st_build(const float *__restrict__ in_max, const float *__restrict__ in_min, int64_t n, int64_t half,
+												   float *out_max, float *out_min)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n)
+		return;
+	float mx = in_max[g], mn = in_min[g];
+	if (g + half < n) {
+		mx = fmaxf(mx, in_max[g + half]);
+		mn = fminf(mn, in_min[g + half]);
+	}
+	out_max[g] = mx;
+	out_min[g] = mn;
+}
+
+// extremum of the full groups [gs, ge) folded into acc: two sparse-table lookups, or the pyramid for very long runs
+template <bool IS_MAX>
+__device__ __forceinline__ float mg_pyr_query_from(const DenseChrom *ch, int level, int64_t lo, int64_t hi, float acc);
+
+template <bool IS_MAX>
+__device__ __forceinline__ float mg_groups_ext(const DenseChrom *ch, int64_t gs, int64_t ge, float acc)
+{
+	const int64_t len = ge - gs;
+	if (len <= 0)
+		return acc;
+	if (len >= (1ll << MG_ST_LEVELS))
+		return mg_pyr_query_from<IS_MAX>(ch, 1, gs, ge, acc);
+	const int j = 31 - __clz((int)len);
+	const float *t = IS_MAX ? ch->smax[j] : ch->smin[j];
+	const float a = __ldg(t + gs), b = __ldg(t + ge - (1ll << j));
+	return IS_MAX ? fmaxf(acc, fmaxf(a, b)) : fminf(acc, fminf(a, b));
+}
+
 // extremum over entries [lo, hi) of one aligned group of 8 (lo, hi within [g, g+8]); two 16-byte loads = one sector
 template <bool IS_MAX>
 __device__ __forceinline__ float mg_group_ext(const float *__restrict__ p, int64_t g, int lo, int hi, float acc)
@@ -424,12 +458,12 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 		}
 		if (MM) { // an extremum still at its -inf / +inf seed means the window holds no value
 			if (q.out[MG_MAX]) {
-				const float v = mg_pyr_query_from<true>(w.ch, 1, wb.gs, wb.ge, wb.mx);
+				const float v = mg_groups_ext<true>(w.ch, wb.gs, wb.ge, wb.mx);
 				if (v != __int_as_float(0xff800000))
 					mx = (double)v;
 			}
 			if (q.out[MG_MIN]) {
-				const float v = mg_pyr_query_from<false>(w.ch, 1, wb.gs, wb.ge, wb.mn);
+				const float v = mg_groups_ext<false>(w.ch, wb.gs, wb.ge, wb.mn);
 				if (v != __int_as_float(0x7f800000))
 					mn = (double)v;
 			}

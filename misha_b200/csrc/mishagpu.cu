@@ -213,6 +213,37 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 			nchild = nparent;
 		}
 	}
+	// sparse tables over the groups of 8 (level 0 = pyramid level 1)
+	{
+		const int64_t ng = mg_div_up(nbins > 0 ? nbins : 1, 8);
+		dc.ngroups = ng;
+		if (!dc.pmax[0]) { // chromosomes of <= 8 bins have no pyramid level: build the single group entry
+			float *pmax = nullptr, *pmin = nullptr;
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmin))
+				return 1;
+			k_pyr_build<<<1, 256>>>(dc.vals, dc.vals, nbins, pmax, pmin, 16);
+			MG_LAUNCH_CHECK(ctx);
+			dc.smax[0] = pmax;
+			dc.smin[0] = pmin;
+		} else {
+			dc.smax[0] = dc.pmax[0];
+			dc.smin[0] = dc.pmin[0];
+		}
+		for (int j = 1; j < MG_ST_LEVELS; ++j) {
+			if ((1ll << j) > ng) { // never selected: a run of len groups uses level floor(log2 len)
+				dc.smax[j] = dc.smax[j - 1];
+				dc.smin[j] = dc.smin[j - 1];
+				continue;
+			}
+			float *smax = nullptr, *smin = nullptr;
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smin))
+				return 1;
+			k_st_build<<<(unsigned)mg_div_up(ng, 256), 256>>>(dc.smax[j - 1], dc.smin[j - 1], ng, 1ll << (j - 1), smax, smin);
+			MG_LAUNCH_CHECK(ctx);
+			dc.smax[j] = smax;
+			dc.smin[j] = smin;
+		}
+	}
 	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
 	{
 		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_S);
