@@ -49,47 +49,58 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every ~3 ms through NVML while the timed regions run (nvidia-smi's own
+    polling is too coarse for regions that last tens of milliseconds). mark(True/False) brackets the timed regions; only
+    samples taken inside them count."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.proc = None
+        self.samples = []
+        self.active = False
+        self.stop_flag = False
+        self.err = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.lines = []
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001 -- no NVML: report it, never fail the bench
+            self.err = "nvml unavailable: %s" % e
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        nv = self.nv
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:  # noqa: BLE001 -- older bindings
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append((sm, rs))
+                except Exception as e:  # noqa: BLE001
+                    self.err = str(e)
+                    return
+            time.sleep(0.003)
+
+    def mark(self, on):
+        self.active = on
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v == "Active":
-                    reasons.add(name)
-        # "under load" = samples at or above the median (idle samples between regions pull the raw median down)
-        load = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.err and not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err], "samples": 0}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        sm = [x for x, _ in self.samples]
+        reasons = sorted({name for _, rs in self.samples for name, bit in self.REASONS if rs & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm),
+                "how": "NVML, ~3 ms period, inside the timed regions only"}
 
 
 def build_workload(args, rank, world):
@@ -182,11 +193,15 @@ def run_ours(args):
     barrier()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark(True)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    if sampler:
+        sampler.mark(False)
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     launches = ctx.launch_count() - launches0
 
@@ -194,11 +209,15 @@ def run_ours(args):
     for _ in range(2):
         dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
     barrier()
+    if sampler:
+        sampler.mark(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    if sampler:
+        sampler.mark(False)
     launches += ctx.launch_count() - launches0 - launches
 
     # ---- per-kernel timing for the roofline (each function group alone, same stream, CUDA events) ----
@@ -210,11 +229,15 @@ def run_ours(args):
             dense.window_dev(rows, funcs, SSHIFT, ESHIFT, out=outs, stream=stream)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.mark(True)
         a.record()
         for _ in range(args.steps):
             dense.window_dev(rows, funcs, SSHIFT, ESHIFT, out=outs, stream=stream)
         b.record()
         torch.cuda.synchronize()
+        if sampler:
+            sampler.mark(False)
         ms = a.elapsed_time(b) / args.steps
         alg = 4 * nbins_mine + n_mine * (20 + 8 * len(funcs))  # unique track bytes + interval in + value columns out
         kernels.append({"kernel": name, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6})
@@ -239,7 +262,11 @@ def run_ours(args):
     # the step is one fused launch today; the dominant kernel is the step's kernel
     dom = kernels[-1]
     alg_total_launch = dom["alg_bytes"]
-    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": None,
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the step's kernel, from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if world == 1 and args.intervals == N_INTERVALS and args.scale == 1.0 and os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_dense_rowquery[avg+max+quantile(0.9)]")
+    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic,
                 "kernel": dom["kernel"], "alg_bytes_per_launch": alg_total_launch, "peak_source": peak_src,
                 "per_kernel": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels]}
 
@@ -254,7 +281,7 @@ def run_ours(args):
         "config": {"workload": "C3: gextract avg/max/quantile(0.9) vtracks, sshift/eshift +-5kb, %d sorted intervals (100-300 bp), "
                                "20 bp dense track on a synthetic %.2f Gbp genome (24 hg38-length chromosomes)" % (n_total, sum(sizes) / 1e9),
                    "intervals": n_total, "bin_size": BIN, "funcs": ["avg", "max", "quantile(0.9)"], "sharding": "chromosomes, LPT over ranks",
-                   "l2_policy": "inputs larger than L2 (track 0.62 GB + prefix 2.5 GB + intervals 0.2 GB vs 126 MB L2)",
+                   "l2_policy": "inputs larger than L2 (track 0.62 GB + index structures 3 GB touched + intervals 0.2 GB vs 126 MB L2)",
                    "staging_s_one_time": round(stage_s, 3), "hbm_bytes_staged_rank0": dense.bytes()},
         "e2e": {"value": n_total / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n_mine * 20), "d2h_bytes_per_step": int(n_mine * 8 * len(FUNCS)),
                 "ms_per_step": e2e_s * 1e3, "api": "mg_h_dense_window (pinned host arrays in, host columns out)"},

@@ -29,6 +29,7 @@ struct mg_ctx {
 	int64_t pipe_chunk_rows = 1 << 19; // rows per slot of the host-buffer pipeline (measured best of 2^17..2^22 on B200 / PCIe Gen5)
 	bool zero_copy = false; // host-buffer entry points: kernels read rows / write columns straight in pinned host memory.
 	                        // Measured SLOWER than the 3-slot DMA pipeline on B200 (5.9 vs 5.3 ms for C3), hence off by default.
+	bool pwm_strict = false; // PWM strand / anchor log-sum-exp with double-precision exp / log (correctly rounded float results)
 	bool prefetch = true;    // row-query kernels prefetch their block record / window lines (off: ablation)
 	bool block_wm = true;    // quantiles of windows <= MG_BW_S bins walk the block-local wavelet matrices (off: ablation / tests of the
 	                         // chromosome-wide matrix)

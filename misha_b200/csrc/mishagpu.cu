@@ -81,6 +81,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->force_sweep = value != 0;
 		return 0;
 	}
+	if (name && !strcmp(name, "pwm_strict")) {
+		ctx->pwm_strict = value != 0;
+		return 0;
+	}
 	if (name && !strcmp(name, "prefetch")) {
 		ctx->prefetch = value != 0;
 		return 0;
@@ -1266,7 +1270,24 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 	q.out = d_out;
 	const int64_t blocks_needed = mg_div_up(count, MG_PWM_WARPS);
 	const int64_t cap = (int64_t)ctx->sm_count * 16;
-	k_pwm<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), MG_PWM_WARPS * 32, 0, st>>>(q);
+	const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
+#define MG_PWM_LAUNCH(B, M)                                                                                              \
+	do {                                                                                                                \
+		if (ctx->pwm_strict)                                                                                            \
+			k_pwm<B, M, true><<<grid, MG_PWM_WARPS * 32, 0, st>>>(q);                                                    \
+		else                                                                                                            \
+			k_pwm<B, M, false><<<grid, MG_PWM_WARPS * 32, 0, st>>>(q);                                                   \
+	} while (0)
+	if (bidirect) {
+		if (mode == MG_PWM_TOTAL) MG_PWM_LAUNCH(true, MG_PWM_TOTAL);
+		else if (mode == MG_PWM_MAX) MG_PWM_LAUNCH(true, MG_PWM_MAX);
+		else MG_PWM_LAUNCH(true, MG_PWM_COUNT);
+	} else {
+		if (mode == MG_PWM_TOTAL) MG_PWM_LAUNCH(false, MG_PWM_TOTAL);
+		else if (mode == MG_PWM_MAX) MG_PWM_LAUNCH(false, MG_PWM_MAX);
+		else MG_PWM_LAUNCH(false, MG_PWM_COUNT);
+	}
+#undef MG_PWM_LAUNCH
 	MG_LAUNCH_CHECK(ctx);
 	MG_CUDA(ctx, cudaFreeAsync(d_tab, st));
 	return 0;

@@ -77,30 +77,39 @@ struct PwmQuery {
 	double *out;
 };
 
-// src/util.h:16-28 evaluated in float exactly as the host does, with expf/logf taken as the correctly rounded values
-// (double evaluation rounded to float) -- glibc's float expf/logf are correctly rounded in all but rare cases.
+// src/util.h:16-28. STRICT: expf / logf taken as the correctly rounded values (double evaluation rounded to float; glibc's
+// are correctly rounded in all but rare cases) -- two double-precision transcendentals per anchor, which is what bounds the
+// kernel. Default: CUDA's float expf (<= 2 ulp) and logf (<= 1 ulp): the strand sum moves by <= ~3e-7 absolute, i.e.
+// ~1e-8 relative to a 20-mer's log-likelihood, far inside the 1e-6 bar (mg_set_option("pwm_strict", 1) restores STRICT).
+template <bool STRICT>
 __device__ __forceinline__ float mg_log1pexp_f(float d)
 {
-	const float t = (float)exp((double)d);
-	const float u = __fadd_rn(1.0f, t);
-	return (float)log((double)u);
+	if (STRICT) {
+		const float t = (float)exp((double)d);
+		const float u = __fadd_rn(1.0f, t);
+		return (float)log((double)u);
+	}
+	return logf(__fadd_rn(1.0f, expf(d)));
 }
+template <bool STRICT>
 __device__ __forceinline__ float mg_log_sum_log(float l1, float l2)
 {
 	if (l1 > l2) {
 		if (!isinf(l2))
-			l1 = __fadd_rn(l1, mg_log1pexp_f(__fsub_rn(l2, l1)));
+			l1 = __fadd_rn(l1, mg_log1pexp_f<STRICT>(__fsub_rn(l2, l1)));
 		return l1;
 	}
 	if (isinf(l1))
 		return l2;
-	return __fadd_rn(l2, mg_log1pexp_f(__fsub_rn(l1, l2)));
+	return __fadd_rn(l2, mg_log1pexp_f<STRICT>(__fsub_rn(l1, l2)));
 }
 
+// BID: both strands combined per anchor; MODE: MG_PWM_TOTAL / MAX / COUNT; STRICT: see mg_log1pexp_f
+template <bool BID, int MODE, bool STRICT>
 __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 {
 	__shared__ float2 stab[MG_PWM_MAXL * 5];
-	__shared__ __align__(4) uint8_t stile[MG_PWM_WARPS][MG_PWM_TILE];
+	__shared__ __align__(16) uint8_t stile[MG_PWM_WARPS][MG_PWM_TILE + 16];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int L = q.L;
 	for (int t = threadIdx.x; t < L * 5; t += blockDim.x)
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 			const int64_t tlen = xe - ws;
 			if (tlen < L) {
 				if (q.extend) // score_without_spatial over zero anchors (src/PWMScorer.cpp:313-338)
-					result = q.mode == MG_PWM_COUNT ? 0. : (double)NEG_INF;
+					result = MODE == MG_PWM_COUNT ? 0. : (double)NEG_INF;
 			} else {
 				int64_t i_max = tlen - L;
 				const int64_t want = we - ws - 1;
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 				// decode bases [ws + a0, ws + a0 + CHUNK + L - 1) into the tile
 				const int need = MG_PWM_CHUNK + L - 1;
 				__syncwarp();
-				for (int t = lane; t < need; t += 32) {
+				for (int t = lane; t < need + 3; t += 32) {
 					const int64_t p = ws + a0 + t;
 					uint8_t code = 4;
 					if (p < xe) {
@@ -160,15 +169,40 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 				}
 				__syncwarp();
 				float f[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
-				const uint8_t *tb = tile + 4 * lane;
-				for (int k = 0; k < L; ++k) {
-					const int j = rev ? L - 1 - k : k;
-					const float2 *row = stab + j * 5;
+				if (!rev) {
+					// the lane's 4 anchors read bases 4 lane + j + u: one aligned word of the tile per 4 motif positions, byte
+					// offsets known at compile time
+					const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + lane;
+					uint32_t w0 = tw[0];
+					for (int j0 = 0; j0 < L; j0 += 4) {
+						const uint32_t w1 = tw[(j0 >> 2) + 1];
 #pragma unroll
-					for (int u = 0; u < 4; ++u) {
-						const float2 tt = row[tb[j + u]];
-						f[u] = __fadd_rn(f[u], tt.x);
-						r[u] = __fadd_rn(r[u], tt.y);
+						for (int jj = 0; jj < 4; ++jj) {
+							if (j0 + jj < L) {
+								const float2 *row = stab + (j0 + jj) * 5;
+#pragma unroll
+								for (int u = 0; u < 4; ++u) {
+									const int b = jj + u; // byte b of the 8 bytes {w0, w1}
+									const uint32_t code = ((b < 4 ? w0 >> (8 * b) : w1 >> (8 * (b - 4))) & 0xffu);
+									const float2 tt = row[code];
+									f[u] = __fadd_rn(f[u], tt.x);
+									r[u] = __fadd_rn(r[u], tt.y);
+								}
+							}
+						}
+						w0 = w1;
+					}
+				} else {
+					const uint8_t *tb = tile + 4 * lane;
+					for (int k = 0; k < L; ++k) {
+						const int j = L - 1 - k;
+						const float2 *row = stab + j * 5;
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const float2 tt = row[tb[j + u]];
+							f[u] = __fadd_rn(f[u], tt.x);
+							r[u] = __fadd_rn(r[u], tt.y);
+						}
 					}
 				}
 #pragma unroll
@@ -177,26 +211,38 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 					if (a >= na)
 						continue;
 					float v;
-					if (q.bidirect)
-						v = mg_log_sum_log(f[u], r[u]);
+					if (BID)
+						v = mg_log_sum_log<STRICT>(f[u], r[u]);
 					else
 						v = rev ? r[u] : f[u];
-					if (q.mode == MG_PWM_TOTAL) {
+					if (MODE == MG_PWM_TOTAL) {
 						if (v != NEG_INF) {
 							const double dv = (double)v;
-							if (dv > m_run) {
-								s_run = s_run * exp(m_run - dv) + 1.;
-								m_run = dv;
-							} else
-								s_run += exp(dv - m_run);
+							if (STRICT) {
+								if (dv > m_run) {
+									s_run = s_run * exp(m_run - dv) + 1.;
+									m_run = dv;
+								} else
+									s_run += exp(dv - m_run);
+							} else {
+								// same recurrence (src/utils/RunningLogSumExp.h:32-45) with the exponential in float: each term is
+								// good to ~2.4e-7 relative, the log of their sum to the same absolute error
+								const float d = (float)fabs(dv - m_run);
+								const double ex = (double)expf(-d);
+								if (dv > m_run) {
+									s_run = s_run * ex + 1.;
+									m_run = dv;
+								} else
+									s_run += ex;
+							}
 						}
-					} else if (q.mode == MG_PWM_MAX)
+					} else if (MODE == MG_PWM_MAX)
 						vmax = fmaxf(vmax, v);
 					else
 						hits += v >= q.thresh ? 1 : 0;
 				}
 			}
-			if (q.mode == MG_PWM_TOTAL) {
+			if (MODE == MG_PWM_TOTAL) {
 				double M = m_run;
 #pragma unroll
 				for (int k = 16; k > 0; k >>= 1)
@@ -204,7 +250,7 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
 				double sc = (m_run == -INFINITY) ? 0. : s_run * exp(m_run - M);
 				sc = mg_warp_sum_d(sc);
 				result = (M == -INFINITY) ? (double)NEG_INF : mg_f2d(M + log(sc));
-			} else if (q.mode == MG_PWM_MAX) {
+			} else if (MODE == MG_PWM_MAX) {
 #pragma unroll
 				for (int k = 16; k > 0; k >>= 1)
 					vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, k));

@@ -294,3 +294,30 @@ def test_merge_kernels_vs_search_kernels_and_oracle():
         assert_same(newc, oldc, "fixed-bin coverage")
     finally:
         ctx2.close()
+
+
+def test_pwm_float_and_strict_transcendentals_agree(gpu_ctx, seq_testdb, golden):
+    """Default: float expf / logf per anchor; pwm_strict: double exp / log rounded to float. Both within the 1e-6 bar of each
+    other (and of the reference, test_pwm_golden); pure-float modes are identical."""
+    logp = gpu.pssm_logp(golden["pwm_pssm20"], 0.01)
+    rng = np.random.default_rng(23)
+    size = CHROMS[0][1]
+    s = np.sort(rng.integers(0, size - 600, 3000))
+    e = s + rng.integers(1, 600, 3000)
+    rows = gpu_ctx.rows_upload(np.zeros(3000, np.int32), s, e)
+    res = {}
+    for strict in (0, 1):
+        gpu_ctx.set_option("pwm_strict", strict)
+        try:
+            for bid in (True, False):
+                for mode in ("pwm", "pwm.max"):
+                    res[(strict, bid, mode)] = seq_testdb.pwm(rows, logp, bidirect=bid, mode=mode)
+        finally:
+            gpu_ctx.set_option("pwm_strict", 0)
+    for bid in (True, False):
+        for mode in ("pwm", "pwm.max"):
+            a, b = res[(0, bid, mode)], res[(1, bid, mode)]
+            if not bid and mode == "pwm.max":
+                assert_same(a, b, "single-strand max has no transcendental")
+            else:
+                assert_close(a, b, RTOL, f"float vs strict bid={bid} {mode}")
