@@ -1647,11 +1647,24 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 		memcpy(ft.thr, thr.data(), sizeof(float) * thr.size());
 		SegTable tab;
 		mg_make_segtable(segs, tab);
-		const size_t smem = ((size_t)((nb + 3 + 3) & ~3) + (size_t)(MG_HIST_THREADS / 32) * nb * 32) * 4;
-		MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)(220 * 1024) / (int64_t)(smem + 1024)));
-		const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(tab.tile0[tab.nseg], (int64_t)ctx->sm_count * per_sm));
-		k_segs_hist<<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+		// 16-bit private columns (half the shared memory, twice the resident warps) whenever no thread can count past 65535
+		const size_t thr_bytes = (size_t)((nb + 3 + 3) & ~3) * 4, cols = (size_t)(MG_HIST_THREADS / 32) * nb * 32;
+		const int64_t tiles = tab.tile0[tab.nseg];
+		for (int pass = 0; pass < 2; ++pass) {
+			const size_t smem = thr_bytes + cols * (pass == 0 ? 2 : 4);
+			const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)(220 * 1024) / (int64_t)(smem + 1024)));
+			const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)ctx->sm_count * per_sm));
+			if (pass == 0) {
+				if (mg_div_up(tiles, blocks) * 16 > 65535)
+					continue;
+				MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				k_segs_hist<uint16_t><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+			} else {
+				MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				k_segs_hist<uint32_t><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+			}
+			break;
+		}
 		MG_LAUNCH_CHECK(ctx);
 		return 0;
 	}

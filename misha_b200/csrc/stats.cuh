@@ -452,13 +452,26 @@ __device__ __forceinline__ float mg_lds_f(uint32_t a)
 	asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
 	return v;
 }
-__device__ __forceinline__ void mg_smem_inc(uint32_t a)
+template <typename C>
+__device__ __forceinline__ void mg_smem_inc(uint32_t a);
+template <>
+__device__ __forceinline__ void mg_smem_inc<uint32_t>(uint32_t a)
 {
 	uint32_t c;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(a) : "memory");
 	asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(c + 1u) : "memory");
 }
+template <>
+__device__ __forceinline__ void mg_smem_inc<uint16_t>(uint32_t a)
+{
+	uint16_t c;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c) : "r"(a) : "memory");
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)(c + 1)) : "memory");
+}
 
+// C = counter type of the private columns: uint16_t halves the shared memory (twice the resident warps) and is used whenever
+// no thread can see more than 65535 values (the host checks tiles per block x 16).
+template <typename C>
 __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st, const FloatThr ft, unsigned long long *counts)
 {
 	extern __shared__ __align__(16) uint32_t hsmem[];
@@ -467,14 +480,15 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 	// P[0] = -inf, P[j] = thr[j-1] (j = 1..nb+1), P[nb+2] = +inf: c = #thresholds below v is right iff P[c] < v <= P[c+1]
 	float *P = reinterpret_cast<float *>(hsmem);
 	const int thr_words = (nb + 3 + 3) & ~3;
-	uint32_t *hall = hsmem + thr_words, *h = hall + warp * nb * 32;
+	C *hall = reinterpret_cast<C *>(hsmem + thr_words), *h = hall + warp * nb * 32;
 	for (int t = threadIdx.x; t <= nb + 2; t += blockDim.x)
 		P[t] = t == 0 ? __int_as_float(0xff800000) : (t == nb + 2 ? __int_as_float(0x7f800000) : ft.thr[t - 1]);
 	for (int t = lane; t < nb * 32; t += 32)
 		h[t] = 0;
 	__syncthreads();
+	constexpr uint32_t COL = 32u * sizeof(C); // bytes per bin column
 	const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(P);
-	const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(h) + 4u * lane - 128u; // column of bin c - 1 at hbase + 128 c
+	const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(h) + (uint32_t)sizeof(C) * lane - COL; // column of bin c - 1 at hbase + COL c
 	if (ft.uniform) {
 		const float b0 = ft.b0, inv = ft.inv_binsize, top = (float)(nb + 1);
 		mg_stream_segtable(st, [&](float v) {
@@ -489,13 +503,13 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 					--c;
 			}
 			if ((unsigned)(c - 1) < (unsigned)nb)
-				mg_smem_inc(hbase + 128u * c);
+				mg_smem_inc<C>(hbase + COL * c);
 		});
 	} else {
 		mg_stream_segtable(st, [&](float v) {
 			const int b = mg_float_bin(P + 1, nb, v);
 			if (b >= 0)
-				mg_smem_inc(hbase + 128u * (b + 1));
+				mg_smem_inc<C>(hbase + COL * (b + 1));
 		});
 	}
 	__syncthreads();
