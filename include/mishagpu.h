@@ -171,6 +171,17 @@ int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t f
 int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
 					int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream);
 
+/* gscreen predicates that are comparisons of value columns against constants, all joined by `&` or all by `|` (e.g.   */
+/* "near > 0.5 & cov > 0.25"): d_flag[i] = 1 where R's result is TRUE, else 0. A comparison with NaN is NA in R, and  */
+/* NA & x / NA | FALSE are never TRUE, so a NaN operand counts as FALSE; the TRUE set is exactly R's                 */
+/* (src/GenomeTrackScreener.cpp:203: only LOGICAL == 1 opens or extends an interval). Saves the device-to-host copy  */
+/* of the columns (2.5 GB for two columns at a 20 bp iterator over hg38). The host keeps evaluating every other       */
+/* expression on the returned vectors as before.                                                                     */
+enum mg_cmp_op { MG_CMP_GT = 0, MG_CMP_GE = 1, MG_CMP_LT = 2, MG_CMP_LE = 3, MG_CMP_EQ = 4, MG_CMP_NE = 5 };
+#define MG_PRED_MAX_TERMS 8
+int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, const int *ops, const double *thresholds, int combine_or,
+					  int64_t n, int8_t *d_flag, void *stream);
+
 /* ---- host-buffer convenience: what a .Call entry point does per vtrack group --------------------------------- */
 /* Host arrays in, host columns out; uploads, kernels and downloads are chunked and overlapped on internal        */
 /* streams. This is the end-to-end path bench.py times as `e2e`.                                                  */

@@ -448,14 +448,39 @@ class MishaDB:
         rows, _ = self._rows([expr], intervals, iterator, unify_scope=True)
         if rows.n == 0:
             return None
-        v = self._eval(expr, rows, {})
-        if v.dtype != np.bool_:
-            raise MishaError("Expression \"%s\" does not produce a logical result" % expr)  # src/TrackExpressionScanner.h:158-173
-        flag = self.ctx.alloc(rows.n, np.int8).from_host(v.astype(np.int8))
+        flag = self._screen_flags_on_device(expr, rows)
+        if flag is None:  # general expressions are evaluated by the host on the returned vectors, as in the reference
+            v = self._eval(expr, rows, {})
+            if v.dtype != np.bool_:
+                raise MishaError("Expression \"%s\" does not produce a logical result" % expr)  # src/TrackExpressionScanner.h:158-173
+            flag = self.ctx.alloc(rows.n, np.int8).from_host(v.astype(np.int8))
         c, s, e = gpu.screen_merge(self.ctx, rows, flag)
         if len(c) == 0:
             return None
         return Intervals(np.array(self.chrom_names, dtype=object)[c], s, e)
+
+    _TERM = re.compile(r"^\s*([A-Za-z_.][A-Za-z0-9_.]*)\s*(>=|<=|==|!=|>|<)\s*([-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?)\s*$")
+
+    def _screen_flags_on_device(self, expr, rows):
+        """Predicates of the form `var op number` joined by all `&` or all `|`: the columns stay in HBM and only the flags'
+        merge result leaves the device. None = not of that form."""
+        for sep, is_or in (("&", False), ("|", True)):
+            parts = expr.split(sep)
+            if len(parts) > 8 or (sep == "|" and len(parts) == 1):
+                continue
+            terms = [self._TERM.match(p) for p in parts]
+            if not all(terms):
+                continue
+            names = [t.group(1) for t in terms]
+            if not all(n in self.vtracks or self.gtrack_exists(n) for n in names):
+                return None
+            cols = {}
+            for n in names:
+                if n not in cols:
+                    cols[n] = self._var_column(n, rows)
+            return gpu.screen_compare(self.ctx, [cols[n] for n in names], [t.group(2) for t in terms], [float(t.group(3)) for t in terms],
+                                      is_or, rows.n)
+        return None
 
     def gsummary(self, expr, intervals=None, iterator=None):
         """R/compute-core.R:286. Returns the named 7-vector as a dict."""

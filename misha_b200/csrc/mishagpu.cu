@@ -1696,6 +1696,29 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 }
 
 // ---- gscreen -----------------------------------------------------------------------------------------------------------
+extern "C" int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, const int *ops, const double *thresholds, int combine_or,
+								 int64_t n, int8_t *d_flag, void *stream)
+{
+	MG_REQUIRE(ctx, nterms >= 1 && nterms <= MG_PRED_MAX_TERMS, "mg_screen_compare: %d terms (1..%d supported)", nterms, MG_PRED_MAX_TERMS);
+	MG_REQUIRE(ctx, n >= 0 && d_flag, "mg_screen_compare: bad arguments");
+	PredSpec p;
+	memset(&p, 0, sizeof(p));
+	p.nterms = nterms;
+	p.combine_or = combine_or != 0;
+	for (int k = 0; k < nterms; ++k) {
+		MG_REQUIRE(ctx, d_cols[k], "mg_screen_compare: column %d is NULL", k);
+		MG_REQUIRE(ctx, ops[k] >= MG_CMP_GT && ops[k] <= MG_CMP_NE, "mg_screen_compare: unknown comparison %d", ops[k]);
+		p.col[k] = d_cols[k];
+		p.op[k] = ops[k];
+		p.thr[k] = thresholds[k];
+	}
+	if (!n)
+		return 0;
+	k_pred_flags<<<(unsigned)mg_div_up(mg_div_up(n, 4), 256), 256, 0, mg_stream(stream)>>>(p, n, d_flag);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
 extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
 							   int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream)
 {

@@ -560,6 +560,60 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_dense_hist_global(const Den
 	}
 }
 
+// ---- gscreen comparison predicates on the device -----------------------------------------------------------------------------
+struct PredSpec {
+	int nterms, combine_or;
+	const double *col[MG_PRED_MAX_TERMS];
+	int op[MG_PRED_MAX_TERMS];
+	double thr[MG_PRED_MAX_TERMS];
+};
+
+__device__ __forceinline__ bool mg_cmp(int op, double v, double t)
+{
+	switch (op) { // every comparison with a NaN operand is false (R: NA, which never counts as TRUE)
+	case MG_CMP_GT: return v > t;
+	case MG_CMP_GE: return v >= t;
+	case MG_CMP_LT: return v < t;
+	case MG_CMP_LE: return v <= t;
+	case MG_CMP_EQ: return v == t;
+	default: return v < t || v > t;
+	}
+}
+
+// 4 rows per thread: two 16-byte loads per column, one 4-byte store of flags
+__global__ void __launch_bounds__(256) k_pred_flags(const PredSpec p, int64_t n, int8_t *__restrict__ flag)
+{
+	const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i0 >= n)
+		return;
+	bool r[4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j)
+		r[j] = p.combine_or == 0;
+	const bool full = i0 + 4 <= n;
+	for (int k = 0; k < p.nterms; ++k) {
+		double v[4];
+		if (full && (reinterpret_cast<uintptr_t>(p.col[k]) & 15) == 0) {
+			const double2 a = __ldcs(reinterpret_cast<const double2 *>(p.col[k] + i0)), b = __ldcs(reinterpret_cast<const double2 *>(p.col[k] + i0 + 2));
+			v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+		} else {
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				v[j] = i0 + j < n ? __ldcs(p.col[k] + i0 + j) : mg_nan();
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const bool c = mg_cmp(p.op[k], v[j], p.thr[k]);
+			r[j] = p.combine_or ? (r[j] || c) : (r[j] && c);
+		}
+	}
+	if (full && (reinterpret_cast<uintptr_t>(flag) & 3) == 0)
+		*reinterpret_cast<char4 *>(flag + i0) = make_char4(r[0], r[1], r[2], r[3]);
+	else
+		for (int j = 0; j < 4 && i0 + j < n; ++j)
+			flag[i0 + j] = r[j];
+}
+
 // ---- gscreen run merge ---------------------------------------------------------------------------------------------------
 // A TRUE row continues the current output interval iff the previous row is TRUE, on the same chromosome, and ends where
 // this one starts (src/GenomeTrackScreener.cpp:203-211); otherwise it is a run HEAD. A TRUE row whose successor does not

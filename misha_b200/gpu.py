@@ -34,9 +34,10 @@ class DevBuf:
         ctx._check(ctx.lib.mg_dev_alloc(ctx.h, c_i64(self.n * self.dtype.itemsize), ctypes.byref(ptr)))
         self.ptr = ptr.value
 
-    def to_host(self, stream=None):
-        out = np.empty(self.n, dtype=self.dtype)
-        if self.n:
+    def to_host(self, stream=None, count=None):
+        """Host copy of the first `count` elements (default: all)."""
+        out = np.empty(self.n if count is None else int(count), dtype=self.dtype)
+        if out.size:
             self.ctx._check(self.ctx.lib.mg_copy_d2h(self.ctx.h, _p(out), c_vp(self.ptr), c_i64(out.nbytes), c_vp(stream)))
         self.ctx.sync(stream)
         return out
@@ -377,12 +378,28 @@ def hist_dev(ctx, dcols, n, breaks_list, counts, include_lowest=False, stream=No
                                c_vp(stream)))
 
 
-def screen_merge(ctx, rows, dflag, first=0, count=None, stream=None):
-    """Returns (chrom, start, end) host arrays of merged TRUE runs."""
+CMP_OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
+
+
+def screen_compare(ctx, cols, ops, thresholds, combine_or, n, dflag=None, stream=None):
+    """d_flag[i] = 1 where every (any, with combine_or) comparison cols[k][i] ops[k] thresholds[k] holds; NaN -> 0."""
+    dflag = ctx.alloc(n, np.int8) if dflag is None else dflag
+    k = len(cols)
+    cp = (ctypes.c_void_p * k)(*[c.ptr for c in cols])
+    op = (ctypes.c_int * k)(*[CMP_OPS[o] if isinstance(o, str) else int(o) for o in ops])
+    th = (ctypes.c_double * k)(*[float(t) for t in thresholds])
+    ctx._check(ctx.lib.mg_screen_compare(ctx.h, ctypes.c_int(k), cp, op, th, ctypes.c_int(int(bool(combine_or))), c_i64(n), c_vp(dflag.ptr),
+                                         c_vp(stream)))
+    return dflag
+
+
+def screen_merge(ctx, rows, dflag, first=0, count=None, stream=None, scratch=None):
+    """Returns (chrom, start, end) host arrays of merged TRUE runs. `scratch` = (int32, int64, int64) device buffers of
+    >= count elements to reuse across calls (allocated here otherwise)."""
     count = rows.n - first if count is None else count
-    dc, ds, de = ctx.alloc(count, np.int32), ctx.alloc(count, np.int64), ctx.alloc(count, np.int64)
+    dc, ds, de = scratch if scratch is not None else (ctx.alloc(count, np.int32), ctx.alloc(count, np.int64), ctx.alloc(count, np.int64))
     nout = c_i64()
     ctx._check(ctx.lib.mg_screen_merge(ctx.h, rows.h, c_i64(first), c_i64(count), c_vp(dflag.ptr), c_vp(dc.ptr), c_vp(ds.ptr),
                                        c_vp(de.ptr), ctypes.byref(nout), c_vp(stream)))
     m = nout.value
-    return dc.to_host()[:m], ds.to_host()[:m], de.to_host()[:m]
+    return dc.to_host(stream, m), ds.to_host(stream, m), de.to_host(stream, m)

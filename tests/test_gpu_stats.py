@@ -192,3 +192,26 @@ def test_stream_hist_values_on_breaks():
         assert_close(got[4:], exp[4:], 1e-12, "moments")
     finally:
         ctx2.close()
+
+
+def test_screen_compare_matches_r_semantics(gpu_ctx):
+    """Device-side comparison predicates: TRUE exactly where R's `&` / `|` of comparisons is TRUE (NA never is)."""
+    from misha_b200 import gpu
+    rng = np.random.default_rng(31)
+    for n in (0, 1, 3, 4, 1001, 40000):
+        a = rng.normal(size=n); b = rng.normal(size=n); c = rng.integers(0, 3, n).astype(np.float64)
+        for col in (a, b, c):
+            col[rng.random(n) < 0.1] = np.nan
+        da, db_, dc = (gpu_ctx.alloc(n, np.float64).from_host(x) for x in (a, b, c))
+        with np.errstate(invalid="ignore"):
+            cases = [
+                ([da], [">"], [0.3], False, a > 0.3),
+                ([da, db_], [">", "<="], [0.0, 0.5], False, (a > 0.0) & (b <= 0.5)),
+                ([da, db_, dc], ["<", ">=", "=="], [-0.2, 1.0, 2.0], True, (a < -0.2) | (b >= 1.0) | (c == 2.0)),
+                ([dc, da], ["!=", ">"], [1.0, 10.0], True, ((c < 1.0) | (c > 1.0)) | (a > 10.0)),
+            ]
+        for cols, ops, thr, is_or, exp in cases:
+            if n == 0:
+                continue
+            flag = gpu.screen_compare(gpu_ctx, cols, ops, thr, is_or, n).to_host()
+            assert np.array_equal(flag.astype(bool), exp), (n, ops, is_or)

@@ -95,6 +95,22 @@ def main():
         ms2 = timed(torch, lambda: iv.coverage_dev(rows, out=out2, stream=stream), args.steps)
         report("C4 coverage @ 20bp iterator", ms2, 16 * nrec + 8 * rows.n, rows.n)
         report("C4 nearest + coverage (two launches)", ms1 + ms2, 20 * nrec + 16 * rows.n, rows.n)
+        # the whole gscreen: both columns, the comparison predicate on the device, the run merge (synchronises: returns the count)
+        flag = ctx.alloc(rows.n, np.int8)
+        scratch = (ctx.alloc(rows.n, np.int32), ctx.alloc(rows.n, np.int64), ctx.alloc(rows.n, np.int64))
+
+        def screen():
+            sp.window_dev(rows, ["nearest"], out=out, stream=stream)
+            iv.coverage_dev(rows, out=out2, stream=stream)
+            gpu.screen_compare(ctx, [out[0], out2], [">", ">"], [0.5, 0.25], False, rows.n, dflag=flag, stream=stream)
+            return gpu.screen_merge(ctx, rows, flag, stream=stream, scratch=scratch)
+        t0 = time.perf_counter()
+        res = screen()
+        for _ in range(args.steps - 1):
+            screen()
+        wall = (time.perf_counter() - t0) / args.steps * 1e3
+        report("C4 gscreen(near > 0.5 & cov > 0.25) end to end: columns + device predicate + merge + intervals to host (wall clock)", wall,
+               20 * nrec + 16 * rows.n, rows.n, {"intervals_out": int(len(res[0]))})
         sp.free(); iv.free()
 
     if "C5" in want:
