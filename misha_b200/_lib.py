@@ -4,7 +4,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libmishagpu.so")
+SO = os.environ.get("MISHAGPU_LIB") or os.path.join(HERE, "libmishagpu.so")  # MISHAGPU_LIB: development builds of the same ABI
 HEADER = os.path.join(HERE, "..", "include", "mishagpu.h")
 
 c_i64 = ctypes.c_int64

@@ -396,8 +396,13 @@ __device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint
 //       lost too many digits (low variance against the mean, or a window that is tiny against the chromosome's running
 //       sum of squares) the window is re-read and Welford's update is run in bin order, i.e. the reference's arithmetic.
 #define MG_SD_DIRECT_BINS 8
+// Resident blocks per SM, measured on B200 at the C3 shape: the kernel is bound by memory latency, so more warps win even at the
+// price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several (0.695 -> 0.616 ms for avg + max + quantile).
+#define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) ((SD) ? 4 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 8 : 6))
+// the levels of a block record (the pos_of_rank half is touched at one or two places per row: not worth prefetching)
+#define MG_PREFETCH_LINES (MG_BW_LB * MG_BW_LEVEL_BYTES / 128)
 template <bool SUM, bool MM, bool Q, bool SD>
-__global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
+__global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const DenseQuery q)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.count)
@@ -421,8 +426,8 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 		// pull all of it towards L1 / L2 long before the dependent loads of the walk arrive.
 		const uint8_t *rec = w.ch->bw + (size_t)(w.sbin >> (MG_BW_LB - 1)) * MG_BW_RECORD_BYTES;
 		const unsigned t = threadIdx.x;
-		mg_prefetch(rec + ((2 * t) % (MG_BW_RECORD_BYTES / 128)) * 128);
-		mg_prefetch(rec + ((2 * t + 1) % (MG_BW_RECORD_BYTES / 128)) * 128);
+		mg_prefetch(rec + ((2 * t) % MG_PREFETCH_LINES) * 128);
+		mg_prefetch(rec + ((2 * t + 1) % MG_PREFETCH_LINES) * 128);
 		const int64_t pb = w.sbin + (int64_t)(t & 15) * 32;
 		if (pb < w.ebin)
 			mg_prefetch(w.ch->vals + pb);
@@ -432,10 +437,15 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 		mg_win_basic<SUM || SD, MM, SUM || SD || Q>(w.ch, w.sbin, w.ebin, wb);
 		if (SUM || SD)
 			mg_row_sum(w.ch, wb, w.sbin, w.ebin, rs);
-		else {
-			rs.size = (double)wb.n;
-			rs.exists = wb.n > 0 ? 1. : 0.;
-		}
+	}
+	if (SUM) { // every column is stored as soon as it is known: short live ranges keep the kernel at 6-8 blocks per SM
+		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, rs.avg);
+		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, rs.avg);
+		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, rs.sum);
+		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, rs.size);
+		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, rs.exists);
+	}
+	if (nb > 0) {
 		if (SD && wb.n > 1) {
 			const double S1 = wb.S, S2 = __ldg(w.ch->pref2 + w.ebin) - __ldg(w.ch->pref2 + w.sbin);
 			double m2 = S2 - S1 * S1 / (double)wb.n;
@@ -469,19 +479,12 @@ __global__ void __launch_bounds__(256, 4) k_dense_rowquery(const DenseQuery q)
 			}
 		}
 	}
-	if (SUM) {
-		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, rs.avg);
-		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, rs.avg);
-		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, rs.sum);
-		if (q.out[MG_SIZE]) mg_st_stream(q.out[MG_SIZE] + i, rs.size);
-		if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, rs.exists);
-	}
+	if (SD)
+		mg_st_stream(q.out[MG_STDDEV] + i, sd);
 	if (MM) {
 		if (q.out[MG_MIN]) mg_st_stream(q.out[MG_MIN] + i, mn);
 		if (q.out[MG_MAX]) mg_st_stream(q.out[MG_MAX] + i, mx);
 	}
-	if (SD)
-		mg_st_stream(q.out[MG_STDDEV] + i, sd);
 	if (Q) {
 		// every quantile column is stored as soon as it is known (a per-thread array indexed by k would live in local memory)
 		const long long n = wb.n;
