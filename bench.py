@@ -139,18 +139,19 @@ def run_ours(args):
             ctx.set_option(opt.split("=")[0], int(opt.split("=")[1]))
 
     # ---- stage the track once (one-time cost, reported separately) ----
-    t0 = time.perf_counter()
     dense = gpu.DenseTrack(ctx, BIN)
     nbins_mine = 0
     host_bins = {}
+    stage_s = 0.0
     for i in mine:
-        b = synth.dense_bins(i, sizes[i], BIN)
+        b = synth.dense_bins(i, sizes[i], BIN)  # synthesis is not staging
         nbins_mine += len(b)
+        t0 = time.perf_counter()
         dense.stage(i, b)
+        ctx.sync()
+        stage_s += time.perf_counter() - t0
         if rank == 0 and world == 1:
             host_bins[i] = b  # the CPU baseline reads the same data
-    ctx.sync()
-    stage_s = time.perf_counter() - t0
 
     # ---- intervals in pinned host memory ----
     n_mine = int(sum(counts[i] for i in mine))
