@@ -16,9 +16,15 @@
 #include "common.cuh"
 #include "dense.cuh"
 
+#ifndef MG_BW_LB
 #define MG_BW_LB 11
+#endif
 #define MG_BW_B (1 << MG_BW_LB)
-#define MG_BW_S (MG_BW_B / 2)
+#ifndef MG_BW_STRIDE
+#define MG_BW_STRIDE (MG_BW_B / 2) // block b covers bins [b * STRIDE, b * STRIDE + B)
+#endif
+#define MG_BW_S (MG_BW_B - MG_BW_STRIDE) // longest window that is guaranteed to lie inside one block
+#define MG_BW_HALF (MG_BW_B / 2)         // zeros of every level (the ranks are a permutation of [0, B))
 #define MG_BW_UNITS (MG_BW_B / 32)
 #define MG_BW_LEVEL_BYTES (MG_BW_UNITS * 8)
 #define MG_BW_RECORD_BYTES (MG_BW_LB * MG_BW_LEVEL_BYTES + MG_BW_B * 2)
@@ -37,10 +43,10 @@ __device__ __forceinline__ uint32_t mg_bw_key(float v)
 __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *__restrict__ vals, int64_t nbins, uint8_t *__restrict__ records)
 {
 	__shared__ unsigned long long skey[MG_BW_B];
-	__shared__ uint16_t sa[MG_BW_B], sb[MG_BW_B];
 	__shared__ uint32_t sbits[MG_BW_UNITS], scnt[MG_BW_UNITS];
+	uint16_t *sa = reinterpret_cast<uint16_t *>(skey), *sb = sa + MG_BW_B; // reuse the sort buffer once the ranks are known
 	const int t = threadIdx.x;
-	const int64_t base = (int64_t)blockIdx.x * MG_BW_S;
+	const int64_t base = (int64_t)blockIdx.x * MG_BW_STRIDE;
 	uint8_t *rec = records + (size_t)blockIdx.x * MG_BW_RECORD_BYTES;
 #pragma unroll
 	for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
@@ -65,13 +71,17 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 	}
 	uint16_t *pos_of_rank = reinterpret_cast<uint16_t *>(rec + MG_BW_LB * MG_BW_LEVEL_BYTES);
 	uint16_t *cur = sa, *nxt = sb;
+	uint32_t mypos[MG_BW_PER_THREAD];
 #pragma unroll
 	for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
 		const int r = t + j * MG_BW_BUILD_THREADS;
-		const uint32_t pos = (uint32_t)skey[r];
-		pos_of_rank[r] = (uint16_t)pos;
-		cur[pos] = (uint16_t)r;
+		mypos[j] = (uint32_t)skey[r];
+		pos_of_rank[r] = (uint16_t)mypos[j];
 	}
+	__syncthreads(); // every key has been read: the buffer becomes the two rank arrays
+#pragma unroll
+	for (int j = 0; j < MG_BW_PER_THREAD; ++j)
+		cur[mypos[j]] = (uint16_t)(t + j * MG_BW_BUILD_THREADS);
 	__syncthreads();
 	uint2 *level = reinterpret_cast<uint2 *>(rec);
 	for (int lv = 0; lv < MG_BW_LB; ++lv, level += MG_BW_UNITS) {
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 			const uint32_t bits = myword[j], lane = t & 31;
 			const uint32_t ones_before = scnt[e >> 5] + __popc(bits & ((1u << lane) - 1u));
 			const uint16_t v = cur[e];
-			nxt[((bits >> lane) & 1u) ? MG_BW_S + ones_before : (uint32_t)e - ones_before] = v;
+			nxt[((bits >> lane) & 1u) ? MG_BW_HALF + ones_before : (uint32_t)e - ones_before] = v;
 			if (lane == 0)
 				level[e >> 5] = make_uint2(scnt[e >> 5], bits);
 		}
@@ -151,8 +161,8 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, co
 		const uint32_t ol = mg_bw_rank_lo(lv, l), orr = mg_bw_rank_hi(lv, r);
 		const uint32_t nz = (r - l) - (orr - ol);
 		const bool one = k >= nz;
-		l = one ? MG_BW_S + ol : l - ol;
-		r = one ? MG_BW_S + orr : r - orr;
+		l = one ? MG_BW_HALF + ol : l - ol;
+		r = one ? MG_BW_HALF + orr : r - orr;
 		k = one ? k - nz : k;
 		rank = (rank << 1) | (one ? 1u : 0u);
 	}

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_
 		// Rows that are neighbours in position share their block record (76 lines of 128 bytes) and most of their window:
 		// every thread asks for two lines of its record and one line of its window, so between them the rows of a block
 		// pull all of it towards L1 / L2 long before the dependent loads of the walk arrive.
-		const uint8_t *rec = w.ch->bw + (size_t)(w.sbin >> (MG_BW_LB - 1)) * MG_BW_RECORD_BYTES;
+		const uint8_t *rec = w.ch->bw + (size_t)((uint32_t)w.sbin / MG_BW_STRIDE) * MG_BW_RECORD_BYTES;
 		const unsigned t = threadIdx.x;
 		mg_prefetch(rec + ((2 * t) % MG_PREFETCH_LINES) * 128);
 		mg_prefetch(rec + ((2 * t + 1) % MG_PREFETCH_LINES) * 128);
@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_
 		// every quantile column is stored as soon as it is known (a per-thread array indexed by k would live in local memory)
 		const long long n = wb.n;
 		const bool use_bw = q.use_bw && nb <= MG_BW_S;
-		const int64_t blk = w.sbin >> (MG_BW_LB - 1);
-		const uint32_t l = (uint32_t)w.sbin & (MG_BW_S - 1);
+		const uint32_t blk = (uint32_t)w.sbin / MG_BW_STRIDE;
+		const uint32_t l = (uint32_t)w.sbin - blk * MG_BW_STRIDE;
 		long long before = wb.before;
 		if (!use_bw && n > 0 && before < 0)
 			before = mg_win_before(w.ch, w.sbin);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_
 				const bool want2 = index != fl; // ceil(index) != floor(index)
 				float x1, x2;
 				if (use_bw)
-					mg_bw_select(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, w.ch->vals + blk * MG_BW_S, l, l + (uint32_t)nb, (uint32_t)i1, want2,
+					mg_bw_select(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, w.ch->vals + (size_t)blk * MG_BW_STRIDE, l, l + (uint32_t)nb, (uint32_t)i1, want2,
 								 x1, x2);
 				else
 					mg_wm_select(w.ch, (uint32_t)before, (uint32_t)(before + n), (uint32_t)i1, want2, x1, x2);

@@ -250,7 +250,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	}
 	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
 	{
-		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_S);
+		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_STRIDE);
 		uint8_t *bw = nullptr;
 		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nblk * MG_BW_RECORD_BYTES, &bw))
 			return 1;
