@@ -105,8 +105,11 @@ __device__ __forceinline__ float mg_log_sum_log(float l1, float l2)
 }
 
 // BID: both strands combined per anchor; MODE: MG_PWM_TOTAL / MAX / COUNT; STRICT: see mg_log1pexp_f
+#ifndef MG_PWM_MINBLOCKS
+#define MG_PWM_MINBLOCKS 1
+#endif
 template <bool BID, int MODE, bool STRICT>
-__global__ void __launch_bounds__(MG_PWM_WARPS * 32) k_pwm(const PwmQuery q)
+__global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(const PwmQuery q)
 {
 	__shared__ float2 stab[MG_PWM_MAXL * 5];
 	__shared__ __align__(16) uint8_t stile[MG_PWM_WARPS][MG_PWM_TILE + 16];
