@@ -35,6 +35,30 @@ def deps():
     return out
 
 
+HOST = os.path.join(HERE, "host")
+HOST_SO = os.path.join(HERE, "libmishahost.so")
+HOST_DEMO = os.path.join(HERE, "mg_host_demo")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_host(force=False):
+    """The C++ host layer above the C ABI (misha_b200/host): libmishahost.so (GpuTrackExprScanner, the mirror of the
+    reference's TrackExprScanner for this path) and the mg_host_demo driver the tests run."""
+    srcs = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [SO]
+    if not force and all(os.path.exists(p) and all(os.path.getmtime(s) <= os.path.getmtime(p) for s in srcs) for p in (HOST_SO, HOST_DEMO)):
+        return HOST_SO
+    import shutil
+    if shutil.which(CXX) is None:
+        if os.path.exists(HOST_SO) and os.path.exists(HOST_DEMO):
+            return HOST_SO  # GPU box without a compiler: the prebuilt files travelled with the snapshot
+        raise RuntimeError("%s not found and no prebuilt host layer" % CXX)
+    common = [CXX, "-std=c++17", "-O2", "-Wall"]
+    link = ["-L" + HERE, "-lmishagpu", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(common + ["-fPIC", "-shared", "-o", HOST_SO, os.path.join(HOST, "GpuTrackExprScanner.cpp")] + link)
+    subprocess.check_call(common + ["-o", HOST_DEMO, os.path.join(HOST, "mg_host_demo.cpp"), "-L" + HERE, "-lmishahost"] + link[1:])
+    return HOST_SO
+
+
 def up_to_date():
     if not os.path.exists(SO):
         return False
@@ -58,4 +82,5 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    build_host(force="--force" in sys.argv)
     print(SO)

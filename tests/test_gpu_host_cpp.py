@@ -1,0 +1,152 @@
+"""The C++ host layer (misha_b200/host: GpuTrackExprScanner, the mirror of the reference's TrackExprScanner for this path)
+driven through mg_host_demo, against the oracle: row coordinates / intervalID bit-exact, values at the usual bars. The demo
+itself checks that the reference-shaped per-row loop (next() / last_real()) and the whole-column access agree bitwise."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, assert_same
+from misha_b200 import build
+from oracle import port
+
+RTOL = 1e-6
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _write_intervals(path, chrom, start, end):
+    raw = np.empty(1 + 3 * len(chrom), np.int64)
+    raw[0] = len(chrom)
+    raw[1::3], raw[2::3], raw[3::3] = chrom, start, end
+    raw.tofile(path)
+
+
+def _read_out(path, nexprs):
+    b = open(path, "rb").read()
+    n, ne = struct.unpack_from("<qq", b, 0)
+    assert ne == nexprs
+    off = 16
+    chrom = np.frombuffer(b, np.int32, n, off); off += 4 * n
+    start = np.frombuffer(b, np.int64, n, off); off += 8 * n
+    end = np.frombuffer(b, np.int64, n, off); off += 8 * n
+    iid = np.frombuffer(b, np.int32, n, off); off += 4 * n
+    cols = []
+    for _ in range(ne):
+        cols.append(np.frombuffer(b, np.float64, n, off)); off += 8 * n
+    return chrom, start, end, iid, cols
+
+
+def test_host_layer_builds_and_exports():
+    """CPU: the host layer compiles against include/mishagpu.h and links libmishagpu.so; the scanner's interface is there."""
+    build.build()
+    so = build.build_host()
+    syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
+    for name in ("mishagpu::GpuTrackExprScanner::begin", "mishagpu::GpuTrackExprScanner::next()", "mishagpu::gextract", "mishagpu::gsummary_dense"):
+        assert name in syms, name
+    assert os.access(build.HOST_DEMO, os.X_OK)
+
+
+@pytest.mark.gpu
+def test_cpp_scanner_gextract_vs_oracle(tmp_path):
+    build.build_host()
+    rng = np.random.default_rng(77)
+    sizes = [400000, 250000]
+    bs = 20
+    bins = []
+    for c, size in enumerate(sizes):
+        b = rng.lognormal(size=(size + bs - 1) // bs).astype(np.float32)
+        b[rng.random(len(b)) < 0.05] = np.nan
+        b[rng.integers(0, len(b), 5)] = np.inf
+        b.tofile(tmp_path / f"dense{c}.f32")
+        bins.append(b)
+    recs = []
+    for c, size in enumerate(sizes):
+        st = np.sort(rng.choice(size // 50 - 2, 800, replace=False)) * 50
+        en = st + rng.integers(1, 50, 800)
+        val = rng.random(800).astype(np.float32)
+        with open(tmp_path / f"sparse{c}.bin", "wb") as f:
+            f.write(struct.pack("<q", 800)); st.astype(np.int64).tofile(f); en.astype(np.int64).tofile(f); val.tofile(f)
+        with open(tmp_path / f"iv{c}.bin", "wb") as f:
+            f.write(struct.pack("<q", 800)); st.astype(np.int64).tofile(f); en.astype(np.int64).tofile(f)
+        recs.append((st, en, val))
+    # scope in arbitrary order: intervalID must refer to the caller's order
+    n = 3000
+    chrom = rng.integers(0, 2, n).astype(np.int64)
+    start = (rng.random(n) * (np.array(sizes)[chrom] - 400)).astype(np.int64)
+    end = start + rng.integers(1, 400, n)
+    _write_intervals(tmp_path / "scope.bin", chrom, start, end)
+    spec = tmp_path / "spec.txt"
+    spec.write_text("\n".join([
+        "chroms 2 %d %d" % tuple(sizes),
+        "dense d %d %s %s" % (bs, tmp_path / "dense0.f32", tmp_path / "dense1.f32"),
+        "sparse s %s %s" % (tmp_path / "sparse0.bin", tmp_path / "sparse1.bin"),
+        "ivset iv %s %s" % (tmp_path / "iv0.bin", tmp_path / "iv1.bin"),
+        "vtrack v_avg dense d 0 0 -5000 5000",
+        "vtrack v_max dense d 3 0 -5000 5000",
+        "vtrack v_q dense d 5 0.9 -5000 5000",
+        "vtrack v_sum dense d 1 0 0 0",
+        "vtrack v_near sparse s 6 0 0 0",
+        "vtrack v_cov coverage iv 0 0 -100 100",
+        "scope %s" % (tmp_path / "scope.bin"),
+        "iterator intervals %s" % (tmp_path / "scope.bin"),
+        "buffer 1024",
+        "exprs v_avg v_max v_q v_sum v_near v_cov",
+        "out %s" % (tmp_path / "out.bin"),
+    ]) + "\n")
+    r = subprocess.run([build.HOST_DEMO, str(spec)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    oc, os_, oe, iid, cols = _read_out(tmp_path / "out.bin", 6)
+    # the intervals iterator over the scope itself: sorted, overlaps merged (touching kept apart); every row maps to a scope row
+    assert np.all(np.diff(oc) >= 0)
+    assert np.all((start[iid - 1] < oe) & (end[iid - 1] > os_) & (chrom[iid - 1] == oc)), "intervalID points at an overlapping scope row"
+    for c in range(2):
+        m = oc == c
+        exp = port.dense_window(bins[c], bs, sizes[c], os_[m], oe[m], -5000, 5000, 0.9, ("avg", "max", "quantile"))
+        assert_close(cols[0][m], exp["avg"], RTOL, "avg")
+        assert_same(cols[1][m], exp["max"], "max")
+        assert_same(cols[2][m], exp["quantile"], "quantile")
+        exp0 = port.dense_window(bins[c], bs, sizes[c], os_[m], oe[m], 0, 0, 0.5, ("sum",))
+        assert_close(cols[3][m], exp0["sum"], RTOL, "sum")
+        near = port.sparse_window(*recs[c], sizes[c], os_[m], oe[m], funcs=("nearest",))["nearest"]
+        assert_same(cols[4][m], near, "nearest")
+        _, us, ue = port.unify(np.zeros(800), recs[c][0], recs[c][1], True)
+        assert_same(cols[5][m], port.coverage(us, ue, sizes[c], os_[m], oe[m], -100, 100), "coverage")
+
+
+@pytest.mark.gpu
+def test_cpp_scanner_fixedbin_and_summary(tmp_path):
+    build.build_host()
+    rng = np.random.default_rng(78)
+    sizes = [300000]
+    bs = 50
+    b = rng.normal(size=sizes[0] // bs).astype(np.float32)
+    b[100:140] = np.nan
+    b.tofile(tmp_path / "dense0.f32")
+    _write_intervals(tmp_path / "scope.bin", [0, 0], [120000, 1010], [200000, 90000])  # unsorted scope
+    spec = tmp_path / "spec.txt"
+    spec.write_text("\n".join([
+        "chroms 1 %d" % sizes[0],
+        "dense d %d %s" % (bs, tmp_path / "dense0.f32"),
+        "vtrack x dense d 0 0 0 0",
+        "scope %s" % (tmp_path / "scope.bin"),
+        "iterator 1000",
+        "buffer 1024",
+        "exprs x",
+        "out %s" % (tmp_path / "out.bin"),
+        "summary d %d %s" % (bs, tmp_path / "sum.bin"),
+    ]) + "\n")
+    r = subprocess.run([build.HOST_DEMO, str(spec)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    oc, os_, oe, iid, cols = _read_out(tmp_path / "out.bin", 1)
+    ec, es, ee, ek = port.fixedbin_rows(1000, [0, 0], [1010, 120000], [90000, 200000])
+    assert np.array_equal(os_, es) and np.array_equal(oe, ee)
+    assert np.array_equal(iid, np.where(ek == 0, 2, 1)), "intervalID = row of the caller's (unsorted) scope"
+    exp = port.dense_window(b, bs, sizes[0], es, ee, 0, 0, 0.5, ("avg",))
+    assert_close(cols[0], exp["avg"], RTOL, "avg @ iterator 1000")
+    got = np.fromfile(tmp_path / "sum.bin", np.float64)
+    c, s, e, _ = port.fixedbin_rows(bs, [0, 0], [1010, 120000], [90000, 200000])
+    vals = port.dense_window(b, bs, sizes[0], s, e, 0, 0, 0.5, ("avg",))["avg"]
+    exp_s = port.summary(vals)
+    assert np.array_equal(got[:4], exp_s[:4]) and np.allclose(got[4:], exp_s[4:], rtol=1e-9)
