@@ -81,6 +81,17 @@ struct PwmQuery {
 // are correctly rounded in all but rare cases) -- two double-precision transcendentals per anchor, which is what bounds the
 // kernel. Default: CUDA's float expf (<= 2 ulp) and logf (<= 1 ulp): the strand sum moves by <= ~3e-7 absolute, i.e.
 // ~1e-8 relative to a 20-mer's log-likelihood, far inside the 1e-6 bar (mg_set_option("pwm_strict", 1) restores STRICT).
+__device__ __forceinline__ uint32_t mg_lds_u32(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void mg_lds_f2(uint32_t a, float &x, float &y)
+{
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
+}
+
 template <bool STRICT>
 __device__ __forceinline__ float mg_log1pexp_f(float d)
 {
@@ -91,17 +102,15 @@ __device__ __forceinline__ float mg_log1pexp_f(float d)
 	}
 	return logf(__fadd_rn(1.0f, expf(d)));
 }
+// log(exp(l1) + exp(l2)), src/util.h:16-28, without its branches: with hi = max, lo = min the reference returns
+// hi + log1pexp(lo - hi), skipping the term when lo is -inf -- where it is exactly 0 anyway (exp(-inf) = 0, log(1) = 0).
+// Only hi = -inf (both strands impossible: lo - hi = NaN) needs a guard. Same values, no divergence between lanes.
 template <bool STRICT>
 __device__ __forceinline__ float mg_log_sum_log(float l1, float l2)
 {
-	if (l1 > l2) {
-		if (!isinf(l2))
-			l1 = __fadd_rn(l1, mg_log1pexp_f<STRICT>(__fsub_rn(l2, l1)));
-		return l1;
-	}
-	if (isinf(l1))
-		return l2;
-	return __fadd_rn(l2, mg_log1pexp_f<STRICT>(__fsub_rn(l1, l2)));
+	const float hi = fmaxf(l1, l2), lo = fminf(l1, l2);
+	const float r = __fadd_rn(hi, mg_log1pexp_f<STRICT>(__fsub_rn(lo, hi)));
+	return hi == __int_as_float(0xff800000) ? hi : r;
 }
 
 // BID: both strands combined per anchor; MODE: MG_PWM_TOTAL / MAX / COUNT; STRICT: see mg_log1pexp_f
@@ -113,12 +122,15 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 {
 	__shared__ float2 stab[MG_PWM_MAXL * 5];
 	__shared__ __align__(16) uint8_t stile[MG_PWM_WARPS][MG_PWM_TILE + 16];
+	__shared__ uint32_t spk[MG_PWM_WARPS][3 * ((MG_PWM_TILE + 16 + 31) / 32 + 2)]; // {inval, codes lo, codes hi} per 32 bases
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int L = q.L;
-	for (int t = threadIdx.x; t < L * 5; t += blockDim.x)
-		stab[t] = q.tab[t];
+	const int L = q.L, Lpad = (L + 3) & ~3; // motif rows padded to a multiple of 4 with zeros: adding 0.f changes nothing
+	for (int t = threadIdx.x; t < Lpad * 5; t += blockDim.x)
+		stab[t] = t < L * 5 ? q.tab[t] : make_float2(0.f, 0.f);
 	__syncthreads();
+	const uint32_t stab_s = (uint32_t)__cvta_generic_to_shared(stab);
 	uint8_t *tile = stile[warp];
+	uint32_t *wpk = spk[warp];
 	const float NEG_INF = __int_as_float(0xff800000);
 	const bool rev = q.strand == -1; // the reference scores the reverse-complemented target: terms are added j = L-1..0
 	const int64_t nwarps_total = (int64_t)gridDim.x * MG_PWM_WARPS;
@@ -157,40 +169,46 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 			float vmax = NEG_INF;
 			long long hits = 0;
 			for (int64_t a0 = 0; a0 < na; a0 += MG_PWM_CHUNK) {
-				// decode bases [ws + a0, ws + a0 + CHUNK + L - 1) into the tile
-				const int need = MG_PWM_CHUNK + L - 1;
+				// decode bases [ws + a0, ws + a0 + CHUNK + L + 2) into the tile: the packed words the chunk spans are fetched once
+				// (one load per lane), every base is then a shift and a mask in 32-bit arithmetic
+				const int need = MG_PWM_CHUNK + Lpad - 1 + 3;
+				const int64_t p0 = ws + a0, pw0 = p0 & ~31ll; // chunk start, and the 32-base boundary below it
+				const int off = (int)(p0 - pw0), span = off + need; // bases from pw0 on
 				__syncwarp();
-				for (int t = lane; t < need + 3; t += 32) {
-					const int64_t p = ws + a0 + t;
-					uint8_t code = 4;
-					if (p < xe) {
-						const uint32_t w = __ldg(ch.codes + (p >> 4));
-						const uint32_t bad = __ldg(ch.inval + (p >> 5));
-						code = ((bad >> (p & 31)) & 1u) ? 4 : (uint8_t)((w >> (2 * (p & 15))) & 3u);
-					}
-					tile[t] = code;
+				for (int t = lane; t < ((span + 31) >> 5); t += 32) { // inval word t, codes words 2t and 2t + 1
+					const int64_t wi = (pw0 >> 5) + t;
+					const bool in = (wi << 5) < ch.len;
+					wpk[3 * t] = in ? __ldg(ch.inval + wi) : 0xffffffffu;
+					wpk[3 * t + 1] = in ? __ldg(ch.codes + 2 * wi) : 0u;
+					wpk[3 * t + 2] = in && (wi << 5) + 16 < ch.len ? __ldg(ch.codes + 2 * wi + 1) : 0u;
+				}
+				__syncwarp();
+				const int lim = (int)min((int64_t)0x7fffffff, xe - pw0); // bases at or past xe read as non-ACGT
+				for (int t = lane; t < need; t += 32) {
+					const int b = off + t, w = b >> 5, k = b & 31;
+					const uint32_t bad = (wpk[3 * w] >> k) & 1u;
+					const uint32_t code = (wpk[3 * w + 1 + (k >> 4)] >> (2 * (k & 15))) & 3u;
+					tile[t] = (uint8_t)(8u * ((bad || b >= lim) ? 4u : code)); // byte offset of the table column
 				}
 				__syncwarp();
 				float f[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
 				if (!rev) {
 					// the lane's 4 anchors read bases 4 lane + j + u: one aligned word of the tile per 4 motif positions, byte
-					// offsets known at compile time
-					const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + lane;
-					uint32_t w0 = tw[0];
-					for (int j0 = 0; j0 < L; j0 += 4) {
-						const uint32_t w1 = tw[(j0 >> 2) + 1];
+					// offsets known at compile time; a lookup is PRMT (column offset) + add + LDS.64 + 2 FADD
+					const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile) + 4u * lane;
+					uint32_t w0 = mg_lds_u32(tile_s), rowb = stab_s;
+					for (int j0 = 0; j0 < Lpad; j0 += 4, rowb += 4 * 40) {
+						const uint32_t w1 = mg_lds_u32(tile_s + j0 + 4);
 #pragma unroll
 						for (int jj = 0; jj < 4; ++jj) {
-							if (j0 + jj < L) {
-								const float2 *row = stab + (j0 + jj) * 5;
 #pragma unroll
-								for (int u = 0; u < 4; ++u) {
-									const int b = jj + u; // byte b of the 8 bytes {w0, w1}
-									const uint32_t code = ((b < 4 ? w0 >> (8 * b) : w1 >> (8 * (b - 4))) & 0xffu);
-									const float2 tt = row[code];
-									f[u] = __fadd_rn(f[u], tt.x);
-									r[u] = __fadd_rn(r[u], tt.y);
-								}
+							for (int u = 0; u < 4; ++u) {
+								// byte jj + u of the 8 bytes {w0, w1}, zero-extended: one PRMT (selector 4 = a byte of the zero operand)
+								const uint32_t off = __byte_perm(jj + u < 4 ? w0 : w1, 0u, 0x4440 + ((jj + u) & 3));
+								float x, y;
+								mg_lds_f2(rowb + off + jj * 40, x, y);
+								f[u] = __fadd_rn(f[u], x);
+								r[u] = __fadd_rn(r[u], y);
 							}
 						}
 						w0 = w1;
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 						const float2 *row = stab + j * 5;
 #pragma unroll
 						for (int u = 0; u < 4; ++u) {
-							const float2 tt = row[tb[j + u]];
+							const float2 tt = row[tb[j + u] >> 3];
 							f[u] = __fadd_rn(f[u], tt.x);
 							r[u] = __fadd_rn(r[u], tt.y);
 						}
@@ -219,25 +237,18 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 					else
 						v = rev ? r[u] : f[u];
 					if (MODE == MG_PWM_TOTAL) {
+						// src/utils/RunningLogSumExp.h:32-45 as selects: the new maximum rescales the running sum, anything else adds
+						// its own term; an impossible anchor (-inf) adds nothing
+						const double dv = (double)v;
+						const bool up = dv > m_run;
+						double ex;
+						if (STRICT)
+							ex = exp(-fabs(dv - m_run));
+						else // each term good to ~2.4e-7 relative, the log of their sum to the same absolute error
+							ex = (double)expf(-(float)fabs(dv - m_run));
 						if (v != NEG_INF) {
-							const double dv = (double)v;
-							if (STRICT) {
-								if (dv > m_run) {
-									s_run = s_run * exp(m_run - dv) + 1.;
-									m_run = dv;
-								} else
-									s_run += exp(dv - m_run);
-							} else {
-								// same recurrence (src/utils/RunningLogSumExp.h:32-45) with the exponential in float: each term is
-								// good to ~2.4e-7 relative, the log of their sum to the same absolute error
-								const float d = (float)fabs(dv - m_run);
-								const double ex = (double)expf(-d);
-								if (dv > m_run) {
-									s_run = s_run * ex + 1.;
-									m_run = dv;
-								} else
-									s_run += ex;
-							}
+							s_run = up ? s_run * ex + 1. : s_run + ex;
+							m_run = up ? dv : m_run;
 						}
 					} else if (MODE == MG_PWM_MAX)
 						vmax = fmaxf(vmax, v);
