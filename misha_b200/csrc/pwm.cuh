@@ -115,7 +115,7 @@ __device__ __forceinline__ float mg_log_sum_log(float l1, float l2)
 
 // BID: both strands combined per anchor; MODE: MG_PWM_TOTAL / MAX / COUNT; STRICT: see mg_log1pexp_f
 #ifndef MG_PWM_MINBLOCKS
-#define MG_PWM_MINBLOCKS 1
+#define MG_PWM_MINBLOCKS 3
 #endif
 template <bool BID, int MODE, bool STRICT>
 __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(const PwmQuery q)
