@@ -73,10 +73,17 @@ int mg_init(int device, int nchroms, const int64_t *chrom_sizes, mg_ctx **out);
 void mg_shutdown(mg_ctx *ctx);
 const char *mg_last_error(const mg_ctx *ctx); /* ctx may be NULL: error of the last failed mg_init in this thread */
 int mg_sync(mg_ctx *ctx, void *stream);
-/* Tuning / ablation switches. "force_sweep" = 1 routes min / max / quantile through the warp-per-row sweep kernel
- * instead of the per-chromosome index structures (same results; used by tests and profiling). "pipe_chunk_rows" = rows per
- * slot of the host-buffer pipeline (default 2^19). "zero_copy" = 1 lets mg_h_* kernels read / write pinned host buffers
- * directly instead of staging them through the DMA pipeline (default 0: measured slower on B200). */
+/* Tuning / ablation switches (same results whatever their value, except pwm_strict's last float bits):
+ *   "force_sweep" = 1    dense min / max / quantile through the warp-per-row sweep kernel, sparse / coverage through the
+ *                        per-row search kernels, instead of the index structures / merge kernels (tests, profiling)
+ *   "block_wm" = 0       quantiles from the chromosome-wide wavelet matrix only (default 1: block-local matrices for windows
+ *                        of <= 1024 bins)
+ *   "prefetch" = 0       no L1 prefetch of block records / window lines in the row-query kernels
+ *   "pwm_strict" = 1     PWM log-sum-exp with double-precision exp / log rounded to float (default: float expf / logf)
+ *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 2^19)
+ *   "zero_copy" = 1      mg_h_* kernels read / write pinned host buffers directly instead of the DMA pipeline (default 0:
+ *                        measured slower on B200)
+ *   "l2_fetch_granularity" = 32 / 64 / 128   cudaLimitMaxL2FetchGranularity */
 int mg_set_option(mg_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this ctx has launched since mg_init (bench.py's gpu_launches claim) */
 int64_t mg_launch_count(const mg_ctx *ctx);
@@ -94,7 +101,8 @@ int mg_dev_memset(mg_ctx *ctx, void *d_ptr, int value, int64_t bytes, void *stre
 
 /* ---- staging ("stages chromosome track blocks into HBM once") ------------------------------------------ */
 /* Dense: h_bins = payload of the per-chromosome file after the 4-byte bin-size header (may hold +-inf, which */
-/* become NaN on load as in read_bins_bulk). Builds the per-chromosome prefix sums used by avg/sum.           */
+/* become NaN on load as in read_bins_bulk). Builds the chromosome's index structures once: group-of-8 prefix  */
+/* sums (avg/sum/size), sparse tables and pyramids (min/max), wavelet matrices (quantile) -- DESIGN.md 2.     */
 int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out);
 int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float *h_bins, int64_t nbins);
 void mg_dense_free(mg_ctx *ctx, mg_dense *t);
