@@ -174,6 +174,14 @@ int mg_hist(mg_ctx *ctx, int ndim, const double *const *d_cols, int64_t n, const
 int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
 				  int func, double param, const double *h_breaks, int nbreaks, int include_lowest, uint64_t *d_counts, void *stream);
 
+/* gquantiles (C_gquantiles, src/GenomeTrackQuantiles.cpp:124-262) over a device column of row values: every value is   */
+/* narrowed to float, NaN rows are dropped, and quantile q of the N kept values is s[floor(i)] (1 - w) + s[ceil(i)] w in   */
+/* double, i = (N - 1) clamp(q, 0, 1) -- the reference's exact regime. Selection is exact for any N: where the reference   */
+/* switches to R-RNG reservoir sampling beyond gmax.data.size values, this call still returns the exact quantiles.        */
+/* h_out[nq] (host), *h_nkept = N (may be NULL). Synchronises the stream. At most 64 quantiles per call.                  */
+int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
+				 void *stream);
+
 /* gscreen: merge consecutive TRUE rows (d_flag[i] == 1) of rows [first, first+count) into intervals. Outputs are   */
 /* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */
 int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,

@@ -482,6 +482,25 @@ class MishaDB:
                                       is_or, rows.n)
         return None
 
+    def gquantiles(self, expr, percentiles=0.5, intervals=None, iterator=None):
+        """R/compute-distribution.R gquantiles -> C_gquantiles (src/GenomeTrackQuantiles.cpp:124-262): quantiles of the expression's
+        values over all iterator rows. Returns a dict percentile -> value (the named vector R returns)."""
+        pcts = np.atleast_1d(np.asarray(percentiles, dtype=np.float64))
+        for p in pcts:
+            if not (0 <= p <= 1):
+                raise MishaError("Percentile (%g) is not in [0, 1] range\n" % p)
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows([expr], intervals, iterator, unify_scope=True)
+        expr = expr.strip()
+        if rows.n == 0:
+            return {float(p): float("nan") for p in pcts}
+        if expr in self.vtracks or self.gtrack_exists(expr):
+            col = self._var_column(expr, rows)  # stays in HBM
+        else:
+            col = self.ctx.alloc(rows.n, np.float64).from_host(np.asarray(self._eval(expr, rows, {}), dtype=np.float64))
+        q, _ = gpu.quantiles(self.ctx, col, rows.n, pcts)
+        return {float(p): float(v) for p, v in zip(pcts, q)}
+
     def gsummary(self, expr, intervals=None, iterator=None):
         """R/compute-core.R:286. Returns the named 7-vector as a dict."""
         intervals = self.gintervals_all() if intervals is None else intervals

@@ -1695,6 +1695,101 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 	return 0;
 }
 
+// ---- gquantiles --------------------------------------------------------------------------------------------------------
+extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
+							void *stream)
+{
+	MG_REQUIRE(ctx, n >= 0 && nq >= 1 && nq <= MG_QS_MAXSLOTS / 2 && h_percentiles && h_out, "mg_quantiles: bad arguments (1..%d quantiles)",
+			   MG_QS_MAXSLOTS / 2);
+	for (int k = 0; k < nq; ++k) // C_gquantiles rejects these before scanning (src/GenomeTrackQuantiles.cpp:140-143)
+		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
+	cudaStream_t st = mg_stream(stream);
+	const double nan = std::numeric_limits<double>::quiet_NaN();
+	unsigned long long *d_hist = nullptr;
+	const size_t hist_words = (size_t)MG_QS_MAXSLOTS * 2048 + 1;
+	MG_CUDA(ctx, cudaMallocAsync(&d_hist, hist_words * 8, st));
+	std::vector<unsigned long long> h((size_t)MG_QS_MAXSLOTS * 2048 + 1);
+	const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8));
+	// pass 0: top 11 bits of every key + the NaN count
+	QsPass p;
+	memset(&p, 0, sizeof(p));
+	MG_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (2048 + 1) * 8, st));
+	if (n) {
+		k_qs_count<<<grid, 256, 0, st>>>(d_vals, n, p, d_hist + 1, d_hist);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	MG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_hist, (2048 + 1) * 8, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	const int64_t N = n - (int64_t)h[0];
+	if (h_nkept)
+		*h_nkept = N;
+	if (N <= 0) {
+		for (int k = 0; k < nq; ++k)
+			h_out[k] = nan;
+		MG_CUDA(ctx, cudaFreeAsync(d_hist, st));
+		return 0;
+	}
+	// target ranks: floor / ceil of (N - 1) q for every quantile, unique, ascending (src/GenomeTrackQuantiles.cpp:183-195)
+	std::vector<uint64_t> targets;
+	for (int k = 0; k < nq; ++k) {
+		const double idx = (double)(N - 1) * h_percentiles[k];
+		targets.push_back((uint64_t)floor(idx));
+		targets.push_back((uint64_t)ceil(idx));
+	}
+	std::sort(targets.begin(), targets.end());
+	targets.erase(std::unique(targets.begin(), targets.end()), targets.end());
+	const size_t T = targets.size();
+	std::vector<uint64_t> rank(targets);     // rank of the target inside its current prefix bucket
+	std::vector<uint32_t> prefix(T, 0);      // bits of its key found so far
+	auto descend = [&](const unsigned long long *hist, size_t t, int nbins) { // digit whose cumulative count passes rank[t]
+		unsigned long long acc = 0;
+		for (int d = 0; d < nbins; ++d) {
+			if (acc + hist[d] > rank[t]) {
+				rank[t] -= acc;
+				return (uint32_t)d;
+			}
+			acc += hist[d];
+		}
+		return (uint32_t)(nbins - 1); // unreachable: rank < bucket population
+	};
+	for (size_t t = 0; t < T; ++t)
+		prefix[t] = descend(h.data() + 1, t, 2048);
+	for (int pass = 1; pass <= 2; ++pass) {
+		const int nbins = pass == 1 ? 2048 : 1024;
+		std::vector<uint32_t> slots(prefix);
+		std::sort(slots.begin(), slots.end());
+		slots.erase(std::unique(slots.begin(), slots.end()), slots.end());
+		memset(&p, 0, sizeof(p));
+		p.pass = pass;
+		p.nslots = (int)slots.size();
+		for (size_t j = 0; j < slots.size(); ++j)
+			p.prefix[j] = slots[j];
+		MG_CUDA(ctx, cudaMemsetAsync(d_hist, 0, slots.size() * (size_t)nbins * 8, st));
+		k_qs_count<<<grid, 256, 0, st>>>(d_vals, n, p, d_hist, nullptr);
+		MG_LAUNCH_CHECK(ctx);
+		MG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_hist, slots.size() * (size_t)nbins * 8, cudaMemcpyDeviceToHost, st));
+		MG_CUDA(ctx, cudaStreamSynchronize(st));
+		for (size_t t = 0; t < T; ++t) {
+			const size_t slot = std::lower_bound(slots.begin(), slots.end(), prefix[t]) - slots.begin();
+			const uint32_t d = descend(h.data() + slot * (size_t)nbins, t, nbins);
+			prefix[t] = (prefix[t] << (pass == 1 ? 11 : 10)) | d;
+		}
+	}
+	MG_CUDA(ctx, cudaFreeAsync(d_hist, st));
+	std::vector<double> value(T);
+	for (size_t t = 0; t < T; ++t)
+		value[t] = (double)mg_host_fkey_inv(prefix[t]);
+	for (int k = 0; k < nq; ++k) { // src/GenomeTrackQuantiles.cpp:222-232
+		const double idx = (double)(N - 1) * h_percentiles[k];
+		const uint64_t i1 = (uint64_t)floor(idx), i2 = (uint64_t)ceil(idx);
+		const double w = idx - (double)i1;
+		const size_t p1 = std::lower_bound(targets.begin(), targets.end(), i1) - targets.begin();
+		const size_t p2 = std::lower_bound(targets.begin(), targets.end(), i2) - targets.begin();
+		h_out[k] = value[p1] * (1.0 - w) + value[p2] * w;
+	}
+	return 0;
+}
+
 // ---- gscreen -----------------------------------------------------------------------------------------------------------
 extern "C" int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, const int *ops, const double *thresholds, int combine_or,
 								 int64_t n, int8_t *d_flag, void *stream)

@@ -560,6 +560,76 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_dense_hist_global(const Den
 	}
 }
 
+// ---- gquantiles: exact order statistics of a whole value column ------------------------------------------------------------
+// Three counting passes over the column (11 + 11 + 10 bits of the order-preserving float key) find every requested rank at
+// once: pass 0 histograms the top digit of all keys; passes 1 and 2 only count keys whose prefix is one a target rank fell
+// into (a 2048-entry table in shared memory maps the top digit to its prefix slots). No sort, no temporary copy of the data.
+#define MG_QS_MAXSLOTS 128
+struct QsPass {
+	int pass;   // 0, 1, 2
+	int nslots; // distinct prefixes still followed (passes 1, 2)
+	uint32_t prefix[MG_QS_MAXSLOTS]; // pass 1: top 11 bits; pass 2: top 22 bits; ascending
+};
+
+__device__ __forceinline__ uint32_t mg_qs_key(double v)
+{
+	const float f = (float)v; // the reference narrows every row value to float first (src/GenomeTrackQuantiles.cpp:168)
+	if (f != f)
+		return 0xffffffffu;
+	const uint32_t b = __float_as_uint(f);
+	return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) k_qs_count(const double *__restrict__ vals, int64_t n, const QsPass p, unsigned long long *hist,
+												   unsigned long long *nan_count)
+{
+	__shared__ uint32_t sh[2048];     // pass 0: the histogram; passes 1-2: first slot of every top digit (or 0xffffffff)
+	for (int t = threadIdx.x; t < 2048; t += blockDim.x)
+		sh[t] = p.pass == 0 ? 0u : 0xffffffffu;
+	__syncthreads();
+	if (p.pass > 0) {
+		for (int t = threadIdx.x; t < p.nslots; t += blockDim.x) {
+			const uint32_t top = p.pass == 1 ? p.prefix[t] : p.prefix[t] >> 11;
+			atomicMin(&sh[top], (uint32_t)t); // prefixes ascend: the slots of one top digit are contiguous
+		}
+		__syncthreads();
+	}
+	unsigned long long nans = 0;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint32_t key = mg_qs_key(__ldcs(vals + i));
+		if (key == 0xffffffffu) {
+			++nans;
+			continue;
+		}
+		if (p.pass == 0) {
+			atomicAdd(&sh[key >> 21], 1u);
+			continue;
+		}
+		uint32_t slot = sh[key >> 21];
+		if (slot == 0xffffffffu)
+			continue;
+		if (p.pass == 1) {
+			atomicAdd(hist + (size_t)slot * 2048 + ((key >> 10) & 2047u), 1ull);
+		} else {
+			const uint32_t pre = key >> 10;
+			for (; slot < (uint32_t)p.nslots && (p.prefix[slot] >> 11) == (pre >> 11); ++slot)
+				if (p.prefix[slot] == pre) {
+					atomicAdd(hist + (size_t)slot * 1024 + (key & 1023u), 1ull);
+					break;
+				}
+		}
+	}
+	if (p.pass == 0) {
+		__syncthreads();
+		for (int t = threadIdx.x; t < 2048; t += blockDim.x)
+			if (sh[t])
+				atomicAdd(hist + t, (unsigned long long)sh[t]);
+		if (nans)
+			atomicAdd(nan_count, nans);
+	}
+}
+
 // ---- gscreen comparison predicates on the device -----------------------------------------------------------------------------
 struct PredSpec {
 	int nterms, combine_or;

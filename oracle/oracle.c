@@ -65,6 +65,41 @@ float orc_percentile(float *vals, int64_t n, double percentile)
 	return orc_percentile_sorted(vals, n, percentile);
 }
 
+static int cmp_double(const void *a, const void *b)
+{
+	double x = *(const double *)a, y = *(const double *)b;
+	return (x > y) - (x < y);
+}
+
+/* gquantiles, exact regime (every value fits the reservoir). src/GenomeTrackQuantiles.cpp:167-173: each row's value is  */
+/* narrowed to float, NaN rows are dropped; :183-232 / src/StreamPercentiler.h:210-217: the quantile of the N kept      */
+/* values is samples[floor(idx)] * (1 - w) + samples[ceil(idx)] * w in double with idx = (N - 1) * clamp(pct, 0, 1);   */
+/* NaN when nothing was kept (:113-116). Returns N.                                                                    */
+int64_t orc_gquantiles(const double *vals, int64_t n, int nq, const double *pct, double *out)
+{
+	double *s = (double *)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+	int64_t N = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		float v = (float)vals[i];
+		if (!isnan(v))
+			s[N++] = (double)v;
+	}
+	qsort(s, (size_t)N, sizeof(double), cmp_double);
+	for (int k = 0; k < nq; ++k) {
+		if (!N) {
+			out[k] = ORC_NAN;
+			continue;
+		}
+		double p = pct[k] < 0. ? 0. : (pct[k] > 1. ? 1. : pct[k]);
+		double idx = (double)(N - 1) * p;
+		uint64_t i1 = (uint64_t)floor(idx), i2 = (uint64_t)ceil(idx);
+		double w = idx - (double)i1;
+		out[k] = s[i1] * (1.0 - w) + s[i2] * w;
+	}
+	free(s);
+	return N;
+}
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* Dense (fixed-bin) track window functions.                                                               */
 /* src/GenomeTrackFixedBin.cpp:607-1016 (generic path), :460-591 (single-function path), :1028-1075         */

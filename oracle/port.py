@@ -25,6 +25,7 @@ def lib():
             build()
         _lib = ctypes.CDLL(_SO)
         _lib.orc_percentile.restype = ctypes.c_float
+        _lib.orc_gquantiles.restype = c_i64
         _lib.orc_unify.restype = c_i64
         _lib.orc_fixedbin_rows.restype = c_i64
         _lib.orc_intervals_rows.restype = c_i64
@@ -81,6 +82,15 @@ def sparse_window(rs, re, rv, chromsize, start, end, sshift=0, eshift=0, percent
 def percentile(vals, p):
     v = np.array(vals, dtype=np.float32)
     return float(lib().orc_percentile(_p(v), c_i64(len(v)), ctypes.c_double(p)))
+
+
+def gquantiles(vals, percentiles):
+    """Exact-regime gquantiles of a value column (src/GenomeTrackQuantiles.cpp:167-232). Returns (quantiles, N kept)."""
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    p = np.ascontiguousarray(percentiles, dtype=np.float64)
+    out = np.empty(len(p), dtype=np.float64)
+    n = lib().orc_gquantiles(_p(v), c_i64(len(v)), ctypes.c_int(len(p)), _p(p), _p(out))
+    return out, int(n)
 
 
 def unify(chrom, start, end, unify_touching=True):

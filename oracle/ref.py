@@ -80,6 +80,14 @@ def sparse_eval(chrom_file, chromid, start, end, funcs=("avg",), percentile=0.5)
     return _eval(lib().ref_sparse_eval, chrom_file, chromid, start, end, funcs, percentile)
 
 
+def gquantiles(vals, percentiles):
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    p = np.ascontiguousarray(percentiles, dtype=np.float64)
+    out = np.empty(len(p), dtype=np.float64)
+    _check(lib().ref_gquantiles(_p(v), c_i64(len(v)), ctypes.c_int(len(p)), _p(p), _p(out)))
+    return out
+
+
 def percentile(vals, p):
     v = np.ascontiguousarray(vals, dtype=np.float32)
     out = ctypes.c_float()

@@ -119,6 +119,25 @@ extern "C" int ref_sparse_eval(const char *chrom_file, int chromid, uint32_t fun
 	REF_CATCH
 }
 
+// gquantiles' own object and loop, src/GenomeTrackQuantiles.cpp:165-173 + calc_medians' exact branch (:100-105):
+// StreamPercentiler<double> fed with float-narrowed non-NaN values, one get_percentile per requested quantile.
+extern "C" int ref_gquantiles(const double *vals, int64_t n, int nq, const double *pct, double *out)
+{
+	REF_TRY
+	StreamPercentiler<double> sp(n + 16, 1000, 1000);
+	for (int64_t i = 0; i < n; ++i) {
+		float val = vals[i];
+		if (!std::isnan(val))
+			sp.add(val, NULL);
+	}
+	for (int k = 0; k < nq; ++k) {
+		bool est;
+		out[k] = sp.stream_size() ? sp.get_percentile(pct[k], est) : std::numeric_limits<double>::quiet_NaN();
+	}
+	return 0;
+	REF_CATCH
+}
+
 // Exact-regime percentile (n <= reservoir), src/StreamPercentiler.h:191-217.
 extern "C" int ref_percentile(const float *vals, int64_t n, double percentile, float *out)
 {

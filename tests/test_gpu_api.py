@@ -189,3 +189,23 @@ def test_pwm_vtrack(db, golden):
     db.gvtrack_rm("motif")
     with pytest.raises(api.MishaError):
         db.gvtrack_create("motif", None, "pwm", dict(pssm=np.ones((5, 3))))
+
+
+def test_gquantiles(db):
+    """gquantiles over a windowed vtrack (the authors' flagship workload, NEWS.md:130) and over a bare track."""
+    bs, bins = read_dense("dense_track", "chr1")
+    db.gvtrack_create("wmax", "dense_track", "max")
+    db.gvtrack_iterator("wmax", sshift=-500, eshift=500)
+    pcts = [0.1, 0.5, 0.9, 0.999]
+    got = db.gquantiles("wmax", pcts, intervals=db.gintervals(1), iterator=200)
+    c, s, e, _ = port.fixedbin_rows(200, [0], [0], [500000])
+    col = port.dense_window(bins, bs, 500000, s, e, -500, 500, 0.5, ("max",))["max"]
+    exp, _ = port.gquantiles(col, pcts)
+    assert [got[p] for p in pcts] == list(exp)
+    got = db.gquantiles("dense_track", 0.5, intervals=db.gintervals(1, 0, 100000))
+    v = bins[:2000].astype(np.float64)
+    v[np.isinf(v)] = np.nan
+    assert got[0.5] == port.gquantiles(v, [0.5])[0][0]
+    with pytest.raises(api.MishaError, match="not in"):
+        db.gquantiles("dense_track", 2)
+    db.gvtrack_rm("wmax")

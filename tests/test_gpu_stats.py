@@ -215,3 +215,32 @@ def test_screen_compare_matches_r_semantics(gpu_ctx):
                 continue
             flag = gpu.screen_compare(gpu_ctx, cols, ops, thr, is_or, n).to_host()
             assert np.array_equal(flag.astype(bool), exp), (n, ops, is_or)
+
+
+def test_quantiles_golden_and_oracle(gpu_ctx):
+    """mg_quantiles (gquantiles' exact regime) against the reference's own vectors and the oracle, bit for bit."""
+    import os
+    from misha_b200 import gpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gquantiles_vectors.npz"))
+    pcts = g["pcts"]
+    ok = (pcts >= 0) & (pcts <= 1)  # the entry point rejects the rest, as C_gquantiles does
+    for key in g.files:
+        if not key.startswith("vals_"):
+            continue
+        v = g[key]
+        d = gpu_ctx.alloc(len(v), np.float64).from_host(v)
+        got, n = gpu.quantiles(gpu_ctx, d, len(v), pcts[ok])
+        assert np.array_equal(got, g["q_" + key[5:]][ok], equal_nan=True), key
+        assert n == int(np.sum(~np.isnan(v.astype(np.float32))))
+    with pytest.raises(gpu.MishaGpuError, match="not in"):
+        gpu.quantiles(gpu_ctx, d, len(v), [1.5])
+    rng = np.random.default_rng(41)
+    for n in (1, 2, 1000, 300001):
+        for gen in (lambda m: rng.normal(size=m), lambda m: np.round(rng.normal(size=m) * 2), lambda m: -rng.lognormal(size=m) * 1e-30,
+                    lambda m: np.where(rng.random(m) < 0.5, np.nan, rng.random(m))):
+            v = gen(n).astype(np.float64)
+            p = np.concatenate([[0, 1, 0.5], rng.random(20)])
+            d = gpu_ctx.alloc(n, np.float64).from_host(v)
+            got, nk = gpu.quantiles(gpu_ctx, d, n, p)
+            exp, en = port.gquantiles(v, p)
+            assert nk == en and np.array_equal(got, exp, equal_nan=True), n

@@ -157,3 +157,26 @@ def test_port_matches_compiled_reference_live():
         o = port.sparse_window(rs, re, rv, size, s, e, 0, 0, 0.37, funcs)
         for k in funcs:
             assert_same(o[k], r[k], f"sparse {c} {k}")
+
+
+def test_gquantiles_oracle_vs_reference_vectors():
+    """oracle.c's gquantiles against vectors produced by the reference's own StreamPercentiler<double>
+    (tests/golden/make_gquantiles_fixtures.py), bit for bit; and against the compiled reference live when it is present."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gquantiles_vectors.npz"))
+    pcts = g["pcts"]
+    for key in g.files:
+        if not key.startswith("vals_"):
+            continue
+        got, n = port.gquantiles(g[key], pcts)
+        assert np.array_equal(got, g["q_" + key[5:]], equal_nan=True), key
+        assert n == int(np.sum(~np.isnan(g[key].astype(np.float32))))
+    try:
+        from oracle import ref
+        ref.lib()
+    except Exception:  # noqa: BLE001 -- no compiled reference on this box
+        return
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=7777)
+    v[::13] = np.nan
+    assert np.array_equal(port.gquantiles(v, [0.1, 0.5, 0.93])[0], ref.gquantiles(v, [0.1, 0.5, 0.93]))
