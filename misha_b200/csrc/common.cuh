@@ -12,6 +12,8 @@
 #include <new>
 #include <algorithm>
 #include <limits>
+#include <chrono>
+#include <cstdlib>
 
 #include "../../include/mishagpu.h"
 

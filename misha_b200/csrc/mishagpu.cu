@@ -36,6 +36,13 @@ extern "C" int mg_init(int device, int nchroms, const int64_t *chrom_sizes, mg_c
 		delete ctx;
 		return mg_fail(nullptr, "mg_init: %s", cudaGetErrorString(e));
 	}
+	{ // staging scratch comes from the stream-ordered pool: keep what it frees (re-mapping memory per chromosome costs seconds)
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			uint64_t keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->cc = prop.major * 10 + prop.minor;
 	ctx->hbm_bytes = (int64_t)prop.totalGlobalMem;
@@ -157,11 +164,34 @@ extern "C" int mg_dev_memset(mg_ctx *ctx, void *d_ptr, int value, int64_t bytes,
 	return 0;
 }
 
+// Bump allocation out of large chunks: a staged dense chromosome is ~40 arrays, and cudaMalloc of hundreds of megabytes is
+// slow enough (it maps physical memory) that one chunk per chromosome instead of one call per array takes seconds off staging.
+struct MgArena {
+	char *cur = nullptr;
+	size_t left = 0, chunk = 0;
+};
+
 template <typename T>
-static int mg_alloc_tracked(mg_ctx *ctx, std::vector<void *> &allocs, int64_t &bytes, int64_t count, T **out)
+static int mg_alloc_tracked(mg_ctx *ctx, std::vector<void *> &allocs, int64_t &bytes, int64_t count, T **out, MgArena *arena = nullptr)
 {
 	void *p = nullptr;
 	size_t sz = sizeof(T) * (size_t)(count > 0 ? count : 1);
+	if (arena) {
+		sz = (sz + 255) & ~(size_t)255;
+		if (sz > arena->left) {
+			const size_t chunk = std::max(sz, arena->chunk);
+			MG_CUDA(ctx, cudaMalloc(&p, chunk));
+			allocs.push_back(p);
+			arena->cur = (char *)p;
+			arena->left = chunk;
+		}
+		p = arena->cur;
+		arena->cur += sz;
+		arena->left -= sz;
+		bytes += (int64_t)sz;
+		*out = (T *)p;
+		return 0;
+	}
 	MG_CUDA(ctx, cudaMalloc(&p, sz));
 	allocs.push_back(p);
 	bytes += (int64_t)sz;
@@ -196,17 +226,33 @@ extern "C" int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out)
 }
 
 // min/max pyramids + wavelet matrix of one staged chromosome (dense_index.cuh)
-static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const Pref *pref /* per-bin, staging only */)
+// MISHAGPU_STAGE_TIMING=1 prints the phases of the index build (development aid)
+struct StagePhase {
+	const char *name;
+	std::chrono::steady_clock::time_point t0;
+	bool on;
+	explicit StagePhase(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("MISHAGPU_STAGE_TIMING") != nullptr) {}
+	~StagePhase()
+	{
+		if (!on)
+			return;
+		cudaDeviceSynchronize();
+		fprintf(stderr, "[stage] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+
+static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const Pref *pref /* per-bin, staging only */, MgArena &arena)
 {
 	const int64_t nbins = dc.nbins;
 	// pyramids: level j+1 exists while level j has more than one group of 8
 	{
+		StagePhase ph("pyramids");
 		const float *cmax = dc.vals, *cmin = dc.vals;
 		int64_t nchild = nbins;
 		for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
 			const int64_t nparent = mg_div_up(nchild, 8), padded = (nparent + 7) / 8 * 8 + 8;
 			float *pmax = nullptr, *pmin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmin))
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmin, &arena))
 				return 1;
 			k_pyr_build<<<(unsigned)mg_div_up(padded, 256), 256>>>(cmax, cmin, nchild, pmax, pmin, padded);
 			MG_LAUNCH_CHECK(ctx);
@@ -219,11 +265,12 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	}
 	// sparse tables over the groups of 8 (level 0 = pyramid level 1)
 	{
+		StagePhase ph("sparse tables");
 		const int64_t ng = mg_div_up(nbins > 0 ? nbins : 1, 8);
 		dc.ngroups = ng;
 		if (!dc.pmax[0]) { // chromosomes of <= 8 bins have no pyramid level: build the single group entry
 			float *pmax = nullptr, *pmin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmin))
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmin, &arena))
 				return 1;
 			k_pyr_build<<<1, 256>>>(dc.vals, dc.vals, nbins, pmax, pmin, 16);
 			MG_LAUNCH_CHECK(ctx);
@@ -240,7 +287,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 				continue;
 			}
 			float *smax = nullptr, *smin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smax) || mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smin))
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smin, &arena))
 				return 1;
 			k_st_build<<<(unsigned)mg_div_up(ng, 256), 256>>>(dc.smax[j - 1], dc.smin[j - 1], ng, 1ll << (j - 1), smax, smin);
 			MG_LAUNCH_CHECK(ctx);
@@ -250,15 +297,17 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	}
 	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
 	{
+		StagePhase ph("block wavelet matrices");
 		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_STRIDE);
 		uint8_t *bw = nullptr;
-		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nblk * MG_BW_RECORD_BYTES, &bw))
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nblk * MG_BW_RECORD_BYTES, &bw, &arena))
 			return 1;
 		k_bw_build<<<(unsigned)nblk, MG_BW_BUILD_THREADS>>>(dc.vals, nbins, bw);
 		MG_LAUNCH_CHECK(ctx);
 		dc.bw = bw;
 	}
 	// wavelet matrix over the dense ranks of the non-NaN values
+	StagePhase ph_wm("chromosome wavelet matrix");
 	long long m = 0;
 	MG_CUDA(ctx, cudaMemcpy(&m, &pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
 	dc.wm_m = m;
@@ -270,8 +319,8 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	uint2 *wm = nullptr;
 	uint32_t *zeros = nullptr;
 	float *sorted = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * (nlevels > 0 ? nlevels : 1), &wm) ||
-		mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros) || mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &sorted))
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * (nlevels > 0 ? nlevels : 1), &wm, &arena) ||
+		mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &sorted, &arena))
 		return 1;
 	dc.wm = wm;
 	dc.wm_zeros = zeros;
@@ -279,12 +328,12 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	const size_t mm = (size_t)(m > 0 ? m : 1);
 	uint32_t *keys[2] = {nullptr, nullptr}, *pos[2] = {nullptr, nullptr}, *d_zero = nullptr;
 	uint2 *scratch = nullptr;
-	MG_CUDA(ctx, cudaMalloc(&keys[0], sizeof(uint32_t) * mm));
-	MG_CUDA(ctx, cudaMalloc(&keys[1], sizeof(uint32_t) * mm));
-	MG_CUDA(ctx, cudaMalloc(&pos[0], sizeof(uint32_t) * mm));
-	MG_CUDA(ctx, cudaMalloc(&pos[1], sizeof(uint32_t) * mm));
-	MG_CUDA(ctx, cudaMalloc(&scratch, sizeof(uint2) * dc.wm_blocks));
-	MG_CUDA(ctx, cudaMalloc(&d_zero, sizeof(uint32_t)));
+	MG_CUDA(ctx, cudaMallocAsync(&keys[0], sizeof(uint32_t) * mm, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&keys[1], sizeof(uint32_t) * mm, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&pos[0], sizeof(uint32_t) * mm, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&pos[1], sizeof(uint32_t) * mm, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(uint2) * dc.wm_blocks, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&d_zero, sizeof(uint32_t), 0));
 	if (nbins) {
 		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, pref, nbins, keys[0], pos[0]);
 		MG_LAUNCH_CHECK(ctx);
@@ -318,7 +367,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 		const uint32_t *src = wk[lv & 1];
 		if (lv >= 4 && (lv & 3) == 0) { // checkpoint: the rank keys in the order entering this level
 			uint32_t *ck = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &ck))
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &ck, &arena))
 				return 1;
 			MG_CUDA(ctx, cudaMemset(ck + m, 0xff, sizeof(uint32_t) * 16));
 			k_wm_ckpt<<<gm, 256>>>(src, m, sorted, ck);
@@ -334,12 +383,12 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 		MG_LAUNCH_CHECK(ctx);
 	}
 	MG_CUDA(ctx, cudaDeviceSynchronize());
-	cudaFree(keys[0]);
-	cudaFree(keys[1]);
-	cudaFree(pos[0]);
-	cudaFree(pos[1]);
-	cudaFree(scratch);
-	cudaFree(d_zero);
+	cudaFreeAsync(keys[0], 0);
+	cudaFreeAsync(keys[1], 0);
+	cudaFreeAsync(pos[0], 0);
+	cudaFreeAsync(pos[1], 0);
+	cudaFreeAsync(scratch, 0);
+	cudaFreeAsync(d_zero, 0);
 	return 0;
 }
 
@@ -353,25 +402,27 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	MG_REQUIRE(ctx, nbins == expect, "mg_dense_stage: chromosome %d holds %lld bins, expected %lld for bin size %u", chromid,
 			   (long long)nbins, (long long)expect, t->bin_size);
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	MgArena arena;
+	arena.chunk = (size_t)72 * (size_t)nbins + ((size_t)4 << 20); // ~64 bytes per bin of index structures: one chunk per chromosome
 	float *vals = nullptr;
 	Pref *pref = nullptr;
 	const int64_t padded = (nbins + 7) / 8 * 8 + 8; // group-of-8 / float4-safe tail, NaN filled
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals))
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals, &arena))
 		return 1;
-	MG_CUDA(ctx, cudaMalloc(&pref, sizeof(Pref) * (size_t)(nbins + 1))); // per-bin prefix: staging scratch, released below
+	MG_CUDA(ctx, cudaMallocAsync(&pref, sizeof(Pref) * (size_t)(nbins + 1), 0)); // per-bin prefix: staging scratch, released below
 	MG_CUDA(ctx, cudaMemset(vals, 0xff, sizeof(float) * padded)); // 0xffffffff is a NaN
 	if (nbins)
 		MG_CUDA(ctx, cudaMemcpy(vals, h_bins, sizeof(float) * nbins, cudaMemcpyHostToDevice));
 	const int64_t ntiles = mg_div_up(nbins + 1, MG_ST_TILE); // +1: the closing entry pref[nbins]
 	double *tile_sum = nullptr, *tile_abs = nullptr, *tile_sq = nullptr, *abs_total = nullptr, *pref2 = nullptr;
 	long long *tile_cnt = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref2))
+	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref2, &arena))
 		return 1;
-	MG_CUDA(ctx, cudaMalloc(&tile_sum, sizeof(double) * ntiles));
-	MG_CUDA(ctx, cudaMalloc(&tile_abs, sizeof(double) * ntiles));
-	MG_CUDA(ctx, cudaMalloc(&tile_sq, sizeof(double) * ntiles));
-	MG_CUDA(ctx, cudaMalloc(&tile_cnt, sizeof(long long) * ntiles));
-	MG_CUDA(ctx, cudaMalloc(&abs_total, sizeof(double) * 2));
+	MG_CUDA(ctx, cudaMallocAsync(&tile_sum, sizeof(double) * ntiles, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&tile_abs, sizeof(double) * ntiles, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&tile_sq, sizeof(double) * ntiles, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&tile_cnt, sizeof(long long) * ntiles, 0));
+	MG_CUDA(ctx, cudaMallocAsync(&abs_total, sizeof(double) * 2, 0));
 	k_dense_clean_reduce<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_abs, tile_sq);
 	MG_LAUNCH_CHECK(ctx);
 	k_dense_tile_scan<<<1, 1024>>>(tile_sum, tile_cnt, tile_abs, tile_sq, ntiles, abs_total);
@@ -384,7 +435,7 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	{
 		const int64_t nent = mg_div_up(nbins, 8) + 1;
 		Pref *p8 = nullptr;
-		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nent, &p8))
+		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nent, &p8, &arena))
 			return 1;
 		k_p8_build<<<(unsigned)mg_div_up(nent, 256), 256>>>(pref, nbins, p8, nent);
 		MG_LAUNCH_CHECK(ctx);
@@ -398,16 +449,16 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 		dc.abs_sum = tot[0];
 		dc.sq_sum = tot[1];
 	}
-	if (mg_dense_build_index(ctx, t, dc, pref))
+	if (mg_dense_build_index(ctx, t, dc, pref, arena))
 		return 1;
-	cudaFree(pref);
+	cudaFreeAsync(pref, 0);
 	t->h_table[chromid] = dc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &dc, sizeof(DenseChrom), cudaMemcpyHostToDevice));
-	cudaFree(tile_sum);
-	cudaFree(tile_abs);
-	cudaFree(tile_sq);
-	cudaFree(tile_cnt);
-	cudaFree(abs_total);
+	cudaFreeAsync(tile_sum, 0);
+	cudaFreeAsync(tile_abs, 0);
+	cudaFreeAsync(tile_sq, 0);
+	cudaFreeAsync(tile_cnt, 0);
+	cudaFreeAsync(abs_total, 0);
 	return 0;
 }
 
