@@ -8,7 +8,9 @@
 //   * the k-th smallest non-NaN value of a window is the k-th smallest RANK of the window's positions (k < n, n = the
 //     window's non-NaN count from the prefix entries) -- NaNs never need compacting;
 //   * the (k+1)-th is the next larger rank whose position lies in the window: a short scan of pos_of_rank.
-// A block record is LB levels x B/32 units {uint32 ones before the unit, uint32 bits} followed by pos_of_rank[B] (uint16).
+// A block record is LB levels x B/32 units {uint32 ones before the unit, uint32 bits}, one more such level marking the NaN
+// bins (a quantile-only query gets its non-NaN count from it: two lookups instead of the prefix entries and two sectors of
+// bins), and pos_of_rank[B] (uint16).
 // Rows sorted by position walk the same 5.6 KB of levels as their neighbours: the walk runs out of L1 instead of paying
 // one L2/HBM round trip per level as the chromosome-wide matrix (dense_index.cuh) does. The value of a rank is read from
 // the track itself: vals[b*S + pos_of_rank[rank]].
@@ -27,7 +29,9 @@
 #define MG_BW_HALF (MG_BW_B / 2)         // zeros of every level (the ranks are a permutation of [0, B))
 #define MG_BW_UNITS (MG_BW_B / 32)
 #define MG_BW_LEVEL_BYTES (MG_BW_UNITS * 8)
-#define MG_BW_RECORD_BYTES (MG_BW_LB * MG_BW_LEVEL_BYTES + MG_BW_B * 2)
+#define MG_BW_NAN_OFFSET (MG_BW_LB * MG_BW_LEVEL_BYTES)              // one more level-shaped bitmap: bit = the bin is NaN
+#define MG_BW_POS_OFFSET (MG_BW_NAN_OFFSET + MG_BW_LEVEL_BYTES)        // pos_of_rank[B] (uint16)
+#define MG_BW_RECORD_BYTES (MG_BW_POS_OFFSET + MG_BW_B * 2)
 #define MG_BW_BUILD_THREADS 1024
 #define MG_BW_PER_THREAD (MG_BW_B / MG_BW_BUILD_THREADS)
 
@@ -54,6 +58,16 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 		const int64_t i = base + e;
 		const float v = i < nbins ? vals[i] : mg_nanf();
 		skey[e] = ((unsigned long long)mg_bw_key(v) << 32) | (unsigned)e;
+		const uint32_t nanbits = __ballot_sync(0xffffffffu, v != v);
+		if ((t & 31) == 0)
+			sbits[e >> 5] = nanbits;
+	}
+	__syncthreads();
+	if (t < MG_BW_UNITS) { // the NaN level: few units, a serial count per unit is fine
+		uint32_t before = 0;
+		for (int u = 0; u < t; ++u)
+			before += __popc(sbits[u]);
+		reinterpret_cast<uint2 *>(rec + MG_BW_NAN_OFFSET)[t] = make_uint2(before, sbits[t]);
 	}
 	__syncthreads();
 	for (int k = 2; k <= MG_BW_B; k <<= 1) {
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 			__syncthreads();
 		}
 	}
-	uint16_t *pos_of_rank = reinterpret_cast<uint16_t *>(rec + MG_BW_LB * MG_BW_LEVEL_BYTES);
+	uint16_t *pos_of_rank = reinterpret_cast<uint16_t *>(rec + MG_BW_POS_OFFSET);
 	uint16_t *cur = sa, *nxt = sb;
 	uint32_t mypos[MG_BW_PER_THREAD];
 #pragma unroll
@@ -148,6 +162,13 @@ __device__ __forceinline__ uint32_t mg_bw_rank_hi(const uint2 *__restrict__ lv, 
 	return u.x + __popc(u.y << (~j & 31u));
 }
 
+// non-NaN bins of the block-local window [l, r), r > l
+__device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ rec, uint32_t l, uint32_t r)
+{
+	const uint2 *lv = reinterpret_cast<const uint2 *>(rec + MG_BW_NAN_OFFSET);
+	return (r - l) - (mg_bw_rank_hi(lv, r) - mg_bw_rank_lo(lv, l));
+}
+
 // k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l; with want2 (k + 1 < n) also the
 // (k+1)-th. vals_block = the track at the block's first bin.
 __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l, uint32_t r, uint32_t k,
@@ -166,7 +187,7 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, co
 		k = one ? k - nz : k;
 		rank = (rank << 1) | (one ? 1u : 0u);
 	}
-	const uint16_t *pos_of_rank = reinterpret_cast<const uint16_t *>(rec + MG_BW_LB * MG_BW_LEVEL_BYTES);
+	const uint16_t *pos_of_rank = reinterpret_cast<const uint16_t *>(rec + MG_BW_POS_OFFSET);
 	x1 = __ldg(vals_block + __ldg(pos_of_rank + rank));
 	x2 = x1;
 	if (want2) {

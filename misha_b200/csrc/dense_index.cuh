@@ -400,7 +400,7 @@ __device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint
 // price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several (0.695 -> 0.616 ms for avg + max + quantile).
 #define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) ((SD) ? 4 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 8 : 6))
 // the levels of a block record (the pos_of_rank half is touched at one or two places per row: not worth prefetching)
-#define MG_PREFETCH_LINES (MG_BW_LB * MG_BW_LEVEL_BYTES / 128)
+#define MG_PREFETCH_LINES (MG_BW_POS_OFFSET / 128)
 template <bool SUM, bool MM, bool Q, bool SD>
 __global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const DenseQuery q)
 {
@@ -432,7 +432,12 @@ __global__ void __launch_bounds__(256, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_
 		if (pb < w.ebin)
 			mg_prefetch(w.ch->vals + pb);
 	}
-	if (nb > 0) {
+	// a quantile-only row inside one block needs neither bins nor prefix entries: its non-NaN count is in the block record
+	const bool count_from_block = Q && !SUM && !SD && !MM && q.use_bw && nb > 0 && nb <= MG_BW_S;
+	if (count_from_block) {
+		const uint32_t blk = (uint32_t)w.sbin / MG_BW_STRIDE, l = (uint32_t)w.sbin - blk * MG_BW_STRIDE;
+		wb.n = mg_bw_count(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, l, l + (uint32_t)nb);
+	} else if (nb > 0) {
 		// one pass over the window's two partial groups feeds the sum, the count and level 0 of the pyramids
 		mg_win_basic<SUM || SD, MM, SUM || SD || Q>(w.ch, w.sbin, w.ebin, wb);
 		if (SUM || SD)
