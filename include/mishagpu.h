@@ -78,6 +78,8 @@ int mg_sync(mg_ctx *ctx, void *stream);
  *                        per-row search kernels, instead of the index structures / merge kernels (tests, profiling)
  *   "block_wm" = 0       quantiles from the chromosome-wide wavelet matrix only (default 1: block-local matrices for windows
  *                        of <= 1024 bins)
+ *   "stage_slots" = n    block records a row-query thread block stages in shared memory for its quantile walks (default 5,
+ *                        0 = every walk reads its record through L1; at most 12)
  *   "prefetch" = 0       no L1 prefetch of block records / window lines in the row-query kernels
  *   "pwm_strict" = 1     PWM log-sum-exp with double-precision exp / log rounded to float (default: float expf / logf)
  *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 2^19)

@@ -67,6 +67,7 @@ struct DenseQuery {
 	int nq;
 	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
+	int stage_slots; // block records a thread block of the row-query kernel stages in shared memory (0 = none)
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
 };

@@ -8,12 +8,13 @@
 //   * the k-th smallest non-NaN value of a window is the k-th smallest RANK of the window's positions (k < n, n = the
 //     window's non-NaN count from the prefix entries) -- NaNs never need compacting;
 //   * the (k+1)-th is the next larger rank whose position lies in the window: a short scan of pos_of_rank.
-// A block record is LB levels x B/32 units {uint32 ones before the unit, uint32 bits}, one more such level marking the NaN
-// bins (a quantile-only query gets its non-NaN count from it: two lookups instead of the prefix entries and two sectors of
-// bins), and pos_of_rank[B] (uint16).
-// Rows sorted by position walk the same 5.6 KB of levels as their neighbours: the walk runs out of L1 instead of paying
-// one L2/HBM round trip per level as the chromosome-wide matrix (dense_index.cuh) does. The value of a rank is read from
-// the track itself: vals[b*S + pos_of_rank[rank]].
+// A block record is LB levels of {uint64 bits[B/64], uint16 ones_before_word[B/64]} (10 bytes per 64 bins: 320 bytes a level
+// for B = 2048), one more such level marking the NaN bins (a quantile-only query gets its non-NaN count from it: two
+// lookups instead of the prefix entries and two sectors of bins), and pos_of_rank[B] (uint16).
+// Rows sorted by position walk the same 3.8 KB of levels as their neighbours. The row-query kernel stages the levels of the
+// records its 256 rows need in shared memory with one bulk copy each (cp.async.bulk + mbarrier), so the LB dependent steps
+// of a walk are shared-memory reads; a row whose record is not among the staged ones walks the same bytes through L1. The
+// value of a rank is read from the track itself: vals[b*S + pos_of_rank[rank]].
 #pragma once
 #include "common.cuh"
 #include "dense.cuh"
@@ -27,10 +28,14 @@
 #endif
 #define MG_BW_S (MG_BW_B - MG_BW_STRIDE) // longest window that is guaranteed to lie inside one block
 #define MG_BW_HALF (MG_BW_B / 2)         // zeros of every level (the ranks are a permutation of [0, B))
-#define MG_BW_UNITS (MG_BW_B / 32)
-#define MG_BW_LEVEL_BYTES (MG_BW_UNITS * 8)
+#define MG_BW_UNITS (MG_BW_B / 32)                                    // 32-bit ballots per level (build only)
+#define MG_BW_WORDS (MG_BW_B / 64)                                    // 64-bit words per level
+#define MG_BW_CNT_OFFSET (MG_BW_WORDS * 8)                            // uint16 ones before each word, after the words
+#define MG_BW_LEVEL_BYTES (MG_BW_WORDS * 10)
 #define MG_BW_NAN_OFFSET (MG_BW_LB * MG_BW_LEVEL_BYTES)              // one more level-shaped bitmap: bit = the bin is NaN
 #define MG_BW_POS_OFFSET (MG_BW_NAN_OFFSET + MG_BW_LEVEL_BYTES)        // pos_of_rank[B] (uint16)
+#define MG_BW_STAGE_BYTES MG_BW_POS_OFFSET                            // what a staged record holds: the levels and the NaN level
+static_assert(MG_BW_LEVEL_BYTES % 16 == 0 && MG_BW_B <= 65536, "levels must stay 16-byte multiples (bulk copies) with 16-bit counts");
 #define MG_BW_RECORD_BYTES (MG_BW_POS_OFFSET + MG_BW_B * 2)
 #define MG_BW_BUILD_THREADS 1024
 #define MG_BW_PER_THREAD (MG_BW_B / MG_BW_BUILD_THREADS)
@@ -63,11 +68,12 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 			sbits[e >> 5] = nanbits;
 	}
 	__syncthreads();
-	if (t < MG_BW_UNITS) { // the NaN level: few units, a serial count per unit is fine
+	if (t < MG_BW_WORDS) { // the NaN level: few words, a serial count per word is fine
 		uint32_t before = 0;
-		for (int u = 0; u < t; ++u)
+		for (int u = 0; u < 2 * t; ++u)
 			before += __popc(sbits[u]);
-		reinterpret_cast<uint2 *>(rec + MG_BW_NAN_OFFSET)[t] = make_uint2(before, sbits[t]);
+		reinterpret_cast<unsigned long long *>(rec + MG_BW_NAN_OFFSET)[t] = ((unsigned long long)sbits[2 * t + 1] << 32) | sbits[2 * t];
+		reinterpret_cast<uint16_t *>(rec + MG_BW_NAN_OFFSET + MG_BW_CNT_OFFSET)[t] = (uint16_t)before;
 	}
 	__syncthreads();
 	for (int k = 2; k <= MG_BW_B; k <<= 1) {
@@ -97,8 +103,8 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 	for (int j = 0; j < MG_BW_PER_THREAD; ++j)
 		cur[mypos[j]] = (uint16_t)(t + j * MG_BW_BUILD_THREADS);
 	__syncthreads();
-	uint2 *level = reinterpret_cast<uint2 *>(rec);
-	for (int lv = 0; lv < MG_BW_LB; ++lv, level += MG_BW_UNITS) {
+	uint8_t *level = rec;
+	for (int lv = 0; lv < MG_BW_LB; ++lv, level += MG_BW_LEVEL_BYTES) {
 		const int shift = MG_BW_LB - 1 - lv;
 		uint32_t myword[MG_BW_PER_THREAD];
 #pragma unroll
@@ -138,8 +144,11 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 			const uint32_t ones_before = scnt[e >> 5] + __popc(bits & ((1u << lane) - 1u));
 			const uint16_t v = cur[e];
 			nxt[((bits >> lane) & 1u) ? MG_BW_HALF + ones_before : (uint32_t)e - ones_before] = v;
-			if (lane == 0)
-				level[e >> 5] = make_uint2(scnt[e >> 5], bits);
+			if (lane == 0) { // little-endian: ballot 2w is the low half of word w
+				reinterpret_cast<uint32_t *>(level)[e >> 5] = bits;
+				if (!((e >> 5) & 1))
+					reinterpret_cast<uint16_t *>(level + MG_BW_CNT_OFFSET)[e >> 6] = (uint16_t)scnt[e >> 5];
+			}
 		}
 		__syncthreads();
 		uint16_t *tmp = cur;
@@ -148,38 +157,51 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 	}
 }
 
-// ones among positions [0, i) of a level, 0 <= i < B
-__device__ __forceinline__ uint32_t mg_bw_rank_lo(const uint2 *__restrict__ lv, uint32_t i)
+// G: the record is read from global memory through the read-only path (true) or from its shared-memory copy (false)
+template <bool G, typename T>
+__device__ __forceinline__ T mg_bw_ld(const T *p)
 {
-	const uint2 u = __ldg(lv + (i >> 5));
-	return u.x + __popc(u.y & ((1u << (i & 31u)) - 1u));
+	return G ? __ldg(p) : *p;
 }
-// ones among positions [0, i) of a level, 1 <= i <= B (looks at the unit of position i - 1, so i == B needs no padding unit)
-__device__ __forceinline__ uint32_t mg_bw_rank_hi(const uint2 *__restrict__ lv, uint32_t i)
+// ones among positions [0, i) of a level, 0 <= i < B
+template <bool G>
+__device__ __forceinline__ uint32_t mg_bw_rank_lo(const uint8_t *__restrict__ lv, uint32_t i)
 {
-	const uint32_t j = i - 1u;
-	const uint2 u = __ldg(lv + (j >> 5));
-	return u.x + __popc(u.y << (~j & 31u));
+	const uint32_t w = i >> 6;
+	const unsigned long long bits = mg_bw_ld<G>(reinterpret_cast<const unsigned long long *>(lv) + w);
+	const uint32_t c = mg_bw_ld<G>(reinterpret_cast<const uint16_t *>(lv + MG_BW_CNT_OFFSET) + w);
+	return c + __popcll(bits & ((1ull << (i & 63u)) - 1ull));
+}
+// ones among positions [0, i) of a level, 1 <= i <= B (looks at the word of position i - 1, so i == B needs no padding word)
+template <bool G>
+__device__ __forceinline__ uint32_t mg_bw_rank_hi(const uint8_t *__restrict__ lv, uint32_t i)
+{
+	const uint32_t j = i - 1u, w = j >> 6;
+	const unsigned long long bits = mg_bw_ld<G>(reinterpret_cast<const unsigned long long *>(lv) + w);
+	const uint32_t c = mg_bw_ld<G>(reinterpret_cast<const uint16_t *>(lv + MG_BW_CNT_OFFSET) + w);
+	return c + __popcll(bits << (~j & 63u));
 }
 
-// non-NaN bins of the block-local window [l, r), r > l
-__device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ rec, uint32_t l, uint32_t r)
+// non-NaN bins of the block-local window [l, r), r > l; lv = the record's levels (global or staged)
+template <bool G>
+__device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ lv, uint32_t l, uint32_t r)
 {
-	const uint2 *lv = reinterpret_cast<const uint2 *>(rec + MG_BW_NAN_OFFSET);
-	return (r - l) - (mg_bw_rank_hi(lv, r) - mg_bw_rank_lo(lv, l));
+	lv += MG_BW_NAN_OFFSET;
+	return (r - l) - (mg_bw_rank_hi<G>(lv, r) - mg_bw_rank_lo<G>(lv, l));
 }
 
 // k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l; with want2 (k + 1 < n) also the
-// (k+1)-th. vals_block = the track at the block's first bin.
-__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l, uint32_t r, uint32_t k,
-											 bool want2, float &x1, float &x2)
+// (k+1)-th. lv = the record's levels (global or staged), rec = the record in global memory (pos_of_rank is read there),
+// vals_block = the track at the block's first bin.
+template <bool G>
+__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l,
+											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
 {
-	const uint2 *lv = reinterpret_cast<const uint2 *>(rec);
 	const uint32_t l0 = l, len = r - l;
 	uint32_t rank = 0;
 #pragma unroll
-	for (int level = 0; level < MG_BW_LB; ++level, lv += MG_BW_UNITS) {
-		const uint32_t ol = mg_bw_rank_lo(lv, l), orr = mg_bw_rank_hi(lv, r);
+	for (int level = 0; level < MG_BW_LB; ++level, lv += MG_BW_LEVEL_BYTES) {
+		const uint32_t ol = mg_bw_rank_lo<G>(lv, l), orr = mg_bw_rank_hi<G>(lv, r);
 		const uint32_t nz = (r - l) - (orr - ol);
 		const bool one = k >= nz;
 		l = one ? MG_BW_HALF + ol : l - ol;
@@ -199,4 +221,35 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ rec, co
 		} while (p - l0 >= len && rank < MG_BW_B - 1);
 		x2 = __ldg(vals_block + p);
 	}
+}
+
+// ---- staging a record's levels in shared memory: one bulk copy per record, completion on an mbarrier ---------------------
+__device__ __forceinline__ uint32_t mg_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mg_mbar_init(uint64_t *bar, uint32_t arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mg_smem_addr(bar)), "r"(arrivals) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mg_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mg_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mg_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mg_smem_addr(dst)), "l"(src), "r"(bytes),
+				 "r"(mg_smem_addr(bar))
+				 : "memory");
+}
+__device__ __forceinline__ void mg_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n"
+				 ".reg .pred p;\n"
+				 "MG_WAIT_%=:\n"
+				 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+				 "@p bra MG_DONE_%=;\n"
+				 "bra MG_WAIT_%=;\n"
+				 "MG_DONE_%=:\n"
+				 "}" ::"r"(mg_smem_addr(bar)),
+				 "r"(parity)
+				 : "memory");
 }

@@ -96,6 +96,12 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->prefetch = value != 0;
 		return 0;
 	}
+	if (name && !strcmp(name, "stage_slots")) {
+		if (value < 0 || value * MG_BW_STAGE_BYTES > 48 * 1024)
+			return mg_fail(ctx, "mg_set_option: stage_slots must be in [0, %d]", 48 * 1024 / MG_BW_STAGE_BYTES);
+		ctx->stage_slots = (int)value;
+		return 0;
+	}
 	if (name && !strcmp(name, "block_wm")) {
 		ctx->block_wm = value != 0;
 		return 0;
@@ -635,6 +641,7 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
 	q.use_bw = ctx->block_wm ? 1 : 0;
 	q.prefetch = ctx->prefetch ? 1 : 0;
+	q.stage_slots = ctx->stage_slots;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {
 		const int f = funcs[k];
@@ -669,10 +676,11 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		// everything else comes from the index structures, one thread per row
 		const unsigned grid = (unsigned)mg_div_up(q.count, 256);
 		const bool want_sd = q.out[MG_STDDEV] != nullptr;
+		const size_t stage_bytes = q.nq > 0 && q.use_bw ? (size_t)q.stage_slots * MG_BW_STAGE_BYTES : 0;
 		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0) | (want_sd ? 8 : 0);
 #define MG_RQ_CASE(K)                                                                                                    \
 	case K:                                                                                                             \
-		k_dense_rowquery<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, 256, 0, st>>>(q);           \
+		k_dense_rowquery<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, MG_RQ_THREADS, stage_bytes, st>>>(q); \
 		break;
 		switch (key) {
 			MG_RQ_CASE(1) MG_RQ_CASE(2) MG_RQ_CASE(3) MG_RQ_CASE(4) MG_RQ_CASE(5) MG_RQ_CASE(6) MG_RQ_CASE(7) MG_RQ_CASE(8) MG_RQ_CASE(9)

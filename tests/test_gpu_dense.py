@@ -205,3 +205,67 @@ def test_block_wavelet_matches_global_and_oracle():
             assert_same(blk[k], exp["quantile"], f"block wavelet q{p} vs oracle")
     finally:
         ctx2.close()
+
+
+def test_staged_block_records_any_row_order():
+    """The row-query kernel stages the block records of its 256 rows in shared memory (bulk copy + mbarrier) when they are
+    neighbours; rows of another chromosome, rows far apart and unsorted rows take the L1 path inside the same thread block.
+    Whatever the mix: identical to stage_slots = 0 and to the oracle, bit for bit."""
+    from misha_b200 import gpu
+    nbs = [2048 * 6 + 300, 2048 * 3 + 11]
+    sizes = [nb * 20 - 3 for nb in nbs]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(4242)
+        tracks = []
+        t = gpu.DenseTrack(ctx2, 20)
+        for c, nb in enumerate(nbs):
+            bins = rng.normal(0, 2, nb).astype(np.float32)
+            bins[rng.integers(0, nb, nb // 20)] = np.nan
+            bins[rng.integers(0, nb, nb // 30)] = np.float32(0.25)
+            tracks.append(bins)
+            t.stage(c, bins)
+
+        def check(chrom, s, e, sshift, eshift, label):
+            rows = ctx2.rows_upload(chrom.astype(np.int32), s, e)
+            funcs = [("quantile", 0.9), ("quantile", 0.31), "avg", "max"]
+            outs = {}
+            for slots in (5, 0, 1, 12):
+                ctx2.set_option("stage_slots", slots)
+                outs[slots] = t.window(rows, funcs, sshift=sshift, eshift=eshift)
+                outs[(slots, "q")] = t.window(rows, [("quantile", 0.9)], sshift=sshift, eshift=eshift)  # count from the staged NaN level
+            ctx2.set_option("stage_slots", 5)
+            for slots in (0, 1, 12):
+                for k in range(len(funcs)):
+                    assert_same(outs[5][k], outs[slots][k], f"{label}: stage_slots 5 vs {slots}, {funcs[k]}")
+                assert_same(outs[(5, "q")][0], outs[(slots, "q")][0], f"{label}: quantile-only, stage_slots 5 vs {slots}")
+            assert_same(outs[(5, "q")][0], outs[5][0], f"{label}: quantile-only vs fused")
+            for c in range(len(nbs)):
+                m = chrom == c
+                if m.any():
+                    for k, p in ((0, 0.9), (1, 0.31)):
+                        exp = port.dense_window(tracks[c], 20, sizes[c], s[m], e[m], sshift, eshift, p, ("quantile",))
+                        assert_same(outs[5][k][m], exp["quantile"], f"{label}: q{p} vs oracle, chrom {c}")
+
+        # dense sorted rows over both chromosomes (thread blocks that straddle the chromosome change)
+        per = [3000, 1500]
+        chrom = np.repeat(np.arange(2), per)
+        s = np.concatenate([np.sort(rng.integers(0, sizes[c] - 400, per[c])) for c in range(2)])
+        e = s + rng.integers(100, 300, len(s))
+        check(chrom, s, e, -5000, 5000, "sorted")
+        # the same rows shuffled
+        perm = rng.permutation(len(s))
+        check(chrom[perm], s[perm], e[perm], -5000, 5000, "shuffled")
+        # few rows, far apart (more blocks than slots), windows of every size up to the block limit and beyond
+        n = 700
+        chrom = np.sort(rng.integers(0, 2, n))
+        s = np.array([rng.integers(0, sizes[c] - 30000) for c in chrom])
+        order = np.lexsort((s, chrom))
+        chrom, s = chrom[order], s[order]
+        e = s + rng.choice([1, 20, 2000, 20480, 20500, 29000], n)
+        check(chrom, s, e, 0, 0, "sparse")
+        # partial last thread block, every row in one block record
+        s = np.arange(0, 300) * 20 + 40000
+        check(np.zeros(300, np.int64), s, s + 1000, -200, 200, "one-record")
+    finally:
+        ctx2.close()
