@@ -60,7 +60,18 @@ enum mg_func {
 	MG_NEAREST = 6,  /* "nearest" (dense: == avg) */
 	MG_SIZE = 7,     /* "size": number of non-NaN values */
 	MG_EXISTS = 8,   /* "exists" */
-	MG_NUM_FUNCS = 9
+	/* the order-dependent functions of the generic read_interval path (src/GenomeTrackFixedBin.cpp:881-939,
+	 * src/GenomeTrackSparse.h:143-259). Positions are absolute coordinates -- dense: max(bin start, window start), sparse: the
+	 * record's start -- or, with param != 0, relative to the (shifted, clamped) window start as the "*.pos.relative" vtrack
+	 * functions return them (src/TrackVarProcessor.cpp:113-173). "sample" / "sample.pos.*" draw from R's RNG: not offered. */
+	MG_LSE = 9,        /* "lse": log(sum(exp(v))) */
+	MG_FIRST = 10,     /* "first": first non-NaN value */
+	MG_LAST = 11,      /* "last" */
+	MG_FIRST_POS = 12, /* "first.pos.abs" / "first.pos.relative" */
+	MG_LAST_POS = 13,  /* "last.pos.abs" / "last.pos.relative" */
+	MG_MIN_POS = 14,   /* "min.pos.abs" / "min.pos.relative": position of the first bin / record holding the minimum */
+	MG_MAX_POS = 15,   /* "max.pos.abs" / "max.pos.relative" */
+	MG_NUM_FUNCS = 16
 };
 
 /* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */

@@ -17,7 +17,17 @@ import numpy as np
 
 from . import gpu
 
-TRACK_FUNCS = ("avg", "sum", "min", "max", "stddev", "quantile", "nearest", "size", "exists")
+FUSED_FUNCS = ("avg", "sum", "min", "max", "stddev", "quantile", "nearest", "size", "exists")
+# "<f>.pos.abs" / "<f>.pos.relative" (R/vtrack.R; src/TrackVarProcessor.cpp:113-173): one device function, param = relative
+POS_FUNCS = {"%s.pos.%s" % (f, k): ("%s.pos" % f, float(k == "relative")) for f in ("first", "last", "min", "max") for k in ("abs", "relative")}
+TRACK_FUNCS = FUSED_FUNCS + ("lse", "first", "last") + tuple(POS_FUNCS)
+
+
+def _gpu_func(vt):
+    """The (name, param) the C ABI takes for a track vtrack's function."""
+    if vt.func == "quantile":
+        return ("quantile", float(vt.params))
+    return POS_FUNCS.get(vt.func, vt.func)
 PWM_FUNCS = ("pwm", "pwm.max", "pwm.count")
 
 
@@ -378,7 +388,7 @@ class MishaDB:
         if vt is None:  # a bare track name: avg (src/TrackExpressionVars.cpp:1543-1546)
             vt = _VTrack(name, name, "avg", None)
         if isinstance(vt.src, str):
-            f = vt.func if vt.func != "quantile" else ("quantile", float(vt.params))
+            f = _gpu_func(vt)
             kind = self._track_type(vt.src)
             t = self._dense_track(vt.src) if kind == "dense" else self._sparse_track(vt.src)
             return t.window_dev(rows, [f], vt.sshift, vt.eshift)[0]
@@ -509,13 +519,13 @@ class MishaDB:
         expr = expr.strip()
         vt = self.vtracks.get(expr)
         bare_dense = (vt is None and self.gtrack_exists(expr) and self._track_type(expr) == "dense") or \
-                     (vt is not None and isinstance(vt.src, str) and self._track_type(vt.src) == "dense")
+                     (vt is not None and isinstance(vt.src, str) and self._track_type(vt.src) == "dense" and vt.func in FUSED_FUNCS)
         if rows.n:
             if bare_dense:  # fused on the device: values never leave the chip
                 if vt is None:
                     self._dense_track(expr).summary_dev(rows, "avg", part)
                 else:
-                    f = vt.func if vt.func != "quantile" else ("quantile", float(vt.params))
+                    f = _gpu_func(vt)
                     self._dense_track(vt.src).summary_dev(rows, f, part, vt.sshift, vt.eshift)
             else:
                 v = np.asarray(self._eval(expr, rows, {}), dtype=np.float64)

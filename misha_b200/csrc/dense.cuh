@@ -64,6 +64,7 @@ struct DenseQuery {
 	uint32_t bin_size;
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
 	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
+	uint32_t pos_rel; // bit f set: position function f is reported relative to the window start
 	int nq;
 	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const floa
 struct DenseWin {
 	const DenseChrom *ch;
 	int64_t sbin, ebin;
+	int64_t ws;    // the window's start coordinate
+	bool one_bin;  // the window lies inside one bin (before the clamp to the track's end): the reference's single-bin assignment
 };
 
 __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, DenseWin &w)
@@ -249,6 +252,7 @@ __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, D
 	if (!mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we))
 		return false;
 	w.ch = q.table + chrom;
+	w.ws = ws;
 	int64_t eb;
 	if ((uint64_t)we <= 0xffffffffull - q.bin_size && q.bin_magic) { // 0 <= ws < we: both fit the magic-number division
 		w.sbin = (int64_t)__umul64hi((uint64_t)ws, q.bin_magic);             // src/GenomeTrackFixedBin.cpp:675
@@ -258,6 +262,7 @@ __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, D
 		eb = mg_ceildiv(we, q.bin_size);
 	}
 	int64_t nb = w.ch->nbins;
+	w.one_bin = eb == w.sbin + 1;
 	w.ebin = eb < nb ? eb : nb;                           // read_bins_bulk clamp :1036-1041
 	return true;
 }
@@ -638,6 +643,131 @@ __global__ void __launch_bounds__(MG_SW_WARPS * 32) k_dense_sweep(const DenseQue
 			if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
 			for (int k = 0; k < q.nq; ++k)
 				mg_st_stream(q.q_out[k] + i, qv[k]);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_dense_ext: one warp per row; the order-dependent functions of the reference's generic path
+// (src/GenomeTrackFixedBin.cpp:881-939): first / last (+ position), min.pos / max.pos, lse.
+//   first / last  : ballots from either end of the window stop at the first group of 32 bins that holds a value;
+//   min / max pos : every lane keeps (value, bin) of its stride with the reference's strict comparisons, lanes merge on
+//                   (value, then smaller bin): the first bin holding the extremum, as :886-905 leave it;
+//   lse           : M + log(sum exp(v - M)) in double with M the window's maximum, rounded to float -- the value the
+//                   reference's reducer path produces (RunningLogSumExp::value, src/utils/RunningLogSumExp.h:32-45,175-178);
+//                   its generic path accumulates pairwise in float (src/GenomeTrack1D.h:20-42) and agrees to ~1e-6.
+// Position of bin b: max(b * bin_size, window start) (:883-884), as a double.
+#define MG_EXT_WARPS 8
+template <bool SCAN>
+__global__ void __launch_bounds__(MG_EXT_WARPS * 32) k_dense_ext(const DenseQuery q)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t nwarps_total = (int64_t)gridDim.x * MG_EXT_WARPS;
+	for (int64_t i = (int64_t)blockIdx.x * MG_EXT_WARPS + warp; i < q.count; i += nwarps_total) {
+		DenseWin w;
+		const bool ok = mg_dense_win(q, q.first + i, w);
+		const float *vals = ok ? w.ch->vals : nullptr;
+		const int64_t sbin = ok ? w.sbin : 0, ebin = ok ? w.ebin : 0;
+		int64_t fb = -1, lb = -1, mnb = -1, mxb = -1;
+		float fv = mg_nanf(), lv = mg_nanf();
+		double lse = mg_nan();
+		if (q.out[MG_FIRST] || q.out[MG_FIRST_POS]) {
+			for (int64_t b0 = sbin; b0 < ebin; b0 += 32) {
+				const int64_t b = b0 + lane;
+				const float v = b < ebin ? __ldg(vals + b) : mg_nanf();
+				const unsigned m = __ballot_sync(0xffffffffu, v == v);
+				if (m) {
+					const int src = __ffs(m) - 1;
+					fv = __shfl_sync(0xffffffffu, v, src);
+					fb = b0 + src;
+					break;
+				}
+			}
+		}
+		if (q.out[MG_LAST] || q.out[MG_LAST_POS]) {
+			for (int64_t b1 = ebin; b1 > sbin; b1 -= 32) {
+				const int64_t b = b1 - 32 + lane;
+				const float v = b >= sbin ? __ldg(vals + b) : mg_nanf();
+				const unsigned m = __ballot_sync(0xffffffffu, v == v);
+				if (m) {
+					const int src = 31 - __clz(m);
+					lv = __shfl_sync(0xffffffffu, v, src);
+					lb = b1 - 32 + src;
+					break;
+				}
+			}
+		}
+		if (SCAN) {
+			float mnv = __int_as_float(0x7f800000), mxv = __int_as_float(0xff800000);
+			for (int64_t b = sbin + lane; b < ebin; b += 32) {
+				const float v = __ldg(vals + b);
+				if (v == v) {
+					if (v < mnv || mnb < 0) { // bins ascend within a lane: strict comparisons keep the first occurrence
+						mnv = v;
+						mnb = b;
+					}
+					if (v > mxv || mxb < 0) {
+						mxv = v;
+						mxb = b;
+					}
+				}
+			}
+#pragma unroll
+			for (int m = 16; m > 0; m >>= 1) {
+				const float ov = __shfl_xor_sync(0xffffffffu, mnv, m), oV = __shfl_xor_sync(0xffffffffu, mxv, m);
+				const int64_t ob = __shfl_xor_sync(0xffffffffu, mnb, m), oB = __shfl_xor_sync(0xffffffffu, mxb, m);
+				if (ob >= 0 && (mnb < 0 || ov < mnv || (ov == mnv && ob < mnb))) {
+					mnv = ov;
+					mnb = ob;
+				}
+				if (oB >= 0 && (mxb < 0 || oV > mxv || (oV == mxv && oB < mxb))) {
+					mxv = oV;
+					mxb = oB;
+				}
+			}
+			if (q.out[MG_LSE] && mxb >= 0) {
+				const double M = (double)mxv;
+				double s = 0;
+				for (int64_t b = sbin + lane; b < ebin; b += 32) {
+					const float v = __ldg(vals + b);
+					if (v == v)
+						s += exp((double)v - M);
+				}
+#pragma unroll
+				for (int m = 16; m > 0; m >>= 1)
+					s += __shfl_xor_sync(0xffffffffu, s, m);
+				lse = mg_f2d(M + log(s));
+			}
+		}
+		if (ok && w.one_bin && sbin < ebin) {
+			// assign_single_bin_value (src/GenomeTrackFixedBin.cpp:150-180): a window inside one bin reports the bin's position for
+			// every position function and the bin's value for lse / first / last, whatever the value (a NaN bin keeps its position)
+			fv = lv = __ldg(vals + sbin);
+			lse = (double)fv;
+			fb = lb = mnb = mxb = sbin;
+		}
+		if (lane == 0) {
+			const double bs = (double)q.bin_size, ws = ok ? (double)w.ws : 0.;
+#define MG_EXT_POS(F, BIN)                                                                                              \
+	if (q.out[F]) {                                                                                                     \
+		double p = mg_nan();                                                                                            \
+		if ((BIN) >= 0) {                                                                                               \
+			p = fmax((double)(BIN) * bs, ws);                                                                           \
+			if (q.pos_rel & (1u << (F)))                                                                                \
+				p -= ws;                                                                                                \
+		}                                                                                                               \
+		mg_st_stream(q.out[F] + i, p);                                                                                  \
+	}
+			if (q.out[MG_FIRST]) mg_st_stream(q.out[MG_FIRST] + i, (double)fv);
+			if (q.out[MG_LAST]) mg_st_stream(q.out[MG_LAST] + i, (double)lv);
+			MG_EXT_POS(MG_FIRST_POS, fb)
+			MG_EXT_POS(MG_LAST_POS, lb)
+			if (SCAN) {
+				MG_EXT_POS(MG_MIN_POS, mnb)
+				MG_EXT_POS(MG_MAX_POS, mxb)
+				if (q.out[MG_LSE]) mg_st_stream(q.out[MG_LSE] + i, lse);
+			}
+#undef MG_EXT_POS
 		}
 	}
 }

@@ -659,9 +659,19 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 			q.out[f] = d_out[k];
 			if (f == MG_MIN || f == MG_MAX || f == MG_STDDEV)
 				need_sweep = true;
+			if (f >= MG_FIRST_POS && f <= MG_MAX_POS && params && params[k] != 0.)
+				q.pos_rel |= 1u << f;
 		}
 	}
 	return 0;
+}
+
+static bool mg_any_out(double *const *out, int lo, int hi)
+{
+	for (int f = lo; f <= hi; ++f)
+		if (out[f])
+			return true;
+	return false;
 }
 
 static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cudaStream_t st)
@@ -670,6 +680,18 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		return 0;
 	const bool want_sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST] || q.out[MG_SIZE] || q.out[MG_EXISTS];
 	const bool want_mm = q.out[MG_MIN] || q.out[MG_MAX];
+	if (mg_any_out(q.out, MG_LSE, MG_MAX_POS)) { // the order-dependent functions: their own warp-per-row kernel
+		const int64_t blocks_needed = mg_div_up(q.count, MG_EXT_WARPS);
+		const int64_t cap = (int64_t)ctx->sm_count * 64;
+		const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
+		if (q.out[MG_LSE] || q.out[MG_MIN_POS] || q.out[MG_MAX_POS])
+			k_dense_ext<true><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
+		else
+			k_dense_ext<false><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
+		MG_LAUNCH_CHECK(ctx);
+		if (!want_sum && !want_mm && !q.out[MG_STDDEV] && q.nq == 0)
+			return 0;
+	}
 	if (!need_sweep) {
 		k_dense_prefix<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
 	} else if (!ctx->force_sweep) {
@@ -1167,12 +1189,14 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 		} else {
 			MG_REQUIRE(ctx, !q.out[f], "function %d requested twice in one call", f);
 			q.out[f] = d_out[k];
+			if (f >= MG_FIRST_POS && f <= MG_MAX_POS && params && params[k] != 0.)
+				q.pos_rel |= 1u << f;
 		}
 	}
 	if (!count)
 		return 0;
 	MG_REQUIRE(ctx, count < (1ll << 31) * (MG_SP_THREADS * MG_SF_ROWS), "row range too long for one launch");
-	if (!q.out[MG_STDDEV] && q.nq == 0 && !ctx->force_sweep) {
+	if (!q.out[MG_STDDEV] && q.nq == 0 && !ctx->force_sweep && !mg_any_out(q.out, MG_LSE, MG_MAX_POS)) {
 		const unsigned grid = (unsigned)mg_div_up(count, MG_SP_THREADS * MG_SF_ROWS);
 		cudaStream_t st = mg_stream(stream);
 		switch (nfuncs == 1 ? funcs[0] : -1) { // one requested column: the kernel specialised on it

@@ -43,10 +43,25 @@ struct SparseQuery {
 	const SparseChrom *table;
 	const int64_t *chrom_sizes;
 	double *out[MG_NUM_FUNCS];
+	uint32_t pos_rel; // bit f set: position function f is reported relative to the window start
 	int nq;
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
 };
+
+// src/GenomeTrack1D.h:20-30: the pairwise float accumulation the sparse reader's lse runs in record order
+__device__ __forceinline__ void mg_lse_accumulate(float &l1, float l2)
+{
+	if (l1 > l2) {
+		if (!isinf(l2))
+			l1 += logf(1.0f + expf(l2 - l1));
+	} else {
+		if (isinf(l1))
+			l1 = l2;
+		else
+			l1 = l2 + logf(1.0f + expf(l1 - l2));
+	}
+}
 
 // distance between query [qs,qe) and record [rs,re): src/GInterval.cpp:33-44 with strand 0
 __device__ __forceinline__ int64_t mg_dist(int64_t qs, int64_t qe, int64_t rs, int64_t re)
@@ -236,6 +251,8 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 #pragma unroll
 	for (int k = 0; k < MG_MAX_Q; ++k)
 		qv[k] = mg_nan();
+	// the order-dependent functions (src/GenomeTrackSparse.h:166-224): positions are record starts
+	double lse = mg_nan(), v_first = mg_nan(), v_last = mg_nan(), first_pos = mg_nan(), last_pos = mg_nan(), min_pos = mg_nan(), max_pos = mg_nan();
 	if (ok) {
 		size = 0;
 		exists = 0;
@@ -259,12 +276,28 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 					long long n = 0;
 					double S = 0, mean = 0, m2 = 0;
 					float fmin = 3.402823466e+38f, fmax = -3.402823466e+38f;
+					float flse = __int_as_float(0xff800000);
 					int64_t r = first;
 					for (; r < ch.n && ch.start[r] < we; ++r) {
 						const float v = ch.val[r];
 						if (isnan(v))
 							continue;
 						S += (double)v;
+						if (FULL) {
+							const double pos = (double)ch.start[r];
+							if (v < fmin || n == 0)
+								min_pos = pos; // later ties start further right: the first occurrence stays (:174-180)
+							if (v > fmax)
+								max_pos = pos;
+							if (n == 0) {
+								v_first = (double)v;
+								first_pos = pos;
+							}
+							v_last = (double)v;
+							last_pos = pos;
+							if (q.out[MG_LSE])
+								mg_lse_accumulate(flse, v);
+						}
 						if (v < fmin) fmin = v;
 						if (v > fmax) fmax = v;
 						++n;
@@ -274,6 +307,8 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 							m2 += d * ((double)v - mean);
 						}
 					}
+					if (FULL && n > 0)
+						lse = (double)flse;
 					size = (double)n;
 					if (n > 0) {
 						exists = 1;
@@ -313,6 +348,16 @@ __device__ __forceinline__ void mg_sparse_row(const SparseQuery &q, const SpLoca
 	if (q.out[MG_EXISTS]) mg_st_stream(q.out[MG_EXISTS] + i, exists);
 	for (int k = 0; FULL && k < q.nq; ++k)
 		mg_st_stream(q.q_out[k] + i, qv[k]);
+	if (FULL) {
+		const double base = (double)ws;
+		if (q.out[MG_LSE]) mg_st_stream(q.out[MG_LSE] + i, lse);
+		if (q.out[MG_FIRST]) mg_st_stream(q.out[MG_FIRST] + i, v_first);
+		if (q.out[MG_LAST]) mg_st_stream(q.out[MG_LAST] + i, v_last);
+		if (q.out[MG_FIRST_POS]) mg_st_stream(q.out[MG_FIRST_POS] + i, (q.pos_rel >> MG_FIRST_POS) & 1 ? first_pos - base : first_pos);
+		if (q.out[MG_LAST_POS]) mg_st_stream(q.out[MG_LAST_POS] + i, (q.pos_rel >> MG_LAST_POS) & 1 ? last_pos - base : last_pos);
+		if (q.out[MG_MIN_POS]) mg_st_stream(q.out[MG_MIN_POS] + i, (q.pos_rel >> MG_MIN_POS) & 1 ? min_pos - base : min_pos);
+		if (q.out[MG_MAX_POS]) mg_st_stream(q.out[MG_MAX_POS] + i, (q.pos_rel >> MG_MAX_POS) & 1 ? max_pos - base : max_pos);
+	}
 }
 
 template <typename Q>

@@ -271,6 +271,149 @@ void orc_sparse_window(const int64_t *rs, const int64_t *re, const float *rv, in
 }
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* The order-dependent functions: lse, first / last (+ position), min.pos / max.pos.                       */
+/* Output columns of both functions below (ORC_EXT_COLS doubles per row):                                  */
+/*   0 lse  1 first  2 last  3 first.pos  4 last.pos  5 min.pos  6 max.pos   (positions absolute)          */
+#define ORC_EXT_COLS 7
+
+/* src/GenomeTrack1D.h:20-30 (the float overload the track readers use) */
+static void orc_lse_accumulate(float *l1, float l2)
+{
+	if (*l1 > l2) {
+		if (!isinf(l2))
+			*l1 += logf(1.0f + expf(l2 - *l1));
+	} else {
+		if (isinf(*l1))
+			*l1 = l2;
+		else
+			*l1 = l2 + logf(1.0f + expf(*l1 - l2));
+	}
+}
+
+/* Dense, generic path src/GenomeTrackFixedBin.cpp:881-939: position of a bin = max(bin start, window start) (:883-884);
+ * min.pos keeps the first bin of the minimum (:886-895), max.pos the first bin of the maximum (:897-903).
+ * lse: lse_mode 0 = the reducer path's value, (float)(M + log(sum exp(v - M))) as RunningLogSumExp::push / value build it
+ * for a fresh window (src/utils/RunningLogSumExp.h:82-96,175-178; src/GenomeTrackFixedBin.cpp:379-392) -- what a vtrack with
+ * func = "lse" alone on its track runs; lse_mode 1 = the generic path's pairwise float accumulation (:918-919). */
+void orc_dense_window_ext(const float *bins, int64_t nbins, uint32_t bin_size, int64_t chromsize, int64_t n, const int64_t *start,
+						  const int64_t *end, int64_t sshift, int64_t eshift, int lse_mode, double *out /* n x ORC_EXT_COLS */)
+{
+	for (int64_t i = 0; i < n; ++i) {
+		double *o = out + i * ORC_EXT_COLS;
+		for (int k = 0; k < ORC_EXT_COLS; ++k)
+			o[k] = ORC_NAN;
+		int64_t ws, we;
+		if (!orc_window(start[i], end[i], sshift, eshift, chromsize, &ws, &we))
+			continue;
+		int64_t sbin = (int64_t)(ws / bin_size);
+		int64_t ebin = (int64_t)ceil(we / (double)bin_size);
+		if (ebin == sbin + 1) {
+			/* a window inside one bin: assign_single_bin_value (:150-180, called at :703-708) sets every position to the
+			 * bin's overlap start and lse / first / last to the bin's value WHATEVER that value is (a NaN bin still reports
+			 * its position); past the end of the track everything stays NaN (assign_single_bin_missing) */
+			if (sbin < nbins) {
+				float v = bins[sbin];
+				double bin_start = (double)(sbin * (int64_t)bin_size);
+				double pos = bin_start > (double)ws ? bin_start : (double)ws;
+				o[0] = o[1] = o[2] = isinf(v) ? ORC_NAN : (double)v;
+				o[3] = o[4] = o[5] = o[6] = pos;
+			}
+			continue;
+		}
+		if (ebin > nbins)
+			ebin = nbins;
+		uint64_t num_vs = 0;
+		float fmin = 3.402823466e+38F, fmax = -3.402823466e+38F, flse = -INFINITY;
+		double M = -INFINITY, sum_scaled = 0;
+		for (int64_t b = sbin; b < ebin; ++b) {
+			float v = bins[b];
+			if (isinf(v) || isnan(v))
+				continue;
+			double bin_start = (double)(b * (int64_t)bin_size);
+			double pos = bin_start > (double)ws ? bin_start : (double)ws;
+			if (v < fmin) {
+				fmin = v;
+				o[5] = pos;
+			} else if (v == fmin && (isnan(o[5]) || pos < o[5]))
+				o[5] = pos;
+			if (v > fmax) {
+				fmax = v;
+				o[6] = pos;
+			}
+			orc_lse_accumulate(&flse, v);
+			if (v > M) { /* RunningLogSumExp::push */
+				if (isfinite(M))
+					sum_scaled *= exp(M - (double)v);
+				M = v;
+			}
+			sum_scaled += exp((double)v - M);
+			if (num_vs == 0) {
+				o[1] = v;
+				o[3] = pos;
+			}
+			o[2] = v;
+			o[4] = pos;
+			++num_vs;
+		}
+		if (num_vs > 0)
+			o[0] = lse_mode ? (double)flse : (double)(float)(M + log(sum_scaled));
+		else
+			o[5] = ORC_NAN;
+	}
+}
+
+/* Sparse, calc_vals src/GenomeTrackSparse.h:166-224: positions are the records' starts; lse accumulates in float, record order. */
+void orc_sparse_window_ext(const int64_t *rs, const int64_t *re, const float *rv, int64_t nrec, int64_t chromsize, int64_t n,
+						   const int64_t *start, const int64_t *end, int64_t sshift, int64_t eshift, double *out /* n x ORC_EXT_COLS */)
+{
+	for (int64_t i = 0; i < n; ++i) {
+		double *o = out + i * ORC_EXT_COLS;
+		for (int k = 0; k < ORC_EXT_COLS; ++k)
+			o[k] = ORC_NAN;
+		int64_t ws, we;
+		if (!orc_window(start[i], end[i], sshift, eshift, chromsize, &ws, &we) || nrec == 0 || rs[0] >= we || re[nrec - 1] <= ws)
+			continue;
+		int64_t lo = 0, hi = nrec;
+		while (lo < hi) {
+			int64_t mid = lo + (hi - lo) / 2;
+			if (re[mid] > ws)
+				hi = mid;
+			else
+				lo = mid + 1;
+		}
+		uint64_t num_vs = 0;
+		float fmin = 3.402823466e+38F, fmax = -3.402823466e+38F, flse = -INFINITY;
+		for (int64_t r = lo; r < nrec && rs[r] < we; ++r) {
+			float v = rv[r];
+			if (isnan(v) || isinf(v))
+				continue;
+			double pos = (double)rs[r];
+			if (v < fmin) {
+				fmin = v;
+				o[5] = pos;
+			} else if (v == fmin && (isnan(o[5]) || pos < o[5]))
+				o[5] = pos;
+			if (v > fmax) {
+				fmax = v;
+				o[6] = pos;
+			}
+			orc_lse_accumulate(&flse, v);
+			if (num_vs == 0) {
+				o[1] = v;
+				o[3] = pos;
+			}
+			o[2] = v;
+			o[4] = pos;
+			++num_vs;
+		}
+		if (num_vs > 0)
+			o[0] = (double)flse;
+		else
+			o[5] = ORC_NAN;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* Intervals: sort by (chromid,start) and unify overlaps. src/GIntervals.cpp:59-74.                        */
 typedef struct { int32_t chrom; int64_t start, end, idx; } orc_iv;
 

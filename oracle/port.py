@@ -79,6 +79,30 @@ def sparse_window(rs, re, rv, chromsize, start, end, sshift=0, eshift=0, percent
     return {f: outs[f] for f in funcs}
 
 
+EXT_COLS = ("lse", "first", "last", "first.pos", "last.pos", "min.pos", "max.pos")
+
+
+def dense_window_ext(bins, bin_size, chromsize, start, end, sshift=0, eshift=0, lse_mode=0):
+    """Dict name -> float64[n] of the order-dependent functions (absolute positions). lse_mode 0: the reducer path's value
+    (func = "lse" alone), 1: the generic path's pairwise float accumulation."""
+    bins = np.ascontiguousarray(bins, dtype=np.float32)
+    start, end = _i64(start), _i64(end)
+    out = np.empty((len(start), len(EXT_COLS)), dtype=np.float64)
+    lib().orc_dense_window_ext(_p(bins), c_i64(len(bins)), ctypes.c_uint32(bin_size), c_i64(chromsize), c_i64(len(start)), _p(start), _p(end),
+                               c_i64(sshift), c_i64(eshift), ctypes.c_int(lse_mode), _p(out))
+    return {f: out[:, k].copy() for k, f in enumerate(EXT_COLS)}
+
+
+def sparse_window_ext(rs, re, rv, chromsize, start, end, sshift=0, eshift=0):
+    rs, re = _i64(rs), _i64(re)
+    rv = np.ascontiguousarray(rv, dtype=np.float32)
+    start, end = _i64(start), _i64(end)
+    out = np.empty((len(start), len(EXT_COLS)), dtype=np.float64)
+    lib().orc_sparse_window_ext(_p(rs), _p(re), _p(rv), c_i64(len(rs)), c_i64(chromsize), c_i64(len(start)), _p(start), _p(end),
+                                c_i64(sshift), c_i64(eshift), _p(out))
+    return {f: out[:, k].copy() for k, f in enumerate(EXT_COLS)}
+
+
 def percentile(vals, p):
     v = np.array(vals, dtype=np.float32)
     return float(lib().orc_percentile(_p(v), c_i64(len(v)), ctypes.c_double(p)))

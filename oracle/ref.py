@@ -80,6 +80,32 @@ def sparse_eval(chrom_file, chromid, start, end, funcs=("avg",), percentile=0.5)
     return _eval(lib().ref_sparse_eval, chrom_file, chromid, start, end, funcs, percentile)
 
 
+EXT_COLS = ("lse", "first", "last", "first.pos", "last.pos", "min.pos", "max.pos")
+# GenomeTrack1D::Functions (src/GenomeTrack1D.h:47)
+EXT_BIT = {"lse": 6, "max.pos": 7, "min.pos": 8, "first": 13, "first.pos": 14, "last": 15, "last.pos": 16}
+
+
+def _eval_ext(fn, chrom_file, chromid, start, end, funcs, extra_funcs=()):
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    mask = _mask(extra_funcs)
+    for f in funcs:
+        mask |= 1 << EXT_BIT[f]
+    out = np.empty((len(start), len(EXT_COLS)), dtype=np.float64)
+    _check(fn(chrom_file.encode(), ctypes.c_int(chromid), ctypes.c_uint32(mask), c_i64(len(start)), _p(start), _p(end), _p(out)))
+    return {f: out[:, EXT_COLS.index(f)].copy() for f in funcs}
+
+
+def dense_eval_ext(chrom_file, chromid, start, end, funcs=EXT_COLS, extra_funcs=()):
+    """lse / first / last / positions from ONE GenomeTrackFixedBin fed in row order. funcs = ("lse",) alone runs the reference's
+    reducer path, anything else (or extra_funcs such as ("avg", "max")) its generic path."""
+    return _eval_ext(lib().ref_dense_eval_ext, chrom_file, chromid, start, end, funcs, extra_funcs)
+
+
+def sparse_eval_ext(chrom_file, chromid, start, end, funcs=EXT_COLS, extra_funcs=()):
+    return _eval_ext(lib().ref_sparse_eval_ext, chrom_file, chromid, start, end, funcs, extra_funcs)
+
+
 def gquantiles(vals, percentiles):
     v = np.ascontiguousarray(vals, dtype=np.float64)
     p = np.ascontiguousarray(percentiles, dtype=np.float64)

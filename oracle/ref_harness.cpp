@@ -92,6 +92,51 @@ extern "C" int ref_dense_eval(const char *chrom_file, int chromid, uint32_t func
 	REF_CATCH
 }
 
+// The order-dependent functions through the reference's own readers. out: n x 7 doubles in the order of oracle.c's
+// orc_*_window_ext: lse, first, last, first.pos, last.pos, min.pos, max.pos (absolute). func_mask picks what is registered:
+// the reducer path (LSE alone) and the generic path (LSE next to other functions) compute lse differently.
+template <class T>
+static void eval_ext(T &t, int chromid, uint32_t func_mask, int64_t n, const int64_t *start, const int64_t *end, double *out)
+{
+	const double nan = std::numeric_limits<double>::quiet_NaN();
+	for (int64_t i = 0; i < n; ++i) {
+		GInterval iv(chromid, start[i], end[i], 0);
+		t.read_interval(iv);
+		double *o = out + i * 7;
+		o[0] = (func_mask & (1u << GenomeTrack1D::LSE)) ? t.last_lse() : nan;
+		o[1] = (func_mask & (1u << GenomeTrack1D::FIRST)) ? t.last_first() : nan;
+		o[2] = (func_mask & (1u << GenomeTrack1D::LAST)) ? t.last_last() : nan;
+		o[3] = (func_mask & (1u << GenomeTrack1D::FIRST_POS)) ? t.last_first_pos() : nan;
+		o[4] = (func_mask & (1u << GenomeTrack1D::LAST_POS)) ? t.last_last_pos() : nan;
+		o[5] = (func_mask & (1u << GenomeTrack1D::MIN_POS)) ? t.last_min_pos() : nan;
+		o[6] = (func_mask & (1u << GenomeTrack1D::MAX_POS)) ? t.last_max_pos() : nan;
+	}
+}
+
+extern "C" int ref_dense_eval_ext(const char *chrom_file, int chromid, uint32_t func_mask, int64_t n, const int64_t *start, const int64_t *end,
+								  double *out)
+{
+	REF_TRY
+	GenomeTrackFixedBin t;
+	t.init_read(chrom_file, chromid);
+	register_funcs(t, func_mask, 0, 0);
+	eval_ext(t, chromid, func_mask, n, start, end, out);
+	return 0;
+	REF_CATCH
+}
+
+extern "C" int ref_sparse_eval_ext(const char *chrom_file, int chromid, uint32_t func_mask, int64_t n, const int64_t *start, const int64_t *end,
+								   double *out)
+{
+	REF_TRY
+	GenomeTrackSparse t;
+	t.init_read(chrom_file, chromid);
+	register_funcs(t, func_mask, 0, 0);
+	eval_ext(t, chromid, func_mask, n, start, end, out);
+	return 0;
+	REF_CATCH
+}
+
 extern "C" int ref_dense_info(const char *chrom_file, int chromid, uint32_t *bin_size, int64_t *num_samples)
 {
 	REF_TRY

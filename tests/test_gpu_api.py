@@ -110,6 +110,35 @@ def test_vtracks_on_dense_with_shifts(db):
         db.gvtrack_create("q", "no_such_track", "avg")
 
 
+def test_vtrack_order_dependent_functions(db):
+    """gvtrack.create with lse / first / last / *.pos.abs / *.pos.relative (R/vtrack.R; src/TrackVarProcessor.cpp:113-173)."""
+    iv = db.gintervals([1, 2, "X"], [0, 1000, 150000], [30000, 9000, 200000])
+    for func, col, rel in (("lse", "lse", False), ("first", "first", False), ("last", "last", False), ("max.pos.abs", "max.pos", False),
+                           ("max.pos.relative", "max.pos", True), ("min.pos.relative", "min.pos", True), ("first.pos.abs", "first.pos", False),
+                           ("last.pos.relative", "last.pos", True)):
+        for track in ("dense_track", "sparse_track"):
+            db.gvtrack_create("v", track, func)
+            db.gvtrack_iterator("v", sshift=-130, eshift=220)
+            r = db.gextract("v", intervals=iv, iterator=170)
+            for cid, (c, size) in enumerate(CHROMS):
+                m = r["chrom"] == c
+                s, e = r["start"][m], r["end"][m]
+                if track == "dense_track":
+                    bs, bins = read_dense("dense_track", c)
+                    exp = port.dense_window_ext(bins, bs, size, s, e, -130, 220, 0)[col]
+                else:
+                    exp = port.sparse_window_ext(*read_sparse("sparse_track", c), size, s, e, -130, 220)[col]
+                if rel:
+                    exp = exp - np.maximum(s - 130, 0)
+                if func == "lse":
+                    np.testing.assert_allclose(r["v"][m], exp, rtol=1e-6, atol=1e-6, equal_nan=True)
+                else:
+                    assert_same(r["v"][m], exp, f"{track} {func} {c}")
+    db.gvtrack_rm("v")
+    with pytest.raises(api.MishaError):
+        db.gvtrack_create("v", "dense_track", "sample")  # draws from R's RNG: not offered
+
+
 def test_sparse_track_implicit_iterator_and_nearest(db):
     r = db.gextract("sparse_track", intervals=db.gintervals(1, 0, 10000))  # iterator = the track's own records
     rs, re, rv = read_sparse("sparse_track", "chr1")

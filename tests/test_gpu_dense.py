@@ -269,3 +269,74 @@ def test_staged_block_records_any_row_order():
         check(np.zeros(300, np.int64), s, s + 1000, -200, 200, "one-record")
     finally:
         ctx2.close()
+
+
+EXT = ("lse", "first", "last", "first.pos", "last.pos", "min.pos", "max.pos")
+
+
+def test_order_dependent_functions_golden_and_oracle(gpu_ctx, dense_testdb):
+    """lse / first / last / first.pos / last.pos / min.pos / max.pos (k_dense_ext) against the reference's compiled reader
+    (ref_vectors_ext.npz) and the oracle: values and positions bit for bit -- the single-bin assignment quirk, ties of the
+    extremum (first bin wins), NaN runs, windows clamped by the chromosome end; lse equals the reference's reducer path
+    (double max-trick) to float rounding and its generic path (pairwise float) within 1e-6."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_vectors_ext.npz"))
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        got = dense_testdb.window(rows, list(EXT))
+        for k, name in enumerate(EXT):
+            if name == "lse":
+                np.testing.assert_allclose(got[k], g[f"dense_{c}_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
+                np.testing.assert_allclose(got[k], g[f"dense_{c}_lse_reducer"], rtol=2e-7, atol=0, equal_nan=True)
+                exact = (got[k] == g[f"dense_{c}_lse_reducer"]) | np.isnan(got[k])
+                assert exact.mean() > 0.999, exact.mean()
+            else:
+                assert_same(got[k], g[f"dense_{c}_{name}"], f"{c} {name}")
+        # shifted windows, relative positions, mixed with the index-structure functions in one call
+        bs, bins = read_dense("dense_track", c)
+        rng = np.random.default_rng(31 + cid)
+        s = np.sort(rng.integers(0, size - 1, 3000))
+        e = np.minimum(s + rng.choice([1, 10, 50, 120, 3000], 3000), size)
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        for sshift, eshift in ((0, 0), (-700, 900), (40, -10), (-10**7, 10**7)):
+            funcs = ["max", ("first.pos", 1), ("last.pos", 1), ("min.pos", 1), ("max.pos", 1), "first", "last", "avg"]
+            got = dense_testdb.window(rows, funcs, sshift, eshift) + dense_testdb.window(rows, ["min.pos"], sshift, eshift)
+            exp = port.dense_window_ext(bins, bs, size, s, e, sshift, eshift, 0)
+            base = port.dense_window(bins, bs, size, s, e, sshift, eshift, 0.5, ("max", "avg"))
+            ws = np.maximum(s + sshift, 0).astype(np.float64)
+            assert_same(got[0], base["max"], f"{c} max next to ext {sshift}")
+            assert_close(got[7], base["avg"], RTOL, f"{c} avg next to ext")
+            for k, name in ((1, "first.pos"), (2, "last.pos"), (3, "min.pos"), (4, "max.pos")):
+                assert_same(got[k], exp[name] - ws, f"{c} {name} relative {sshift},{eshift}")
+            assert_same(got[5], exp["first"], f"{c} first {sshift}")
+            assert_same(got[6], exp["last"], f"{c} last {sshift}")
+            assert_same(got[8], exp["min.pos"], f"{c} min.pos abs {sshift}")
+
+
+def test_order_dependent_functions_synthetic_ties_and_nans():
+    from misha_b200 import gpu
+    nb = 5000
+    size = nb * 10 - 4
+    ctx2 = gpu.Context([size])
+    try:
+        rng = np.random.default_rng(8)
+        bins = np.round(rng.normal(0, 2, nb)).astype(np.float32)  # few distinct values: extremum ties everywhere
+        bins[rng.integers(0, nb, 800)] = np.nan
+        bins[1000:1400] = np.nan
+        bins[3000] = np.inf
+        t = gpu.DenseTrack(ctx2, 10)
+        t.stage(0, bins)
+        s = rng.integers(0, size - 1, 8000)
+        e = np.minimum(s + rng.choice([1, 9, 10, 11, 100, 333, 2500, 6000], 8000), size)
+        rows = ctx2.rows_upload(np.zeros(len(s), np.int32), s, e)
+        got = t.window(rows, list(EXT), sshift=-15, eshift=25)
+        exp = port.dense_window_ext(bins, 10, size, s, e, -15, 25, 0)
+        for k, name in enumerate(EXT):
+            if name == "lse":
+                np.testing.assert_allclose(got[k], exp[name], rtol=2e-7, atol=0, equal_nan=True)
+            else:
+                assert_same(got[k], exp[name], name)
+    finally:
+        ctx2.close()

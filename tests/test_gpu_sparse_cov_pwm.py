@@ -321,3 +321,34 @@ def test_pwm_float_and_strict_transcendentals_agree(gpu_ctx, seq_testdb, golden)
                 assert_same(a, b, "single-strand max has no transcendental")
             else:
                 assert_close(a, b, RTOL, f"float vs strict bid={bid} {mode}")
+
+
+def test_sparse_order_dependent_functions(gpu_ctx, sparse_testdb):
+    """lse / first / last / positions on a sparse track (record order, positions = record starts) against the reference's
+    compiled reader (ref_vectors_ext.npz) and the oracle with shifts; lse accumulates pairwise in float in record order
+    like the reference, so it differs only by the last bits of expf / logf."""
+    import os
+    from conftest import GOLDEN
+    ext = ("lse", "first", "last", "first.pos", "last.pos", "min.pos", "max.pos")
+    g = np.load(os.path.join(GOLDEN, "ref_vectors_ext.npz"))
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        got = sparse_testdb.window(rows, list(ext))
+        for k, name in enumerate(ext):
+            if name == "lse":
+                np.testing.assert_allclose(got[k], g[f"sparse_{c}_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
+            else:
+                assert_same(got[k], g[f"sparse_{c}_{name}"], f"{c} {name}")
+        rs, re, rv = read_sparse("sparse_track", c)
+        for sshift, eshift in ((-2500, 2500), (300, 800)):
+            got = sparse_testdb.window(rows, ["avg", ("first.pos", 1), ("max.pos", 1), "last", ("min.pos", 0)], sshift, eshift)
+            exp = port.sparse_window_ext(rs, re, rv, size, s, e, sshift, eshift)
+            avg = port.sparse_window(rs, re, rv, size, s, e, sshift, eshift, 0.5, ("avg",))["avg"]
+            ws = np.maximum(s + sshift, 0).astype(np.float64)
+            ok = (s + sshift < size) & (np.minimum(e + eshift, size) > np.maximum(s + sshift, 0))
+            assert_same(got[0], avg, f"{c} avg next to ext")
+            assert_same(got[1][ok], (exp["first.pos"] - ws)[ok], f"{c} first.pos relative")
+            assert_same(got[2][ok], (exp["max.pos"] - ws)[ok], f"{c} max.pos relative")
+            assert_same(got[3], exp["last"], f"{c} last")
+            assert_same(got[4], exp["min.pos"], f"{c} min.pos")

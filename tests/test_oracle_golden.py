@@ -180,3 +180,50 @@ def test_gquantiles_oracle_vs_reference_vectors():
     v = rng.normal(size=7777)
     v[::13] = np.nan
     assert np.array_equal(port.gquantiles(v, [0.1, 0.5, 0.93])[0], ref.gquantiles(v, [0.1, 0.5, 0.93]))
+
+
+def test_order_dependent_functions_match_reference_golden():
+    """lse, first / last and the four position functions of oracle.c against the reference's own compiled readers
+    (tests/golden/ref_vectors_ext.npz, make_fixtures_ext.py): bit for bit, the single-bin assignment quirk included. The
+    reference's generic-path lse may reuse its sliding state when two random rows happen to line up: 1e-6 there."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_vectors_ext.npz"))
+    for c, size in CHROMS:
+        bs, bins = read_dense("dense_track", c)
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        out = port.dense_window_ext(bins, bs, size, s, e, 0, 0, 1)
+        for k in port.EXT_COLS:
+            if k == "lse":
+                np.testing.assert_allclose(out[k], g[f"dense_{c}_{k}"], rtol=1e-6, atol=1e-6, equal_nan=True)
+                assert np.mean((out[k] == g[f"dense_{c}_{k}"]) | np.isnan(out[k])) > 0.99
+            else:
+                assert_same(out[k], g[f"dense_{c}_{k}"], f"dense {c} {k}")
+        assert_same(port.dense_window_ext(bins, bs, size, s, e, 0, 0, 0)["lse"], g[f"dense_{c}_lse_reducer"], f"dense {c} lse (reducer path)")
+        rs, re, rv = read_sparse("sparse_track", c)
+        out = port.sparse_window_ext(rs, re, rv, size, s, e)
+        for k in port.EXT_COLS:
+            assert_same(out[k], g[f"sparse_{c}_{k}"], f"sparse {c} {k}")
+
+
+@pytest.mark.skipif(not ref.available(), reason="compiled reference not present")
+def test_order_dependent_functions_match_reference_live():
+    rng = np.random.default_rng(77)
+    import os
+    from conftest import TESTDB
+    for cid, (c, size) in enumerate(CHROMS):
+        s = rng.integers(0, size - 1, 1500)
+        e = np.minimum(s + rng.choice([1, 30, 50, 77, 450, 2500, 30000], 1500), size)
+        bs, bins = read_dense("dense_track", c)
+        f = os.path.join(TESTDB, "tracks", "dense_track.track", c)
+        got = port.dense_window_ext(bins, bs, size, s, e, 0, 0, 0)
+        exp = ref.dense_eval_ext(f, cid, s, e, tuple(k for k in ref.EXT_COLS if k != "lse"), extra_funcs=("max",))
+        for k in exp:
+            assert_same(got[k], exp[k], f"dense {c} {k}")
+        assert_same(got["lse"], ref.dense_eval_ext(f, cid, s, e, ("lse",))["lse"], f"dense {c} lse")
+        rs, re, rv = read_sparse("sparse_track", c)
+        f = os.path.join(TESTDB, "tracks", "sparse_track.track", c)
+        got = port.sparse_window_ext(rs, re, rv, size, s, e)
+        exp = ref.sparse_eval_ext(f, cid, s, e)
+        for k in exp:
+            assert_same(got[k], exp[k], f"sparse {c} {k}")
