@@ -75,7 +75,7 @@ enum mg_func {
 };
 
 /* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */
-enum mg_pwm_mode { MG_PWM_TOTAL = 0 /* "pwm" */, MG_PWM_MAX = 1 /* "pwm.max" */, MG_PWM_COUNT = 3 /* "pwm.count" */ };
+enum mg_pwm_mode { MG_PWM_TOTAL = 0 /* "pwm" */, MG_PWM_MAX = 1 /* "pwm.max" */, MG_PWM_MAX_POS = 2 /* "pwm.max.pos" */, MG_PWM_COUNT = 3 /* "pwm.count" */ };
 
 /* ---- context ------------------------------------------------------------------------------------------- */
 int mg_abi_version(void);

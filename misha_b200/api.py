@@ -28,7 +28,7 @@ def _gpu_func(vt):
     if vt.func == "quantile":
         return ("quantile", float(vt.params))
     return POS_FUNCS.get(vt.func, vt.func)
-PWM_FUNCS = ("pwm", "pwm.max", "pwm.count")
+PWM_FUNCS = ("pwm", "pwm.max", "pwm.max.pos", "pwm.count")
 
 
 # What rerror()/verror() raise in R (src/rdbutils.cpp:708-733): host-side validation and C-ABI failures are one error type.
@@ -280,7 +280,7 @@ class MishaDB:
                 raise MishaError("Virtual track %s: function %s is not supported for interval sources by this build" % (vtrack, func))
         elif src is None:
             if func not in PWM_FUNCS:
-                raise MishaError("Virtual track %s: a NULL source requires a sequence function (pwm, pwm.max, pwm.count)" % vtrack)
+                raise MishaError("Virtual track %s: a NULL source requires a sequence function (pwm, pwm.max, pwm.max.pos, pwm.count)" % vtrack)
             p = dict(params) if isinstance(params, dict) else {"pssm": params}
             pssm = np.asarray(p.get("pssm"), dtype=np.float64)
             if pssm.ndim != 2 or pssm.shape[1] != 4:

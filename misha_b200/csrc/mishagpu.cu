@@ -1270,9 +1270,15 @@ extern "C" int mg_seq_stage(mg_ctx *ctx, mg_seq *s, int chromid, const char *h_a
 	MG_CUDA(ctx, cudaMalloc(&d_ascii, (size_t)(len > 0 ? len : 1)));
 	if (len) {
 		MG_CUDA(ctx, cudaMemcpy(d_ascii, h_ascii, (size_t)len, cudaMemcpyHostToDevice));
-		k_seq_pack<<<(unsigned)mg_div_up(nthreads, 256), 256>>>(d_ascii, len, codes, inval);
+		int *d_other = nullptr, h_other = 0;
+		MG_CUDA(ctx, cudaMalloc(&d_other, sizeof(int)));
+		MG_CUDA(ctx, cudaMemset(d_other, 0, sizeof(int)));
+		k_seq_pack<<<(unsigned)mg_div_up(nthreads, 256), 256>>>(d_ascii, len, codes, inval, d_other);
 		MG_LAUNCH_CHECK(ctx);
-		MG_CUDA(ctx, cudaDeviceSynchronize());
+		MG_CUDA(ctx, cudaMemcpy(&h_other, d_other, sizeof(int), cudaMemcpyDeviceToHost));
+		cudaFree(d_other);
+		if (h_other)
+			s->has_other = true;
 	}
 	cudaFree(d_ascii);
 	SeqChrom sc{codes, inval, len};
@@ -1320,7 +1326,9 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 {
 	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
 	MG_REQUIRE(ctx, L >= 1 && L <= MG_PWM_MAXL, "PSSM length %d not in [1, %d]", L, MG_PWM_MAXL);
-	MG_REQUIRE(ctx, mode == MG_PWM_TOTAL || mode == MG_PWM_MAX || mode == MG_PWM_COUNT, "unsupported pwm mode %d", mode);
+	MG_REQUIRE(ctx, mode == MG_PWM_TOTAL || mode == MG_PWM_MAX || mode == MG_PWM_COUNT || mode == MG_PWM_MAX_POS, "unsupported pwm mode %d", mode);
+	MG_REQUIRE(ctx, mode != MG_PWM_MAX_POS || !s->has_other,
+			   "pwm.max.pos: the staged sequence holds characters other than ACGT / N / *, which the packed form cannot tell from N");
 	MG_REQUIRE(ctx, strand == 1 || strand == -1, "strand must be 1 or -1");
 	if (!count)
 		return 0;
@@ -1330,6 +1338,10 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 		for (int c = 0; c < 4; ++c)
 			tab[j * 5 + c] = make_float2(h_logp[j * 4 + c], h_logp[(L - 1 - j) * 4 + (3 - c)]);
 		tab[j * 5 + 4] = make_float2(-INFINITY, -INFINITY);
+		if (mode == MG_PWM_MAX_POS) { // max_like_match scores N as the row's average log-probability (src/DnaPSSM.cpp:306-308, DnaPSSM.h:133-135)
+			const float *a = h_logp + j * 4, *b = h_logp + (L - 1 - j) * 4;
+			tab[j * 5 + 4] = make_float2((a[0] + a[1] + a[2] + a[3]) / 4, (b[0] + b[1] + b[2] + b[3]) / 4);
+		}
 	}
 	float2 *d_tab = nullptr;
 	MG_CUDA(ctx, cudaMallocAsync(&d_tab, sizeof(float2) * tab.size(), st));
@@ -1361,7 +1373,12 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 		else                                                                                                            \
 			k_pwm<B, M, false><<<grid, MG_PWM_WARPS * 32, 0, st>>>(q);                                                   \
 	} while (0)
-	if (bidirect) {
+	if (mode == MG_PWM_MAX_POS) { // no transcendental in this mode: one instantiation per strand handling
+		if (bidirect)
+			k_pwm<true, MG_PWM_MAX_POS, false><<<grid, MG_PWM_WARPS * 32, 0, st>>>(q);
+		else
+			k_pwm<false, MG_PWM_MAX_POS, false><<<grid, MG_PWM_WARPS * 32, 0, st>>>(q);
+	} else if (bidirect) {
 		if (mode == MG_PWM_TOTAL) MG_PWM_LAUNCH(true, MG_PWM_TOTAL);
 		else if (mode == MG_PWM_MAX) MG_PWM_LAUNCH(true, MG_PWM_MAX);
 		else MG_PWM_LAUNCH(true, MG_PWM_COUNT);

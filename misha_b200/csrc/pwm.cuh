@@ -21,6 +21,7 @@ struct SeqChrom {
 
 struct mg_seq {
 	int nchroms = 0;
+	bool has_other = false; // some staged character is neither ACGT nor N / * (see k_seq_pack)
 	std::vector<SeqChrom> h_table;
 	SeqChrom *d_table = nullptr;
 	std::vector<void *> allocs;
@@ -28,7 +29,9 @@ struct mg_seq {
 };
 
 // one thread per 32 bases
-__global__ void __launch_bounds__(256) k_seq_pack(const uint8_t *__restrict__ ascii, int64_t len, uint32_t *codes, uint32_t *inval)
+// *other is set when a character is neither ACGT nor neutral (N, n, *: DnaLookupTables::NEUTRAL_CHAR, src/DnaPSSM.h:21): pwm.max.pos
+// scores those two kinds of non-ACGT characters differently (src/DnaPSSM.cpp:306-316) and the packed form keeps one bit for both.
+__global__ void __launch_bounds__(256) k_seq_pack(const uint8_t *__restrict__ ascii, int64_t len, uint32_t *codes, uint32_t *inval, int *other)
 {
 	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t p0 = t * 32;
@@ -46,7 +49,11 @@ __global__ void __launch_bounds__(256) k_seq_pack(const uint8_t *__restrict__ as
 			else if (ch == 'C') code = 1;
 			else if (ch == 'G') code = 2;
 			else if (ch == 'T') code = 3;
-			else inv = 1;
+			else {
+				inv = 1;
+				if (ch != 'N' && ascii[p] != '*')
+					*other = 1;
+			}
 		}
 		if (k < 16)
 			c0 |= code << (2 * k);
@@ -60,6 +67,7 @@ __global__ void __launch_bounds__(256) k_seq_pack(const uint8_t *__restrict__ as
 }
 
 #define MG_PWM_MAXL 128
+#define MG_PWM_MAX_RANGE 1000000 // anchors 0..10^6 of the target are scored, the rest ignored (DnaPSSM::m_max_range)
 #define MG_PWM_WARPS 8
 #define MG_PWM_CHUNK 128 // anchors per warp pass (4 per lane)
 #define MG_PWM_TILE (MG_PWM_CHUNK + MG_PWM_MAXL)
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 		const int64_t chromsize = __ldg(q.chrom_sizes + chrom);
 		double result = mg_nan();
 		bool scan = false;
-		int64_t na = 0, xe = 0;
+		int64_t na = 0, xe = 0, a_base = 0;
 		if (mg_window(s, e, q.sshift, q.eshift, chromsize, ws, we)) {
 			xe = we;
 			if (q.extend && L > 1) { // src/GenomeSeqScorer.cpp:16-38: extend the END only
@@ -152,14 +160,25 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 			}
 			const int64_t tlen = xe - ws;
 			if (tlen < L) {
-				if (q.extend) // score_without_spatial over zero anchors (src/PWMScorer.cpp:313-338)
+				if (q.extend) { // score_without_spatial over zero anchors (src/PWMScorer.cpp:313-338)
 					result = MODE == MG_PWM_COUNT ? 0. : (double)NEG_INF;
+					if (MODE == MG_PWM_MAX_POS) {
+						// max_like_match returns the target's begin and leaves best_dir unset (src/DnaPSSM.cpp:288-291): index 0 through
+						// compute_position_result; with both strands the sign is the reference's uninitialised int -> NaN here
+						const float pos = rev ? __fadd_rn(__fsub_rn(__fsub_rn((float)tlen, 1.0f), (float)L), 1.0f) : 1.0f;
+						result = BID ? mg_nan() : (double)pos;
+					}
+				}
 			} else {
 				int64_t i_max = tlen - L;
 				const int64_t want = we - ws - 1;
 				if (want < i_max)
 					i_max = want;
+				if (i_max > MG_PWM_MAX_RANGE) // DnaPSSM's default scan range, m_max_range (src/DnaPSSM.h:186-187)
+					i_max = MG_PWM_MAX_RANGE;
 				na = i_max + 1;
+				// strand -1 scores the reverse complement: its first na anchors are the LAST na genomic ones
+				a_base = rev ? (tlen - L + 1) - na : 0;
 				scan = true;
 			}
 		}
@@ -168,11 +187,12 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 			double m_run = -INFINITY, s_run = 0; // online log-sum-exp per lane
 			float vmax = NEG_INF;
 			long long hits = 0;
+			int best_i = -1, best_dir = 1; // pwm.max.pos: index in the scored target (the reverse complement for strand -1)
 			for (int64_t a0 = 0; a0 < na; a0 += MG_PWM_CHUNK) {
 				// decode bases [ws + a0, ws + a0 + CHUNK + L + 2) into the tile: the packed words the chunk spans are fetched once
 				// (one load per lane), every base is then a shift and a mask in 32-bit arithmetic
 				const int need = MG_PWM_CHUNK + Lpad - 1 + 3;
-				const int64_t p0 = ws + a0, pw0 = p0 & ~31ll; // chunk start, and the 32-base boundary below it
+				const int64_t p0 = ws + a_base + a0, pw0 = p0 & ~31ll; // chunk start, and the 32-base boundary below it
 				const int off = (int)(p0 - pw0), span = off + need; // bases from pw0 on
 				__syncwarp();
 				for (int t = lane; t < ((span + 31) >> 5); t += 32) { // inval word t, codes words 2t and 2t + 1
@@ -232,6 +252,26 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 					if (a >= na)
 						continue;
 					float v;
+					if (MODE == MG_PWM_MAX_POS) {
+						// DnaPSSM::max_like_match with combine_strands = false (src/DnaPSSM.cpp:285-365): the better strand of the anchor
+						// (the reverse one only when strictly better), the first strictly greater anchor in target order wins
+						const float l = rev ? r[u] : f[u], rl = rev ? f[u] : r[u];
+						int d = 1;
+						v = l;
+						if (BID && rl > l) {
+							v = rl;
+							d = -1;
+						}
+						// target index: strand -1 scores the reverse complement, whose index runs against the genomic anchor; a lane
+						// meets its anchors in genomic order, so there an equal later anchor (smaller target index) replaces the held one
+						const int ti = rev ? (int)(na - 1 - a) : (int)a;
+						if (v > vmax || (rev && v == vmax && v != NEG_INF)) {
+							vmax = v;
+							best_i = ti;
+							best_dir = d;
+						}
+						continue;
+					}
 					if (BID)
 						v = mg_log_sum_log<STRICT>(f[u], r[u]);
 					else
@@ -269,6 +309,25 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 				for (int k = 16; k > 0; k >>= 1)
 					vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, k));
 				result = (double)vmax;
+			} else if (MODE == MG_PWM_MAX_POS) {
+#pragma unroll
+				for (int k = 16; k > 0; k >>= 1) { // larger score, then smaller target index
+					const float ov = __shfl_xor_sync(0xffffffffu, vmax, k);
+					const int oi = __shfl_xor_sync(0xffffffffu, best_i, k), od = __shfl_xor_sync(0xffffffffu, best_dir, k);
+					if (oi >= 0 && (best_i < 0 || ov > vmax || (ov == vmax && oi < best_i))) {
+						vmax = ov;
+						best_i = oi;
+						best_dir = od;
+					}
+				}
+				if (best_i >= 0) { // PWMScorer::compute_position_result (src/PWMScorer.cpp:168-182), in float like the reference
+					float pos = __fadd_rn((float)best_i, 1.0f);
+					if (rev)
+						pos = __fadd_rn(__fsub_rn(__fsub_rn((float)(xe - ws), pos), (float)L), 1.0f);
+					if (BID)
+						pos = pos * (float)best_dir;
+					result = (double)pos;
+				}
 			} else {
 #pragma unroll
 				for (int k = 16; k > 0; k >>= 1)

@@ -12,7 +12,7 @@ from ._lib import MishaGpuError, c_dbl, c_i64, c_int, c_vp, load  # noqa: F401 (
 FUNC_IDS = {"avg": 0, "sum": 1, "min": 2, "max": 3, "stddev": 4, "quantile": 5, "nearest": 6, "size": 7, "exists": 8,
             # order-dependent functions; the *.pos ones take param = 1 for positions relative to the window start
             "lse": 9, "first": 10, "last": 11, "first.pos": 12, "last.pos": 13, "min.pos": 14, "max.pos": 15}
-PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.count": 3}
+PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.max.pos": 2, "pwm.count": 3}
 
 
 def _p(a):

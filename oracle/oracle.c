@@ -751,9 +751,44 @@ static float orc_like_rc(const float *logp, int L, const char *s, int rev_order)
 	return lp;
 }
 
+/* pwm.max.pos scores through DnaPSSM::max_like_match (src/DnaPSSM.cpp:285-365), whose per-base rule differs from     */
+/* calc_like's: N / n / * add the row's average log-probability (DnaPSSM.h:133-135), any other non-ACGT character    */
+/* adds nothing. fwd: rows p = 0..L-1 over s[0..L); rc: rows L-1..0 with complemented codes. rev_order as above.     */
+static float orc_row_avg(const float *lp) { return (lp[0] + lp[1] + lp[2] + lp[3]) / 4; }
+static int orc_neutral(char c) { return c == 'N' || c == 'n' || c == '*'; }
+
+static float orc_match_fwd(const float *logp, int L, const char *s, int rev_order)
+{
+	float lp = 0;
+	for (int k = 0; k < L; ++k) {
+		int p = rev_order ? L - 1 - k : k;
+		int code = ORC_BASE[(unsigned char)s[p]] - 1;
+		if (orc_neutral(s[p]))
+			lp += orc_row_avg(logp + p * 4);
+		else if (code >= 0)
+			lp += logp[p * 4 + code];
+	}
+	return lp;
+}
+
+static float orc_match_rc(const float *logp, int L, const char *s, int rev_order)
+{
+	float lp = 0;
+	for (int k = 0; k < L; ++k) {
+		int j = rev_order ? L - 1 - k : k;
+		int p = L - 1 - j;
+		int code = ORC_BASE[(unsigned char)s[j]] - 1;
+		if (orc_neutral(s[j]))
+			lp += orc_row_avg(logp + p * 4);
+		else if (code >= 0)
+			lp += logp[p * 4 + (3 - code)];
+	}
+	return lp;
+}
+
 /* One chromosome. seq = ASCII bases of the whole chromosome (len = chromsize).                              */
 /* mode: 0 = pwm (log-sum-exp over anchors, src/utils/RunningLogSumExp.h:32-45,175-178), 1 = pwm.max,         */
-/* 3 = pwm.count (src/PWMScorer.cpp:660-690). strand: 1 / -1 (used when !bidirect and for the add order).     */
+/* 2 = pwm.max.pos, 3 = pwm.count (src/PWMScorer.cpp:660-690). strand: 1 / -1 (used when !bidirect and for the add order).     */
 /* score_interval: src/PWMScorer.cpp:742-861; expansion src/GenomeSeqScorer.cpp:16-38.                        */
 void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int bidirect, int extend, int mode, int strand,
 			 float score_thresh, int64_t n, const int64_t *start, const int64_t *end, int64_t sshift, int64_t eshift, double *out)
@@ -776,20 +811,61 @@ void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int b
 			continue;            /* :750-752 NaN */
 		if (tlen < L) {          /* extend=TRUE clipped by the chromosome end: score_without_spatial over zero anchors, */
 			out[i] = mode == 3 ? 0. : -INFINITY; /* src/PWMScorer.cpp:313-338 -> -inf (pwm, pwm.max) / 0 hits (pwm.count) */
+			if (mode == 2) /* max_like_match returns begin with best_dir unset: index 0; the bidirect sign is undefined there */
+				out[i] = bidirect ? ORC_NAN : (strand == -1 ? (double)((float)tlen - 1.0f - (float)L + 1) : 1.0);
 			continue;
 		}
-		int64_t i_max = tlen - L; /* get_max_range() is unbounded without spat_min/max */
+		int64_t i_max = tlen - L;
 		int64_t want = we - ws - 1;
 		if (want < i_max)
 			i_max = want;
+		if (i_max > 1000000) /* DnaPSSM::m_max_range default (src/DnaPSSM.h:186-187; :774 and DnaPSSM.cpp:293) */
+			i_max = 1000000;
 		int64_t na = i_max + 1;
+		/* strand -1 scores the reverse complement of [ws, xe): target index t <-> genomic anchor (tlen - L) - t, */
+		/* so the first na target anchors are the last na genomic ones */
+		int64_t a_base = strand == -1 ? (tlen - L + 1) - na : 0;
+		if (mode == 2) {
+			/* pwm.max.pos: src/PWMScorer.cpp:325-337 -> max_like_match(combine_strands = false) over the target, */
+			/* then compute_position_result (:168-182), all in float */
+			int rev = strand == -1, best_dir = 1;
+			int64_t best_t = -1;
+			float best = -INFINITY;
+			for (int64_t t = 0; t < na; ++t) {
+				const char *s = seq + ws + (rev ? (tlen - L) - t : t);
+				float l = rev ? orc_match_rc(logp, L, s, 1) : orc_match_fwd(logp, L, s, 0);
+				float total = l;
+				int dir = 1;
+				if (bidirect) {
+					float rl = rev ? orc_match_fwd(logp, L, s, 1) : orc_match_rc(logp, L, s, 0);
+					if (rl > l) {
+						total = rl;
+						dir = -1;
+					}
+				}
+				if (total > best) {
+					best = total;
+					best_t = t;
+					best_dir = dir;
+				}
+			}
+			if (best_t >= 0) {
+				float pos = (float)best_t + 1.0f;
+				if (rev)
+					pos = (float)tlen - pos - (float)L + 1;
+				if (bidirect)
+					pos = pos * best_dir;
+				out[i] = pos;
+			}
+			continue;
+		}
 		if (na > cap) {
 			cap = na * 2;
 			vals = (float *)realloc(vals, (size_t)cap * sizeof(float));
 		}
 		int rev = strand == -1;
 		for (int64_t a = 0; a < na; ++a) {
-			const char *s = seq + ws + a;
+			const char *s = seq + ws + a_base + a;
 			float v;
 			if (bidirect) {
 				float f = orc_like_fwd(logp, L, s, rev), r = orc_like_rc(logp, L, s, rev);

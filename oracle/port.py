@@ -214,7 +214,7 @@ def pssm_logp(pssm, prior):
     return out
 
 
-PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.count": 3}
+PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.max.pos": 2, "pwm.count": 3}
 
 
 def pwm(seq, logp, start, end, bidirect=True, extend=True, mode="pwm", strand=1, score_thresh=0.0, sshift=0, eshift=0):

@@ -38,6 +38,18 @@ def main():
         r = ref.sparse_eval_ext(f, cid, s, e, ref.EXT_COLS, extra_funcs=("avg",))
         for k in ref.EXT_COLS:
             out[f"sparse_{c}_{k}"] = r[k]
+    # pwm.max.pos (PWMScorer MAX_LIKELIHOOD_POS -> DnaPSSM::max_like_match): same PSSM and rows as ref_vectors.npz's pwm_* entries
+    base = np.load(os.path.join(HERE, "ref_vectors.npz"))
+    names = [c for c, _ in CHROMS]
+    sizes = [z for _, z in CHROMS]
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = base[f"pwm_{c}_start"], base[f"pwm_{c}_end"]
+        ch = np.full(len(s), cid, dtype=np.int32)
+        for bid in (True, False):
+            for ext in (True, False):
+                for strand in (1, -1):
+                    out[f"pwm_{c}_pwm.max.pos_bid{int(bid)}_ext{int(ext)}_str{strand}"] = ref.pwm_eval(
+                        db, names, sizes, base["pwm_pssm20"], ch, s, e, bid, 0.01, ext, "pwm.max.pos", strand, 0.0)
     np.savez_compressed(os.path.join(HERE, "ref_vectors_ext.npz"), **out)
     print("wrote ref_vectors_ext.npz:", len(out), "arrays")
 

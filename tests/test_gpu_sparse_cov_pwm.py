@@ -352,3 +352,42 @@ def test_sparse_order_dependent_functions(gpu_ctx, sparse_testdb):
             assert_same(got[2][ok], (exp["max.pos"] - ws)[ok], f"{c} max.pos relative")
             assert_same(got[3], exp["last"], f"{c} last")
             assert_same(got[4], exp["min.pos"], f"{c} min.pos")
+
+
+def test_pwm_max_pos_golden_and_oracle(gpu_ctx, seq_testdb, golden):
+    """pwm.max.pos (PWMScorer MAX_LIKELIHOOD_POS -> DnaPSSM::max_like_match): best strand per anchor, first strictly greater
+    anchor in target order, N scored as the row average, 1-based signed position in float -- bit for bit against the
+    reference's compiled scorer (ref_vectors_ext.npz) and the oracle with shifts. Rows clipped below the motif length with
+    both strands are the reference's uninitialised-sign case (NaN here, excluded)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_vectors_ext.npz"))
+    logp = gpu.pssm_logp(golden["pwm_pssm20"], 0.01)
+    L = logp.shape[0]
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = golden[f"pwm_{c}_start"], golden[f"pwm_{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        seq = read_seq(c)
+        for bid in (True, False):
+            for ext in (True, False):
+                for strand in (1, -1):
+                    exp = g[f"pwm_{c}_pwm.max.pos_bid{int(bid)}_ext{int(ext)}_str{strand}"]
+                    got = seq_testdb.pwm(rows, logp, bidirect=bid, extend=ext, mode="pwm.max.pos", strand=strand)
+                    defined = ~(bid & ext & (np.minimum(e + L - 1, size) - s < L))
+                    assert defined.sum() >= len(s) - 2
+                    assert_same(got[defined], exp[defined], f"{c} pwm.max.pos bid={bid} ext={ext} strand={strand}")
+                    assert np.all(np.isnan(got[~defined]))
+                    for sshift, eshift in ((-150, 90), (7, 300)):
+                        got = seq_testdb.pwm(rows, logp, bidirect=bid, extend=ext, mode="pwm.max.pos", strand=strand, sshift=sshift, eshift=eshift)
+                        exp = port.pwm(seq, logp, s, e, bid, ext, "pwm.max.pos", strand, 0.0, sshift, eshift)
+                        assert_same(got, exp, f"{c} pwm.max.pos shifted bid={bid} ext={ext} strand={strand}")
+    # long rows (several 128-anchor chunks per warp), ties between equal anchors on a low-complexity PSSM
+    flat = gpu.pssm_logp(np.tile([[0.7, 0.1, 0.1, 0.1]], (3, 1)), 0.01)
+    seq = read_seq("chr2")
+    s = np.array([0, 1000, 250000, 298000]); e = np.array([5000, 3300, 251000, 300000])
+    rows = gpu_ctx.rows_upload(np.full(len(s), 1), s, e)
+    for lp in (logp, flat):
+        for bid in (True, False):
+            for strand in (1, -1):
+                got = seq_testdb.pwm(rows, lp, bidirect=bid, mode="pwm.max.pos", strand=strand)
+                assert_same(got, port.pwm(seq, lp, s, e, bid, True, "pwm.max.pos", strand), f"long rows bid={bid} strand={strand}")

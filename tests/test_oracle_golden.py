@@ -128,6 +128,25 @@ def test_pwm_matches_reference_golden(golden):
                         assert_same(got, golden[f"pwm_{c}_{mode}_bid{int(bid)}_ext{int(ext)}_str{strand}"], f"{c} {mode} {bid} {ext} {strand}")
 
 
+def test_pwm_max_pos_matches_reference_golden(golden):
+    """pwm.max.pos of oracle.c against the reference's compiled PWMScorer (ref_vectors_ext.npz); rows clipped below the motif
+    length with both strands carry the reference's uninitialised sign and are excluded."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_vectors_ext.npz"))
+    logp = port.pssm_logp(golden["pwm_pssm20"], 0.01)
+    for c, size in CHROMS:
+        seq = read_seq(c)
+        s, e = golden[f"pwm_{c}_start"], golden[f"pwm_{c}_end"]
+        for bid in (True, False):
+            for ext in (True, False):
+                for strand in (1, -1):
+                    got = port.pwm(seq, logp, s, e, bid, ext, "pwm.max.pos", strand)
+                    exp = g[f"pwm_{c}_pwm.max.pos_bid{int(bid)}_ext{int(ext)}_str{strand}"]
+                    defined = ~(bid & ext & (np.minimum(e + logp.shape[0] - 1, size) - s < logp.shape[0]))
+                    assert_same(got[defined], exp[defined], f"{c} pwm.max.pos {bid} {ext} {strand}")
+
+
 def test_summary_and_screen_merge():
     v = np.array([1.0, np.nan, 3.0, 2.0])
     out = port.summary(v)
