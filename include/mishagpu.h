@@ -216,6 +216,14 @@ int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, cons
 /* streams. This is the end-to-end path bench.py times as `e2e`.                                                  */
 int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
 					  int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out);
+/* The same pipeline for the other sources: arguments as mg_sparse_window / mg_coverage / mg_pwm with the rows and the result  */
+/* column(s) in host memory.                                                                                                 */
+int mg_h_sparse_window(mg_ctx *ctx, const mg_sparse *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+					   int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out);
+int mg_h_coverage(mg_ctx *ctx, const mg_ivset *s, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+				  int64_t sshift, int64_t eshift, double *h_out);
+int mg_h_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
+			 int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int64_t sshift, int64_t eshift, double *h_out);
 
 #ifdef __cplusplus
 }

@@ -760,6 +760,49 @@ static int mg_pipe_prepare(mg_ctx *ctx, int64_t bytes_per_slot)
 	return 0;
 }
 
+// Rows in host memory -> result columns in host memory: chunks of pipe_chunk_rows rows travel through three device slots, each
+// on its own stream (upload, the launch the caller supplies, download), so the copies of one chunk overlap the kernel of
+// another in both directions. launch(rows, m, d_cols, stream) enqueues the computation of one chunk of m rows.
+template <typename Launch>
+static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
+						 double *const *h_out, Launch launch)
+{
+	MG_REQUIRE(ctx, n >= 0 && ncols > 0 && ncols <= 32, "host pipeline: bad arguments");
+	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end && h_out), "host pipeline: NULL row or output arrays");
+	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows per pipeline slot
+	const int64_t slot_bytes = CHUNK * (20 + 8 * (int64_t)ncols);
+	if (mg_pipe_prepare(ctx, slot_bytes))
+		return 1;
+	int64_t done = 0;
+	for (int64_t c = 0; done < n; ++c, done += CHUNK) {
+		const int slot = (int)(c % 3);
+		cudaStream_t st = ctx->pipe_stream[slot];
+		const int64_t m = n - done < CHUNK ? n - done : CHUNK;
+		char *base = (char *)ctx->pipe_dev[slot];
+		int64_t *d_start = (int64_t *)base, *d_end = (int64_t *)(base + CHUNK * 8);
+		int32_t *d_chrom = (int32_t *)(base + CHUNK * 16);
+		double *d_cols[32];
+		for (int k = 0; k < ncols; ++k)
+			d_cols[k] = (double *)(base + CHUNK * 20 + (int64_t)k * CHUNK * 8);
+		MG_CUDA(ctx, cudaMemcpyAsync(d_start, h_start + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_end, h_end + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_chrom, h_chrom + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+		mg_rows rows;
+		rows.src.kind = 0;
+		rows.src.n = m;
+		rows.src.chrom = d_chrom;
+		rows.src.start = d_start;
+		rows.src.end = d_end;
+		if (launch(rows, m, d_cols, st))
+			return 1;
+		for (int k = 0; k < ncols; ++k)
+			MG_CUDA(ctx, cudaMemcpyAsync(h_out[k] + done, d_cols[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+	}
+	for (int i = 0; i < 3; ++i)
+		MG_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]));
+	return 0;
+}
+
 extern "C" int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start,
 								 const int64_t *h_end, int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params,
 								 double *const *h_out)
@@ -805,41 +848,12 @@ extern "C" int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, cons
 			return 0;
 		}
 	}
-	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows per pipeline slot
-	const int64_t slot_bytes = CHUNK * (20 + 8 * (int64_t)nfuncs);
-	if (mg_pipe_prepare(ctx, slot_bytes))
-		return 1;
-	int64_t done = 0;
-	for (int64_t c = 0; done < n; ++c, done += CHUNK) {
-		const int slot = (int)(c % 3);
-		cudaStream_t st = ctx->pipe_stream[slot];
-		const int64_t m = n - done < CHUNK ? n - done : CHUNK;
-		char *base = (char *)ctx->pipe_dev[slot];
-		int64_t *d_start = (int64_t *)base, *d_end = (int64_t *)(base + CHUNK * 8);
-		int32_t *d_chrom = (int32_t *)(base + CHUNK * 16);
-		double *d_cols[32];
-		for (int k = 0; k < nfuncs; ++k)
-			d_cols[k] = (double *)(base + CHUNK * 20 + (int64_t)k * CHUNK * 8);
-		MG_CUDA(ctx, cudaMemcpyAsync(d_start, h_start + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
-		MG_CUDA(ctx, cudaMemcpyAsync(d_end, h_end + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
-		MG_CUDA(ctx, cudaMemcpyAsync(d_chrom, h_chrom + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-		mg_rows rows;
-		rows.src.kind = 0;
-		rows.src.n = m;
-		rows.src.chrom = d_chrom;
-		rows.src.start = d_start;
-		rows.src.end = d_end;
+	return mg_h_pipeline(ctx, n, h_chrom, h_start, h_end, nfuncs, h_out, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
 		DenseQuery q;
 		bool need_sweep;
-		if (mg_fill_dense_query(ctx, t, &rows, 0, m, sshift, eshift, nfuncs, funcs, params, d_cols, q, need_sweep) ||
-			mg_launch_dense(ctx, q, need_sweep, st))
-			return 1;
-		for (int k = 0; k < nfuncs; ++k)
-			MG_CUDA(ctx, cudaMemcpyAsync(h_out[k] + done, d_cols[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-	}
-	for (int i = 0; i < 3; ++i)
-		MG_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]));
-	return 0;
+		return mg_fill_dense_query(ctx, t, &rows, 0, m, sshift, eshift, nfuncs, funcs, params, d_cols, q, need_sweep) ||
+			   mg_launch_dense(ctx, q, need_sweep, st);
+	});
 }
 
 // ---- generic device exclusive scan of int64 (tile reduce -> one-block scan -> tile write) -------------------------
@@ -1391,6 +1405,33 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 	MG_LAUNCH_CHECK(ctx);
 	MG_CUDA(ctx, cudaFreeAsync(d_tab, st));
 	return 0;
+}
+
+// ---- host-buffer forms of the sparse / coverage / PWM calls (the same three-slot pipeline as mg_h_dense_window) -------------
+extern "C" int mg_h_sparse_window(mg_ctx *ctx, const mg_sparse *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+								  int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out)
+{
+	return mg_h_pipeline(ctx, n, h_chrom, h_start, h_end, nfuncs, h_out, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
+		return mg_sparse_window(ctx, t, &rows, 0, m, sshift, eshift, nfuncs, funcs, params, d_cols, st);
+	});
+}
+
+extern "C" int mg_h_coverage(mg_ctx *ctx, const mg_ivset *s, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+							 int64_t sshift, int64_t eshift, double *h_out)
+{
+	double *cols[1] = {h_out};
+	return mg_h_pipeline(ctx, n, h_chrom, h_start, h_end, 1, cols, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
+		return mg_coverage(ctx, s, &rows, 0, m, sshift, eshift, d_cols[0], st);
+	});
+}
+
+extern "C" int mg_h_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
+						int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int64_t sshift, int64_t eshift, double *h_out)
+{
+	double *cols[1] = {h_out};
+	return mg_h_pipeline(ctx, n, h_chrom, h_start, h_end, 1, cols, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
+		return mg_pwm(ctx, s, h_logp, L, bidirect, extend, mode, strand, score_thresh, &rows, 0, m, sshift, eshift, d_cols[0], st);
+	});
 }
 
 // ---- gsummary ------------------------------------------------------------------------------------------------------

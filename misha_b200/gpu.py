@@ -275,6 +275,17 @@ class SparseTrack:
     def window(self, rows, funcs, sshift=0, eshift=0, first=0, count=None):
         return [b.to_host() for b in self.window_dev(rows, funcs, sshift, eshift, first, count)]
 
+    def window_host(self, chrom, start, end, funcs, sshift=0, eshift=0, out=None):
+        """End-to-end: host arrays in, host columns out (mg_h_sparse_window)."""
+        chrom, start, end = _arr(chrom, np.int32), _arr(start, np.int64), _arr(end, np.int64)
+        ids, params = _func_args(funcs)
+        out = out or [np.empty(len(chrom), dtype=np.float64) for _ in ids]
+        ptrs = (c_vp * len(out))(*[o.ctypes.data_as(c_vp) for o in out])
+        c = self.ctx
+        c._check(c.lib.mg_h_sparse_window(c.h, self.h, c_i64(len(chrom)), _p(chrom), _p(start), _p(end), c_i64(sshift), c_i64(eshift),
+                                          c_int(len(ids)), _p(ids), _p(params), ptrs))
+        return out
+
     def free(self):
         if self.h:
             self.ctx.lib.mg_sparse_free(self.ctx.h, self.h)
@@ -303,6 +314,14 @@ class IntervalSet:
 
     def coverage(self, rows, sshift=0, eshift=0, first=0, count=None):
         return self.coverage_dev(rows, sshift, eshift, first, count).to_host()
+
+    def coverage_host(self, chrom, start, end, sshift=0, eshift=0, out=None):
+        """End-to-end: host arrays in, host column out (mg_h_coverage)."""
+        chrom, start, end = _arr(chrom, np.int32), _arr(start, np.int64), _arr(end, np.int64)
+        out = np.empty(len(chrom), dtype=np.float64) if out is None else out
+        c = self.ctx
+        c._check(c.lib.mg_h_coverage(c.h, self.h, c_i64(len(chrom)), _p(chrom), _p(start), _p(end), c_i64(sshift), c_i64(eshift), _p(out)))
+        return out
 
     def free(self):
         if self.h:
@@ -336,6 +355,17 @@ class Sequence:
 
     def pwm(self, rows, logp, **kw):
         return self.pwm_dev(rows, logp, **kw).to_host()
+
+    def pwm_host(self, chrom, start, end, logp, bidirect=True, extend=True, mode="pwm", strand=1, score_thresh=0.0, sshift=0, eshift=0, out=None):
+        """End-to-end: host arrays in, host column out (mg_h_pwm)."""
+        chrom, start, end = _arr(chrom, np.int32), _arr(start, np.int64), _arr(end, np.int64)
+        lp = _arr(logp, np.float32)
+        out = np.empty(len(chrom), dtype=np.float64) if out is None else out
+        c = self.ctx
+        c._check(c.lib.mg_h_pwm(c.h, self.h, _p(lp), c_int(lp.shape[0]), c_int(int(bidirect)), c_int(int(extend)), c_int(PWM_MODES[mode]),
+                                c_int(strand), ctypes.c_float(score_thresh), c_i64(len(chrom)), _p(chrom), _p(start), _p(end), c_i64(sshift),
+                                c_i64(eshift), _p(out)))
+        return out
 
     def free(self):
         if self.h:

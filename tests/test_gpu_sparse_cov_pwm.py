@@ -391,3 +391,44 @@ def test_pwm_max_pos_golden_and_oracle(gpu_ctx, seq_testdb, golden):
             for strand in (1, -1):
                 got = seq_testdb.pwm(rows, lp, bidirect=bid, mode="pwm.max.pos", strand=strand)
                 assert_same(got, port.pwm(seq, lp, s, e, bid, True, "pwm.max.pos", strand), f"long rows bid={bid} strand={strand}")
+
+
+def test_host_buffer_pipeline_sparse_coverage_pwm(gpu_ctx, sparse_testdb, seq_testdb, golden):
+    """mg_h_sparse_window / mg_h_coverage / mg_h_pwm (host rows in, host columns out through the three-slot copy pipeline)
+    equal the device-resident calls bit for bit, over several chunks and a ragged last one."""
+    rng = np.random.default_rng(64)
+    n = 5000
+    chrom = np.sort(rng.integers(0, 3, n)).astype(np.int32)
+    sizes = np.array([z for _, z in CHROMS])
+    s = np.array([rng.integers(0, sizes[c] - 700) for c in chrom])
+    order = np.lexsort((s, chrom))
+    chrom, s = chrom[order], s[order]
+    e = s + rng.integers(1, 600, n)
+    rows = gpu_ctx.rows_upload(chrom, s, e)
+    gpu_ctx.set_option("pipe_chunk_rows", 1024)
+    try:
+        funcs = ["avg", "nearest", "max", ("quantile", 0.5), ("max.pos", 1)]
+        dev = sparse_testdb.window(rows, funcs, -300, 450)
+        host = sparse_testdb.window_host(chrom, s, e, funcs, -300, 450)
+        for k in range(len(funcs)):
+            assert_same(host[k], dev[k], f"sparse host pipeline {funcs[k]}")
+        iv = gpu.IntervalSet(gpu_ctx)
+        for cid, (c, size) in enumerate(CHROMS):
+            st = np.sort(rng.integers(0, size - 500, 300))
+            en = st + rng.integers(1, 400, 300)
+            us, ue = [], []
+            for a, b in zip(st, en):
+                if us and a <= ue[-1]:
+                    ue[-1] = max(ue[-1], b)
+                else:
+                    us.append(a); ue.append(b)
+            iv.stage(cid, np.array(us), np.array(ue))
+        assert_same(iv.coverage_host(chrom, s, e, -100, 100), iv.coverage(rows, -100, 100), "coverage host pipeline")
+        iv.free()
+        logp = gpu.pssm_logp(golden["pwm_pssm20"], 0.01)
+        for mode in ("pwm", "pwm.max", "pwm.max.pos", "pwm.count"):
+            got = seq_testdb.pwm_host(chrom, s, e, logp, mode=mode, score_thresh=-25.0, sshift=-10, eshift=10)
+            assert_same(got, seq_testdb.pwm(rows, logp, mode=mode, score_thresh=-25.0, sshift=-10, eshift=10), f"pwm host pipeline {mode}")
+        assert len(sparse_testdb.window_host(chrom[:0], s[:0], e[:0], ["avg"])[0]) == 0
+    finally:
+        gpu_ctx.set_option("pipe_chunk_rows", 1 << 19)
