@@ -193,13 +193,20 @@ __device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ lv, 
 // k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l; with want2 (k + 1 < n) also the
 // (k+1)-th. lv = the record's levels (global or staged), rec = the record in global memory (pos_of_rank is read there),
 // vals_block = the track at the block's first bin.
+#ifndef MG_BW_SELECT_INLINE
+#define MG_BW_SELECT_INLINE __forceinline__
+#endif
+#ifndef MG_BW_UNROLL
+#define MG_BW_UNROLL MG_BW_LB
+#endif
 template <bool G>
-__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l,
+__device__ MG_BW_SELECT_INLINE void mg_bw_select(const uint8_t *__restrict__ lv, const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l,
 											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
 {
 	const uint32_t l0 = l, len = r - l;
 	uint32_t rank = 0;
-#pragma unroll
+	constexpr int unroll = MG_BW_UNROLL;
+#pragma unroll unroll
 	for (int level = 0; level < MG_BW_LB; ++level, lv += MG_BW_LEVEL_BYTES) {
 		const uint32_t ol = mg_bw_rank_lo<G>(lv, l), orr = mg_bw_rank_hi<G>(lv, r);
 		const uint32_t nz = (r - l) - (orr - ol);
@@ -240,16 +247,20 @@ __device__ __forceinline__ void mg_bulk_g2s(void *dst, const void *src, uint32_t
 				 "r"(mg_smem_addr(bar))
 				 : "memory");
 }
+// a waiting thread is suspended by the hardware for up to this long per try instead of spinning on the barrier word
+#ifndef MG_MBAR_SUSPEND_NS
+#define MG_MBAR_SUSPEND_NS 100000u
+#endif
 __device__ __forceinline__ void mg_mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile("{\n"
 				 ".reg .pred p;\n"
 				 "MG_WAIT_%=:\n"
-				 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+				 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 				 "@p bra MG_DONE_%=;\n"
 				 "bra MG_WAIT_%=;\n"
 				 "MG_DONE_%=:\n"
 				 "}" ::"r"(mg_smem_addr(bar)),
-				 "r"(parity)
+				 "r"(parity), "r"(MG_MBAR_SUSPEND_NS)
 				 : "memory");
 }
