@@ -102,6 +102,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->stage_slots = (int)value;
 		return 0;
 	}
+	if (name && !strcmp(name, "cov_raster")) {
+		ctx->cov_raster = value != 0;
+		return 0;
+	}
 	if (name && !strcmp(name, "block_wm")) {
 		ctx->block_wm = value != 0;
 		return 0;
@@ -565,6 +569,8 @@ extern "C" int mg_rows_fixedbin(mg_ctx *ctx, int64_t binsize, int64_t nscope, co
 	r->h_sstart.assign(h_start, h_start + nscope);
 	r->h_send.assign(h_end, h_end + nscope);
 	r->h_srow0 = row0;
+	for (int64_t k = 0; k <= nscope && k <= MG_SCOPE_INLINE; ++k)
+		r->src.srow0_inl[k] = row0[k];
 	if (nscope) {
 		if ((e = cudaMemcpy((void *)r->src.sstart, h_start, (size_t)nscope * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
 			(e = cudaMemcpy((void *)r->src.send, h_end, (size_t)nscope * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -1245,6 +1251,8 @@ extern "C" int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, 
 	q.table = s->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.out = d_out;
+	q.raster = ctx->cov_raster && rows->src.kind == 1 && rows->src.binsize < (1 << 20) ? 1 : 0;
+	q.div = mg_covdiv_make(rows->src.kind == 1 ? rows->src.binsize : 1);
 	if (ctx->force_sweep)
 		k_coverage<<<(unsigned)mg_div_up(count, MG_SP_THREADS * MG_SP_ROWS), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 	else

@@ -6,6 +6,7 @@
 #pragma once
 #include "common.cuh"
 
+#define MG_SCOPE_INLINE 32
 struct RowSrc {
 	int kind; // 0 explicit, 1 fixed-bin
 	int64_t n;
@@ -22,6 +23,9 @@ struct RowSrc {
 	const int64_t *send;
 	const int64_t *srow0; // nscope + 1 exclusive prefix of rows per scope interval
 	const int64_t *sbin0; // floor(sstart / binsize) per scope interval (host-computed)
+	// a copy of srow0 that travels in the kernel parameters when the scope is short (a genome's chromosomes): the search for a
+	// row's scope interval then reads the constant bank instead of paying a chain of dependent global loads per thread block
+	int64_t srow0_inl[MG_SCOPE_INLINE + 1];
 };
 
 struct mg_rows {
@@ -36,6 +40,17 @@ struct mg_rows {
 // scope interval of implicit row r: last k with srow0[k] <= r
 __device__ __forceinline__ int64_t mg_scope_of_row(const RowSrc &rs, int64_t r)
 {
+	if (rs.nscope <= MG_SCOPE_INLINE) {
+		int lo = 0, hi = (int)rs.nscope;
+		while (hi - lo > 1) {
+			const int mid = (lo + hi) >> 1;
+			if (rs.srow0_inl[mid] <= r)
+				lo = mid;
+			else
+				hi = mid;
+		}
+		return lo;
+	}
 	int64_t lo = 0, hi = rs.nscope; // invariant: srow0[lo] <= r < srow0[hi]
 	while (hi - lo > 1) {
 		int64_t mid = (lo + hi) >> 1;

@@ -419,6 +419,21 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_sparse_window(const SparseQue
 }
 
 // coverage = sum of overlaps with the unified source intervals / window length. src/IntervVarProcessor.cpp:242-325.
+// floor(x / b) and ceil(x / b) for |x| < 2^30 by a multiplication: x is lifted by K b (a multiple of b above 2^30) so that the
+// unsigned magic-number division applies; magic = ceil(2^64 / b). Filled on the host (the divisor is the iterator's bin size).
+struct CovDiv {
+	unsigned long long magic;
+	int b, K;
+};
+static inline CovDiv mg_covdiv_make(int64_t b)
+{
+	CovDiv d;
+	d.b = (int)b;
+	d.magic = b > 1 ? ~0ull / (unsigned long long)b + 1ull : 0ull;
+	d.K = (int)(((1ll << 30) + b - 1) / b);
+	return d;
+}
+
 struct CoverageQuery {
 	RowSrc rows;
 	int64_t first, count;
@@ -426,6 +441,8 @@ struct CoverageQuery {
 	const SparseChrom *table;
 	const int64_t *chrom_sizes;
 	double *out;
+	int raster; // regular-grid blocks rasterise their records (k_coverage_merge); 0: per-row cursors (ablation)
+	CovDiv div; // division by the fixed-bin iterator's bin size
 };
 
 __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery q)
@@ -502,6 +519,9 @@ struct SfSmem {
 	int n;          // staged records
 	int chrom;
 	int mode;       // 1 = staged, 0 = per-row search over the whole chromosome
+	// regular-grid blocks: what warp 0 worked out for everybody (mg_sf_grid_setup)
+	int64_t g_origin, g_first;
+	int g_chrom, g_len, g_nrows, g_n, g_status;
 };
 
 // rows of lane l: block_base + warp * 32 * MG_SF_ROWS + l + 32 k
@@ -765,21 +785,60 @@ __device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
 	return true;
 }
 
-// stages the records a regular-grid block can touch; false = does not fit (count or 32-bit range): use the search path
-__device__ __forceinline__ bool mg_sf_stage_grid(SfSmem &sm, const SparseChrom *table, const SfGrid &g, int64_t binsize, bool want_val, int &n_out)
+// Regular-grid set-up of a thread block: 0 = not a regular grid (general path), 1 = grid and its records are staged,
+// 2 = grid whose records do not fit the stage (count or 32-bit range): per-row search path. Warp 0 alone does the scope lookup,
+// the grid geometry and the two coarse-index lookups that bracket the records (uniform work: seven warps skip ~200
+// instructions each, they would only wait at the barrier anyway); after one barrier every thread stages its record.
+template <typename Q>
+__device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const SparseChrom *table, bool want_val, SfGrid &g, int &n_out)
 {
-	const SparseChrom ch = table[g.chrom];
-	int n = 0;
-	int64_t first = 0;
+	if (q.rows.kind != 1)
+		return 0;
+	if (threadIdx.x < 32) {
+		SfGrid gg;
+		gg.chrom = 0;
+		gg.origin = 0;
+		gg.len = gg.nrows = 0;
+		int status = 0, n = 0;
+		int64_t first = 0;
+		if (mg_sf_grid_block(q, gg)) {
+			status = 1;
+			const SparseChrom ch = table[gg.chrom];
+			if (ch.n > 0) {
+				const int64_t hull_end = gg.origin + (int64_t)(gg.nrows - 1) * q.rows.binsize + gg.len;
+				const int64_t c0 = min(gg.origin >> ch.coarse_shift, ch.ncoarse - 1), c1 = min((hull_end >> ch.coarse_shift) + 1, ch.ncoarse - 1);
+				const int64_t lo = (int64_t)__ldg(ch.coarse + c0), hi = (int64_t)__ldg(ch.coarse + c1) + 1;
+				first = lo > 0 ? lo - 1 : 0;
+				const int64_t cnt = min(hi + 1, ch.n) - first;
+				if (cnt > MG_SF_CAP)
+					status = 2;
+				else
+					n = (int)cnt;
+			}
+		}
+		if (threadIdx.x == 0) {
+			sm.g_origin = gg.origin;
+			sm.g_first = first;
+			sm.g_chrom = gg.chrom;
+			sm.g_len = gg.len;
+			sm.g_nrows = gg.nrows;
+			sm.g_n = n;
+			sm.g_status = status;
+		}
+	}
+	__syncthreads();
+	const int status = sm.g_status;
+	if (status != 1)
+		return status;
+	g.chrom = sm.g_chrom;
+	g.origin = sm.g_origin;
+	g.len = sm.g_len;
+	g.nrows = sm.g_nrows;
+	const int n = sm.g_n;
 	bool bad = false;
-	if (ch.n > 0) {
-		const int64_t hull_end = g.origin + (int64_t)(g.nrows - 1) * binsize + g.len;
-		const int64_t c0 = min(g.origin >> ch.coarse_shift, ch.ncoarse - 1), c1 = min((hull_end >> ch.coarse_shift) + 1, ch.ncoarse - 1);
-		const int64_t lo = (int64_t)__ldg(ch.coarse + c0), hi = (int64_t)__ldg(ch.coarse + c1) + 1;
-		first = lo > 0 ? lo - 1 : 0;
-		const int64_t cnt = min(hi + 1, ch.n) - first;
-		bad = cnt > MG_SF_CAP;
-		n = bad ? 0 : (int)cnt;
+	if ((int)threadIdx.x < n + 3) {
+		const SparseChrom ch = table[g.chrom];
+		const int64_t first = sm.g_first;
 		for (int t = threadIdx.x; t < n + 3; t += MG_SP_THREADS) {
 			int st = t == 0 ? -MG_SF_SENT : MG_SF_SENT, en = st;
 			float v = mg_nanf();
@@ -797,7 +856,7 @@ __device__ __forceinline__ bool mg_sf_stage_grid(SfSmem &sm, const SparseChrom *
 		}
 	}
 	n_out = n;
-	return !__syncthreads_or(bad);
+	return __syncthreads_or(bad) ? 2 : 1;
 }
 
 // Statistics of one window [a, b) over the staged records (indices 1..n between sentinels); lo = this lane's cursor.
@@ -885,12 +944,13 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_sparse_merge
 	__shared__ SfSmem sm;
 	constexpr bool SUM = F < 0 || F == MG_AVG || F == MG_SUM || F == MG_NEAREST, MM = F < 0 || F == MG_MIN || F == MG_MAX;
 	SfGrid g;
-	if (mg_sf_grid_block(q, g)) { // block-uniform
-		int n;
-		if (!mg_sf_stage_grid(sm, q.table, g, q.rows.binsize, true, n)) {
-			mg_sparse_rows_search(q);
-			return;
-		}
+	int n;
+	const int grid = mg_sf_grid_setup(q, sm, q.table, true, g, n); // block-uniform
+	if (grid == 2) {
+		mg_sparse_rows_search(q);
+		return;
+	}
+	if (grid == 1) {
 		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
 		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + j0;
 		int a = j0 * (int)q.rows.binsize, lo = 1;
@@ -913,7 +973,7 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_sparse_merge
 		return;
 	}
 	const int64_t origin = sm.origin;
-	const int n = sm.n;
+	n = sm.n;
 	int lo = 1, prev = INT_MIN;
 #pragma unroll
 	for (int k = 0; k < MG_SF_ROWS; ++k) {
@@ -981,14 +1041,136 @@ __device__ __forceinline__ void mg_coverage_rows_search(const CoverageQuery &q)
 	}
 }
 
+// ---- coverage of a regular-grid block by rasterising the records ---------------------------------------------------------
+// Row j's window is [j b, j b + len) in block coordinates. Instead of every row searching its records, every staged record
+// [s, e) marks the rows it touches: the rows it covers completely (ceil(s / b) <= j <= floor((e - len) / b)) through a
+// difference array that a prefix sum turns into "+len" per row -- the source intervals are disjoint, so such a row has no
+// other contribution -- and the few rows it covers partly (at most 2 ceil(len / b) + 2 per record) with shared-memory atomic
+// adds of the overlap. Each warp rasterises its own 256 rows (lane r takes the r-th record that can touch them), so after the
+// one block barrier of the staging everything is warp-synchronous. A row then costs a few shared-memory accesses, a compare
+// and its store, against ~87 instructions per row of the per-row cursor path.
+// Same integers as the cursor path (total overlap, window length), so the same doubles come out.
+#define MG_COV_RASTER_MAX_BINS 8 // windows of up to this many bins (len <= 8 b): beyond that a record touches too many rows
+#define MG_SF_BLOCK_ROWS (MG_SP_THREADS * MG_SF_ROWS)
+#define MG_SF_WARP_ROWS (32 * MG_SF_ROWS)
+#define MG_CR_PAD(j) ((j) + ((j) >> 5)) // one pad word per 32: lane-strided and 8-per-lane accesses are both conflict-free
+#define MG_COV_QT 256 // window lengths below this take their quotient total / len from a per-block table
+struct CovRaster {
+	double qt[MG_COV_QT]; // qt[t] = (double)t / (double)len: len + 1 possible results, one division per thread instead of one per row
+	// per warp: overlap collected from partly covering records, then the row's total / +len at the first completely covered
+	// row of a record, -len after the last
+	int acc[MG_SP_THREADS / 32][MG_CR_PAD(MG_SF_WARP_ROWS) + 1];
+	int diff[MG_SP_THREADS / 32][MG_CR_PAD(MG_SF_WARP_ROWS + 1) + 1];
+};
+
+__device__ __forceinline__ int mg_floordiv_i(int x, const CovDiv &d)
+{
+	if (d.b == 1)
+		return x;
+	const unsigned long long y = (unsigned long long)((long long)x + (long long)d.K * d.b); // < 2^32
+	return (int)__umul64hi(y, d.magic) - d.K;
+}
+__device__ __forceinline__ int mg_ceildiv_i(int x, const CovDiv &d) { return -mg_floordiv_i(-x, d); }
+
+__device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, int n, const SfGrid &g, const CovDiv &b, double *__restrict__ out)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, len = g.len, bsz = b.b;
+	const int row0 = warp * MG_SF_WARP_ROWS, wrows = min(MG_SF_WARP_ROWS, g.nrows - row0);
+	if (wrows <= 0)
+		return;
+	int *acc = cr.acc[warp], *diff = cr.diff[warp];
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		acc[MG_CR_PAD(lane + 32 * k)] = 0;
+		diff[MG_CR_PAD(lane + 32 * k)] = 0;
+	}
+	if (lane == 0)
+		diff[MG_CR_PAD(MG_SF_WARP_ROWS)] = 0;
+	__syncwarp();
+	if (n > 0) {
+		const int A = row0 * bsz, B = (row0 + wrows - 1) * bsz + len; // hull of the warp's windows
+		int lo = 1, hi = n + 1;                                    // first staged record with end > A (the right sentinel qualifies)
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (sm.end[mid] > A)
+				hi = mid;
+			else
+				lo = mid + 1;
+		}
+		for (int r = lo + lane; r <= n && sm.start[r] < B; r += 32) {
+			const int s = sm.start[r] - A, e = sm.end[r] - A; // in the warp's coordinates: row j's window starts at j b
+			if (e <= s)
+				continue;
+			const int jlo = max(0, mg_floordiv_i(s - len, b) + 1); // j b + len > s
+			const int jhi = min(wrows - 1, mg_ceildiv_i(e, b) - 1); // j b < e
+			if (jlo > jhi)
+				continue;
+			const int flo = max(jlo, mg_ceildiv_i(s, b));        // j b >= s
+			const int fhi = min(jhi, mg_floordiv_i(e - len, b)); // j b + len <= e
+			int p1 = jhi, p2 = jhi + 1; // partly covered rows: [jlo, p1] and [p2, jhi]
+			if (flo <= fhi) {
+				atomicAdd(&diff[MG_CR_PAD(flo)], len);
+				atomicAdd(&diff[MG_CR_PAD(fhi + 1)], -len);
+				p1 = flo - 1;
+				p2 = fhi + 1;
+			}
+			for (int j = jlo; j <= p1; ++j)
+				atomicAdd(&acc[MG_CR_PAD(j)], min(j * bsz + len, e) - max(j * bsz, s));
+			for (int j = p2; j <= jhi; ++j)
+				atomicAdd(&acc[MG_CR_PAD(j)], min(j * bsz + len, e) - max(j * bsz, s));
+		}
+	}
+	__syncwarp();
+	{ // prefix sum of the difference array: 8 consecutive entries per lane, a shuffle scan of the lane totals
+		int v[MG_SF_ROWS], sum = 0;
+#pragma unroll
+		for (int u = 0; u < MG_SF_ROWS; ++u) {
+			sum += diff[MG_CR_PAD(lane * MG_SF_ROWS + u)];
+			v[u] = sum;
+		}
+		int incl = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int o = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d)
+				incl += o;
+		}
+		const int before = incl - sum;
+#pragma unroll
+		for (int u = 0; u < MG_SF_ROWS; ++u)
+			acc[MG_CR_PAD(lane * MG_SF_ROWS + u)] += before + v[u];
+	}
+	__syncwarp();
+	out += row0;
+#pragma unroll
+	for (int k = 0; k < MG_SF_ROWS; ++k) {
+		const int j = lane + 32 * k;
+		if (j < wrows) {
+			const int total = acc[MG_CR_PAD(j)];
+			mg_st_stream(out + j, len < MG_COV_QT ? cr.qt[total] : (total == 0 ? 0. : (total == len ? 1. : (double)total / (double)len)));
+		}
+	}
+}
+
 __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_coverage_merge(const CoverageQuery q)
 {
 	__shared__ SfSmem sm;
+	__shared__ CovRaster cr;
 	SfGrid g;
-	if (mg_sf_grid_block(q, g)) { // block-uniform
-		int n;
-		if (!mg_sf_stage_grid(sm, q.table, g, q.rows.binsize, false, n)) {
-			mg_coverage_rows_search(q);
+	int n;
+	const int grid = mg_sf_grid_setup(q, sm, q.table, false, g, n); // block-uniform
+	if (grid == 2) {
+		mg_coverage_rows_search(q);
+		return;
+	}
+	if (grid == 1) {
+		if (q.raster && (int64_t)g.len <= MG_COV_RASTER_MAX_BINS * q.rows.binsize && (int64_t)MG_SF_BLOCK_ROWS * q.rows.binsize + g.len < MG_SF_RANGE) {
+			if (g.len < MG_COV_QT) { // the len + 1 possible quotients, one division per thread instead of one per row
+				if ((int)threadIdx.x <= g.len)
+					cr.qt[threadIdx.x] = (double)(int)threadIdx.x / (double)g.len;
+				__syncthreads();
+			}
+			mg_cov_raster(sm, cr, n, g, q.div, q.out + (int64_t)blockIdx.x * MG_SF_BLOCK_ROWS);
 			return;
 		}
 		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
@@ -1011,7 +1193,7 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_coverage_mer
 		return;
 	}
 	const int64_t origin = sm.origin;
-	const int n = sm.n;
+	n = sm.n;
 	int lo = 1, prev = INT_MIN;
 #pragma unroll
 	for (int k = 0; k < MG_SF_ROWS; ++k) {

@@ -432,3 +432,61 @@ def test_host_buffer_pipeline_sparse_coverage_pwm(gpu_ctx, sparse_testdb, seq_te
         assert len(sparse_testdb.window_host(chrom[:0], s[:0], e[:0], ["avg"])[0]) == 0
     finally:
         gpu_ctx.set_option("pipe_chunk_rows", 1 << 19)
+
+
+def test_coverage_rasterised_grid_blocks():
+    """Coverage over fixed-bin rows rasterises the source intervals into the block's rows (difference array for completely
+    covered rows + atomics for the partly covered ones). Against the oracle and the per-row cursor path (cov_raster = 0):
+    bin sizes that do and do not divide the coordinates, windows of 1..8 bins and longer (the cursor path takes over),
+    intervals longer than a whole block, 1 bp intervals, touching intervals, scopes that start off the bin grid."""
+    sizes = [700000, 90000]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(2027)
+        iv = gpu.IntervalSet(ctx2)
+        srcs = []
+        for cid, size in enumerate(sizes):
+            cuts = np.unique(rng.integers(0, size, 6000))
+            st, en = cuts[0:-1:2].copy(), cuts[1::2].copy()
+            m = min(len(st), len(en))
+            st, en = st[:m], en[:m]
+            en[::7] = st[::7] + 1                          # 1 bp intervals
+            st[5::11] = en[4::11][:len(st[5::11])]         # touching neighbours
+            keep = en > st
+            st, en = st[keep], en[keep]
+            if cid == 0:                                   # one interval longer than several blocks of rows, one ending at the chromosome end
+                inside = (st >= 200000) & (st < 420000)
+                st, en = st[~inside], en[~inside]
+                st = np.sort(np.concatenate([st, [200003]])); en = np.sort(np.concatenate([en[en <= 200003] if False else en, [419999]]))
+            # re-unify: sorted, disjoint
+            order = np.argsort(st)
+            st, en = st[order], np.maximum.accumulate(en[order])
+            us, ue = [], []
+            for a, b in zip(st, en):
+                if us and a <= ue[-1]:
+                    ue[-1] = max(ue[-1], b)
+                else:
+                    us.append(a); ue.append(b)
+            st, en = np.array(us, np.int64), np.array(ue, np.int64)
+            iv.stage(cid, st, en)
+            srcs.append((st, en))
+        scope_c = np.array([0, 0, 1], np.int32)
+        scope_s = np.array([0, 350007, 13], np.int64)
+        scope_e = np.array([333333, 700000, 90000], np.int64)
+        for binsize in (20, 7, 50, 1000):
+            rows = ctx2.rows_fixedbin(binsize, scope_c, scope_s, scope_e)
+            c, s, e, _ = rows.coords()
+            for sshift, eshift in ((0, 0), (-binsize, binsize), (3, 2 * binsize + 5), (-4 * binsize, 3 * binsize), (-20 * binsize, 20 * binsize), (5, -3)):
+                got = iv.coverage(rows, sshift, eshift)
+                ctx2.set_option("cov_raster", 0)
+                try:
+                    cur = iv.coverage(rows, sshift, eshift)
+                finally:
+                    ctx2.set_option("cov_raster", 1)
+                assert_same(got, cur, f"raster vs cursor bin {binsize} shift {sshift},{eshift}")
+                for cid in range(2):
+                    m = c == cid
+                    assert_same(got[m], port.coverage(srcs[cid][0], srcs[cid][1], sizes[cid], s[m], e[m], sshift, eshift),
+                                f"raster vs oracle chrom{cid} bin {binsize} shift {sshift},{eshift}")
+    finally:
+        ctx2.close()
