@@ -790,7 +790,8 @@ __device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
 // the grid geometry and the two coarse-index lookups that bracket the records (uniform work: seven warps skip ~200
 // instructions each, they would only wait at the barrier anyway); after one barrier every thread stages its record.
 template <typename Q>
-__device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const SparseChrom *table, bool want_val, SfGrid &g, int &n_out)
+__device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const SparseChrom *table, bool want_val, SfGrid &g, int &n_out,
+												double *qt = nullptr, int qt_size = 0)
 {
 	if (q.rows.kind != 1)
 		return 0;
@@ -836,6 +837,10 @@ __device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const Sp
 	g.nrows = sm.g_nrows;
 	const int n = sm.g_n;
 	bool bad = false;
+	// coverage: the len + 1 possible quotients total / len, one division per thread instead of one per row (visible after the
+	// barrier that ends the staging)
+	if (qt && g.len < qt_size && (int)threadIdx.x <= g.len)
+		qt[threadIdx.x] = (double)(int)threadIdx.x / (double)g.len;
 	if ((int)threadIdx.x < n + 3) {
 		const SparseChrom ch = table[g.chrom];
 		const int64_t first = sm.g_first;
@@ -1043,24 +1048,19 @@ __device__ __forceinline__ void mg_coverage_rows_search(const CoverageQuery &q)
 
 // ---- coverage of a regular-grid block by rasterising the records ---------------------------------------------------------
 // Row j's window is [j b, j b + len) in block coordinates. Instead of every row searching its records, every staged record
-// [s, e) marks the rows it touches: the rows it covers completely (ceil(s / b) <= j <= floor((e - len) / b)) through a
-// difference array that a prefix sum turns into "+len" per row -- the source intervals are disjoint, so such a row has no
-// other contribution -- and the few rows it covers partly (at most 2 ceil(len / b) + 2 per record) with shared-memory atomic
-// adds of the overlap. Each warp rasterises its own 256 rows (lane r takes the r-th record that can touch them), so after the
-// one block barrier of the staging everything is warp-synchronous. A row then costs a few shared-memory accesses, a compare
-// and its store, against ~87 instructions per row of the per-row cursor path.
+// [s, e) marks the rows it touches. The source intervals are disjoint, so a row is either covered completely by ONE record
+// (ceil(s / b) <= j <= floor((e - len) / b): its total is len, a plain store) or touched partly by a few (at most
+// 2 ceil(len / b) + 2 rows per record: shared-memory atomic adds of the overlap). Each warp rasterises its own 256 rows -- lane r
+// takes the r-th record that can touch them -- so after the block barriers of the staging everything is warp-synchronous. A row
+// then costs two shared-memory reads and its store, against ~87 instructions per row of the per-row cursor path.
 // Same integers as the cursor path (total overlap, window length), so the same doubles come out.
 #define MG_COV_RASTER_MAX_BINS 8 // windows of up to this many bins (len <= 8 b): beyond that a record touches too many rows
 #define MG_SF_BLOCK_ROWS (MG_SP_THREADS * MG_SF_ROWS)
 #define MG_SF_WARP_ROWS (32 * MG_SF_ROWS)
-#define MG_CR_PAD(j) ((j) + ((j) >> 5)) // one pad word per 32: lane-strided and 8-per-lane accesses are both conflict-free
 #define MG_COV_QT 256 // window lengths below this take their quotient total / len from a per-block table
 struct CovRaster {
-	double qt[MG_COV_QT]; // qt[t] = (double)t / (double)len: len + 1 possible results, one division per thread instead of one per row
-	// per warp: overlap collected from partly covering records, then the row's total / +len at the first completely covered
-	// row of a record, -len after the last
-	int acc[MG_SP_THREADS / 32][MG_CR_PAD(MG_SF_WARP_ROWS) + 1];
-	int diff[MG_SP_THREADS / 32][MG_CR_PAD(MG_SF_WARP_ROWS + 1) + 1];
+	double qt[MG_COV_QT];                              // qt[t] = (double)t / (double)len
+	int acc[MG_SP_THREADS / 32][MG_SF_WARP_ROWS];      // per warp: the rows' total overlap
 };
 
 __device__ __forceinline__ int mg_floordiv_i(int x, const CovDiv &d)
@@ -1078,18 +1078,14 @@ __device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, i
 	const int row0 = warp * MG_SF_WARP_ROWS, wrows = min(MG_SF_WARP_ROWS, g.nrows - row0);
 	if (wrows <= 0)
 		return;
-	int *acc = cr.acc[warp], *diff = cr.diff[warp];
+	int *acc = cr.acc[warp];
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
-		acc[MG_CR_PAD(lane + 32 * k)] = 0;
-		diff[MG_CR_PAD(lane + 32 * k)] = 0;
-	}
-	if (lane == 0)
-		diff[MG_CR_PAD(MG_SF_WARP_ROWS)] = 0;
+	for (int k = 0; k < MG_SF_ROWS; ++k)
+		acc[lane + 32 * k] = 0;
 	__syncwarp();
 	if (n > 0) {
 		const int A = row0 * bsz, B = (row0 + wrows - 1) * bsz + len; // hull of the warp's windows
-		int lo = 1, hi = n + 1;                                    // first staged record with end > A (the right sentinel qualifies)
+		int lo = 1, hi = n + 1;                                        // first staged record with end > A (the right sentinel qualifies)
 		while (lo < hi) {
 			const int mid = (lo + hi) >> 1;
 			if (sm.end[mid] > A)
@@ -1109,36 +1105,16 @@ __device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, i
 			const int fhi = min(jhi, mg_floordiv_i(e - len, b)); // j b + len <= e
 			int p1 = jhi, p2 = jhi + 1; // partly covered rows: [jlo, p1] and [p2, jhi]
 			if (flo <= fhi) {
-				atomicAdd(&diff[MG_CR_PAD(flo)], len);
-				atomicAdd(&diff[MG_CR_PAD(fhi + 1)], -len);
+				for (int j = flo; j <= fhi; ++j) // no other record touches these rows
+					acc[j] = len;
 				p1 = flo - 1;
 				p2 = fhi + 1;
 			}
 			for (int j = jlo; j <= p1; ++j)
-				atomicAdd(&acc[MG_CR_PAD(j)], min(j * bsz + len, e) - max(j * bsz, s));
+				atomicAdd(&acc[j], min(j * bsz + len, e) - max(j * bsz, s));
 			for (int j = p2; j <= jhi; ++j)
-				atomicAdd(&acc[MG_CR_PAD(j)], min(j * bsz + len, e) - max(j * bsz, s));
+				atomicAdd(&acc[j], min(j * bsz + len, e) - max(j * bsz, s));
 		}
-	}
-	__syncwarp();
-	{ // prefix sum of the difference array: 8 consecutive entries per lane, a shuffle scan of the lane totals
-		int v[MG_SF_ROWS], sum = 0;
-#pragma unroll
-		for (int u = 0; u < MG_SF_ROWS; ++u) {
-			sum += diff[MG_CR_PAD(lane * MG_SF_ROWS + u)];
-			v[u] = sum;
-		}
-		int incl = sum;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const int o = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= d)
-				incl += o;
-		}
-		const int before = incl - sum;
-#pragma unroll
-		for (int u = 0; u < MG_SF_ROWS; ++u)
-			acc[MG_CR_PAD(lane * MG_SF_ROWS + u)] += before + v[u];
 	}
 	__syncwarp();
 	out += row0;
@@ -1146,7 +1122,7 @@ __device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, i
 	for (int k = 0; k < MG_SF_ROWS; ++k) {
 		const int j = lane + 32 * k;
 		if (j < wrows) {
-			const int total = acc[MG_CR_PAD(j)];
+			const int total = acc[j];
 			mg_st_stream(out + j, len < MG_COV_QT ? cr.qt[total] : (total == 0 ? 0. : (total == len ? 1. : (double)total / (double)len)));
 		}
 	}
@@ -1158,18 +1134,13 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_coverage_mer
 	__shared__ CovRaster cr;
 	SfGrid g;
 	int n;
-	const int grid = mg_sf_grid_setup(q, sm, q.table, false, g, n); // block-uniform
+	const int grid = mg_sf_grid_setup(q, sm, q.table, false, g, n, cr.qt, MG_COV_QT); // block-uniform
 	if (grid == 2) {
 		mg_coverage_rows_search(q);
 		return;
 	}
 	if (grid == 1) {
 		if (q.raster && (int64_t)g.len <= MG_COV_RASTER_MAX_BINS * q.rows.binsize && (int64_t)MG_SF_BLOCK_ROWS * q.rows.binsize + g.len < MG_SF_RANGE) {
-			if (g.len < MG_COV_QT) { // the len + 1 possible quotients, one division per thread instead of one per row
-				if ((int)threadIdx.x <= g.len)
-					cr.qt[threadIdx.x] = (double)(int)threadIdx.x / (double)g.len;
-				__syncthreads();
-			}
 			mg_cov_raster(sm, cr, n, g, q.div, q.out + (int64_t)blockIdx.x * MG_SF_BLOCK_ROWS);
 			return;
 		}
