@@ -102,6 +102,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		ctx->stage_slots = (int)value;
 		return 0;
 	}
+	if (name && !strcmp(name, "hist_red")) {
+		ctx->hist_red = value != 0;
+		return 0;
+	}
 	if (name && !strcmp(name, "cov_raster")) {
 		ctx->cov_raster = value != 0;
 		return 0;
@@ -1806,11 +1810,16 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 			if (pass == 0) {
 				if (mg_div_up(tiles, blocks) * 16 > 65535)
 					continue;
-				MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-				k_segs_hist<uint16_t><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+				if (ctx->hist_red) {
+					MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+					k_segs_hist<uint16_t, true><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+				} else {
+					MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+					k_segs_hist<uint16_t, false><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+				}
 			} else {
-				MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-				k_segs_hist<uint32_t><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
+				MG_CUDA(ctx, cudaFuncSetAttribute(k_segs_hist<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				k_segs_hist<uint32_t, false><<<(unsigned)blocks, MG_HIST_THREADS, smem, st>>>(tab, ft, (unsigned long long *)d_counts);
 			}
 			break;
 		}

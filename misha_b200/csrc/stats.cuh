@@ -471,7 +471,10 @@ __device__ __forceinline__ void mg_smem_inc<uint16_t>(uint32_t a)
 
 // C = counter type of the private columns: uint16_t halves the shared memory (twice the resident warps) and is used whenever
 // no thread can see more than 65535 values (the host checks tiles per block x 16).
-template <typename C>
+// PAIR (with C = uint16_t): the 16-bit counters of warps w and w + nwarps / 2 share 32-bit words (low / high half), and a count is
+// ONE shared-memory reduction `red.shared.add.u32` of 1 or 65536 -- no load whose latency the thread has to wait out before
+// its store, half the shared-memory instructions -- instead of a 16-bit load / add / store; same bytes of shared memory.
+template <typename C, bool PAIR>
 __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st, const FloatThr ft, unsigned long long *counts)
 {
 	extern __shared__ __align__(16) uint32_t hsmem[];
@@ -481,14 +484,30 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 	float *P = reinterpret_cast<float *>(hsmem);
 	const int thr_words = (nb + 3 + 3) & ~3;
 	C *hall = reinterpret_cast<C *>(hsmem + thr_words), *h = hall + warp * nb * 32;
+	uint32_t *hw = hsmem + thr_words; // PAIR: [nwarps / 2][nb][32] words
+	const int npairs = nwarps >> 1, pair = warp % npairs, half = warp / npairs;
 	for (int t = threadIdx.x; t <= nb + 2; t += blockDim.x)
 		P[t] = t == 0 ? __int_as_float(0xff800000) : (t == nb + 2 ? __int_as_float(0x7f800000) : ft.thr[t - 1]);
-	for (int t = lane; t < nb * 32; t += 32)
-		h[t] = 0;
+	if (PAIR) {
+		for (int t = threadIdx.x; t < npairs * nb * 32; t += blockDim.x)
+			hw[t] = 0;
+	} else {
+		for (int t = lane; t < nb * 32; t += 32)
+			h[t] = 0;
+	}
 	__syncthreads();
-	constexpr uint32_t COL = 32u * sizeof(C); // bytes per bin column
+	constexpr uint32_t COL = PAIR ? 128u : 32u * sizeof(C); // bytes per bin column
 	const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(P);
-	const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(h) + (uint32_t)sizeof(C) * lane - COL; // column of bin c - 1 at hbase + COL c
+	// column of bin c - 1 at hbase + COL c
+	const uint32_t hbase = PAIR ? (uint32_t)__cvta_generic_to_shared(hw + pair * nb * 32) + 4u * lane - COL
+								: (uint32_t)__cvta_generic_to_shared(h) + (uint32_t)sizeof(C) * lane - COL;
+	const uint32_t one = 1u << (16 * half);
+	auto count_bin = [&](uint32_t addr) {
+		if (PAIR)
+			asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(one) : "memory");
+		else
+			mg_smem_inc<C>(addr);
+	};
 	if (ft.uniform) {
 		const float b0 = ft.b0, inv = ft.inv_binsize, top = (float)(nb + 1);
 		mg_stream_segtable(st, [&](float v) {
@@ -503,20 +522,27 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 					--c;
 			}
 			if ((unsigned)(c - 1) < (unsigned)nb)
-				mg_smem_inc<C>(hbase + COL * c);
+				count_bin(hbase + COL * c);
 		});
 	} else {
 		mg_stream_segtable(st, [&](float v) {
 			const int b = mg_float_bin(P + 1, nb, v);
 			if (b >= 0)
-				mg_smem_inc<C>(hbase + COL * (b + 1));
+				count_bin(hbase + COL * (b + 1));
 		});
 	}
 	__syncthreads();
 	for (int b = warp; b < nb; b += nwarps) {
 		unsigned long long c = 0;
-		for (int w = 0; w < nwarps; ++w)
-			c += hall[(w * nb + b) * 32 + lane];
+		if (PAIR) {
+			for (int p = 0; p < npairs; ++p) {
+				const uint32_t w = hw[(p * nb + b) * 32 + lane];
+				c += (w & 0xffffu) + (w >> 16);
+			}
+		} else {
+			for (int w = 0; w < nwarps; ++w)
+				c += hall[(w * nb + b) * 32 + lane];
+		}
 #pragma unroll
 		for (int k = 16; k > 0; k >>= 1)
 			c += __shfl_xor_sync(0xffffffffu, c, k);

@@ -52,6 +52,9 @@ def main():
     chroms = synth.genome(args.scale)
     sizes = [s for _, s in chroms]
     ctx = gpu.Context(sizes)
+    for opt in os.environ.get("MG_OPTIONS", "").split(","):  # experiments: MG_OPTIONS=name=value,...
+        if "=" in opt:
+            ctx.set_option(opt.split("=")[0], int(opt.split("=")[1]))
     want = args.configs.split(",")
     sc = np.arange(len(chroms), dtype=np.int32)
     ss, se = np.zeros(len(chroms), np.int64), np.array(sizes, np.int64)
