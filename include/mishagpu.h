@@ -92,6 +92,9 @@ int mg_sync(mg_ctx *ctx, void *stream);
  *   "stage_slots" = n    block records a row-query thread block stages in shared memory for its quantile walks (default 5,
  *                        0 = every walk reads its record through L1; at most 12)
  *   "cov_raster" = 0     coverage over fixed-bin rows by per-row cursors instead of rasterising the records into the rows
+ *   "merge_rows" = 8     sparse / coverage merge kernels always at 8 rows per thread (default 0: 16 for fixed-bin rows whose
+ *                        thread blocks are expected to hold few records)
+ *   "hist_red" = 0       gdist over a dense track counts with a 16-bit load / add / store instead of one red.shared.add
  *   "prefetch" = 0       no L1 prefetch of block records / window lines in the row-query kernels
  *   "pwm_strict" = 1     PWM log-sum-exp with double-precision exp / log rounded to float (default: float expf / logf)
  *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 2^19)

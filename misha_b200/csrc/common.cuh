@@ -33,6 +33,7 @@ struct mg_ctx {
 	                        // Measured SLOWER than the 3-slot DMA pipeline on B200 (5.9 vs 5.3 ms for C3), hence off by default.
 	bool pwm_strict = false; // PWM strand / anchor log-sum-exp with double-precision exp / log (correctly rounded float results)
 	bool prefetch = true;    // row-query kernels prefetch their block record / window lines (off: ablation)
+	int merge_rows = 0;      // 8: merge kernels at 8 rows per thread whatever the row source (0: chosen per launch)
 	bool hist_red = true;    // gdist over a dense track: 16-bit counters of warp pairs packed in 32-bit words, one red.shared.add per value
 	bool cov_raster = true;  // coverage over a regular grid of rows: records rasterised into the block's rows (off: per-row cursors; ablation)
 	int stage_slots = 5;     // block records a row-query thread block stages in shared memory (0: walk them through L1; ablation)

@@ -500,18 +500,26 @@ __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery 
 //     search covers unsorted rows);
 //   * blocks that span chromosomes, hold more than MG_SF_CAP records or do not fit 32-bit offsets take the per-row
 //     search path (mg_sparse_row / the coverage search) over the row's whole chromosome.
-#define MG_SF_ROWS 8
+// ROWS (template parameter of everything below) = rows per thread: a block takes 256 x ROWS rows. The per-block set-up -- scope
+// lookup, coarse-index lookups, staging the records: three dependent memory round trips behind two barriers -- is paid once per
+// block, so more rows per block amortise it (C4: 8 -> 16 rows per thread took nearest from 0.44 to 0.39 ms, coverage from 0.41
+// to 0.32 ms); the host picks the largest ROWS whose expected record count per block stays well inside MG_SF_CAP.
+#ifndef MG_SF_CAP
 #define MG_SF_CAP 1024
+#endif
 #define MG_SF_SENT (1 << 30) // sentinel coordinate; real offsets stay within +-MG_SF_RANGE so distances never overflow
 #define MG_SF_RANGE (1 << 28)
 
 // Staged records live at indices 1..n between sentinels: [0] = {-SENT, -SENT}, [n+1] = [n+2] = {+SENT, +SENT}. With them
 // "first record with end > a" always exists, the neighbours lo - 1 / lo + 1 can be read unguarded, and a sentinel never
 // wins the nearest-neighbour comparison against a real record.
-struct SfSmem {
+// VAL = false (coverage: interval sets carry no values) drops the value array and its 4 KB of shared memory.
+template <bool VAL>
+struct SfSmemT {
+	static constexpr bool has_val = VAL;
 	int start[MG_SF_CAP + 3];
 	int end[MG_SF_CAP + 3];
-	float val[MG_SF_CAP + 3];
+	float val[VAL ? MG_SF_CAP + 3 : 1];
 	int64_t red_min[MG_SP_THREADS / 32], red_max[MG_SP_THREADS / 32];
 	int red_clo[MG_SP_THREADS / 32], red_chi[MG_SP_THREADS / 32];
 	int64_t origin; // staged positions are relative to the block hull's start
@@ -523,23 +531,24 @@ struct SfSmem {
 	int64_t g_origin, g_first;
 	int g_chrom, g_len, g_nrows, g_n, g_status;
 };
+typedef SfSmemT<true> SfSmem;
 
-// rows of lane l: block_base + warp * 32 * MG_SF_ROWS + l + 32 k
-template <typename Q>
+// rows of lane l: block_base + warp * 32 * ROWS + l + 32 k
+template <int ROWS, typename Q>
 __device__ __forceinline__ int64_t mg_sf_row(const Q &q, int k)
 {
-	return (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + (int64_t)(threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31) + 32 * k;
+	return (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS) + (int64_t)(threadIdx.x >> 5) * (32 * ROWS) + (threadIdx.x & 31) + 32 * k;
 }
 
 // windows of this lane's rows; bit k of the result = row k exists and its window is non-empty
-template <typename Q>
-__device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_SF_ROWS], int64_t (&we)[MG_SF_ROWS], int (&chrom)[MG_SF_ROWS])
+template <int ROWS, typename Q>
+__device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[ROWS], int64_t (&we)[ROWS], int (&chrom)[ROWS])
 {
 	unsigned ok = 0;
-	const int64_t i0 = mg_sf_row(q, 0);
+	const int64_t i0 = mg_sf_row<ROWS>(q, 0);
 	if (q.rows.kind == 0) {
 #pragma unroll
-		for (int k = 0; k < MG_SF_ROWS; ++k) {
+		for (int k = 0; k < ROWS; ++k) {
 			const int64_t i = i0 + 32 * k;
 			chrom[k] = 0;
 			ws[k] = we[k] = 0;
@@ -557,7 +566,7 @@ __device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_S
 	const int64_t binsize = q.rows.binsize, step = 32 * binsize;
 	int64_t r = q.first + i0, kscope = -1, row1 = 0, sstart = 0, send = 0, csize = 0, coord = 0;
 	int c = 0;
-	if (i0 + 32 * (MG_SF_ROWS - 1) < q.count) {
+	if (i0 + 32 * (ROWS - 1) < q.count) {
 		// Regular case: all rows of the lane are interior rows of ONE scope interval and no window is clamped. Then row k's
 		// window is the first row's shifted by k * 32 bins: one scope lookup and two additions per row.
 		kscope = mg_scope_of_row(q.rows, r);
@@ -568,21 +577,21 @@ __device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_S
 		c = __ldg(q.rows.schrom + kscope);
 		csize = __ldg(q.chrom_sizes + c);
 		coord = (__ldg(q.rows.sbin0 + kscope) + (r - row0)) * binsize;
-		const int64_t last = coord + (MG_SF_ROWS - 1) * step;
+		const int64_t last = coord + (ROWS - 1) * step;
 		const int64_t w0 = coord + q.sshift, len = binsize + q.eshift - q.sshift;
-		if (r > row0 && r + 32 * (MG_SF_ROWS - 1) < row1 - 1 && w0 >= 0 && last + binsize + q.eshift <= csize && len > 0) {
+		if (r > row0 && r + 32 * (ROWS - 1) < row1 - 1 && w0 >= 0 && last + binsize + q.eshift <= csize && len > 0) {
 #pragma unroll
-			for (int k = 0; k < MG_SF_ROWS; ++k) {
+			for (int k = 0; k < ROWS; ++k) {
 				chrom[k] = c;
 				ws[k] = w0 + k * step;
 				we[k] = ws[k] + len;
 			}
-			return (1u << MG_SF_ROWS) - 1u;
+			return ROWS == 32 ? 0xffffffffu : (1u << (ROWS & 31)) - 1u;
 		}
 		kscope = -1; // fall through to the general path
 	}
 #pragma unroll 1
-	for (int k = 0; k < MG_SF_ROWS; ++k, r += 32, coord += step) {
+	for (int k = 0; k < ROWS; ++k, r += 32, coord += step) {
 		int64_t wsk = 0, wek = 0;
 		bool okk = false;
 		if (i0 + 32 * k < q.count) {
@@ -603,7 +612,7 @@ __device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_S
 		}
 		// ws[] / we[] must stay in registers: write them with compile-time indices
 #pragma unroll
-		for (int j = 0; j < MG_SF_ROWS; ++j)
+		for (int j = 0; j < ROWS; ++j)
 			if (j == k) {
 				chrom[j] = c;
 				ws[j] = wsk;
@@ -616,13 +625,14 @@ __device__ __forceinline__ unsigned mg_sf_windows(const Q &q, int64_t (&ws)[MG_S
 }
 
 // block hull -> record slice -> shared memory. Every thread passes the hull of its own valid rows.
-__device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table, unsigned okmask, const int64_t (&ws)[MG_SF_ROWS],
-											 const int64_t (&we)[MG_SF_ROWS], const int (&chrom)[MG_SF_ROWS], bool want_val)
+template <int ROWS, typename SM>
+__device__ __forceinline__ void mg_sf_stage(SM &sm, const SparseChrom *table, unsigned okmask, const int64_t (&ws)[ROWS],
+											 const int64_t (&we)[ROWS], const int (&chrom)[ROWS], bool want_val)
 {
 	int64_t mn = INT64_MAX, mx = INT64_MIN;
 	int clo = INT_MAX, chi = INT_MIN;
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k)
+	for (int k = 0; k < ROWS; ++k)
 		if ((okmask >> k) & 1u) {
 			mn = min(mn, ws[k]);
 			mx = max(mx, we[k]);
@@ -704,7 +714,8 @@ __device__ __forceinline__ void mg_sf_stage(SfSmem &sm, const SparseChrom *table
 			}
 			sm.start[t] = st;
 			sm.end[t] = en;
-			sm.val[t] = v;
+			if (SM::has_val)
+				sm.val[t] = v;
 		}
 	}
 	__syncthreads();
@@ -733,12 +744,13 @@ __device__ __forceinline__ int mg_sf_advance(const int *__restrict__ end, int n,
 
 // the per-row search path of a block the merge kernel cannot stage (windows are recomputed: indexing the caller's ws[] / we[]
 // by a loop counter would put them in local memory)
+template <int ROWS>
 __device__ __forceinline__ void mg_sparse_rows_search(const SparseQuery &q)
 {
 	RowCache rc;
 #pragma unroll 1
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
-		const int64_t i = mg_sf_row(q, k);
+	for (int k = 0; k < ROWS; ++k) {
+		const int64_t i = mg_sf_row<ROWS>(q, k);
 		if (i >= q.count)
 			break;
 		int c;
@@ -761,13 +773,13 @@ struct SfGrid {
 	int nrows;      // rows of this block
 };
 
-template <typename Q>
+template <int ROWS, typename Q>
 __device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
 {
 	if (q.rows.kind != 1)
 		return false;
-	const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS);
-	const int64_t nrows = min((int64_t)(MG_SP_THREADS * MG_SF_ROWS), q.count - i0);
+	const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS);
+	const int64_t nrows = min((int64_t)(MG_SP_THREADS * ROWS), q.count - i0);
 	const int64_t r0 = q.first + i0, r1 = r0 + nrows - 1;
 	const int64_t k = mg_scope_of_row(q.rows, r0);
 	const int64_t row0 = __ldg(q.rows.srow0 + k), row1 = __ldg(q.rows.srow0 + k + 1);
@@ -789,8 +801,8 @@ __device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
 // 2 = grid whose records do not fit the stage (count or 32-bit range): per-row search path. Warp 0 alone does the scope lookup,
 // the grid geometry and the two coarse-index lookups that bracket the records (uniform work: seven warps skip ~200
 // instructions each, they would only wait at the barrier anyway); after one barrier every thread stages its record.
-template <typename Q>
-__device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const SparseChrom *table, bool want_val, SfGrid &g, int &n_out,
+template <int ROWS, typename Q, typename SM>
+__device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SM &sm, const SparseChrom *table, bool want_val, SfGrid &g, int &n_out,
 												double *qt = nullptr, int qt_size = 0)
 {
 	if (q.rows.kind != 1)
@@ -802,7 +814,7 @@ __device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const Sp
 		gg.len = gg.nrows = 0;
 		int status = 0, n = 0;
 		int64_t first = 0;
-		if (mg_sf_grid_block(q, gg)) {
+		if (mg_sf_grid_block<ROWS>(q, gg)) {
 			status = 1;
 			const SparseChrom ch = table[gg.chrom];
 			if (ch.n > 0) {
@@ -857,7 +869,8 @@ __device__ __forceinline__ int mg_sf_grid_setup(const Q &q, SfSmem &sm, const Sp
 			}
 			sm.start[t] = st;
 			sm.end[t] = en;
-			sm.val[t] = v;
+			if (SM::has_val)
+				sm.val[t] = v;
 		}
 	}
 	n_out = n;
@@ -943,24 +956,24 @@ __device__ __forceinline__ void mg_sf_store(const SparseQuery &q, int64_t i, con
 #ifndef MG_SF_MINBLOCKS
 #define MG_SF_MINBLOCKS 8 // resident blocks per SM: barrier- and latency-bound, measured 0.77 -> 0.46 ms (nearest, C4) from 3 to 8
 #endif
-template <int F>
+template <int F, int ROWS>
 __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_sparse_merge(const SparseQuery q)
 {
 	__shared__ SfSmem sm;
 	constexpr bool SUM = F < 0 || F == MG_AVG || F == MG_SUM || F == MG_NEAREST, MM = F < 0 || F == MG_MIN || F == MG_MAX;
 	SfGrid g;
 	int n;
-	const int grid = mg_sf_grid_setup(q, sm, q.table, true, g, n); // block-uniform
+	const int grid = mg_sf_grid_setup<ROWS>(q, sm, q.table, true, g, n); // block-uniform
 	if (grid == 2) {
-		mg_sparse_rows_search(q);
+		mg_sparse_rows_search<ROWS>(q);
 		return;
 	}
 	if (grid == 1) {
-		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
-		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + j0;
+		const int j0 = (threadIdx.x >> 5) * (32 * ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
+		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS) + j0;
 		int a = j0 * (int)q.rows.binsize, lo = 1;
 #pragma unroll
-		for (int k = 0; k < MG_SF_ROWS; ++k, a += step) {
+		for (int k = 0; k < ROWS; ++k, a += step) {
 			if (j0 + 32 * k >= g.nrows)
 				break;
 			SpVals o;
@@ -969,20 +982,20 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_sparse_merge
 		}
 		return;
 	}
-	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
-	int chrom[MG_SF_ROWS];
-	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
-	mg_sf_stage(sm, q.table, okmask, ws, we, chrom, true);
+	int64_t ws[ROWS], we[ROWS];
+	int chrom[ROWS];
+	const unsigned okmask = mg_sf_windows<ROWS>(q, ws, we, chrom);
+	mg_sf_stage<ROWS>(sm, q.table, okmask, ws, we, chrom, true);
 	if (sm.mode == 0) { // rare: per-row search over the row's whole chromosome
-		mg_sparse_rows_search(q);
+		mg_sparse_rows_search<ROWS>(q);
 		return;
 	}
 	const int64_t origin = sm.origin;
 	n = sm.n;
 	int lo = 1, prev = INT_MIN;
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
-		const int64_t i = mg_sf_row(q, k);
+	for (int k = 0; k < ROWS; ++k) {
+		const int64_t i = mg_sf_row<ROWS>(q, k);
 		if (i >= q.count)
 			break;
 		SpVals o;
@@ -1000,7 +1013,8 @@ __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_sparse_merge
 
 // coverage of [a, b) by the staged source intervals: 0 / len and len / len need no divide (most rows of a fine iterator lie
 // fully outside or inside a source interval)
-__device__ __forceinline__ double mg_sf_coverage(const SfSmem &sm, int n, int &lo, int a, int b)
+template <typename SM>
+__device__ __forceinline__ double mg_sf_coverage(const SM &sm, int n, int &lo, int a, int b)
 {
 	int total = 0;
 	if (n > 0) {
@@ -1011,12 +1025,13 @@ __device__ __forceinline__ double mg_sf_coverage(const SfSmem &sm, int n, int &l
 	return total == 0 ? 0. : (total == b - a ? 1. : (double)total / (double)(b - a));
 }
 
+template <int ROWS>
 __device__ __forceinline__ void mg_coverage_rows_search(const CoverageQuery &q)
 {
 	RowCache rc;
 #pragma unroll 1
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
-		const int64_t i = mg_sf_row(q, k);
+	for (int k = 0; k < ROWS; ++k) {
+		const int64_t i = mg_sf_row<ROWS>(q, k);
 		if (i >= q.count)
 			break;
 		double cov = mg_nan();
@@ -1055,12 +1070,11 @@ __device__ __forceinline__ void mg_coverage_rows_search(const CoverageQuery &q)
 // then costs two shared-memory reads and its store, against ~87 instructions per row of the per-row cursor path.
 // Same integers as the cursor path (total overlap, window length), so the same doubles come out.
 #define MG_COV_RASTER_MAX_BINS 8 // windows of up to this many bins (len <= 8 b): beyond that a record touches too many rows
-#define MG_SF_BLOCK_ROWS (MG_SP_THREADS * MG_SF_ROWS)
-#define MG_SF_WARP_ROWS (32 * MG_SF_ROWS)
 #define MG_COV_QT 256 // window lengths below this take their quotient total / len from a per-block table
+template <int ROWS>
 struct CovRaster {
 	double qt[MG_COV_QT];                              // qt[t] = (double)t / (double)len
-	int acc[MG_SP_THREADS / 32][MG_SF_WARP_ROWS];      // per warp: the rows' total overlap
+	int acc[MG_SP_THREADS / 32][(32 * ROWS)];      // per warp: the rows' total overlap
 };
 
 __device__ __forceinline__ int mg_floordiv_i(int x, const CovDiv &d)
@@ -1072,15 +1086,16 @@ __device__ __forceinline__ int mg_floordiv_i(int x, const CovDiv &d)
 }
 __device__ __forceinline__ int mg_ceildiv_i(int x, const CovDiv &d) { return -mg_floordiv_i(-x, d); }
 
-__device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, int n, const SfGrid &g, const CovDiv &b, double *__restrict__ out)
+template <int ROWS, typename SM>
+__device__ __forceinline__ void mg_cov_raster(const SM &sm, CovRaster<ROWS> &cr, int n, const SfGrid &g, const CovDiv &b, double *__restrict__ out)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, len = g.len, bsz = b.b;
-	const int row0 = warp * MG_SF_WARP_ROWS, wrows = min(MG_SF_WARP_ROWS, g.nrows - row0);
+	const int row0 = warp * (32 * ROWS), wrows = min((32 * ROWS), g.nrows - row0);
 	if (wrows <= 0)
 		return;
 	int *acc = cr.acc[warp];
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k)
+	for (int k = 0; k < ROWS; ++k)
 		acc[lane + 32 * k] = 0;
 	__syncwarp();
 	if (n > 0) {
@@ -1119,7 +1134,7 @@ __device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, i
 	__syncwarp();
 	out += row0;
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
+	for (int k = 0; k < ROWS; ++k) {
 		const int j = lane + 32 * k;
 		if (j < wrows) {
 			const int total = acc[j];
@@ -1128,47 +1143,48 @@ __device__ __forceinline__ void mg_cov_raster(const SfSmem &sm, CovRaster &cr, i
 	}
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(MG_SP_THREADS, MG_SF_MINBLOCKS) k_coverage_merge(const CoverageQuery q)
 {
-	__shared__ SfSmem sm;
-	__shared__ CovRaster cr;
+	__shared__ SfSmemT<false> sm;
+	__shared__ CovRaster<ROWS> cr;
 	SfGrid g;
 	int n;
-	const int grid = mg_sf_grid_setup(q, sm, q.table, false, g, n, cr.qt, MG_COV_QT); // block-uniform
+	const int grid = mg_sf_grid_setup<ROWS>(q, sm, q.table, false, g, n, cr.qt, MG_COV_QT); // block-uniform
 	if (grid == 2) {
-		mg_coverage_rows_search(q);
+		mg_coverage_rows_search<ROWS>(q);
 		return;
 	}
 	if (grid == 1) {
-		if (q.raster && (int64_t)g.len <= MG_COV_RASTER_MAX_BINS * q.rows.binsize && (int64_t)MG_SF_BLOCK_ROWS * q.rows.binsize + g.len < MG_SF_RANGE) {
-			mg_cov_raster(sm, cr, n, g, q.div, q.out + (int64_t)blockIdx.x * MG_SF_BLOCK_ROWS);
+		if (q.raster && (int64_t)g.len <= MG_COV_RASTER_MAX_BINS * q.rows.binsize && (int64_t)(MG_SP_THREADS * ROWS) * q.rows.binsize + g.len < MG_SF_RANGE) {
+			mg_cov_raster<ROWS>(sm, cr, n, g, q.div, q.out + (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS));
 			return;
 		}
-		const int j0 = (threadIdx.x >> 5) * (32 * MG_SF_ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
-		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * MG_SF_ROWS) + j0;
+		const int j0 = (threadIdx.x >> 5) * (32 * ROWS) + (threadIdx.x & 31), step = 32 * (int)q.rows.binsize;
+		const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS) + j0;
 		int a = j0 * (int)q.rows.binsize, lo = 1;
 #pragma unroll
-		for (int k = 0; k < MG_SF_ROWS; ++k, a += step) {
+		for (int k = 0; k < ROWS; ++k, a += step) {
 			if (j0 + 32 * k >= g.nrows)
 				break;
 			mg_st_stream(q.out + i0 + 32 * k, mg_sf_coverage(sm, n, lo, a, a + g.len));
 		}
 		return;
 	}
-	int64_t ws[MG_SF_ROWS], we[MG_SF_ROWS];
-	int chrom[MG_SF_ROWS];
-	const unsigned okmask = mg_sf_windows(q, ws, we, chrom);
-	mg_sf_stage(sm, q.table, okmask, ws, we, chrom, false);
+	int64_t ws[ROWS], we[ROWS];
+	int chrom[ROWS];
+	const unsigned okmask = mg_sf_windows<ROWS>(q, ws, we, chrom);
+	mg_sf_stage<ROWS>(sm, q.table, okmask, ws, we, chrom, false);
 	if (sm.mode == 0) {
-		mg_coverage_rows_search(q);
+		mg_coverage_rows_search<ROWS>(q);
 		return;
 	}
 	const int64_t origin = sm.origin;
 	n = sm.n;
 	int lo = 1, prev = INT_MIN;
 #pragma unroll
-	for (int k = 0; k < MG_SF_ROWS; ++k) {
-		const int64_t i = mg_sf_row(q, k);
+	for (int k = 0; k < ROWS; ++k) {
+		const int64_t i = mg_sf_row<ROWS>(q, k);
 		if (i >= q.count)
 			break;
 		double cov = mg_nan();

@@ -477,7 +477,12 @@ def test_coverage_rasterised_grid_blocks():
             rows = ctx2.rows_fixedbin(binsize, scope_c, scope_s, scope_e)
             c, s, e, _ = rows.coords()
             for sshift, eshift in ((0, 0), (-binsize, binsize), (3, 2 * binsize + 5), (-4 * binsize, 3 * binsize), (-20 * binsize, 20 * binsize), (5, -3)):
-                got = iv.coverage(rows, sshift, eshift)
+                got = iv.coverage(rows, sshift, eshift)                      # 16 rows per thread (few records per block)
+                ctx2.set_option("merge_rows", 8)
+                try:
+                    assert_same(iv.coverage(rows, sshift, eshift), got, f"8 vs 16 rows per thread, bin {binsize} shift {sshift},{eshift}")
+                finally:
+                    ctx2.set_option("merge_rows", 0)
                 ctx2.set_option("cov_raster", 0)
                 try:
                     cur = iv.coverage(rows, sshift, eshift)
@@ -488,5 +493,49 @@ def test_coverage_rasterised_grid_blocks():
                     m = c == cid
                     assert_same(got[m], port.coverage(srcs[cid][0], srcs[cid][1], sizes[cid], s[m], e[m], sshift, eshift),
                                 f"raster vs oracle chrom{cid} bin {binsize} shift {sshift},{eshift}")
+    finally:
+        ctx2.close()
+
+
+def test_sparse_merge_rows_per_thread_fixed_bin():
+    """Fixed-bin rows over a sparse track: the merge kernel at 16 rows per thread (chosen when a block is expected to hold few
+    records) and at 8 give the same columns, equal to the oracle; scope intervals that start off the grid, shifts, a
+    chromosome without records."""
+    sizes = [900000, 120000, 50000]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(515)
+        t = gpu.SparseTrack(ctx2)
+        recs = []
+        for cid, size in enumerate(sizes):
+            n = (2500, 300, 0)[cid]
+            st = np.sort(rng.choice(size // 40 - 2, n, replace=False)) * 40
+            en = st + rng.integers(1, 40, n)
+            v = rng.random(n).astype(np.float32)
+            v[rng.random(n) < 0.04] = np.nan
+            t.stage(cid, st, en, v)
+            recs.append((st, en, v))
+        scope_c = np.array([0, 0, 1, 2], np.int32)
+        scope_s = np.array([11, 500003, 0, 7], np.int64)
+        scope_e = np.array([480000, 900000, 120000, 50000], np.int64)
+        names = ["nearest", "avg", "max", "size"]
+        for binsize in (20, 33):
+            rows = ctx2.rows_fixedbin(binsize, scope_c, scope_s, scope_e)
+            c, s, e, _ = rows.coords()
+            for sshift, eshift in ((0, 0), (-90, 140)):
+                got = t.window(rows, names, sshift, eshift)
+                one = t.window(rows, ["nearest"], sshift, eshift)[0]
+                ctx2.set_option("merge_rows", 8)
+                try:
+                    ref8 = t.window(rows, names, sshift, eshift)
+                finally:
+                    ctx2.set_option("merge_rows", 0)
+                assert_same(one, got[0], "single-function kernel")
+                for k, name in enumerate(names):
+                    assert_same(got[k], ref8[k], f"{name}: 16 vs 8 rows per thread, bin {binsize}")
+                    for cid in range(3):
+                        m = c == cid
+                        exp = port.sparse_window(*recs[cid], sizes[cid], s[m], e[m], sshift, eshift, 0.5, funcs=(name,))[name]
+                        assert_same(got[k][m], exp, f"{name} chrom{cid} bin {binsize} shift {sshift}")
     finally:
         ctx2.close()
