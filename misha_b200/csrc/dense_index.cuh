@@ -398,14 +398,16 @@ __device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint
 #define MG_SD_DIRECT_BINS 8
 // Resident blocks per SM, measured on B200 at the C3 shape: the kernel is bound by memory latency, so more warps win even at the
 // price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several (0.695 -> 0.616 ms for avg + max + quantile).
+#ifndef MG_RQ_THREADS
+#define MG_RQ_THREADS 256
+#endif
 #ifdef MG_RQ_MB // build-time override (tuning)
 #define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) MG_RQ_MB
 #else
-#define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) ((SD) ? 4 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 8 : 6))
+#define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) (((SD) ? 1024 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 2048 : 1536)) / MG_RQ_THREADS)
 #endif
 // the levels of a block record (the pos_of_rank half is touched at one or two places per row: not worth prefetching)
 #define MG_PREFETCH_LINES (MG_BW_POS_OFFSET / 128)
-#define MG_RQ_THREADS 256
 #define MG_STAGE_BLK_BITS 21
 // Staged block records (Q): the 256 rows of a thread block are neighbours in position when the rows are sorted (what the scanner
 // produces), so between them they need the records of a handful of consecutive blocks. The thread block finds the range of

@@ -710,7 +710,7 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		k_dense_prefix<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
 	} else if (!ctx->force_sweep) {
 		// everything else comes from the index structures, one thread per row
-		const unsigned grid = (unsigned)mg_div_up(q.count, 256);
+		const unsigned grid = (unsigned)mg_div_up(q.count, MG_RQ_THREADS);
 		const bool want_sd = q.out[MG_STDDEV] != nullptr;
 		const size_t stage_bytes = q.nq > 0 && q.use_bw ? (size_t)q.stage_slots * MG_BW_STAGE_BYTES : 0;
 		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0) | (want_sd ? 8 : 0);
