@@ -1207,6 +1207,50 @@ static int mg_merge_rows_per_thread(const mg_ctx *ctx, const mg_rows *rows, int6
 	return per_block <= MG_SF_CAP / 2 ? 16 : 8;
 }
 
+// The regular-grid blocks of a merge-kernel launch (GridTable, sparse.cuh): the predicate of mg_sf_grid_block evaluated on the
+// host. Every condition is a lower or an upper bound on the block index, so per scope interval the qualifying blocks form one range.
+static void mg_make_grid_table(const mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, int rpt,
+							   GridTable &gt)
+{
+	memset(&gt, 0, sizeof(gt));
+	gt.n = -1;
+	const RowSrc &rs = rows->src;
+	if (rs.kind != 1 || rs.nscope > MG_SCOPE_INLINE)
+		return;
+	gt.n = 0;
+	const int64_t R = (int64_t)MG_SP_THREADS * rpt, binsize = rs.binsize, len = binsize + eshift - sshift;
+	if (len <= 0 || len > MG_SF_RANGE || count <= 0)
+		return;
+	gt.len = (int)len;
+	gt.step = R * binsize;
+	const int64_t nblocks = mg_div_up(count, R);
+	for (int64_t k = 0; k < rs.nscope && gt.n < MG_SCOPE_INLINE; ++k) {
+		const int64_t row0 = rows->h_srow0[k], row1 = rows->h_srow0[k + 1], sbin0 = rows->h_sstart[k] / binsize;
+		const int64_t csize = ctx->chrom_sizes[rows->h_schrom[k]];
+		auto grid_block = [&](int64_t b) {
+			const int64_t nrows = std::min(R, count - b * R), r0 = first + b * R, r1 = r0 + nrows - 1;
+			if (!(r0 > row0 && r1 < row1 - 1))
+				return false;
+			const int64_t w0 = (sbin0 + (r0 - row0)) * binsize + sshift, span = (nrows - 1) * binsize + len;
+			return !(w0 < 0 || span > MG_SF_RANGE || w0 + span > csize);
+		};
+		// blocks whose first row lies in this scope interval
+		int64_t bf = row0 >= first ? mg_div_up(row0 - first, R) : 0, bl = row1 - 1 >= first ? (row1 - 1 - first) / R : -1;
+		bl = std::min(bl, nblocks - 1);
+		while (bf <= bl && !grid_block(bf))
+			++bf;
+		while (bl > bf && !grid_block(bl))
+			--bl;
+		if (bf > bl || bl >= (1ll << 32))
+			continue;
+		gt.bfirst[gt.n] = (unsigned)bf;
+		gt.blast[gt.n] = (unsigned)bl;
+		gt.origin0[gt.n] = (sbin0 + (first + bf * R - row0)) * binsize + sshift;
+		gt.chrom[gt.n] = rows->h_schrom[k];
+		gt.n++;
+	}
+}
+
 extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift,
 								int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *d_out, void *stream)
 {
@@ -1246,6 +1290,7 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 			nrec += c.n;
 		const int rpt = mg_merge_rows_per_thread(ctx, rows, nrec);
 		const unsigned grid = (unsigned)mg_div_up(count, MG_SP_THREADS * rpt);
+		mg_make_grid_table(ctx, rows, first, count, sshift, eshift, rpt, q.grid);
 #define MG_MERGE_CASE(F)                                                                                                 \
 	if (rpt == 16)                                                                                                      \
 		k_sparse_merge<F, 16><<<grid, MG_SP_THREADS, 0, st>>>(q);                                                        \
@@ -1294,7 +1339,9 @@ extern "C" int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, 
 		int64_t nrec = 0;
 		for (const SparseChrom &c : s->h_table)
 			nrec += c.n;
-		if (mg_merge_rows_per_thread(ctx, rows, nrec) == 16)
+		const int rpt = mg_merge_rows_per_thread(ctx, rows, nrec);
+		mg_make_grid_table(ctx, rows, first, count, sshift, eshift, rpt, q.grid);
+		if (rpt == 16)
 			k_coverage_merge<16><<<(unsigned)mg_div_up(count, MG_SP_THREADS * 16), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);
 		else
 			k_coverage_merge<8><<<(unsigned)mg_div_up(count, MG_SP_THREADS * 8), MG_SP_THREADS, 0, mg_stream(stream)>>>(q);

@@ -36,6 +36,19 @@ struct mg_ivset {
 	int64_t bytes = 0;
 };
 
+// Regular-grid thread blocks of a launch over fixed-bin rows, worked out on the host (mg_make_grid_table): per scope interval the
+// range of block indices whose rows all lie strictly inside it with unclamped windows, and the window start of the first of
+// them. A thread block finds its entry by a short search in the kernel parameters and derives its geometry with one
+// multiply-add, instead of the scope search, the 64-bit row arithmetic and the range checks of mg_sf_grid_block.
+struct GridTable {
+	int n; // entries; 0 = no regular-grid block in this launch; -1 = not worked out (long scopes): the device decides per block
+	int len;      // window length
+	int64_t step; // rows per block x bin size
+	unsigned bfirst[MG_SCOPE_INLINE], blast[MG_SCOPE_INLINE];
+	int64_t origin0[MG_SCOPE_INLINE];
+	int chrom[MG_SCOPE_INLINE];
+};
+
 struct SparseQuery {
 	RowSrc rows;
 	int64_t first, count;
@@ -47,6 +60,7 @@ struct SparseQuery {
 	int nq;
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
+	GridTable grid;
 };
 
 // src/GenomeTrack1D.h:20-30: the pairwise float accumulation the sparse reader's lse runs in record order
@@ -443,6 +457,7 @@ struct CoverageQuery {
 	double *out;
 	int raster; // regular-grid blocks rasterise their records (k_coverage_merge); 0: per-row cursors (ablation)
 	CovDiv div; // division by the fixed-bin iterator's bin size
+	GridTable grid;
 };
 
 __global__ void __launch_bounds__(MG_SP_THREADS) k_coverage(const CoverageQuery q)
@@ -780,6 +795,26 @@ __device__ __forceinline__ bool mg_sf_grid_block(const Q &q, SfGrid &g)
 		return false;
 	const int64_t i0 = (int64_t)blockIdx.x * (MG_SP_THREADS * ROWS);
 	const int64_t nrows = min((int64_t)(MG_SP_THREADS * ROWS), q.count - i0);
+	if (q.grid.n >= 0) { // the host's table
+		if (q.grid.n == 0)
+			return false;
+		const unsigned b = blockIdx.x;
+		int lo = 0, hi = q.grid.n; // last entry with bfirst <= b
+		while (hi - lo > 1) {
+			const int mid = (lo + hi) >> 1;
+			if (q.grid.bfirst[mid] <= b)
+				lo = mid;
+			else
+				hi = mid;
+		}
+		if (b < q.grid.bfirst[lo] || b > q.grid.blast[lo])
+			return false;
+		g.chrom = q.grid.chrom[lo];
+		g.origin = q.grid.origin0[lo] + (int64_t)(b - q.grid.bfirst[lo]) * q.grid.step;
+		g.len = q.grid.len;
+		g.nrows = (int)nrows;
+		return true;
+	}
 	const int64_t r0 = q.first + i0, r1 = r0 + nrows - 1;
 	const int64_t k = mg_scope_of_row(q.rows, r0);
 	const int64_t row0 = __ldg(q.rows.srow0 + k), row1 = __ldg(q.rows.srow0 + k + 1);
