@@ -700,8 +700,10 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
 		if (q.out[MG_LSE] || q.out[MG_MIN_POS] || q.out[MG_MAX_POS])
 			k_dense_ext<true><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
-		else
+		else if (ctx->force_sweep)
 			k_dense_ext<false><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
+		else // first / last only: a thread per row
+			k_dense_firstlast<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
 		MG_LAUNCH_CHECK(ctx);
 		if (!want_sum && !want_mm && !q.out[MG_STDDEV] && q.nq == 0)
 			return 0;

@@ -338,5 +338,18 @@ def test_order_dependent_functions_synthetic_ties_and_nans():
                 np.testing.assert_allclose(got[k], exp[name], rtol=2e-7, atol=0, equal_nan=True)
             else:
                 assert_same(got[k], exp[name], name)
+        # first / last alone take the thread-per-row kernel; force_sweep keeps them on the warp-per-row one
+        fl = ["first", "last", "first.pos", ("last.pos", 1)]
+        ws = np.maximum(s - 15, 0).astype(np.float64)
+        for sweep in (0, 1):
+            ctx2.set_option("force_sweep", sweep)
+            try:
+                got = t.window(rows, fl, sshift=-15, eshift=25)
+            finally:
+                ctx2.set_option("force_sweep", 0)
+            assert_same(got[0], exp["first"], f"first (sweep={sweep})")
+            assert_same(got[1], exp["last"], f"last (sweep={sweep})")
+            assert_same(got[2], exp["first.pos"], f"first.pos (sweep={sweep})")
+            assert_same(got[3], exp["last.pos"] - ws, f"last.pos relative (sweep={sweep})")
     finally:
         ctx2.close()

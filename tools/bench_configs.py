@@ -80,6 +80,26 @@ def main():
         report("C2b gsummary iterator=200 (prefix path)", ms, 4 * nb, rows2.n)
         dense.free()
 
+    if "C3x" in want:
+        # the order-dependent functions (k_dense_ext, warp per row) and stddev at the C3 shape: off the headline path, timed for the record
+        dense = gpu.DenseTrack(ctx, 20)
+        nb = 0
+        for i in range(len(chroms)):
+            b = synth.dense_bins(i, sizes[i], 20)
+            nb += len(b)
+            dense.stage(i, b)
+        counts = synth.interval_counts(chroms, int(10_000_000 * args.scale))
+        cs, ss3, se3 = [], [], []
+        for i in range(len(chroms)):
+            s3, e3 = synth.intervals(i, sizes[i], counts[i])
+            cs.append(np.full(len(s3), i, np.int32)); ss3.append(s3); se3.append(e3)
+        rows3 = ctx.rows_upload(np.concatenate(cs), np.concatenate(ss3), np.concatenate(se3))
+        out = ctx.alloc(rows3.n, np.float64)
+        for name, f in (("first", "first"), ("last.pos", "last.pos"), ("max.pos", "max.pos"), ("lse", "lse"), ("stddev", "stddev")):
+            ms = timed(torch, lambda: dense.window_dev(rows3, [f], -5000, 5000, out=[out], stream=stream), args.steps)
+            report("C3x %s, +-5 kb, 10 M intervals" % name, ms, 4 * nb + rows3.n * 28, rows3.n)
+        del dense
+
     if "C4" in want:
         sp = gpu.SparseTrack(ctx)
         iv = gpu.IntervalSet(ctx)
