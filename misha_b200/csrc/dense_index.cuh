@@ -390,6 +390,103 @@ __device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// k_dense_argext: min.pos / max.pos, one thread per row, from the same structures as min / max: the extremum m of the window
+// first (two partial groups + two sparse-table entries), then the FIRST bin holding it -- the reference's strict comparisons
+// keep the first occurrence (src/GenomeTrackFixedBin.cpp:886-905) -- in window order: the head group's bins, then the full
+// groups by a descent through the sparse tables (is m in the left 2^j groups? one lookup per halving, <= 12), then the tail
+// group's bins. A warp-per-row sweep of the C3 windows takes 8.9 ms; windows of 2^12 groups and more (not covered by the sparse
+// tables) are scanned by their thread.
+template <bool IS_MAX>
+__device__ __forceinline__ int64_t mg_first_bin_eq(const float *__restrict__ vals, int64_t lo, int64_t hi, float m)
+{
+	for (int64_t b = lo; b < hi; ++b)
+		if (__ldg(vals + b) == m)
+			return b;
+	return -1;
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ int64_t mg_arg_ext(const DenseChrom *ch, int64_t sbin, int64_t ebin)
+{
+	const float *vals = ch->vals;
+	const float seed = IS_MAX ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+	const int64_t g0 = sbin >> 3, g1 = (ebin - 1) >> 3;
+	if (g0 == g1 || g1 - g0 - 1 >= (1ll << MG_ST_LEVELS)) { // inside one group, or too long for the tables: scan
+		float m = seed;
+		int64_t at = -1;
+		for (int64_t b = sbin; b < ebin; ++b) {
+			const float v = __ldg(vals + b);
+			if (v == v && (IS_MAX ? v > m : v < m)) {
+				m = v;
+				at = b;
+			}
+		}
+		return at;
+	}
+	const int64_t gs = g0 + 1, ge = g1; // full groups
+	const float mh = mg_group_ext<IS_MAX>(vals, 8 * g0, (int)(sbin & 7), 8, seed);
+	const float mt = mg_group_ext<IS_MAX>(vals, 8 * g1, 0, (int)(ebin - 8 * g1), seed);
+	const float mf = mg_groups_ext<IS_MAX>(ch, gs, ge, seed);
+	const float m = IS_MAX ? fmaxf(mh, fmaxf(mf, mt)) : fminf(mh, fminf(mf, mt));
+	if (m == seed)
+		return -1; // no value in the window
+	if (mh == m)
+		return mg_first_bin_eq<IS_MAX>(vals, sbin, 8 * gs, m);
+	if (mf == m) {
+		int64_t lo = gs, hi = ge; // some group of [lo, hi) holds m, none before lo does
+		while (hi - lo > 1) {
+			const int j = 31 - __clz((int)(hi - lo - 1)); // 2^j < hi - lo <= 2^(j+1)
+			const float left = __ldg((IS_MAX ? ch->smax[j] : ch->smin[j]) + lo);
+			if (left == m)
+				hi = lo + (1ll << j);
+			else
+				lo += 1ll << j;
+		}
+		return mg_first_bin_eq<IS_MAX>(vals, 8 * lo, 8 * lo + 8, m);
+	}
+	return mg_first_bin_eq<IS_MAX>(vals, 8 * g1, ebin, m);
+}
+
+__global__ void __launch_bounds__(256) k_dense_argext(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	const bool ok = mg_dense_win(q, q.first + i, w);
+	int64_t mnb = -1, mxb = -1;
+	if (ok && w.ebin > w.sbin) {
+		if (w.one_bin) // assign_single_bin_value: the bin's position whatever its value (see k_dense_ext)
+			mnb = mxb = w.sbin;
+		else {
+			if (q.out[MG_MAX_POS])
+				mxb = mg_arg_ext<true>(w.ch, w.sbin, w.ebin);
+			if (q.out[MG_MIN_POS])
+				mnb = mg_arg_ext<false>(w.ch, w.sbin, w.ebin);
+		}
+	}
+	const double bs = (double)q.bin_size, ws = ok ? (double)w.ws : 0.;
+	if (q.out[MG_MAX_POS]) {
+		double p = mg_nan();
+		if (mxb >= 0) {
+			p = fmax((double)mxb * bs, ws);
+			if (q.pos_rel & (1u << MG_MAX_POS))
+				p -= ws;
+		}
+		mg_st_stream(q.out[MG_MAX_POS] + i, p);
+	}
+	if (q.out[MG_MIN_POS]) {
+		double p = mg_nan();
+		if (mnb >= 0) {
+			p = fmax((double)mnb * bs, ws);
+			if (q.pos_rel & (1u << MG_MIN_POS))
+				p -= ws;
+		}
+		mg_st_stream(q.out[MG_MIN_POS] + i, p);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_dense_rowquery: one thread per row, every function from the index structures.
 //   SUM: avg / sum / nearest / size / exists   MM: min / max   Q: quantiles
 //   SD: stddev = sqrt(M2 / (n - 1)) with M2 = S2 - S1^2 / n from the prefix sums of v and v^2. When that difference has

@@ -694,17 +694,35 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		return 0;
 	const bool want_sum = q.out[MG_AVG] || q.out[MG_SUM] || q.out[MG_NEAREST] || q.out[MG_SIZE] || q.out[MG_EXISTS];
 	const bool want_mm = q.out[MG_MIN] || q.out[MG_MAX];
-	if (mg_any_out(q.out, MG_LSE, MG_MAX_POS)) { // the order-dependent functions: their own warp-per-row kernel
+	if (mg_any_out(q.out, MG_LSE, MG_MAX_POS)) {
+		// the order-dependent functions: first / last and min.pos / max.pos by a thread per row (early exit / sparse-table descent),
+		// lse by a warp per row; force_sweep keeps everything on the warp-per-row kernel
 		const int64_t blocks_needed = mg_div_up(q.count, MG_EXT_WARPS);
 		const int64_t cap = (int64_t)ctx->sm_count * 64;
-		const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
-		if (q.out[MG_LSE] || q.out[MG_MIN_POS] || q.out[MG_MAX_POS])
-			k_dense_ext<true><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
-		else if (ctx->force_sweep)
-			k_dense_ext<false><<<grid, MG_EXT_WARPS * 32, 0, st>>>(q);
-		else // first / last only: a thread per row
-			k_dense_firstlast<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
-		MG_LAUNCH_CHECK(ctx);
+		const unsigned wgrid = (unsigned)(blocks_needed < cap ? blocks_needed : cap), tgrid = (unsigned)mg_div_up(q.count, 256);
+		if (ctx->force_sweep) {
+			if (q.out[MG_LSE] || q.out[MG_MIN_POS] || q.out[MG_MAX_POS])
+				k_dense_ext<true><<<wgrid, MG_EXT_WARPS * 32, 0, st>>>(q);
+			else
+				k_dense_ext<false><<<wgrid, MG_EXT_WARPS * 32, 0, st>>>(q);
+			MG_LAUNCH_CHECK(ctx);
+		} else {
+			if (mg_any_out(q.out, MG_FIRST, MG_LAST_POS)) {
+				k_dense_firstlast<<<tgrid, 256, 0, st>>>(q);
+				MG_LAUNCH_CHECK(ctx);
+			}
+			if (q.out[MG_MIN_POS] || q.out[MG_MAX_POS]) {
+				k_dense_argext<<<tgrid, 256, 0, st>>>(q);
+				MG_LAUNCH_CHECK(ctx);
+			}
+			if (q.out[MG_LSE]) {
+				DenseQuery ql = q; // the sweep kernel writes every order-dependent column it is given: give it lse alone
+				for (int f = MG_FIRST; f <= MG_MAX_POS; ++f)
+					ql.out[f] = nullptr;
+				k_dense_ext<true><<<wgrid, MG_EXT_WARPS * 32, 0, st>>>(ql);
+				MG_LAUNCH_CHECK(ctx);
+			}
+		}
 		if (!want_sum && !want_mm && !q.out[MG_STDDEV] && q.nq == 0)
 			return 0;
 	}
