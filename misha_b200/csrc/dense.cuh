@@ -42,6 +42,8 @@ struct DenseChrom {
 	const float *wm_sorted;   // the non-NaN values in ascending order: value of rank r
 	const uint32_t *wm_ckpt[7]; // rank keys in the order ENTERING levels 4, 8, ..., 28: a walk whose range shrank to <= 8 finishes here
 	const uint8_t *bw;        // block-local wavelet matrices (dense_blockwm.cuh), one record per half-overlapping block
+	// lse pyramid (dense_index.cuh): plse[j][i] = log-sum-exp (double) of the non-NaN bins [8^(j+1) i, 8^(j+1) (i + 1)), -inf when none
+	const double *plse[MG_PYR_MAX];
 };
 
 struct mg_dense {

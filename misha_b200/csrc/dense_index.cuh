@@ -390,6 +390,82 @@ __device__ __noinline__ void mg_wm_select(const DenseChrom *ch, uint32_t l, uint
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// lse pyramid: fan-out 8 like the min / max pyramids, entries = log-sum-exp of their 8 children in double. A window decomposes
+// into <= 7 head + <= 7 tail entries per level (at most ~45 terms for the 517 bins of a C3 window instead of 517), and
+// lse(window) = M + log(sum exp(term - M)) over those terms with M their maximum -- every term is exact to double rounding,
+// so the result equals the direct sum's to ~1e-15 before the cast to float. One thread per row.
+template <typename T>
+__global__ void __launch_bounds__(256) k_lse_build(const T *__restrict__ child, int64_t nchild, double *__restrict__ parent, int64_t nparent)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nparent)
+		return;
+	double v[8], m = -INFINITY;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const int64_t c = i * 8 + j;
+		const double x = c < nchild ? (double)child[c] : -INFINITY;
+		v[j] = x == x ? x : -INFINITY; // NaN bins hold no value
+		m = fmax(m, v[j]);
+	}
+	double s = 0;
+	if (m > -INFINITY) {
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			s += exp(v[j] - m); // exp(-inf) = 0
+	}
+	parent[i] = m > -INFINITY ? m + log(s) : -INFINITY;
+}
+
+// calls f(term) for every term of the decomposition of bins [lo, hi) (lo < hi), NaN bins included (as NaN)
+template <typename F>
+__device__ __forceinline__ void mg_lse_terms(const DenseChrom *ch, int64_t lo, int64_t hi, F f)
+{
+	for (int level = 0; lo < hi; ++level) {
+		const float *pv = ch->vals;
+		const double *pd = level ? ch->plse[level - 1] : nullptr;
+		const int64_t glo = (lo + 7) & ~7ll, ghi = hi & ~7ll;
+		if (glo >= ghi || level == MG_PYR_MAX || !ch->plse[level]) { // no full group in between (or no level above): take the entries
+			for (int64_t i = lo; i < hi; ++i)
+				f(level ? __ldg(pd + i) : (double)__ldg(pv + i));
+			return;
+		}
+		for (int64_t i = lo; i < glo; ++i)
+			f(level ? __ldg(pd + i) : (double)__ldg(pv + i));
+		for (int64_t i = ghi; i < hi; ++i)
+			f(level ? __ldg(pd + i) : (double)__ldg(pv + i));
+		lo = glo >> 3;
+		hi = ghi >> 3;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_dense_lse(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	double lse = mg_nan();
+	if (mg_dense_win(q, q.first + i, w) && w.ebin > w.sbin) {
+		if (w.one_bin) // assign_single_bin_value: the bin's value
+			lse = (double)__ldg(w.ch->vals + w.sbin);
+		else {
+			double M = -INFINITY;
+			mg_lse_terms(w.ch, w.sbin, w.ebin, [&](double x) { M = fmax(M, x); }); // fmax skips NaN
+			if (M > -INFINITY) {
+				double s = 0;
+				mg_lse_terms(w.ch, w.sbin, w.ebin, [&](double x) {
+					if (x == x)
+						s += exp(x - M);
+				});
+				lse = mg_f2d(M + log(s));
+			}
+		}
+	}
+	mg_st_stream(q.out[MG_LSE] + i, lse);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_dense_argext: min.pos / max.pos, one thread per row, from the same structures as min / max: the extremum m of the window
 // first (two partial groups + two sparse-table entries), then the FIRST bin holding it -- the reference's strict comparisons
 // keep the first occurrence (src/GenomeTrackFixedBin.cpp:886-905) -- in window order: the head group's bins, then the full

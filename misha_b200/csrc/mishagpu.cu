@@ -281,6 +281,26 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 			nchild = nparent;
 		}
 	}
+	// lse pyramid (double): level j+1 exists while level j has more than one group of 8
+	{
+		StagePhase ph("lse pyramid");
+		const double *child = nullptr;
+		int64_t nchild = nbins;
+		for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
+			const int64_t nparent = mg_div_up(nchild, 8);
+			double *pl = nullptr;
+			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nparent, &pl, &arena))
+				return 1;
+			if (lv == 0)
+				k_lse_build<float><<<(unsigned)mg_div_up(nparent, 256), 256>>>(dc.vals, nchild, pl, nparent);
+			else
+				k_lse_build<double><<<(unsigned)mg_div_up(nparent, 256), 256>>>(child, nchild, pl, nparent);
+			MG_LAUNCH_CHECK(ctx);
+			dc.plse[lv] = pl;
+			child = pl;
+			nchild = nparent;
+		}
+	}
 	// sparse tables over the groups of 8 (level 0 = pyramid level 1)
 	{
 		StagePhase ph("sparse tables");
@@ -716,10 +736,7 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 				MG_LAUNCH_CHECK(ctx);
 			}
 			if (q.out[MG_LSE]) {
-				DenseQuery ql = q; // the sweep kernel writes every order-dependent column it is given: give it lse alone
-				for (int f = MG_FIRST; f <= MG_MAX_POS; ++f)
-					ql.out[f] = nullptr;
-				k_dense_ext<true><<<wgrid, MG_EXT_WARPS * 32, 0, st>>>(ql);
+				k_dense_lse<<<tgrid, 256, 0, st>>>(q);
 				MG_LAUNCH_CHECK(ctx);
 			}
 		}

@@ -339,7 +339,7 @@ def test_order_dependent_functions_synthetic_ties_and_nans():
             else:
                 assert_same(got[k], exp[name], name)
         # first / last alone take the thread-per-row kernel; force_sweep keeps them on the warp-per-row one
-        fl = ["first", "last", "first.pos", ("last.pos", 1), "min.pos", ("max.pos", 1)]  # argext: sparse-table descent
+        fl = ["first", "last", "first.pos", ("last.pos", 1), "min.pos", ("max.pos", 1), "lse"]  # argext: sparse-table descent; lse: pyramid
         ws = np.maximum(s - 15, 0).astype(np.float64)
         for sweep in (0, 1):
             ctx2.set_option("force_sweep", sweep)
@@ -353,5 +353,7 @@ def test_order_dependent_functions_synthetic_ties_and_nans():
             assert_same(got[3], exp["last.pos"] - ws, f"last.pos relative (sweep={sweep})")
             assert_same(got[4], exp["min.pos"], f"min.pos (sweep={sweep})")
             assert_same(got[5], exp["max.pos"] - ws, f"max.pos relative (sweep={sweep})")
+            np.testing.assert_allclose(got[6], exp["lse"], rtol=2e-7, atol=0, equal_nan=True)
+            assert np.mean((got[6] == exp["lse"]) | np.isnan(got[6])) > 0.999
     finally:
         ctx2.close()
