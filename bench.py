@@ -10,9 +10,11 @@ One "step" = one gextract pass producing the three value columns for every inter
   python bench.py --impl reference ...                           the reference's own CPU arithmetic (oracle/_ref),
                                                                  all host threads it would use, bounded sample per step
 
-N > 1 is launched by torch.distributed.run, one rank per GPU; chromosomes are sharded over ranks (whole chromosomes,
-LPT), there is no data-path collective (each rank owns a disjoint row range) and scaling is weak in the per-GPU sense
-of "the same total job split N ways" -> reported as "strong" (total work fixed).
+N > 1 is launched by torch.distributed.run, one rank per GPU; every rank takes one contiguous 1/N slice of the
+chromosome-major rows and stages the chromosomes its slice touches, there is no data-path collective (each rank owns a
+disjoint row range) and the total job is fixed whatever N -> reported as "strong".
+`value`: the K timed steps are captured once in a CUDA graph and replayed between two CUDA events on the launching stream
+(barrier + synchronize on both sides, max over ranks). `e2e`: the same step through mg_h_dense_window with pinned host arrays.
 """
 import argparse
 import json
