@@ -539,3 +539,33 @@ def test_sparse_merge_rows_per_thread_fixed_bin():
                         assert_same(got[k][m], exp, f"{name} chrom{cid} bin {binsize} shift {sshift}")
     finally:
         ctx2.close()
+
+
+def test_merge_kernels_long_scope_device_grid_path():
+    """More than 32 scope intervals: the regular-grid blocks are not worked out on the host (GridTable.n = -1) and every thread
+    block decides on the device (mg_sf_grid_block), the scope search reads global memory. Same results as the oracle."""
+    sizes = [2_000_000]
+    ctx2 = gpu.Context(sizes)
+    try:
+        rng = np.random.default_rng(90210)
+        n = 6000
+        st = np.sort(rng.choice(sizes[0] // 50 - 2, n, replace=False)) * 50
+        en = st + rng.integers(1, 50, n)
+        v = rng.random(n).astype(np.float32)
+        t = gpu.SparseTrack(ctx2); t.stage(0, st, en, v)
+        iv = gpu.IntervalSet(ctx2); iv.stage(0, st, en)
+        edges = np.sort(rng.choice(np.arange(1, 1999), 79, replace=False)) * 1000 + rng.integers(0, 17, 79)
+        ss, se = np.concatenate([[3], edges[1::2]]), np.concatenate([edges[0::2], [sizes[0]]])[:len(np.concatenate([[3], edges[1::2]]))]
+        keep = se > ss
+        ss, se = ss[keep].astype(np.int64), se[keep].astype(np.int64)
+        assert len(ss) > 32
+        rows = ctx2.rows_fixedbin(20, np.zeros(len(ss), np.int32), ss, se)
+        c, s, e, _ = rows.coords()
+        for sshift, eshift in ((0, 0), (-30, 45)):
+            assert_same(iv.coverage(rows, sshift, eshift), port.coverage(st, en, sizes[0], s, e, sshift, eshift), f"coverage {sshift}")
+            got = t.window(rows, ["nearest", "avg"], sshift, eshift)
+            exp = port.sparse_window(st, en, v, sizes[0], s, e, sshift, eshift, 0.5, funcs=("nearest", "avg"))
+            assert_same(got[0], exp["nearest"], f"nearest {sshift}")
+            assert_same(got[1], exp["avg"], f"avg {sshift}")
+    finally:
+        ctx2.close()
