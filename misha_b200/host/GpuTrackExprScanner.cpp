@@ -57,6 +57,27 @@ void GpuTrackExprScanner::vtrack_coverage(const std::string &name, const mg_ivse
 	m_vtracks[name] = v;
 }
 
+void GpuTrackExprScanner::vtrack_pwm(const std::string &name, const mg_seq *seq, int mode, const std::vector<double> &pssm, double prior, bool bidirect,
+									 bool extend, int strand, float score_thresh, int64_t sshift, int64_t eshift)
+{
+	if (pssm.empty() || pssm.size() % 4)
+		throw MishaGpuException("Virtual track " + name + ": PWM functions require a matrix with columns A, C, G, T");
+	VTrack v;
+	v.source = VTrack::PWM;
+	v.seq = seq;
+	v.pwm_mode = mode;
+	v.logp.resize(pssm.size());
+	if (mg_pssm_logp(pssm.data(), (int)(pssm.size() / 4), prior, v.logp.data()))
+		throw MishaGpuException("Virtual track " + name + ": invalid PSSM");
+	v.bidirect = bidirect;
+	v.extend = extend;
+	v.strand = strand;
+	v.score_thresh = score_thresh;
+	v.sshift = sshift;
+	v.eshift = eshift;
+	m_vtracks[name] = v;
+}
+
 void GpuTrackExprScanner::vtrack_rm(const std::string &name) { m_vtracks.erase(name); }
 
 void GpuTrackExprScanner::release()
@@ -203,6 +224,12 @@ bool GpuTrackExprScanner::fill(int64_t first)
 		const VTrack &v = *m_vars[i];
 		if (v.source == VTrack::COVERAGE) {
 			check(mg_coverage(m_ctx, v.ivset, m_rows, first, count, v.sshift, v.eshift, m_dcols[i], nullptr));
+			done[i] = true;
+			continue;
+		}
+		if (v.source == VTrack::PWM) { // PWMScorer::score_interval per row (src/SequenceVarProcessor.cpp:471) -> one mg_pwm per vtrack
+			check(mg_pwm(m_ctx, v.seq, v.logp.data(), (int)(v.logp.size() / 4), v.bidirect, v.extend, v.pwm_mode, v.strand, v.score_thresh, m_rows,
+						 first, count, v.sshift, v.eshift, m_dcols[i], nullptr));
 			done[i] = true;
 			continue;
 		}

@@ -36,11 +36,16 @@ struct Interval {
 };
 
 struct VTrack {
-	enum Source { DENSE, SPARSE, COVERAGE };
+	enum Source { DENSE, SPARSE, COVERAGE, PWM };
 	Source source = DENSE;
 	const mg_dense *dense = nullptr;
 	const mg_sparse *sparse = nullptr;
 	const mg_ivset *ivset = nullptr;
+	// sequence vtracks (pwm, pwm.max, pwm.max.pos, pwm.count): PWMParams, src/TrackExpressionParams.h:74-240
+	const mg_seq *seq = nullptr;
+	std::vector<float> logp; // L x 4 log-probabilities (mg_pssm_logp)
+	int pwm_mode = MG_PWM_TOTAL, bidirect = 1, extend = 1, strand = 1;
+	float score_thresh = 0;
 	int func = MG_AVG;   // enum mg_func
 	double param = 0;    // percentile of MG_QUANTILE
 	int64_t sshift = 0, eshift = 0;
@@ -57,6 +62,10 @@ public:
 	void vtrack_dense(const std::string &name, const mg_dense *track, int func, double param = 0, int64_t sshift = 0, int64_t eshift = 0);
 	void vtrack_sparse(const std::string &name, const mg_sparse *track, int func, double param = 0, int64_t sshift = 0, int64_t eshift = 0);
 	void vtrack_coverage(const std::string &name, const mg_ivset *src, int64_t sshift = 0, int64_t eshift = 0);
+	// gvtrack.create(name, NULL, "pwm" | "pwm.max" | "pwm.max.pos" | "pwm.count", list(pssm = , bidirect = , prior = , extend = , strand = ,
+	// score.thresh = )): pssm = L x 4 probabilities (A, C, G, T), turned into the reference's log table by mg_pssm_logp
+	void vtrack_pwm(const std::string &name, const mg_seq *seq, int mode, const std::vector<double> &pssm, double prior = 0.01, bool bidirect = true,
+					bool extend = true, int strand = 1, float score_thresh = 0, int64_t sshift = 0, int64_t eshift = 0);
 	void vtrack_rm(const std::string &name);
 
 	// Fixed-bin iterator (iterator = binsize) or intervals iterator over `scope`. The scope is sorted by (chromid, start) as

@@ -7,6 +7,8 @@
 //   sparse <name> <file chrom0> ...          (per chromosome: int64 n, then n starts, n ends (int64), n float32 values)
 //   ivset <name> <file chrom0> ...           (per chromosome: int64 n, n starts, n ends)
 //   vtrack <vname> dense|sparse|coverage <source name> <func id> <param> <sshift> <eshift>
+//   seq <name> <file chrom0> ...             (ASCII bases per chromosome)
+//   pwm <vname> <seq name> <mode> <pssm file: float64 L x 4> <prior> <bidirect> <extend> <strand> <score thresh> <sshift> <eshift>
 //   scope <file>                             (int64 n, then n x {int64 chromid, start, end})
 //   iterator <binsize> | iterator intervals <file>
 //   buffer <rows>
@@ -63,6 +65,17 @@ int main(int argc, char **argv)
 		std::map<std::string, mg_sparse *> sparse;
 		std::map<std::string, mg_ivset *> ivsets;
 		std::vector<std::tuple<std::string, std::string, std::string, int, double, int64_t, int64_t>> vtracks;
+		std::map<std::string, mg_seq *> seqs;
+		struct PwmSpec {
+			std::string name, seq;
+			int mode;
+			std::vector<double> pssm;
+			double prior;
+			int bidirect, extend, strand;
+			float thresh;
+			int64_t ss, es;
+		};
+		std::vector<PwmSpec> pwms;
 		std::vector<Interval> scope, iter_intervals;
 		int64_t binsize = 0, buffer = int64_t(1) << 20;
 		bool use_iter_intervals = false;
@@ -128,6 +141,23 @@ int main(int argc, char **argv)
 				int64_t ss, es;
 				in >> v >> kind >> src >> func >> param >> ss >> es;
 				vtracks.emplace_back(v, kind, src, func, param, ss, es);
+			} else if (cmd == "seq") {
+				std::string name, path;
+				in >> name;
+				mg_seq *q = nullptr;
+				chk(mg_seq_create(ctx, &q));
+				for (size_t c = 0; c < sizes.size(); ++c) {
+					in >> path;
+					const std::vector<char> bases = read_raw<char>(path);
+					chk(mg_seq_stage(ctx, q, (int)c, bases.data(), (int64_t)bases.size()));
+				}
+				seqs[name] = q;
+			} else if (cmd == "pwm") {
+				PwmSpec p;
+				std::string path;
+				in >> p.name >> p.seq >> p.mode >> path >> p.prior >> p.bidirect >> p.extend >> p.strand >> p.thresh >> p.ss >> p.es;
+				p.pssm = read_raw<double>(path);
+				pwms.push_back(p);
 			} else if (cmd == "scope") {
 				std::string path;
 				in >> path;
@@ -161,6 +191,8 @@ int main(int argc, char **argv)
 					else
 						scanner.vtrack_coverage(std::get<0>(vt), ivsets.at(src), std::get<5>(vt), std::get<6>(vt));
 				}
+				for (auto &p : pwms)
+					scanner.vtrack_pwm(p.name, seqs.at(p.seq), p.mode, p.pssm, p.prior, p.bidirect != 0, p.extend != 0, p.strand, p.thresh, p.ss, p.es);
 				// both ways of consuming the scanner must agree: the reference-shaped per-row loop and whole columns
 				const ExtractResult a = gextract(scanner, exprs, scope, binsize, use_iter_intervals ? &iter_intervals : nullptr, true);
 				const ExtractResult b = gextract(scanner, exprs, scope, binsize, use_iter_intervals ? &iter_intervals : nullptr, false);
@@ -196,6 +228,8 @@ int main(int argc, char **argv)
 			mg_sparse_free(ctx, kv.second);
 		for (auto &kv : ivsets)
 			mg_ivset_free(ctx, kv.second);
+		for (auto &kv : seqs)
+			mg_seq_free(ctx, kv.second);
 		mg_shutdown(ctx);
 	} catch (const std::exception &e) {
 		std::fprintf(stderr, "mg_host_demo: %s\n", e.what());

@@ -150,3 +150,56 @@ def test_cpp_scanner_fixedbin_and_summary(tmp_path):
     vals = port.dense_window(b, bs, sizes[0], s, e, 0, 0, 0.5, ("avg",))["avg"]
     exp_s = port.summary(vals)
     assert np.array_equal(got[:4], exp_s[:4]) and np.allclose(got[4:], exp_s[4:], rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_cpp_scanner_sequence_and_order_dependent_vtracks(tmp_path):
+    """The host scanner with sequence vtracks (vtrack_pwm: pwm, pwm.max, pwm.max.pos through mg_pwm) next to dense vtracks of the
+    order-dependent functions (lse, first, max.pos.relative), over a fixed-bin iterator: against the oracle."""
+    build.build_host()
+    rng = np.random.default_rng(79)
+    sizes = [120000, 60000]
+    bs = 20
+    bins, seqs = [], []
+    for c, size in enumerate(sizes):
+        b = rng.normal(size=(size + bs - 1) // bs).astype(np.float32)
+        b[rng.random(len(b)) < 0.07] = np.nan
+        b.tofile(tmp_path / f"dense{c}.f32")
+        bins.append(b)
+        s = rng.choice(np.frombuffer(b"ACGTacgtN", np.uint8), size, p=[0.2, 0.2, 0.2, 0.2, 0.04, 0.04, 0.04, 0.04, 0.04])
+        s.tofile(tmp_path / f"seq{c}.txt")
+        seqs.append(s.tobytes())
+    pssm = rng.dirichlet([0.5] * 4, size=12)
+    pssm.astype(np.float64).tofile(tmp_path / "pssm.f64")
+    _write_intervals(tmp_path / "scope.bin", [1, 0, 0], [100, 50000, 37], [59000, 119990, 30011])
+    spec = tmp_path / "spec.txt"
+    spec.write_text("\n".join([
+        "chroms 2 %d %d" % tuple(sizes),
+        "dense d %d %s %s" % (bs, tmp_path / "dense0.f32", tmp_path / "dense1.f32"),
+        "seq g %s %s" % (tmp_path / "seq0.txt", tmp_path / "seq1.txt"),
+        "vtrack v_lse dense d 9 0 -300 300",
+        "vtrack v_first dense d 10 0 -300 300",
+        "vtrack v_maxpos dense d 15 1 -300 300",
+        "pwm v_pwm g 0 %s 0.01 1 1 1 0 0 0" % (tmp_path / "pssm.f64"),
+        "pwm v_pmax g 1 %s 0.01 1 1 1 0 -40 40" % (tmp_path / "pssm.f64"),
+        "pwm v_ppos g 2 %s 0.01 1 0 -1 0 0 0" % (tmp_path / "pssm.f64"),
+        "scope %s" % (tmp_path / "scope.bin"),
+        "iterator 170",
+        "buffer 512",
+        "exprs v_lse v_first v_maxpos v_pwm v_pmax v_ppos",
+        "out %s" % (tmp_path / "out.bin"),
+    ]) + "\n")
+    r = subprocess.run([build.HOST_DEMO, str(spec)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    oc, os_, oe, iid, cols = _read_out(tmp_path / "out.bin", 6)
+    logp = port.pssm_logp(pssm, 0.01)
+    assert len(oc) > 900
+    for c in range(2):
+        m = oc == c
+        ext = port.dense_window_ext(bins[c], bs, sizes[c], os_[m], oe[m], -300, 300, 0)
+        np.testing.assert_allclose(cols[0][m], ext["lse"], rtol=2e-7, atol=0, equal_nan=True)
+        assert_same(cols[1][m], ext["first"], "first")
+        assert_same(cols[2][m], ext["max.pos"] - np.maximum(os_[m] - 300, 0), "max.pos.relative")
+        assert_close(cols[3][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, True, "pwm", 1), RTOL, "pwm")
+        assert_close(cols[4][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, True, "pwm.max", 1, 0.0, -40, 40), RTOL, "pwm.max")
+        assert_same(cols[5][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, False, "pwm.max.pos", -1), "pwm.max.pos")
