@@ -511,6 +511,40 @@ class MishaDB:
         q, _ = gpu.quantiles(self.ctx, col, rows.n, pcts)
         return {float(p): float(v) for p, v in zip(pcts, q)}
 
+    def gintervals_quantiles(self, expr, percentiles=0.5, intervals=None, iterator=None):
+        """R gintervals.quantiles -> gintervals_quantiles (src/GenomeTrackQuantiles.cpp:612-860, 1-D): per interval of the SORTED
+        (not unified) intervals, the quantiles of the expression's non-NaN values over the iterator rows inside it -- a
+        StreamPercentiler<double> fed the float-narrowed values, reset at every scope interval (:726-741), calc_medians' exact
+        branch. Returns a dict: chrom / start / end of the sorted intervals and one float64 column per percentile (NaN where an
+        interval holds no value). The value column stays in HBM; each interval's slice goes through mg_quantiles."""
+        pcts = np.atleast_1d(np.asarray(percentiles, dtype=np.float64))
+        for p in pcts:
+            if not (0 <= p <= 1):
+                raise MishaError("Percentile (%g) is not in [0, 1] range\n" % p)
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, order = self._rows([expr], intervals, iterator, unify_scope=False)
+        expr = expr.strip()
+        n_int = len(order)
+        out = {"chrom": np.asarray(intervals["chrom"])[order], "start": np.asarray(intervals["start"])[order],
+               "end": np.asarray(intervals["end"])[order]}
+        cols = np.full((len(pcts), n_int), np.nan)
+        if rows.n:
+            if expr in self.vtracks or self.gtrack_exists(expr):
+                col = self._var_column(expr, rows)
+            else:
+                col = self.ctx.alloc(rows.n, np.float64).from_host(np.asarray(self._eval(expr, rows, {}), dtype=np.float64))
+            scope = rows.coords()[3]  # index of each row's interval in the sorted scope; rows of one interval are contiguous
+            cuts = np.flatnonzero(np.diff(scope)) + 1
+            firsts = np.concatenate([[0], cuts])
+            counts = np.diff(np.concatenate([firsts, [rows.n]]))
+            for f, c in zip(firsts, counts):
+                q, nk = gpu.quantiles(self.ctx, col, int(c), pcts, first=int(f))
+                if nk:
+                    cols[:, scope[f]] = q
+        for k, p in enumerate(pcts):
+            out[float(p)] = cols[k]
+        return out
+
     def gsummary(self, expr, intervals=None, iterator=None):
         """R/compute-core.R:286. Returns the named 7-vector as a dict."""
         intervals = self.gintervals_all() if intervals is None else intervals

@@ -410,12 +410,13 @@ def hist_dev(ctx, dcols, n, breaks_list, counts, include_lowest=False, stream=No
                                c_vp(stream)))
 
 
-def quantiles(ctx, dcol, n, percentiles, stream=None):
-    """Exact gquantiles of a device column: (quantiles, number of non-NaN values)."""
+def quantiles(ctx, dcol, n, percentiles, stream=None, first=0):
+    """Exact gquantiles of n values of a device column from element `first` on: (quantiles, number of non-NaN values)."""
     p = _arr(percentiles, np.float64)
     out = np.empty(len(p), dtype=np.float64)
     nk = c_i64()
-    ctx._check(ctx.lib.mg_quantiles(ctx.h, c_vp(dcol.ptr), c_i64(n), ctypes.c_int(len(p)), _p(p), _p(out), ctypes.byref(nk), c_vp(stream)))
+    ctx._check(ctx.lib.mg_quantiles(ctx.h, c_vp(dcol.ptr + 8 * int(first)), c_i64(n), ctypes.c_int(len(p)), _p(p), _p(out), ctypes.byref(nk),
+                                    c_vp(stream)))
     return out, int(nk.value)
 
 

@@ -238,3 +238,28 @@ def test_gquantiles(db):
     with pytest.raises(api.MishaError, match="not in"):
         db.gquantiles("dense_track", 2)
     db.gvtrack_rm("wmax")
+
+
+def test_gintervals_quantiles(db):
+    """gintervals.quantiles: per interval of the sorted (possibly overlapping) intervals, the quantiles of the expression over the
+    iterator rows inside it; NaN where an interval holds no value. Expected from the oracle: rows of the interval, the value
+    column, the reference's StreamPercentiler<double> restatement (port.gquantiles)."""
+    pcts = [0.0, 0.25, 0.5, 0.9, 1.0]
+    iv = db.gintervals([2, 1, 1, "X", 1], [1000, 300000, 10, 150000, 299000], [9000, 330000, 2010, 200000, 305000])  # unsorted, two overlap
+    db.gvtrack_create("wavg", "dense_track", "avg")
+    db.gvtrack_iterator("wavg", sshift=-120, eshift=80)
+    for expr, iterator, sshift, eshift in (("dense_track", None, 0, 0), ("wavg", 170, -120, 80)):
+        r = db.gintervals_quantiles(expr, pcts, intervals=iv, iterator=iterator)
+        cid = np.array([[c for c, _ in CHROMS].index(x) for x in r["chrom"]])
+        assert np.all(np.diff(cid) >= 0) and len(cid) == 5
+        for k in range(5):
+            c, size = CHROMS[cid[k]]
+            bs, bins = read_dense("dense_track", c)
+            _, s, e, _ = port.fixedbin_rows(bs if iterator is None else iterator, [0], [r["start"][k]], [r["end"][k]])
+            col = port.dense_window(bins, bs, size, s, e, sshift, eshift, 0.5, ("avg",))["avg"]
+            exp, nk = port.gquantiles(col, pcts)
+            for j, p in enumerate(pcts):
+                assert (np.isnan(r[p][k]) and nk == 0) or r[p][k] == exp[j], (expr, k, p)
+    db.gvtrack_rm("wavg")
+    with pytest.raises(api.MishaError, match="not in"):
+        db.gintervals_quantiles("dense_track", [0.5, 1.5], intervals=iv)
