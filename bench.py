@@ -231,7 +231,13 @@ def run_ours(args):
     barrier()
     if sampler:
         sampler.mark(False)
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    ms_mine = ev0.elapsed_time(ev1) / args.steps
+    ms_step = max_over_ranks(ms_mine)
+    ms_ranks = [ms_mine]
+    if world > 1:  # every rank's own step time: the slowest one sets the job's
+        t = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(t, torch.tensor([ms_mine], dtype=torch.float64, device="cuda"))
+        ms_ranks = [float(x.item()) for x in t]
     launches = args.steps if graph is not None else ctx.launch_count() - launches0
 
     # ---- end to end through the host-buffer C-ABI call: pinned host arrays in, host columns out ----
@@ -311,6 +317,7 @@ def run_ours(args):
                                "20 bp dense track on a synthetic %.2f Gbp genome (24 hg38-length chromosomes)" % (n_total, sum(sizes) / 1e9),
                    "intervals": n_total, "bin_size": BIN, "funcs": ["avg", "max", "quantile(0.9)"], "sharding": "contiguous 1/N slices of the chromosome-major rows; a rank stages the chromosomes its slice touches",
                    "step_launch": "the K steps replayed from one CUDA graph" if graph is not None else "K plain launches",
+                   "ms_per_step_by_rank": [round(x, 4) for x in ms_ranks],
                    "l2_policy": "inputs larger than L2 (track 0.62 GB + index structures 3 GB touched + intervals 0.2 GB vs 126 MB L2)",
                    "staging_s_one_time": round(stage_s, 3), "hbm_bytes_staged_rank0": dense.bytes()},
         "e2e": {"value": n_total / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n_mine * 20), "d2h_bytes_per_step": int(n_mine * 8 * len(FUNCS)),
