@@ -199,6 +199,16 @@ int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_t f
 int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
 				 void *stream);
 
+/* gintervals.quantiles (gintervals_quantiles, src/GenomeTrackQuantiles.cpp:612-860, 1-D): the reference resets one          */
+/* StreamPercentiler<double> at every scope interval (:726-741) and reads the percentiles with calc_medians (:95-120). Here    */
+/* the value column of ALL rows stays in HBM and segment s = rows [h_seg_first[s], h_seg_first[s+1]) is one scope interval's  */
+/* run of rows (nseg + 1 ascending host offsets). Segments up to 16384 rows are sorted in shared memory, one warp or one     */
+/* thread block each, all in at most two launches; longer ones go through mg_quantiles' counting passes. Same arithmetic as  */
+/* mg_quantiles; h_out[k * nseg + s] = quantile k of segment s (NaN for a segment without values), h_nkept[s] (may be NULL)  */
+/* its number of non-NaN values. Synchronises the stream. At most 64 quantiles per call.                                      */
+int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, int nq, const double *h_percentiles,
+						   double *h_out, int64_t *h_nkept, void *stream);
+
 /* gscreen: merge consecutive TRUE rows (d_flag[i] == 1) of rows [first, first+count) into intervals. Outputs are   */
 /* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */
 int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,

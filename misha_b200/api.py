@@ -516,7 +516,7 @@ class MishaDB:
         (not unified) intervals, the quantiles of the expression's non-NaN values over the iterator rows inside it -- a
         StreamPercentiler<double> fed the float-narrowed values, reset at every scope interval (:726-741), calc_medians' exact
         branch. Returns a dict: chrom / start / end of the sorted intervals and one float64 column per percentile (NaN where an
-        interval holds no value). The value column stays in HBM; each interval's slice goes through mg_quantiles."""
+        interval holds no value). The value column stays in HBM; all intervals' slices go through one mg_quantiles_segmented call."""
         pcts = np.atleast_1d(np.asarray(percentiles, dtype=np.float64))
         for p in pcts:
             if not (0 <= p <= 1):
@@ -536,11 +536,8 @@ class MishaDB:
             scope = rows.coords()[3]  # index of each row's interval in the sorted scope; rows of one interval are contiguous
             cuts = np.flatnonzero(np.diff(scope)) + 1
             firsts = np.concatenate([[0], cuts])
-            counts = np.diff(np.concatenate([firsts, [rows.n]]))
-            for f, c in zip(firsts, counts):
-                q, nk = gpu.quantiles(self.ctx, col, int(c), pcts, first=int(f))
-                if nk:
-                    cols[:, scope[f]] = q
+            q, _ = gpu.quantiles_segmented(self.ctx, col, np.concatenate([firsts, [rows.n]]), pcts)  # NaN where nothing was kept
+            cols[:, scope[firsts]] = q
         for k, p in enumerate(pcts):
             out[float(p)] = cols[k]
         return out

@@ -2070,6 +2070,87 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 	return 0;
 }
 
+// ---- gintervals.quantiles: segmented form ----------------------------------------------------------------------------------
+extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, int nq,
+									  const double *h_percentiles, double *h_out, int64_t *h_nkept, void *stream)
+{
+	MG_REQUIRE(ctx, nseg >= 0 && nseg < (int64_t)INT32_MAX && h_seg_first && nq >= 1 && nq <= MG_QS_MAXSLOTS / 2 && h_percentiles && h_out,
+			   "mg_quantiles_segmented: bad arguments (1..%d quantiles)", MG_QS_MAXSLOTS / 2);
+	for (int k = 0; k < nq; ++k) // gintervals_quantiles rejects these before scanning (src/GenomeTrackQuantiles.cpp:632-635)
+		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
+	for (int64_t s = 0; s < nseg; ++s)
+		MG_REQUIRE(ctx, h_seg_first[s] >= 0 && h_seg_first[s] <= h_seg_first[s + 1], "mg_quantiles_segmented: segment offsets must ascend (segment %lld)",
+				   (long long)s);
+	if (!nseg)
+		return 0;
+	MG_REQUIRE(ctx, d_vals || h_seg_first[nseg] == 0, "mg_quantiles_segmented: no value column");
+	cudaStream_t st = mg_stream(stream);
+	std::vector<int32_t> list[2]; // 0: one warp per segment, 1: one thread block per segment
+	std::vector<int64_t> large;   // beyond a thread block's shared memory: the whole-device counting passes of mg_quantiles
+	for (int64_t s = 0; s < nseg; ++s) {
+		const int64_t c = h_seg_first[s + 1] - h_seg_first[s];
+		if (c <= MG_QSEG_WARP_CAP)
+			list[0].push_back((int32_t)s);
+		else if (c <= MG_QSEG_BLOCK_CAP)
+			list[1].push_back((int32_t)s);
+		else
+			large.push_back(s);
+	}
+	char *d_buf = nullptr;
+	const size_t off_first = 0, off_pct = off_first + (size_t)(nseg + 1) * 8, off_out = off_pct + (size_t)nq * 8,
+				 off_kept = off_out + (size_t)nq * nseg * 8, off_list = off_kept + (size_t)nseg * 8, total = off_list + (size_t)nseg * 4;
+	MG_CUDA(ctx, cudaMallocAsync(&d_buf, total, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(d_buf + off_first, h_seg_first, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(d_buf + off_pct, h_percentiles, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+	QsegArgs a;
+	a.vals = d_vals;
+	a.seg_first = (const int64_t *)(d_buf + off_first);
+	a.nseg = nseg;
+	a.nq = nq;
+	a.pct = (const double *)(d_buf + off_pct);
+	a.out = (double *)(d_buf + off_out);
+	a.nkept = (long long *)(d_buf + off_kept);
+	size_t list_pos = 0;
+	for (int tier = 0; tier < 2; ++tier) {
+		if (list[tier].empty())
+			continue;
+		int32_t *d_list = (int32_t *)(d_buf + off_list) + list_pos;
+		list_pos += list[tier].size();
+		MG_CUDA(ctx, cudaMemcpyAsync(d_list, list[tier].data(), list[tier].size() * 4, cudaMemcpyHostToDevice, st));
+		a.list = d_list;
+		a.nlist = (int64_t)list[tier].size();
+		if (tier == 0) {
+			const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(a.nlist, 8), (int64_t)ctx->sm_count * 16);
+			k_qseg<true><<<grid, 256, 8 * MG_QSEG_WARP_CAP * 4, st>>>(a);
+		} else {
+			const int smem = MG_QSEG_BLOCK_CAP * 4;
+			MG_CUDA(ctx, cudaFuncSetAttribute(k_qseg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			const unsigned grid = (unsigned)std::min<int64_t>(a.nlist, (int64_t)ctx->sm_count * 3);
+			k_qseg<false><<<grid, MG_QSEG_BLOCK_THREADS, smem, st>>>(a);
+		}
+		MG_LAUNCH_CHECK(ctx);
+	}
+	std::vector<long long> kept((size_t)nseg);
+	MG_CUDA(ctx, cudaMemcpyAsync(h_out, d_buf + off_out, (size_t)nq * nseg * 8, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(kept.data(), d_buf + off_kept, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
+	std::vector<double> q((size_t)nq);
+	for (int64_t s : large) {
+		int64_t nk = 0;
+		const int rc = mg_quantiles(ctx, d_vals + h_seg_first[s], h_seg_first[s + 1] - h_seg_first[s], nq, h_percentiles, q.data(), &nk, stream);
+		if (rc)
+			return rc;
+		kept[(size_t)s] = nk;
+		for (int k = 0; k < nq; ++k)
+			h_out[(size_t)k * nseg + s] = q[(size_t)k];
+	}
+	if (h_nkept)
+		for (int64_t s = 0; s < nseg; ++s)
+			h_nkept[s] = kept[(size_t)s];
+	return 0;
+}
+
 // ---- gscreen -----------------------------------------------------------------------------------------------------------
 extern "C" int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, const int *ops, const double *thresholds, int combine_or,
 								 int64_t n, int8_t *d_flag, void *stream)

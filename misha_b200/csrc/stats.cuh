@@ -656,6 +656,84 @@ __global__ void __launch_bounds__(256) k_qs_count(const double *__restrict__ val
 	}
 }
 
+// ---- gintervals.quantiles: the quantiles of many contiguous segments of a value column in one launch ------------------------
+// The reference keeps one StreamPercentiler<double> and resets it at every scope interval (src/GenomeTrackQuantiles.cpp:726-741);
+// a segment is the run of rows of one scope interval. A segment's keys (mg_qs_key: float-narrowed, NaN = 0xffffffff sorts last,
+// like the padding) are sorted in shared memory -- by one warp (WARP, up to MG_QSEG_WARP_CAP rows) or one thread block (up to
+// MG_QSEG_BLOCK_CAP rows) -- and each quantile is interpolated in double as src/StreamPercentiler.h:210-216 does.
+#define MG_QSEG_WARP_CAP 256
+#define MG_QSEG_BLOCK_CAP 16384
+#define MG_QSEG_BLOCK_THREADS 512
+struct QsegArgs {
+	const double *vals;
+	const int64_t *seg_first; // nseg + 1 ascending row offsets
+	const int32_t *list;      // the segments of this launch
+	int64_t nlist, nseg;
+	int nq;
+	const double *pct; // nq percentiles in [0, 1]
+	double *out;       // out[k * nseg + s]
+	long long *nkept;  // non-NaN values of segment s
+};
+
+template <bool WARP> __global__ void __launch_bounds__(WARP ? 256 : MG_QSEG_BLOCK_THREADS) k_qseg(const QsegArgs a)
+{
+	extern __shared__ uint32_t qseg_sh[];
+	const int T = WARP ? 32 : (int)blockDim.x;
+	const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+	uint32_t *s = WARP ? qseg_sh + (threadIdx.x >> 5) * MG_QSEG_WARP_CAP : qseg_sh;
+	const int64_t worker = WARP ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : (int64_t)blockIdx.x;
+	const int64_t nworkers = WARP ? (int64_t)gridDim.x * (blockDim.x >> 5) : (int64_t)gridDim.x;
+	for (int64_t e = worker; e < a.nlist; e += nworkers) {
+		const int64_t seg = a.list[e];
+		const int64_t first = a.seg_first[seg];
+		const int c = (int)(a.seg_first[seg + 1] - first);
+		int P = 32;
+		while (P < c)
+			P <<= 1;
+		for (int t = tid; t < P; t += T)
+			s[t] = t < c ? mg_qs_key(__ldcs(a.vals + first + t)) : 0xffffffffu;
+		if (WARP) __syncwarp(); else __syncthreads();
+		for (int k = 2; k <= P; k <<= 1) {
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				for (int t = tid; t < (P >> 1); t += T) {
+					const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+					const int ixj = i | j;
+					const uint32_t x = s[i], y = s[ixj];
+					if ((x > y) == ((i & k) == 0)) {
+						s[i] = y;
+						s[ixj] = x;
+					}
+				}
+				if (WARP) __syncwarp(); else __syncthreads();
+			}
+		}
+		// N = number of keys below the NaN key (every non-NaN float's key is <= 0xff800000)
+		int lo = 0, hi = c;
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (s[mid] == 0xffffffffu)
+				hi = mid;
+			else
+				lo = mid + 1;
+		}
+		const int N = lo;
+		if (tid == 0)
+			a.nkept[seg] = N;
+		for (int k = tid; k < a.nq; k += T) {
+			double r = mg_nan();
+			if (N > 0) {
+				const double idx = __dmul_rn((double)(N - 1), a.pct[k]);
+				const double f1 = floor(idx);
+				const int i1 = (int)f1, i2 = (int)ceil(idx);
+				const double w = __dsub_rn(idx, f1);
+				r = __dadd_rn(__dmul_rn((double)mg_fkey_inv(s[i1]), __dsub_rn(1.0, w)), __dmul_rn((double)mg_fkey_inv(s[i2]), w));
+			}
+			a.out[(int64_t)k * a.nseg + seg] = r;
+		}
+		if (WARP) __syncwarp(); else __syncthreads();
+	}
+}
+
 // ---- gscreen comparison predicates on the device -----------------------------------------------------------------------------
 struct PredSpec {
 	int nterms, combine_or;

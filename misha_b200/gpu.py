@@ -420,6 +420,19 @@ def quantiles(ctx, dcol, n, percentiles, stream=None, first=0):
     return out, int(nk.value)
 
 
+def quantiles_segmented(ctx, dcol, seg_first, percentiles, stream=None):
+    """mg_quantiles_segmented: the quantiles of every segment [seg_first[s], seg_first[s+1]) of a device column in at most two
+    launches. Returns (out[len(percentiles), nseg], number of non-NaN values per segment)."""
+    p = _arr(percentiles, np.float64)
+    sf = _arr(seg_first, np.int64)
+    nseg = len(sf) - 1
+    out = np.empty((len(p), max(nseg, 0)), dtype=np.float64)
+    nk = np.empty(max(nseg, 0), dtype=np.int64)
+    ctx._check(ctx.lib.mg_quantiles_segmented(ctx.h, c_vp(dcol.ptr if dcol is not None else None), c_i64(nseg), _p(sf), ctypes.c_int(len(p)),
+                                              _p(p), _p(out), _p(nk), c_vp(stream)))
+    return out, nk
+
+
 CMP_OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 
 

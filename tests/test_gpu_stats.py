@@ -244,3 +244,45 @@ def test_quantiles_golden_and_oracle(gpu_ctx):
             got, nk = gpu.quantiles(gpu_ctx, d, n, p)
             exp, en = port.gquantiles(v, p)
             assert nk == en and np.array_equal(got, exp, equal_nan=True), n
+
+
+def test_quantiles_segmented(gpu_ctx):
+    """mg_quantiles_segmented (gintervals.quantiles: one percentiler per scope interval, src/GenomeTrackQuantiles.cpp:726-741):
+    every segment bit for bit against the oracle's StreamPercentiler<double> restatement and against the golden vectors --
+    empty, one-row, all-NaN segments, the warp / thread block / whole-device tiers and their borders."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gquantiles_vectors.npz"))
+    pcts = g["pcts"]
+    pcts = pcts[(pcts >= 0) & (pcts <= 1)]
+    keys = [k for k in g.files if k.startswith("vals_")]
+    col = np.concatenate([g[k] for k in keys]).astype(np.float64)
+    sf = np.concatenate([[0], np.cumsum([len(g[k]) for k in keys])])
+    d = gpu_ctx.alloc(max(len(col), 1), np.float64).from_host(col)
+    got, nk = gpu.quantiles_segmented(gpu_ctx, d, sf, pcts)
+    for s, k in enumerate(keys):
+        assert np.array_equal(got[:, s], g["q_" + k[5:]][(g["pcts"] >= 0) & (g["pcts"] <= 1)], equal_nan=True), k
+        assert nk[s] == int(np.sum(~np.isnan(g[k].astype(np.float32))))
+
+    rng = np.random.default_rng(97)
+    sizes = [0, 1, 2, 31, 32, 33, 255, 256, 257, 0, 1000, 5000, 16383, 16384, 16385, 40000, 7, 0] + list(rng.integers(0, 600, 300))
+    sf = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(sf[-1])
+    col = np.where(rng.random(n) < 0.2, np.nan, np.round(rng.normal(size=n) * 50) / 8 + rng.normal(size=n) * (rng.random(n) < 0.5))
+    col[rng.integers(0, n, 50)] = np.inf
+    col[rng.integers(0, n, 50)] = -np.inf
+    col[sf[10]:sf[11]] = np.nan      # a 1000-row segment without values
+    col[sf[16]:sf[17]] = np.nan
+    d = gpu_ctx.alloc(n, np.float64).from_host(col)
+    p = np.concatenate([[0, 1, 0.5, 0.9], rng.random(9)])
+    got, nk = gpu.quantiles_segmented(gpu_ctx, d, sf, p)
+    assert got.shape == (len(p), len(sizes))
+    for s in range(len(sizes)):
+        exp, en = port.gquantiles(col[sf[s]:sf[s + 1]], p)
+        assert nk[s] == en, s
+        assert np.array_equal(got[:, s], exp, equal_nan=True), (s, sizes[s])
+    got0, nk0 = gpu.quantiles_segmented(gpu_ctx, d, [0], p)  # no segment at all
+    assert got0.shape == (len(p), 0) and len(nk0) == 0
+    with pytest.raises(gpu.MishaGpuError, match="not in"):
+        gpu.quantiles_segmented(gpu_ctx, d, sf, [1.5])
+    with pytest.raises(gpu.MishaGpuError, match="ascend"):
+        gpu.quantiles_segmented(gpu_ctx, d, [0, 10, 5], [0.5])

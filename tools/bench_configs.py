@@ -157,6 +157,30 @@ def main():
             report("C5 %s 20-mer bidirect, 1M x 500bp" % mode, ms, rows.n * (130 + 8), rows.n,
                    {"anchors_per_s": anchors / ms * 1e3, "strand_scores_per_s": 2 * anchors / ms * 1e3, "seq_staging_s": round(stage_s, 2)})
         seq.free()
+    if "Q" in want:
+        # gintervals.quantiles shape: a 20 M row value column in HBM cut into segments (one per scope interval), 5 quantiles each.
+        # The call is host-synchronous (offsets up, quantile columns down), so it is timed on the host clock.
+        rng = np.random.default_rng(5)
+        n = int(20_000_000 * args.scale)
+        col = np.where(rng.random(n) < 0.05, np.nan, rng.lognormal(size=n))
+        d = ctx.alloc(n, np.float64).from_host(col)
+        p = np.array([0.1, 0.25, 0.5, 0.75, 0.9])
+        for name, lo, hi in (("4-36 rows", 4, 37), ("100-400 rows", 100, 401), ("2000-12000 rows", 2000, 12001)):
+            sz = rng.integers(lo, hi, int(n / ((lo + hi) / 2)) + 1)
+            sf = np.concatenate([[0], np.cumsum(sz)])
+            sf = sf[sf <= n].astype(np.int64)
+            for _ in range(2):
+                gpu.quantiles_segmented(ctx, d, sf, p)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                gpu.quantiles_segmented(ctx, d, sf, p)
+            ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            t0 = time.perf_counter()
+            for s in range(200):  # the loop of whole-device mg_quantiles calls this replaced, on the first 200 segments
+                gpu.quantiles(ctx, d, int(sf[s + 1] - sf[s]), p, first=int(sf[s]))
+            loop_ms = (time.perf_counter() - t0) * 1e3 / 200 * (len(sf) - 1)
+            report("Q gintervals.quantiles, segments of %s, 5 quantiles (host clock, copies included)" % name, ms, 8 * int(sf[-1]), int(sf[-1]),
+                   {"segments": len(sf) - 1, "per_segment_loop_ms_extrapolated": round(loop_ms, 1)})
     ctx.close()
 
 
