@@ -209,6 +209,23 @@ int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const dou
 int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, int nq, const double *h_percentiles,
 						   double *h_out, int64_t *h_nkept, void *stream);
 
+/* gintervals.summary (gintervals_summary, src/GenomeTrackSummary.cpp:248-431): one IntervalSummary per scope interval. */
+/* Segments as in mg_quantiles_segmented; h_partials[6 * s ..] = segment s' six doubles (mg_summary_finalize turns them   */
+/* into the result row). One launch, a warp per segment; segments beyond 2^18 rows use mg_summary's kernels. Row values   */
+/* are narrowed to float first (`float val = scanner.last_real(0)`). Synchronises the stream.                            */
+int mg_summary_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, double *h_partials, void *stream);
+
+/* gbins.summary (gbins_summary, src/GenomeTrackSummary.cpp:433-506): IntervalSummary of d_vals' rows grouped by the N-D  */
+/* bin (BinsManager::vals2idx, src/BinsManager.h:53-72) of their ndim bin columns; breaks as in mg_hist, first dimension */
+/* fastest. h_partials[6 * b ..] = bin b's six doubles. Rows outside every bin are skipped. Synchronises the stream.     */
+int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, const double *const *d_bin_cols, int64_t n, const double *h_breaks,
+					const int *nbreaks, int include_lowest, double *h_partials, void *stream);
+/* gbins.quantiles (gbins_quantiles, src/GenomeTrackQuantiles.cpp:1199-1330): a StreamPercentiler<double> per bin, exact */
+/* regime. The non-NaN values are scattered next to their bin's others on the device and the bins go through             */
+/* mg_quantiles_segmented. h_out[k * total_bins + b], NaN for an empty bin; h_nkept[b] may be NULL. Synchronises.        */
+int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, const double *const *d_bin_cols, int64_t n, const double *h_breaks,
+					  const int *nbreaks, int include_lowest, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept, void *stream);
+
 /* gscreen: merge consecutive TRUE rows (d_flag[i] == 1) of rows [first, first+count) into intervals. Outputs are   */
 /* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */
 int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,

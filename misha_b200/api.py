@@ -584,6 +584,68 @@ class MishaDB:
                 gpu.hist_dev(self.ctx, cols, rows.n, breaks, counts, include_lowest)
         return counts.to_host().astype(np.float64).reshape(shape, order="F")
 
+    def _column(self, expr, rows, cache):
+        """The expression's value column in HBM: a vtrack / track name is computed there, anything else is evaluated on the host."""
+        expr = expr.strip()
+        if expr in self.vtracks or self.gtrack_exists(expr):
+            return self._var_column(expr, rows)
+        return self.ctx.alloc(rows.n, np.float64).from_host(np.asarray(self._eval(expr, rows, cache), dtype=np.float64))
+
+    def gintervals_summary(self, expr, intervals=None, iterator=None):
+        """R gintervals.summary -> gintervals_summary (src/GenomeTrackSummary.cpp:248-431, 1-D): the gsummary row of every interval of
+        the SORTED intervals (an interval without iterator rows: 0 rows, NaN statistics). Returns chrom / start / end and the seven
+        summary columns. One mg_summary_segmented call over the value column in HBM."""
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, order = self._rows([expr], intervals, iterator, unify_scope=False)
+        out = {"chrom": np.asarray(intervals["chrom"])[order], "start": np.asarray(intervals["start"])[order],
+               "end": np.asarray(intervals["end"])[order]}
+        res = np.tile(gpu.summary_finalize(np.array([0, 0, 0, 1.7976931348623157e308, -1.7976931348623157e308, 0.0])), (len(order), 1))
+        if rows.n:
+            col = self._column(expr, rows, {})
+            scope = rows.coords()[3]
+            firsts = np.concatenate([[0], np.flatnonzero(np.diff(scope)) + 1])
+            res[scope[firsts]] = gpu.summary_segmented(self.ctx, col, np.concatenate([firsts, [rows.n]]))
+        for k, name in enumerate(gpu.SUMMARY_NAMES):
+            out[name] = res[:, k]
+        return out
+
+    def _gbins_args(self, args, usage):
+        if len(args) < 2 or len(args) % 2:
+            raise MishaError(usage)
+        return [a.strip() for a in args[0::2]], [np.asarray(b, dtype=np.float64) for b in args[1::2]]
+
+    def gbins_summary(self, *args, expr=None, intervals=None, iterator=None, include_lowest=False):
+        """R gbins.summary(bin_expr1, breaks1, ..., expr=) -> gbins_summary (src/GenomeTrackSummary.cpp:433-506): the gsummary row of
+        `expr` over the rows of every N-D bin of the bin expressions. Returns an array of shape (bins of dim 1, ..., 7)."""
+        bexprs, breaks = self._gbins_args(args, "Usage: gbins.summary([expr, breaks]+, expr, intervals = ALLGENOME, include.lowest = FALSE, iterator = NULL)")
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows([expr] + bexprs, intervals, iterator, unify_scope=True)
+        shape = tuple(len(b) - 1 for b in breaks)
+        cache = {}
+        n = rows.n
+        col = self._column(expr, rows, cache) if n else self.ctx.alloc(1, np.float64)
+        bcols = [self._column(e, rows, cache) if n else col for e in bexprs]
+        res = gpu.bins_summary(self.ctx, col, bcols, n, breaks, include_lowest)
+        return res.reshape(shape + (7,), order="F")
+
+    def gbins_quantiles(self, *args, expr=None, percentiles=0.5, intervals=None, iterator=None, include_lowest=False):
+        """R gbins.quantiles -> gbins_quantiles (src/GenomeTrackQuantiles.cpp:1199-1330): the quantiles of `expr` over the rows of every
+        N-D bin of the bin expressions (NaN for a bin without values). Returns an array of shape (bins of dim 1, ..., percentiles)."""
+        bexprs, breaks = self._gbins_args(args, "Usage: gbins.quantiles([expr, breaks]+, expr, percentiles = 0.5, intervals = ALLGENOME, include.lowest = FALSE, iterator = NULL)")
+        pcts = np.atleast_1d(np.asarray(percentiles, dtype=np.float64))
+        for p in pcts:
+            if not (0 <= p <= 1):
+                raise MishaError("Percentile (%g) is not in [0, 1] range\n" % p)
+        intervals = self.gintervals_all() if intervals is None else intervals
+        rows, _ = self._rows([expr] + bexprs, intervals, iterator, unify_scope=True)
+        shape = tuple(len(b) - 1 for b in breaks)
+        cache = {}
+        n = rows.n
+        col = self._column(expr, rows, cache) if n else self.ctx.alloc(1, np.float64)
+        bcols = [self._column(e, rows, cache) if n else col for e in bexprs]
+        q, _ = gpu.bins_quantiles(self.ctx, col, bcols, n, breaks, pcts, include_lowest)
+        return q.T.reshape(shape + (len(pcts),), order="F")
+
 
 def gdb_init(groot, device=0):
     return MishaDB(groot, device)

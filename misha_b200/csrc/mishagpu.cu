@@ -2151,6 +2151,126 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 	return 0;
 }
 
+// ---- gintervals.summary --------------------------------------------------------------------------------------------------
+extern "C" int mg_summary_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, double *h_partials, void *stream)
+{
+	MG_REQUIRE(ctx, nseg >= 0 && h_seg_first && h_partials, "mg_summary_segmented: bad arguments");
+	for (int64_t s = 0; s < nseg; ++s)
+		MG_REQUIRE(ctx, h_seg_first[s] >= 0 && h_seg_first[s] <= h_seg_first[s + 1], "mg_summary_segmented: segment offsets must ascend (segment %lld)",
+				   (long long)s);
+	if (!nseg)
+		return 0;
+	MG_REQUIRE(ctx, d_vals || h_seg_first[nseg] == 0, "mg_summary_segmented: no value column");
+	cudaStream_t st = mg_stream(stream);
+	const int64_t big = (int64_t)1 << 18; // rows one warp still sums itself
+	char *d_buf = nullptr;
+	const size_t off_part = (size_t)(nseg + 1) * 8;
+	MG_CUDA(ctx, cudaMallocAsync(&d_buf, off_part + (size_t)nseg * 48, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(d_buf, h_seg_first, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+	double *d_part = (double *)(d_buf + off_part);
+	const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(nseg, 8), (int64_t)ctx->sm_count * 16);
+	k_summary_segs<<<grid, 256, 0, st>>>(d_vals, (const int64_t *)d_buf, nseg, big, d_part);
+	MG_LAUNCH_CHECK(ctx);
+	for (int64_t s = 0; s < nseg; ++s) {
+		const int64_t c = h_seg_first[s + 1] - h_seg_first[s];
+		if (c > big && mg_summary(ctx, d_vals + h_seg_first[s], c, d_part + 6 * s, stream))
+			return 1;
+	}
+	MG_CUDA(ctx, cudaMemcpyAsync(h_partials, d_part, (size_t)nseg * 48, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
+	return 0;
+}
+
+// ---- gbins.summary / gbins.quantiles ------------------------------------------------------------------------------------------
+#define MG_BINS_MAX_TOTAL ((long long)1 << 24)
+extern "C" int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, const double *const *d_bin_cols, int64_t n, const double *h_breaks,
+							   const int *nbreaks, int include_lowest, double *h_partials, void *stream)
+{
+	MG_REQUIRE(ctx, n >= 0 && d_bin_cols && h_breaks && nbreaks && h_partials, "mg_bins_summary: bad arguments");
+	cudaStream_t st = mg_stream(stream);
+	HistSpec hs;
+	double *d_breaks = nullptr;
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
+	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_summary: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
+	unsigned long long *d_acc = nullptr;
+	MG_CUDA(ctx, cudaMallocAsync(&d_acc, (size_t)hs.total * 96, st));
+	double *d_part = (double *)(d_acc + 6 * hs.total);
+	k_bins_init<<<(unsigned)std::min<long long>(mg_div_up(hs.total, 256), 1024), 256, 0, st>>>(d_acc, hs.total);
+	MG_LAUNCH_CHECK(ctx);
+	if (n > 0) {
+		HistCols cols;
+		for (int d = 0; d < ndim; ++d)
+			cols.col[d] = d_bin_cols[d];
+		const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8);
+		if (hs.total <= MG_BINS_SMEM_MAX)
+			k_bins_summary<true><<<grid, 256, (size_t)hs.total * 48, st>>>(d_vals, cols, n, hs, d_acc);
+		else
+			k_bins_summary<false><<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_acc);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	k_bins_finalize<<<(unsigned)std::min<long long>(mg_div_up(hs.total, 256), 1024), 256, 0, st>>>(d_acc, hs.total, d_part);
+	MG_LAUNCH_CHECK(ctx);
+	MG_CUDA(ctx, cudaMemcpyAsync(h_partials, d_part, (size_t)hs.total * 48, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	MG_CUDA(ctx, cudaFreeAsync(d_acc, st));
+	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+	return 0;
+}
+
+extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, const double *const *d_bin_cols, int64_t n, const double *h_breaks,
+								 const int *nbreaks, int include_lowest, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
+								 void *stream)
+{
+	MG_REQUIRE(ctx, n >= 0 && n < (int64_t)1 << 40 && d_bin_cols && h_breaks && nbreaks && h_out && h_percentiles && nq >= 1,
+			   "mg_bins_quantiles: bad arguments");
+	for (int k = 0; k < nq; ++k) // src/GenomeTrackQuantiles.cpp:1223
+		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
+	cudaStream_t st = mg_stream(stream);
+	HistSpec hs;
+	double *d_breaks = nullptr;
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
+	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_quantiles: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
+	const size_t T = (size_t)hs.total;
+	std::vector<int64_t> seg_first(T + 1, 0);
+	char *d_buf = nullptr;
+	const size_t off_idx = T * 8, off_sorted = (off_idx + (size_t)n * 4 + 7) & ~(size_t)7;
+	if (n > 0) {
+		MG_CUDA(ctx, cudaMallocAsync(&d_buf, off_sorted + (size_t)n * 8, st));
+		unsigned long long *d_counts = (unsigned long long *)d_buf;
+		int32_t *d_idx = (int32_t *)(d_buf + off_idx);
+		double *d_sorted = (double *)(d_buf + off_sorted);
+		MG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, T * 8, st));
+		HistCols cols;
+		for (int d = 0; d < ndim; ++d)
+			cols.col[d] = d_bin_cols[d];
+		const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8);
+		k_bins_index<<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_idx, d_counts);
+		MG_LAUNCH_CHECK(ctx);
+		std::vector<unsigned long long> counts(T);
+		MG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_counts, T * 8, cudaMemcpyDeviceToHost, st));
+		MG_CUDA(ctx, cudaStreamSynchronize(st));
+		for (size_t b = 0; b < T; ++b)
+			seg_first[b + 1] = seg_first[b] + (int64_t)counts[b];
+		MG_CUDA(ctx, cudaMemcpyAsync(d_counts, seg_first.data(), T * 8, cudaMemcpyHostToDevice, st)); // the bins' write cursors
+		k_bins_scatter<<<grid, 256, 0, st>>>(d_vals, d_idx, n, d_counts, d_sorted);
+		MG_LAUNCH_CHECK(ctx);
+		const int rc = mg_quantiles_segmented(ctx, d_sorted, (int64_t)T, seg_first.data(), nq, h_percentiles, h_out, h_nkept, stream);
+		MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
+		MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+		return rc;
+	}
+	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
+	for (size_t j = 0; j < T * (size_t)nq; ++j)
+		h_out[j] = std::numeric_limits<double>::quiet_NaN();
+	if (h_nkept)
+		for (size_t b = 0; b < T; ++b)
+			h_nkept[b] = 0;
+	return 0;
+}
+
 // ---- gscreen -----------------------------------------------------------------------------------------------------------
 extern "C" int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d_cols, const int *ops, const double *thresholds, int combine_or,
 								 int64_t n, int8_t *d_flag, void *stream)

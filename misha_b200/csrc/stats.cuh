@@ -734,6 +734,175 @@ template <bool WARP> __global__ void __launch_bounds__(WARP ? 256 : MG_QSEG_BLOC
 	}
 }
 
+// ---- gintervals.summary: one IntervalSummary per scope interval (src/GenomeTrackSummary.cpp:248-431) ---------------------------
+// A warp per segment (the run of rows of one scope interval); the row value is narrowed to float first, as `float val =
+// scanner.last_real(0)` does. Segments beyond `big` rows only get their record initialised: the host sends those through
+// mg_summary's whole-device kernels.
+__global__ void __launch_bounds__(256) k_summary_segs(const double *__restrict__ vals, const int64_t *__restrict__ seg_first, int64_t nseg,
+													   int64_t big, double *partials)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+	for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nseg; s += nwarps) {
+		const int64_t first = seg_first[s], c = seg_first[s + 1] - first;
+		Moments m;
+		mom_init(m);
+		if (c <= big)
+			for (int64_t i = lane; i < c; i += 32)
+				mom_add(m, (double)(float)__ldcs(vals + first + i));
+#pragma unroll
+		for (int k = 16; k > 0; k >>= 1) {
+			Moments o = mom_shfl_xor(m, k);
+			mom_merge(m, o);
+		}
+		if (lane == 0) {
+			double *p = partials + 6 * s;
+			p[0] = m.n, p[1] = m.nn, p[2] = m.sum, p[3] = m.mn, p[4] = m.mx, p[5] = m.ssq;
+		}
+	}
+}
+
+// ---- gbins.summary / gbins.quantiles: rows grouped by the N-D bin of their bin columns -----------------------------------------
+// (src/GenomeTrackSummary.cpp:433-506, src/GenomeTrackQuantiles.cpp:1199-1300; bin = BinsManager::vals2idx, src/BinsManager.h:53-72)
+__device__ __forceinline__ long long mg_vals2idx(const HistCols &cols, const HistSpec &hs, int64_t i)
+{
+	long long idx = 0;
+	for (int d = 0; d < hs.ndim; ++d) {
+		const int b = mg_val2bin(hs.breaks + hs.boff[d], hs.nbreaks[d], hs.binsize[d], hs.include_lowest, __ldcs(cols.col[d] + i));
+		if (b < 0)
+			return -1;
+		idx += b * hs.mult[d];
+	}
+	return idx;
+}
+
+// order-preserving 64-bit key of a double (no NaN reaches it): min / max become integer atomics
+__device__ __forceinline__ unsigned long long mg_dkey(double v)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double mg_dkey_inv(unsigned long long k)
+{
+	const unsigned long long b = k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull);
+	return __longlong_as_double((long long)b);
+}
+
+// accumulator record of one bin: {rows, non-NaN rows, sum, min key, max key, sum of squares}, 6 x 8 bytes
+#define MG_BINS_SMEM_MAX 1024 // bins whose records fit a thread block's 48 KB of shared memory
+__device__ __forceinline__ void mg_bins_rec_init(unsigned long long *r)
+{
+	r[0] = 0, r[1] = 0, r[2] = 0 /* 0.0 */, r[3] = ~0ull, r[4] = 0, r[5] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_bins_init(unsigned long long *acc, long long total)
+{
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (long long)gridDim.x * blockDim.x)
+		mg_bins_rec_init(acc + 6 * b);
+}
+
+template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_summary(const double *__restrict__ vals, const HistCols cols, int64_t n,
+																			 const HistSpec hs, unsigned long long *acc)
+{
+	extern __shared__ unsigned long long bins_sh[];
+	unsigned long long *a = SMEM ? bins_sh : acc;
+	if (SMEM) {
+		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x)
+			mg_bins_rec_init(a + 6 * b);
+		__syncthreads();
+	}
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const long long idx = mg_vals2idx(cols, hs, i);
+		if (idx < 0)
+			continue;
+		unsigned long long *r = a + 6 * idx;
+		const double v = (double)(float)__ldcs(vals + i);
+		atomicAdd(r, 1ull);
+		if (!isnan(v)) {
+			atomicAdd(r + 1, 1ull);
+			atomicAdd((double *)(r + 2), v);
+			atomicMin(r + 3, mg_dkey(v));
+			atomicMax(r + 4, mg_dkey(v));
+			atomicAdd((double *)(r + 5), __dmul_rn(v, v));
+		}
+	}
+	if (SMEM) {
+		__syncthreads();
+		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x) {
+			const unsigned long long *r = a + 6 * b;
+			unsigned long long *g = acc + 6 * (long long)b;
+			if (!r[0])
+				continue;
+			atomicAdd(g, r[0]);
+			if (r[1]) {
+				atomicAdd(g + 1, r[1]);
+				atomicAdd((double *)(g + 2), __longlong_as_double((long long)r[2]));
+				atomicMin(g + 3, r[3]);
+				atomicMax(g + 4, r[4]);
+				atomicAdd((double *)(g + 5), __longlong_as_double((long long)r[5]));
+			}
+		}
+	}
+}
+
+// accumulator records -> IntervalSummary's six doubles {num_bins, num_non_nan, sum, min, max, sum_sq}
+__global__ void __launch_bounds__(256) k_bins_finalize(const unsigned long long *acc, long long total, double *partials)
+{
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (long long)gridDim.x * blockDim.x) {
+		const unsigned long long *r = acc + 6 * b;
+		double *p = partials + 6 * b;
+		p[0] = (double)r[0];
+		p[1] = (double)r[1];
+		p[2] = __longlong_as_double((long long)r[2]);
+		p[3] = r[1] ? mg_dkey_inv(r[3]) : 1.7976931348623157e308;
+		p[4] = r[1] ? mg_dkey_inv(r[4]) : -1.7976931348623157e308;
+		p[5] = __longlong_as_double((long long)r[5]);
+	}
+}
+
+// gbins.quantiles, step 1: the bin of every row whose (float-narrowed) value is not NaN, -1 otherwise, and the bins' populations.
+// Lanes of a warp that hit the same bin count once (__match_any_sync).
+__global__ void __launch_bounds__(256) k_bins_index(const double *__restrict__ vals, const HistCols cols, int64_t n, const HistSpec hs, int32_t *idx_out,
+													 unsigned long long *counts)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	const int64_t n32 = (n + 31) & ~(int64_t)31; // whole warps stay in the loop for the warp-wide match
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
+		long long idx = -1;
+		if (i < n) {
+			const float v = (float)__ldcs(vals + i);
+			if (v == v)
+				idx = mg_vals2idx(cols, hs, i);
+			idx_out[i] = (int32_t)idx;
+		}
+		const unsigned peers = __match_any_sync(0xffffffffu, idx);
+		if (idx >= 0 && lane == __ffs(peers) - 1)
+			atomicAdd(counts + idx, (unsigned long long)__popc(peers));
+	}
+}
+
+// step 2: scatter the values next to their bin's others (order inside a bin is irrelevant: the segment gets sorted)
+__global__ void __launch_bounds__(256) k_bins_scatter(const double *__restrict__ vals, const int32_t *__restrict__ idx_in, int64_t n,
+													   unsigned long long *cursor, double *out)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	const int64_t n32 = (n + 31) & ~(int64_t)31;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
+		const int idx = i < n ? idx_in[i] : -1;
+		const unsigned peers = __match_any_sync(0xffffffffu, idx);
+		const int leader = __ffs(peers) - 1;
+		unsigned long long base = 0;
+		if (idx >= 0 && lane == leader)
+			base = atomicAdd(cursor + idx, (unsigned long long)__popc(peers));
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if (idx >= 0)
+			out[base + __popc(peers & ((1u << lane) - 1))] = vals[i];
+	}
+}
+
 // ---- gscreen comparison predicates on the device -----------------------------------------------------------------------------
 struct PredSpec {
 	int nterms, combine_or;

@@ -433,6 +433,42 @@ def quantiles_segmented(ctx, dcol, seg_first, percentiles, stream=None):
     return out, nk
 
 
+def summary_segmented(ctx, dcol, seg_first, stream=None):
+    """mg_summary_segmented: IntervalSummary of every segment of a device column; returns the nseg x 7 result rows."""
+    sf = _arr(seg_first, np.int64)
+    nseg = len(sf) - 1
+    part = np.empty((max(nseg, 0), 6), dtype=np.float64)
+    ctx._check(ctx.lib.mg_summary_segmented(ctx.h, c_vp(dcol.ptr if dcol is not None else None), c_i64(nseg), _p(sf), _p(part), c_vp(stream)))
+    return np.array([summary_finalize(r) for r in part]).reshape(max(nseg, 0), 7)
+
+
+def _bins_args(dcols, breaks_list):
+    nb = np.array([len(b) for b in breaks_list], dtype=np.int32)
+    allb = _arr(np.concatenate([np.asarray(b, dtype=np.float64) for b in breaks_list]), np.float64)
+    ptrs = (c_vp * len(dcols))(*[c_vp(d.ptr if isinstance(d, DevBuf) else d) for d in dcols])
+    return nb, allb, ptrs, int(np.prod(nb - 1))
+
+
+def bins_summary(ctx, dvals, dcols, n, breaks_list, include_lowest=False, stream=None):
+    """mg_bins_summary: total_bins x 7 summary rows (bins flattened first dimension fastest)."""
+    nb, allb, ptrs, total = _bins_args(dcols, breaks_list)
+    part = np.empty((total, 6), dtype=np.float64)
+    ctx._check(ctx.lib.mg_bins_summary(ctx.h, c_vp(dvals.ptr), c_int(len(dcols)), ptrs, c_i64(n), _p(allb), _p(nb), c_int(int(include_lowest)),
+                                       _p(part), c_vp(stream)))
+    return np.array([summary_finalize(r) for r in part]).reshape(total, 7)
+
+
+def bins_quantiles(ctx, dvals, dcols, n, breaks_list, percentiles, include_lowest=False, stream=None):
+    """mg_bins_quantiles: (out[len(percentiles), total_bins], non-NaN values per bin)."""
+    nb, allb, ptrs, total = _bins_args(dcols, breaks_list)
+    p = _arr(percentiles, np.float64)
+    out = np.empty((len(p), total), dtype=np.float64)
+    nk = np.empty(total, dtype=np.int64)
+    ctx._check(ctx.lib.mg_bins_quantiles(ctx.h, c_vp(dvals.ptr), c_int(len(dcols)), ptrs, c_i64(n), _p(allb), _p(nb), c_int(int(include_lowest)),
+                                         c_int(len(p)), _p(p), _p(out), _p(nk), c_vp(stream)))
+    return out, nk
+
+
 CMP_OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import CHROMS, TESTDB, assert_close, assert_same, read_dense, read_seq, read_sparse
-from misha_b200 import api
+from misha_b200 import api, gpu
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -263,3 +263,39 @@ def test_gintervals_quantiles(db):
     db.gvtrack_rm("wavg")
     with pytest.raises(api.MishaError, match="not in"):
         db.gintervals_quantiles("dense_track", [0.5, 1.5], intervals=iv)
+
+
+def test_gintervals_summary_and_gbins(db):
+    """gintervals.summary / gbins.summary / gbins.quantiles of the API mirror against the oracle's IntervalSummary and percentiler
+    restatements over the gextract columns of the same rows."""
+    iv = db.gintervals([2, 1, 1, "X", 1], [1000, 300000, 10, 150000, 299000], [9000, 330000, 2010, 200000, 305000])
+    r = db.gintervals_summary("dense_track", intervals=iv, iterator=150)
+    assert len(r["start"]) == 5 and list(r)[3:] == list(gpu.SUMMARY_NAMES)
+    for k in range(5):
+        one = db.gintervals([r["chrom"][k]], [r["start"][k]], [r["end"][k]])
+        col = db.gextract("dense_track", intervals=one, iterator=150)["dense_track"]
+        exp = port.summary(col)
+        got = np.array([r[nm][k] for nm in gpu.SUMMARY_NAMES])
+        assert_same(got[:4], exp[:4], "counts/min/max")
+        assert_close(got[4:6], exp[4:6], 1e-11, "sum/mean")
+        assert_close(got[6:], exp[6:], 1e-7, "sd")
+    scope = db.gintervals([1, 2], [0, 0], [200000, 100000])
+    e = db.gextract("dense_track", "sparse_track", intervals=scope, iterator=200)
+    dv, sv = e["dense_track"], e["sparse_track"]
+    br = [0, 0.1, 0.2, 0.4, 1]
+    bidx = port.val2bin(br, sv)
+    s = db.gbins_summary("sparse_track", br, expr="dense_track", intervals=scope, iterator=200)
+    q = db.gbins_quantiles("sparse_track", br, expr="dense_track", percentiles=[0.25, 0.5, 0.9], intervals=scope, iterator=200)
+    assert s.shape == (4, 7) and q.shape == (4, 3)
+    for k in range(4):
+        exp = port.summary(dv[bidx == k])
+        assert_same(s[k, :4], exp[:4], "bin counts/min/max")
+        assert_close(s[k, 4:6], exp[4:6], 1e-11, "bin sum/mean")
+        assert_close(s[k, 6:], exp[6:], 1e-7, "bin sd")
+        eq, _ = port.gquantiles(dv[bidx == k], [0.25, 0.5, 0.9])
+        assert np.array_equal(q[k], eq, equal_nan=True)
+    s2 = db.gbins_summary("sparse_track", br, "dense_track", [0, 0.05, 0.5], expr="dense_track", intervals=scope, iterator=200)
+    assert s2.shape == (4, 2, 7)
+    assert s2[..., 0].sum() == np.sum((bidx >= 0) & (port.val2bin([0, 0.05, 0.5], dv) >= 0))
+    with pytest.raises(api.MishaError):
+        db.gbins_summary("sparse_track", expr="dense_track")

@@ -286,3 +286,80 @@ def test_quantiles_segmented(gpu_ctx):
         gpu.quantiles_segmented(gpu_ctx, d, sf, [1.5])
     with pytest.raises(gpu.MishaGpuError, match="ascend"):
         gpu.quantiles_segmented(gpu_ctx, d, [0, 10, 5], [0.5])
+
+
+def _exp_summary_rows(groups):
+    return np.array([port.summary(np.asarray(g, dtype=np.float32).astype(np.float64)) for g in groups]).reshape(len(groups), 7)
+
+
+def _check_summary_rows(got, exp, what):
+    assert_same(got[:, :4], exp[:, :4], what + " counts/min/max")  # exact
+    assert_close(got[:, 4:6], exp[:, 4:6], 1e-11, what + " sum/mean")
+    assert_close(got[:, 6], exp[:, 6], 1e-7, what + " sd")       # the reference's one-pass formula cancels: sd carries sqrt of the sums' last bits
+
+
+def test_summary_segmented(gpu_ctx):
+    """mg_summary_segmented (gintervals.summary: one IntervalSummary per scope interval, src/GenomeTrackSummary.cpp:248-431) against
+    the oracle's IntervalSummary restatement per segment: empty / one-row / all-NaN segments and one beyond the warp tier."""
+    rng = np.random.default_rng(12)
+    sizes = [0, 1, 2, 33, 0, 1000, 7, 300000, 5] + list(rng.integers(0, 200, 500))
+    sf = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(sf[-1])
+    col = np.where(rng.random(n) < 0.1, np.nan, rng.lognormal(size=n)).astype(np.float32).astype(np.float64)
+    col[sf[6]:sf[7]] = np.nan
+    d = gpu_ctx.alloc(n, np.float64).from_host(col)
+    got = gpu.summary_segmented(gpu_ctx, d, sf)
+    exp = _exp_summary_rows([col[sf[s]:sf[s + 1]] for s in range(len(sizes))])
+    _check_summary_rows(got, exp, "segments")
+    assert gpu.summary_segmented(gpu_ctx, d, [0]).shape == (0, 7)
+    with pytest.raises(gpu.MishaGpuError, match="ascend"):
+        gpu.summary_segmented(gpu_ctx, d, [0, 10, 5])
+
+
+def _bin_index(cols, breaks, include_lowest):
+    idx = np.zeros(len(cols[0]), dtype=np.int64)
+    ok = np.ones(len(cols[0]), dtype=bool)
+    mult = 1
+    for c, b in zip(cols, breaks):
+        k = port.val2bin(b, c, include_lowest).astype(np.int64)
+        ok &= k >= 0
+        idx += np.where(k >= 0, k, 0) * mult
+        mult *= len(b) - 1
+    return np.where(ok, idx, -1), mult
+
+
+@pytest.mark.parametrize("case", ["1d_few", "2d", "1d_many", "include_lowest"])
+def test_bins_summary_and_quantiles(gpu_ctx, case):
+    """mg_bins_summary / mg_bins_quantiles (gbins.summary, src/GenomeTrackSummary.cpp:433-506; gbins.quantiles,
+    src/GenomeTrackQuantiles.cpp:1199-1330): rows grouped by BinsManager::vals2idx of their bin columns -- expected from the oracle's
+    val2bin, IntervalSummary and StreamPercentiler<double> restatements. Counts / min / max / quantiles exact, sums to the last bits."""
+    rng = np.random.default_rng({"1d_few": 1, "2d": 2, "1d_many": 3, "include_lowest": 4}[case])
+    n = 40001
+    vals = np.where(rng.random(n) < 0.15, np.nan, rng.lognormal(size=n) * 3)  # one sign: no cancellation in the sums
+    a = np.where(rng.random(n) < 0.05, np.nan, np.round(rng.random(n) * 40) / 40)  # many values exactly on breaks
+    b = rng.normal(size=n)
+    if case == "1d_few":
+        bcols, breaks, il = [a], [np.linspace(0, 1, 11)], False
+    elif case == "include_lowest":
+        bcols, breaks, il = [a], [np.array([0, 0.1, 0.35, 0.5, 0.9])], True
+    elif case == "2d":
+        bcols, breaks, il = [a, b], [np.linspace(0, 1, 6), np.array([-10, -1, 0, 0.5, 3])], False
+    else:  # more bins than a thread block's shared memory holds records for
+        bcols, breaks, il = [b], [np.linspace(-3, 3, 1501)], False
+    idx, total = _bin_index(bcols, breaks, il)
+    dv = gpu_ctx.alloc(n, np.float64).from_host(vals)
+    dc = [gpu_ctx.alloc(n, np.float64).from_host(c) for c in bcols]
+    got = gpu.bins_summary(gpu_ctx, dv, dc, n, breaks, il)
+    exp = _exp_summary_rows([vals[idx == k] for k in range(total)])
+    _check_summary_rows(got, exp, case)
+    p = [0, 0.1, 0.5, 0.99, 1]
+    q, nk = gpu.bins_quantiles(gpu_ctx, dv, dc, n, breaks, p, il)
+    assert q.shape == (len(p), total)
+    for k in range(total):
+        e, en = port.gquantiles(vals[idx == k], p)
+        assert nk[k] == en and np.array_equal(q[:, k], e, equal_nan=True), (case, k)
+    q0, nk0 = gpu.bins_quantiles(gpu_ctx, dv, dc, 0, breaks, p, il)  # no rows: every bin empty
+    assert np.isnan(q0).all() and not nk0.any()
+    assert gpu.bins_summary(gpu_ctx, dv, dc, 0, breaks, il)[:, 0].sum() == 0
+    with pytest.raises(gpu.MishaGpuError, match="not sorted|not unique"):
+        gpu.bins_summary(gpu_ctx, dv, dc[:1], n, [[0, 0.5, 0.2]], il)

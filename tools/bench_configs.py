@@ -181,6 +181,27 @@ def main():
             loop_ms = (time.perf_counter() - t0) * 1e3 / 200 * (len(sf) - 1)
             report("Q gintervals.quantiles, segments of %s, 5 quantiles (host clock, copies included)" % name, ms, 8 * int(sf[-1]), int(sf[-1]),
                    {"segments": len(sf) - 1, "per_segment_loop_ms_extrapolated": round(loop_ms, 1)})
+    if "B" in want:
+        # gbins.summary / gbins.quantiles / gintervals.summary shape: 50 M rows, value and bin columns in HBM, 100 bins (host clock:
+        # the calls return host arrays)
+        rng = np.random.default_rng(6)
+        n = int(50_000_000 * args.scale)
+        dv = ctx.alloc(n, np.float64).from_host(np.where(rng.random(n) < 0.05, np.nan, rng.lognormal(size=n)).astype(np.float32))
+        db_ = ctx.alloc(n, np.float64).from_host(np.clip(rng.lognormal(size=n) * 10, 0, 100).astype(np.float32))
+        br = np.linspace(0, 100, 101)
+        p = np.array([0.1, 0.5, 0.9])
+        sz = rng.integers(100, 401, n // 250 + 1)
+        sf = np.concatenate([[0], np.cumsum(sz)])
+        sf = sf[sf <= n].astype(np.int64)
+        for name, fn, byts in (("gbins.summary, 100 bins", lambda: gpu.bins_summary(ctx, dv, [db_], n, [br]), 16 * n),
+                               ("gbins.quantiles, 100 bins, 3 quantiles", lambda: gpu.bins_quantiles(ctx, dv, [db_], n, [br], p), 16 * n),
+                               ("gintervals.summary, %d segments of 100-400 rows" % (len(sf) - 1), lambda: gpu.summary_segmented(ctx, dv, sf), 8 * n)):
+            for _ in range(2):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            report("B " + name + " (host clock)", (time.perf_counter() - t0) * 1e3 / args.steps, byts, n)
     ctx.close()
 
 
