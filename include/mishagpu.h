@@ -183,6 +183,8 @@ int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows, int64_
 					 int func, double param, double *d_partial, void *stream);
 /* host arithmetic of gtracksummary's result vector (src/GenomeTrackSummary.cpp:148-155): 6 partials -> 7 outputs */
 void mg_summary_finalize(const double partial[6], double out[7]);
+/* the same for n records (gintervals.summary / gbins.summary result rows): partials[6 n] -> out[7 n] */
+void mg_summary_finalize_rows(const double *partials, int64_t n, double *out);
 
 /* N-D histogram (gdist). h_breaks = concatenated break vectors, nbreaks[d] each; d_counts has prod(nbreaks[d]-1)  */
 /* uint64 cells, first dimension fastest; counts are ACCUMULATED (zero them first). Bit-exact bins.               */

@@ -1740,6 +1740,12 @@ extern "C" void mg_summary_finalize(const double p[6], double out[7])
 		out[6] = nan;
 }
 
+extern "C" void mg_summary_finalize_rows(const double *partials, int64_t n, double *out)
+{
+	for (int64_t i = 0; i < n; ++i)
+		mg_summary_finalize(partials + 6 * i, out + 7 * i);
+}
+
 // ---- gdist -----------------------------------------------------------------------------------------------------------
 static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, const int *nbreaks, int include_lowest, HistSpec &hs, double **d_breaks,
 							 cudaStream_t st)

@@ -402,6 +402,13 @@ def summary_finalize(partial6):
     return out
 
 
+def summary_finalize_rows(partials):
+    p = _arr(partials, np.float64).reshape(-1, 6)
+    out = np.empty((len(p), 7), dtype=np.float64)
+    load().mg_summary_finalize_rows(_p(p), c_i64(len(p)), _p(out))
+    return out
+
+
 def hist_dev(ctx, dcols, n, breaks_list, counts, include_lowest=False, stream=None):
     nb = np.array([len(b) for b in breaks_list], dtype=np.int32)
     allb = _arr(np.concatenate([np.asarray(b, dtype=np.float64) for b in breaks_list]), np.float64)
@@ -439,7 +446,7 @@ def summary_segmented(ctx, dcol, seg_first, stream=None):
     nseg = len(sf) - 1
     part = np.empty((max(nseg, 0), 6), dtype=np.float64)
     ctx._check(ctx.lib.mg_summary_segmented(ctx.h, c_vp(dcol.ptr if dcol is not None else None), c_i64(nseg), _p(sf), _p(part), c_vp(stream)))
-    return np.array([summary_finalize(r) for r in part]).reshape(max(nseg, 0), 7)
+    return summary_finalize_rows(part)
 
 
 def _bins_args(dcols, breaks_list):
@@ -455,7 +462,7 @@ def bins_summary(ctx, dvals, dcols, n, breaks_list, include_lowest=False, stream
     part = np.empty((total, 6), dtype=np.float64)
     ctx._check(ctx.lib.mg_bins_summary(ctx.h, c_vp(dvals.ptr), c_int(len(dcols)), ptrs, c_i64(n), _p(allb), _p(nb), c_int(int(include_lowest)),
                                        _p(part), c_vp(stream)))
-    return np.array([summary_finalize(r) for r in part]).reshape(total, 7)
+    return summary_finalize_rows(part)
 
 
 def bins_quantiles(ctx, dvals, dcols, n, breaks_list, percentiles, include_lowest=False, stream=None):
