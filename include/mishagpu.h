@@ -205,7 +205,7 @@ int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const dou
 /* StreamPercentiler<double> at every scope interval (:726-741) and reads the percentiles with calc_medians (:95-120). Here    */
 /* the value column of ALL rows stays in HBM and segment s = rows [h_seg_first[s], h_seg_first[s+1]) is one scope interval's  */
 /* run of rows (nseg + 1 ascending host offsets). Segments up to 16384 rows are sorted in shared memory, one warp or one     */
-/* thread block each, all in at most two launches; longer ones go through mg_quantiles' counting passes. Same arithmetic as  */
+/* thread block each; longer ones are radix-selected by one thread block each: at most three launches. Same arithmetic as  */
 /* mg_quantiles; h_out[k * nseg + s] = quantile k of segment s (NaN for a segment without values), h_nkept[s] (may be NULL)  */
 /* its number of non-NaN values. Synchronises the stream. At most 64 quantiles per call.                                      */
 int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t nseg, const int64_t *h_seg_first, int nq, const double *h_percentiles,

@@ -2091,14 +2091,19 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 		return 0;
 	MG_REQUIRE(ctx, d_vals || h_seg_first[nseg] == 0, "mg_quantiles_segmented: no value column");
 	cudaStream_t st = mg_stream(stream);
-	std::vector<int32_t> list[2]; // 0: one warp per segment, 1: one thread block per segment
-	std::vector<int64_t> large;   // beyond a thread block's shared memory: the whole-device counting passes of mg_quantiles
+	// 0: one warp per segment (sort), 1: one thread block per segment (sort), 2: one thread block per segment (radix select in global memory)
+	std::vector<int32_t> list[4]; // 3: radix select with the counting spread over the device (k_qlong_*)
+	std::vector<int64_t> large; // 2^31 rows and more: the whole-device counting passes of mg_quantiles
 	for (int64_t s = 0; s < nseg; ++s) {
 		const int64_t c = h_seg_first[s + 1] - h_seg_first[s];
 		if (c <= MG_QSEG_WARP_CAP)
 			list[0].push_back((int32_t)s);
 		else if (c <= MG_QSEG_BLOCK_CAP)
 			list[1].push_back((int32_t)s);
+		else if (c <= MG_QLONG_MIN)
+			list[2].push_back((int32_t)s);
+		else if (c < ((int64_t)1 << 31))
+			list[3].push_back((int32_t)s);
 		else
 			large.push_back(s);
 	}
@@ -2117,7 +2122,7 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 	a.out = (double *)(d_buf + off_out);
 	a.nkept = (long long *)(d_buf + off_kept);
 	size_t list_pos = 0;
-	for (int tier = 0; tier < 2; ++tier) {
+	for (int tier = 0; tier < 3; ++tier) {
 		if (list[tier].empty())
 			continue;
 		int32_t *d_list = (int32_t *)(d_buf + off_list) + list_pos;
@@ -2128,19 +2133,65 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 		if (tier == 0) {
 			const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(a.nlist, 8), (int64_t)ctx->sm_count * 16);
 			k_qseg<true><<<grid, 256, 8 * MG_QSEG_WARP_CAP * 4, st>>>(a);
-		} else {
+		} else if (tier == 1) {
 			const int smem = MG_QSEG_BLOCK_CAP * 4;
 			MG_CUDA(ctx, cudaFuncSetAttribute(k_qseg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 			const unsigned grid = (unsigned)std::min<int64_t>(a.nlist, (int64_t)ctx->sm_count * 3);
 			k_qseg<false><<<grid, MG_QSEG_BLOCK_THREADS, smem, st>>>(a);
+		} else {
+			const int smem = std::min(2 * nq, (int)MG_QSEL_MAXT) * 1024; // a 256-entry histogram per distinct prefix
+			MG_CUDA(ctx, cudaFuncSetAttribute(k_qseg_select, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+			const unsigned grid = (unsigned)std::min<int64_t>(a.nlist, (int64_t)ctx->sm_count * (smem <= 32768 ? 4 : 1));
+			k_qseg_select<<<grid, MG_QSEL_THREADS, smem, st>>>(a);
 		}
 		MG_LAUNCH_CHECK(ctx);
+	}
+	char *d_long = nullptr;
+	if (!list[3].empty()) {
+		const size_t nl = list[3].size();
+		std::vector<int32_t> chunk_seg;
+		std::vector<int64_t> chunk_off;
+		for (size_t e = 0; e < nl; ++e) {
+			const int64_t c = h_seg_first[list[3][e] + 1] - h_seg_first[list[3][e]];
+			for (int64_t o = 0; o < c; o += MG_QLONG_CHUNK) {
+				chunk_seg.push_back((int32_t)e);
+				chunk_off.push_back(o);
+			}
+		}
+		const size_t nch = chunk_seg.size();
+		const int maxS = std::min(2 * nq, (int)MG_QSEL_MAXT);
+		const size_t o_state = 0, o_hist = o_state + nl * sizeof(QlongState), o_off = (o_hist + nl * (size_t)maxS * 1024 + 7) & ~(size_t)7,
+					 o_cseg = o_off + nch * 8, o_list = o_cseg + nch * 4, tot = o_list + nl * 4;
+		MG_CUDA(ctx, cudaMallocAsync(&d_long, tot, st));
+		MG_CUDA(ctx, cudaMemsetAsync(d_long, 0, o_off, st)); // states and counters
+		MG_CUDA(ctx, cudaMemcpyAsync(d_long + o_off, chunk_off.data(), nch * 8, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_long + o_cseg, chunk_seg.data(), nch * 4, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_long + o_list, list[3].data(), nl * 4, cudaMemcpyHostToDevice, st));
+		QlongArgs ql;
+		ql.a = a;
+		ql.a.list = (const int32_t *)(d_long + o_list);
+		ql.a.nlist = (int64_t)nl;
+		ql.chunk_seg = (const int32_t *)(d_long + o_cseg);
+		ql.chunk_off = (const int64_t *)(d_long + o_off);
+		ql.state = (QlongState *)(d_long + o_state);
+		ql.hist = (uint32_t *)(d_long + o_hist);
+		ql.maxS = maxS;
+		const int smem = maxS * 1024;
+		MG_CUDA(ctx, cudaFuncSetAttribute(k_qlong_count, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		for (int pass = 0; pass < 4; ++pass) {
+			k_qlong_count<<<(unsigned)nch, MG_QSEL_THREADS, smem, st>>>(ql, pass);
+			MG_LAUNCH_CHECK(ctx);
+			k_qlong_update<<<(unsigned)nl, 256, 0, st>>>(ql, pass);
+			MG_LAUNCH_CHECK(ctx);
+		}
 	}
 	std::vector<long long> kept((size_t)nseg);
 	MG_CUDA(ctx, cudaMemcpyAsync(h_out, d_buf + off_out, (size_t)nq * nseg * 8, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaMemcpyAsync(kept.data(), d_buf + off_kept, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
 	MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
+	if (d_long)
+		MG_CUDA(ctx, cudaFreeAsync(d_long, st));
 	std::vector<double> q((size_t)nq);
 	for (int64_t s : large) {
 		int64_t nk = 0;
@@ -2253,7 +2304,11 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 		for (int d = 0; d < ndim; ++d)
 			cols.col[d] = d_bin_cols[d];
 		const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8);
-		k_bins_index<<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_idx, d_counts);
+		const bool smem = hs.total <= MG_BINS_SCATTER_SMEM_MAX;
+		if (smem)
+			k_bins_index<true><<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_idx, d_counts);
+		else
+			k_bins_index<false><<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_idx, d_counts);
 		MG_LAUNCH_CHECK(ctx);
 		std::vector<unsigned long long> counts(T);
 		MG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_counts, T * 8, cudaMemcpyDeviceToHost, st));
@@ -2261,7 +2316,10 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 		for (size_t b = 0; b < T; ++b)
 			seg_first[b + 1] = seg_first[b] + (int64_t)counts[b];
 		MG_CUDA(ctx, cudaMemcpyAsync(d_counts, seg_first.data(), T * 8, cudaMemcpyHostToDevice, st)); // the bins' write cursors
-		k_bins_scatter<<<grid, 256, 0, st>>>(d_vals, d_idx, n, d_counts, d_sorted);
+		if (smem)
+			k_bins_scatter<true><<<grid, 256, 0, st>>>(d_vals, d_idx, n, hs.total, d_counts, d_sorted);
+		else
+			k_bins_scatter<false><<<grid, 256, 0, st>>>(d_vals, d_idx, n, hs.total, d_counts, d_sorted);
 		MG_LAUNCH_CHECK(ctx);
 		const int rc = mg_quantiles_segmented(ctx, d_sorted, (int64_t)T, seg_first.data(), nq, h_percentiles, h_out, h_nkept, stream);
 		MG_CUDA(ctx, cudaFreeAsync(d_buf, st));

@@ -734,6 +734,372 @@ template <bool WARP> __global__ void __launch_bounds__(WARP ? 256 : MG_QSEG_BLOC
 	}
 }
 
+// Segments too long for a thread block's shared memory: one thread block per segment selects the target ranks by MSD radix
+// select over the segment in global memory -- four passes of 8 bits; a pass counts, per distinct key prefix a target rank fell
+// into (a sorted list in shared memory, found by bisection), the next digit of the keys under it (mg_warp_count).
+// Count `what` (0xffffffff = nothing) into hist, one shared-memory atomic per distinct value for the first two values a warp
+// holds (the high digits of a track's keys are nearly constant across a warp), one per lane for the rest.
+__device__ __forceinline__ void mg_warp_count(uint32_t *hist, uint32_t what, int lane)
+{
+	unsigned remaining = __ballot_sync(0xffffffffu, what != 0xffffffffu);
+#pragma unroll
+	for (int r = 0; r < 2; ++r) {
+		if (!remaining)
+			return;
+		const int leader = __ffs(remaining) - 1;
+		const uint32_t lv = __shfl_sync(0xffffffffu, what, leader);
+		const unsigned m = __ballot_sync(0xffffffffu, what == lv) & remaining;
+		if (lane == leader)
+			atomicAdd(&hist[lv], (uint32_t)__popc(m));
+		remaining &= ~m;
+	}
+	if ((remaining >> lane) & 1u)
+		atomicAdd(&hist[what], 1u);
+}
+
+#define MG_QSEL_THREADS 1024
+#define MG_QSEL_UNROLL 8 // keys a thread has in flight: one thread block streams its segment alone
+#define MG_QSEL_MAXT (MG_QS_MAXSLOTS) // 2 x 64 quantiles
+__global__ void __launch_bounds__(MG_QSEL_THREADS) k_qseg_select(const QsegArgs a)
+{
+	extern __shared__ uint32_t qsel_hist[]; // [slot][256]
+	__shared__ uint32_t s_slot[MG_QSEL_MAXT];          // distinct prefixes of this pass, ascending
+	__shared__ uint32_t s_prefix[MG_QSEL_MAXT];        // per target: the digits of its key found so far
+	__shared__ unsigned long long s_rank[MG_QSEL_MAXT]; // per target: its rank among the keys under its prefix
+	__shared__ unsigned long long s_target[MG_QSEL_MAXT];
+	__shared__ int s_T, s_S;
+	__shared__ unsigned long long s_nan;
+	const int tid = threadIdx.x, lane = tid & 31;
+	for (int64_t e = blockIdx.x; e < a.nlist; e += gridDim.x) {
+		const int64_t seg = a.list[e];
+		const int64_t first = a.seg_first[seg];
+		const int64_t c = a.seg_first[seg + 1] - first, c32 = (c + 31) & ~(int64_t)31;
+		const double *v = a.vals + first;
+		// pass 0: top digit of every key, NaN rows
+		for (int t = tid; t < 256; t += MG_QSEL_THREADS)
+			qsel_hist[t] = 0;
+		if (tid == 0)
+			s_nan = 0;
+		__syncthreads();
+		unsigned long long nans = 0;
+		for (int64_t base = 0; base < c32; base += MG_QSEL_UNROLL * MG_QSEL_THREADS) {
+			uint32_t key[MG_QSEL_UNROLL];
+			double raw[MG_QSEL_UNROLL]; // all loads first (clamped, unconditional): a thread block streams its segment alone
+#pragma unroll
+			for (int j = 0; j < MG_QSEL_UNROLL; ++j)
+				raw[j] = __ldcs(v + min(base + j * MG_QSEL_THREADS + tid, c - 1));
+#pragma unroll
+			for (int j = 0; j < MG_QSEL_UNROLL; ++j)
+				key[j] = base + j * MG_QSEL_THREADS + tid < c ? mg_qs_key(raw[j]) : 0xfffffffeu; // beyond the segment: neither a key nor a NaN row
+#pragma unroll
+			for (int j = 0; j < MG_QSEL_UNROLL; ++j) {
+				nans += key[j] == 0xffffffffu;
+				const uint32_t what = key[j] >= 0xfffffffeu ? 0xffffffffu : key[j] >> 24;
+				mg_warp_count(qsel_hist, what, lane);
+			}
+		}
+		nans = __reduce_add_sync(0xffffffffu, (unsigned)nans);
+		if (lane == 0 && nans)
+			atomicAdd(&s_nan, nans);
+		__syncthreads();
+		const long long N = c - (long long)s_nan;
+		if (tid == 0) {
+			a.nkept[seg] = N;
+			int T = 0;
+			if (N > 0) {
+				for (int k = 0; k < a.nq; ++k) { // floor / ceil of (N - 1) q, sorted and unique (insertion: T <= 128)
+					const double idx = __dmul_rn((double)(N - 1), a.pct[k]);
+					const unsigned long long two[2] = {(unsigned long long)floor(idx), (unsigned long long)ceil(idx)};
+					for (int h = 0; h < 2; ++h) {
+						int j = 0;
+						while (j < T && s_target[j] < two[h])
+							++j;
+						if (j < T && s_target[j] == two[h])
+							continue;
+						for (int m = T; m > j; --m)
+							s_target[m] = s_target[m - 1];
+						s_target[j] = two[h];
+						++T;
+					}
+				}
+			}
+			s_T = T;
+		}
+		__syncthreads();
+		const int T = s_T;
+		if (T == 0) {
+			for (int k = tid; k < a.nq; k += MG_QSEL_THREADS)
+				a.out[(int64_t)k * a.nseg + seg] = mg_nan();
+			__syncthreads();
+			continue;
+		}
+		if (tid < T) { // digit 0 of every target
+			unsigned long long r = s_target[tid], acc = 0;
+			int d = 0;
+			for (; d < 255; ++d) {
+				if (acc + qsel_hist[d] > r)
+					break;
+				acc += qsel_hist[d];
+			}
+			s_rank[tid] = r - acc;
+			s_prefix[tid] = (uint32_t)d;
+		}
+		__syncthreads();
+		for (int pass = 1; pass < 4; ++pass) {
+			const int shift = 32 - 8 * pass; // the key's bits above `shift` are the prefix, the 8 below the digit counted now
+			if (tid == 0) {
+				int S = 0;
+				for (int t = 0; t < T; ++t)
+					if (!S || s_slot[S - 1] != s_prefix[t]) // targets ascend, so do their prefixes
+						s_slot[S++] = s_prefix[t];
+				s_S = S;
+			}
+			__syncthreads();
+			const int S = s_S;
+			for (int t = tid; t < S * 256; t += MG_QSEL_THREADS)
+				qsel_hist[t] = 0;
+			__syncthreads();
+			for (int64_t base = 0; base < c32; base += MG_QSEL_UNROLL * MG_QSEL_THREADS) {
+				uint32_t keys[MG_QSEL_UNROLL];
+				double raw[MG_QSEL_UNROLL];
+#pragma unroll
+				for (int j = 0; j < MG_QSEL_UNROLL; ++j)
+					raw[j] = __ldcs(v + min(base + j * MG_QSEL_THREADS + tid, c - 1));
+#pragma unroll
+				for (int j = 0; j < MG_QSEL_UNROLL; ++j)
+					keys[j] = base + j * MG_QSEL_THREADS + tid < c ? mg_qs_key(raw[j]) : 0xffffffffu;
+#pragma unroll
+				for (int j = 0; j < MG_QSEL_UNROLL; ++j) {
+					uint32_t what = 0xffffffffu;
+					{
+						const uint32_t key = keys[j];
+						if (key != 0xffffffffu) {
+							const uint32_t pre = key >> shift;
+							int lo = 0, hi = S;
+							while (lo < hi) {
+								const int mid = (lo + hi) >> 1;
+								if (s_slot[mid] < pre)
+									lo = mid + 1;
+								else
+									hi = mid;
+							}
+							if (lo < S && s_slot[lo] == pre)
+								what = ((uint32_t)lo << 8) | ((key >> (shift - 8)) & 255u);
+						}
+					}
+					mg_warp_count(qsel_hist, what, lane);
+				}
+			}
+			__syncthreads();
+			if (tid < T) {
+				int j = 0;
+				while (s_slot[j] != s_prefix[tid])
+					++j;
+				const uint32_t *h = qsel_hist + j * 256;
+				unsigned long long r = s_rank[tid], acc = 0;
+				int d = 0;
+				for (; d < 255; ++d) {
+					if (acc + h[d] > r)
+						break;
+					acc += h[d];
+				}
+				s_rank[tid] = r - acc;
+				s_prefix[tid] = (s_prefix[tid] << 8) | (uint32_t)d;
+			}
+			__syncthreads();
+		}
+		for (int k = tid; k < a.nq; k += MG_QSEL_THREADS) {
+			const double idx = __dmul_rn((double)(N - 1), a.pct[k]);
+			const double f1 = floor(idx);
+			const unsigned long long i1 = (unsigned long long)f1, i2 = (unsigned long long)ceil(idx);
+			int p1 = 0, p2 = 0;
+			while (s_target[p1] != i1)
+				++p1;
+			while (s_target[p2] != i2)
+				++p2;
+			const double w = __dsub_rn(idx, f1);
+			a.out[(int64_t)k * a.nseg + seg] =
+				__dadd_rn(__dmul_rn((double)mg_fkey_inv(s_prefix[p1]), __dsub_rn(1.0, w)), __dmul_rn((double)mg_fkey_inv(s_prefix[p2]), w));
+		}
+		__syncthreads();
+	}
+}
+
+// Segments beyond MG_QLONG_MIN rows: the same radix select with the counting spread over the device -- k_qlong_count, one thread
+// block per chunk of MG_QLONG_CHUNK rows (shared-memory histograms flushed into the segment's global ones), and k_qlong_update,
+// one thread block per segment, which descends the target ranks by one digit and prepares the next pass; eight launches, no
+// host round trip in between.
+#define MG_QLONG_MIN ((int64_t)1 << 18)
+#define MG_QLONG_CHUNK ((int64_t)1 << 16)
+struct QlongState {
+	unsigned long long nan;
+	long long N;
+	int T, S;
+	unsigned long long target[MG_QSEL_MAXT], rank[MG_QSEL_MAXT];
+	uint32_t prefix[MG_QSEL_MAXT], slot[MG_QSEL_MAXT];
+};
+struct QlongArgs {
+	QsegArgs a;                // list = the long segments
+	const int32_t *chunk_seg;  // per chunk: index into a.list
+	const int64_t *chunk_off;  // per chunk: first row, relative to its segment
+	QlongState *state;         // per long segment
+	uint32_t *hist;            // per long segment: maxS x 256 counters, zero before every counting pass
+	int maxS;
+};
+
+__global__ void __launch_bounds__(MG_QSEL_THREADS) k_qlong_count(const QlongArgs q, int pass)
+{
+	extern __shared__ uint32_t qsel_hist[];
+	__shared__ uint32_t s_slot[MG_QSEL_MAXT];
+	__shared__ unsigned long long s_nan;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int e = q.chunk_seg[blockIdx.x];
+	const int64_t seg = q.a.list[e];
+	const int64_t first = q.a.seg_first[seg] + q.chunk_off[blockIdx.x];
+	const int64_t c = min(q.a.seg_first[seg + 1] - first, MG_QLONG_CHUNK);
+	const double *v = q.a.vals + first;
+	const QlongState *stt = q.state + e;
+	const int S = pass == 0 ? 1 : stt->S;
+	if (pass > 0 && stt->T == 0)
+		return;
+	for (int t = tid; t < S * 256; t += MG_QSEL_THREADS)
+		qsel_hist[t] = 0;
+	if (tid < S && pass > 0)
+		s_slot[tid] = stt->slot[tid];
+	if (tid == 0)
+		s_nan = 0;
+	__syncthreads();
+	const int shift = 32 - 8 * pass;
+	unsigned nans = 0;
+	for (int64_t base = 0; base < c; base += MG_QSEL_UNROLL * MG_QSEL_THREADS) {
+		double raw[MG_QSEL_UNROLL];
+#pragma unroll
+		for (int j = 0; j < MG_QSEL_UNROLL; ++j)
+			raw[j] = __ldcs(v + min(base + j * MG_QSEL_THREADS + tid, c - 1));
+#pragma unroll
+		for (int j = 0; j < MG_QSEL_UNROLL; ++j) {
+			const bool in = base + j * MG_QSEL_THREADS + tid < c;
+			const uint32_t key = in ? mg_qs_key(raw[j]) : 0xffffffffu;
+			uint32_t what = 0xffffffffu;
+			if (pass == 0) {
+				nans += in && key == 0xffffffffu;
+				if (key != 0xffffffffu)
+					what = key >> 24;
+			} else if (key != 0xffffffffu) {
+				const uint32_t pre = key >> shift;
+				int lo = 0, hi = S;
+				while (lo < hi) {
+					const int mid = (lo + hi) >> 1;
+					if (s_slot[mid] < pre)
+						lo = mid + 1;
+					else
+						hi = mid;
+				}
+				if (lo < S && s_slot[lo] == pre)
+					what = ((uint32_t)lo << 8) | ((key >> (shift - 8)) & 255u);
+			}
+			mg_warp_count(qsel_hist, what, lane);
+		}
+	}
+	if (pass == 0) {
+		nans = __reduce_add_sync(0xffffffffu, nans);
+		if (lane == 0 && nans)
+			atomicAdd(&s_nan, (unsigned long long)nans);
+	}
+	__syncthreads();
+	uint32_t *g = q.hist + (size_t)e * q.maxS * 256;
+	for (int t = tid; t < S * 256; t += MG_QSEL_THREADS)
+		if (qsel_hist[t])
+			atomicAdd(g + t, qsel_hist[t]);
+	if (pass == 0 && tid == 0 && s_nan)
+		atomicAdd(&q.state[e].nan, s_nan);
+}
+
+__global__ void __launch_bounds__(256) k_qlong_update(const QlongArgs q, int pass)
+{
+	const int e = blockIdx.x, tid = threadIdx.x;
+	const int64_t seg = q.a.list[e];
+	QlongState *stt = q.state + e;
+	uint32_t *g = q.hist + (size_t)e * q.maxS * 256;
+	if (pass == 0) {
+		if (tid == 0) {
+			const long long N = (q.a.seg_first[seg + 1] - q.a.seg_first[seg]) - (long long)stt->nan;
+			stt->N = N;
+			q.a.nkept[seg] = N;
+			int T = 0;
+			if (N > 0)
+				for (int k = 0; k < q.a.nq; ++k) {
+					const double idx = __dmul_rn((double)(N - 1), q.a.pct[k]);
+					const unsigned long long two[2] = {(unsigned long long)floor(idx), (unsigned long long)ceil(idx)};
+					for (int h = 0; h < 2; ++h) {
+						int j = 0;
+						while (j < T && stt->target[j] < two[h])
+							++j;
+						if (j < T && stt->target[j] == two[h])
+							continue;
+						for (int m = T; m > j; --m)
+							stt->target[m] = stt->target[m - 1];
+						stt->target[j] = two[h];
+						++T;
+					}
+				}
+			stt->T = T;
+		}
+		__syncthreads();
+	}
+	const int T = stt->T;
+	if (T == 0) {
+		if (pass == 3)
+			for (int k = tid; k < q.a.nq; k += blockDim.x)
+				q.a.out[(int64_t)k * q.a.nseg + seg] = mg_nan();
+		return;
+	}
+	const int S_old = pass == 0 ? 1 : stt->S;
+	if (tid < T) {
+		int j = 0;
+		if (pass > 0)
+			while (stt->slot[j] != stt->prefix[tid])
+				++j;
+		const uint32_t *h = g + j * 256;
+		unsigned long long r = pass == 0 ? stt->target[tid] : stt->rank[tid], acc = 0;
+		int d = 0;
+		for (; d < 255; ++d) {
+			if (acc + h[d] > r)
+				break;
+			acc += h[d];
+		}
+		stt->rank[tid] = r - acc;
+		stt->prefix[tid] = pass == 0 ? (uint32_t)d : (stt->prefix[tid] << 8) | (uint32_t)d;
+	}
+	__syncthreads();
+	if (pass < 3) {
+		for (int t = tid; t < S_old * 256; t += blockDim.x) // the counters of the pass just read
+			g[t] = 0;
+		if (tid == 0) {
+			int S = 0;
+			for (int t = 0; t < T; ++t)
+				if (!S || stt->slot[S - 1] != stt->prefix[t])
+					stt->slot[S++] = stt->prefix[t];
+			stt->S = S;
+		}
+		return;
+	}
+	const long long N = stt->N;
+	for (int k = tid; k < q.a.nq; k += blockDim.x) {
+		const double idx = __dmul_rn((double)(N - 1), q.a.pct[k]);
+		const double f1 = floor(idx);
+		const unsigned long long i1 = (unsigned long long)f1, i2 = (unsigned long long)ceil(idx);
+		int p1 = 0, p2 = 0;
+		while (stt->target[p1] != i1)
+			++p1;
+		while (stt->target[p2] != i2)
+			++p2;
+		const double w = __dsub_rn(idx, f1);
+		q.a.out[(int64_t)k * q.a.nseg + seg] =
+			__dadd_rn(__dmul_rn((double)mg_fkey_inv(stt->prefix[p1]), __dsub_rn(1.0, w)), __dmul_rn((double)mg_fkey_inv(stt->prefix[p2]), w));
+	}
+}
+
 // ---- gintervals.summary: one IntervalSummary per scope interval (src/GenomeTrackSummary.cpp:248-431) ---------------------------
 // A warp per segment (the run of rows of one scope interval); the row value is narrowed to float first, as `float val =
 // scanner.last_real(0)` does. Segments beyond `big` rows only get their record initialised: the host sends those through
@@ -861,45 +1227,85 @@ __global__ void __launch_bounds__(256) k_bins_finalize(const unsigned long long 
 	}
 }
 
-// gbins.quantiles, step 1: the bin of every row whose (float-narrowed) value is not NaN, -1 otherwise, and the bins' populations.
-// Lanes of a warp that hit the same bin count once (__match_any_sync).
-__global__ void __launch_bounds__(256) k_bins_index(const double *__restrict__ vals, const HistCols cols, int64_t n, const HistSpec hs, int32_t *idx_out,
-													 unsigned long long *counts)
+// gbins.quantiles, step 1: the bin of every row whose (float-narrowed) value is not NaN, -1 otherwise, and the bins' populations
+// (SMEM: counted in a shared-memory histogram per thread block, flushed once; otherwise global atomics -- many bins, little contention).
+#define MG_BINS_SCATTER_SMEM_MAX 2048
+#define MG_BINS_SCATTER_ITEMS 8
+template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_index(const double *__restrict__ vals, const HistCols cols, int64_t n,
+																		   const HistSpec hs, int32_t *idx_out, unsigned long long *counts)
 {
-	const int lane = threadIdx.x & 31;
+	__shared__ uint32_t sh_cnt[SMEM ? MG_BINS_SCATTER_SMEM_MAX : 1];
+	if (SMEM) {
+		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x)
+			sh_cnt[b] = 0;
+		__syncthreads();
+	}
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	const int64_t n32 = (n + 31) & ~(int64_t)31; // whole warps stay in the loop for the warp-wide match
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		long long idx = -1;
-		if (i < n) {
-			const float v = (float)__ldcs(vals + i);
-			if (v == v)
-				idx = mg_vals2idx(cols, hs, i);
-			idx_out[i] = (int32_t)idx;
+		const float v = (float)__ldcs(vals + i);
+		if (v == v)
+			idx = mg_vals2idx(cols, hs, i);
+		idx_out[i] = (int32_t)idx;
+		if (idx >= 0) {
+			if (SMEM)
+				atomicAdd(&sh_cnt[idx], 1u); // a thread block sees fewer than 2^32 rows
+			else
+				atomicAdd(counts + idx, 1ull);
 		}
-		const unsigned peers = __match_any_sync(0xffffffffu, idx);
-		if (idx >= 0 && lane == __ffs(peers) - 1)
-			atomicAdd(counts + idx, (unsigned long long)__popc(peers));
+	}
+	if (SMEM) {
+		__syncthreads();
+		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x)
+			if (sh_cnt[b])
+				atomicAdd(counts + b, (unsigned long long)sh_cnt[b]);
 	}
 }
 
-// step 2: scatter the values next to their bin's others (order inside a bin is irrelevant: the segment gets sorted)
-__global__ void __launch_bounds__(256) k_bins_scatter(const double *__restrict__ vals, const int32_t *__restrict__ idx_in, int64_t n,
-													   unsigned long long *cursor, double *out)
+// step 2: scatter the values next to their bin's others (order inside a bin is irrelevant: the segment gets selected / sorted).
+// SMEM: a thread block takes tiles of 256 x 8 rows; a shared-memory atomic gives every row its rank among the tile's rows of its
+// bin, one global atomic per (tile, bin) reserves the range, the rows then store. Otherwise one global atomic per row.
+template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_scatter(const double *__restrict__ vals, const int32_t *__restrict__ idx_in,
+																			 int64_t n, long long total, unsigned long long *cursor, double *out)
 {
-	const int lane = threadIdx.x & 31;
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	const int64_t n32 = (n + 31) & ~(int64_t)31;
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
-		const int idx = i < n ? idx_in[i] : -1;
-		const unsigned peers = __match_any_sync(0xffffffffu, idx);
-		const int leader = __ffs(peers) - 1;
-		unsigned long long base = 0;
-		if (idx >= 0 && lane == leader)
-			base = atomicAdd(cursor + idx, (unsigned long long)__popc(peers));
-		base = __shfl_sync(0xffffffffu, base, leader);
-		if (idx >= 0)
-			out[base + __popc(peers & ((1u << lane) - 1))] = vals[i];
+	__shared__ uint32_t sh_cnt[SMEM ? MG_BINS_SCATTER_SMEM_MAX : 1];
+	__shared__ unsigned long long sh_base[SMEM ? MG_BINS_SCATTER_SMEM_MAX : 1];
+	if (!SMEM) {
+		const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+		for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+			const int idx = idx_in[i];
+			if (idx >= 0)
+				out[atomicAdd(cursor + idx, 1ull)] = vals[i];
+		}
+		return;
+	}
+	const int64_t tile = (int64_t)blockDim.x * MG_BINS_SCATTER_ITEMS;
+	for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+		for (int b = threadIdx.x; b < (int)total; b += blockDim.x)
+			sh_cnt[b] = 0;
+		__syncthreads();
+		int idx[MG_BINS_SCATTER_ITEMS];
+		uint32_t rank[MG_BINS_SCATTER_ITEMS];
+		double v[MG_BINS_SCATTER_ITEMS];
+#pragma unroll
+		for (int j = 0; j < MG_BINS_SCATTER_ITEMS; ++j) {
+			const int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+			idx[j] = i < n ? idx_in[i] : -1;
+			v[j] = i < n ? __ldcs(vals + i) : 0.;
+		}
+#pragma unroll
+		for (int j = 0; j < MG_BINS_SCATTER_ITEMS; ++j)
+			rank[j] = idx[j] >= 0 ? atomicAdd(&sh_cnt[idx[j]], 1u) : 0u;
+		__syncthreads();
+		for (int b = threadIdx.x; b < (int)total; b += blockDim.x)
+			if (sh_cnt[b])
+				sh_base[b] = atomicAdd(cursor + b, (unsigned long long)sh_cnt[b]);
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < MG_BINS_SCATTER_ITEMS; ++j)
+			if (idx[j] >= 0)
+				out[sh_base[idx[j]] + rank[j]] = v[j];
+		__syncthreads();
 	}
 }
 

@@ -249,7 +249,7 @@ def test_quantiles_golden_and_oracle(gpu_ctx):
 def test_quantiles_segmented(gpu_ctx):
     """mg_quantiles_segmented (gintervals.quantiles: one percentiler per scope interval, src/GenomeTrackQuantiles.cpp:726-741):
     every segment bit for bit against the oracle's StreamPercentiler<double> restatement and against the golden vectors --
-    empty, one-row, all-NaN segments, the warp / thread block / whole-device tiers and their borders."""
+    empty, one-row, all-NaN segments, the four tiers (warp sort, thread block sort, thread block select, multi-block select) and their borders."""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gquantiles_vectors.npz"))
     pcts = g["pcts"]
@@ -264,7 +264,7 @@ def test_quantiles_segmented(gpu_ctx):
         assert nk[s] == int(np.sum(~np.isnan(g[k].astype(np.float32))))
 
     rng = np.random.default_rng(97)
-    sizes = [0, 1, 2, 31, 32, 33, 255, 256, 257, 0, 1000, 5000, 16383, 16384, 16385, 40000, 7, 0] + list(rng.integers(0, 600, 300))
+    sizes = [0, 1, 2, 31, 32, 33, 255, 256, 257, 0, 1000, 5000, 16383, 16384, 16385, 40000, 7, 0, 300001, 20000, 270000, 262144, 262145] + list(rng.integers(0, 600, 300))
     sf = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n = int(sf[-1])
     col = np.where(rng.random(n) < 0.2, np.nan, np.round(rng.normal(size=n) * 50) / 8 + rng.normal(size=n) * (rng.random(n) < 0.5))
@@ -272,10 +272,17 @@ def test_quantiles_segmented(gpu_ctx):
     col[rng.integers(0, n, 50)] = -np.inf
     col[sf[10]:sf[11]] = np.nan      # a 1000-row segment without values
     col[sf[16]:sf[17]] = np.nan
+    col[sf[19]:sf[20]] = np.nan      # a select-tier segment without values
+    col[sf[20]:sf[21]] = np.nan      # and one of the multi-block tier
+    col[sf[18]:sf[18] + 250000] = 1.5  # long runs of one value in a select-tier segment
     d = gpu_ctx.alloc(n, np.float64).from_host(col)
     p = np.concatenate([[0, 1, 0.5, 0.9], rng.random(9)])
     got, nk = gpu.quantiles_segmented(gpu_ctx, d, sf, p)
     assert got.shape == (len(p), len(sizes))
+    p64 = np.concatenate([[1, 0], rng.random(62)])  # the most quantiles a call takes: 128 target ranks in the select tier
+    got64, _ = gpu.quantiles_segmented(gpu_ctx, d, sf[15:24], p64)
+    for s in range(15, 23):
+        assert np.array_equal(got64[:, s - 15], port.gquantiles(col[sf[s]:sf[s + 1]], p64)[0], equal_nan=True), s
     for s in range(len(sizes)):
         exp, en = port.gquantiles(col[sf[s]:sf[s + 1]], p)
         assert nk[s] == en, s
