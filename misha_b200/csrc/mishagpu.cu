@@ -2261,10 +2261,13 @@ extern "C" int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, cons
 		for (int d = 0; d < ndim; ++d)
 			cols.col[d] = d_bin_cols[d];
 		const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8);
-		if (hs.total <= MG_BINS_SMEM_MAX)
-			k_bins_summary<true><<<grid, 256, (size_t)hs.total * 48, st>>>(d_vals, cols, n, hs, d_acc);
-		else
-			k_bins_summary<false><<<grid, 256, 0, st>>>(d_vals, cols, n, hs, d_acc);
+		if (hs.total <= MG_BINS_SMEM_MAX) {
+			int rep = 1;
+			while (rep < 8 && hs.total * rep * 2 <= MG_BINS_SMEM_MAX)
+				rep *= 2;
+			k_bins_summary<true><<<grid, 256, (size_t)hs.total * rep * 48, st>>>(d_vals, cols, n, hs, rep, d_acc);
+		} else
+			k_bins_summary<false><<<grid, 256, 0, st>>>(d_vals, cols, n, hs, 1, d_acc);
 		MG_LAUNCH_CHECK(ctx);
 	}
 	k_bins_finalize<<<(unsigned)std::min<long long>(mg_div_up(hs.total, 256), 1024), 256, 0, st>>>(d_acc, hs.total, d_part);

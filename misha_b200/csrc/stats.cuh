@@ -1167,13 +1167,17 @@ __global__ void __launch_bounds__(256) k_bins_init(unsigned long long *acc, long
 		mg_bins_rec_init(acc + 6 * b);
 }
 
+// SMEM: `rep` (a power of two) copies of every bin's record in shared memory, a lane uses copy lane % rep -- the rows of a warp
+// crowd into few bins, and a shared-memory double add is a compare-and-swap loop that same-address neighbours make retry.
 template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_summary(const double *__restrict__ vals, const HistCols cols, int64_t n,
-																			 const HistSpec hs, unsigned long long *acc)
+																			 const HistSpec hs, int rep, unsigned long long *acc)
 {
 	extern __shared__ unsigned long long bins_sh[];
 	unsigned long long *a = SMEM ? bins_sh : acc;
+	const int nrec = SMEM ? (int)hs.total * rep : 0;
+	const int mine = SMEM ? (int)(threadIdx.x & (rep - 1)) : 0;
 	if (SMEM) {
-		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x)
+		for (int b = threadIdx.x; b < nrec; b += blockDim.x)
 			mg_bins_rec_init(a + 6 * b);
 		__syncthreads();
 	}
@@ -1182,7 +1186,7 @@ template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_summary(const
 		const long long idx = mg_vals2idx(cols, hs, i);
 		if (idx < 0)
 			continue;
-		unsigned long long *r = a + 6 * idx;
+		unsigned long long *r = a + 6 * (SMEM ? idx * rep + mine : idx);
 		const double v = (double)(float)__ldcs(vals + i);
 		atomicAdd(r, 1ull);
 		if (!isnan(v)) {
@@ -1195,9 +1199,9 @@ template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_summary(const
 	}
 	if (SMEM) {
 		__syncthreads();
-		for (int b = threadIdx.x; b < (int)hs.total; b += blockDim.x) {
+		for (int b = threadIdx.x; b < nrec; b += blockDim.x) {
 			const unsigned long long *r = a + 6 * b;
-			unsigned long long *g = acc + 6 * (long long)b;
+			unsigned long long *g = acc + 6 * (long long)(b / rep);
 			if (!r[0])
 				continue;
 			atomicAdd(g, r[0]);
