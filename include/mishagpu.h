@@ -75,6 +75,7 @@ enum mg_func {
 };
 
 /* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */
+enum mg_kmer_mode { MG_KMER_COUNT = 0 /* "kmer.count" */, MG_KMER_FRAC = 1 /* "kmer.frac" */ };
 enum mg_pwm_mode { MG_PWM_TOTAL = 0 /* "pwm" */, MG_PWM_MAX = 1 /* "pwm.max" */, MG_PWM_MAX_POS = 2 /* "pwm.max.pos" */, MG_PWM_COUNT = 3 /* "pwm.count" */ };
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -169,6 +170,13 @@ int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, int64_t fir
 /* h_logp: L x 4 float log-probabilities (A,C,G,T) after normalisation and prior (mg_pssm_logp). strand: 1 / -1. */
 int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
 		   const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream);
+/* kmer.count / kmer.frac vtracks (KmerCounter::score_interval, src/KmerCounter.cpp:38-176; SequenceVarProcessor calls it per  */
+/* row like score_interval of the PWM scorer): occurrences of `kmer` (case folded; A, C, G, T only, at most 32 bases) starting   */
+/* inside the window, on the forward strand (strand 1), as its reverse complement (strand -1) or both (strand 0); `extend`       */
+/* lets a match run up to k - 1 bases past the window's end. MG_KMER_FRAC divides by the (window length - k + 1) starts, twice     */
+/* that for both strands, in float as the reference does. Bit-exact. d_out[i] for rows [first, first + count).                    */
+int mg_kmer(mg_ctx *ctx, const mg_seq *s, const char *kmer, int mode, int extend, int strand, const mg_rows *rows, int64_t first, int64_t count,
+			int64_t sshift, int64_t eshift, double *d_out, void *stream);
 /* PSSM rows (L x 4 probabilities, A,C,G,T) -> the float log table the reference scores with                    */
 /* (src/PWMScorer.cpp:1452-1459, src/DnaPSSM.cpp:77-106,703-719). Host arithmetic, float, bit-exact.            */
 int mg_pssm_logp(const double *h_pssm, int L, double prior, float *h_logp);
@@ -227,6 +235,13 @@ int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, const double *c
 /* mg_quantiles_segmented. h_out[k * total_bins + b], NaN for an empty bin; h_nkept[b] may be NULL. Synchronises.        */
 int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, const double *const *d_bin_cols, int64_t n, const double *h_breaks,
 					  const int *nbreaks, int include_lowest, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept, void *stream);
+
+/* global.percentile / global.percentile.min / global.percentile.max (src/TrackVarProcessor.cpp:98-110): the column of the   */
+/* vtrack's avg / min / max values (mg_*_window) is mapped IN PLACE through the track's precomputed percentile table --     */
+/* h_breaks[nbreaks] and h_bins[nbreaks], the `breaks` attribute and the values of <track>/vars/pv.percentiles, which the    */
+/* host keeps reading as before (src/TrackExpressionVars.cpp:1788-1823). NaN stays NaN; a value at or below the first break */
+/* gets bins[0], one above the last break 1. Enqueues on the stream.                                                        */
+int mg_percentile_lookup(mg_ctx *ctx, double *d_col, int64_t n, const double *h_breaks, const double *h_bins, int nbreaks, void *stream);
 
 /* gscreen: merge consecutive TRUE rows (d_flag[i] == 1) of rows [first, first+count) into intervals. Outputs are   */
 /* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */

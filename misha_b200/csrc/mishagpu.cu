@@ -1468,6 +1468,46 @@ extern "C" int mg_pssm_logp(const double *h_pssm, int L, double prior, float *h_
 	return 0;
 }
 
+extern "C" int mg_kmer(mg_ctx *ctx, const mg_seq *s, const char *kmer, int mode, int extend, int strand, const mg_rows *rows, int64_t first,
+					   int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, kmer && kmer[0], "Kmer string cannot be empty"); // src/KmerCounter.cpp:12-15
+	MG_REQUIRE(ctx, mode == MG_KMER_COUNT || mode == MG_KMER_FRAC, "unsupported kmer mode %d", mode);
+	MG_REQUIRE(ctx, strand == 0 || strand == 1 || strand == -1, "strand must be 0, 1 or -1");
+	const size_t k = strlen(kmer);
+	MG_REQUIRE(ctx, k <= 32, "kmer of %d bases: the device path compares at most 32", (int)k);
+	KmerQuery q;
+	q.fwd = q.rev = 0;
+	for (size_t j = 0; j < k; ++j) {
+		const char c = (char)toupper((unsigned char)kmer[j]);
+		const char *at = strchr("ACGT", c);
+		MG_REQUIRE(ctx, at != nullptr, "kmer \"%s\": the device path matches A, C, G, T only", kmer);
+		const uint64_t code = (uint64_t)(at - "ACGT");
+		q.fwd |= code << (2 * j);
+		q.rev |= (3 - code) << (2 * (k - 1 - j));
+	}
+	if (!count)
+		return 0;
+	q.rows = rows->src;
+	q.first = first;
+	q.count = count;
+	q.sshift = sshift;
+	q.eshift = eshift;
+	q.table = s->d_table;
+	q.chrom_sizes = ctx->d_chrom_sizes;
+	q.k = (int)k;
+	q.mode = mode;
+	q.extend = extend;
+	q.strand = strand;
+	q.out = d_out;
+	const int64_t blocks_needed = mg_div_up(count, 8);
+	const int64_t cap = (int64_t)ctx->sm_count * 16;
+	k_kmer<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), 256, 0, mg_stream(stream)>>>(q);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
 extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand,
 					  float score_thresh, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out,
 					  void *stream)
@@ -2335,6 +2375,28 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 	if (h_nkept)
 		for (size_t b = 0; b < T; ++b)
 			h_nkept[b] = 0;
+	return 0;
+}
+
+// ---- global.percentile* ------------------------------------------------------------------------------------------------------
+extern "C" int mg_percentile_lookup(mg_ctx *ctx, double *d_col, int64_t n, const double *h_breaks, const double *h_bins, int nbreaks, void *stream)
+{
+	MG_REQUIRE(ctx, n >= 0 && h_breaks && h_bins, "mg_percentile_lookup: bad arguments");
+	cudaStream_t st = mg_stream(stream);
+	HistSpec hs;
+	double *d_breaks = nullptr, *d_bins = nullptr;
+	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, 0, hs, &d_breaks, st)) // BinFinder::init's checks (src/BinFinder.cpp:10-43)
+		return 1;
+	MG_CUDA(ctx, cudaMallocAsync(&d_bins, sizeof(double) * nbreaks, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(d_bins, h_bins, sizeof(double) * nbreaks, cudaMemcpyHostToDevice, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st)); // h_bins may be pageable: staged before the call returns
+	if (n > 0) {
+		const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(n, 256 * 4), (int64_t)ctx->sm_count * 16);
+		k_percentile_lookup<<<grid, 256, 0, st>>>(d_col, n, hs, d_bins);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	MG_CUDA(ctx, cudaFreeAsync(d_bins, st));
+	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	return 0;
 }
 

@@ -339,3 +339,77 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 			mg_st_stream(q.out + i, result);
 	}
 }
+
+// ---- kmer.count / kmer.frac (KmerCounter::score_interval, src/KmerCounter.cpp:38-176) -------------------------------------------
+// A warp per row. The reference fetches [ws, xe) (xe = the window's end extended by k - 1 when `extend`, clipped to the chromosome:
+// src/GenomeSeqScorer.cpp:16-38), reverse-complements it for the reverse strand, and compares the k-mer at every start inside the
+// original window that still fits. Both strands visit the same genomic starts g in [ws, xe - k]: the forward strand matches the
+// k-mer at g, the reverse strand its reverse complement. A start is one 2k-bit compare on the packed codes plus the invalid bits
+// (a k-mer of ACGT never matches N or any other character).
+struct KmerQuery {
+	RowSrc rows;
+	int64_t first, count;
+	int64_t sshift, eshift;
+	const SeqChrom *table;
+	const int64_t *chrom_sizes;
+	uint64_t fwd, rev; // base j of the k-mer (of its reverse complement) at bits 2j
+	int k, mode, extend, strand;
+	double *out;
+};
+
+__global__ void __launch_bounds__(256) k_kmer(const KmerQuery q)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+	const int k = q.k;
+	const uint64_t cmask = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
+	const uint32_t imask = k < 32 ? (1u << k) - 1u : ~0u;
+	for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < q.count; i += nwarps) {
+		int chrom;
+		int64_t s, e, scope;
+		mg_get_row(q.rows, q.first + i, chrom, s, e, scope);
+		const int64_t chromsize = __ldg(q.chrom_sizes + chrom);
+		int64_t ws, we;
+		double result = mg_nan();
+		if (mg_window(s, e, q.sshift, q.eshift, chromsize, ws, we)) {
+			int64_t xe = we;
+			if (q.extend && k > 1) {
+				xe = we + (k - 1);
+				if (xe > chromsize)
+					xe = chromsize;
+			}
+			unsigned nf = 0, nr = 0;
+			const bool fits = xe - ws >= k;
+			if (fits) {
+				const SeqChrom ch = q.table[chrom];
+				const unsigned long long *codes = (const unsigned long long *)ch.codes;
+				const int64_t nwords = (ch.len + 31) >> 5;
+				const int64_t last = min(we - 1, xe - k);
+				for (int64_t g = ws + lane; g <= last; g += 32) {
+					const int64_t w = g >> 5;
+					const int off = (int)(g & 31);
+					const bool more = off && w + 1 < nwords;
+					const unsigned long long lo = __ldg(codes + w), hi = more ? __ldg(codes + w + 1) : 0ull;
+					const uint32_t ilo = __ldg(ch.inval + w), ihi = more ? __ldg(ch.inval + w + 1) : 0xffffffffu;
+					const unsigned long long code = (off ? (lo >> (2 * off)) | (hi << (64 - 2 * off)) : lo) & cmask;
+					const uint32_t inv = (off ? (ilo >> off) | (ihi << (32 - off)) : ilo) & imask;
+					nf += inv == 0 && code == q.fwd;
+					nr += inv == 0 && code == q.rev;
+				}
+			}
+			nf = __reduce_add_sync(0xffffffffu, nf);
+			nr = __reduce_add_sync(0xffffffffu, nr);
+			const unsigned long long total = (q.strand >= 0 ? nf : 0u) + (unsigned long long)(q.strand <= 0 ? nr : 0u);
+			if (q.mode == MG_KMER_FRAC) {
+				const unsigned long long possible = fits ? (unsigned long long)(we - ws) : 0ull;
+				unsigned long long valid = possible > (unsigned long long)(k - 1) ? possible - (unsigned long long)(k - 1) : 0ull;
+				if (q.strand == 0)
+					valid *= 2;
+				result = valid > 0 ? (double)__fdiv_rn((float)total, (float)valid) : 0.;
+			} else
+				result = (double)(float)total;
+		}
+		if (lane == 0)
+			q.out[i] = result;
+	}
+}

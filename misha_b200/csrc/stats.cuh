@@ -1313,6 +1313,21 @@ template <bool SMEM> __global__ void __launch_bounds__(256) k_bins_scatter(const
 	}
 }
 
+// ---- global.percentile / global.percentile.min / global.percentile.max ---------------------------------------------------------
+// The vtrack's avg / min / max value is replaced by the track's precomputed percentile of it (src/TrackVarProcessor.cpp:98-110):
+// bins[val2bin(v)]; a value at or below the first break gets bins[0], one above the last break 1; NaN stays NaN.
+__global__ void __launch_bounds__(256) k_percentile_lookup(double *col, int64_t n, const HistSpec hs, const double *__restrict__ bins)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const double v = col[i];
+		if (isnan(v))
+			continue;
+		const int b = mg_val2bin(hs.breaks, hs.nbreaks[0], hs.binsize[0], 0, v);
+		col[i] = b >= 0 ? __ldg(bins + b) : (v <= hs.breaks[0] ? __ldg(bins) : 1.);
+	}
+}
+
 // ---- gscreen comparison predicates on the device -----------------------------------------------------------------------------
 struct PredSpec {
 	int nterms, combine_or;

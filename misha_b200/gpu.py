@@ -12,6 +12,7 @@ from ._lib import MishaGpuError, c_dbl, c_i64, c_int, c_vp, load  # noqa: F401 (
 FUNC_IDS = {"avg": 0, "sum": 1, "min": 2, "max": 3, "stddev": 4, "quantile": 5, "nearest": 6, "size": 7, "exists": 8,
             # order-dependent functions; the *.pos ones take param = 1 for positions relative to the window start
             "lse": 9, "first": 10, "last": 11, "first.pos": 12, "last.pos": 13, "min.pos": 14, "max.pos": 15}
+KMER_MODES = {"kmer.count": 0, "kmer.frac": 1}
 PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.max.pos": 2, "pwm.count": 3}
 
 
@@ -356,6 +357,15 @@ class Sequence:
     def pwm(self, rows, logp, **kw):
         return self.pwm_dev(rows, logp, **kw).to_host()
 
+    def kmer_dev(self, rows, kmer, mode="kmer.count", extend=True, strand=0, sshift=0, eshift=0, first=0, count=None, out=None, stream=None):
+        """mg_kmer: kmer.count / kmer.frac of the rows (device column)."""
+        count = rows.n - first if count is None else count
+        out = out or self.ctx.alloc(count, np.float64)
+        c = self.ctx
+        c._check(c.lib.mg_kmer(c.h, self.h, kmer.encode(), c_int(KMER_MODES[mode]), c_int(int(extend)), c_int(strand), rows.h, c_i64(first),
+                               c_i64(count), c_i64(sshift), c_i64(eshift), c_vp(out.ptr), c_vp(stream)))
+        return out
+
     def pwm_host(self, chrom, start, end, logp, bidirect=True, extend=True, mode="pwm", strand=1, score_thresh=0.0, sshift=0, eshift=0, out=None):
         """End-to-end: host arrays in, host column out (mg_h_pwm)."""
         chrom, start, end = _arr(chrom, np.int32), _arr(start, np.int64), _arr(end, np.int64)
@@ -474,6 +484,14 @@ def bins_quantiles(ctx, dvals, dcols, n, breaks_list, percentiles, include_lowes
     ctx._check(ctx.lib.mg_bins_quantiles(ctx.h, c_vp(dvals.ptr), c_int(len(dcols)), ptrs, c_i64(n), _p(allb), _p(nb), c_int(int(include_lowest)),
                                          c_int(len(p)), _p(p), _p(out), _p(nk), c_vp(stream)))
     return out, nk
+
+
+def percentile_lookup(ctx, dcol, n, breaks, bins, stream=None):
+    """mg_percentile_lookup: global.percentile* -- the device column mapped in place through the track's percentile table."""
+    b, v = _arr(breaks, np.float64), _arr(bins, np.float64)
+    if len(b) != len(v):
+        raise MishaGpuError("percentile table: breaks and bins differ in length")
+    ctx._check(ctx.lib.mg_percentile_lookup(ctx.h, c_vp(dcol.ptr), c_i64(n), _p(b), _p(v), c_int(len(b)), c_vp(stream)))
 
 
 CMP_OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}

@@ -16,6 +16,7 @@
  * that change low-order bits / rare corner cases depending on the previous row. This file restates the
  * "fresh window" semantics; DESIGN.md lists the history-dependent corners.
  */
+#include <ctype.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -909,4 +910,78 @@ void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int b
 		}
 	}
 	free(vals);
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* kmer.count / kmer.frac: KmerCounter::score_interval + count_in_interval (src/KmerCounter.cpp:38-176),    */
+/* interval expansion src/GenomeSeqScorer.cpp:16-38, reverse complement of the fetched target               */
+/* src/GenomeSeqFetch.cpp:147-160. seq = the chromosome's bytes as stored (mixed case). mode 0 = count, 1 = */
+/* fraction; strand 0 = both, 1, -1. The reference is followed step by step: fetch, reverse-complement,     */
+/* upper-case, memcmp at every start inside the original interval.                                          */
+static char orc_complement(char c)
+{ /* basepair2complementary, src/GenomeUtils.h */
+	switch (c) {
+	case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+	case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+	default: return c;
+	}
+}
+
+void orc_kmer(const char *seq, int64_t chromsize, const char *kmer_in, int mode, int extend, int strand, int64_t n, const int64_t *start,
+			  const int64_t *end, int64_t sshift, int64_t eshift, double *out)
+{
+	const int64_t k = (int64_t)strlen(kmer_in);
+	char *kmer = (char *)malloc((size_t)k + 1);
+	for (int64_t j = 0; j <= k; ++j)
+		kmer[j] = (char)toupper((unsigned char)kmer_in[j]);
+	char *target = NULL;
+	int64_t cap = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		int64_t ws, we;
+		out[i] = ORC_NAN;
+		if (!orc_window(start[i], end[i], sshift, eshift, chromsize, &ws, &we))
+			continue;
+		int64_t xe = we;
+		if (extend && k > 1) {
+			xe = we + (k - 1);
+			if (xe > chromsize)
+				xe = chromsize;
+		}
+		const int64_t tlen = xe - ws;
+		if (tlen > cap) {
+			cap = tlen;
+			target = (char *)realloc(target, (size_t)cap);
+		}
+		uint64_t total = 0, possible = 0;
+		for (int dir = 1; dir >= -1; dir -= 2) {
+			if (!(strand == 0 || strand == dir))
+				continue;
+			uint64_t count = 0;
+			possible = 0;
+			if (tlen >= k) {
+				for (int64_t t = 0; t < tlen; ++t) {
+					char c = dir == 1 ? seq[ws + t] : orc_complement(seq[xe - 1 - t]);
+					target[t] = (char)toupper((unsigned char)c);
+				}
+				const int64_t ostart = 0; /* fetch start == original start: only the end is extended */
+				int64_t oend = tlen - (xe - we);
+				if (oend > tlen)
+					oend = tlen;
+				possible = oend > ostart ? (uint64_t)(oend - ostart) : 0;
+				for (int64_t pos = ostart; pos < oend && pos <= tlen - k; ++pos)
+					if (memcmp(target + pos, kmer, (size_t)k) == 0)
+						++count;
+			}
+			total += count;
+		}
+		if (mode == 1) {
+			uint64_t valid = possible > (uint64_t)(k - 1) ? possible - (uint64_t)(k - 1) : 0;
+			if (strand == 0)
+				valid *= 2;
+			out[i] = valid > 0 ? (double)((float)total / (float)valid) : 0.0;
+		} else
+			out[i] = (double)(float)total;
+	}
+	free(target);
+	free(kmer);
 }

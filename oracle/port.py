@@ -227,3 +227,13 @@ def pwm(seq, logp, start, end, bidirect=True, extend=True, mode="pwm", strand=1,
                   ctypes.c_int(PWM_MODES[mode]), ctypes.c_int(strand), ctypes.c_float(score_thresh), c_i64(len(start)), _p(start),
                   _p(end), c_i64(sshift), c_i64(eshift), _p(out))
     return out
+
+
+def kmer(seq, kmer, start, end, mode="kmer.count", extend=True, strand=0, sshift=0, eshift=0):
+    """kmer.count / kmer.frac of one chromosome's bytes per interval (KmerCounter restatement). Returns float64[n]."""
+    s = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+    start, end = _i64(start), _i64(end)
+    out = np.empty(len(start), dtype=np.float64)
+    lib().orc_kmer(_p(s), c_i64(len(s)), kmer.encode(), ctypes.c_int({"kmer.count": 0, "kmer.frac": 1}[mode]), ctypes.c_int(int(extend)),
+                   ctypes.c_int(strand), c_i64(len(start)), _p(start), _p(end), c_i64(sshift), c_i64(eshift), _p(out))
+    return out

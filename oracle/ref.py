@@ -153,6 +153,19 @@ def pwm_eval(groot, chrom_names, chrom_sizes, pssm, chromid, start, end, bidirec
     return out.astype(np.float64)
 
 
+def kmer_eval(groot, chrom_names, chrom_sizes, kmer, chromid, start, end, mode="kmer.count", extend=True, strand=0):
+    """KmerCounter::score_interval (src/KmerCounter.cpp:38-101) per interval."""
+    sizes = np.ascontiguousarray(chrom_sizes, dtype=np.int64)
+    chromid = np.ascontiguousarray(chromid, dtype=np.int32)
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    out = np.empty(len(start), dtype=np.float32)
+    _check(lib().ref_kmer_eval(groot.encode(), ctypes.c_int(len(chrom_names)), _names(chrom_names), _p(sizes), kmer.encode(),
+                               ctypes.c_int({"kmer.count": 0, "kmer.frac": 1}[mode]), ctypes.c_int(int(extend)), ctypes.c_int(strand),
+                               c_i64(len(start)), _p(chromid), _p(start), _p(end), _p(out)))
+    return out.astype(np.float64)
+
+
 def pssm_logp(pssm, prior):
     p = np.ascontiguousarray(pssm, dtype=np.float64)
     out = np.empty((p.shape[0], 4), dtype=np.float32)

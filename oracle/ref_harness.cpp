@@ -31,6 +31,7 @@
 #include "GIntervals.h"
 #include "PWMScorer.h"
 #include "DnaPSSM.h"
+#include "KmerCounter.h"
 #include "TrackExpressionFixedBinIterator.h"
 #include "TrackExpressionIntervals1DIterator.h"
 
@@ -236,6 +237,23 @@ extern "C" int ref_pwm_eval(const char *groot, int nchroms, const char *const *n
 	for (int64_t i = 0; i < n; ++i) {
 		GInterval iv(chromid[i], start[i], end[i], 0);
 		out[i] = scorer.score_interval(iv, ck);
+	}
+	return 0;
+	REF_CATCH
+}
+
+// kmer.count / kmer.frac vtracks: KmerCounter::score_interval (src/KmerCounter.cpp:38-101). mode: 0 = count (SUM), 1 = fraction;
+// strand: 0 = both, 1, -1.
+extern "C" int ref_kmer_eval(const char *groot, int nchroms, const char *const *names, const int64_t *sizes, const char *kmer, int mode,
+							 int extend, int strand, int64_t n, const int32_t *chromid, const int64_t *start, const int64_t *end, float *out)
+{
+	REF_TRY
+	GenomeChromKey ck;
+	make_chromkey(ck, nchroms, names, sizes);
+	KmerCounter counter(std::string(kmer), std::string(groot), (KmerCounter::CountMode)mode, extend != 0, (char)strand);
+	for (int64_t i = 0; i < n; ++i) {
+		GInterval iv(chromid[i], start[i], end[i], 0);
+		out[i] = counter.score_interval(iv, ck);
 	}
 	return 0;
 	REF_CATCH

@@ -299,3 +299,23 @@ def test_gintervals_summary_and_gbins(db):
     assert s2[..., 0].sum() == np.sum((bidx >= 0) & (port.val2bin([0, 0.05, 0.5], dv) >= 0))
     with pytest.raises(api.MishaError):
         db.gbins_summary("sparse_track", expr="dense_track")
+
+
+def test_kmer_vtrack(db):
+    """gvtrack.create(NULL, "kmer.count" / "kmer.frac", list(kmer=, extend=, strand=)) through gextract, against the KmerCounter restatement;
+    parameter checks of .vtrack_params_kmer (R/vtrack.R:292-329)."""
+    iv = db.gintervals([1, 1, 2, "X"], [1000, 200000, 50000, 199500], [1500, 200200, 50020, 200000])
+    for func, params in (("kmer.count", dict(kmer="CG")), ("kmer.frac", dict(kmer="ttagg", strand=1, extend=False)), ("kmer.count", "GGCC")):
+        db.gvtrack_create("km", None, func, params)
+        db.gvtrack_iterator("km", sshift=-50, eshift=50)
+        r = db.gextract("km", intervals=iv, iterator=iv)
+        p = params if isinstance(params, dict) else dict(kmer=params)
+        for c, _ in CHROMS:
+            m = r["chrom"] == c
+            exp = port.kmer(read_seq(c), p["kmer"], r["start"][m], r["end"][m], func, p.get("extend", True), p.get("strand", 0), -50, 50)
+            assert_same(r["km"][m], exp, f"{func} {c}")
+        db.gvtrack_rm("km")
+    with pytest.raises(api.MishaError, match="empty"):
+        db.gvtrack_create("km", None, "kmer.count", dict(kmer=""))
+    with pytest.raises(api.MishaError, match="unknown"):
+        db.gvtrack_create("km", None, "kmer.count", dict(kmer="ACG", bidirect=True))

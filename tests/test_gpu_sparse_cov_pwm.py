@@ -569,3 +569,28 @@ def test_merge_kernels_long_scope_device_grid_path():
             assert_same(got[1], exp["avg"], f"avg {sshift}")
     finally:
         ctx2.close()
+
+
+def test_kmer_golden_and_oracle(gpu_ctx, seq_testdb):
+    """mg_kmer (kmer.count / kmer.frac) bit for bit against the reference's compiled KmerCounter (tests/golden/kmer_vectors.npz, made by
+    make_kmer_fixtures.py) -- every k-mer, strand and extend combination, chromosome-edge and shorter-than-kmer rows -- and against
+    the oracle restatement with iterator shifts."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kmer_vectors.npz"))
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        for ki, kmer in enumerate(g["kmers"]):
+            for mode in ("kmer.count", "kmer.frac"):
+                for ext in (True, False):
+                    for strand in (0, 1, -1):
+                        got = seq_testdb.kmer_dev(rows, str(kmer), mode=mode, extend=ext, strand=strand).to_host()
+                        assert_same(got, g[f"{c}_k{ki}_{mode}_ext{int(ext)}_str{strand}"], f"{c} {kmer} {mode} ext={ext} strand={strand}")
+        seq = read_seq(c)
+        for sshift, eshift in ((-300, 200), (5, -5), (0, 40)):
+            for kmer, mode, strand in (("cg", "kmer.count", 0), ("TTAGG", "kmer.frac", -1)):
+                got = seq_testdb.kmer_dev(rows, kmer, mode=mode, strand=strand, sshift=sshift, eshift=eshift).to_host()
+                assert_same(got, port.kmer(seq, kmer, s, e, mode, True, strand, sshift, eshift), f"{c} {kmer} shift {sshift} {eshift}")
+    for bad, msg in (("", "empty"), ("ACGN", "A, C, G, T"), ("A" * 33, "at most 32")):
+        with pytest.raises(gpu.MishaGpuError, match=msg):
+            seq_testdb.kmer_dev(rows, bad)

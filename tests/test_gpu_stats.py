@@ -370,3 +370,23 @@ def test_bins_summary_and_quantiles(gpu_ctx, case):
     assert gpu.bins_summary(gpu_ctx, dv, dc, 0, breaks, il)[:, 0].sum() == 0
     with pytest.raises(gpu.MishaGpuError, match="not sorted|not unique"):
         gpu.bins_summary(gpu_ctx, dv, dc[:1], n, [[0, 0.5, 0.2]], il)
+
+
+def test_percentile_lookup(gpu_ctx):
+    """mg_percentile_lookup (global.percentile*, src/TrackVarProcessor.cpp:98-110) against the oracle's val2bin: values on breaks,
+    below the first, above the last, NaN; evenly spaced breaks (the ceil shortcut) and ragged ones (bisection)."""
+    rng = np.random.default_rng(8)
+    for breaks in (np.linspace(0, 2, 201), np.sort(rng.random(50)) * 3):
+        bins = np.sort(rng.random(len(breaks)))
+        v = np.concatenate([rng.normal(size=5000) + 1, breaks, breaks - 1e-9, breaks + 1e-9, [np.nan, -np.inf, np.inf, breaks[0], breaks[-1]]])
+        v = v.astype(np.float32).astype(np.float64)
+        d = gpu_ctx.alloc(len(v), np.float64).from_host(v)
+        gpu.percentile_lookup(gpu_ctx, d, len(v), breaks, bins)
+        gpu_ctx.sync()
+        got = d.to_host()
+        b = port.val2bin(breaks, np.where(np.isnan(v), 0, v))
+        exp = np.where(b >= 0, bins[np.maximum(b, 0)], np.where(v <= breaks[0], bins[0], 1.0))
+        exp[np.isnan(v)] = np.nan
+        assert np.array_equal(got, exp, equal_nan=True)
+    with pytest.raises(gpu.MishaGpuError, match="not sorted|not unique"):
+        gpu.percentile_lookup(gpu_ctx, d, 1, [0, 2, 1], [0, 0.5, 1])

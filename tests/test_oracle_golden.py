@@ -246,3 +246,18 @@ def test_order_dependent_functions_match_reference_live():
         exp = ref.sparse_eval_ext(f, cid, s, e)
         for k in exp:
             assert_same(got[k], exp[k], f"sparse {c} {k}")
+
+
+def test_kmer_matches_reference_golden():
+    """kmer.count / kmer.frac of oracle.c against the reference's compiled KmerCounter (tests/golden/kmer_vectors.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kmer_vectors.npz"))
+    for c, _ in CHROMS:
+        seq = read_seq(c)
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        for ki, kmer in enumerate(g["kmers"]):
+            for mode in ("kmer.count", "kmer.frac"):
+                for ext in (True, False):
+                    for strand in (0, 1, -1):
+                        got = port.kmer(seq, str(kmer), s, e, mode, ext, strand)
+                        assert_same(got, g[f"{c}_k{ki}_{mode}_ext{int(ext)}_str{strand}"], f"{c} {kmer} {mode} {ext} {strand}")
