@@ -156,6 +156,10 @@ def main():
             anchors = rows.n * 500
             report("C5 %s 20-mer bidirect, 1M x 500bp" % mode, ms, rows.n * (130 + 8), rows.n,
                    {"anchors_per_s": anchors / ms * 1e3, "strand_scores_per_s": 2 * anchors / ms * 1e3, "seq_staging_s": round(stage_s, 2)})
+        for kmer, strand in (("TTAGGG", 0), ("GGCCAGGCTGGTCTCGAACTCC", 1)):
+            ms = timed(torch, lambda: seq.kmer_dev(rows, kmer, strand=strand, out=out, stream=stream), args.steps)
+            report("C5-shaped kmer.count %d-mer strand %d, 1M x 500bp" % (len(kmer), strand), ms, rows.n * (130 + 8), rows.n,
+                   {"starts_per_s": rows.n * 500 / ms * 1e3})
         seq.free()
     if "Q" in want:
         # gintervals.quantiles shape: a 20 M row value column in HBM cut into segments (one per scope interval), 5 quantiles each.
