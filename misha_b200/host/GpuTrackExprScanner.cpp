@@ -57,6 +57,23 @@ void GpuTrackExprScanner::vtrack_coverage(const std::string &name, const mg_ivse
 	m_vtracks[name] = v;
 }
 
+void GpuTrackExprScanner::vtrack_kmer(const std::string &name, const mg_seq *seq, int mode, const std::string &kmer, bool extend, int strand,
+									  int64_t sshift, int64_t eshift)
+{
+	if (kmer.empty())
+		throw MishaGpuException("kmer sequence cannot be empty");
+	VTrack v;
+	v.source = VTrack::KMER;
+	v.seq = seq;
+	v.kmer_mode = mode;
+	v.kmer = kmer;
+	v.extend = extend;
+	v.strand = strand;
+	v.sshift = sshift;
+	v.eshift = eshift;
+	m_vtracks[name] = v;
+}
+
 void GpuTrackExprScanner::vtrack_pwm(const std::string &name, const mg_seq *seq, int mode, const std::vector<double> &pssm, double prior, bool bidirect,
 									 bool extend, int strand, float score_thresh, int64_t sshift, int64_t eshift)
 {
@@ -230,6 +247,11 @@ bool GpuTrackExprScanner::fill(int64_t first)
 		if (v.source == VTrack::PWM) { // PWMScorer::score_interval per row (src/SequenceVarProcessor.cpp:471) -> one mg_pwm per vtrack
 			check(mg_pwm(m_ctx, v.seq, v.logp.data(), (int)(v.logp.size() / 4), v.bidirect, v.extend, v.pwm_mode, v.strand, v.score_thresh, m_rows,
 						 first, count, v.sshift, v.eshift, m_dcols[i], nullptr));
+			done[i] = true;
+			continue;
+		}
+		if (v.source == VTrack::KMER) { // KmerCounter::score_interval per row -> one mg_kmer per vtrack
+			check(mg_kmer(m_ctx, v.seq, v.kmer.c_str(), v.kmer_mode, v.extend, v.strand, m_rows, first, count, v.sshift, v.eshift, m_dcols[i], nullptr));
 			done[i] = true;
 			continue;
 		}

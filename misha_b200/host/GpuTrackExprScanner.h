@@ -36,7 +36,7 @@ struct Interval {
 };
 
 struct VTrack {
-	enum Source { DENSE, SPARSE, COVERAGE, PWM };
+	enum Source { DENSE, SPARSE, COVERAGE, PWM, KMER };
 	Source source = DENSE;
 	const mg_dense *dense = nullptr;
 	const mg_sparse *sparse = nullptr;
@@ -46,6 +46,9 @@ struct VTrack {
 	std::vector<float> logp; // L x 4 log-probabilities (mg_pssm_logp)
 	int pwm_mode = MG_PWM_TOTAL, bidirect = 1, extend = 1, strand = 1;
 	float score_thresh = 0;
+	// kmer.count / kmer.frac (KmerCounter, src/KmerCounter.cpp): mg_kmer_mode, the k-mer; extend / strand above (strand 0 = both)
+	int kmer_mode = MG_KMER_COUNT;
+	std::string kmer;
 	int func = MG_AVG;   // enum mg_func
 	double param = 0;    // percentile of MG_QUANTILE
 	int64_t sshift = 0, eshift = 0;
@@ -66,6 +69,9 @@ public:
 	// score.thresh = )): pssm = L x 4 probabilities (A, C, G, T), turned into the reference's log table by mg_pssm_logp
 	void vtrack_pwm(const std::string &name, const mg_seq *seq, int mode, const std::vector<double> &pssm, double prior = 0.01, bool bidirect = true,
 					bool extend = true, int strand = 1, float score_thresh = 0, int64_t sshift = 0, int64_t eshift = 0);
+	// gvtrack.create(name, NULL, "kmer.count" | "kmer.frac", list(kmer = , extend = TRUE, strand = 0)), .vtrack_params_kmer R/vtrack.R:292-329
+	void vtrack_kmer(const std::string &name, const mg_seq *seq, int mode, const std::string &kmer, bool extend = true, int strand = 0,
+					 int64_t sshift = 0, int64_t eshift = 0);
 	void vtrack_rm(const std::string &name);
 
 	// Fixed-bin iterator (iterator = binsize) or intervals iterator over `scope`. The scope is sorted by (chromid, start) as

@@ -8,6 +8,7 @@
 //   ivset <name> <file chrom0> ...           (per chromosome: int64 n, n starts, n ends)
 //   vtrack <vname> dense|sparse|coverage <source name> <func id> <param> <sshift> <eshift>
 //   seq <name> <file chrom0> ...             (ASCII bases per chromosome)
+//   kmer <vname> <seq name> <mode 0 count / 1 frac> <kmer> <extend> <strand> <sshift> <eshift>
 //   pwm <vname> <seq name> <mode> <pssm file: float64 L x 4> <prior> <bidirect> <extend> <strand> <score thresh> <sshift> <eshift>
 //   scope <file>                             (int64 n, then n x {int64 chromid, start, end})
 //   iterator <binsize> | iterator intervals <file>
@@ -76,6 +77,12 @@ int main(int argc, char **argv)
 			int64_t ss, es;
 		};
 		std::vector<PwmSpec> pwms;
+		struct KmerSpec {
+			std::string name, seq, kmer;
+			int mode, extend, strand;
+			int64_t ss, es;
+		};
+		std::vector<KmerSpec> kmers;
 		std::vector<Interval> scope, iter_intervals;
 		int64_t binsize = 0, buffer = int64_t(1) << 20;
 		bool use_iter_intervals = false;
@@ -158,6 +165,10 @@ int main(int argc, char **argv)
 				in >> p.name >> p.seq >> p.mode >> path >> p.prior >> p.bidirect >> p.extend >> p.strand >> p.thresh >> p.ss >> p.es;
 				p.pssm = read_raw<double>(path);
 				pwms.push_back(p);
+			} else if (cmd == "kmer") {
+				KmerSpec k;
+				in >> k.name >> k.seq >> k.mode >> k.kmer >> k.extend >> k.strand >> k.ss >> k.es;
+				kmers.push_back(k);
 			} else if (cmd == "scope") {
 				std::string path;
 				in >> path;
@@ -193,6 +204,8 @@ int main(int argc, char **argv)
 				}
 				for (auto &p : pwms)
 					scanner.vtrack_pwm(p.name, seqs.at(p.seq), p.mode, p.pssm, p.prior, p.bidirect != 0, p.extend != 0, p.strand, p.thresh, p.ss, p.es);
+				for (auto &k : kmers)
+					scanner.vtrack_kmer(k.name, seqs.at(k.seq), k.mode, k.kmer, k.extend != 0, k.strand, k.ss, k.es);
 				// both ways of consuming the scanner must agree: the reference-shaped per-row loop and whole columns
 				const ExtractResult a = gextract(scanner, exprs, scope, binsize, use_iter_intervals ? &iter_intervals : nullptr, true);
 				const ExtractResult b = gextract(scanner, exprs, scope, binsize, use_iter_intervals ? &iter_intervals : nullptr, false);

@@ -183,15 +183,17 @@ def test_cpp_scanner_sequence_and_order_dependent_vtracks(tmp_path):
         "pwm v_pwm g 0 %s 0.01 1 1 1 0 0 0" % (tmp_path / "pssm.f64"),
         "pwm v_pmax g 1 %s 0.01 1 1 1 0 -40 40" % (tmp_path / "pssm.f64"),
         "pwm v_ppos g 2 %s 0.01 1 0 -1 0 0 0" % (tmp_path / "pssm.f64"),
+        "kmer v_kcount g 0 ac 1 0 -25 25",
+        "kmer v_kfrac g 1 TGA 0 -1 0 0",
         "scope %s" % (tmp_path / "scope.bin"),
         "iterator 170",
         "buffer 512",
-        "exprs v_lse v_first v_maxpos v_pwm v_pmax v_ppos",
+        "exprs v_lse v_first v_maxpos v_pwm v_pmax v_ppos v_kcount v_kfrac",
         "out %s" % (tmp_path / "out.bin"),
     ]) + "\n")
     r = subprocess.run([build.HOST_DEMO, str(spec)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    oc, os_, oe, iid, cols = _read_out(tmp_path / "out.bin", 6)
+    oc, os_, oe, iid, cols = _read_out(tmp_path / "out.bin", 8)
     logp = port.pssm_logp(pssm, 0.01)
     assert len(oc) > 900
     for c in range(2):
@@ -203,3 +205,5 @@ def test_cpp_scanner_sequence_and_order_dependent_vtracks(tmp_path):
         assert_close(cols[3][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, True, "pwm", 1), RTOL, "pwm")
         assert_close(cols[4][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, True, "pwm.max", 1, 0.0, -40, 40), RTOL, "pwm.max")
         assert_same(cols[5][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, False, "pwm.max.pos", -1), "pwm.max.pos")
+        assert_same(cols[6][m], port.kmer(seqs[c], "ac", os_[m], oe[m], "kmer.count", True, 0, -25, 25), "kmer.count")  # vtrack_kmer -> mg_kmer
+        assert_same(cols[7][m], port.kmer(seqs[c], "TGA", os_[m], oe[m], "kmer.frac", False, -1), "kmer.frac")
