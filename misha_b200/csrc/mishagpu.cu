@@ -2288,9 +2288,11 @@ extern "C" int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, cons
 	cudaStream_t st = mg_stream(stream);
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
 		return 1;
 	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_summary: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
 	unsigned long long *d_acc = nullptr;
 	MG_CUDA(ctx, cudaMallocAsync(&d_acc, (size_t)hs.total * 96, st));
 	double *d_part = (double *)(d_acc + 6 * hs.total);
@@ -2330,9 +2332,11 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 	cudaStream_t st = mg_stream(stream);
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
 		return 1;
 	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_quantiles: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
+	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+		return 1;
 	const size_t T = (size_t)hs.total;
 	std::vector<int64_t> seg_first(T + 1, 0);
 	char *d_buf = nullptr;
