@@ -23,20 +23,25 @@ def _dev():
 
 
 def reduce_summary(partial6):
-    """All-reduce of IntervalSummary partials {n, nn, sum, min, max, ssq}: sum / min / max as IntervalSummary::merge."""
+    """All-reduce of IntervalSummary partials {n, nn, sum, min, max, ssq}: sum / min / max as IntervalSummary::merge. One record
+    (gsummary) or an array of records of shape (..., 6) -- the per-bin partials of gbins.summary, which every rank holds for the
+    same bins -- reduced in the same three collectives."""
     import torch
     import torch.distributed as dist
     p = np.asarray(partial6, dtype=np.float64)
+    if p.shape[-1] != 6:
+        raise ValueError("summary partials have 6 values per record")
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return p.copy()
-    t = torch.from_numpy(p.copy()).to(_dev())
-    sums = t[[0, 1, 2, 5]].contiguous()
-    mn, mx = t[3:4].clone(), t[4:5].clone()
+    t = torch.from_numpy(p.reshape(-1, 6).copy()).to(_dev())
+    sums = t[:, [0, 1, 2, 5]].contiguous()
+    mn, mx = t[:, 3].contiguous(), t[:, 4].contiguous()
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     s = sums.cpu().numpy()
-    return np.array([s[0], s[1], s[2], float(mn.item()), float(mx.item()), s[3]], dtype=np.float64)
+    out = np.stack([s[:, 0], s[:, 1], s[:, 2], mn.cpu().numpy(), mx.cpu().numpy(), s[:, 3]], axis=1)
+    return out.reshape(p.shape)
 
 
 def reduce_hist(counts):

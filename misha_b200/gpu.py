@@ -466,13 +466,14 @@ def _bins_args(dcols, breaks_list):
     return nb, allb, ptrs, int(np.prod(nb - 1))
 
 
-def bins_summary(ctx, dvals, dcols, n, breaks_list, include_lowest=False, stream=None):
-    """mg_bins_summary: total_bins x 7 summary rows (bins flattened first dimension fastest)."""
+def bins_summary(ctx, dvals, dcols, n, breaks_list, include_lowest=False, stream=None, partials=False):
+    """mg_bins_summary: total_bins x 7 summary rows (bins flattened first dimension fastest); partials=True returns the total_bins x 6
+    IntervalSummary partials instead -- what dist.reduce_summary combines across ranks before summary_finalize_rows."""
     nb, allb, ptrs, total = _bins_args(dcols, breaks_list)
     part = np.empty((total, 6), dtype=np.float64)
     ctx._check(ctx.lib.mg_bins_summary(ctx.h, c_vp(dvals.ptr), c_int(len(dcols)), ptrs, c_i64(n), _p(allb), _p(nb), c_int(int(include_lowest)),
                                        _p(part), c_vp(stream)))
-    return summary_finalize_rows(part)
+    return part if partials else summary_finalize_rows(part)
 
 
 def bins_quantiles(ctx, dvals, dcols, n, breaks_list, percentiles, include_lowest=False, stream=None):

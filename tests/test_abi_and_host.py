@@ -112,6 +112,20 @@ tot = mdist.reduce_summary(part)
 exp = port.summary(v)
 assert tot[0] == exp[0] and tot[0] - tot[1] == exp[1] and tot[3] == exp[2] and tot[4] == exp[3]
 assert abs(tot[2] - exp[4]) <= 1e-12 * abs(exp[4])
+# gbins.summary across ranks: every rank holds the six partials of the same bins
+key = rng.random(len(v)); keys = [key[:9000], key[9000:]]
+bb = np.array([0, 0.2, 0.5, 0.7, 1.0])
+def bin_partials(vals, ks):
+    b = port.val2bin(bb, ks)
+    out = []
+    for j in range(4):
+        x = vals[b == j]; f = x[~np.isnan(x)]
+        out.append([len(x), len(f), f.sum(), f.min() if len(f) else 1.7976931348623157e308, f.max() if len(f) else -1.7976931348623157e308, (f * f).sum()])
+    return np.array(out)
+tb = mdist.reduce_summary(bin_partials(mine, keys[rank]))
+eb = bin_partials(v, key)
+assert tb.shape == (4, 6) and np.array_equal(tb[:, [0, 1, 3, 4]], eb[:, [0, 1, 3, 4]])
+assert np.all(np.abs(tb[:, [2, 5]] - eb[:, [2, 5]]) <= 1e-12 * np.abs(eb[:, [2, 5]]))
 br = np.linspace(0, 10, 41)
 h = mdist.reduce_hist(port.hist(mine, [br]))
 assert np.array_equal(h, port.hist(v, [br]))
