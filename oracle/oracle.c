@@ -985,3 +985,26 @@ void orc_kmer(const char *seq, int64_t chromsize, const char *kmer_in, int mode,
 	free(target);
 	free(kmer);
 }
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* masked.count / masked.frac: MaskedBpCounter::score_interval (src/MaskedBpCounter.cpp:19-64): lower-case  */
+/* (soft-masked) bases of the window, no extension, no strand; the fraction is float / size_t -> float.     */
+/* (Oracle only so far: the 2-bit staged sequence drops the case bit; the device path is the next step.)    */
+void orc_masked(const char *seq, int64_t chromsize, int mode, int64_t n, const int64_t *start, const int64_t *end, int64_t sshift,
+				int64_t eshift, double *out)
+{
+	for (int64_t i = 0; i < n; ++i) {
+		int64_t ws, we;
+		out[i] = ORC_NAN;
+		if (!orc_window(start[i], end[i], sshift, eshift, chromsize, &ws, &we))
+			continue;
+		uint64_t masked = 0;
+		for (int64_t t = ws; t < we; ++t)
+			masked += islower((unsigned char)seq[t]) != 0;
+		const uint64_t len = (uint64_t)(we - ws);
+		if (len == 0)
+			out[i] = 0.;
+		else
+			out[i] = mode == 1 ? (double)((float)masked / (float)len) : (double)(float)masked;
+	}
+}

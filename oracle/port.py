@@ -237,3 +237,13 @@ def kmer(seq, kmer, start, end, mode="kmer.count", extend=True, strand=0, sshift
     lib().orc_kmer(_p(s), c_i64(len(s)), kmer.encode(), ctypes.c_int({"kmer.count": 0, "kmer.frac": 1}[mode]), ctypes.c_int(int(extend)),
                    ctypes.c_int(strand), c_i64(len(start)), _p(start), _p(end), c_i64(sshift), c_i64(eshift), _p(out))
     return out
+
+
+def masked(seq, start, end, mode="masked.count", sshift=0, eshift=0):
+    """masked.count / masked.frac of one chromosome's bytes per interval (MaskedBpCounter restatement). Returns float64[n]."""
+    s = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+    start, end = _i64(start), _i64(end)
+    out = np.empty(len(start), dtype=np.float64)
+    lib().orc_masked(_p(s), c_i64(len(s)), ctypes.c_int({"masked.count": 0, "masked.frac": 1}[mode]), c_i64(len(start)), _p(start), _p(end),
+                     c_i64(sshift), c_i64(eshift), _p(out))
+    return out

@@ -166,6 +166,19 @@ def kmer_eval(groot, chrom_names, chrom_sizes, kmer, chromid, start, end, mode="
     return out.astype(np.float64)
 
 
+def masked_eval(groot, chrom_names, chrom_sizes, chromid, start, end, mode="masked.count"):
+    """MaskedBpCounter::score_interval (src/MaskedBpCounter.cpp:19-64) per interval."""
+    sizes = np.ascontiguousarray(chrom_sizes, dtype=np.int64)
+    chromid = np.ascontiguousarray(chromid, dtype=np.int32)
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    out = np.empty(len(start), dtype=np.float32)
+    _check(lib().ref_masked_eval(groot.encode(), ctypes.c_int(len(chrom_names)), _names(chrom_names), _p(sizes),
+                                 ctypes.c_int({"masked.count": 0, "masked.frac": 1}[mode]), c_i64(len(start)), _p(chromid), _p(start), _p(end),
+                                 _p(out)))
+    return out.astype(np.float64)
+
+
 def pssm_logp(pssm, prior):
     p = np.ascontiguousarray(pssm, dtype=np.float64)
     out = np.empty((p.shape[0], 4), dtype=np.float32)

@@ -32,6 +32,7 @@
 #include "PWMScorer.h"
 #include "DnaPSSM.h"
 #include "KmerCounter.h"
+#include "MaskedBpCounter.h"
 #include "TrackExpressionFixedBinIterator.h"
 #include "TrackExpressionIntervals1DIterator.h"
 
@@ -251,6 +252,22 @@ extern "C" int ref_kmer_eval(const char *groot, int nchroms, const char *const *
 	GenomeChromKey ck;
 	make_chromkey(ck, nchroms, names, sizes);
 	KmerCounter counter(std::string(kmer), std::string(groot), (KmerCounter::CountMode)mode, extend != 0, (char)strand);
+	for (int64_t i = 0; i < n; ++i) {
+		GInterval iv(chromid[i], start[i], end[i], 0);
+		out[i] = counter.score_interval(iv, ck);
+	}
+	return 0;
+	REF_CATCH
+}
+
+// masked.count / masked.frac vtracks: MaskedBpCounter::score_interval (src/MaskedBpCounter.cpp:19-64). mode: 0 = count, 1 = fraction.
+extern "C" int ref_masked_eval(const char *groot, int nchroms, const char *const *names, const int64_t *sizes, int mode, int64_t n,
+							   const int32_t *chromid, const int64_t *start, const int64_t *end, float *out)
+{
+	REF_TRY
+	GenomeChromKey ck;
+	make_chromkey(ck, nchroms, names, sizes);
+	MaskedBpCounter counter(std::string(groot), (MaskedBpCounter::CountMode)mode);
 	for (int64_t i = 0; i < n; ++i) {
 		GInterval iv(chromid[i], start[i], end[i], 0);
 		out[i] = counter.score_interval(iv, ck);

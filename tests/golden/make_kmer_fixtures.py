@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/kmer_vectors.npz (run in the build container only): outputs of the reference's OWN compiled KmerCounter
 (oracle/_ref/libmisha_ref.so, src/KmerCounter.cpp) for kmer.count / kmer.frac over the bundled example DB's sequence
-(tests/golden/testdb/seq): random intervals plus chromosome-edge and shorter-than-kmer ones, every strand / extend combination."""
+(tests/golden/testdb/seq): random intervals plus chromosome-edge and shorter-than-kmer ones, every strand / extend combination;
+and of its MaskedBpCounter (src/MaskedBpCounter.cpp) for masked.count / masked.frac over the same intervals."""
 import os
 import sys
 
@@ -30,6 +31,8 @@ def main():
         s = np.concatenate([s, [0, 0, size - 3, size - 1, size - 40, size - 8]]).astype(np.int64)
         e = np.concatenate([e, [1, 1000, size, size, size, size - 2]]).astype(np.int64)
         out[f"{c}_start"], out[f"{c}_end"] = s, e
+        for mode in ("masked.count", "masked.frac"):
+            out[f"{c}_{mode}"] = ref.masked_eval(db, names, sizes, np.full(len(s), cid), s, e, mode)
         for ki, kmer in enumerate(KMERS):
             for mode in ("kmer.count", "kmer.frac"):
                 for ext in (True, False):

@@ -261,3 +261,16 @@ def test_kmer_matches_reference_golden():
                     for strand in (0, 1, -1):
                         got = port.kmer(seq, str(kmer), s, e, mode, ext, strand)
                         assert_same(got, g[f"{c}_k{ki}_{mode}_ext{int(ext)}_str{strand}"], f"{c} {kmer} {mode} {ext} {strand}")
+
+
+def test_masked_matches_reference_golden():
+    """masked.count / masked.frac of oracle.c against the reference's compiled MaskedBpCounter (tests/golden/kmer_vectors.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kmer_vectors.npz"))
+    for c, _ in CHROMS:
+        seq = read_seq(c)
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        for mode in ("masked.count", "masked.frac"):
+            exp = g[f"{c}_{mode}"]
+            assert exp.max() > 0
+            assert_same(port.masked(seq, s, e, mode), exp, f"{c} {mode}")
