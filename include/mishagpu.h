@@ -75,6 +75,7 @@ enum mg_func {
 };
 
 /* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */
+enum mg_masked_mode { MG_MASKED_COUNT = 0 /* "masked.count" */, MG_MASKED_FRAC = 1 /* "masked.frac" */ };
 enum mg_kmer_mode { MG_KMER_COUNT = 0 /* "kmer.count" */, MG_KMER_FRAC = 1 /* "kmer.frac" */ };
 enum mg_pwm_mode { MG_PWM_TOTAL = 0 /* "pwm" */, MG_PWM_MAX = 1 /* "pwm.max" */, MG_PWM_MAX_POS = 2 /* "pwm.max.pos" */, MG_PWM_COUNT = 3 /* "pwm.count" */ };
 
@@ -177,6 +178,11 @@ int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirec
 /* that for both strands, in float as the reference does. Bit-exact. d_out[i] for rows [first, first + count).                    */
 int mg_kmer(mg_ctx *ctx, const mg_seq *s, const char *kmer, int mode, int extend, int strand, const mg_rows *rows, int64_t first, int64_t count,
 			int64_t sshift, int64_t eshift, double *d_out, void *stream);
+/* masked.count / masked.frac vtracks (MaskedBpCounter::score_interval, src/MaskedBpCounter.cpp:19-64): lower-case (soft-masked) */
+/* bases of the window -- a popcount over the lower-case bit staged per base by mg_seq_stage; MG_MASKED_FRAC divides by the      */
+/* window length in float as the reference does. Bit-exact.                                                                     */
+int mg_masked(mg_ctx *ctx, const mg_seq *s, int mode, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+			  double *d_out, void *stream);
 /* PSSM rows (L x 4 probabilities, A,C,G,T) -> the float log table the reference scores with                    */
 /* (src/PWMScorer.cpp:1452-1459, src/DnaPSSM.cpp:77-106,703-719). Host arithmetic, float, bit-exact.            */
 int mg_pssm_logp(const double *h_pssm, int L, double prior, float *h_logp);

@@ -30,6 +30,7 @@ def _gpu_func(vt):
     return POS_FUNCS.get(vt.func, vt.func)
 PWM_FUNCS = ("pwm", "pwm.max", "pwm.max.pos", "pwm.count")
 KMER_FUNCS = ("kmer.count", "kmer.frac")
+MASKED_FUNCS = ("masked.count", "masked.frac")
 
 
 # What rerror()/verror() raise in R (src/rdbutils.cpp:708-733): host-side validation and C-ABI failures are one error type.
@@ -279,6 +280,8 @@ class MishaDB:
             func = func or "coverage"
             if func != "coverage":
                 raise MishaError("Virtual track %s: function %s is not supported for interval sources by this build" % (vtrack, func))
+        elif src is None and func in MASKED_FUNCS:  # no parameters (R/vtrack.R)
+            params = {}
         elif src is None and func in KMER_FUNCS:  # .vtrack_params_kmer, R/vtrack.R:292-329
             p = dict(params) if isinstance(params, dict) else {"kmer": params}
             unknown = set(p) - {"kmer", "extend", "strand"}
@@ -291,7 +294,7 @@ class MishaDB:
             params = dict(kmer=p["kmer"], extend=bool(p.get("extend", True)), strand=int(p.get("strand", 0)))
         elif src is None:
             if func not in PWM_FUNCS:
-                raise MishaError("Virtual track %s: a NULL source requires a sequence function (pwm, pwm.max, pwm.max.pos, pwm.count, kmer.count, kmer.frac)" % vtrack)
+                raise MishaError("Virtual track %s: a NULL source requires a sequence function (pwm, pwm.max, pwm.max.pos, pwm.count, kmer.count, kmer.frac, masked.count, masked.frac)" % vtrack)
             p = dict(params) if isinstance(params, dict) else {"pssm": params}
             pssm = np.asarray(p.get("pssm"), dtype=np.float64)
             if pssm.ndim != 2 or pssm.shape[1] != 4:
@@ -406,6 +409,8 @@ class MishaDB:
         if isinstance(vt.src, Intervals):
             return self._ivset(vt).coverage_dev(rows, vt.sshift, vt.eshift)
         p = vt.params
+        if vt.func in MASKED_FUNCS:
+            return self._sequence().masked_dev(rows, mode=vt.func, sshift=vt.sshift, eshift=vt.eshift)
         if vt.func in KMER_FUNCS:
             return self._sequence().kmer_dev(rows, p["kmer"], mode=vt.func, extend=p["extend"], strand=p["strand"], sshift=vt.sshift, eshift=vt.eshift)
         logp = gpu.pssm_logp(p["pssm"], p["prior"])

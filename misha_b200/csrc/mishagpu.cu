@@ -1409,9 +1409,11 @@ extern "C" int mg_seq_stage(mg_ctx *ctx, mg_seq *s, int chromid, const char *h_a
 	MG_REQUIRE(ctx, s->h_table[chromid].codes == nullptr, "mg_seq_stage: chromosome %d already staged", chromid);
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
 	const int64_t nthreads = mg_div_up(len, 32);
-	uint32_t *codes = nullptr, *inval = nullptr;
-	if (mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads * 2 + 8, &codes) || mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads + 8, &inval))
+	uint32_t *codes = nullptr, *inval = nullptr, *lower = nullptr;
+	if (mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads * 2 + 8, &codes) || mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads + 8, &inval) ||
+		mg_alloc_tracked(ctx, s->allocs, s->bytes, nthreads + 8, &lower))
 		return 1;
+	MG_CUDA(ctx, cudaMemset(lower, 0, sizeof(uint32_t) * (nthreads + 8)));
 	MG_CUDA(ctx, cudaMemset(codes, 0, sizeof(uint32_t) * (nthreads * 2 + 8)));
 	MG_CUDA(ctx, cudaMemset(inval, 0xff, sizeof(uint32_t) * (nthreads + 8)));
 	uint8_t *d_ascii = nullptr;
@@ -1423,13 +1425,15 @@ extern "C" int mg_seq_stage(mg_ctx *ctx, mg_seq *s, int chromid, const char *h_a
 		MG_CUDA(ctx, cudaMemset(d_other, 0, sizeof(int)));
 		k_seq_pack<<<(unsigned)mg_div_up(nthreads, 256), 256>>>(d_ascii, len, codes, inval, d_other);
 		MG_LAUNCH_CHECK(ctx);
+		k_seq_lower<<<(unsigned)mg_div_up(nthreads, 256), 256>>>(d_ascii, len, lower);
+		MG_LAUNCH_CHECK(ctx);
 		MG_CUDA(ctx, cudaMemcpy(&h_other, d_other, sizeof(int), cudaMemcpyDeviceToHost));
 		cudaFree(d_other);
 		if (h_other)
 			s->has_other = true;
 	}
 	cudaFree(d_ascii);
-	SeqChrom sc{codes, inval, len};
+	SeqChrom sc{codes, inval, len, lower};
 	s->h_table[chromid] = sc;
 	MG_CUDA(ctx, cudaMemcpy(s->d_table + chromid, &sc, sizeof(SeqChrom), cudaMemcpyHostToDevice));
 	return 0;
@@ -1504,6 +1508,30 @@ extern "C" int mg_kmer(mg_ctx *ctx, const mg_seq *s, const char *kmer, int mode,
 	const int64_t blocks_needed = mg_div_up(count, 8);
 	const int64_t cap = (int64_t)ctx->sm_count * 16;
 	k_kmer<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), 256, 0, mg_stream(stream)>>>(q);
+	MG_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
+extern "C" int mg_masked(mg_ctx *ctx, const mg_seq *s, int mode, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift,
+						 double *d_out, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, mode == MG_MASKED_COUNT || mode == MG_MASKED_FRAC, "unsupported masked mode %d", mode);
+	if (!count)
+		return 0;
+	MaskedQuery q;
+	q.rows = rows->src;
+	q.first = first;
+	q.count = count;
+	q.sshift = sshift;
+	q.eshift = eshift;
+	q.table = s->d_table;
+	q.chrom_sizes = ctx->d_chrom_sizes;
+	q.mode = mode;
+	q.out = d_out;
+	const int64_t blocks_needed = mg_div_up(count, 8);
+	const int64_t cap = (int64_t)ctx->sm_count * 16;
+	k_masked<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), 256, 0, mg_stream(stream)>>>(q);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
 }

@@ -17,6 +17,7 @@ struct SeqChrom {
 	const uint32_t *codes;
 	const uint32_t *inval;
 	int64_t len;
+	const uint32_t *lower; // bit k of word t: base 32 t + k is a lower-case (soft-masked) letter
 };
 
 struct mg_seq {
@@ -408,6 +409,73 @@ __global__ void __launch_bounds__(256) k_kmer(const KmerQuery q)
 				result = valid > 0 ? (double)__fdiv_rn((float)total, (float)valid) : 0.;
 			} else
 				result = (double)(float)total;
+		}
+		if (lane == 0)
+			q.out[i] = result;
+	}
+}
+
+// ---- masked.count / masked.frac (MaskedBpCounter::score_interval, src/MaskedBpCounter.cpp:19-64) ---------------------------------
+// The lower-case bit of every base, one thread per 32 bases (staging) ...
+__global__ void __launch_bounds__(256) k_seq_lower(const uint8_t *__restrict__ ascii, int64_t len, uint32_t *lower)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t p0 = t * 32;
+	if (p0 >= len)
+		return;
+	uint32_t m = 0;
+#pragma unroll 8
+	for (int k = 0; k < 32; ++k) {
+		const int64_t p = p0 + k;
+		if (p < len) {
+			const uint8_t ch = ascii[p];
+			m |= (uint32_t)(ch >= 'a' && ch <= 'z') << k; // islower in the C locale
+		}
+	}
+	lower[t] = m;
+}
+
+// ... and a warp per row counting them over the window's words: no extension, no strand; the fraction is float / size_t -> float.
+struct MaskedQuery {
+	RowSrc rows;
+	int64_t first, count;
+	int64_t sshift, eshift;
+	const SeqChrom *table;
+	const int64_t *chrom_sizes;
+	int mode;
+	double *out;
+};
+
+__global__ void __launch_bounds__(256) k_masked(const MaskedQuery q)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+	for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < q.count; i += nwarps) {
+		int chrom;
+		int64_t s, e, scope;
+		mg_get_row(q.rows, q.first + i, chrom, s, e, scope);
+		int64_t ws, we;
+		double result = mg_nan();
+		if (mg_window(s, e, q.sshift, q.eshift, __ldg(q.chrom_sizes + chrom), ws, we)) {
+			unsigned n = 0;
+			if (we > ws) {
+				const uint32_t *lower = q.table[chrom].lower;
+				const int64_t w0 = ws >> 5, w1 = (we - 1) >> 5;
+				for (int64_t w = w0 + lane; w <= w1; w += 32) {
+					uint32_t m = __ldg(lower + w);
+					if (w == w0)
+						m &= 0xffffffffu << (ws & 31);
+					if (w == w1)
+						m &= 0xffffffffu >> (31 - ((we - 1) & 31));
+					n += __popc(m);
+				}
+			}
+			n = __reduce_add_sync(0xffffffffu, n);
+			const unsigned long long len = (unsigned long long)(we - ws);
+			if (len == 0)
+				result = 0.;
+			else
+				result = q.mode == MG_MASKED_FRAC ? (double)__fdiv_rn((float)n, (float)len) : (double)(float)n;
 		}
 		if (lane == 0)
 			q.out[i] = result;

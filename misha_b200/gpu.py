@@ -13,6 +13,7 @@ FUNC_IDS = {"avg": 0, "sum": 1, "min": 2, "max": 3, "stddev": 4, "quantile": 5, 
             # order-dependent functions; the *.pos ones take param = 1 for positions relative to the window start
             "lse": 9, "first": 10, "last": 11, "first.pos": 12, "last.pos": 13, "min.pos": 14, "max.pos": 15}
 KMER_MODES = {"kmer.count": 0, "kmer.frac": 1}
+MASKED_MODES = {"masked.count": 0, "masked.frac": 1}
 PWM_MODES = {"pwm": 0, "pwm.max": 1, "pwm.max.pos": 2, "pwm.count": 3}
 
 
@@ -356,6 +357,15 @@ class Sequence:
 
     def pwm(self, rows, logp, **kw):
         return self.pwm_dev(rows, logp, **kw).to_host()
+
+    def masked_dev(self, rows, mode="masked.count", sshift=0, eshift=0, first=0, count=None, out=None, stream=None):
+        """mg_masked: masked.count / masked.frac of the rows (device column)."""
+        count = rows.n - first if count is None else count
+        out = out or self.ctx.alloc(count, np.float64)
+        c = self.ctx
+        c._check(c.lib.mg_masked(c.h, self.h, c_int(MASKED_MODES[mode]), rows.h, c_i64(first), c_i64(count), c_i64(sshift), c_i64(eshift),
+                                 c_vp(out.ptr), c_vp(stream)))
+        return out
 
     def kmer_dev(self, rows, kmer, mode="kmer.count", extend=True, strand=0, sshift=0, eshift=0, first=0, count=None, out=None, stream=None):
         """mg_kmer: kmer.count / kmer.frac of the rows (device column)."""

@@ -989,7 +989,6 @@ void orc_kmer(const char *seq, int64_t chromsize, const char *kmer_in, int mode,
 /* ------------------------------------------------------------------------------------------------------ */
 /* masked.count / masked.frac: MaskedBpCounter::score_interval (src/MaskedBpCounter.cpp:19-64): lower-case  */
 /* (soft-masked) bases of the window, no extension, no strand; the fraction is float / size_t -> float.     */
-/* (Oracle only so far: the 2-bit staged sequence drops the case bit; the device path is the next step.)    */
 void orc_masked(const char *seq, int64_t chromsize, int mode, int64_t n, const int64_t *start, const int64_t *end, int64_t sshift,
 				int64_t eshift, double *out)
 {

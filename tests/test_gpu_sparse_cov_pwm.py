@@ -594,3 +594,19 @@ def test_kmer_golden_and_oracle(gpu_ctx, seq_testdb):
     for bad, msg in (("", "empty"), ("ACGN", "A, C, G, T"), ("A" * 33, "at most 32")):
         with pytest.raises(gpu.MishaGpuError, match=msg):
             seq_testdb.kmer_dev(rows, bad)
+
+
+def test_masked_golden_and_oracle(gpu_ctx, seq_testdb):
+    """mg_masked (masked.count / masked.frac) bit for bit against the reference's compiled MaskedBpCounter (kmer_vectors.npz) and,
+    with iterator shifts and long windows, against the oracle restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kmer_vectors.npz"))
+    for cid, (c, size) in enumerate(CHROMS):
+        s, e = g[f"{c}_start"], g[f"{c}_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid), s, e)
+        seq = read_seq(c)
+        for mode in ("masked.count", "masked.frac"):
+            assert_same(seq_testdb.masked_dev(rows, mode=mode).to_host(), g[f"{c}_{mode}"], f"{c} {mode}")
+            for sshift, eshift in ((-3000, 4000), (7, -3), (0, 31)):
+                got = seq_testdb.masked_dev(rows, mode=mode, sshift=sshift, eshift=eshift).to_host()
+                assert_same(got, port.masked(seq, s, e, mode, sshift, eshift), f"{c} {mode} shift {sshift} {eshift}")
