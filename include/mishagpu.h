@@ -19,9 +19,17 @@
  *                  GenomeTrackSparse::read_interval    src/GenomeTrackSparse.cpp:237-340  -> mg_sparse_window
  *                  IntervVarProcessor::process_coverage src/IntervVarProcessor.cpp:242-325 -> mg_coverage
  *                  PWMScorer::score_interval           src/PWMScorer.cpp:742-861          -> mg_pwm
+ *                  KmerCounter::score_interval         src/KmerCounter.cpp:38-176         -> mg_kmer
+ *                  MaskedBpCounter::score_interval     src/MaskedBpCounter.cpp:19-64      -> mg_masked
+ *                  global.percentile* lookup           src/TrackVarProcessor.cpp:98-110   -> mg_percentile_lookup
  *   consumers    IntervalSummary::update/merge         src/GenomeTrackSummary.cpp:22-69   -> mg_summary*, mg_summary_finalize
  *                BinsManager::vals2idx + counters      src/BinsManager.h:53-72, src/GenomeTrackDistribution.cpp:121-141 -> mg_hist*
  *                C_gscreen run merge                   src/GenomeTrackScreener.cpp:195-220 -> mg_screen_merge
+ *                C_gquantiles                          src/GenomeTrackQuantiles.cpp:124-262 -> mg_quantiles
+ *                gintervals_quantiles / _summary       src/GenomeTrackQuantiles.cpp:612-860, src/GenomeTrackSummary.cpp:248-431
+ *                                                                                          -> mg_quantiles_segmented, mg_summary_segmented
+ *                gbins_summary / gbins_quantiles       src/GenomeTrackSummary.cpp:433-506, src/GenomeTrackQuantiles.cpp:1199-1330
+ *                                                                                          -> mg_bins_summary, mg_bins_quantiles
  *
  * Conventions
  *   - One mg_ctx per process and GPU; calls on one ctx are serialised by the caller (R is single-threaded).
