@@ -36,9 +36,11 @@ struct mg_ctx {
 	int merge_rows = 0;      // 8: merge kernels at 8 rows per thread whatever the row source (0: chosen per launch)
 	bool hist_red = true;    // gdist over a dense track: 16-bit counters of warp pairs packed in 32-bit words, one red.shared.add per value
 	bool cov_raster = true;  // coverage over a regular grid of rows: records rasterised into the block's rows (off: per-row cursors; ablation)
-	int stage_slots = 5;     // block records a row-query thread block stages in shared memory (0: walk them through L1; ablation)
 	bool block_wm = true;    // quantiles of windows <= MG_BW_S bins walk the block-local wavelet matrices (off: ablation / tests of the
 	                         // chromosome-wide matrix)
+	int tile_kernel = 1;     // dense window functions by k_dense_tile (thread block per tile of rows, everything from shared memory);
+	                         // 0: the per-row index kernels (k_dense_prefix / k_dense_rowquery), 2: also for avg / sum alone
+	uint32_t tile_attr = 0;  // k_dense_tile instantiations whose dynamic shared-memory limit has been raised on this device
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;
 	// exact float thresholds of the last 1-D break set (mg_dense_hist streaming path)

@@ -67,10 +67,10 @@ struct DenseQuery {
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
 	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
 	uint32_t pos_rel; // bit f set: position function f is reported relative to the window start
+	uint32_t out_mask; // bit f set: out[f] is requested
 	int nq;
 	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
-	int stage_slots; // block records a thread block of the row-query kernel stages in shared memory (0 = none)
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
 };

@@ -4,17 +4,22 @@
 // so every window of <= S bins lies inside block floor(sbin / S). Inside a block the bins are ranked 0..B-1 by
 // (value, position) with NaN (and the padding past the chromosome end) ranked last; the ranks are a permutation of
 // [0, B), therefore
-//   * a wavelet matrix over the ranks has LB levels and every level has exactly B/2 zeros -- no per-level constant;
+//   * a wavelet matrix over the ranks has every level split exactly in half (B/2 zeros) -- no per-level constant;
 //   * the k-th smallest non-NaN value of a window is the k-th smallest RANK of the window's positions (k < n, n = the
-//     window's non-NaN count from the prefix entries) -- NaNs never need compacting;
-//   * the (k+1)-th is the next larger rank whose position lies in the window: a short scan of pos_of_rank.
-// A block record is LB levels of {uint64 bits[B/64], uint16 ones_before_word[B/64]} (10 bytes per 64 bins: 320 bytes a level
-// for B = 2048), one more such level marking the NaN bins (a quantile-only query gets its non-NaN count from it: two
-// lookups instead of the prefix entries and two sectors of bins), and pos_of_rank[B] (uint16).
-// Rows sorted by position walk the same 3.8 KB of levels as their neighbours. The row-query kernel stages the levels of the
-// records its 256 rows need in shared memory with one bulk copy each (cp.async.bulk + mbarrier), so the LB dependent steps
-// of a walk are shared-memory reads; a row whose record is not among the staged ones walks the same bytes through L1. The
-// value of a rank is read from the track itself: vals[b*S + pos_of_rank[rank]].
+//     window's non-NaN count) -- NaNs never need compacting.
+// Only the TOP MG_BW_WL = LB - 4 levels are stored and walked: they resolve the k-th smallest rank to its bucket of 16 consecutive
+// ranks and the number k' of window members of that bucket below it. The rest is one look at pos_of_rank: the positions of the
+// bucket's 16 ranks and of the next bucket's are 64 contiguous bytes; a 32-bit membership mask (position inside the window?)
+// gives the (k'+1)-th member = the k-th smallest, and the next set bit = the (k+1)-th smallest the interpolation of
+// src/StreamPercentiler.h:210-217 needs. That replaces 4 more levels (8 dependent rank queries) and a separate successor search.
+//
+// A block record: WL levels + one level-shaped NaN bitmap, each {uint32 bits[B/32 + 1], uint16 ones_before_word[B/32 + 1]} padded
+// to 16 bytes (the extra unit serves rank(B): a walk's upper end reaches B) -- a rank query is a 4-byte and a 2-byte load at
+// offsets derived from one index, straight from the copy a thread block stages in shared memory (no re-layout pass) or from L1;
+// then pos_of_rank[B + 16] (uint16; the tail holds B - 1, a position no window of <= S bins starting below S reaches). Inside every
+// group of 16 ranks the entries are interleaved -- halfword 2j holds rank j, halfword 2j + 1 rank j + 8 (mg_bw_pos_slot) -- so that
+// the membership test of two positions packed in one 32-bit word leaves its two result bits 16 apart in rank order.
+// The value of a rank is read from the track itself (or its staged copy): vals[b*S + pos_of_rank[rank]].
 #pragma once
 #include "common.cuh"
 #include "dense.cuh"
@@ -28,17 +33,25 @@
 #endif
 #define MG_BW_S (MG_BW_B - MG_BW_STRIDE) // longest window that is guaranteed to lie inside one block
 #define MG_BW_HALF (MG_BW_B / 2)         // zeros of every level (the ranks are a permutation of [0, B))
-#define MG_BW_UNITS (MG_BW_B / 32)                                    // 32-bit ballots per level (build only)
-#define MG_BW_WORDS (MG_BW_B / 64)                                    // 64-bit words per level
-#define MG_BW_CNT_OFFSET (MG_BW_WORDS * 8)                            // uint16 ones before each word, after the words
-#define MG_BW_LEVEL_BYTES (MG_BW_WORDS * 10)
-#define MG_BW_NAN_OFFSET (MG_BW_LB * MG_BW_LEVEL_BYTES)              // one more level-shaped bitmap: bit = the bin is NaN
-#define MG_BW_POS_OFFSET (MG_BW_NAN_OFFSET + MG_BW_LEVEL_BYTES)        // pos_of_rank[B] (uint16)
-#define MG_BW_STAGE_BYTES MG_BW_POS_OFFSET                            // what a staged record holds: the levels and the NaN level
-static_assert(MG_BW_LEVEL_BYTES % 16 == 0 && MG_BW_B <= 65536, "levels must stay 16-byte multiples (bulk copies) with 16-bit counts");
-#define MG_BW_RECORD_BYTES (MG_BW_POS_OFFSET + MG_BW_B * 2)
+#define MG_BW_BUCKET_BITS 4
+#define MG_BW_BUCKET (1 << MG_BW_BUCKET_BITS)                            // ranks resolved by the pos_of_rank scan
+#define MG_BW_WL (MG_BW_LB - MG_BW_BUCKET_BITS)                          // levels stored and walked
+#define MG_BW_UNITS (MG_BW_B / 32)                                      // 32-bit words per level
+#define MG_BW_CNT_OFFSET ((MG_BW_UNITS + 1) * 4)                         // uint16 ones before each word, after the words
+#define MG_BW_LEVEL_BYTES ((((MG_BW_UNITS + 1) * 6) + 15) & ~15)
+#define MG_BW_NAN_OFFSET (MG_BW_WL * MG_BW_LEVEL_BYTES)                 // one more level-shaped bitmap: bit = the bin is NaN
+#define MG_BW_POS_OFFSET (MG_BW_NAN_OFFSET + MG_BW_LEVEL_BYTES)           // pos_of_rank[B + 16] (uint16)
+#define MG_BW_STAGE_BYTES MG_BW_NAN_OFFSET                               // what a staged record holds: the walked levels
+#define MG_BW_POS_PAD 16
+static_assert(MG_BW_LEVEL_BYTES % 16 == 0 && MG_BW_LB <= 14, "levels must stay 16-byte multiples (bulk copies); packed position tests need B <= 2^14");
+static_assert(MG_BW_STRIDE + MG_BW_S <= MG_BW_B && MG_BW_S <= MG_BW_B / 2, "window geometry");
+#define MG_BW_RECORD_BYTES (MG_BW_POS_OFFSET + (MG_BW_B + MG_BW_POS_PAD) * 2)
+static_assert(MG_BW_RECORD_BYTES % 16 == 0, "records must stay 16-byte aligned");
 #define MG_BW_BUILD_THREADS 1024
 #define MG_BW_PER_THREAD (MG_BW_B / MG_BW_BUILD_THREADS)
+
+// where pos_of_rank keeps rank r
+__device__ __forceinline__ uint32_t mg_bw_pos_slot(uint32_t r) { return (r & ~15u) | ((r & 7u) << 1) | ((r >> 3) & 1u); }
 
 __device__ __forceinline__ uint32_t mg_bw_key(float v)
 {
@@ -48,7 +61,43 @@ __device__ __forceinline__ uint32_t mg_bw_key(float v)
 	return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
 }
 
-// one CTA per block: rank the block's bins (bitonic sort of (key, position)), then build the LB levels in shared memory
+// one level's words and counts from the ballots in sbits[] / their exclusive prefix in scnt[]
+__device__ __forceinline__ void mg_bw_store_level(uint8_t *level, const uint32_t *sbits, const uint32_t *scnt, int t)
+{
+	if (t < MG_BW_UNITS) {
+		reinterpret_cast<uint32_t *>(level)[t] = sbits[t];
+		reinterpret_cast<uint16_t *>(level + MG_BW_CNT_OFFSET)[t] = (uint16_t)scnt[t];
+	} else if (t == MG_BW_UNITS) { // the unit of rank(B): every bit below it is counted
+		reinterpret_cast<uint32_t *>(level)[t] = 0u;
+		reinterpret_cast<uint16_t *>(level + MG_BW_CNT_OFFSET)[t] = (uint16_t)(scnt[MG_BW_UNITS - 1] + __popc(sbits[MG_BW_UNITS - 1]));
+	}
+}
+
+// exclusive scan of the MG_BW_UNITS word popcounts by one warp
+__device__ __forceinline__ void mg_bw_scan_units(const uint32_t *sbits, uint32_t *scnt, int t)
+{
+	uint32_t c[MG_BW_UNITS / 32], s = 0;
+#pragma unroll
+	for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
+		c[j] = __popc(sbits[t * (MG_BW_UNITS / 32) + j]);
+		s += c[j];
+	}
+	uint32_t incl = s;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+		if (t >= d)
+			incl += o;
+	}
+	uint32_t run = incl - s;
+#pragma unroll
+	for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
+		scnt[t * (MG_BW_UNITS / 32) + j] = run;
+		run += c[j];
+	}
+}
+
+// one CTA per block: rank the block's bins (bitonic sort of (key, position)), then build the walked levels in shared memory
 __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *__restrict__ vals, int64_t nbins, uint8_t *__restrict__ records)
 {
 	__shared__ unsigned long long skey[MG_BW_B];
@@ -68,13 +117,10 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 			sbits[e >> 5] = nanbits;
 	}
 	__syncthreads();
-	if (t < MG_BW_WORDS) { // the NaN level: few words, a serial count per word is fine
-		uint32_t before = 0;
-		for (int u = 0; u < 2 * t; ++u)
-			before += __popc(sbits[u]);
-		reinterpret_cast<unsigned long long *>(rec + MG_BW_NAN_OFFSET)[t] = ((unsigned long long)sbits[2 * t + 1] << 32) | sbits[2 * t];
-		reinterpret_cast<uint16_t *>(rec + MG_BW_NAN_OFFSET + MG_BW_CNT_OFFSET)[t] = (uint16_t)before;
-	}
+	if (t < 32)
+		mg_bw_scan_units(sbits, scnt, t);
+	__syncthreads();
+	mg_bw_store_level(rec + MG_BW_NAN_OFFSET, sbits, scnt, t);
 	__syncthreads();
 	for (int k = 2; k <= MG_BW_B; k <<= 1) {
 		for (int j = k >> 1; j > 0; j >>= 1) {
@@ -96,15 +142,17 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 	for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
 		const int r = t + j * MG_BW_BUILD_THREADS;
 		mypos[j] = (uint32_t)skey[r];
-		pos_of_rank[r] = (uint16_t)mypos[j];
+		pos_of_rank[mg_bw_pos_slot((uint32_t)r)] = (uint16_t)mypos[j];
 	}
+	if (t < MG_BW_POS_PAD)
+		pos_of_rank[MG_BW_B + t] = (uint16_t)(MG_BW_B - 1);
 	__syncthreads(); // every key has been read: the buffer becomes the two rank arrays
 #pragma unroll
 	for (int j = 0; j < MG_BW_PER_THREAD; ++j)
 		cur[mypos[j]] = (uint16_t)(t + j * MG_BW_BUILD_THREADS);
 	__syncthreads();
 	uint8_t *level = rec;
-	for (int lv = 0; lv < MG_BW_LB; ++lv, level += MG_BW_LEVEL_BYTES) {
+	for (int lv = 0; lv < MG_BW_WL; ++lv, level += MG_BW_LEVEL_BYTES) {
 		const int shift = MG_BW_LB - 1 - lv;
 		uint32_t myword[MG_BW_PER_THREAD];
 #pragma unroll
@@ -115,40 +163,16 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 				sbits[e >> 5] = myword[j];
 		}
 		__syncthreads();
-		if (t < 32) { // exclusive scan of the MG_BW_UNITS word popcounts by one warp
-			uint32_t c[MG_BW_UNITS / 32], s = 0;
-#pragma unroll
-			for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
-				c[j] = __popc(sbits[t * (MG_BW_UNITS / 32) + j]);
-				s += c[j];
-			}
-			uint32_t incl = s;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-				if (t >= d)
-					incl += o;
-			}
-			uint32_t run = incl - s;
-#pragma unroll
-			for (int j = 0; j < MG_BW_UNITS / 32; ++j) {
-				scnt[t * (MG_BW_UNITS / 32) + j] = run;
-				run += c[j];
-			}
-		}
+		if (t < 32)
+			mg_bw_scan_units(sbits, scnt, t);
 		__syncthreads();
+		mg_bw_store_level(level, sbits, scnt, t);
 #pragma unroll
 		for (int j = 0; j < MG_BW_PER_THREAD; ++j) {
 			const int e = t + j * MG_BW_BUILD_THREADS;
 			const uint32_t bits = myword[j], lane = t & 31;
 			const uint32_t ones_before = scnt[e >> 5] + __popc(bits & ((1u << lane) - 1u));
-			const uint16_t v = cur[e];
-			nxt[((bits >> lane) & 1u) ? MG_BW_HALF + ones_before : (uint32_t)e - ones_before] = v;
-			if (lane == 0) { // little-endian: ballot 2w is the low half of word w
-				reinterpret_cast<uint32_t *>(level)[e >> 5] = bits;
-				if (!((e >> 5) & 1))
-					reinterpret_cast<uint16_t *>(level + MG_BW_CNT_OFFSET)[e >> 6] = (uint16_t)scnt[e >> 5];
-			}
+			nxt[((bits >> lane) & 1u) ? MG_BW_HALF + ones_before : (uint32_t)e - ones_before] = cur[e];
 		}
 		__syncthreads();
 		uint16_t *tmp = cur;
@@ -157,76 +181,83 @@ __global__ void __launch_bounds__(MG_BW_BUILD_THREADS) k_bw_build(const float *_
 	}
 }
 
-// G: the record is read from global memory through the read-only path (true) or from its shared-memory copy (false)
+// G: the levels are read from global memory through the read-only path (true) or from their shared-memory copy (false)
 template <bool G, typename T>
 __device__ __forceinline__ T mg_bw_ld(const T *p)
 {
 	return G ? __ldg(p) : *p;
 }
-// ones among positions [0, i) of a level, 0 <= i < B
+// ones among positions [0, i) of a level, 0 <= i <= B
 template <bool G>
-__device__ __forceinline__ uint32_t mg_bw_rank_lo(const uint8_t *__restrict__ lv, uint32_t i)
+__device__ __forceinline__ uint32_t mg_bw_rank(const uint8_t *__restrict__ lv, uint32_t i)
 {
-	const uint32_t w = i >> 6;
-	const unsigned long long bits = mg_bw_ld<G>(reinterpret_cast<const unsigned long long *>(lv) + w);
+	const uint32_t w = i >> 5;
+	const uint32_t bits = mg_bw_ld<G>(reinterpret_cast<const uint32_t *>(lv) + w);
 	const uint32_t c = mg_bw_ld<G>(reinterpret_cast<const uint16_t *>(lv + MG_BW_CNT_OFFSET) + w);
-	return c + __popcll(bits & ((1ull << (i & 63u)) - 1ull));
-}
-// ones among positions [0, i) of a level, 1 <= i <= B (looks at the word of position i - 1, so i == B needs no padding word)
-template <bool G>
-__device__ __forceinline__ uint32_t mg_bw_rank_hi(const uint8_t *__restrict__ lv, uint32_t i)
-{
-	const uint32_t j = i - 1u, w = j >> 6;
-	const unsigned long long bits = mg_bw_ld<G>(reinterpret_cast<const unsigned long long *>(lv) + w);
-	const uint32_t c = mg_bw_ld<G>(reinterpret_cast<const uint16_t *>(lv + MG_BW_CNT_OFFSET) + w);
-	return c + __popcll(bits << (~j & 63u));
+	return c + __popc(bits & ((1u << (i & 31u)) - 1u));
 }
 
-// non-NaN bins of the block-local window [l, r), r > l; lv = the record's levels (global or staged)
-template <bool G>
-__device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ lv, uint32_t l, uint32_t r)
+// non-NaN bins of the block-local window [l, r), r > l; rec = the record (its NaN level is read in place)
+__device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ rec, uint32_t l, uint32_t r)
 {
-	lv += MG_BW_NAN_OFFSET;
-	return (r - l) - (mg_bw_rank_hi<G>(lv, r) - mg_bw_rank_lo<G>(lv, l));
+	const uint8_t *lv = rec + MG_BW_NAN_OFFSET;
+	return (r - l) - (mg_bw_rank<true>(lv, r) - mg_bw_rank<true>(lv, l));
 }
 
-// k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l; with want2 (k + 1 < n) also the
-// (k+1)-th. lv = the record's levels (global or staged), rec = the record in global memory (pos_of_rank is read there),
-// vals_block = the track at the block's first bin.
-#ifndef MG_BW_SELECT_INLINE
-#define MG_BW_SELECT_INLINE __forceinline__
-#endif
-#ifndef MG_BW_UNROLL
-#define MG_BW_UNROLL MG_BW_LB
-#endif
+// k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l <= S; with want2 (k + 1 < n) also the
+// (k+1)-th. lv = the record's walked levels (global or staged), pos = the record's pos_of_rank in global memory, vals_block =
+// the track (or its staged copy) at the block's first bin.
 template <bool G>
-__device__ MG_BW_SELECT_INLINE void mg_bw_select(const uint8_t *__restrict__ lv, const uint8_t *__restrict__ rec, const float *__restrict__ vals_block, uint32_t l,
+__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint16_t *__restrict__ pos, const float *__restrict__ vals_block, uint32_t l,
 											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
 {
 	const uint32_t l0 = l, len = r - l;
-	uint32_t rank = 0;
-	constexpr int unroll = MG_BW_UNROLL;
-#pragma unroll unroll
-	for (int level = 0; level < MG_BW_LB; ++level, lv += MG_BW_LEVEL_BYTES) {
-		const uint32_t ol = mg_bw_rank_lo<G>(lv, l), orr = mg_bw_rank_hi<G>(lv, r);
+	uint32_t bucket = 0;
+#pragma unroll
+	for (int level = 0; level < MG_BW_WL; ++level, lv += MG_BW_LEVEL_BYTES) {
+		const uint32_t ol = mg_bw_rank<G>(lv, l), orr = mg_bw_rank<G>(lv, r);
 		const uint32_t nz = (r - l) - (orr - ol);
 		const bool one = k >= nz;
 		l = one ? MG_BW_HALF + ol : l - ol;
 		r = one ? MG_BW_HALF + orr : r - orr;
 		k = one ? k - nz : k;
-		rank = (rank << 1) | (one ? 1u : 0u);
+		bucket = (bucket << 1) | (one ? 1u : 0u);
 	}
-	const uint16_t *pos_of_rank = reinterpret_cast<const uint16_t *>(rec + MG_BW_POS_OFFSET);
-	x1 = __ldg(vals_block + __ldg(pos_of_rank + rank));
+	// the bucket's 16 ranks hold r - l >= k + 1 window members; the k-th smallest is the (k+1)-th of them in rank order, its
+	// successor the next member, here or in the ranks that follow. Membership of two positions at once: with p < B <= 2^14 in either
+	// half of a word, p + (2^15 - l0) has bit 15 set iff p >= l0 and p + (2^15 - l0 - len) has it clear iff p < l0 + len, neither
+	// addition carries into the other half.
+	const uint32_t rank0 = bucket << MG_BW_BUCKET_BITS;
+	const uint4 *p4 = reinterpret_cast<const uint4 *>(pos + rank0);
+	const uint32_t addlo = (0x8000u - l0) * 0x10001u, addhi = (0x8000u - l0 - len) * 0x10001u;
+	uint32_t m = 0;
+#pragma unroll
+	for (int g = 0; g < 4; ++g) {
+		const uint4 qv = __ldg(p4 + g);
+		const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const int j = (g & 1) * 4 + e; // word j of its group of 16 ranks: ranks j (low half) and j + 8 (high half)
+			const uint32_t in = (w[e] + addlo) & ~(w[e] + addhi) & 0x80008000u;
+			// first group: rank j -> bit j, rank j + 8 -> bit 16 + j; second group: bits 8 + j and 24 + j
+			m |= g < 2 ? in >> (15 - j) : in >> (7 - j);
+		}
+	}
+	m = __byte_perm(m, 0, 0x3120); // bytes (ranks 0-7, 16-23, 8-15, 24-31) -> rank order
+	for (uint32_t j = 0; j < k; ++j) // drop the k members below
+		m &= m - 1u;
+	const uint32_t j1 = __ffs(m) - 1;
+	x1 = mg_bw_ld<G>(vals_block + __ldg(pos + mg_bw_pos_slot(rank0 + j1)));
 	x2 = x1;
 	if (want2) {
-		// the next larger rank whose position lies in the window; exists because k + 1 < n
-		uint32_t p;
-		do {
-			++rank;
-			p = __ldg(pos_of_rank + rank);
-		} while (p - l0 >= len && rank < MG_BW_B - 1);
-		x2 = __ldg(vals_block + p);
+		m &= m - 1u;
+		uint32_t rk = rank0 + (uint32_t)__ffs(m) - 1u;
+		if (!m) { // no member among the 31 ranks that follow: walk on (exists because k + 1 < n)
+			rk = rank0 + 2 * MG_BW_BUCKET;
+			while (rk < MG_BW_B - 1 && (uint32_t)__ldg(pos + mg_bw_pos_slot(rk)) - l0 >= len)
+				++rk;
+		}
+		x2 = mg_bw_ld<G>(vals_block + __ldg(pos + mg_bw_pos_slot(rk)));
 	}
 }
 

@@ -563,85 +563,28 @@ __global__ void __launch_bounds__(256) k_dense_argext(const DenseQuery q)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_dense_rowquery: one thread per row, every function from the index structures.
+// k_dense_rowquery: one thread per row, every function from the index structures read through L1 / L2 -- the path for rows in
+// any order and at any distance from each other (k_dense_tile, dense_tile.cuh, serves sorted rows out of shared memory and falls
+// back to mg_rq_row for the tiles it cannot hold).
 //   SUM: avg / sum / nearest / size / exists   MM: min / max   Q: quantiles
 //   SD: stddev = sqrt(M2 / (n - 1)) with M2 = S2 - S1^2 / n from the prefix sums of v and v^2. When that difference has
 //       lost too many digits (low variance against the mean, or a window that is tiny against the chromosome's running
 //       sum of squares) the window is re-read and Welford's update is run in bin order, i.e. the reference's arithmetic.
 #define MG_SD_DIRECT_BINS 8
-// Resident blocks per SM, measured on B200 at the C3 shape: the kernel is bound by memory latency, so more warps win even at the
-// price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several (0.695 -> 0.616 ms for avg + max + quantile).
 #ifndef MG_RQ_THREADS
 #define MG_RQ_THREADS 256
 #endif
-#ifdef MG_RQ_MB // build-time override (tuning)
-#define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) MG_RQ_MB
-#else
+// Resident blocks per SM, measured on B200 at the C3 shape: the kernel is bound by memory latency, so more warps win even at the
+// price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several.
 #define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) (((SD) ? 1024 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 2048 : 1536)) / MG_RQ_THREADS)
-#endif
-// the levels of a block record (the pos_of_rank half is touched at one or two places per row: not worth prefetching)
-#define MG_PREFETCH_LINES (MG_BW_POS_OFFSET / 128)
-#define MG_STAGE_BLK_BITS 21
-// Staged block records (Q): the 256 rows of a thread block are neighbours in position when the rows are sorted (what the scanner
-// produces), so between them they need the records of a handful of consecutive blocks. The thread block finds the range of
-// block ids its rows need (a min / max reduction, no assumption about the row order), thread 0 issues one bulk copy per
-// record -- at most q.stage_slots, the levels only -- into dynamic shared memory, the rows compute their avg / min / max from
-// global memory while the copies fly, and the walks then run on shared memory. A row whose record is not among the staged ones
-// (another chromosome, rows far apart, unsorted rows) walks the record through L1 as before: correctness never depends on the order.
+
 template <bool SUM, bool MM, bool Q, bool SD>
-__global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const DenseQuery q)
+__device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const DenseWin &w, bool ok)
 {
-	extern __shared__ __align__(128) uint8_t s_stage[];
-	__shared__ uint64_t s_bar;
-	__shared__ uint32_t s_kmin, s_kmax;
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = i < q.count;
-	const bool staging = Q && q.stage_slots > 0 && q.use_bw;
-	if (!staging && !live)
-		return;
-	if (staging && threadIdx.x == 0) {
-		s_kmin = 0xffffffffu;
-		s_kmax = 0;
-		mg_mbar_init(&s_bar, 1);
-	}
-	DenseWin w;
 	RowSum rs;
 	rs.avg = rs.sum = rs.size = rs.exists = mg_nan();
 	double mn = mg_nan(), mx = mg_nan(), sd = mg_nan();
-	const bool ok = live && mg_dense_win(q, q.first + i, w);
 	const int64_t nb = ok ? w.ebin - w.sbin : 0;
-	const uint8_t *lv_staged = nullptr; // this row's levels in shared memory, when its record is staged
-	bool staged = false;
-	if (staging) {
-		// one key per row: chromosome in the high bits, block id in the low MG_STAGE_BLK_BITS (rows beyond either range walk through L1)
-		const uint32_t blk = nb > 0 ? (uint32_t)w.sbin / MG_BW_STRIDE : 0;
-		const uint32_t chrom = nb > 0 ? (uint32_t)(w.ch - q.table) : 0;
-		const bool mine = nb > 0 && nb <= MG_BW_S && blk < (1u << MG_STAGE_BLK_BITS) && chrom < (1u << (32 - MG_STAGE_BLK_BITS)) - 1u;
-		const uint32_t key = (chrom << MG_STAGE_BLK_BITS) | blk;
-		__syncthreads(); // the seeds and the barrier are initialised
-		const uint32_t wmin = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu), wmax = __reduce_max_sync(0xffffffffu, mine ? key : 0u);
-		if ((threadIdx.x & 31) == 0 && wmin != 0xffffffffu) {
-			atomicMin(&s_kmin, wmin);
-			atomicMax(&s_kmax, wmax);
-		}
-		__syncthreads();
-		const uint32_t kmin = s_kmin, kmax = s_kmax;
-		// one chromosome, and dense enough that the staged records serve most of the rows
-		staged = kmin <= kmax && (kmin >> MG_STAGE_BLK_BITS) == (kmax >> MG_STAGE_BLK_BITS) && kmax - kmin < 2u * (uint32_t)q.stage_slots;
-		if (staged) {
-			const uint32_t nslots = min(kmax - kmin + 1u, (uint32_t)q.stage_slots);
-			if (threadIdx.x == 0) {
-				const uint8_t *src = q.table[kmin >> MG_STAGE_BLK_BITS].bw + (size_t)(kmin & ((1u << MG_STAGE_BLK_BITS) - 1u)) * MG_BW_RECORD_BYTES;
-				mg_mbar_expect_tx(&s_bar, nslots * MG_BW_STAGE_BYTES);
-				for (uint32_t sl = 0; sl < nslots; ++sl)
-					mg_bulk_g2s(s_stage + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar);
-			}
-			if (mine && key - kmin < nslots)
-				lv_staged = s_stage + (key - kmin) * MG_BW_STAGE_BYTES;
-		}
-		if (!live) // a partial last block: its live rows wait for the copies
-			return;
-	}
 	WinBasic wb;
 	wb.n = 0;
 	wb.before = 0;
@@ -649,35 +592,18 @@ __global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)
 		rs.size = 0;
 		rs.exists = 0;
 	}
-	if (Q && q.prefetch && nb > 0 && nb <= MG_BW_S && q.use_bw && !lv_staged) {
-		// Rows that are neighbours in position share their block record (76 lines of 128 bytes) and most of their window:
-		// every thread asks for two lines of its record and one line of its window, so between them the rows of a block
-		// pull all of it towards L1 / L2 long before the dependent loads of the walk arrive.
-		const uint8_t *rec = w.ch->bw + (size_t)((uint32_t)w.sbin / MG_BW_STRIDE) * MG_BW_RECORD_BYTES;
-		const unsigned t = threadIdx.x;
-		mg_prefetch(rec + ((2 * t) % MG_PREFETCH_LINES) * 128);
-		mg_prefetch(rec + ((2 * t + 1) % MG_PREFETCH_LINES) * 128);
-		const int64_t pb = w.sbin + (int64_t)(t & 15) * 32;
-		if (pb < w.ebin)
-			mg_prefetch(w.ch->vals + pb);
-	}
 	// a quantile-only row inside one block needs neither bins nor prefix entries: its non-NaN count is in the block record
 	const bool count_from_block = Q && !SUM && !SD && !MM && q.use_bw && nb > 0 && nb <= MG_BW_S;
 	if (count_from_block) {
 		const uint32_t blk = (uint32_t)w.sbin / MG_BW_STRIDE, l = (uint32_t)w.sbin - blk * MG_BW_STRIDE;
-		if (staged) {
-			mg_mbar_wait(&s_bar, 0);
-			staged = false; // waited
-		}
-		wb.n = lv_staged ? mg_bw_count<false>(lv_staged, l, l + (uint32_t)nb)
-						 : mg_bw_count<true>(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, l, l + (uint32_t)nb);
+		wb.n = mg_bw_count(w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, l, l + (uint32_t)nb);
 	} else if (nb > 0) {
 		// one pass over the window's two partial groups feeds the sum, the count and level 0 of the pyramids
 		mg_win_basic<SUM || SD, MM, SUM || SD || Q>(w.ch, w.sbin, w.ebin, wb);
 		if (SUM || SD)
 			mg_row_sum(w.ch, wb, w.sbin, w.ebin, rs);
 	}
-	if (SUM) { // every column is stored as soon as it is known: short live ranges keep the kernel at 6-8 blocks per SM
+	if (SUM) { // every column is stored as soon as it is known: short live ranges
 		if (q.out[MG_AVG]) mg_st_stream(q.out[MG_AVG] + i, rs.avg);
 		if (q.out[MG_NEAREST]) mg_st_stream(q.out[MG_NEAREST] + i, rs.avg);
 		if (q.out[MG_SUM]) mg_st_stream(q.out[MG_SUM] + i, rs.sum);
@@ -727,30 +653,24 @@ __global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)
 	if (Q) {
 		// every quantile column is stored as soon as it is known (a per-thread array indexed by k would live in local memory)
 		const long long n = wb.n;
-		const bool use_bw = q.use_bw && nb <= MG_BW_S;
-		const uint32_t blk = (uint32_t)w.sbin / MG_BW_STRIDE;
-		const uint32_t l = (uint32_t)w.sbin - blk * MG_BW_STRIDE;
+		const bool use_bw = q.use_bw && nb <= MG_BW_S && nb > 0;
+		const uint32_t blk = nb > 0 ? (uint32_t)w.sbin / MG_BW_STRIDE : 0u;
+		const uint32_t l = nb > 0 ? (uint32_t)w.sbin - blk * MG_BW_STRIDE : 0u;
 		long long before = wb.before;
 		if (!use_bw && n > 0 && before < 0)
 			before = mg_win_before(w.ch, w.sbin);
-		if (staged) // every thread of a staging block waits for the copies (none may be in flight when the block retires)
-			mg_mbar_wait(&s_bar, 0);
 		for (int k = 0; k < q.nq; ++k) {
 			double qv = mg_nan();
 			if (n > 0) {
-				double pct = q.q_pct[k];
-				pct = pct < 0. ? 0. : (pct > 1. ? 1. : pct);
-				const double index = __dmul_rn((double)(n - 1), pct);
+				const double index = __dmul_rn((double)(n - 1), q.q_pct[k]); // q_pct: clamped to [0, 1] by the host
 				const double fl = floor(index);
 				const long long i1 = (long long)fl;
 				const bool want2 = index != fl; // ceil(index) != floor(index)
 				float x1, x2;
-				if (lv_staged)
-					mg_bw_select<false>(lv_staged, w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES, w.ch->vals + (size_t)blk * MG_BW_STRIDE, l, l + (uint32_t)nb,
-										(uint32_t)i1, want2, x1, x2);
-				else if (use_bw) {
+				if (use_bw) {
 					const uint8_t *rec = w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES;
-					mg_bw_select<true>(rec, rec, w.ch->vals + (size_t)blk * MG_BW_STRIDE, l, l + (uint32_t)nb, (uint32_t)i1, want2, x1, x2);
+					mg_bw_select<true>(rec, reinterpret_cast<const uint16_t *>(rec + MG_BW_POS_OFFSET), w.ch->vals + (size_t)blk * MG_BW_STRIDE, l,
+									   l + (uint32_t)nb, (uint32_t)i1, want2, x1, x2);
 				} else
 					mg_wm_select(w.ch, (uint32_t)before, (uint32_t)(before + n), (uint32_t)i1, want2, x1, x2);
 				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
@@ -758,4 +678,15 @@ __global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)
 			mg_st_stream(q.q_out[k] + i, qv);
 		}
 	}
+}
+
+template <bool SUM, bool MM, bool Q, bool SD>
+__global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	const bool ok = mg_dense_win(q, q.first + i, w);
+	mg_rq_row<SUM, MM, Q, SD>(q, i, w, ok);
 }

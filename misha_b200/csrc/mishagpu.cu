@@ -5,6 +5,7 @@
 #include "rows.cuh"
 #include "dense.cuh"
 #include "dense_index.cuh"
+#include "dense_tile.cuh"
 #include "sparse.cuh"
 #include "stats.cuh"
 #include "pwm.cuh"
@@ -97,10 +98,7 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		return 0;
 	}
 	if (name && !strcmp(name, "stage_slots")) {
-		if (value < 0 || value * MG_BW_STAGE_BYTES > 48 * 1024)
-			return mg_fail(ctx, "mg_set_option: stage_slots must be in [0, %d]", 48 * 1024 / MG_BW_STAGE_BYTES);
-		ctx->stage_slots = (int)value;
-		return 0;
+		return 0; // retired (the per-row kernel no longer stages block records; k_dense_tile stages what its tile needs): accepted, ignored
 	}
 	if (name && !strcmp(name, "merge_rows")) { // 8: the sparse / coverage merge kernels always take 8 rows per thread (ablation)
 		ctx->merge_rows = (int)value;
@@ -112,6 +110,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 	}
 	if (name && !strcmp(name, "cov_raster")) {
 		ctx->cov_raster = value != 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "tile_kernel")) {
+		ctx->tile_kernel = (int)value;
 		return 0;
 	}
 	if (name && !strcmp(name, "block_wm")) {
@@ -675,7 +677,6 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
 	q.use_bw = ctx->block_wm ? 1 : 0;
 	q.prefetch = ctx->prefetch ? 1 : 0;
-	q.stage_slots = ctx->stage_slots;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {
 		const int f = funcs[k];
@@ -684,13 +685,14 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 		if (f == MG_QUANTILE) {
 			MG_REQUIRE(ctx, q.nq < MG_MAX_Q, "at most %d quantile columns per call", MG_MAX_Q);
 			MG_REQUIRE(ctx, params, "quantile needs a percentile parameter");
-			q.q_pct[q.nq] = params[k];
+			q.q_pct[q.nq] = params[k] < 0. ? 0. : (params[k] > 1. ? 1. : params[k]); // src/StreamPercentiler.h:193-194
 			q.q_out[q.nq] = d_out[k];
 			q.nq++;
 			need_sweep = true;
 		} else {
 			MG_REQUIRE(ctx, !q.out[f], "function %d requested twice in one call", f);
 			q.out[f] = d_out[k];
+			q.out_mask |= 1u << f;
 			if (f == MG_MIN || f == MG_MAX || f == MG_STDDEV)
 				need_sweep = true;
 			if (f >= MG_FIRST_POS && f <= MG_MAX_POS && params && params[k] != 0.)
@@ -743,17 +745,39 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		if (!want_sum && !want_mm && !q.out[MG_STDDEV] && q.nq == 0)
 			return 0;
 	}
-	if (!need_sweep) {
+	const bool tile_ok = ctx->tile_kernel && !ctx->force_sweep && !q.out[MG_STDDEV] && (q.nq == 0 || q.use_bw) &&
+						 (need_sweep || ctx->tile_kernel >= 2);
+	if (tile_ok) {
+		// a thread block per tile of rows, everything from shared memory (dense_tile.cuh)
+		const unsigned grid = (unsigned)mg_div_up(q.count, MG_TL_THREADS);
+		const int key = (want_sum ? 1 : 0) | (q.out[MG_MAX] ? 2 : 0) | (q.out[MG_MIN] ? 4 : 0) | (q.nq > 0 ? 8 : 0);
+#define MG_TILE_CASE(K)                                                                                                  \
+	case K: {                                                                                                           \
+		auto kern = k_dense_tile<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0>;                       \
+		constexpr int smem_bytes = mg_tile_layout((((K) & 2) ? 1 : 0) + (((K) & 4) ? 1 : 0), ((K) & 8) != 0).total;                                \
+		if (!(ctx->tile_attr & (1u << (K)))) {                                                                          \
+			MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));            \
+			ctx->tile_attr |= 1u << (K);                                                                                \
+		}                                                                                                               \
+		kern<<<grid, MG_TL_THREADS, smem_bytes, st>>>(q);                                                               \
+		break;                                                                                                          \
+	}
+		switch (key) {
+			MG_TILE_CASE(1) MG_TILE_CASE(2) MG_TILE_CASE(3) MG_TILE_CASE(4) MG_TILE_CASE(5) MG_TILE_CASE(6) MG_TILE_CASE(7) MG_TILE_CASE(8)
+			MG_TILE_CASE(9) MG_TILE_CASE(10) MG_TILE_CASE(11) MG_TILE_CASE(12) MG_TILE_CASE(13) MG_TILE_CASE(14) MG_TILE_CASE(15)
+		default: break;
+		}
+#undef MG_TILE_CASE
+	} else if (!need_sweep) {
 		k_dense_prefix<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
 	} else if (!ctx->force_sweep) {
 		// everything else comes from the index structures, one thread per row
 		const unsigned grid = (unsigned)mg_div_up(q.count, MG_RQ_THREADS);
 		const bool want_sd = q.out[MG_STDDEV] != nullptr;
-		const size_t stage_bytes = q.nq > 0 && q.use_bw ? (size_t)q.stage_slots * MG_BW_STAGE_BYTES : 0;
 		const int key = (want_sum ? 1 : 0) | (want_mm ? 2 : 0) | (q.nq > 0 ? 4 : 0) | (want_sd ? 8 : 0);
 #define MG_RQ_CASE(K)                                                                                                    \
 	case K:                                                                                                             \
-		k_dense_rowquery<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, MG_RQ_THREADS, stage_bytes, st>>>(q); \
+		k_dense_rowquery<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0><<<grid, MG_RQ_THREADS, 0, st>>>(q); \
 		break;
 		switch (key) {
 			MG_RQ_CASE(1) MG_RQ_CASE(2) MG_RQ_CASE(3) MG_RQ_CASE(4) MG_RQ_CASE(5) MG_RQ_CASE(6) MG_RQ_CASE(7) MG_RQ_CASE(8) MG_RQ_CASE(9)
