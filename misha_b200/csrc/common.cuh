@@ -36,10 +36,14 @@ struct mg_ctx {
 	int merge_rows = 0;      // 8: merge kernels at 8 rows per thread whatever the row source (0: chosen per launch)
 	bool hist_red = true;    // gdist over a dense track: 16-bit counters of warp pairs packed in 32-bit words, one red.shared.add per value
 	bool cov_raster = true;  // coverage over a regular grid of rows: records rasterised into the block's rows (off: per-row cursors; ablation)
+	bool stage_records = true; // k_dense_rowquery stages block records in shared memory (option "stage_slots" = 0 turns it off)
 	bool block_wm = true;    // quantiles of windows <= MG_BW_S bins walk the block-local wavelet matrices (off: ablation / tests of the
 	                         // chromosome-wide matrix)
-	int tile_kernel = 1;     // dense window functions by k_dense_tile (thread block per tile of rows, everything from shared memory);
-	                         // 0: the per-row index kernels (k_dense_prefix / k_dense_rowquery), 2: also for avg / sum alone
+	int tile_kernel = 3;     // dense window functions: 0 the per-row index kernels (k_dense_prefix / k_dense_rowquery) only; 1 k_dense_tile
+	                         // (thread block per tile of rows, everything built in shared memory, sums to the reference's bits) for
+	                         // min / max / quantile sets, 2 also for avg / sum alone; 3 (default) k_dense_thin (staged bins and block
+	                         // records, sums / extrema from the chromosome's structures) when two or more function groups share a
+	                         // scan, the per-row kernels for a single group (measured: they win there); 4 k_dense_thin for everything
 	uint32_t tile_attr = 0;  // k_dense_tile instantiations whose dynamic shared-memory limit has been raised on this device
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;
@@ -108,6 +112,7 @@ __device__ __forceinline__ float mg_ldg_f(const float *p) { return __ldg(p); }
 __device__ __forceinline__ void mg_st_stream(double *p, double v) { __stcs(p, v); }
 
 __device__ __forceinline__ void mg_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void mg_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Window transform, src/TrackExpressionVars.h:395-402. Returns false when out of range.
 __device__ __forceinline__ bool mg_window(int64_t start, int64_t end, int64_t sshift, int64_t eshift, int64_t chromsize, int64_t &ws,

@@ -71,6 +71,7 @@ struct DenseQuery {
 	int nq;
 	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
+	int stage;  // k_dense_rowquery stages the block records its rows need in shared memory (0: walk them through L1; ablation)
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
 };
@@ -257,8 +258,9 @@ __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, D
 	w.ws = ws;
 	int64_t eb;
 	if ((uint64_t)we <= 0xffffffffull - q.bin_size && q.bin_magic) { // 0 <= ws < we: both fit the magic-number division
-		w.sbin = (int64_t)__umul64hi((uint64_t)ws, q.bin_magic);             // src/GenomeTrackFixedBin.cpp:675
-		eb = (int64_t)__umul64hi((uint64_t)we + q.bin_size - 1, q.bin_magic); // :676
+		// both operands fit 32 bits here: say so, the product is then two 32 x 32 multiplies instead of four
+		w.sbin = (int64_t)__umul64hi((uint64_t)(uint32_t)ws, q.bin_magic);                    // src/GenomeTrackFixedBin.cpp:675
+		eb = (int64_t)__umul64hi((uint64_t)((uint32_t)we + q.bin_size - 1u), q.bin_magic); // :676
 	} else {
 		w.sbin = mg_floordiv(ws, q.bin_size);
 		eb = mg_ceildiv(we, q.bin_size);
@@ -291,19 +293,36 @@ __device__ __forceinline__ Pref mg_ld_pref(const Pref *p)
 
 // bins [lo, hi) of the aligned group of 8 starting at bin 8 g: one 32-byte sector. Sum in bin order (exact for the few
 // floats involved), non-NaN count, extrema.
+// x when it is a number and bit J of sel is set, else 0; counts it in n. Inline PTX: left to the compiler, the select moves behind
+// the conversion to double and becomes two selects on the halves.
+template <uint32_t J>
+__device__ __forceinline__ float mg_take(float x, uint32_t sel, int &n)
+{
+	float c;
+	uint32_t b;
+	asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\tsetp.num.and.f32 p, %2, %2, p;\n\tselp.f32 %0, %2, 0f00000000, p;\n\t"
+		"selp.u32 %1, 1, 0, p;\n\t}"
+		: "=f"(c), "=r"(b)
+		: "f"(x), "r"(sel), "n"(1u << J));
+	n += (int)b;
+	return c;
+}
+
 template <bool SUM, bool MM>
 __device__ __forceinline__ void mg_part8(const float *__restrict__ vals, int64_t g, int lo, int hi, double &S, int &n, float &mx, float &mn)
 {
 	const float4 a = __ldg(reinterpret_cast<const float4 *>(vals + 8 * g));
 	const float4 b = __ldg(reinterpret_cast<const float4 *>(vals + 8 * g + 4));
-	const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+	const uint32_t sel = ((1u << hi) - 1u) & ~((1u << lo) - 1u); // bins lo .. hi - 1
+	const float c0 = mg_take<0>(a.x, sel, n), c1 = mg_take<1>(a.y, sel, n), c2 = mg_take<2>(a.z, sel, n), c3 = mg_take<3>(a.w, sel, n);
+	const float c4 = mg_take<4>(b.x, sel, n), c5 = mg_take<5>(b.y, sel, n), c6 = mg_take<6>(b.z, sel, n), c7 = mg_take<7>(b.w, sel, n);
+	if (SUM) // bin order
+		S = (((((((S + (double)c0) + (double)c1) + (double)c2) + (double)c3) + (double)c4) + (double)c5) + (double)c6) + (double)c7;
+	if (MM) {
+		const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-	for (int j = 0; j < 8; ++j) {
-		const bool in = j >= lo && j < hi && v[j] == v[j];
-		if (SUM)
-			S += in ? (double)v[j] : 0.;
-		n += in ? 1 : 0;
-		if (MM) {
+		for (int j = 0; j < 8; ++j) {
+			const bool in = (sel >> j) & 1u; // NaN operands are skipped by fmaxf / fminf
 			mx = fmaxf(mx, in ? v[j] : __int_as_float(0xff800000));
 			mn = fminf(mn, in ? v[j] : __int_as_float(0x7f800000));
 		}

@@ -207,7 +207,8 @@ __device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ rec,
 // k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l <= S; with want2 (k + 1 < n) also the
 // (k+1)-th. lv = the record's walked levels (global or staged), pos = the record's pos_of_rank in global memory, vals_block =
 // the track (or its staged copy) at the block's first bin.
-template <bool G>
+// G: where the levels live (true: global memory), GV: where the bins live
+template <bool G, bool GV = G>
 __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint16_t *__restrict__ pos, const float *__restrict__ vals_block, uint32_t l,
 											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
 {
@@ -247,7 +248,7 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, con
 	for (uint32_t j = 0; j < k; ++j) // drop the k members below
 		m &= m - 1u;
 	const uint32_t j1 = __ffs(m) - 1;
-	x1 = mg_bw_ld<G>(vals_block + __ldg(pos + mg_bw_pos_slot(rank0 + j1)));
+	x1 = mg_bw_ld<GV>(vals_block + __ldg(pos + mg_bw_pos_slot(rank0 + j1)));
 	x2 = x1;
 	if (want2) {
 		m &= m - 1u;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, con
 			while (rk < MG_BW_B - 1 && (uint32_t)__ldg(pos + mg_bw_pos_slot(rk)) - l0 >= len)
 				++rk;
 		}
-		x2 = mg_bw_ld<G>(vals_block + __ldg(pos + mg_bw_pos_slot(rk)));
+		x2 = mg_bw_ld<GV>(vals_block + __ldg(pos + mg_bw_pos_slot(rk)));
 	}
 }
 

@@ -576,10 +576,17 @@ __global__ void __launch_bounds__(256) k_dense_argext(const DenseQuery q)
 #endif
 // Resident blocks per SM, measured on B200 at the C3 shape: the kernel is bound by memory latency, so more warps win even at the
 // price of a few spills -- 8 blocks (32 registers) for one function group, 6 for several.
+#ifdef MG_RQ_MB // build-time override (tuning)
+#define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) MG_RQ_MB
+#else
 #define MG_RQ_MINBLOCKS(SUM, MM, Q, SD) (((SD) ? 1024 : ((int)(SUM) + (int)(MM) + (int)(Q) <= 1 ? 2048 : 1536)) / MG_RQ_THREADS)
+#endif
 
+// lv_staged: this row's walked levels in shared memory (null: read them through L1); bar: the mbarrier the staging copies complete
+// on (null: nothing to wait for) -- waited for as late as possible, the sums and extrema are computed while the copies fly
 template <bool SUM, bool MM, bool Q, bool SD>
-__device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const DenseWin &w, bool ok)
+__device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const DenseWin &w, bool ok, const uint8_t *lv_staged = nullptr,
+										  uint64_t *bar = nullptr)
 {
 	RowSum rs;
 	rs.avg = rs.sum = rs.size = rs.exists = mg_nan();
@@ -659,6 +666,8 @@ __device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const 
 		long long before = wb.before;
 		if (!use_bw && n > 0 && before < 0)
 			before = mg_win_before(w.ch, w.sbin);
+		if (bar) // every thread of a staging block waits for the copies (none may be in flight when the block retires)
+			mg_mbar_wait(bar, 0);
 		for (int k = 0; k < q.nq; ++k) {
 			double qv = mg_nan();
 			if (n > 0) {
@@ -669,8 +678,12 @@ __device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const 
 				float x1, x2;
 				if (use_bw) {
 					const uint8_t *rec = w.ch->bw + (size_t)blk * MG_BW_RECORD_BYTES;
-					mg_bw_select<true>(rec, reinterpret_cast<const uint16_t *>(rec + MG_BW_POS_OFFSET), w.ch->vals + (size_t)blk * MG_BW_STRIDE, l,
-									   l + (uint32_t)nb, (uint32_t)i1, want2, x1, x2);
+					const uint16_t *pos = reinterpret_cast<const uint16_t *>(rec + MG_BW_POS_OFFSET);
+					const float *vb = w.ch->vals + (size_t)blk * MG_BW_STRIDE;
+					if (lv_staged)
+						mg_bw_select<false, true>(lv_staged, pos, vb, l, l + (uint32_t)nb, (uint32_t)i1, want2, x1, x2);
+					else
+						mg_bw_select<true, true>(rec, pos, vb, l, l + (uint32_t)nb, (uint32_t)i1, want2, x1, x2);
 				} else
 					mg_wm_select(w.ch, (uint32_t)before, (uint32_t)(before + n), (uint32_t)i1, want2, x1, x2);
 				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
@@ -680,13 +693,67 @@ __device__ __forceinline__ void mg_rq_row(const DenseQuery &q, int64_t i, const 
 	}
 }
 
+// Staged block records (Q): the 256 rows of a thread block are neighbours in position when the rows are sorted (what the scanner
+// produces), so between them they need the records of a handful of consecutive blocks. The thread block finds the range of
+// block ids its rows need (a min / max reduction, no assumption about the row order), thread 0 issues one bulk copy per
+// record -- at most MG_RQ_SLOTS, the walked levels only -- into shared memory, the rows compute their avg / min / max from
+// global memory while the copies fly, and the walks then run on shared memory. A row whose record is not among the staged ones
+// (another chromosome, rows far apart, unsorted rows) walks the record through L1: correctness never depends on the order.
+#define MG_RQ_SLOTS 5
+#define MG_STAGE_BLK_BITS 21
 template <bool SUM, bool MM, bool Q, bool SD>
-__global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const DenseQuery q)
+__global__ void __launch_bounds__(MG_RQ_THREADS, MG_RQ_MINBLOCKS(SUM, MM, Q, SD)) k_dense_rowquery(const __grid_constant__ DenseQuery q)
 {
+	__shared__ __align__(128) uint8_t s_stage[Q ? MG_RQ_SLOTS * MG_BW_STAGE_BYTES : 16];
+	__shared__ uint64_t s_bar;
+	__shared__ uint32_t s_kmin, s_kmax;
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= q.count)
+	const bool live = i < q.count;
+	const bool staging = Q && q.use_bw && q.stage;
+	if (!staging && !live)
 		return;
+	if (staging && threadIdx.x == 0) {
+		s_kmin = 0xffffffffu;
+		s_kmax = 0;
+		mg_mbar_init(&s_bar, 1);
+	}
 	DenseWin w;
-	const bool ok = mg_dense_win(q, q.first + i, w);
-	mg_rq_row<SUM, MM, Q, SD>(q, i, w, ok);
+	const bool ok = live && mg_dense_win(q, q.first + i, w);
+	const uint8_t *lv_staged = nullptr;
+	bool staged = false;
+	if (staging) {
+		const int64_t nb = ok ? w.ebin - w.sbin : 0;
+		// one key per row: chromosome in the high bits, block id in the low MG_STAGE_BLK_BITS (rows beyond either range walk through L1)
+		const uint32_t blk = nb > 0 ? (uint32_t)w.sbin / MG_BW_STRIDE : 0;
+		const uint32_t chrom = nb > 0 ? (uint32_t)(w.ch - q.table) : 0;
+		const bool mine = nb > 0 && nb <= MG_BW_S && blk < (1u << MG_STAGE_BLK_BITS) && chrom < (1u << (32 - MG_STAGE_BLK_BITS)) - 1u;
+		const uint32_t key = (chrom << MG_STAGE_BLK_BITS) | blk;
+		__syncthreads(); // the seeds and the barrier are initialised
+		const uint32_t wmin = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu), wmax = __reduce_max_sync(0xffffffffu, mine ? key : 0u);
+		if ((threadIdx.x & 31) == 0 && wmin != 0xffffffffu) {
+			atomicMin(&s_kmin, wmin);
+			atomicMax(&s_kmax, wmax);
+		}
+		__syncthreads();
+		const uint32_t kmin = s_kmin, kmax = s_kmax;
+		// one chromosome, and dense enough that the staged records serve most of the rows
+		staged = kmin <= kmax && (kmin >> MG_STAGE_BLK_BITS) == (kmax >> MG_STAGE_BLK_BITS) && kmax - kmin < 2u * MG_RQ_SLOTS;
+		if (staged) {
+			const uint32_t nslots = min(kmax - kmin + 1u, (uint32_t)MG_RQ_SLOTS);
+			if (threadIdx.x == 0) {
+				const uint8_t *src = q.table[kmin >> MG_STAGE_BLK_BITS].bw + (size_t)(kmin & ((1u << MG_STAGE_BLK_BITS) - 1u)) * MG_BW_RECORD_BYTES;
+				mg_mbar_expect_tx(&s_bar, nslots * MG_BW_STAGE_BYTES);
+				for (uint32_t sl = 0; sl < nslots; ++sl)
+					mg_bulk_g2s(s_stage + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar);
+			}
+			if (mine && key - kmin < nslots)
+				lv_staged = s_stage + (key - kmin) * MG_BW_STAGE_BYTES;
+		}
+		if (!live) { // a partial last block: the copies must have landed before the block retires
+			if (staged)
+				mg_mbar_wait(&s_bar, 0);
+			return;
+		}
+	}
+	mg_rq_row<SUM, MM, Q, SD>(q, i, w, ok, lv_staged, staged ? &s_bar : nullptr);
 }

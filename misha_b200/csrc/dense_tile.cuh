@@ -530,3 +530,206 @@ __global__ void __launch_bounds__(MG_TL_THREADS, (Q && WMAX && WMIN) ? 2 : 3) k_
 		}
 	}
 }
+
+// ---- k_dense_thin: the staging of k_dense_tile without its cooperative passes ---------------------------------------------------
+// The thread block stages its rows' bins and block records exactly as k_dense_tile does, but builds nothing: a row sums its two
+// partial groups of 8 bins out of shared memory and takes the whole groups in between from the chromosome's p8 prefix and sparse
+// tables (dense.cuh / dense_index.cuh) -- four independent global loads issued BEFORE the wait for the bulk copies, so they fly with
+// them. After the wait a row touches global memory once more (the 64 bytes of pos_of_rank behind its quantile); the bins under the
+// quantile come from the staged copy. Against k_dense_rowquery: three dependent global round trips per row instead of six, no
+// sector over-fetch on the track; against k_dense_tile: ~350 fewer instructions per row and half the shared memory (5-6 resident
+// thread blocks per SM), at the price of the p8 / sparse-table traffic (2.5 B/bin) and of sums that are not re-summed to the
+// reference's bits (they are within 1e-6, like k_dense_rowquery's).
+// Measured and dropped: an L2 prefetch hint (one warp pulling the rows, bins, records and prefix entries of the tile one or two
+// waves of resident thread blocks ahead into L2): 0.402 -> 0.485 / 0.551 ms for the C3 step -- the kernel is short of DRAM bandwidth,
+// not of latency tolerance, and the hint's own traffic and issue slots cost more than the shorter round trips return.
+#ifndef MG_TH_MB
+#define MG_TH_MB 6 // measured on B200 at the C3 shape: 4 / 5 / 6 resident thread blocks per SM -> 0.456 / 0.412 / 0.398 ms
+#endif
+#define MG_TH_SZ_VALS ((MG_TL_CAP + 8) * 4)
+
+template <bool SUM, bool MM>
+__device__ __forceinline__ void mg_part8_smem(const float *__restrict__ svals /* staged bins at the group's first bin */, int lo, int hi, double &S, int &n,
+											  float &mx, float &mn)
+{
+	const float4 a = reinterpret_cast<const float4 *>(svals)[0], b = reinterpret_cast<const float4 *>(svals)[1];
+	const uint32_t sel = ((1u << hi) - 1u) & ~((1u << lo) - 1u); // bins lo .. hi - 1
+	const float c0 = mg_take<0>(a.x, sel, n), c1 = mg_take<1>(a.y, sel, n), c2 = mg_take<2>(a.z, sel, n), c3 = mg_take<3>(a.w, sel, n);
+	const float c4 = mg_take<4>(b.x, sel, n), c5 = mg_take<5>(b.y, sel, n), c6 = mg_take<6>(b.z, sel, n), c7 = mg_take<7>(b.w, sel, n);
+	if (SUM) // bin order
+		S = (((((((S + (double)c0) + (double)c1) + (double)c2) + (double)c3) + (double)c4) + (double)c5) + (double)c6) + (double)c7;
+	if (MM) {
+		const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const bool in = (sel >> j) & 1u; // NaN operands are skipped by fmaxf / fminf
+			mx = fmaxf(mx, in ? v[j] : __int_as_float(0xff800000));
+			mn = fminf(mn, in ? v[j] : __int_as_float(0x7f800000));
+		}
+	}
+}
+
+template <bool SUM, bool WMAX, bool WMIN, bool Q>
+__global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __grid_constant__ DenseQuery q)
+{
+	constexpr bool MM = WMAX || WMIN;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint64_t s_bar;
+	__shared__ __align__(16) uint32_t s_acc[8]; // chrom min, chrom max, min sbin, max ebin, -, -, any bad row, -
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const int64_t i = (int64_t)blockIdx.x * MG_TL_THREADS + t;
+	const bool live = i < q.count;
+	if (t == 0)
+		mg_mbar_init(&s_bar, 1);
+	if (t < 8)
+		s_acc[t] = (t == 0 || t == 2) ? 0xffffffffu : 0u;
+
+	// ---- 1. the rows' windows; the tile's bin range, chromosome and record range ----
+	TileRow r;
+	mg_tile_row(q, q.first + i, live, r);
+	const uint32_t sb = r.sb, eb = r.eb, nb = eb - sb;
+	const bool ok = r.ok, reg = r.reg;
+	__syncthreads(); // the accumulators are initialised
+	{
+		const uint32_t r_cmin = __reduce_min_sync(0xffffffffu, reg ? r.chrom : 0xffffffffu), r_cmax = __reduce_max_sync(0xffffffffu, r.chrom);
+		const uint32_t r_bmin = __reduce_min_sync(0xffffffffu, reg ? sb : 0xffffffffu), r_bmax = __reduce_max_sync(0xffffffffu, eb);
+		const bool r_bad = __any_sync(0xffffffffu, r.bad || (Q && nb > MG_BW_S));
+		if (lane == 0) {
+			atomicMin(&s_acc[0], r_cmin);
+			atomicMax(&s_acc[1], r_cmax);
+			atomicMin(&s_acc[2], r_bmin);
+			atomicMax(&s_acc[3], r_bmax);
+			if (r_bad)
+				s_acc[6] = 1u;
+		}
+	}
+	__syncthreads();
+	const uint4 acc0 = *reinterpret_cast<const uint4 *>(s_acc);
+	const uint32_t cmin = acc0.x, cmax = acc0.y, bmin = acc0.z, bmax = acc0.w, anybad = s_acc[6];
+	const bool anyreg = cmin != 0xffffffffu;
+	const uint32_t b0 = bmin & ~7u;                                // group-aligned start of the staged bins
+	const uint32_t span8 = anyreg ? ((bmax - b0 + 7u) & ~7u) : 0u; // staged bins: whole groups of 8 (the track is padded with NaN)
+	const uint32_t blk0 = bmin / MG_BW_STRIDE, nrec = anyreg ? (bmax - 1u) / MG_BW_STRIDE - blk0 + 1u : 0u;
+	const DenseChrom *ch = q.table + cmin;
+	bool fast = anyreg && !anybad && cmin == cmax && span8 <= MG_TL_CAP;
+	if (Q)
+		fast = fast && q.use_bw && nrec <= MG_TL_SLOTS;
+	if (!fast) {
+		if (live)
+			mg_tile_slow_row<SUM, MM, Q>(q, i);
+		return;
+	}
+
+	// ---- 2. bulk copies: the bins, the walked levels of the block records ----
+	float *s_vals = reinterpret_cast<float *>(smem);
+	uint8_t *s_lv = smem + MG_TH_SZ_VALS;
+	if (t == 0) {
+		const float *vsrc = ch->vals;
+		const uint32_t vbytes = span8 * 4u;
+		mg_mbar_expect_tx(&s_bar, vbytes + (Q ? nrec * MG_BW_STAGE_BYTES : 0u));
+		mg_bulk_g2s(s_vals, vsrc + b0, vbytes, &s_bar);
+		if (Q) {
+			const uint8_t *src = ch->bw + (size_t)blk0 * MG_BW_RECORD_BYTES;
+			for (uint32_t sl = 0; sl < nrec; ++sl)
+				mg_bulk_g2s(s_lv + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar);
+		}
+	}
+	// ---- 3. what the whole groups of the window contribute, from the chromosome's structures: loads that fly with the copies ----
+	const uint32_t g0 = sb >> 3, g1 = reg ? (eb - 1u) >> 3 : 0u;
+	const bool multi = reg && g0 != g1;
+	Pref pa, pb;
+	pa.sum = pb.sum = 0;
+	pa.cnt = pb.cnt = 0;
+	float tmx = __int_as_float(0xff800000), tmn = __int_as_float(0x7f800000);
+	if (multi) {
+		pa = mg_ld_pref(ch->p8 + g0 + 1);
+		pb = mg_ld_pref(ch->p8 + g1);
+		const uint32_t gs = g0 + 1, len = g1 - gs;
+		if (MM && len > 0) { // len < 2^MG_ST_LEVELS: the tile holds MG_TL_CAP bins
+			const int j = 31 - __clz((int)len);
+			if (WMAX)
+				tmx = fmaxf(__ldg(ch->smax[j] + gs), __ldg(ch->smax[j] + g1 - (1u << j)));
+			if (WMIN)
+				tmn = fminf(__ldg(ch->smin[j] + gs), __ldg(ch->smin[j] + g1 - (1u << j)));
+		}
+	}
+	// one warp watches the barrier, the others park at the thread-block barrier (no issue slots spent on polling)
+	if (warp == 0)
+		mg_mbar_wait(&s_bar, 0);
+	__syncthreads();
+	if (!live)
+		return;
+
+	// ---- 4. the row ----
+	const uint32_t om = q.out_mask; // bit f: column f is requested
+	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan();
+	uint32_t n = 0;
+	if (ok) {
+		size = 0;
+		exists = 0;
+	}
+	if (reg) {
+		double S = 0;
+		int nh = 0, nt = 0;
+		float pmx = tmx, pmn = tmn;
+		const float *gh = s_vals + (8u * g0 - b0);
+		if (!multi) {
+			mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), (int)(eb - 8u * g0), S, nh, pmx, pmn);
+			n = (uint32_t)nh;
+		} else {
+			double St = 0;
+			mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), 8, S, nh, pmx, pmn);
+			mg_part8_smem<SUM, MM>(s_vals + (8u * g1 - b0), 0, (int)(eb - 8u * g1), St, nt, pmx, pmn);
+			S = (S + (pb.sum - pa.sum)) + St;
+			n = (uint32_t)nh + (uint32_t)(pb.cnt - pa.cnt) + (uint32_t)nt;
+			// the prefix difference has lost too many digits against the chromosome's running sum: the bins in order, from the staged copy
+			if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
+				S = 0;
+				for (uint32_t b = sb - b0; b < eb - b0; ++b) {
+					const float v = s_vals[b];
+					if (v == v)
+						S += (double)v;
+				}
+			}
+		}
+		if (SUM) {
+			size = (double)n;
+			exists = n > 0 ? 1. : 0.;
+			if (n > 0) {
+				avg = mg_f2d(S / (double)n);
+				sum = mg_f2d(S);
+			}
+		}
+		if (MM && n > 0) {
+			mx = (double)pmx;
+			mn = (double)pmn;
+		}
+	}
+	if (SUM) {
+		if (om & (1u << MG_AVG)) mg_st_stream(q.out[MG_AVG] + i, avg);
+		if (om & (1u << MG_NEAREST)) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+		if (om & (1u << MG_SUM)) mg_st_stream(q.out[MG_SUM] + i, sum);
+		if (om & (1u << MG_SIZE)) mg_st_stream(q.out[MG_SIZE] + i, size);
+		if (om & (1u << MG_EXISTS)) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+	}
+	if (WMIN) mg_st_stream(q.out[MG_MIN] + i, mn);
+	if (WMAX) mg_st_stream(q.out[MG_MAX] + i, mx);
+	if (Q) {
+		const uint32_t blk = sb / MG_BW_STRIDE, l = sb - blk * MG_BW_STRIDE;
+		const uint8_t *lv = s_lv + (size_t)(blk - blk0) * MG_BW_STAGE_BYTES;
+		const uint16_t *pos = reinterpret_cast<const uint16_t *>(ch->bw + (size_t)blk * MG_BW_RECORD_BYTES + MG_BW_POS_OFFSET);
+		const float *vblk = s_vals + ((int)(blk * MG_BW_STRIDE) - (int)b0); // block-local position -> staged bin
+		for (int k = 0; k < q.nq; ++k) {
+			double qv = mg_nan();
+			if (n > 0) {
+				const double index = __dmul_rn((double)(n - 1), q.q_pct[k]); // q_pct is clamped to [0, 1] by the host
+				const double fl = floor(index);
+				const bool want2 = index != fl;
+				float x1, x2;
+				mg_bw_select<false>(lv, pos, vblk, l, l + nb, (uint32_t)fl, want2, x1, x2);
+				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
+			}
+			mg_st_stream(q.q_out[k] + i, qv);
+		}
+	}
+}

@@ -98,7 +98,8 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 		return 0;
 	}
 	if (name && !strcmp(name, "stage_slots")) {
-		return 0; // retired (the per-row kernel no longer stages block records; k_dense_tile stages what its tile needs): accepted, ignored
+		ctx->stage_records = value != 0; // 0: the per-row kernel walks the block records through L1 (ablation); the slot count is fixed
+		return 0;
 	}
 	if (name && !strcmp(name, "merge_rows")) { // 8: the sparse / coverage merge kernels always take 8 rows per thread (ablation)
 		ctx->merge_rows = (int)value;
@@ -676,6 +677,7 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.bin_size = t->bin_size;
 	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
 	q.use_bw = ctx->block_wm ? 1 : 0;
+	q.stage = ctx->stage_records ? 1 : 0;
 	q.prefetch = ctx->prefetch ? 1 : 0;
 	need_sweep = false;
 	for (int k = 0; k < nfuncs; ++k) {
@@ -745,8 +747,9 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		if (!want_sum && !want_mm && !q.out[MG_STDDEV] && q.nq == 0)
 			return 0;
 	}
+	const int ngroups = (want_sum ? 1 : 0) + (want_mm ? 1 : 0) + (q.nq > 0 ? 1 : 0);
 	const bool tile_ok = ctx->tile_kernel && !ctx->force_sweep && !q.out[MG_STDDEV] && (q.nq == 0 || q.use_bw) &&
-						 (need_sweep || ctx->tile_kernel >= 2);
+						 (ctx->tile_kernel == 3 ? ngroups >= 2 : (need_sweep || ctx->tile_kernel == 2 || ctx->tile_kernel == 4));
 	if (tile_ok) {
 		// a thread block per tile of rows, everything from shared memory (dense_tile.cuh)
 		const unsigned grid = (unsigned)mg_div_up(q.count, MG_TL_THREADS);
@@ -762,6 +765,25 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		kern<<<grid, MG_TL_THREADS, smem_bytes, st>>>(q);                                                               \
 		break;                                                                                                          \
 	}
+		if (ctx->tile_kernel >= 3) { // staging only (k_dense_thin): sums / extrema from the chromosome's structures
+#define MG_THIN_CASE(K)                                                                                                  \
+	case K: {                                                                                                           \
+		auto kern = k_dense_thin<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0>;                       \
+		constexpr int smem_bytes = MG_TH_SZ_VALS + (((K) & 8) ? MG_TL_SLOTS * MG_BW_STAGE_BYTES : 0);                    \
+		if (!(ctx->tile_attr & (1u << (16 + (K))))) {                                                                   \
+			MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));            \
+			ctx->tile_attr |= 1u << (16 + (K));                                                                         \
+		}                                                                                                               \
+		kern<<<grid, MG_TL_THREADS, smem_bytes, st>>>(q);                                                               \
+		break;                                                                                                          \
+	}
+			switch (key) {
+				MG_THIN_CASE(1) MG_THIN_CASE(2) MG_THIN_CASE(3) MG_THIN_CASE(4) MG_THIN_CASE(5) MG_THIN_CASE(6) MG_THIN_CASE(7) MG_THIN_CASE(8)
+				MG_THIN_CASE(9) MG_THIN_CASE(10) MG_THIN_CASE(11) MG_THIN_CASE(12) MG_THIN_CASE(13) MG_THIN_CASE(14) MG_THIN_CASE(15)
+			default: break;
+			}
+#undef MG_THIN_CASE
+		} else
 		switch (key) {
 			MG_TILE_CASE(1) MG_TILE_CASE(2) MG_TILE_CASE(3) MG_TILE_CASE(4) MG_TILE_CASE(5) MG_TILE_CASE(6) MG_TILE_CASE(7) MG_TILE_CASE(8)
 			MG_TILE_CASE(9) MG_TILE_CASE(10) MG_TILE_CASE(11) MG_TILE_CASE(12) MG_TILE_CASE(13) MG_TILE_CASE(14) MG_TILE_CASE(15)

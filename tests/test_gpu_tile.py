@@ -71,6 +71,7 @@ def oracle_cols(bins, chrom, start, end, ss, es):
 def check(track, chrom, start, end, ss, es, what):
     ctx, t = track["ctx"], track["t"]
     rows = ctx.rows_upload(chrom, start, end)
+    ctx.set_option("tile_kernel", 1)  # k_dense_tile: the path with sums to the reference's bits
     got = t.window(rows, FUNCS, ss, es)
     exp = oracle_cols(track["bins"], chrom, start, end, ss, es)
     names = ["avg", "sum", "min", "max", "q0.9", "size", "avg", None, "q0.5", "q0.0", "q1.0"]
@@ -92,6 +93,22 @@ def check(track, chrom, start, end, ss, es, what):
             assert_close(got[k], old[k], 1e-6, "%s old kernel %s" % (what, FUNCS[k]))
         else:
             assert_same(got[k], old[k], "%s old kernel %s" % (what, FUNCS[k]))
+    # k_dense_thin (staging only; sums from the chromosome's prefix entries: within 1e-6)
+    ctx.set_option("tile_kernel", 4)
+    try:
+        thin = t.window(rows, FUNCS, ss, es)
+        thin_q = t.window(rows, [("quantile", 0.9)], ss, es)[0]
+        thin_m = t.window(rows, ["min", "max"], ss, es)
+    finally:
+        ctx.set_option("tile_kernel", 1)
+    for k in range(len(FUNCS)):
+        if FUNCS[k] in ("avg", "sum", "nearest"):
+            assert_close(thin[k], got[k], 1e-6, "%s thin kernel %s" % (what, FUNCS[k]))
+        else:
+            assert_same(thin[k], got[k], "%s thin kernel %s" % (what, FUNCS[k]))
+    assert_same(thin_q, got[4], "%s thin kernel, quantile alone" % what)
+    assert_same(thin_m[0], got[2], "%s thin kernel, min alone" % what)
+    assert_same(thin_m[1], got[3], "%s thin kernel, max alone" % what)
     # each function group alone runs another instantiation of the kernel
     for sub in (["avg"], ["max"], ["min", "max"], [("quantile", 0.9)], ["sum", ("quantile", 0.5)], ["avg", "min"]):
         ctx.set_option("tile_kernel", 2)
@@ -101,6 +118,13 @@ def check(track, chrom, start, end, ss, es, what):
             ctx.set_option("tile_kernel", 1)
         for f, col in zip(sub, one):
             assert_same(col, got[FUNCS.index(f)], "%s alone %s" % (what, f))
+    ctx.set_option("tile_kernel", 3)  # the default dispatch
+    dflt = t.window(rows, FUNCS, ss, es)
+    for k in range(len(FUNCS)):
+        if FUNCS[k] in ("avg", "sum", "nearest"):
+            assert_close(dflt[k], got[k], 1e-6, "%s default dispatch %s" % (what, FUNCS[k]))
+        else:
+            assert_same(dflt[k], got[k], "%s default dispatch %s" % (what, FUNCS[k]))
 
 
 def dense_rows(rng, cid, n, lo=100, hi=300):
@@ -160,7 +184,14 @@ def test_fixed_bin_rows(track):
     """The fixed-bin iterator's implicit rows (no row arrays in HBM) under a window."""
     ctx, t = track["ctx"], track["t"]
     rows = ctx.rows_fixedbin(BIN, [0, 1], [1000, 0], [900_000, 500_000])
+    ctx.set_option("tile_kernel", 4)
+    thin = t.window(rows, ["avg", "max", ("quantile", 0.9), "size"], -2000, 2000)
+    ctx.set_option("tile_kernel", 1)
     got = t.window(rows, ["avg", "max", ("quantile", 0.9), "size"], -2000, 2000)
+    ctx.set_option("tile_kernel", 3)
+    assert_close(thin[0], got[0], 1e-6, "fixed-bin rows, thin kernel avg")
+    for k in (1, 2, 3):
+        assert_same(thin[k], got[k], "fixed-bin rows, thin kernel column %d" % k)
     ch, st, en = [], [], []
     for cid, a, b in ((0, 1000, 900_000), (1, 0, 500_000)):
         s = np.arange(a // BIN * BIN, b, BIN, dtype=np.int64)
