@@ -30,9 +30,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO):
+    if "MISHAGPU_LIB" not in os.environ:
         from . import build
-        build.build()
+        build.build()  # no-op when the library is newer than every source (or when there is no nvcc: the prebuilt one is used)
     lib = ctypes.CDLL(SO)
     lib.mg_last_error.restype = ctypes.c_char_p
     lib.mg_last_error.argtypes = [c_vp]

@@ -185,6 +185,31 @@ extern "C" int mg_dev_memset(mg_ctx *ctx, void *d_ptr, int value, int64_t bytes,
 	return 0;
 }
 
+// Stream-ordered scratch of one entry point: whatever exit path the function takes (every MG_CUDA / MG_REQUIRE is a return), what
+// was allocated is handed back to the pool in stream order.
+struct MgScratch {
+	cudaStream_t st;
+	std::vector<void *> ptrs;
+	explicit MgScratch(cudaStream_t s) : st(s) {}
+	MgScratch(const MgScratch &) = delete;
+	MgScratch &operator=(const MgScratch &) = delete;
+	~MgScratch()
+	{
+		for (void *p : ptrs)
+			cudaFreeAsync(p, st);
+	}
+	template <typename T>
+	cudaError_t alloc(T **out, size_t bytes)
+	{
+		void *p = nullptr;
+		const cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, st);
+		if (e == cudaSuccess)
+			ptrs.push_back(p);
+		*out = (T *)p;
+		return e;
+	}
+};
+
 // Bump allocation out of large chunks: a staged dense chromosome is ~40 arrays, and cudaMalloc of hundreds of megabytes is
 // slow enough (it maps physical memory) that one chunk per chromosome instead of one call per array takes seconds off staging.
 struct MgArena {
@@ -515,10 +540,14 @@ extern "C" void mg_dense_free(mg_ctx *ctx, mg_dense *t)
 extern "C" int64_t mg_dense_bytes(const mg_dense *t) { return t->bytes; }
 
 // ---- rows ------------------------------------------------------------------------------------------------
+static int mg_check_rows(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, const char *who);
 extern "C" int mg_rows_upload(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, void *stream,
 							  mg_rows **out)
 {
 	MG_REQUIRE(ctx, n >= 0, "mg_rows_upload: negative row count");
+	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end), "mg_rows_upload: NULL row arrays");
+	if (mg_check_rows(ctx, n, h_chrom, h_start, h_end, "mg_rows_upload"))
+		return 1;
 	mg_rows *r = new (std::nothrow) mg_rows();
 	MG_REQUIRE(ctx, r, "out of memory");
 	const size_t n8 = (size_t)(n > 0 ? n : 1);
@@ -860,16 +889,23 @@ static int mg_pipe_prepare(mg_ctx *ctx, int64_t bytes_per_slot)
 // Rows in host memory -> result columns in host memory: chunks of pipe_chunk_rows rows travel through three device slots, each
 // on its own stream (upload, the launch the caller supplies, download), so the copies of one chunk overlap the kernel of
 // another in both directions. launch(rows, m, d_cols, stream) enqueues the computation of one chunk of m rows.
+// chrom ids index the per-chromosome tables on the device: an id out of range there is an out-of-bounds read and a sticky error for
+// the whole context, so explicit rows are checked where they are still host arrays
+static int mg_check_rows(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *, const int64_t *, const char *who)
+{ // coordinates need no check: the window transform clamps them to the chromosome
+	for (int64_t i = 0; i < n; ++i) {
+		const int32_t c = h_chrom[i];
+		if (c < 0 || c >= ctx->nchroms)
+			return mg_fail(ctx, "%s: row %lld names chromosome id %d (the context holds %d)", who, (long long)i, (int)c, ctx->nchroms);
+	}
+	return 0;
+}
+
 template <typename Launch>
-static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
-						 double *const *h_out, Launch launch)
+static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
+							 double *const *h_out, Launch launch)
 {
-	MG_REQUIRE(ctx, n >= 0 && ncols > 0 && ncols <= 32, "host pipeline: bad arguments");
-	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end && h_out), "host pipeline: NULL row or output arrays");
 	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows per pipeline slot
-	const int64_t slot_bytes = CHUNK * (20 + 8 * (int64_t)ncols);
-	if (mg_pipe_prepare(ctx, slot_bytes))
-		return 1;
 	int64_t done = 0;
 	for (int64_t c = 0; done < n; ++c, done += CHUNK) {
 		const int slot = (int)(c % 3);
@@ -895,9 +931,35 @@ static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 		for (int k = 0; k < ncols; ++k)
 			MG_CUDA(ctx, cudaMemcpyAsync(h_out[k] + done, d_cols[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
 	}
-	for (int i = 0; i < 3; ++i)
-		MG_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]));
 	return 0;
+}
+
+// Rows in host memory -> result columns in host memory: chunks of pipe_chunk_rows rows travel through three device slots, each
+// on its own stream (upload, the launch the caller supplies, download), so the copies of one chunk overlap the kernel of
+// another in both directions. launch(rows, m, d_cols, stream) enqueues the computation of one chunk of m rows.
+// Whatever happens on the way, the three streams are drained before the call returns: earlier chunks' copies into h_out and out of
+// the row arrays may still be in flight when a later step fails, and the caller is free to release its buffers on error.
+template <typename Launch>
+static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
+						 double *const *h_out, Launch launch)
+{
+	MG_REQUIRE(ctx, n >= 0 && ncols > 0 && ncols <= 32, "host pipeline: bad arguments");
+	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end && h_out), "host pipeline: NULL row or output arrays");
+	if (mg_check_rows(ctx, n, h_chrom, h_start, h_end, "host pipeline"))
+		return 1;
+	const int64_t slot_bytes = ctx->pipe_chunk_rows * (20 + 8 * (int64_t)ncols);
+	if (mg_pipe_prepare(ctx, slot_bytes))
+		return 1;
+	int rc = mg_h_pipeline_run(ctx, n, h_chrom, h_start, h_end, ncols, h_out, launch);
+	const std::string first_err = rc ? ctx->err : std::string();
+	for (int i = 0; i < 3; ++i) {
+		const cudaError_t e = cudaStreamSynchronize(ctx->pipe_stream[i]);
+		if (e != cudaSuccess && !rc)
+			rc = mg_fail(ctx, "host pipeline: %s", cudaGetErrorString(e));
+	}
+	if (!first_err.empty())
+		ctx->err = first_err; // the failure that started it, not what the drain reported
+	return rc;
 }
 
 extern "C" int mg_h_dense_window(mg_ctx *ctx, const mg_dense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start,
@@ -1595,6 +1657,7 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 	if (!count)
 		return 0;
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	std::vector<float2> tab((size_t)L * 5);
 	for (int j = 0; j < L; ++j) {
 		for (int c = 0; c < 4; ++c)
@@ -1606,7 +1669,7 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 		}
 	}
 	float2 *d_tab = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&d_tab, sizeof(float2) * tab.size(), st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_tab, sizeof(float2) * tab.size()));
 	MG_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st)); // tab is a stack-lifetime host buffer
 	PwmQuery q;
@@ -1651,7 +1714,6 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 	}
 #undef MG_PWM_LAUNCH
 	MG_LAUNCH_CHECK(ctx);
-	MG_CUDA(ctx, cudaFreeAsync(d_tab, st));
 	return 0;
 }
 
@@ -1704,14 +1766,14 @@ extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *
 	if (n <= 0)
 		return 0;
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	const int nb = mg_summary_blocks(ctx, n);
 	Moments *scratch = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * nb, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&scratch, sizeof(Moments) * nb));
 	k_summary_values<<<nb, MG_SUM_THREADS, 0, st>>>(d_vals, n, scratch);
 	MG_LAUNCH_CHECK(ctx);
 	k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, nb, d_partial);
 	MG_LAUNCH_CHECK(ctx);
-	MG_CUDA(ctx, cudaFreeAsync(scratch, st));
 	return 0;
 }
 
@@ -1793,6 +1855,7 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 	if (!count)
 		return 0;
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	std::vector<StreamSeg> segs;
 	if (mg_is_stream_case(t, rows, sshift, eshift, func) && mg_stream_segments(t, rows, first, count, segs)) {
 		// one pure-streaming launch over every contiguous segment, then the fixed-order final reduction
@@ -1809,7 +1872,7 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 	if (mg_is_stream_case(t, rows, sshift, eshift, func) || mg_is_prefix_func(func)) {
 		const int nb = mg_summary_blocks(ctx, count);
 		Moments *scratch = nullptr;
-		MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(Moments) * nb, st));
+		MG_CUDA(ctx, mg_scratch.alloc(&scratch, sizeof(Moments) * nb));
 		if (mg_is_stream_case(t, rows, sshift, eshift, func)) {
 			k_dense_stream_summary<<<nb, MG_SUM_THREADS, 0, st>>>(rows->src, t->d_table, first, count, scratch);
 		} else {
@@ -1823,15 +1886,13 @@ extern "C" int mg_dense_summary(mg_ctx *ctx, const mg_dense *t, const mg_rows *r
 		MG_LAUNCH_CHECK(ctx);
 		k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, nb, d_partial);
 		MG_LAUNCH_CHECK(ctx);
-		MG_CUDA(ctx, cudaFreeAsync(scratch, st));
 		return 0;
 	}
 	// any other function: materialise the column on the device, then reduce it (values never leave HBM)
 	double *col = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&col, sizeof(double) * count, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&col, sizeof(double) * count));
 	if (mg_dense_window(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &col, stream) || mg_summary(ctx, col, count, d_partial, stream))
 		return 1;
-	MG_CUDA(ctx, cudaFreeAsync(col, st));
 	return 0;
 }
 
@@ -1861,7 +1922,7 @@ extern "C" void mg_summary_finalize_rows(const double *partials, int64_t n, doub
 }
 
 // ---- gdist -----------------------------------------------------------------------------------------------------------
-static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, const int *nbreaks, int include_lowest, HistSpec &hs, double **d_breaks,
+static int mg_make_hist_spec(mg_ctx *ctx, MgScratch &mg_scratch, int ndim, const double *h_breaks, const int *nbreaks, int include_lowest, HistSpec &hs, double **d_breaks,
 							 cudaStream_t st)
 {
 	MG_REQUIRE(ctx, ndim >= 1 && ndim <= MG_HIST_MAX_DIMS, "histogram dimension %d not in [1, %d]", ndim, MG_HIST_MAX_DIMS);
@@ -1893,7 +1954,7 @@ static int mg_make_hist_spec(mg_ctx *ctx, int ndim, const double *h_breaks, cons
 	hs.total = total;
 	if (!d_breaks) // the caller only wants the validated description (breaks travel another way)
 		return 0;
-	MG_CUDA(ctx, cudaMallocAsync(d_breaks, sizeof(double) * off, st));
+	MG_CUDA(ctx, mg_scratch.alloc(d_breaks, sizeof(double) * off));
 	MG_CUDA(ctx, cudaMemcpyAsync(*d_breaks, h_breaks, sizeof(double) * off, cudaMemcpyHostToDevice, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
 	hs.breaks = *d_breaks;
@@ -1978,9 +2039,10 @@ extern "C" int mg_hist(mg_ctx *ctx, int ndim, const double *const *d_cols, int64
 					   int include_lowest, uint64_t *d_counts, void *stream)
 {
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, mg_scratch, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
 		return 1;
 	if (n > 0) {
 		if (ndim == 1 && hs.nbreaks[0] - 1 <= MG_HIST_PRIVATE_MAX) {
@@ -1995,7 +2057,6 @@ extern "C" int mg_hist(mg_ctx *ctx, int ndim, const double *const *d_cols, int64
 		}
 		MG_LAUNCH_CHECK(ctx);
 	}
-	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	return 0;
 }
 
@@ -2004,22 +2065,22 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 {
 	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	const bool stream_case = mg_is_stream_case(t, rows, sshift, eshift, func);
 	if (!stream_case && !mg_is_prefix_func(func)) {
 		if (!count)
 			return 0;
 		double *col = nullptr;
-		MG_CUDA(ctx, cudaMallocAsync(&col, sizeof(double) * count, st));
+		MG_CUDA(ctx, mg_scratch.alloc(&col, sizeof(double) * count));
 		const double *cols[1] = {col};
 		if (mg_dense_window(ctx, t, rows, first, count, sshift, eshift, 1, &func, &param, &col, stream) ||
 			mg_hist(ctx, 1, cols, count, h_breaks, &nbreaks, include_lowest, d_counts, stream))
 			return 1;
-		MG_CUDA(ctx, cudaFreeAsync(col, st));
 		return 0;
 	}
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, nullptr, st))
+	if (mg_make_hist_spec(ctx, mg_scratch, 1, h_breaks, &nbreaks, include_lowest, hs, nullptr, st))
 		return 1;
 	std::vector<StreamSeg> segs;
 	if (count > 0 && stream_case && nbreaks - 1 <= MG_HIST_PRIVATE_MAX && mg_stream_segments(t, rows, first, count, segs)) {
@@ -2068,7 +2129,7 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 		MG_LAUNCH_CHECK(ctx);
 		return 0;
 	}
-	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, mg_scratch, 1, h_breaks, &nbreaks, include_lowest, hs, &d_breaks, st))
 		return 1;
 	if (count > 0) {
 		const bool priv = nbreaks - 1 <= MG_HIST_PRIVATE_MAX;
@@ -2091,7 +2152,6 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 			k_dense_hist_global<<<(unsigned)mg_div_up(count, MG_HIST_THREADS * 4), MG_HIST_THREADS, 0, st>>>(q, func, hs, (unsigned long long *)d_counts);
 		MG_LAUNCH_CHECK(ctx);
 	}
-	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	return 0;
 }
 
@@ -2104,10 +2164,11 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 	for (int k = 0; k < nq; ++k) // C_gquantiles rejects these before scanning (src/GenomeTrackQuantiles.cpp:140-143)
 		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	const double nan = std::numeric_limits<double>::quiet_NaN();
 	unsigned long long *d_hist = nullptr;
 	const size_t hist_words = (size_t)MG_QS_MAXSLOTS * 2048 + 1;
-	MG_CUDA(ctx, cudaMallocAsync(&d_hist, hist_words * 8, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_hist, hist_words * 8));
 	std::vector<unsigned long long> h((size_t)MG_QS_MAXSLOTS * 2048 + 1);
 	const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8));
 	// pass 0: top 11 bits of every key + the NaN count
@@ -2126,7 +2187,6 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 	if (N <= 0) {
 		for (int k = 0; k < nq; ++k)
 			h_out[k] = nan;
-		MG_CUDA(ctx, cudaFreeAsync(d_hist, st));
 		return 0;
 	}
 	// target ranks: floor / ceil of (N - 1) q for every quantile, unique, ascending (src/GenomeTrackQuantiles.cpp:183-195)
@@ -2175,7 +2235,6 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 			prefix[t] = (prefix[t] << (pass == 1 ? 11 : 10)) | d;
 		}
 	}
-	MG_CUDA(ctx, cudaFreeAsync(d_hist, st));
 	std::vector<double> value(T);
 	for (size_t t = 0; t < T; ++t)
 		value[t] = (double)mg_host_fkey_inv(prefix[t]);
@@ -2205,6 +2264,7 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 		return 0;
 	MG_REQUIRE(ctx, d_vals || h_seg_first[nseg] == 0, "mg_quantiles_segmented: no value column");
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	// 0: one warp per segment (sort), 1: one thread block per segment (sort), 2: one thread block per segment (radix select in global memory)
 	std::vector<int32_t> list[4]; // 3: radix select with the counting spread over the device (k_qlong_*)
 	std::vector<int64_t> large; // 2^31 rows and more: the whole-device counting passes of mg_quantiles
@@ -2224,7 +2284,7 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 	char *d_buf = nullptr;
 	const size_t off_first = 0, off_pct = off_first + (size_t)(nseg + 1) * 8, off_out = off_pct + (size_t)nq * 8,
 				 off_kept = off_out + (size_t)nq * nseg * 8, off_list = off_kept + (size_t)nseg * 8, total = off_list + (size_t)nseg * 4;
-	MG_CUDA(ctx, cudaMallocAsync(&d_buf, total, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_buf, total));
 	MG_CUDA(ctx, cudaMemcpyAsync(d_buf + off_first, h_seg_first, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
 	MG_CUDA(ctx, cudaMemcpyAsync(d_buf + off_pct, h_percentiles, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
 	QsegArgs a;
@@ -2276,7 +2336,7 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 		const int maxS = std::min(2 * nq, (int)MG_QSEL_MAXT);
 		const size_t o_state = 0, o_hist = o_state + nl * sizeof(QlongState), o_off = (o_hist + nl * (size_t)maxS * 1024 + 7) & ~(size_t)7,
 					 o_cseg = o_off + nch * 8, o_list = o_cseg + nch * 4, tot = o_list + nl * 4;
-		MG_CUDA(ctx, cudaMallocAsync(&d_long, tot, st));
+		MG_CUDA(ctx, mg_scratch.alloc(&d_long, tot));
 		MG_CUDA(ctx, cudaMemsetAsync(d_long, 0, o_off, st)); // states and counters
 		MG_CUDA(ctx, cudaMemcpyAsync(d_long + o_off, chunk_off.data(), nch * 8, cudaMemcpyHostToDevice, st));
 		MG_CUDA(ctx, cudaMemcpyAsync(d_long + o_cseg, chunk_seg.data(), nch * 4, cudaMemcpyHostToDevice, st));
@@ -2303,9 +2363,6 @@ extern "C" int mg_quantiles_segmented(mg_ctx *ctx, const double *d_vals, int64_t
 	MG_CUDA(ctx, cudaMemcpyAsync(h_out, d_buf + off_out, (size_t)nq * nseg * 8, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaMemcpyAsync(kept.data(), d_buf + off_kept, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
-	MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
-	if (d_long)
-		MG_CUDA(ctx, cudaFreeAsync(d_long, st));
 	std::vector<double> q((size_t)nq);
 	for (int64_t s : large) {
 		int64_t nk = 0;
@@ -2333,10 +2390,11 @@ extern "C" int mg_summary_segmented(mg_ctx *ctx, const double *d_vals, int64_t n
 		return 0;
 	MG_REQUIRE(ctx, d_vals || h_seg_first[nseg] == 0, "mg_summary_segmented: no value column");
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	const int64_t big = (int64_t)1 << 18; // rows one warp still sums itself
 	char *d_buf = nullptr;
 	const size_t off_part = (size_t)(nseg + 1) * 8;
-	MG_CUDA(ctx, cudaMallocAsync(&d_buf, off_part + (size_t)nseg * 48, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_buf, off_part + (size_t)nseg * 48));
 	MG_CUDA(ctx, cudaMemcpyAsync(d_buf, h_seg_first, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
 	double *d_part = (double *)(d_buf + off_part);
 	const unsigned grid = (unsigned)std::min<int64_t>(mg_div_up(nseg, 8), (int64_t)ctx->sm_count * 16);
@@ -2349,7 +2407,6 @@ extern "C" int mg_summary_segmented(mg_ctx *ctx, const double *d_vals, int64_t n
 	}
 	MG_CUDA(ctx, cudaMemcpyAsync(h_partials, d_part, (size_t)nseg * 48, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
-	MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
 	return 0;
 }
 
@@ -2360,15 +2417,16 @@ extern "C" int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, cons
 {
 	MG_REQUIRE(ctx, n >= 0 && d_bin_cols && h_breaks && nbreaks && h_partials, "mg_bins_summary: bad arguments");
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
+	if (mg_make_hist_spec(ctx, mg_scratch, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
 		return 1;
 	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_summary: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, mg_scratch, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
 		return 1;
 	unsigned long long *d_acc = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&d_acc, (size_t)hs.total * 96, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_acc, (size_t)hs.total * 96));
 	double *d_part = (double *)(d_acc + 6 * hs.total);
 	k_bins_init<<<(unsigned)std::min<long long>(mg_div_up(hs.total, 256), 1024), 256, 0, st>>>(d_acc, hs.total);
 	MG_LAUNCH_CHECK(ctx);
@@ -2390,8 +2448,6 @@ extern "C" int mg_bins_summary(mg_ctx *ctx, const double *d_vals, int ndim, cons
 	MG_LAUNCH_CHECK(ctx);
 	MG_CUDA(ctx, cudaMemcpyAsync(h_partials, d_part, (size_t)hs.total * 48, cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
-	MG_CUDA(ctx, cudaFreeAsync(d_acc, st));
-	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	return 0;
 }
 
@@ -2404,19 +2460,20 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 	for (int k = 0; k < nq; ++k) // src/GenomeTrackQuantiles.cpp:1223
 		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	HistSpec hs;
 	double *d_breaks = nullptr;
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
+	if (mg_make_hist_spec(ctx, mg_scratch, ndim, h_breaks, nbreaks, include_lowest, hs, nullptr, st)) // validation only: nothing allocated yet
 		return 1;
 	MG_REQUIRE(ctx, hs.total <= MG_BINS_MAX_TOTAL, "mg_bins_quantiles: %lld bins exceed the limit of %lld", hs.total, MG_BINS_MAX_TOTAL);
-	if (mg_make_hist_spec(ctx, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
+	if (mg_make_hist_spec(ctx, mg_scratch, ndim, h_breaks, nbreaks, include_lowest, hs, &d_breaks, st))
 		return 1;
 	const size_t T = (size_t)hs.total;
 	std::vector<int64_t> seg_first(T + 1, 0);
 	char *d_buf = nullptr;
 	const size_t off_idx = T * 8, off_sorted = (off_idx + (size_t)n * 4 + 7) & ~(size_t)7;
 	if (n > 0) {
-		MG_CUDA(ctx, cudaMallocAsync(&d_buf, off_sorted + (size_t)n * 8, st));
+		MG_CUDA(ctx, mg_scratch.alloc(&d_buf, off_sorted + (size_t)n * 8));
 		unsigned long long *d_counts = (unsigned long long *)d_buf;
 		int32_t *d_idx = (int32_t *)(d_buf + off_idx);
 		double *d_sorted = (double *)(d_buf + off_sorted);
@@ -2443,11 +2500,8 @@ extern "C" int mg_bins_quantiles(mg_ctx *ctx, const double *d_vals, int ndim, co
 			k_bins_scatter<false><<<grid, 256, 0, st>>>(d_vals, d_idx, n, hs.total, d_counts, d_sorted);
 		MG_LAUNCH_CHECK(ctx);
 		const int rc = mg_quantiles_segmented(ctx, d_sorted, (int64_t)T, seg_first.data(), nq, h_percentiles, h_out, h_nkept, stream);
-		MG_CUDA(ctx, cudaFreeAsync(d_buf, st));
-		MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 		return rc;
 	}
-	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	for (size_t j = 0; j < T * (size_t)nq; ++j)
 		h_out[j] = std::numeric_limits<double>::quiet_NaN();
 	if (h_nkept)
@@ -2461,11 +2515,12 @@ extern "C" int mg_percentile_lookup(mg_ctx *ctx, double *d_col, int64_t n, const
 {
 	MG_REQUIRE(ctx, n >= 0 && h_breaks && h_bins, "mg_percentile_lookup: bad arguments");
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	HistSpec hs;
 	double *d_breaks = nullptr, *d_bins = nullptr;
-	if (mg_make_hist_spec(ctx, 1, h_breaks, &nbreaks, 0, hs, &d_breaks, st)) // BinFinder::init's checks (src/BinFinder.cpp:10-43)
+	if (mg_make_hist_spec(ctx, mg_scratch, 1, h_breaks, &nbreaks, 0, hs, &d_breaks, st)) // BinFinder::init's checks (src/BinFinder.cpp:10-43)
 		return 1;
-	MG_CUDA(ctx, cudaMallocAsync(&d_bins, sizeof(double) * nbreaks, st));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_bins, sizeof(double) * nbreaks));
 	MG_CUDA(ctx, cudaMemcpyAsync(d_bins, h_bins, sizeof(double) * nbreaks, cudaMemcpyHostToDevice, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st)); // h_bins may be pageable: staged before the call returns
 	if (n > 0) {
@@ -2473,8 +2528,6 @@ extern "C" int mg_percentile_lookup(mg_ctx *ctx, double *d_col, int64_t n, const
 		k_percentile_lookup<<<grid, 256, 0, st>>>(d_col, n, hs, d_bins);
 		MG_LAUNCH_CHECK(ctx);
 	}
-	MG_CUDA(ctx, cudaFreeAsync(d_bins, st));
-	MG_CUDA(ctx, cudaFreeAsync(d_breaks, st));
 	return 0;
 }
 
@@ -2510,9 +2563,10 @@ extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, 
 	if (!count)
 		return 0;
 	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
 	const int64_t nblocks = mg_div_up(count, MG_SCR_THREADS);
 	long long *blk = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&blk, sizeof(long long) * (2 * nblocks + 1), st));
+	MG_CUDA(ctx, mg_scratch.alloc(&blk, sizeof(long long) * (2 * nblocks + 1)));
 	long long *heads = blk, *tails = blk + nblocks, *total = blk + 2 * nblocks;
 	k_screen_count<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails);
 	MG_LAUNCH_CHECK(ctx);
@@ -2523,7 +2577,6 @@ extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, 
 	long long n = 0;
 	MG_CUDA(ctx, cudaMemcpyAsync(&n, total, sizeof(long long), cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
-	MG_CUDA(ctx, cudaFreeAsync(blk, st));
 	*h_nout = n;
 	return 0;
 }
