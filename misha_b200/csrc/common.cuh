@@ -44,6 +44,7 @@ struct mg_ctx {
 	                         // min / max / quantile sets, 2 also for avg / sum alone; 3 (default) k_dense_thin (staged bins and block
 	                         // records, sums / extrema from the chromosome's structures) when two or more function groups share a
 	                         // scan, the per-row kernels for a single group (measured: they win there); 4 k_dense_thin for everything
+	uint32_t pipe_attr = 0;  // k_dense_pipe instantiations whose shared-memory attributes have been set
 	uint32_t tile_attr = 0;  // k_dense_tile instantiations whose dynamic shared-memory limit has been raised on this device
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
 	std::string err;

@@ -35,7 +35,7 @@
 #define MG_TL_QPC (MG_TL_CHUNK / 4)                  // quads per chunk
 #define MG_TL_CAP (MG_TL_THREADS * MG_TL_CHUNK)      // bins a tile can hold
 #define MG_TL_NQD (MG_TL_CAP / 4)
-#define MG_TL_SLOTS (MG_TL_CAP / MG_BW_STRIDE + 1)   // block records a tile can need
+#define MG_TL_SLOTS ((MG_TL_CAP - 1) / MG_BW_STRIDE + 2) // block records a tile can need
 #define MG_TL_TAB_LEVELS 9                           // sparse table over <= 256 chunk extrema: a run of 2^8 chunks is level 8
 #define MG_TL_NW (MG_TL_THREADS / 32)
 
@@ -730,6 +730,302 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 				qv = mg_interp(x1, x2, __dsub_rn(index, fl));
 			}
 			mg_st_stream(q.q_out[k] + i, qv);
+		}
+	}
+}
+
+// ---- k_dense_pipe: k_dense_thin as a persistent, software-pipelined thread block ---------------------------------------------------
+// k_dense_thin's thread block lives through four dependent memory round trips (rows, bulk copies + prefix entries, pos_of_rank, stores)
+// and only the blocks that happen to sit in their copy phase keep bytes in flight: ~50 KB per SM, which at the loaded DRAM latency
+// is ~5 TB/s -- the measured 4.85. Here a thread block walks tiles blockIdx.x, + gridDim.x, ... with TWO stage buffers: while the
+// rows of tile t are computed out of one buffer, the bulk copies of tile t + G land in the other, the prefix / sparse-table entries
+// of tile t + G and the rows of tile t + 2G are in flight in registers. Every resident thread block always has a tile's worth of
+// copies outstanding, and never waits for one it has just issued.
+// resident thread blocks per SM: DIST + 1 stage buffers each, DIST tiles of copies in flight per thread block
+#define MG_PP_BPS(DIST) ((DIST) == 1 ? 3 : 2)
+#define MG_PP_STAGE(Q) (MG_TH_SZ_VALS + ((Q) ? MG_TL_SLOTS * MG_BW_STAGE_BYTES : 0))
+
+struct PipeRaw { // a row as loaded, before the window transform
+	int32_t chrom;
+	int64_t s, e;
+	bool live;
+};
+struct PipeGeo { // what a tile's rows share (uniform over the thread block)
+	uint32_t b0, blk0, cmin;
+	bool fast;
+};
+struct PipePre { // a row's whole groups from the chromosome's structures, AS LOADED: combining them where they are issued would wait for
+	int4 a, b;    // the loads there, one DRAM round trip per tile; they are consumed an iteration later
+	float mx0, mx1, mn0, mn1;
+};
+__device__ __forceinline__ void mg_pipe_pre_clear(PipePre &p)
+{
+	p.a = p.b = make_int4(0, 0, 0, 0);
+	p.mx0 = p.mx1 = __int_as_float(0xff800000);
+	p.mn0 = p.mn1 = __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ void mg_pipe_load(const DenseQuery &q, int64_t i, PipeRaw &r)
+{
+	r.live = i < q.count;
+	r.chrom = 0;
+	r.s = r.e = 0;
+	if (r.live) {
+		int64_t scope;
+		int chrom;
+		mg_get_row(q.rows, q.first + i, chrom, r.s, r.e, scope);
+		r.chrom = chrom;
+	}
+}
+
+__device__ __forceinline__ void mg_pipe_window(const DenseQuery &q, const PipeRaw &raw, TileRow &r)
+{
+	r.sb = r.eb = r.chrom = 0;
+	r.ok = r.reg = r.bad = false;
+	if (!raw.live)
+		return;
+	const int64_t csize = __ldg(q.chrom_sizes + raw.chrom);
+	int64_t ws = raw.s + q.sshift, we = raw.e + q.eshift;
+	ws = ws < 0 ? 0 : ws;
+	we = we > csize ? csize : we;
+	r.ok = ws < we;
+	if (!r.ok)
+		return;
+	if ((uint64_t)csize <= 0x7fffffffull - q.bin_size && q.bin_magic) {
+		const uint32_t nbins = (uint32_t)q.table[raw.chrom].nbins;
+		const uint32_t a = (uint32_t)ws, b = (uint32_t)we + q.bin_size - 1u;
+		const uint32_t sb = (uint32_t)__umul64hi((uint64_t)a, q.bin_magic);
+		uint32_t eb = (uint32_t)__umul64hi((uint64_t)b, q.bin_magic);
+		eb = eb < nbins ? eb : nbins;
+		r.sb = sb;
+		r.eb = eb;
+		r.chrom = (uint32_t)raw.chrom;
+		r.reg = eb > sb;
+	} else
+		r.bad = true;
+}
+
+template <bool SUM, bool WMAX, bool WMIN, bool Q, int DIST>
+__global__ void __launch_bounds__(MG_TL_THREADS, MG_PP_BPS(DIST)) k_dense_pipe(const __grid_constant__ DenseQuery q)
+{
+	constexpr bool MM = WMAX || WMIN;
+	constexpr uint32_t STAGE = MG_PP_STAGE(Q);
+	constexpr int NBUF = DIST + 1;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint64_t s_bar[NBUF];
+	__shared__ __align__(16) uint32_t s_acc[2][8]; // chrom min, chrom max, min sbin, max ebin, -, -, any bad row, -
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const int64_t ntiles = (q.count + MG_TL_THREADS - 1) / MG_TL_THREADS;
+	const int64_t G = gridDim.x;
+	if (t == 0) {
+#pragma unroll
+		for (int b = 0; b < NBUF; ++b)
+			mg_mbar_init(&s_bar[b], 1);
+	}
+	if (t < 16)
+		(&s_acc[0][0])[t] = ((t & 7) == 0 || (t & 7) == 2) ? 0xffffffffu : 0u;
+	__syncthreads();
+
+	uint32_t phase = 0; // bit b: the parity the next wait on buffer b uses
+	// what travels from one iteration to the next: the windows / geometry / prefix entries of the DIST tiles whose copies are in
+	// flight (slot 0 = the tile computed next), and the rows of the tile after those
+	TileRow rn[DIST];
+	PipeGeo gn[DIST];
+	PipePre pn[DIST];
+	PipeRaw raw;
+#pragma unroll
+	for (int d = 0; d < DIST; ++d) {
+		rn[d].sb = rn[d].eb = rn[d].chrom = 0;
+		rn[d].ok = rn[d].reg = rn[d].bad = false;
+		gn[d].b0 = gn[d].blk0 = gn[d].cmin = 0;
+		gn[d].fast = false;
+		mg_pipe_pre_clear(pn[d]);
+	}
+	mg_pipe_load(q, (int64_t)blockIdx.x * MG_TL_THREADS + t, raw);
+	int buf = 0, ibuf = 0; // buffer of the tile computed in this iteration / of the tile whose copies this iteration issues
+
+	// iterations -DIST .. -1 are the prologue: they only issue copies
+	for (int it = -DIST;; ++it) {
+		const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * G, itile = tile + (int64_t)DIST * G;
+		if (it >= 0 && tile >= ntiles)
+			break;
+		const TileRow r = rn[0];
+		const PipeGeo g = gn[0];
+		const PipePre p = pn[0];
+#pragma unroll
+		for (int d = 0; d + 1 < DIST; ++d) {
+			rn[d] = rn[d + 1];
+			gn[d] = gn[d + 1];
+			pn[d] = pn[d + 1];
+		}
+		// ---- A. tile itile: windows, geometry, bulk copies into buffer ibuf, prefix / sparse-table loads ----
+		if (itile < ntiles) {
+			TileRow &rr = rn[DIST - 1];
+			PipeGeo &gg = gn[DIST - 1];
+			PipePre &pp = pn[DIST - 1];
+			mg_pipe_window(q, raw, rr);
+			const bool reg = rr.reg;
+			const uint32_t nb = rr.eb - rr.sb;
+			uint32_t *acc = s_acc[it & 1];
+			{
+				const uint32_t r_cmin = __reduce_min_sync(0xffffffffu, reg ? rr.chrom : 0xffffffffu), r_cmax = __reduce_max_sync(0xffffffffu, rr.chrom);
+				const uint32_t r_bmin = __reduce_min_sync(0xffffffffu, reg ? rr.sb : 0xffffffffu), r_bmax = __reduce_max_sync(0xffffffffu, rr.eb);
+				const bool r_bad = __any_sync(0xffffffffu, rr.bad || (Q && nb > MG_BW_S));
+				if (lane == 0) {
+					atomicMin(&acc[0], r_cmin);
+					atomicMax(&acc[1], r_cmax);
+					atomicMin(&acc[2], r_bmin);
+					atomicMax(&acc[3], r_bmax);
+					if (r_bad)
+						acc[6] = 1u;
+				}
+			}
+			__syncthreads(); // B1: also, every thread is through with the tile that used buffer ibuf
+			const uint4 acc0 = *reinterpret_cast<const uint4 *>(acc);
+			const uint32_t cmin = acc0.x, cmax = acc0.y, bmin = acc0.z, bmax = acc0.w, anybad = acc[6];
+			if (t < 8) // the other set serves the next iteration; its last readers are behind B1
+				s_acc[(it & 1) ^ 1][t] = (t == 0 || t == 2) ? 0xffffffffu : 0u;
+			const bool anyreg = cmin != 0xffffffffu;
+			const uint32_t b0 = bmin & ~7u;
+			const uint32_t span8 = anyreg ? ((bmax - b0 + 7u) & ~7u) : 0u;
+			const uint32_t blk0 = bmin / MG_BW_STRIDE, nrec = anyreg ? (bmax - 1u) / MG_BW_STRIDE - blk0 + 1u : 0u;
+			bool fast = anyreg && !anybad && cmin == cmax && span8 <= MG_TL_CAP;
+			if (Q)
+				fast = fast && q.use_bw && nrec <= MG_TL_SLOTS;
+			gg.b0 = b0;
+			gg.blk0 = blk0;
+			gg.cmin = cmin;
+			gg.fast = fast;
+			mg_pipe_pre_clear(pp);
+			if (fast) {
+				const DenseChrom *ch = q.table + cmin;
+				if (t == 0) {
+					uint8_t *dst = smem + (size_t)ibuf * STAGE;
+					const uint32_t vbytes = span8 * 4u;
+					mg_mbar_expect_tx(&s_bar[ibuf], vbytes + (Q ? nrec * MG_BW_STAGE_BYTES : 0u));
+					mg_bulk_g2s(dst, ch->vals + b0, vbytes, &s_bar[ibuf]);
+					if (Q) {
+						const uint8_t *src = ch->bw + (size_t)blk0 * MG_BW_RECORD_BYTES;
+						for (uint32_t sl = 0; sl < nrec; ++sl)
+							mg_bulk_g2s(dst + MG_TH_SZ_VALS + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar[ibuf]);
+					}
+				}
+				const uint32_t g0 = rr.sb >> 3, g1 = reg ? (rr.eb - 1u) >> 3 : 0u;
+				if (reg && g0 != g1) {
+					pp.a = __ldg(reinterpret_cast<const int4 *>(ch->p8 + g0 + 1));
+					pp.b = __ldg(reinterpret_cast<const int4 *>(ch->p8 + g1));
+					const uint32_t gs = g0 + 1, len = g1 - gs;
+					if (MM && len > 0) {
+						const int j = 31 - __clz((int)len);
+						if (WMAX) {
+							pp.mx0 = __ldg(ch->smax[j] + gs);
+							pp.mx1 = __ldg(ch->smax[j] + g1 - (1u << j));
+						}
+						if (WMIN) {
+							pp.mn0 = __ldg(ch->smin[j] + gs);
+							pp.mn1 = __ldg(ch->smin[j] + g1 - (1u << j));
+						}
+					}
+				}
+			}
+			// the rows of the tile after that
+			mg_pipe_load(q, (itile + G) * MG_TL_THREADS + t, raw);
+		}
+		ibuf = ibuf + 1 == NBUF ? 0 : ibuf + 1;
+		if (it < 0)
+			continue;
+		// ---- B. tile `tile`: out of buffer buf ----
+		const int cb = buf;
+		buf = buf + 1 == NBUF ? 0 : buf + 1;
+		const int64_t i = tile * MG_TL_THREADS + t;
+		const bool live = i < q.count;
+		if (!g.fast) {
+			if (live)
+				mg_tile_slow_row<SUM, MM, Q>(q, i);
+			__syncthreads(); // B2
+			continue;
+		}
+		if (warp == 0)
+			mg_mbar_wait(&s_bar[cb], (phase >> cb) & 1u);
+		phase ^= 1u << cb;
+		__syncthreads(); // B2
+		if (!live)
+			continue;
+		const float *s_vals = reinterpret_cast<const float *>(smem + (size_t)cb * STAGE);
+		const uint8_t *s_lv = smem + (size_t)cb * STAGE + MG_TH_SZ_VALS;
+		const DenseChrom *ch = q.table + g.cmin;
+		const uint32_t sb = r.sb, eb = r.eb, nb = eb - sb, b0 = g.b0;
+		const bool ok = r.ok, reg = r.reg;
+		const uint32_t om = q.out_mask;
+		double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan();
+		uint32_t n = 0;
+		if (ok) {
+			size = 0;
+			exists = 0;
+		}
+		if (reg) {
+			const uint32_t g0 = sb >> 3, g1 = (eb - 1u) >> 3;
+			double S = 0;
+			int nh = 0, nt = 0;
+			float pmx = fmaxf(p.mx0, p.mx1), pmn = fminf(p.mn0, p.mn1);
+			const float *gh = s_vals + (8u * g0 - b0);
+			if (g0 == g1) {
+				mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), (int)(eb - 8u * g0), S, nh, pmx, pmn);
+				n = (uint32_t)nh;
+			} else {
+				double St = 0;
+				mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), 8, S, nh, pmx, pmn);
+				mg_part8_smem<SUM, MM>(s_vals + (8u * g1 - b0), 0, (int)(eb - 8u * g1), St, nt, pmx, pmn);
+				S = (S + (__hiloint2double(p.b.y, p.b.x) - __hiloint2double(p.a.y, p.a.x))) + St;
+				n = (uint32_t)nh + ((uint32_t)p.b.z - (uint32_t)p.a.z) + (uint32_t)nt;
+				if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
+					S = 0;
+					for (uint32_t b = sb - b0; b < eb - b0; ++b) {
+						const float v = s_vals[b];
+						if (v == v)
+							S += (double)v;
+					}
+				}
+			}
+			if (SUM) {
+				size = (double)n;
+				exists = n > 0 ? 1. : 0.;
+				if (n > 0) {
+					avg = mg_f2d(S / (double)n);
+					sum = mg_f2d(S);
+				}
+			}
+			if (MM && n > 0) {
+				mx = (double)pmx;
+				mn = (double)pmn;
+			}
+		}
+		if (SUM) {
+			if (om & (1u << MG_AVG)) mg_st_stream(q.out[MG_AVG] + i, avg);
+			if (om & (1u << MG_NEAREST)) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+			if (om & (1u << MG_SUM)) mg_st_stream(q.out[MG_SUM] + i, sum);
+			if (om & (1u << MG_SIZE)) mg_st_stream(q.out[MG_SIZE] + i, size);
+			if (om & (1u << MG_EXISTS)) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+		}
+		if (WMIN) mg_st_stream(q.out[MG_MIN] + i, mn);
+		if (WMAX) mg_st_stream(q.out[MG_MAX] + i, mx);
+		if (Q) {
+			const uint32_t blk = sb / MG_BW_STRIDE, l = sb - blk * MG_BW_STRIDE;
+			const uint8_t *lv = s_lv + (size_t)(blk - g.blk0) * MG_BW_STAGE_BYTES;
+			const uint16_t *pos = reinterpret_cast<const uint16_t *>(ch->bw + (size_t)blk * MG_BW_RECORD_BYTES + MG_BW_POS_OFFSET);
+			const float *vblk = s_vals + ((int)(blk * MG_BW_STRIDE) - (int)b0);
+			for (int k = 0; k < q.nq; ++k) {
+				double qv = mg_nan();
+				if (n > 0) {
+					const double index = __dmul_rn((double)(n - 1), q.q_pct[k]);
+					const double fl = floor(index);
+					const bool want2 = index != fl;
+					float x1, x2;
+					mg_bw_select<false>(lv, pos, vblk, l, l + nb, (uint32_t)fl, want2, x1, x2);
+					qv = mg_interp(x1, x2, __dsub_rn(index, fl));
+				}
+				mg_st_stream(q.q_out[k] + i, qv);
+			}
 		}
 	}
 }

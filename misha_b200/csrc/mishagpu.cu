@@ -778,7 +778,7 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 	}
 	const int ngroups = (want_sum ? 1 : 0) + (want_mm ? 1 : 0) + (q.nq > 0 ? 1 : 0);
 	const bool tile_ok = ctx->tile_kernel && !ctx->force_sweep && !q.out[MG_STDDEV] && (q.nq == 0 || q.use_bw) &&
-						 (ctx->tile_kernel == 3 ? ngroups >= 2 : (need_sweep || ctx->tile_kernel == 2 || ctx->tile_kernel == 4));
+						 (ctx->tile_kernel == 3 ? ngroups >= 2 : (need_sweep || ctx->tile_kernel == 2 || ctx->tile_kernel >= 4));
 	if (tile_ok) {
 		// a thread block per tile of rows, everything from shared memory (dense_tile.cuh)
 		const unsigned grid = (unsigned)mg_div_up(q.count, MG_TL_THREADS);
@@ -794,7 +794,39 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 		kern<<<grid, MG_TL_THREADS, smem_bytes, st>>>(q);                                                               \
 		break;                                                                                                          \
 	}
-		if (ctx->tile_kernel >= 3) { // staging only (k_dense_thin): sums / extrema from the chromosome's structures
+		if (ctx->tile_kernel == 5 || ctx->tile_kernel == 6) { // k_dense_thin's arithmetic in a persistent, multi-buffered thread block (k_dense_pipe)
+#define MG_PIPE_CASE2(K, D)                                                                                              \
+	{                                                                                                                   \
+		auto kern = k_dense_pipe<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0, D>;                    \
+		constexpr int smem_bytes = ((D) + 1) * MG_PP_STAGE(((K) & 8) != 0);                                             \
+		const unsigned pgrid = (unsigned)std::min<int64_t>(grid, (int64_t)ctx->sm_count * MG_PP_BPS(D));               \
+		if (!(ctx->pipe_attr & (1u << ((K) + 16 * ((D) - 1))))) {                                                       \
+			MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));            \
+			MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                \
+			ctx->pipe_attr |= 1u << ((K) + 16 * ((D) - 1));                                                             \
+			if (getenv("MG_DEBUG_OCC")) {                                                                               \
+				int nb_ = 0;                                                                                            \
+				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, kern, MG_TL_THREADS, smem_bytes);                   \
+				fprintf(stderr, "k_dense_pipe<%d,%d>: %d resident blocks per SM, %d bytes dynamic smem, grid %u\n", (K), (D), nb_, smem_bytes, pgrid); \
+			}                                                                                                           \
+		}                                                                                                               \
+		kern<<<pgrid, MG_TL_THREADS, smem_bytes, st>>>(q);                                                              \
+	}
+#define MG_PIPE_CASE(K)                                                                                                  \
+	case K:                                                                                                             \
+		if (ctx->tile_kernel == 5)                                                                                      \
+			MG_PIPE_CASE2(K, 1)                                                                                         \
+		else                                                                                                            \
+			MG_PIPE_CASE2(K, 2)                                                                                         \
+		break;
+			switch (key) {
+				MG_PIPE_CASE(1) MG_PIPE_CASE(2) MG_PIPE_CASE(3) MG_PIPE_CASE(4) MG_PIPE_CASE(5) MG_PIPE_CASE(6) MG_PIPE_CASE(7) MG_PIPE_CASE(8)
+				MG_PIPE_CASE(9) MG_PIPE_CASE(10) MG_PIPE_CASE(11) MG_PIPE_CASE(12) MG_PIPE_CASE(13) MG_PIPE_CASE(14) MG_PIPE_CASE(15)
+			default: break;
+			}
+#undef MG_PIPE_CASE2
+#undef MG_PIPE_CASE
+		} else if (ctx->tile_kernel >= 3) { // staging only (k_dense_thin): sums / extrema from the chromosome's structures
 #define MG_THIN_CASE(K)                                                                                                  \
 	case K: {                                                                                                           \
 		auto kern = k_dense_thin<((K) & 1) != 0, ((K) & 2) != 0, ((K) & 4) != 0, ((K) & 8) != 0>;                       \

@@ -38,7 +38,10 @@ class DenseSample:
         self.dir = tempfile.mkdtemp(prefix="misha_cpu_baseline_")
         self.shards = []  # (chromid, file, chromsize, start, end, bins)
 
-    def add(self, chromid, name, chromsize, bins, start, end):
+    def add(self, chromid, name, chromsize, bins, start, end, pieces=1):
+        """One chromosome's intervals; pieces > 1 cuts them into that many shards of consecutive intervals (the reference's
+        prepare4multitasking cuts big chromosomes by range so that the workers end together, src/rdbinterval.cpp:446-564); the
+        shards read the same file."""
         if len(start) == 0:
             return
         last_bin = min(len(bins), int((int(end[-1]) + self.eshift) // self.bin_size + 2))
@@ -47,8 +50,10 @@ class DenseSample:
         with open(path, "wb") as f:
             f.write(np.uint32(self.bin_size).tobytes())
             f.write(np.ascontiguousarray(bins[:last_bin], dtype=np.float32).tobytes())
-        self.shards.append((chromid, path, chromsize, np.ascontiguousarray(start, np.int64), np.ascontiguousarray(end, np.int64),
-                            np.ascontiguousarray(bins[:last_bin], np.float32)))
+        b = np.ascontiguousarray(bins[:last_bin], np.float32)
+        cuts = np.linspace(0, len(start), max(1, min(int(pieces), len(start))) + 1).astype(np.int64)
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            self.shards.append((chromid, path, chromsize, np.ascontiguousarray(start[a:z], np.int64), np.ascontiguousarray(end[a:z], np.int64), b))
 
     def n(self):
         return sum(len(s[3]) for s in self.shards)

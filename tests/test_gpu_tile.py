@@ -109,6 +109,25 @@ def check(track, chrom, start, end, ss, es, what):
     assert_same(thin_q, got[4], "%s thin kernel, quantile alone" % what)
     assert_same(thin_m[0], got[2], "%s thin kernel, min alone" % what)
     assert_same(thin_m[1], got[3], "%s thin kernel, max alone" % what)
+    # k_dense_pipe: the same arithmetic in a persistent, multi-buffered thread block (5: two buffers, 6: three): bit for bit
+    # k_dense_thin's columns
+    for tk in (5, 6):
+        ctx.set_option("tile_kernel", tk)
+        try:
+            pipe = t.window(rows, FUNCS, ss, es)
+            pipe_q = t.window(rows, [("quantile", 0.9)], ss, es)[0]
+            pipe_m = t.window(rows, ["min", "max"], ss, es)
+            pipe_a = t.window(rows, ["avg", "max", ("quantile", 0.9)], ss, es)
+        finally:
+            ctx.set_option("tile_kernel", 1)
+        for k in range(len(FUNCS)):
+            assert_same(pipe[k], thin[k], "%s pipe kernel %d %s" % (what, tk, FUNCS[k]))
+        assert_same(pipe_q, got[4], "%s pipe kernel %d, quantile alone" % (what, tk))
+        assert_same(pipe_m[0], got[2], "%s pipe kernel %d, min alone" % (what, tk))
+        assert_same(pipe_m[1], got[3], "%s pipe kernel %d, max alone" % (what, tk))
+        assert_same(pipe_a[0], thin[0], "%s pipe kernel %d, avg of avg + max + quantile" % (what, tk))
+        assert_same(pipe_a[1], got[3], "%s pipe kernel %d, max of avg + max + quantile" % (what, tk))
+        assert_same(pipe_a[2], got[4], "%s pipe kernel %d, quantile of avg + max + quantile" % (what, tk))
     # each function group alone runs another instantiation of the kernel
     for sub in (["avg"], ["max"], ["min", "max"], [("quantile", 0.9)], ["sum", ("quantile", 0.5)], ["avg", "min"]):
         ctx.set_option("tile_kernel", 2)
@@ -186,6 +205,10 @@ def test_fixed_bin_rows(track):
     rows = ctx.rows_fixedbin(BIN, [0, 1], [1000, 0], [900_000, 500_000])
     ctx.set_option("tile_kernel", 4)
     thin = t.window(rows, ["avg", "max", ("quantile", 0.9), "size"], -2000, 2000)
+    ctx.set_option("tile_kernel", 5)
+    pipe = t.window(rows, ["avg", "max", ("quantile", 0.9), "size"], -2000, 2000)
+    for k in range(4):
+        assert_same(pipe[k], thin[k], "fixed-bin rows, pipe kernel column %d" % k)
     ctx.set_option("tile_kernel", 1)
     got = t.window(rows, ["avg", "max", ("quantile", 0.9), "size"], -2000, 2000)
     ctx.set_option("tile_kernel", 3)
