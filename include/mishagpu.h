@@ -287,6 +287,44 @@ int mg_h_coverage(mg_ctx *ctx, const mg_ivset *s, int64_t n, const int32_t *h_ch
 int mg_h_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
 			 int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int64_t sshift, int64_t eshift, double *h_out);
 
+/* ---- several GPUs behind one host thread ----------------------------------------------------------------------------------- */
+/* Replaces, for a single-threaded R process, what the reference does by forking: prepare4multitasking's split of the scope over     */
+/* child processes (src/rdbinterval.cpp:446-564), the parent's concatenation of the children's rows                                  */
+/* (src/GenomeTrackExtract.cpp:1461-1509) and its merges of their partial results (src/GenomeTrackSummary.cpp:205-216,              */
+/* src/GenomeTrackDistribution.cpp:131-137, src/GenomeTrackQuantiles.cpp:278-400). A group owns one mg_ctx per device; every        */
+/* chromosome is staged on ONE member, its owner (whole chromosomes, longest first, to the member holding the fewest bins: work per  */
+/* member is proportional to the bins it owns); rows are routed to the owner of their chromosome; every member has its work enqueued */
+/* before any is waited for. gsummary / gdist partials meet on member 0 (cudaMemcpyPeerAsync, NVLink where the pair has peer access)  */
+/* and are merged there in member order; gquantiles runs ONE exact selection over the members' columns (the per-pass digit         */
+/* histograms meet on the host). With one device a group call returns what the mg_ctx call returns, bit for bit.                   */
+typedef struct mg_group mg_group;
+typedef struct mg_gdense mg_gdense;
+int mg_group_init(int ndev, const int *dev_ids, int nchroms, const int64_t *chrom_sizes, mg_group **out);
+void mg_group_shutdown(mg_group *g);
+const char *mg_group_last_error(const mg_group *g); /* g may be NULL: error of the last failed mg_group_init in this thread */
+int mg_group_size(const mg_group *g);
+mg_ctx *mg_group_ctx(mg_group *g, int member);
+int mg_group_owner(const mg_group *g, int chromid); /* member that stages / serves this chromosome */
+int mg_group_set_option(mg_group *g, const char *name, int64_t value); /* mg_set_option on every member */
+int mg_group_sync(mg_group *g);
+int mg_group_dense_create(mg_group *g, uint32_t bin_size, mg_gdense **out);
+int mg_group_dense_stage(mg_group *g, mg_gdense *t, int chromid, const float *h_bins, int64_t nbins); /* on the owner */
+void mg_group_dense_free(mg_group *g, mg_gdense *t);
+int64_t mg_group_dense_bytes(const mg_gdense *t, int member);
+/* gextract (mg_h_dense_window over the group): host rows in any order, host columns out in the rows' order */
+int mg_group_h_dense_window(mg_group *g, const mg_gdense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
+							int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out);
+/* gsummary / gdist / gquantiles of one dense-track function over the fixed-bin iterator `binsize` of a scope (host intervals):   */
+/* h_partial[6] as mg_dense_summary accumulates it (finalise with mg_summary_finalize), h_counts[nbreaks - 1], h_out[nq].          */
+int mg_group_dense_summary(mg_group *g, const mg_gdense *t, int64_t binsize, int64_t nscope, const int32_t *h_chrom, const int64_t *h_start,
+						   const int64_t *h_end, int64_t sshift, int64_t eshift, int func, double param, double *h_partial);
+int mg_group_dense_hist(mg_group *g, const mg_gdense *t, int64_t binsize, int64_t nscope, const int32_t *h_chrom, const int64_t *h_start,
+						const int64_t *h_end, int64_t sshift, int64_t eshift, int func, double param, const double *h_breaks, int nbreaks,
+						int include_lowest, uint64_t *h_counts);
+int mg_group_dense_quantiles(mg_group *g, const mg_gdense *t, int64_t binsize, int64_t nscope, const int32_t *h_chrom, const int64_t *h_start,
+							 const int64_t *h_end, int64_t sshift, int64_t eshift, int func, double param, int nq, const double *h_percentiles,
+							 double *h_out, int64_t *h_nkept);
+
 #ifdef __cplusplus
 }
 #endif

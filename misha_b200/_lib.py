@@ -49,6 +49,16 @@ def load():
         if hasattr(lib, name):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [c_vp, c_vp]
+    lib.mg_group_last_error.restype = ctypes.c_char_p
+    lib.mg_group_last_error.argtypes = [c_vp]
+    lib.mg_group_ctx.restype = c_vp
+    lib.mg_group_ctx.argtypes = [c_vp, c_int]
+    lib.mg_group_shutdown.restype = None
+    lib.mg_group_shutdown.argtypes = [c_vp]
+    lib.mg_group_dense_free.restype = None
+    lib.mg_group_dense_free.argtypes = [c_vp, c_vp]
+    lib.mg_group_dense_bytes.restype = c_i64
+    lib.mg_group_dense_bytes.argtypes = [c_vp, c_int]
     if hasattr(lib, "mg_summary_finalize"):
         lib.mg_summary_finalize.restype = None
     _lib = lib

@@ -57,6 +57,7 @@ struct mg_ctx {
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	void *pipe_dev[3] = {nullptr, nullptr, nullptr};
 	int64_t pipe_dev_bytes[3] = {0, 0, 0};
+	int64_t pipe_next = 0; // chunks enqueued so far: the slot of the next one is pipe_next % 3
 };
 
 extern thread_local std::string g_mg_init_err;

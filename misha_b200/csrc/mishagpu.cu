@@ -933,16 +933,25 @@ static int mg_check_rows(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 	return 0;
 }
 
+static int64_t mg_pipe_slot_bytes(const mg_ctx *ctx, int ncols) { return ctx->pipe_chunk_rows * (20 + 8 * (int64_t)ncols); }
+
+// Enqueues the chunks of one batch on the three slots and returns without waiting (mg_h_pipeline and the group calls drain the
+// streams). The slots are taken in turn ACROSS calls (ctx->pipe_next), so consecutive batches on one device keep all three streams
+// busy. A batch shorter than eight full chunks is cut into eight (not below 2^16 rows a chunk): with two or three chunks there is
+// no steady state in which one chunk's upload overlaps another's download -- the 1.25 M rows a rank holds of the 10 M at 8 GPUs
+// were 2.4 chunks.
 template <typename Launch>
 static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
 							 double *const *h_out, Launch launch)
 {
-	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows per pipeline slot
-	int64_t done = 0;
-	for (int64_t c = 0; done < n; ++c, done += CHUNK) {
-		const int slot = (int)(c % 3);
+	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows a slot can hold
+	int64_t step = ((n + 7) / 8 + 1023) & ~(int64_t)1023;
+	step = step < 65536 ? 65536 : step;
+	step = step > CHUNK ? CHUNK : step;
+	for (int64_t done = 0; done < n; done += step) {
+		const int slot = (int)(ctx->pipe_next++ % 3);
 		cudaStream_t st = ctx->pipe_stream[slot];
-		const int64_t m = n - done < CHUNK ? n - done : CHUNK;
+		const int64_t m = n - done < step ? n - done : step;
 		char *base = (char *)ctx->pipe_dev[slot];
 		int64_t *d_start = (int64_t *)base, *d_end = (int64_t *)(base + CHUNK * 8);
 		int32_t *d_chrom = (int32_t *)(base + CHUNK * 16);
@@ -979,8 +988,7 @@ static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end && h_out), "host pipeline: NULL row or output arrays");
 	if (mg_check_rows(ctx, n, h_chrom, h_start, h_end, "host pipeline"))
 		return 1;
-	const int64_t slot_bytes = ctx->pipe_chunk_rows * (20 + 8 * (int64_t)ncols);
-	if (mg_pipe_prepare(ctx, slot_bytes))
+	if (mg_pipe_prepare(ctx, mg_pipe_slot_bytes(ctx, ncols)))
 		return 1;
 	int rc = mg_h_pipeline_run(ctx, n, h_chrom, h_start, h_end, ncols, h_out, launch);
 	const std::string first_err = rc ? ctx->err : std::string();
@@ -2188,31 +2196,76 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 }
 
 // ---- gquantiles --------------------------------------------------------------------------------------------------------
-extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
-							void *stream)
+// The selection over a column that lies in pieces on several devices (one piece = the whole-device case): every counting pass runs
+// on each piece on its own device, the digit histograms (<= 1 MB a pass) meet on the host, which steers the selection anyway.
+// Uses the legacy default stream of every device.
+static int mg_quantiles_multi(int nsrc, mg_ctx *const *ctxs, const double *const *d_vals, const int64_t *ns, int nq, const double *h_percentiles,
+							  double *h_out, int64_t *h_nkept, const cudaStream_t *sts = nullptr)
 {
-	MG_REQUIRE(ctx, n >= 0 && nq >= 1 && nq <= MG_QS_MAXSLOTS / 2 && h_percentiles && h_out, "mg_quantiles: bad arguments (1..%d quantiles)",
+	mg_ctx *ctx = ctxs[0];
+	MG_REQUIRE(ctx, nsrc >= 1 && nq >= 1 && nq <= MG_QS_MAXSLOTS / 2 && h_percentiles && h_out, "mg_quantiles: bad arguments (1..%d quantiles)",
 			   MG_QS_MAXSLOTS / 2);
 	for (int k = 0; k < nq; ++k) // C_gquantiles rejects these before scanning (src/GenomeTrackQuantiles.cpp:140-143)
 		MG_REQUIRE(ctx, h_percentiles[k] >= 0 && h_percentiles[k] <= 1, "Percentile (%g) is not in [0, 1] range\n", h_percentiles[k]);
-	cudaStream_t st = mg_stream(stream);
-	MgScratch mg_scratch(st);
 	const double nan = std::numeric_limits<double>::quiet_NaN();
-	unsigned long long *d_hist = nullptr;
 	const size_t hist_words = (size_t)MG_QS_MAXSLOTS * 2048 + 1;
-	MG_CUDA(ctx, mg_scratch.alloc(&d_hist, hist_words * 8));
-	std::vector<unsigned long long> h((size_t)MG_QS_MAXSLOTS * 2048 + 1);
-	const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_div_up(n, 256 * 8), (int64_t)ctx->sm_count * 8));
+	struct Piece {
+		unsigned long long *d_hist = nullptr;
+		std::vector<unsigned long long> h;
+	};
+	std::vector<Piece> pc(nsrc);
+	struct Release {
+		std::vector<Piece> &pc;
+		mg_ctx *const *ctxs;
+		const cudaStream_t *sts;
+		~Release()
+		{
+			for (size_t s = 0; s < pc.size(); ++s)
+				if (pc[s].d_hist) {
+					cudaSetDevice(ctxs[s]->device);
+					cudaFreeAsync(pc[s].d_hist, sts ? sts[s] : nullptr);
+				}
+		}
+	} release{pc, ctxs, sts};
+	int64_t n = 0;
+	for (int s = 0; s < nsrc; ++s) {
+		MG_REQUIRE(ctx, ns[s] >= 0, "mg_quantiles: negative row count");
+		n += ns[s];
+		MG_CUDA(ctx, cudaSetDevice(ctxs[s]->device));
+		MG_CUDA(ctx, cudaMallocAsync(&pc[s].d_hist, hist_words * 8, sts ? sts[s] : nullptr));
+		pc[s].h.resize(hist_words);
+	}
+	std::vector<unsigned long long> h(hist_words);
+	// one counting pass on every piece, then the sum of the pieces' histograms in h[0 .. words)
+	auto count_pass = [&](const QsPass &p, size_t words, bool first) -> int {
+		for (int s = 0; s < nsrc; ++s) {
+			cudaStream_t st = sts ? sts[s] : nullptr;
+			MG_CUDA(ctx, cudaSetDevice(ctxs[s]->device));
+			MG_CUDA(ctx, cudaMemsetAsync(pc[s].d_hist, 0, words * 8, st));
+			if (ns[s]) {
+				const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_div_up(ns[s], 256 * 8), (int64_t)ctxs[s]->sm_count * 8));
+				if (first)
+					k_qs_count<<<grid, 256, 0, st>>>(d_vals[s], ns[s], p, pc[s].d_hist + 1, pc[s].d_hist);
+				else
+					k_qs_count<<<grid, 256, 0, st>>>(d_vals[s], ns[s], p, pc[s].d_hist, nullptr);
+				MG_LAUNCH_CHECK(ctxs[s]);
+			}
+			MG_CUDA(ctx, cudaMemcpyAsync(pc[s].h.data(), pc[s].d_hist, words * 8, cudaMemcpyDeviceToHost, st));
+		}
+		std::fill(h.begin(), h.begin() + words, 0ull);
+		for (int s = 0; s < nsrc; ++s) {
+			MG_CUDA(ctx, cudaSetDevice(ctxs[s]->device));
+			MG_CUDA(ctx, cudaStreamSynchronize(sts ? sts[s] : nullptr));
+			for (size_t w = 0; w < words; ++w)
+				h[w] += pc[s].h[w];
+		}
+		return 0;
+	};
 	// pass 0: top 11 bits of every key + the NaN count
 	QsPass p;
 	memset(&p, 0, sizeof(p));
-	MG_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (2048 + 1) * 8, st));
-	if (n) {
-		k_qs_count<<<grid, 256, 0, st>>>(d_vals, n, p, d_hist + 1, d_hist);
-		MG_LAUNCH_CHECK(ctx);
-	}
-	MG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_hist, (2048 + 1) * 8, cudaMemcpyDeviceToHost, st));
-	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	if (count_pass(p, 2048 + 1, true))
+		return 1;
 	const int64_t N = n - (int64_t)h[0];
 	if (h_nkept)
 		*h_nkept = N;
@@ -2256,11 +2309,8 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 		p.nslots = (int)slots.size();
 		for (size_t j = 0; j < slots.size(); ++j)
 			p.prefix[j] = slots[j];
-		MG_CUDA(ctx, cudaMemsetAsync(d_hist, 0, slots.size() * (size_t)nbins * 8, st));
-		k_qs_count<<<grid, 256, 0, st>>>(d_vals, n, p, d_hist, nullptr);
-		MG_LAUNCH_CHECK(ctx);
-		MG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_hist, slots.size() * (size_t)nbins * 8, cudaMemcpyDeviceToHost, st));
-		MG_CUDA(ctx, cudaStreamSynchronize(st));
+		if (count_pass(p, slots.size() * (size_t)nbins, false))
+			return 1;
 		for (size_t t = 0; t < T; ++t) {
 			const size_t slot = std::lower_bound(slots.begin(), slots.end(), prefix[t]) - slots.begin();
 			const uint32_t d = descend(h.data() + slot * (size_t)nbins, t, nbins);
@@ -2279,6 +2329,14 @@ extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq
 		h_out[k] = value[p1] * (1.0 - w) + value[p2] * w;
 	}
 	return 0;
+}
+
+extern "C" int mg_quantiles(mg_ctx *ctx, const double *d_vals, int64_t n, int nq, const double *h_percentiles, double *h_out, int64_t *h_nkept,
+							void *stream)
+{
+	MG_REQUIRE(ctx, n >= 0, "mg_quantiles: negative row count");
+	const cudaStream_t st = mg_stream(stream);
+	return mg_quantiles_multi(1, &ctx, &d_vals, &n, nq, h_percentiles, h_out, h_nkept, &st);
 }
 
 // ---- gintervals.quantiles: segmented form ----------------------------------------------------------------------------------
@@ -2612,3 +2670,6 @@ extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, 
 	*h_nout = n;
 	return 0;
 }
+
+// ---- several devices behind one host thread ------------------------------------------------------------------------------
+#include "group.cuh"

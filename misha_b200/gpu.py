@@ -530,3 +530,101 @@ def screen_merge(ctx, rows, dflag, first=0, count=None, stream=None, scratch=Non
                                        c_vp(de.ptr), ctypes.byref(nout), c_vp(stream)))
     m = nout.value
     return dc.to_host(stream, m), ds.to_host(stream, m), de.to_host(stream, m)
+
+
+# ---- several GPUs behind one host thread (mg_group_*) -------------------------------------------------------------------------
+class Group:
+    """One mg_ctx per device, driven from this thread: chromosomes staged on their owners, rows routed to them, the small
+    gsummary / gdist / gquantiles partials combined inside the library (include/mishagpu.h, "several GPUs behind one host thread")."""
+
+    def __init__(self, chrom_sizes, devices):
+        self.lib = load()
+        sizes = _arr(chrom_sizes, np.int64)
+        dev = _arr(devices, np.int32)
+        h = c_vp()
+        if self.lib.mg_group_init(c_int(len(dev)), _p(dev), c_int(len(sizes)), _p(sizes), ctypes.byref(h)):
+            raise MishaGpuError(self.lib.mg_group_last_error(None).decode())
+        self.h, self.n, self.chrom_sizes = h, len(dev), sizes
+
+    def _check(self, rc):
+        if rc:
+            raise MishaGpuError(self.lib.mg_group_last_error(self.h).decode())
+
+    def owner(self, chromid):
+        return int(self.lib.mg_group_owner(self.h, c_int(chromid)))
+
+    def set_option(self, name, value):
+        self._check(self.lib.mg_group_set_option(self.h, name.encode(), c_i64(int(value))))
+
+    def launch_count(self):
+        return sum(int(self.lib.mg_launch_count(c_vp(self.lib.mg_group_ctx(self.h, c_int(k))))) for k in range(self.n))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mg_group_shutdown(self.h)
+            self.h = None
+
+
+class GroupDenseTrack:
+    def __init__(self, group, bin_size):
+        self.g = group
+        h = c_vp()
+        group._check(group.lib.mg_group_dense_create(group.h, ctypes.c_uint32(bin_size), ctypes.byref(h)))
+        self.h = h
+
+    def stage(self, chromid, bins):
+        b = _arr(bins, np.float32)
+        self.g._check(self.g.lib.mg_group_dense_stage(self.g.h, self.h, c_int(chromid), _p(b), c_i64(len(b))))
+
+    def bytes(self, member):
+        return int(self.g.lib.mg_group_dense_bytes(self.h, c_int(member)))
+
+    def window_host(self, chrom, start, end, funcs, sshift=0, eshift=0, out=None):
+        chrom, start, end = _arr(chrom, np.int32), _arr(start, np.int64), _arr(end, np.int64)
+        ids, params = _func_args(funcs)
+        n = len(chrom)
+        out = out or [np.empty(n, dtype=np.float64) for _ in ids]
+        ptrs = (c_vp * len(out))(*[o.ctypes.data_as(c_vp) for o in out])
+        g = self.g
+        g._check(g.lib.mg_group_h_dense_window(g.h, self.h, c_i64(n), _p(chrom), _p(start), _p(end), c_i64(sshift), c_i64(eshift),
+                                               c_int(len(ids)), _p(ids), _p(params), ptrs))
+        return out
+
+    def _scope(self, schrom, sstart, send):
+        return _arr(schrom, np.int32), _arr(sstart, np.int64), _arr(send, np.int64)
+
+    def summary(self, binsize, schrom, sstart, send, func="avg", sshift=0, eshift=0):
+        """gsummary over the fixed-bin iterator of the scope: the six partials (finalise with summary_finalize)."""
+        c, s, e = self._scope(schrom, sstart, send)
+        name, prm = (func, 0.0) if isinstance(func, str) else func
+        out = np.empty(6, dtype=np.float64)
+        g = self.g
+        g._check(g.lib.mg_group_dense_summary(g.h, self.h, c_i64(binsize), c_i64(len(c)), _p(c), _p(s), _p(e), c_i64(sshift), c_i64(eshift),
+                                              c_int(FUNC_IDS[name]), c_dbl(prm), _p(out)))
+        return out
+
+    def hist(self, binsize, schrom, sstart, send, breaks, func="avg", include_lowest=False, sshift=0, eshift=0):
+        c, s, e = self._scope(schrom, sstart, send)
+        name, prm = (func, 0.0) if isinstance(func, str) else func
+        b = _arr(breaks, np.float64)
+        out = np.zeros(len(b) - 1, dtype=np.uint64)
+        g = self.g
+        g._check(g.lib.mg_group_dense_hist(g.h, self.h, c_i64(binsize), c_i64(len(c)), _p(c), _p(s), _p(e), c_i64(sshift), c_i64(eshift),
+                                           c_int(FUNC_IDS[name]), c_dbl(prm), _p(b), c_int(len(b)), c_int(int(include_lowest)), _p(out)))
+        return out
+
+    def quantiles(self, binsize, schrom, sstart, send, percentiles, func="avg", sshift=0, eshift=0):
+        c, s, e = self._scope(schrom, sstart, send)
+        name, prm = (func, 0.0) if isinstance(func, str) else func
+        p = _arr(percentiles, np.float64)
+        out = np.empty(len(p), dtype=np.float64)
+        nk = c_i64()
+        g = self.g
+        g._check(g.lib.mg_group_dense_quantiles(g.h, self.h, c_i64(binsize), c_i64(len(c)), _p(c), _p(s), _p(e), c_i64(sshift), c_i64(eshift),
+                                                c_int(FUNC_IDS[name]), c_dbl(prm), c_int(len(p)), _p(p), _p(out), ctypes.byref(nk)))
+        return out, int(nk.value)
+
+    def free(self):
+        if self.h:
+            self.g.lib.mg_group_dense_free(self.g.h, self.h)
+            self.h = None
