@@ -17,6 +17,7 @@ disjoint row range) and the total job is fixed whatever N -> reported as "strong
 (barrier + synchronize on both sides, max over ranks). `e2e`: the same step through mg_h_dense_window with pinned host arrays.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -44,6 +45,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"],
+                    help="BASELINE.json config to run; C3 (default) is the one the metric is quoted on, the others print the same kind of line "
+                         "for their own workload (tools/bench_lines.py)")
     ap.add_argument("--intervals", type=int, default=N_INTERVALS, help=argparse.SUPPRESS)  # smaller = NOT the named config
     ap.add_argument("--scale", type=float, default=1.0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
@@ -122,6 +126,54 @@ def build_workload(args, rank, world):
     return chroms, counts, mine
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """Pins this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host memory is allocated, so that the
+    row / result buffers are first touched on the GPU's own NUMA node. Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return "no NVML affinity within the allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return "bound to the GPU's %d local CPUs (NVML affinity)" % len(cpus)
+    except Exception as e:  # noqa: BLE001 -- binding is an optimisation, never a failure
+        return "not bound (%s)" % e
+
+
+def copy_bound(torch, ctx, h_in, h_out, barrier, steps):
+    """The hardware bound of the end-to-end step: the same bytes, H2D from and D2H into the same pinned buffers, as plain
+    cudaMemcpyAsync on two streams (both directions at once), every rank at the same time. ms per step on this rank."""
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    d_in = [ctx.alloc(a.size, a.dtype) for a in h_in]
+    d_out = [ctx.alloc(a.size, a.dtype) for a in h_out]
+
+    def once():
+        for d, a in zip(d_in, h_in):
+            ctx._check(ctx.lib.mg_copy_h2d(ctx.h, ctypes.c_void_p(d.ptr), ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(a.nbytes), ctypes.c_void_p(s_in.cuda_stream)))
+        for d, a in zip(d_out, h_out):
+            ctx._check(ctx.lib.mg_copy_d2h(ctx.h, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(d.ptr), ctypes.c_int64(a.nbytes), ctypes.c_void_p(s_out.cuda_stream)))
+    once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    s_in.synchronize()
+    s_out.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    barrier()
+    for d in d_in + d_out:
+        d.free()
+    return dt * 1e3
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -141,6 +193,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    numa = bind_to_gpu_cpus(local)
     chroms, counts, mine = build_workload(args, rank, world)
     sizes = [s for _, s in chroms]
     ctx = gpu.Context(sizes, device=local)
@@ -240,6 +293,8 @@ def run_ours(args):
         ms_ranks = [float(x.item()) for x in t]
     launches = args.steps if graph is not None else ctx.launch_count() - launches0
 
+    # ---- the host link's bound for the end-to-end step (before it: the copies overwrite the result buffers) ----
+    bound_ms = max_over_ranks(copy_bound(torch, ctx, [h_chrom, h_start, h_end], h_out, barrier, args.steps))
     # ---- end to end through the host-buffer C-ABI call: pinned host arrays in, host columns out ----
     for _ in range(2):
         dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
@@ -321,7 +376,9 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (track 0.62 GB + index structures 3 GB touched + intervals 0.2 GB vs 126 MB L2)",
                    "staging_s_one_time": round(stage_s, 3), "hbm_bytes_staged_rank0": dense.bytes()},
         "e2e": {"value": n_total / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n_mine * 20), "d2h_bytes_per_step": int(n_mine * 8 * len(FUNCS)),
-                "ms_per_step": e2e_s * 1e3, "api": "mg_h_dense_window (pinned host arrays in, host columns out)"},
+                "ms_per_step": e2e_s * 1e3, "api": "mg_h_dense_window (pinned host arrays in, host columns out)",
+                "copy_bound_ms": bound_ms, "copy_bound": "the step's H2D + D2H bytes alone, plain cudaMemcpyAsync on two streams from / into the "
+                "same pinned buffers, all ranks at once (max over ranks): what the host link allows", "host_numa": numa},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
     if cpu:
@@ -331,9 +388,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def make_cpu_sample(chroms, counts, host_bins, sizes, n_sample, procs):
+def make_cpu_sample(chroms, counts, host_bins, sizes, n_sample, procs, full=False):
+    """full: every interval of every chromosome (the whole C3 job), each chromosome cut into pieces of about total / (4 procs)
+    intervals so that the workers end together (prepare4multitasking cuts by range too). Otherwise a bounded sample: the first
+    n_sample / procs intervals of `procs` chromosomes."""
     from oracle.cpu_baseline import DenseSample
     sample = DenseSample(BIN, SSHIFT, ESHIFT, ("avg", "max", "quantile"), 0.9)
+    if full:
+        piece = max(1, int(sum(counts)) // (4 * max(procs, 1)))
+        for i in range(len(chroms)):
+            bins = host_bins[i] if i in host_bins else synth.dense_bins(i, sizes[i], BIN)
+            s, e = synth.intervals(i, sizes[i], int(counts[i]))
+            sample.add(i, chroms[i][0], sizes[i], bins, s, e, pieces=-(-len(s) // piece))
+        return sample
     # the reference shards by chromosome: take the first intervals of `procs` chromosomes
     ids = sorted(host_bins)[:max(procs, 1)] if host_bins else list(range(min(procs, len(chroms))))
     per = max(1, n_sample // len(ids))
@@ -375,9 +442,14 @@ def run_reference(args):
     pilot.close()
     per_row = dt / max(n, 1)
     steps, warm = args.steps, max(args.warmup, 1)
-    budget_s = 150.0  # whole run
-    n_sample = int(min(max(budget_s / (steps + warm) * procs / per_row * 0.8, 50000), 3_000_000))
-    sample = make_cpu_sample(chroms, counts, {}, sizes, n_sample, procs)
+    budget_s = 240.0  # whole run: the full job per step when K + W passes over it fit, else a bounded sample of it
+    full_s = per_row * args.intervals / procs * 1.15  # what one pass over the whole job should take with `procs` workers
+    full = full_s * (steps + warm) <= budget_s
+    if full:
+        sample = make_cpu_sample(chroms, counts, {}, sizes, 0, procs, full=True)
+    else:
+        n_sample = int(min(max(budget_s / (steps + warm) * procs / per_row * 0.8, 50000), 3_000_000))
+        sample = make_cpu_sample(chroms, counts, {}, sizes, n_sample, procs)
     for _ in range(warm):
         sample.run(procs)
     t0 = time.perf_counter()
@@ -386,14 +458,19 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     sample.close()
     val = n / dt
-    desc = ("%d of the 10 M intervals per step (first %d of each of %d chromosomes); forked workers sharded by chromosome, "
-            "floor(0.7 x %d cores) = %d processes; R data-frame assembly omitted (optimistic for the CPU)" % (n, n // used, used, os.cpu_count() or 1, procs))
+    if full:
+        desc = ("all %d intervals per step (the whole job, same config as the GPU arm); forked workers over %d range shards, "
+                "floor(0.7 x %d cores) = %d processes; R data-frame assembly omitted (optimistic for the CPU)" % (n, len(sample.shards), os.cpu_count() or 1, procs))
+    else:
+        desc = ("%d of the %d intervals per step (first %d of each of %d chromosomes: the whole job would take %.0f s a step); forked workers "
+                "sharded by chromosome, floor(0.7 x %d cores) = %d processes; R data-frame assembly omitted (optimistic for the CPU)"
+                % (n, args.intervals, n // used, used, full_s, os.cpu_count() or 1, procs))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "intervals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 data / f64 accumulate",
         "data": "synthetic",
         "config": {"workload": "C3: gextract avg/max/quantile(0.9) vtracks, sshift/eshift +-5kb, sorted intervals (100-300 bp), 20 bp dense "
-                               "track on a synthetic %.2f Gbp genome; bounded sample per step" % (sum(sizes) / 1e9),
+                               "track on a synthetic %.2f Gbp genome; %s" % (sum(sizes) / 1e9, "the whole job per step" if full else "bounded sample per step"),
                    "intervals": args.intervals, "bin_size": BIN, "funcs": ["avg", "max", "quantile(0.9)"]},
         "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": used, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -404,7 +481,13 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.config != "C3":  # the other BASELINE.json configurations: the same kind of line, tools/bench_lines.py
+        from tools import bench_lines
+        if a.impl == "reference":
+            bench_lines.run_reference_config(a)
+        else:
+            bench_lines.run_config(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -81,6 +81,16 @@ enum mg_func {
 	MG_MAX_POS = 15,   /* "max.pos.abs" / "max.pos.relative" */
 	MG_NUM_FUNCS = 16
 };
+/* Path flag, OR-ed into a function id of a dense-track call. The reference's dense reader answers MG_SIZE, MG_EXISTS and MG_LSE   */
+/* through one of two code paths, chosen by WHICH OTHER functions share the track object (classify_fast_path_mode,                */
+/* src/GenomeTrackFixedBin.cpp:90-147), and the two disagree:                                                                     */
+/*   reducer path (only sum / lse / exists / size registered; the default here): a window inside one NaN bin has size = exists = 0 */
+/*       (assign_single_value, :231-240); lse = the double max-trick sum (RunningLogSumExp);                                      */
+/*   generic path (any other function or a quantile next to them): a window inside ONE bin reports size = exists = 1 whatever the  */
+/*       bin holds (assign_single_bin_value, :150-180); lse accumulates pairwise in float in bin order (lse_accumulate,           */
+/*       src/GenomeTrack1D.h:18-28).                                                                                              */
+/* The host knows which functions it registered on the track object it replaces and says so per function: MG_SIZE | MG_FUNC_GENERIC. */
+#define MG_FUNC_GENERIC 0x100
 
 /* PWM vtrack modes (PWMScorer::ScoringMode src/PWMScorer.h:16-22). */
 enum mg_masked_mode { MG_MASKED_COUNT = 0 /* "masked.count" */, MG_MASKED_FRAC = 1 /* "masked.frac" */ };

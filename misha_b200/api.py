@@ -88,6 +88,122 @@ def _r_logic_to_python(expr):
     return expr
 
 
+# ---- R's vectors on the host side of an expression --------------------------------------------------------------------------
+# numpy compares NaN as FALSE and negates that to TRUE; R compares NA as NA, and NA is never TRUE: !x > c and x != c over a NaN
+# operand must not select the row (gscreen keeps TRUE rows only, src/GenomeTrackScreener.cpp:185-200). The expression is therefore
+# evaluated over these two wrappers: numeric vectors whose comparisons yield three-valued logicals, combined by R's & | !.
+class RLogical:
+    """TRUE where t, NA where na, FALSE elsewhere."""
+
+    def __init__(self, t, na=None):
+        t = np.asarray(t, dtype=bool)
+        self.na = np.zeros(t.shape, dtype=bool) if na is None else np.asarray(na, dtype=bool)
+        self.t = t & ~self.na
+
+    @property
+    def f(self):
+        return ~self.t & ~self.na
+
+    def __and__(self, o):
+        o = _as_logical(o)
+        t, f = self.t & o.t, self.f | o.f
+        return RLogical(t, ~t & ~f)
+
+    __rand__ = __and__
+
+    def __or__(self, o):
+        o = _as_logical(o)
+        t, f = self.t | o.t, self.f & o.f
+        return RLogical(t, ~t & ~f)
+
+    __ror__ = __or__
+
+    def __invert__(self):
+        return RLogical(self.f, self.na)
+
+    def true(self):
+        """The rows a filter keeps."""
+        return self.t
+
+    def as_numeric(self):
+        """What R stores when a logical lands in a numeric column: 1 / 0 / NA."""
+        return np.where(self.na, np.nan, self.t.astype(np.float64))
+
+
+def _as_logical(x):
+    if isinstance(x, RLogical):
+        return x
+    if isinstance(x, RNumeric):
+        return RLogical(x.v != 0, np.isnan(x.v))
+    return RLogical(np.asarray(x, dtype=bool))
+
+
+class RNumeric:
+    def __init__(self, v):
+        self.v = np.asarray(v.v if isinstance(v, RNumeric) else v, dtype=np.float64)
+
+    @staticmethod
+    def _val(o):
+        if isinstance(o, RNumeric):
+            return o.v
+        if isinstance(o, RLogical):
+            return o.as_numeric()
+        return np.asarray(o, dtype=np.float64)
+
+    def _cmp(self, o, op):
+        b = self._val(o)
+        with np.errstate(invalid="ignore"):
+            return RLogical(op(self.v, b), np.isnan(self.v) | np.isnan(b))
+
+    def __lt__(self, o): return self._cmp(o, np.less)
+    def __le__(self, o): return self._cmp(o, np.less_equal)
+    def __gt__(self, o): return self._cmp(o, np.greater)
+    def __ge__(self, o): return self._cmp(o, np.greater_equal)
+    def __eq__(self, o): return self._cmp(o, np.equal)  # noqa: E704
+    def __ne__(self, o): return self._cmp(o, np.not_equal)
+    __hash__ = None
+
+    def _bin(self, o, op, swap=False):
+        a, b = (self._val(o), self.v) if swap else (self.v, self._val(o))
+        with np.errstate(all="ignore"):
+            return RNumeric(op(a, b))
+
+    def __add__(self, o): return self._bin(o, np.add)
+    def __radd__(self, o): return self._bin(o, np.add, True)
+    def __sub__(self, o): return self._bin(o, np.subtract)
+    def __rsub__(self, o): return self._bin(o, np.subtract, True)
+    def __mul__(self, o): return self._bin(o, np.multiply)
+    def __rmul__(self, o): return self._bin(o, np.multiply, True)
+    def __truediv__(self, o): return self._bin(o, np.divide)
+    def __rtruediv__(self, o): return self._bin(o, np.divide, True)
+    def __pow__(self, o): return self._bin(o, np.power)
+    def __rpow__(self, o): return self._bin(o, np.power, True)
+    def __mod__(self, o): return self._bin(o, np.mod)
+    def __neg__(self): return RNumeric(-self.v)
+    def __pos__(self): return self
+    def __and__(self, o): return _as_logical(self) & o
+    def __or__(self, o): return _as_logical(self) | o
+    def __invert__(self): return ~_as_logical(self)
+
+
+def _rfun(f):
+    def g(*a):
+        with np.errstate(all="ignore"):
+            return RNumeric(f(*[RNumeric._val(x) for x in a]))
+    return g
+
+
+R_FUNCS = {"log": _rfun(np.log), "log2": _rfun(np.log2), "log10": _rfun(np.log10), "exp": _rfun(np.exp), "sqrt": _rfun(np.sqrt), "abs": _rfun(np.abs),
+           "pmin": _rfun(np.minimum), "pmax": _rfun(np.maximum), "floor": _rfun(np.floor), "ceiling": _rfun(np.ceil),
+           "is_na": lambda x: RLogical(np.isnan(RNumeric._val(x))), "NaN": np.nan}
+
+
+def r_eval(py, variables):
+    """Evaluates the rewritten expression over R-like vectors. Returns an RLogical, an RNumeric or a Python scalar."""
+    env = {k: RNumeric(v) for k, v in variables.items()}
+    return eval(py, {"__builtins__": {}}, {**R_FUNCS, **env})  # noqa: S307 - the expression language of the host
+
+
 class Intervals(dict):
     """A 1-D intervals set: columns chrom (names), start, end (+ anything else). Mirrors the R data frame."""
 
@@ -417,8 +533,9 @@ class MishaDB:
         return self._sequence().pwm_dev(rows, logp, bidirect=p["bidirect"], extend=p["extend"], mode=vt.func, strand=p["strand"],
                                         score_thresh=p["score_thresh"], sshift=vt.sshift, eshift=vt.eshift)
 
-    def _eval(self, expr, rows, cache):
-        """Host value vector of a track expression over the rows."""
+    def _eval(self, expr, rows, cache, logical=False):
+        """Host value vector of a track expression over the rows. logical: a logical result is returned as RLogical (R's three-valued
+        vector) instead of being stored as 1 / 0 / NA."""
         expr = expr.strip()
         names = self._expr_vars(expr)
         if not names:
@@ -438,14 +555,15 @@ class MishaDB:
             alias[a] = env[n]
         py = _r_logic_to_python(py).replace("^", "**")
         py = re.sub(r"\bTRUE\b", "True", re.sub(r"\bFALSE\b", "False", py))
-        fns = {"log": np.log, "log2": np.log2, "log10": np.log10, "exp": np.exp, "sqrt": np.sqrt, "abs": np.abs, "pmin": np.minimum,
-               "pmax": np.maximum, "is_na": np.isnan, "floor": np.floor, "ceiling": np.ceil, "NaN": np.nan}
         py = py.replace("is.na(", "is_na(")
         try:
-            with np.errstate(all="ignore"):
-                out = eval(py, {"__builtins__": {}}, {**fns, **alias})  # noqa: S307 - the expression language of the host
+            out = r_eval(py, alias)
         except Exception as e:  # noqa: BLE001
             raise MishaError("Evaluation of track expression \"%s\" failed: %s" % (expr, e))
+        if isinstance(out, RLogical):
+            return out if logical else out.as_numeric()
+        if isinstance(out, RNumeric):
+            out = out.v
         out = np.asarray(out)
         if out.shape == ():
             out = np.full(rows.n, out)
@@ -478,10 +596,10 @@ class MishaDB:
             return None
         flag = self._screen_flags_on_device(expr, rows)
         if flag is None:  # general expressions are evaluated by the host on the returned vectors, as in the reference
-            v = self._eval(expr, rows, {})
-            if v.dtype != np.bool_:
+            v = self._eval(expr, rows, {}, logical=True)
+            if not isinstance(v, RLogical):
                 raise MishaError("Expression \"%s\" does not produce a logical result" % expr)  # src/TrackExpressionScanner.h:158-173
-            flag = self.ctx.alloc(rows.n, np.int8).from_host(v.astype(np.int8))
+            flag = self.ctx.alloc(rows.n, np.int8).from_host(v.true().astype(np.int8))  # NA is not TRUE: the row is dropped
         c, s, e = gpu.screen_merge(self.ctx, rows, flag)
         if len(c) == 0:
             return None

@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC,-O2",
+    "--shared", "-Xcompiler", "-fPIC,-O3",
     "-cudart", "static",
     # IEEE arithmetic everywhere: parity with the reference's libm/FPU results is the first gate
     "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",

@@ -44,6 +44,9 @@ struct mg_ctx {
 	                         // min / max / quantile sets, 2 also for avg / sum alone; 3 (default) k_dense_thin (staged bins and block
 	                         // records, sums / extrema from the chromosome's structures) when two or more function groups share a
 	                         // scan, the per-row kernels for a single group (measured: they win there); 4 k_dense_thin for everything
+	int64_t hbm_budget = 0;  // bytes the dense tracks' index structures + cores may hold on this device (0: 85 % of the device's memory)
+	int64_t use_tick = 0;    // advances with every query: least-recently-used index groups go first when the budget is short
+	std::vector<struct mg_dense *> dense_tracks; // every live dense track of this context (budget accounting)
 	uint32_t pipe_attr = 0;  // k_dense_pipe instantiations whose shared-memory attributes have been set
 	uint32_t tile_attr = 0;  // k_dense_tile instantiations whose dynamic shared-memory limit has been raised on this device
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
@@ -57,6 +60,7 @@ struct mg_ctx {
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	void *pipe_dev[3] = {nullptr, nullptr, nullptr};
 	int64_t pipe_dev_bytes[3] = {0, 0, 0};
+	unsigned long long *d_first_bad = nullptr; // first row of a host batch whose chromosome id was out of range (k_rows_sanitize); ~0: none
 	int64_t pipe_next = 0; // chunks enqueued so far: the slot of the next one is pipe_next % 3
 };
 

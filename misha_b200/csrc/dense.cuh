@@ -46,13 +46,32 @@ struct DenseChrom {
 	const double *plse[MG_PYR_MAX];
 };
 
+// Index structures beyond the core {vals, p8} are built on first use, one GROUP at a time for every staged chromosome of the
+// track, and may be dropped again under the context's HBM budget (mg_set_option "hbm_budget_mb"): an avg-only virtual track holds
+// 6 bytes per bin, not 63.
+enum DenseGroupId {
+	MG_G_SD = 0, // pref2: per-bin prefix of squares (stddev)                                        8 B/bin
+	MG_G_EXT,    // min / max pyramids + sparse tables over the groups of 8 (min, max, min.pos, max.pos) ~12 B/bin
+	MG_G_LSE,    // lse pyramid                                                                      ~1.2 B/bin
+	MG_G_BW,     // block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)              ~7.2 B/bin
+	MG_G_WM,     // chromosome-wide wavelet matrix (6) + 5 rank checkpoints (20) + sorted values (4): longer windows ~30 B/bin
+	MG_G_COUNT
+};
+struct DenseGroup {
+	std::vector<void *> allocs;
+	int64_t bytes = 0;
+	bool built = false;
+	int64_t last_use = 0;
+};
+
 struct mg_dense {
 	uint32_t bin_size = 0;
 	int nchroms = 0;
 	std::vector<DenseChrom> h_table;
 	DenseChrom *d_table = nullptr;
-	std::vector<void *> allocs;
-	int64_t bytes = 0;
+	std::vector<void *> allocs; // the core: table, vals, p8
+	int64_t bytes = 0;          // everything held, groups included
+	DenseGroup group[MG_G_COUNT];
 };
 
 #define MG_MAX_Q 8
@@ -68,6 +87,7 @@ struct DenseQuery {
 	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
 	uint32_t pos_rel; // bit f set: position function f is reported relative to the window start
 	uint32_t out_mask; // bit f set: out[f] is requested
+	uint32_t generic_mask; // bit f set: function f follows the reference's generic read_interval path (MG_FUNC_GENERIC)
 	int nq;
 	int prefetch;
 	int use_bw; // quantiles of windows <= MG_BW_S bins from the block-local matrices
@@ -226,8 +246,10 @@ __global__ void __launch_bounds__(MG_ST_THREADS) k_dense_prefix_write(const floa
 			Pref p;
 			p.sum = s0;
 			p.cnt = c0;
-			pref[i] = p;
-			pref2[i] = q0;
+			if (pref)
+				pref[i] = p;
+			if (pref2)
+				pref2[i] = q0;
 		}
 		if (!isnan(v[j])) {
 			s0 += (double)v[j];

@@ -465,6 +465,64 @@ __global__ void __launch_bounds__(256) k_dense_lse(const DenseQuery q)
 	mg_st_stream(q.out[MG_LSE] + i, lse);
 }
 
+// lse as the reference's GENERIC path accumulates it (MG_FUNC_GENERIC): pairwise in float, bin order, from -inf
+// (lse_accumulate, src/GenomeTrack1D.h:18-28; the loop of src/GenomeTrackFixedBin.cpp:881-990). One thread per row walks its window.
+__device__ __forceinline__ void mg_lse_accumulate_f(float &l1, float l2)
+{
+	if (l1 > l2) {
+		if (!isinf(l2))
+			l1 += logf(1.0f + expf(l2 - l1));
+	} else {
+		if (isinf(l1))
+			l1 = l2;
+		else
+			l1 = l2 + logf(1.0f + expf(l1 - l2));
+	}
+}
+__global__ void __launch_bounds__(256) k_dense_lse_generic(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	double lse = mg_nan();
+	if (mg_dense_win(q, q.first + i, w) && w.ebin > w.sbin) {
+		if (w.one_bin)
+			lse = (double)__ldg(w.ch->vals + w.sbin);
+		else {
+			float l = -INFINITY;
+			int64_t n = 0;
+			for (int64_t b = w.sbin; b < w.ebin; ++b) {
+				const float v = __ldg(w.ch->vals + b);
+				if (v == v) {
+					mg_lse_accumulate_f(l, v);
+					++n;
+				}
+			}
+			if (n)
+				lse = (double)l;
+		}
+	}
+	mg_st_stream(q.out[MG_LSE] + i, lse);
+}
+
+// size / exists as the reference's GENERIC path reports them for a window inside ONE bin: 1 whatever the bin holds
+// (assign_single_bin_value, src/GenomeTrackFixedBin.cpp:150-180; the bin must exist in the file, :664-712). Runs after the kernel
+// that wrote the reducer-path columns and overwrites those rows only.
+__global__ void __launch_bounds__(256) k_dense_generic_counts(const DenseQuery q)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= q.count)
+		return;
+	DenseWin w;
+	if (!mg_dense_win(q, q.first + i, w) || !w.one_bin || w.ebin <= w.sbin)
+		return;
+	if ((q.generic_mask >> MG_SIZE) & 1u)
+		q.out[MG_SIZE][i] = 1.;
+	if ((q.generic_mask >> MG_EXISTS) & 1u)
+		q.out[MG_EXISTS][i] = 1.;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_dense_argext: min.pos / max.pos, one thread per row, from the same structures as min / max: the extremum m of the window
 // first (two partial groups + two sparse-table entries), then the FIRST bin holding it -- the reference's strict comparisons

@@ -198,6 +198,30 @@ struct GroupRun {
 	int member;
 	int64_t first, count;
 };
+// first j > i with h_chrom[j] != h_chrom[i] (n when there is none): two ids per 64-bit compare, four compares per iteration -- the
+// routing pass reads every id of the batch on the host, and for 10 M rows a per-id loop was as long as the batch's transfers
+static int64_t mg_run_end(const int32_t *h_chrom, int64_t i, int64_t n)
+{
+	const uint32_t c = (uint32_t)h_chrom[i];
+	const uint64_t pat = ((uint64_t)c << 32) | c;
+	int64_t j = i + 1;
+	while (j < n && (((uintptr_t)(h_chrom + j)) & 7u)) { // to an 8-byte boundary
+		if ((uint32_t)h_chrom[j] != c)
+			return j;
+		++j;
+	}
+	const uint64_t *w = reinterpret_cast<const uint64_t *>(h_chrom + j);
+	int64_t k = 0;
+	const int64_t nw = (n - j) / 2;
+	for (; k + 4 <= nw; k += 4)
+		if (((w[k] ^ pat) | (w[k + 1] ^ pat) | (w[k + 2] ^ pat) | (w[k + 3] ^ pat)) != 0)
+			break;
+	j += 2 * k;
+	while (j < n && (uint32_t)h_chrom[j] == c)
+		++j;
+	return j;
+}
+
 // maximal runs of rows with one owner; false when a chromosome id is out of range
 static bool mg_group_runs(mg_group *g, int64_t n, const int32_t *h_chrom, std::vector<GroupRun> &runs, int64_t max_runs)
 {
@@ -211,20 +235,14 @@ static bool mg_group_runs(mg_group *g, int64_t n, const int32_t *h_chrom, std::v
 			return false;
 		}
 		const int m = g->owner[c];
-		int64_t j = i + 1;
-		int32_t last = c;
-		while (j < n) {
-			const int32_t cj = h_chrom[j];
-			if (cj != last) {
-				if (cj < 0 || cj >= nch || g->owner[cj] != m)
-					break;
-				last = cj;
-			}
-			++j;
+		const int64_t j = mg_run_end(h_chrom, i, n);
+		if (!runs.empty() && runs.back().member == m && runs.back().first + runs.back().count == i)
+			runs.back().count += j - i; // the next chromosome has the same owner
+		else {
+			runs.push_back(GroupRun{m, i, j - i});
+			if ((int64_t)runs.size() > max_runs)
+				return true; // the caller switches to gather / scatter
 		}
-		runs.push_back(GroupRun{m, i, j - i});
-		if ((int64_t)runs.size() > max_runs)
-			return true; // the caller switches to gather / scatter
 		i = j;
 	}
 	return true;

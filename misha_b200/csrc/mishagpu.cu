@@ -69,6 +69,8 @@ extern "C" void mg_shutdown(mg_ctx *ctx)
 		if (ctx->pipe_stream[i])
 			cudaStreamDestroy(ctx->pipe_stream[i]);
 	}
+	if (ctx->d_first_bad)
+		cudaFree(ctx->d_first_bad);
 	for (auto &kv : ctx->stream_scratch)
 		cudaFree(kv.second);
 	cudaFree(ctx->d_chrom_sizes);
@@ -111,6 +113,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 	}
 	if (name && !strcmp(name, "cov_raster")) {
 		ctx->cov_raster = value != 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "hbm_budget_mb")) { // what the dense tracks may hold on this device; least-recently-used index groups are dropped beyond it
+		ctx->hbm_budget = value > 0 ? value << 20 : 0;
 		return 0;
 	}
 	if (name && !strcmp(name, "tile_kernel")) {
@@ -267,6 +273,7 @@ extern "C" int mg_dense_create(mg_ctx *ctx, uint32_t bin_size, mg_dense **out)
 		mg_dense_free(ctx, t);
 		return mg_fail(ctx, "mg_dense_create: %s", cudaGetErrorString(e));
 	}
+	ctx->dense_tracks.push_back(t);
 	*out = t;
 	return 0;
 }
@@ -287,7 +294,51 @@ struct StagePhase {
 	}
 };
 
-static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const Pref *pref /* per-bin, staging only */, MgArena &arena)
+// ---- index groups: built per staged chromosome, on first use (mg_dense_ensure) --------------------------------------------------
+// allocation into a group of the track
+template <typename T>
+static int mg_group_alloc(mg_ctx *ctx, mg_dense *t, int g, int64_t count, T **out, MgArena *arena)
+{
+	return mg_alloc_tracked(ctx, t->group[g].allocs, t->group[g].bytes, count, out, arena);
+}
+
+// the per-bin prefix {sum, count} (pref, nbins + 1 entries) and / or the prefix of squares (pref2): staging scratch for p8 and the
+// chromosome-wide wavelet matrix, and the stddev group itself. Either output may be null.
+static int mg_dense_prefix_pass(mg_ctx *ctx, float *vals, int64_t nbins, Pref *pref, double *pref2, double *totals /* host: sum |v|, sum v^2; may be null */)
+{
+	const int64_t ntiles = mg_div_up(nbins + 1, MG_ST_TILE); // +1: the closing entry pref[nbins]
+	double *tile_sum = nullptr, *tile_abs = nullptr, *tile_sq = nullptr, *abs_total = nullptr;
+	long long *tile_cnt = nullptr;
+	MgScratch scratch(nullptr);
+	MG_CUDA(ctx, scratch.alloc(&tile_sum, sizeof(double) * ntiles));
+	MG_CUDA(ctx, scratch.alloc(&tile_abs, sizeof(double) * ntiles));
+	MG_CUDA(ctx, scratch.alloc(&tile_sq, sizeof(double) * ntiles));
+	MG_CUDA(ctx, scratch.alloc(&tile_cnt, sizeof(long long) * ntiles));
+	MG_CUDA(ctx, scratch.alloc(&abs_total, sizeof(double) * 2));
+	k_dense_clean_reduce<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_abs, tile_sq);
+	MG_LAUNCH_CHECK(ctx);
+	k_dense_tile_scan<<<1, 1024>>>(tile_sum, tile_cnt, tile_abs, tile_sq, ntiles, abs_total);
+	MG_LAUNCH_CHECK(ctx);
+	if (pref || pref2) {
+		k_dense_prefix_write<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_sq, pref, pref2);
+		MG_LAUNCH_CHECK(ctx);
+	}
+	if (totals)
+		MG_CUDA(ctx, cudaMemcpy(totals, abs_total, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+static int mg_build_sd(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena)
+{
+	StagePhase ph("prefix of squares");
+	double *pref2 = nullptr;
+	if (mg_group_alloc(ctx, t, MG_G_SD, dc.nbins + 1, &pref2, &arena) || mg_dense_prefix_pass(ctx, const_cast<float *>(dc.vals), dc.nbins, nullptr, pref2, nullptr))
+		return 1;
+	dc.pref2 = pref2;
+	return 0;
+}
+
+static int mg_build_ext(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena)
 {
 	const int64_t nbins = dc.nbins;
 	// pyramids: level j+1 exists while level j has more than one group of 8
@@ -298,7 +349,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 		for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
 			const int64_t nparent = mg_div_up(nchild, 8), padded = (nparent + 7) / 8 * 8 + 8;
 			float *pmax = nullptr, *pmin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &pmin, &arena))
+			if (mg_group_alloc(ctx, t, MG_G_EXT, padded, &pmax, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, padded, &pmin, &arena))
 				return 1;
 			k_pyr_build<<<(unsigned)mg_div_up(padded, 256), 256>>>(cmax, cmin, nchild, pmax, pmin, padded);
 			MG_LAUNCH_CHECK(ctx);
@@ -309,71 +360,86 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 			nchild = nparent;
 		}
 	}
-	// lse pyramid (double): level j+1 exists while level j has more than one group of 8
-	{
-		StagePhase ph("lse pyramid");
-		const double *child = nullptr;
-		int64_t nchild = nbins;
-		for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
-			const int64_t nparent = mg_div_up(nchild, 8);
-			double *pl = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nparent, &pl, &arena))
-				return 1;
-			if (lv == 0)
-				k_lse_build<float><<<(unsigned)mg_div_up(nparent, 256), 256>>>(dc.vals, nchild, pl, nparent);
-			else
-				k_lse_build<double><<<(unsigned)mg_div_up(nparent, 256), 256>>>(child, nchild, pl, nparent);
-			MG_LAUNCH_CHECK(ctx);
-			dc.plse[lv] = pl;
-			child = pl;
-			nchild = nparent;
-		}
-	}
 	// sparse tables over the groups of 8 (level 0 = pyramid level 1)
-	{
-		StagePhase ph("sparse tables");
-		const int64_t ng = mg_div_up(nbins > 0 ? nbins : 1, 8);
-		dc.ngroups = ng;
-		if (!dc.pmax[0]) { // chromosomes of <= 8 bins have no pyramid level: build the single group entry
-			float *pmax = nullptr, *pmin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, 16, &pmin, &arena))
-				return 1;
-			k_pyr_build<<<1, 256>>>(dc.vals, dc.vals, nbins, pmax, pmin, 16);
-			MG_LAUNCH_CHECK(ctx);
-			dc.smax[0] = pmax;
-			dc.smin[0] = pmin;
-		} else {
-			dc.smax[0] = dc.pmax[0];
-			dc.smin[0] = dc.pmin[0];
-		}
-		for (int j = 1; j < MG_ST_LEVELS; ++j) {
-			if ((1ll << j) > ng) { // never selected: a run of len groups uses level floor(log2 len)
-				dc.smax[j] = dc.smax[j - 1];
-				dc.smin[j] = dc.smin[j - 1];
-				continue;
-			}
-			float *smax = nullptr, *smin = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smax, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, ng, &smin, &arena))
-				return 1;
-			k_st_build<<<(unsigned)mg_div_up(ng, 256), 256>>>(dc.smax[j - 1], dc.smin[j - 1], ng, 1ll << (j - 1), smax, smin);
-			MG_LAUNCH_CHECK(ctx);
-			dc.smax[j] = smax;
-			dc.smin[j] = smin;
-		}
-	}
-	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
-	{
-		StagePhase ph("block wavelet matrices");
-		const int64_t nblk = mg_div_up(nbins > 0 ? nbins : 1, MG_BW_STRIDE);
-		uint8_t *bw = nullptr;
-		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nblk * MG_BW_RECORD_BYTES, &bw, &arena))
+	StagePhase ph("sparse tables");
+	const int64_t ng = mg_div_up(nbins > 0 ? nbins : 1, 8);
+	dc.ngroups = ng;
+	if (!dc.pmax[0]) { // chromosomes of <= 8 bins have no pyramid level: build the single group entry
+		float *pmax = nullptr, *pmin = nullptr;
+		if (mg_group_alloc(ctx, t, MG_G_EXT, 16, &pmax, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, 16, &pmin, &arena))
 			return 1;
-		k_bw_build<<<(unsigned)nblk, MG_BW_BUILD_THREADS>>>(dc.vals, nbins, bw);
+		k_pyr_build<<<1, 256>>>(dc.vals, dc.vals, nbins, pmax, pmin, 16);
 		MG_LAUNCH_CHECK(ctx);
-		dc.bw = bw;
+		dc.smax[0] = pmax;
+		dc.smin[0] = pmin;
+	} else {
+		dc.smax[0] = dc.pmax[0];
+		dc.smin[0] = dc.pmin[0];
 	}
+	for (int j = 1; j < MG_ST_LEVELS; ++j) {
+		if ((1ll << j) > ng) { // never selected: a run of len groups uses level floor(log2 len)
+			dc.smax[j] = dc.smax[j - 1];
+			dc.smin[j] = dc.smin[j - 1];
+			continue;
+		}
+		float *smax = nullptr, *smin = nullptr;
+		if (mg_group_alloc(ctx, t, MG_G_EXT, ng, &smax, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, ng, &smin, &arena))
+			return 1;
+		k_st_build<<<(unsigned)mg_div_up(ng, 256), 256>>>(dc.smax[j - 1], dc.smin[j - 1], ng, 1ll << (j - 1), smax, smin);
+		MG_LAUNCH_CHECK(ctx);
+		dc.smax[j] = smax;
+		dc.smin[j] = smin;
+	}
+	return 0;
+}
+
+static int mg_build_lse(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena)
+{
+	// lse pyramid (double): level j+1 exists while level j has more than one group of 8
+	StagePhase ph("lse pyramid");
+	const double *child = nullptr;
+	int64_t nchild = dc.nbins;
+	for (int lv = 0; lv < MG_PYR_MAX && nchild > 8; ++lv) {
+		const int64_t nparent = mg_div_up(nchild, 8);
+		double *pl = nullptr;
+		if (mg_group_alloc(ctx, t, MG_G_LSE, nparent, &pl, &arena))
+			return 1;
+		if (lv == 0)
+			k_lse_build<float><<<(unsigned)mg_div_up(nparent, 256), 256>>>(dc.vals, nchild, pl, nparent);
+		else
+			k_lse_build<double><<<(unsigned)mg_div_up(nparent, 256), 256>>>(child, nchild, pl, nparent);
+		MG_LAUNCH_CHECK(ctx);
+		dc.plse[lv] = pl;
+		child = pl;
+		nchild = nparent;
+	}
+	return 0;
+}
+
+static int mg_build_bw(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena)
+{
+	// block-local wavelet matrices (quantiles of windows <= MG_BW_S bins)
+	StagePhase ph("block wavelet matrices");
+	const int64_t nblk = mg_div_up(dc.nbins > 0 ? dc.nbins : 1, MG_BW_STRIDE);
+	uint8_t *bw = nullptr;
+	if (mg_group_alloc(ctx, t, MG_G_BW, nblk * MG_BW_RECORD_BYTES, &bw, &arena))
+		return 1;
+	k_bw_build<<<(unsigned)nblk, MG_BW_BUILD_THREADS>>>(dc.vals, dc.nbins, bw);
+	MG_LAUNCH_CHECK(ctx);
+	dc.bw = bw;
+	return 0;
+}
+
+static int mg_build_wm(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena)
+{
 	// wavelet matrix over the dense ranks of the non-NaN values
 	StagePhase ph_wm("chromosome wavelet matrix");
+	const int64_t nbins = dc.nbins;
+	MgScratch tmp(nullptr);
+	Pref *pref = nullptr; // per-bin prefix: where each non-NaN bin lands in the compacted order
+	MG_CUDA(ctx, tmp.alloc(&pref, sizeof(Pref) * (size_t)(nbins + 1)));
+	if (mg_dense_prefix_pass(ctx, const_cast<float *>(dc.vals), nbins, pref, nullptr, nullptr))
+		return 1;
 	long long m = 0;
 	MG_CUDA(ctx, cudaMemcpy(&m, &pref[nbins].cnt, sizeof(long long), cudaMemcpyDeviceToHost));
 	dc.wm_m = m;
@@ -385,8 +451,8 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	uint2 *wm = nullptr;
 	uint32_t *zeros = nullptr;
 	float *sorted = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, dc.wm_blocks * (nlevels > 0 ? nlevels : 1), &wm, &arena) ||
-		mg_alloc_tracked(ctx, t->allocs, t->bytes, MG_WM_LEVELS, &zeros, &arena) || mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &sorted, &arena))
+	if (mg_group_alloc(ctx, t, MG_G_WM, dc.wm_blocks * (nlevels > 0 ? nlevels : 1), &wm, &arena) ||
+		mg_group_alloc(ctx, t, MG_G_WM, MG_WM_LEVELS, &zeros, &arena) || mg_group_alloc(ctx, t, MG_G_WM, m + 16, &sorted, &arena))
 		return 1;
 	dc.wm = wm;
 	dc.wm_zeros = zeros;
@@ -394,12 +460,12 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 	const size_t mm = (size_t)(m > 0 ? m : 1);
 	uint32_t *keys[2] = {nullptr, nullptr}, *pos[2] = {nullptr, nullptr}, *d_zero = nullptr;
 	uint2 *scratch = nullptr;
-	MG_CUDA(ctx, cudaMallocAsync(&keys[0], sizeof(uint32_t) * mm, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&keys[1], sizeof(uint32_t) * mm, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&pos[0], sizeof(uint32_t) * mm, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&pos[1], sizeof(uint32_t) * mm, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(uint2) * dc.wm_blocks, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&d_zero, sizeof(uint32_t), 0));
+	MG_CUDA(ctx, tmp.alloc(&keys[0], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, tmp.alloc(&keys[1], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, tmp.alloc(&pos[0], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, tmp.alloc(&pos[1], sizeof(uint32_t) * mm));
+	MG_CUDA(ctx, tmp.alloc(&scratch, sizeof(uint2) * dc.wm_blocks));
+	MG_CUDA(ctx, tmp.alloc(&d_zero, sizeof(uint32_t)));
 	if (nbins) {
 		k_wm_compact<<<(unsigned)mg_div_up(nbins, 256), 256>>>(dc.vals, pref, nbins, keys[0], pos[0]);
 		MG_LAUNCH_CHECK(ctx);
@@ -433,7 +499,7 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 		const uint32_t *src = wk[lv & 1];
 		if (lv >= 4 && (lv & 3) == 0) { // checkpoint: the rank keys in the order entering this level
 			uint32_t *ck = nullptr;
-			if (mg_alloc_tracked(ctx, t->allocs, t->bytes, m + 16, &ck, &arena))
+			if (mg_group_alloc(ctx, t, MG_G_WM, m + 16, &ck, &arena))
 				return 1;
 			MG_CUDA(ctx, cudaMemset(ck + m, 0xff, sizeof(uint32_t) * 16));
 			k_wm_ckpt<<<gm, 256>>>(src, m, sorted, ck);
@@ -449,12 +515,135 @@ static int mg_dense_build_index(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, const 
 		MG_LAUNCH_CHECK(ctx);
 	}
 	MG_CUDA(ctx, cudaDeviceSynchronize());
-	cudaFreeAsync(keys[0], 0);
-	cudaFreeAsync(keys[1], 0);
-	cudaFreeAsync(pos[0], 0);
-	cudaFreeAsync(pos[1], 0);
-	cudaFreeAsync(scratch, 0);
-	cudaFreeAsync(d_zero, 0);
+	return 0;
+}
+
+static const int64_t MG_GROUP_EST_BYTES_PER_BIN[MG_G_COUNT] = {8, 13, 2, 8, 32}; // what a group takes, rounded up (budget checks before building)
+static const char *const MG_GROUP_NAME[MG_G_COUNT] = {"stddev prefix", "min / max tables", "lse pyramid", "block wavelet matrices", "chromosome wavelet matrix"};
+
+static int mg_build_group_chrom(mg_ctx *ctx, mg_dense *t, int g, DenseChrom &dc)
+{
+	MgArena arena;
+	arena.chunk = (size_t)MG_GROUP_EST_BYTES_PER_BIN[g] * (size_t)dc.nbins + ((size_t)1 << 20); // one chunk per chromosome and group
+	switch (g) {
+	case MG_G_SD: return mg_build_sd(ctx, t, dc, arena);
+	case MG_G_EXT: return mg_build_ext(ctx, t, dc, arena);
+	case MG_G_LSE: return mg_build_lse(ctx, t, dc, arena);
+	case MG_G_BW: return mg_build_bw(ctx, t, dc, arena);
+	default: return mg_build_wm(ctx, t, dc, arena);
+	}
+}
+
+static void mg_clear_group_pointers(DenseChrom &dc, int g)
+{
+	switch (g) {
+	case MG_G_SD: dc.pref2 = nullptr; break;
+	case MG_G_EXT:
+		for (int j = 0; j < MG_PYR_MAX; ++j)
+			dc.pmax[j] = dc.pmin[j] = nullptr;
+		for (int j = 0; j < MG_ST_LEVELS; ++j)
+			dc.smax[j] = dc.smin[j] = nullptr;
+		break;
+	case MG_G_LSE:
+		for (int j = 0; j < MG_PYR_MAX; ++j)
+			dc.plse[j] = nullptr;
+		break;
+	case MG_G_BW: dc.bw = nullptr; break;
+	default:
+		dc.wm = nullptr;
+		dc.wm_zeros = nullptr;
+		dc.wm_sorted = nullptr;
+		for (int j = 0; j < 7; ++j)
+			dc.wm_ckpt[j] = nullptr;
+		dc.wm_levels = 0;
+		dc.wm_blocks = 0;
+		dc.wm_m = 0;
+	}
+}
+
+static int64_t mg_dense_held(const mg_ctx *ctx)
+{
+	int64_t b = 0;
+	for (const mg_dense *t : ctx->dense_tracks)
+		b += t->bytes;
+	return b;
+}
+static int64_t mg_dense_budget(const mg_ctx *ctx) { return ctx->hbm_budget > 0 ? ctx->hbm_budget : (int64_t)(0.85 * (double)ctx->hbm_bytes); }
+
+// drops one built group of a track (every chromosome's part)
+static int mg_drop_group(mg_ctx *ctx, mg_dense *t, int g)
+{
+	DenseGroup &gr = t->group[g];
+	MG_CUDA(ctx, cudaDeviceSynchronize()); // nothing in flight reads what goes
+	for (DenseChrom &dc : t->h_table)
+		mg_clear_group_pointers(dc, g);
+	MG_CUDA(ctx, cudaMemcpy(t->d_table, t->h_table.data(), sizeof(DenseChrom) * t->nchroms, cudaMemcpyHostToDevice));
+	for (void *p : gr.allocs)
+		cudaFree(p);
+	gr.allocs.clear();
+	t->bytes -= gr.bytes;
+	gr.bytes = 0;
+	gr.built = false;
+	return 0;
+}
+
+// makes room for `need` more bytes: least-recently-used groups go first, never one of `keep_t`'s groups in `keep_mask`
+static int mg_make_room(mg_ctx *ctx, int64_t need, const mg_dense *keep_t, uint32_t keep_mask)
+{
+	const int64_t budget = mg_dense_budget(ctx);
+	while (mg_dense_held(ctx) + need > budget) {
+		mg_dense *vt = nullptr;
+		int vg = -1;
+		for (mg_dense *t : ctx->dense_tracks)
+			for (int g = 0; g < MG_G_COUNT; ++g) {
+				if (!t->group[g].built || (t == keep_t && ((keep_mask >> g) & 1u)))
+					continue;
+				if (!vt || t->group[g].last_use < vt->group[vg].last_use) {
+					vt = t;
+					vg = g;
+				}
+			}
+		if (!vt)
+			return mg_fail(ctx, "dense tracks hold %lld MB and %lld MB more are needed, beyond the budget of %lld MB (option hbm_budget_mb) with nothing left to drop",
+						   (long long)(mg_dense_held(ctx) >> 20), (long long)(need >> 20), (long long)(budget >> 20));
+		if (mg_drop_group(ctx, vt, vg))
+			return 1;
+	}
+	return 0;
+}
+
+// Every group of `mask` built for every staged chromosome of the track; a no-op (one mask test) when they are.
+static int mg_dense_ensure(mg_ctx *ctx, mg_dense *t, uint32_t mask)
+{
+	const int64_t tick = ++ctx->use_tick;
+	uint32_t missing = 0;
+	for (int g = 0; g < MG_G_COUNT; ++g)
+		if ((mask >> g) & 1u) {
+			t->group[g].last_use = tick;
+			if (!t->group[g].built)
+				missing |= 1u << g;
+		}
+	if (!missing)
+		return 0;
+	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	int64_t staged_bins = 0;
+	for (const DenseChrom &dc : t->h_table)
+		if (dc.vals)
+			staged_bins += dc.nbins;
+	for (int g = 0; g < MG_G_COUNT; ++g) {
+		if (!((missing >> g) & 1u))
+			continue;
+		if (mg_make_room(ctx, MG_GROUP_EST_BYTES_PER_BIN[g] * staged_bins, t, mask))
+			return 1;
+		StagePhase ph(MG_GROUP_NAME[g]);
+		for (DenseChrom &dc : t->h_table)
+			if (dc.vals && mg_build_group_chrom(ctx, t, g, dc))
+				return 1;
+		t->bytes += t->group[g].bytes;
+		t->group[g].built = true;
+	}
+	MG_CUDA(ctx, cudaDeviceSynchronize());
+	MG_CUDA(ctx, cudaMemcpy(t->d_table, t->h_table.data(), sizeof(DenseChrom) * t->nchroms, cudaMemcpyHostToDevice));
 	return 0;
 }
 
@@ -468,33 +657,24 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	MG_REQUIRE(ctx, nbins == expect, "mg_dense_stage: chromosome %d holds %lld bins, expected %lld for bin size %u", chromid,
 			   (long long)nbins, (long long)expect, t->bin_size);
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (mg_make_room(ctx, 6 * nbins + (1 << 20), t, ~0u))
+		return 1;
+	// the core: the bins and the per-group-of-8 prefix (6 bytes per bin); everything else waits for the function that needs it
 	MgArena arena;
-	arena.chunk = (size_t)72 * (size_t)nbins + ((size_t)4 << 20); // ~64 bytes per bin of index structures: one chunk per chromosome
+	arena.chunk = (size_t)6 * (size_t)nbins + ((size_t)1 << 20);
 	float *vals = nullptr;
 	Pref *pref = nullptr;
 	const int64_t padded = (nbins + 7) / 8 * 8 + 8; // group-of-8 / float4-safe tail, NaN filled
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals, &arena))
 		return 1;
-	MG_CUDA(ctx, cudaMallocAsync(&pref, sizeof(Pref) * (size_t)(nbins + 1), 0)); // per-bin prefix: staging scratch, released below
+	MgScratch tmp(nullptr);
+	MG_CUDA(ctx, tmp.alloc(&pref, sizeof(Pref) * (size_t)(nbins + 1))); // per-bin prefix: staging scratch
 	MG_CUDA(ctx, cudaMemset(vals, 0xff, sizeof(float) * padded)); // 0xffffffff is a NaN
 	if (nbins)
 		MG_CUDA(ctx, cudaMemcpy(vals, h_bins, sizeof(float) * nbins, cudaMemcpyHostToDevice));
-	const int64_t ntiles = mg_div_up(nbins + 1, MG_ST_TILE); // +1: the closing entry pref[nbins]
-	double *tile_sum = nullptr, *tile_abs = nullptr, *tile_sq = nullptr, *abs_total = nullptr, *pref2 = nullptr;
-	long long *tile_cnt = nullptr;
-	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nbins + 1, &pref2, &arena))
+	double tot[2] = {0, 0};
+	if (mg_dense_prefix_pass(ctx, vals, nbins, pref, nullptr, tot)) // also turns +-inf into NaN in place
 		return 1;
-	MG_CUDA(ctx, cudaMallocAsync(&tile_sum, sizeof(double) * ntiles, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&tile_abs, sizeof(double) * ntiles, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&tile_sq, sizeof(double) * ntiles, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&tile_cnt, sizeof(long long) * ntiles, 0));
-	MG_CUDA(ctx, cudaMallocAsync(&abs_total, sizeof(double) * 2, 0));
-	k_dense_clean_reduce<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_abs, tile_sq);
-	MG_LAUNCH_CHECK(ctx);
-	k_dense_tile_scan<<<1, 1024>>>(tile_sum, tile_cnt, tile_abs, tile_sq, ntiles, abs_total);
-	MG_LAUNCH_CHECK(ctx);
-	k_dense_prefix_write<<<(unsigned)ntiles, MG_ST_THREADS>>>(vals, nbins, tile_sum, tile_cnt, tile_sq, pref, pref2);
-	MG_LAUNCH_CHECK(ctx);
 	DenseChrom dc;
 	memset(&dc, 0, sizeof(dc));
 	dc.vals = vals;
@@ -508,23 +688,20 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 		dc.p8 = p8;
 	}
 	dc.nbins = nbins;
-	dc.pref2 = pref2;
-	{
-		double tot[2] = {0, 0};
-		MG_CUDA(ctx, cudaMemcpy(tot, abs_total, sizeof(tot), cudaMemcpyDeviceToHost));
-		dc.abs_sum = tot[0];
-		dc.sq_sum = tot[1];
-	}
-	if (mg_dense_build_index(ctx, t, dc, pref, arena))
-		return 1;
-	cudaFreeAsync(pref, 0);
+	dc.ngroups = mg_div_up(nbins > 0 ? nbins : 1, 8);
+	dc.abs_sum = tot[0];
+	dc.sq_sum = tot[1];
+	// groups this track already holds for its other chromosomes
+	for (int g = 0; g < MG_G_COUNT; ++g)
+		if (t->group[g].built) {
+			const int64_t b0 = t->group[g].bytes;
+			if (mg_build_group_chrom(ctx, t, g, dc))
+				return 1;
+			t->bytes += t->group[g].bytes - b0;
+		}
+	MG_CUDA(ctx, cudaDeviceSynchronize());
 	t->h_table[chromid] = dc;
 	MG_CUDA(ctx, cudaMemcpy(t->d_table + chromid, &dc, sizeof(DenseChrom), cudaMemcpyHostToDevice));
-	cudaFreeAsync(tile_sum, 0);
-	cudaFreeAsync(tile_abs, 0);
-	cudaFreeAsync(tile_sq, 0);
-	cudaFreeAsync(tile_cnt, 0);
-	cudaFreeAsync(abs_total, 0);
 	return 0;
 }
 
@@ -532,6 +709,11 @@ extern "C" void mg_dense_free(mg_ctx *ctx, mg_dense *t)
 {
 	if (!t)
 		return;
+	if (ctx)
+		ctx->dense_tracks.erase(std::remove(ctx->dense_tracks.begin(), ctx->dense_tracks.end(), t), ctx->dense_tracks.end());
+	for (int g = 0; g < MG_G_COUNT; ++g)
+		for (void *p : t->group[g].allocs)
+			cudaFree(p);
 	for (void *p : t->allocs)
 		cudaFree(p);
 	delete t;
@@ -709,9 +891,37 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.stage = ctx->stage_records ? 1 : 0;
 	q.prefetch = ctx->prefetch ? 1 : 0;
 	need_sweep = false;
+	{ // the index groups these functions read, built now if this is their first use on this track (a mask test otherwise)
+		uint32_t groups = 0;
+		for (int k = 0; k < nfuncs; ++k) {
+			const int f = funcs[k] & ~MG_FUNC_GENERIC;
+			if (f == MG_MIN || f == MG_MAX || f == MG_MIN_POS || f == MG_MAX_POS)
+				groups |= 1u << MG_G_EXT;
+			else if (f == MG_STDDEV)
+				groups |= 1u << MG_G_SD;
+			else if (f == MG_LSE)
+				groups |= 1u << MG_G_LSE;
+			else if (f == MG_QUANTILE) {
+				if (ctx->block_wm)
+					groups |= 1u << MG_G_BW;
+				// windows of more than MG_BW_S bins walk the chromosome-wide matrix. Only the fixed-bin iterator bounds its rows'
+				// length without looking at them: iterator bin + shifts
+				const bool bounded = ctx->block_wm && rows->src.kind == 1 &&
+									 (rows->src.binsize + (eshift > 0 ? eshift : 0) - (sshift < 0 ? sshift : 0)) / (int64_t)t->bin_size + 2 <= MG_BW_S;
+				if (!bounded)
+					groups |= 1u << MG_G_WM;
+			}
+		}
+		if (groups && mg_dense_ensure(ctx, const_cast<mg_dense *>(t), groups))
+			return 1;
+	}
 	for (int k = 0; k < nfuncs; ++k) {
-		const int f = funcs[k];
+		const int f = funcs[k] & ~MG_FUNC_GENERIC;
 		MG_REQUIRE(ctx, f >= 0 && f < MG_NUM_FUNCS, "unknown function id %d", f);
+		if (funcs[k] & MG_FUNC_GENERIC) {
+			MG_REQUIRE(ctx, f == MG_SIZE || f == MG_EXISTS || f == MG_LSE, "MG_FUNC_GENERIC applies to size, exists and lse (function id %d)", f);
+			q.generic_mask |= 1u << f;
+		}
 		MG_REQUIRE(ctx, d_out[k], "output column %d is NULL", k);
 		if (f == MG_QUANTILE) {
 			MG_REQUIRE(ctx, q.nq < MG_MAX_Q, "at most %d quantile columns per call", MG_MAX_Q);
@@ -769,7 +979,10 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 				MG_LAUNCH_CHECK(ctx);
 			}
 			if (q.out[MG_LSE]) {
-				k_dense_lse<<<tgrid, 256, 0, st>>>(q);
+				if ((q.generic_mask >> MG_LSE) & 1u)
+					k_dense_lse_generic<<<tgrid, 256, 0, st>>>(q);
+				else
+					k_dense_lse<<<tgrid, 256, 0, st>>>(q);
 				MG_LAUNCH_CHECK(ctx);
 			}
 		}
@@ -886,6 +1099,10 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 #undef MG_SWEEP_CASE
 	}
 	MG_LAUNCH_CHECK(ctx);
+	if (q.generic_mask & ((1u << MG_SIZE) | (1u << MG_EXISTS))) { // the rows whose window lies inside one bin, as the generic path counts them
+		k_dense_generic_counts<<<(unsigned)mg_div_up(q.count, 256), 256, 0, st>>>(q);
+		MG_LAUNCH_CHECK(ctx);
+	}
 	return 0;
 }
 
@@ -903,6 +1120,10 @@ extern "C" int mg_dense_window(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 static int mg_pipe_prepare(mg_ctx *ctx, int64_t bytes_per_slot)
 {
 	MG_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->d_first_bad) {
+		MG_CUDA(ctx, cudaMalloc(&ctx->d_first_bad, 8));
+		MG_CUDA(ctx, cudaMemset(ctx->d_first_bad, 0xff, 8)); // "no bad row"
+	}
 	for (int i = 0; i < 3; ++i) {
 		if (!ctx->pipe_stream[i])
 			MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
@@ -925,12 +1146,34 @@ static int mg_pipe_prepare(mg_ctx *ctx, int64_t bytes_per_slot)
 // the whole context, so explicit rows are checked where they are still host arrays
 static int mg_check_rows(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *, const int64_t *, const char *who)
 { // coordinates need no check: the window transform clamps them to the chromosome
+	// one branch-free pass (the largest id as unsigned: negative ids become huge), the offending row is looked for only on failure
+	uint32_t worst = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const uint32_t c = (uint32_t)h_chrom[i];
+		worst = c > worst ? c : worst;
+	}
+	if (worst < (uint32_t)ctx->nchroms)
+		return 0;
 	for (int64_t i = 0; i < n; ++i) {
 		const int32_t c = h_chrom[i];
 		if (c < 0 || c >= ctx->nchroms)
 			return mg_fail(ctx, "%s: row %lld names chromosome id %d (the context holds %d)", who, (long long)i, (int)c, ctx->nchroms);
 	}
 	return 0;
+}
+
+// Chromosome ids of a chunk already on the device: an id out of range is replaced by 0 -- the kernels index per-chromosome tables with
+// it -- and the first offending row is recorded; the host looks at the record once, after the drain. (A pass over the ids on the
+// host, even a branch-free one per chunk, cost more than a millisecond of the 5 ms a 10 M-row batch takes end to end.)
+__global__ void __launch_bounds__(256) k_rows_sanitize(int32_t *chrom, int64_t m, int nchroms, int64_t base_row, unsigned long long *first_bad)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m)
+		return;
+	if ((uint32_t)chrom[i] >= (uint32_t)nchroms) {
+		atomicMin(first_bad, (unsigned long long)(base_row + i));
+		chrom[i] = 0;
+	}
 }
 
 static int64_t mg_pipe_slot_bytes(const mg_ctx *ctx, int ncols) { return ctx->pipe_chunk_rows * (20 + 8 * (int64_t)ncols); }
@@ -942,16 +1185,16 @@ static int64_t mg_pipe_slot_bytes(const mg_ctx *ctx, int ncols) { return ctx->pi
 // were 2.4 chunks.
 template <typename Launch>
 static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end, int ncols,
-							 double *const *h_out, Launch launch)
+							 double *const *h_out, Launch launch, int64_t row_base = 0)
 {
 	const int64_t CHUNK = ctx->pipe_chunk_rows; // rows a slot can hold
 	int64_t step = ((n + 7) / 8 + 1023) & ~(int64_t)1023;
 	step = step < 65536 ? 65536 : step;
 	step = step > CHUNK ? CHUNK : step;
 	for (int64_t done = 0; done < n; done += step) {
+		const int64_t m = n - done < step ? n - done : step;
 		const int slot = (int)(ctx->pipe_next++ % 3);
 		cudaStream_t st = ctx->pipe_stream[slot];
-		const int64_t m = n - done < step ? n - done : step;
 		char *base = (char *)ctx->pipe_dev[slot];
 		int64_t *d_start = (int64_t *)base, *d_end = (int64_t *)(base + CHUNK * 8);
 		int32_t *d_chrom = (int32_t *)(base + CHUNK * 16);
@@ -961,6 +1204,8 @@ static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, con
 		MG_CUDA(ctx, cudaMemcpyAsync(d_start, h_start + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
 		MG_CUDA(ctx, cudaMemcpyAsync(d_end, h_end + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
 		MG_CUDA(ctx, cudaMemcpyAsync(d_chrom, h_chrom + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+		k_rows_sanitize<<<(unsigned)mg_div_up(m, 256), 256, 0, st>>>(d_chrom, m, ctx->nchroms, row_base + done, ctx->d_first_bad);
+		MG_LAUNCH_CHECK(ctx);
 		mg_rows rows;
 		rows.src.kind = 0;
 		rows.src.n = m;
@@ -975,6 +1220,17 @@ static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, con
 	return 0;
 }
 
+// After the drain: did k_rows_sanitize meet a chromosome id out of range? (the record is reset either way)
+static int mg_pipe_bad_row(mg_ctx *ctx, const int32_t *h_chrom, const char *who)
+{
+	unsigned long long bad = ~0ull;
+	MG_CUDA(ctx, cudaMemcpy(&bad, ctx->d_first_bad, 8, cudaMemcpyDeviceToHost));
+	if (bad == ~0ull)
+		return 0;
+	MG_CUDA(ctx, cudaMemset(ctx->d_first_bad, 0xff, 8));
+	return mg_fail(ctx, "%s: row %llu names chromosome id %d (the context holds %d)", who, bad, (int)h_chrom[bad], ctx->nchroms);
+}
+
 // Rows in host memory -> result columns in host memory: chunks of pipe_chunk_rows rows travel through three device slots, each
 // on its own stream (upload, the launch the caller supplies, download), so the copies of one chunk overlap the kernel of
 // another in both directions. launch(rows, m, d_cols, stream) enqueues the computation of one chunk of m rows.
@@ -986,8 +1242,6 @@ static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 {
 	MG_REQUIRE(ctx, n >= 0 && ncols > 0 && ncols <= 32, "host pipeline: bad arguments");
 	MG_REQUIRE(ctx, n == 0 || (h_chrom && h_start && h_end && h_out), "host pipeline: NULL row or output arrays");
-	if (mg_check_rows(ctx, n, h_chrom, h_start, h_end, "host pipeline"))
-		return 1;
 	if (mg_pipe_prepare(ctx, mg_pipe_slot_bytes(ctx, ncols)))
 		return 1;
 	int rc = mg_h_pipeline_run(ctx, n, h_chrom, h_start, h_end, ncols, h_out, launch);
@@ -999,6 +1253,8 @@ static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 	}
 	if (!first_err.empty())
 		ctx->err = first_err; // the failure that started it, not what the drain reported
+	if (!rc)
+		rc = mg_pipe_bad_row(ctx, h_chrom, "host pipeline");
 	return rc;
 }
 
@@ -1451,7 +1707,7 @@ extern "C" int mg_sparse_window(mg_ctx *ctx, const mg_sparse *t, const mg_rows *
 	q.table = t->d_table;
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	for (int k = 0; k < nfuncs; ++k) {
-		const int f = funcs[k];
+		const int f = funcs[k]; // the sparse reader has one path: MG_FUNC_GENERIC is a dense-track flag and an unknown id here
 		MG_REQUIRE(ctx, f >= 0 && f < MG_NUM_FUNCS, "unknown function id %d", f);
 		MG_REQUIRE(ctx, d_out[k], "output column %d is NULL", k);
 		if (f == MG_QUANTILE) {

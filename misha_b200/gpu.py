@@ -177,12 +177,20 @@ class Rows:
             pass
 
 
+FUNC_GENERIC = 0x100  # MG_FUNC_GENERIC (include/mishagpu.h): "size:generic", "exists:generic", "lse:generic"
+
+
 def _func_args(funcs):
-    """funcs: list of names or (name, param). Returns (ids int32[], params float64[])."""
+    """funcs: list of names or (name, param). Returns (ids int32[], params float64[]). A ":generic" suffix on size / exists / lse
+    asks for the answer of the reference's generic read_interval path (the one it takes when other functions share the track
+    object) instead of its reducer path."""
     ids, params = [], []
     for f in funcs:
         name, prm = (f, 0.0) if isinstance(f, str) else f
-        ids.append(FUNC_IDS[name])
+        flag = 0
+        if name.endswith(":generic"):
+            name, flag = name[:-len(":generic")], FUNC_GENERIC
+        ids.append(FUNC_IDS[name] | flag)
         params.append(float(prm) if prm is not None else 0.0)
     return np.array(ids, dtype=np.int32), np.array(params, dtype=np.float64)
 

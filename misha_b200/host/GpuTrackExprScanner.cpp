@@ -397,4 +397,124 @@ void gsummary_dense(mg_ctx *ctx, const mg_dense *track, const std::vector<Interv
 	mg_rows_free(ctx, rows);
 }
 
+// ---- GpuGroupSession ---------------------------------------------------------------------------------------------------------
+// sort + unify a scope as gtracksummary / gtrackdist / gquantiles do before scanning (unify_overlaps, src/TrackExpressionScanner.cpp:934-954)
+static void unified_scope(const std::vector<Interval> &scope, std::vector<int32_t> &c, std::vector<int64_t> &s, std::vector<int64_t> &e)
+{
+	std::vector<Interval> sc(scope);
+	std::stable_sort(sc.begin(), sc.end(), [](const Interval &a, const Interval &b) { return std::tie(a.chromid, a.start) < std::tie(b.chromid, b.start); });
+	for (const Interval &iv : sc) {
+		if (!c.empty() && c.back() == iv.chromid && e.back() >= iv.start) {
+			if (e.back() < iv.end)
+				e.back() = iv.end;
+			continue;
+		}
+		c.push_back(iv.chromid);
+		s.push_back(iv.start);
+		e.push_back(iv.end);
+	}
+}
+
+GpuGroupSession::GpuGroupSession(const std::vector<int> &devices, const std::vector<int64_t> &chrom_sizes)
+{
+	if (mg_group_init((int)devices.size(), devices.data(), (int)chrom_sizes.size(), chrom_sizes.data(), &m_g))
+		throw MishaGpuException(mg_group_last_error(nullptr));
+}
+
+GpuGroupSession::~GpuGroupSession()
+{
+	for (mg_gdense *t : m_tracks)
+		mg_group_dense_free(m_g, t);
+	mg_group_shutdown(m_g);
+}
+
+void GpuGroupSession::check(int rc) const
+{
+	if (rc)
+		throw MishaGpuException(mg_group_last_error(m_g));
+}
+
+mg_gdense *GpuGroupSession::dense_create(uint32_t bin_size)
+{
+	mg_gdense *t = nullptr;
+	check(mg_group_dense_create(m_g, bin_size, &t));
+	m_tracks.push_back(t);
+	return t;
+}
+
+void GpuGroupSession::dense_stage(mg_gdense *t, int chromid, const float *bins, int64_t nbins) { check(mg_group_dense_stage(m_g, t, chromid, bins, nbins)); }
+
+ExtractResult GpuGroupSession::gextract(const mg_gdense *t, const std::vector<std::pair<int, double>> &funcs, int64_t sshift, int64_t eshift,
+										const std::vector<Interval> &scope)
+{
+	// the scope sorted by (chromid, start) as C_gextract does before scanning (src/GenomeTrackExtract.cpp:557-562); intervalID keeps
+	// the caller's order
+	std::vector<int64_t> order(scope.size());
+	for (size_t i = 0; i < order.size(); ++i)
+		order[i] = (int64_t)i;
+	std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+		return std::tie(scope[a].chromid, scope[a].start) < std::tie(scope[b].chromid, scope[b].start);
+	});
+	ExtractResult res;
+	const size_t n = scope.size();
+	res.chrom.resize(n);
+	res.start.resize(n);
+	res.end.resize(n);
+	res.interval_id.resize(n);
+	for (size_t i = 0; i < n; ++i) {
+		const Interval &iv = scope[order[i]];
+		res.chrom[i] = iv.chromid;
+		res.start[i] = iv.start;
+		res.end[i] = iv.end;
+		res.interval_id[i] = (int32_t)order[i] + 1;
+	}
+	std::vector<int> ids;
+	std::vector<double> params;
+	std::vector<double *> out;
+	res.values.assign(funcs.size(), std::vector<double>(n));
+	for (size_t k = 0; k < funcs.size(); ++k) {
+		ids.push_back(funcs[k].first);
+		params.push_back(funcs[k].second);
+		out.push_back(res.values[k].data());
+	}
+	check(mg_group_h_dense_window(m_g, t, (int64_t)n, res.chrom.data(), res.start.data(), res.end.data(), sshift, eshift, (int)ids.size(), ids.data(),
+								  params.data(), out.data()));
+	return res;
+}
+
+void GpuGroupSession::gsummary(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param,
+							   int64_t sshift, int64_t eshift, double out[7])
+{
+	std::vector<int32_t> c;
+	std::vector<int64_t> s, e;
+	unified_scope(scope, c, s, e);
+	double part[6];
+	check(mg_group_dense_summary(m_g, t, iterator_binsize, (int64_t)c.size(), c.data(), s.data(), e.data(), sshift, eshift, func, param, part));
+	mg_summary_finalize(part, out);
+}
+
+std::vector<uint64_t> GpuGroupSession::gdist(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param,
+											 int64_t sshift, int64_t eshift, const std::vector<double> &breaks, bool include_lowest)
+{
+	std::vector<int32_t> c;
+	std::vector<int64_t> s, e;
+	unified_scope(scope, c, s, e);
+	std::vector<uint64_t> counts(breaks.size() > 1 ? breaks.size() - 1 : 0);
+	check(mg_group_dense_hist(m_g, t, iterator_binsize, (int64_t)c.size(), c.data(), s.data(), e.data(), sshift, eshift, func, param, breaks.data(),
+							  (int)breaks.size(), include_lowest ? 1 : 0, counts.data()));
+	return counts;
+}
+
+std::vector<double> GpuGroupSession::gquantiles(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func,
+												double param, int64_t sshift, int64_t eshift, const std::vector<double> &percentiles)
+{
+	std::vector<int32_t> c;
+	std::vector<int64_t> s, e;
+	unified_scope(scope, c, s, e);
+	std::vector<double> q(percentiles.size());
+	check(mg_group_dense_quantiles(m_g, t, iterator_binsize, (int64_t)c.size(), c.data(), s.data(), e.data(), sshift, eshift, func, param,
+								   (int)percentiles.size(), percentiles.data(), q.data(), nullptr));
+	return q;
+}
+
 } // namespace mishagpu

@@ -141,4 +141,38 @@ ExtractResult gextract(GpuTrackExprScanner &scanner, const std::vector<std::stri
 void gsummary_dense(mg_ctx *ctx, const mg_dense *track, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param,
 					int64_t sshift, int64_t eshift, double out[7]);
 
+// ---- several GPUs behind this one thread (mg_group_*, include/mishagpu.h) --------------------------------------------------------
+// What gextract_multitask / gtracksummary_multitask / gtrackdist_multitask / gquantiles_multitask do with forked children
+// (src/GenomeTrackExtract.cpp:1128-1560, src/GenomeTrackSummary.cpp:174-226, src/GenomeTrackDistribution.cpp:82-150,
+// src/GenomeTrackQuantiles.cpp:278-400), for dense-track vtracks: the session owns the group and its staged tracks, the calls take
+// the scope the way the .Call entry points get it and return what the parent process assembles.
+class GpuGroupSession {
+public:
+	GpuGroupSession(const std::vector<int> &devices, const std::vector<int64_t> &chrom_sizes);
+	~GpuGroupSession();
+	GpuGroupSession(const GpuGroupSession &) = delete;
+	GpuGroupSession &operator=(const GpuGroupSession &) = delete;
+	mg_group *group() const { return m_g; }
+	int size() const { return mg_group_size(m_g); }
+	// a dense track of the group; every chromosome is staged on its owner
+	mg_gdense *dense_create(uint32_t bin_size);
+	void dense_stage(mg_gdense *t, int chromid, const float *bins, int64_t nbins);
+	// gextract with the scope as the (intervals) iterator: one column per {func, param}, all under the same sshift / eshift; rows come
+	// back in the scope's sorted order with intervalID = 1-based row of the caller's scope, like ExtractResult of the scanner
+	ExtractResult gextract(const mg_gdense *t, const std::vector<std::pair<int, double>> &funcs, int64_t sshift, int64_t eshift,
+						   const std::vector<Interval> &scope);
+	// gsummary / gdist / gquantiles of one function over the fixed-bin iterator of the (sorted, unified) scope
+	void gsummary(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param, int64_t sshift,
+				  int64_t eshift, double out[7]);
+	std::vector<uint64_t> gdist(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param,
+								int64_t sshift, int64_t eshift, const std::vector<double> &breaks, bool include_lowest);
+	std::vector<double> gquantiles(const mg_gdense *t, const std::vector<Interval> &scope, int64_t iterator_binsize, int func, double param,
+								   int64_t sshift, int64_t eshift, const std::vector<double> &percentiles);
+
+private:
+	void check(int rc) const;
+	mg_group *m_g = nullptr;
+	std::vector<mg_gdense *> m_tracks;
+};
+
 } // namespace mishagpu

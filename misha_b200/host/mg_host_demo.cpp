@@ -16,6 +16,10 @@
 //   exprs <vname> ...
 //   out <file>      (int64 nrows, int64 nexprs, chrom int32[n], start int64[n], end int64[n], intervalID int32[n], nexprs x double[n])
 //   summary <dense name> <binsize> <out file> (7 doubles)
+//   group <ndev> <dense name> <binsize> <func id> <param> <sshift> <eshift> <out file>
+//        the same track on a group of the first <ndev> devices (GpuGroupSession): gextract of the scope under the window, then gsummary,
+//        gdist (breaks 0, 1, ..., 100, include.lowest) and gquantiles (0.1, 0.5, 0.9) of the plain track over the fixed-bin iterator
+//        <binsize> -> int64 n, double[n] column, 7 doubles, 100 uint64, 3 doubles
 #include <cstdio>
 #include <cstring>
 #include <tuple>
@@ -63,6 +67,7 @@ int main(int argc, char **argv)
 		mg_ctx *ctx = nullptr;
 		std::vector<int64_t> sizes;
 		std::map<std::string, mg_dense *> dense;
+		std::map<std::string, std::pair<uint32_t, std::vector<std::string>>> dense_files;
 		std::map<std::string, mg_sparse *> sparse;
 		std::map<std::string, mg_ivset *> ivsets;
 		std::vector<std::tuple<std::string, std::string, std::string, int, double, int64_t, int64_t>> vtracks;
@@ -110,8 +115,10 @@ int main(int argc, char **argv)
 				in >> name >> bs;
 				mg_dense *t = nullptr;
 				chk(mg_dense_create(ctx, bs, &t));
+				dense_files[name].first = bs;
 				for (size_t c = 0; c < sizes.size(); ++c) {
 					in >> path;
+					dense_files[name].second.push_back(path);
 					if (path == "-")
 						continue;
 					const std::vector<float> bins = read_raw<float>(path);
@@ -232,6 +239,38 @@ int main(int argc, char **argv)
 				gsummary_dense(ctx, dense.at(name), scope, bs, MG_AVG, 0., 0, 0, out);
 				std::ofstream f(path, std::ios::binary);
 				f.write((const char *)out, sizeof(out));
+			} else if (cmd == "group") {
+				int ndev, func;
+				std::string name, path;
+				int64_t bs, ss, es;
+				double param;
+				in >> ndev >> name >> bs >> func >> param >> ss >> es >> path;
+				std::vector<int> devs;
+				for (int d = 0; d < ndev; ++d)
+					devs.push_back(d);
+				GpuGroupSession session(devs, sizes);
+				const auto &files = dense_files.at(name);
+				mg_gdense *gt = session.dense_create(files.first);
+				for (size_t c = 0; c < files.second.size(); ++c)
+					if (files.second[c] != "-") {
+						const std::vector<float> bins = read_raw<float>(files.second[c]);
+						session.dense_stage(gt, (int)c, bins.data(), (int64_t)bins.size());
+					}
+				const ExtractResult r = session.gextract(gt, {{func, param}}, ss, es, scope);
+				double sum7[7];
+				session.gsummary(gt, scope, bs, MG_AVG, 0., 0, 0, sum7);
+				std::vector<double> breaks;
+				for (int b = 0; b <= 100; ++b)
+					breaks.push_back((double)b);
+				const std::vector<uint64_t> hist = session.gdist(gt, scope, bs, MG_AVG, 0., 0, 0, breaks, true);
+				const std::vector<double> q = session.gquantiles(gt, scope, bs, MG_AVG, 0., 0, 0, {0.1, 0.5, 0.9});
+				std::ofstream f(path, std::ios::binary);
+				const int64_t n = (int64_t)r.values[0].size();
+				f.write((const char *)&n, 8);
+				f.write((const char *)r.values[0].data(), n * 8);
+				f.write((const char *)sum7, sizeof(sum7));
+				f.write((const char *)hist.data(), (std::streamsize)(hist.size() * 8));
+				f.write((const char *)q.data(), (std::streamsize)(q.size() * 8));
 			} else
 				throw std::runtime_error("unknown directive " + cmd);
 		}

@@ -93,6 +93,24 @@ def dense_window_ext(bins, bin_size, chromsize, start, end, sshift=0, eshift=0, 
     return {f: out[:, k].copy() for k, f in enumerate(EXT_COLS)}
 
 
+def dense_counts(bins, bin_size, chromsize, start, end, sshift=0, eshift=0, generic=False):
+    """size / exists of dense windows as the reference's reader reports them: the reducer path counts the non-NaN bins
+    (src/GenomeTrackFixedBin.cpp:196-240); the generic path (generic=True) does the same except for a window inside ONE bin that the
+    file holds, where assign_single_bin_value reports 1 / 1 whatever the bin's value (:150-180, :664-712)."""
+    start, end = _i64(start), _i64(end)
+    size = dense_window(bins, bin_size, chromsize, start, end, sshift, eshift, 0.5, ("size",))["size"]
+    exists = np.where(np.isnan(size), np.nan, (size > 0).astype(np.float64))
+    if generic:
+        ws = np.maximum(start + sshift, 0)
+        we = np.minimum(end + eshift, chromsize)
+        sb = ws // bin_size
+        eb = -(-we // bin_size)
+        one = (ws < we) & (eb == sb + 1) & (sb < len(bins))
+        size = np.where(one, 1.0, size)
+        exists = np.where(one, 1.0, exists)
+    return {"size": size, "exists": exists}
+
+
 def sparse_window_ext(rs, re, rv, chromsize, start, end, sshift=0, eshift=0):
     rs, re = _i64(rs), _i64(re)
     rv = np.ascontiguousarray(rv, dtype=np.float32)

@@ -102,6 +102,19 @@ def dense_eval_ext(chrom_file, chromid, start, end, funcs=EXT_COLS, extra_funcs=
     return _eval_ext(lib().ref_dense_eval_ext, chrom_file, chromid, start, end, funcs, extra_funcs)
 
 
+def dense_eval_counts(chrom_file, chromid, start, end, generic):
+    """{size, exists, lse} of a dense track from the reference's reader with only those three registered (its reducer path) or with
+    avg and max next to them (generic=True: its generic path)."""
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    mask = (1 << 10) | (1 << 9) | (1 << 6)  # SIZE, EXISTS, LSE (GenomeTrack1D::Functions, src/GenomeTrack1D.h:46)
+    if generic:
+        mask |= (1 << 0) | (1 << 2)
+    out = np.empty((len(start), 3), dtype=np.float64)
+    _check(lib().ref_dense_eval_counts(chrom_file.encode(), ctypes.c_int(chromid), ctypes.c_uint32(mask), c_i64(len(start)), _p(start), _p(end), _p(out)))
+    return {"size": out[:, 0].copy(), "exists": out[:, 1].copy(), "lse": out[:, 2].copy()}
+
+
 def sparse_eval_ext(chrom_file, chromid, start, end, funcs=EXT_COLS, extra_funcs=()):
     return _eval_ext(lib().ref_sparse_eval_ext, chrom_file, chromid, start, end, funcs, extra_funcs)
 

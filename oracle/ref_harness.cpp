@@ -127,6 +127,28 @@ extern "C" int ref_dense_eval_ext(const char *chrom_file, int chromid, uint32_t 
 	REF_CATCH
 }
 
+// size / exists / lse of a dense track as the reference's reader reports them under a given set of registered functions: the
+// reducer path (only sum / lse / exists / size registered) and the generic path (anything else next to them) disagree on windows
+// inside one NaN bin (src/GenomeTrackFixedBin.cpp:150-180 vs :231-240). out: n x 3 doubles {size, exists, lse}.
+extern "C" int ref_dense_eval_counts(const char *chrom_file, int chromid, uint32_t func_mask, int64_t n, const int64_t *start, const int64_t *end,
+									 double *out)
+{
+	REF_TRY
+	GenomeTrackFixedBin t;
+	t.init_read(chrom_file, chromid);
+	register_funcs(t, func_mask, 0, 0);
+	const double nan = std::numeric_limits<double>::quiet_NaN();
+	for (int64_t i = 0; i < n; ++i) {
+		GInterval iv(chromid, start[i], end[i], 0);
+		t.read_interval(iv);
+		out[3 * i + 0] = (func_mask & (1u << GenomeTrack1D::SIZE)) ? t.last_size() : nan;
+		out[3 * i + 1] = (func_mask & (1u << GenomeTrack1D::EXISTS)) ? t.last_exists() : nan;
+		out[3 * i + 2] = (func_mask & (1u << GenomeTrack1D::LSE)) ? t.last_lse() : nan;
+	}
+	return 0;
+	REF_CATCH
+}
+
 extern "C" int ref_sparse_eval_ext(const char *chrom_file, int chromid, uint32_t func_mask, int64_t n, const int64_t *start, const int64_t *end,
 								   double *out)
 {

@@ -147,13 +147,27 @@ def test_two_rank_reductions_gloo(tmp_path):
 
 
 def test_r_expression_precedence_rewrite():
-    """R: comparison binds tighter than ! & |; the host rewrites before numpy evaluates (misha_b200/api.py)."""
-    from misha_b200.api import _r_logic_to_python
+    """R: comparison binds tighter than ! & |; the host rewrites before evaluating, and evaluates with R's three-valued logic: a NaN
+    operand makes a comparison NA, NA is never TRUE (`!x > c` and `x != c` must not select the row), FALSE & NA is FALSE,
+    TRUE | NA is TRUE (misha_b200/api.py)."""
+    from misha_b200.api import RLogical, _r_logic_to_python, r_eval
     a, b, c = np.array([0.5, 0.1, 0.9, np.nan]), np.array([0.3, 0.3, 0.1, 0.3]), np.array([1.0, 5.0, 2.0, 3.0])
     env = {"a": a, "b": b, "c": c}
-    with np.errstate(invalid="ignore"):
-        assert eval(_r_logic_to_python("a > 0.4 & b > 0.25"), {}, env).tolist() == [True, False, False, False]
-        assert eval(_r_logic_to_python("a > 0.4 | (b < 0.2 & !c >= 3)"), {}, env).tolist() == [True, False, True, False]
-        assert eval(_r_logic_to_python("!a > 0.4"), {}, env).tolist() == [False, True, False, True]
-        assert eval(_r_logic_to_python("a != b && c > 1.5"), {}, env).tolist() == [False, True, True, True]
-        assert np.allclose(eval(_r_logic_to_python("a*2+c"), {}, env)[:3], [2.0, 5.2, 3.8])
+
+    def true_rows(expr):
+        r = r_eval(_r_logic_to_python(expr).replace("is.na(", "is_na("), env)
+        assert isinstance(r, RLogical)
+        return r.true().tolist()
+
+    assert true_rows("a > 0.4 & b > 0.25") == [True, False, False, False]
+    assert true_rows("a > 0.4 | (b < 0.2 & !c >= 3)") == [True, False, True, False]
+    assert true_rows("!a > 0.4") == [False, True, False, False]          # !NA is NA
+    assert true_rows("a != b && c > 1.5") == [False, True, True, False]  # NA & TRUE is NA
+    assert true_rows("a != b | c > 1.5") == [True, True, True, True]     # NA | TRUE is TRUE
+    assert true_rows("!(a > 0.4 & c > 100)") == [True, True, True, True]  # NA & FALSE is FALSE, its negation TRUE
+    assert true_rows("is.na(a) | a > 0.6") == [False, False, True, True]
+    na = r_eval(_r_logic_to_python("a > 0.4"), env)
+    assert np.array_equal(na.as_numeric(), [1.0, 0.0, 1.0, np.nan], equal_nan=True)  # what gextract stores for a logical expression
+    num = r_eval(_r_logic_to_python("a*2+c").replace("^", "**"), env)
+    assert np.allclose(num.v[:3], [2.0, 5.2, 3.8]) and np.isnan(num.v[3])
+    assert np.allclose(r_eval("pmin(a, b) + log2(c)", env).v[:3], [0.3, 0.1 + np.log2(5), 0.1 + 1.0])

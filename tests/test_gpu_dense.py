@@ -357,3 +357,40 @@ def test_order_dependent_functions_synthetic_ties_and_nans():
             assert np.mean((got[6] == exp["lse"]) | np.isnan(got[6])) > 0.999
     finally:
         ctx2.close()
+
+
+def test_reducer_and_generic_path_counts(gpu_ctx):
+    """size / exists / lse as the reference's reducer path and as its generic path report them (MG_FUNC_GENERIC): golden vectors made
+    from the compiled reference with the respective function sets registered (tests/golden/path_vectors.npz), and the restatement
+    under a window shift."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "path_vectors.npz"))
+    bins, bs, size, s, e = g["bins"], int(g["bin_size"]), int(g["chromsize"]), g["start"], g["end"]
+    ctx2 = gpu.Context([size])
+    try:
+        t = gpu.DenseTrack(ctx2, bs)
+        t.stage(0, bins)
+        rows = ctx2.rows_upload(np.zeros(len(s), np.int32), s, e)
+        red = t.window(rows, ["size", "exists", "lse"])
+        gen = t.window(rows, ["size:generic", "exists:generic", "lse:generic", "avg", "max"])
+        for k, name in enumerate(("size", "exists")):
+            assert_same(red[k], g["reducer_" + name], "reducer path " + name)
+            assert_same(gen[k], g["generic_" + name], "generic path " + name)
+        np.testing.assert_allclose(red[2], g["reducer_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
+        np.testing.assert_allclose(gen[2], g["generic_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
+        assert np.sum(red[0] != gen[0]) == np.sum(g["reducer_size"] != g["generic_size"]) > 100
+        # one flagged function next to an unflagged one, under shifts, through every kernel family
+        for ss, es in ((-7, 3), (-300, 300)):
+            exp_g = port.dense_counts(bins, bs, size, s, e, ss, es, generic=True)
+            exp_r = port.dense_counts(bins, bs, size, s, e, ss, es, generic=False)
+            for tk in (0, 1, 3, 4):
+                ctx2.set_option("tile_kernel", tk)
+                got = t.window(rows, ["size:generic", "exists", "avg", ("quantile", 0.5)], ss, es)
+                assert_same(got[0], exp_g["size"], "generic size, shift %d, kernels %d" % (ss, tk))
+                assert_same(got[1], exp_r["exists"], "reducer exists, shift %d, kernels %d" % (ss, tk))
+            ctx2.set_option("tile_kernel", 3)
+        with pytest.raises(gpu.MishaGpuError):
+            t.window(rows, ["avg:generic"])
+    finally:
+        ctx2.close()

@@ -207,3 +207,57 @@ def test_cpp_scanner_sequence_and_order_dependent_vtracks(tmp_path):
         assert_same(cols[5][m], port.pwm(seqs[c], logp, os_[m], oe[m], True, False, "pwm.max.pos", -1), "pwm.max.pos")
         assert_same(cols[6][m], port.kmer(seqs[c], "ac", os_[m], oe[m], "kmer.count", True, 0, -25, 25), "kmer.count")  # vtrack_kmer -> mg_kmer
         assert_same(cols[7][m], port.kmer(seqs[c], "TGA", os_[m], oe[m], "kmer.frac", False, -1), "kmer.frac")
+
+
+@pytest.mark.gpu
+def test_cpp_group_session(tmp_path):
+    """GpuGroupSession (the host layer over mg_group_*): gextract / gsummary / gdist / gquantiles over a group of every device of
+    the box (one on a single-GPU box), against the oracle."""
+    import torch
+    build.build_host()
+    ndev = min(torch.cuda.device_count(), 2)
+    rng = np.random.default_rng(79)
+    sizes = [400000, 150000, 260000]
+    bs = 20
+    bins, files = [], []
+    for c, size in enumerate(sizes):
+        b = np.clip(np.exp(rng.normal(size=-(-size // bs))), 0, 100).astype(np.float32)
+        b[rng.integers(0, len(b), 50)] = np.nan
+        b.tofile(tmp_path / ("dense%d.f32" % c))
+        bins.append(b); files.append(str(tmp_path / ("dense%d.f32" % c)))
+    n = 3000
+    ch = rng.integers(0, 3, n).astype(np.int32)
+    st = (rng.random(n) * (np.array(sizes)[ch] - 500)).astype(np.int64)
+    en = st + rng.integers(1, 400, n)
+    _write_intervals(tmp_path / "scope.bin", ch, st, en)  # unsorted, overlapping
+    spec = tmp_path / "spec.txt"
+    spec.write_text("\n".join([
+        "chroms 3 %d %d %d" % tuple(sizes),
+        "dense d %d %s" % (bs, " ".join(files)),
+        "scope %s" % (tmp_path / "scope.bin"),
+        "group %d d %d %d 0.9 -2000 2000 %s" % (ndev, bs, 5, tmp_path / "grp.bin"),  # quantile(0.9) under +-2 kb
+    ]) + "\n")
+    r = subprocess.run([build.HOST_DEMO, str(spec)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(tmp_path / "grp.bin", np.uint8)
+    m = int(raw[:8].view(np.int64)[0])
+    assert m == n
+    col = raw[8:8 + 8 * m].view(np.float64)
+    rest = raw[8 + 8 * m:]
+    sum7, hist, q = rest[:56].view(np.float64), rest[56:56 + 800].view(np.uint64), rest[856:880].view(np.float64)
+    o = np.lexsort((st, ch))  # rows come back in the scope's sorted order (stable)
+    for c in range(3):
+        mk = ch[o] == c
+        exp = port.dense_window(bins[c], bs, sizes[c], st[o][mk], en[o][mk], -2000, 2000, 0.9, ("quantile",))["quantile"]
+        assert_same(col[mk], exp, "group gextract quantile chrom %d" % c)
+    uc, us, ue = port.unify(ch, st, en)
+    vals = []
+    for c in range(3):
+        mk = uc == c
+        _, s, e, _ = port.fixedbin_rows(bs, uc[mk], us[mk], ue[mk])
+        vals.append(port.dense_window(bins[c], bs, sizes[c], s, e, 0, 0, 0.5, ("avg",))["avg"])
+    vals = np.concatenate(vals)
+    exp_s = port.summary(vals)
+    assert np.array_equal(sum7[:4], exp_s[:4]) and np.allclose(sum7[4:], exp_s[4:], rtol=1e-9)
+    assert np.array_equal(hist, port.hist(vals, [np.arange(101.0)], True))
+    assert_same(q, port.gquantiles(vals, [0.1, 0.5, 0.9])[0], "group gquantiles")

@@ -5,7 +5,9 @@
 import numpy as np
 import pytest
 
-from conftest import CHROMS, TESTDB, assert_same, read_dense, read_seq, read_sparse
+import os
+
+from conftest import CHROMS, GOLDEN, TESTDB, assert_same, read_dense, read_seq, read_sparse
 from oracle import port, ref
 
 DENSE_FUNCS = ("avg", "min", "max", "stddev", "sum", "quantile")
@@ -274,3 +276,17 @@ def test_masked_matches_reference_golden():
             exp = g[f"{c}_{mode}"]
             assert exp.max() > 0
             assert_same(port.masked(seq, s, e, mode), exp, f"{c} {mode}")
+
+
+def test_path_dependent_counts_and_lse_against_the_compiled_reference():
+    """size / exists / lse through the reference's reducer path and through its generic path (tests/golden/path_vectors.npz, made by
+    make_path_fixtures.py from the compiled reference): the restatement reproduces both."""
+    g = np.load(os.path.join(GOLDEN, "path_vectors.npz"))
+    bins, bs, size, s, e = g["bins"], int(g["bin_size"]), int(g["chromsize"]), g["start"], g["end"]
+    for name, generic in (("reducer", False), ("generic", True)):
+        c = port.dense_counts(bins, bs, size, s, e, generic=generic)
+        assert_same(c["size"], g[name + "_size"], name + " size")
+        assert_same(c["exists"], g[name + "_exists"], name + " exists")
+        lse = port.dense_window_ext(bins, bs, size, s, e, lse_mode=int(generic))["lse"]
+        np.testing.assert_allclose(lse, g[name + "_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert np.sum(g["reducer_size"] != g["generic_size"]) > 100, "the fixture holds windows on which the two paths disagree"
