@@ -171,3 +171,20 @@ def test_r_expression_precedence_rewrite():
     num = r_eval(_r_logic_to_python("a*2+c").replace("^", "**"), env)
     assert np.allclose(num.v[:3], [2.0, 5.2, 3.8]) and np.isnan(num.v[3])
     assert np.allclose(r_eval("pmin(a, b) + log2(c)", env).v[:3], [0.3, 0.1 + np.log2(5), 0.1 + 1.0])
+
+
+def test_r_side_glue_compiles_against_the_reference_headers():
+    """misha_b200/host/rglue/GpuSession.cpp -- the .Call-shaped entry points a maintainer adds to misha's src/  -- is
+    type-checked against the reference's OWN headers and the declaration-only R shim: the R side of the boundary is known to build even
+    though no R exists in this image. Needs /root/reference (the build container); skipped on the GPU box."""
+    import shutil
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src) or shutil.which("g++") is None:
+        pytest.skip("reference sources or g++ not present")
+    src = os.path.join(ROOT, "misha_b200", "host", "rglue", "GpuSession.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-include", "cfloat", "-include", "cstring", "-I", os.path.join(ROOT, "oracle", "shim"),
+                        "-I", ref_src, "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    txt = open(src).read()
+    for sym in ("gtracksummary_gpu", "gtrackdist_gpu", "gquantiles_gpu", "gextract_gpu", "mg_group_dense_summary", "mg_group_h_dense_window"):
+        assert sym in txt
