@@ -15,7 +15,7 @@ import re
 
 import numpy as np
 
-from . import gpu
+from . import formats, gpu
 
 FUSED_FUNCS = ("avg", "sum", "min", "max", "stddev", "quantile", "nearest", "size", "exists")
 # "<f>.pos.abs" / "<f>.pos.relative" (R/vtrack.R; src/TrackVarProcessor.cpp:113-173): one device function, param = relative
@@ -246,6 +246,7 @@ class MishaDB:
         self.ctx = gpu.Context(self.chrom_sizes, device)
         self.vtracks = {}
         self._dense, self._sparse, self._ivsets, self._seq = {}, {}, {}, None
+        self._track_idx = {}
 
     def close(self):
         self.ctx.close()
@@ -301,44 +302,51 @@ class MishaDB:
                     out.append(os.path.relpath(os.path.join(dp, d), root)[:-6].replace(os.sep, "."))
         return sorted(out)
 
+    def _track_index(self, track):
+        """The track's single-file index (track.idx, src/TrackIndex.h) or None for the per-chromosome layout; cached per track."""
+        if track not in self._track_idx:
+            try:
+                self._track_idx[track] = formats.read_track_index(self._track_dir(track))
+            except formats.FormatError as e:
+                raise MishaError(str(e))
+        return self._track_idx[track]
+
     def _track_type(self, track):
         d = self._track_dir(track)
-        for c in self.chrom_names:
-            f = os.path.join(d, c)
-            if os.path.exists(f) and os.path.getsize(f) >= 4:
-                sig = int(np.fromfile(f, dtype=np.int32, count=1)[0])  # src/GenomeTrack.cpp:227-250
-                if sig >= 1:
-                    return "dense"
-                if sig == -1:
-                    return "sparse"
-                raise MishaError("Track %s: unsupported track type (signature %d)" % (track, sig))
-        raise MishaError("Track %s does not exist" % track)
+        if not os.path.isdir(d):
+            raise MishaError("Track %s does not exist" % track)
+        try:
+            t = formats.track_type(d, self.chrom_names)
+        except formats.FormatError as e:
+            raise MishaError("Track %s: %s" % (track, e))
+        if t is None:
+            raise MishaError("Track %s does not exist" % track)
+        return t
 
     def _dense_track(self, track):
         if track not in self._dense:
             d = self._track_dir(track)
+            idx = self._track_index(track)
             t = None
             for cid, c in enumerate(self.chrom_names):
-                f = os.path.join(d, c)
-                if not os.path.exists(f):
-                    raise MishaError("Track %s: missing chromosome file %s" % (track, c))
-                raw = np.fromfile(f, dtype=np.uint8)
-                bin_size = int(raw[:4].view(np.uint32)[0])
+                got = formats.read_dense_chrom(d, c, cid, idx)
+                if got is None:
+                    if idx is None:
+                        raise MishaError("Track %s: missing chromosome file %s" % (track, c))
+                    continue  # an indexed track may hold empty contigs (src/GenomeTrackFixedBin.cpp:1178-1199): their rows are NaN
+                bin_size, bins = got
                 if t is None:
                     t = gpu.DenseTrack(self.ctx, bin_size)
                 elif t.bin_size != bin_size:
                     raise MishaError("Track %s: inconsistent bin size" % track)
-                t.stage(cid, raw[4:].view(np.float32))
+                t.stage(cid, bins)
+            if t is None:
+                raise MishaError("Track %s holds no data" % track)
             self._dense[track] = t
         return self._dense[track]
 
     def _sparse_records(self, track, cid):
-        f = os.path.join(self._track_dir(track), self.chrom_names[cid])
-        if not os.path.exists(f):
-            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32)
-        raw = np.fromfile(f, dtype=np.uint8)
-        rec = raw[4:].view(np.dtype([("s", "<i8"), ("e", "<i8"), ("v", "<f4")]))
-        return rec["s"].copy(), rec["e"].copy(), rec["v"].copy()
+        return formats.read_sparse_chrom(self._track_dir(track), self.chrom_names[cid], cid, self._track_index(track))
 
     def _sparse_track(self, track):
         if track not in self._sparse:
@@ -351,8 +359,13 @@ class MishaDB:
     def _sequence(self):
         if self._seq is None:
             s = gpu.Sequence(self.ctx)
-            for cid, c in enumerate(self.chrom_names):
-                s.stage(cid, np.fromfile(os.path.join(self.groot, "seq", c + ".seq"), dtype=np.uint8))
+            seq_dir = os.path.join(self.groot, "seq")
+            try:
+                gidx = formats.read_genome_index(seq_dir)  # genome.idx + genome.seq (src/GenomeSeqFetch.cpp:66-107) or <chrom>.seq files
+                for cid, c in enumerate(self.chrom_names):
+                    s.stage(cid, formats.read_seq_chrom(seq_dir, c, cid, gidx))
+            except formats.FormatError as e:
+                raise MishaError(str(e))
             self._seq = s
         return self._seq
 

@@ -319,3 +319,37 @@ def test_kmer_vtrack(db):
         db.gvtrack_create("km", None, "kmer.count", dict(kmer=""))
     with pytest.raises(api.MishaError, match="unknown"):
         db.gvtrack_create("km", None, "kmer.count", dict(kmer="ACG", bidirect=True))
+
+
+def test_indexed_database_layout(db, tmp_path):
+    """The bundled DB converted to the single-file layouts (track.idx + track.dat per track, seq/genome.idx + genome.seq; written by
+    misha_b200/formats.py, which the CPU suite checks against the reference's own readers): every entry point returns what it returns
+    on the per-chromosome layout."""
+    import os
+    import shutil
+    from misha_b200 import formats
+    root = str(tmp_path / "indexed")
+    os.makedirs(root)
+    shutil.copy(os.path.join(TESTDB, "chrom_sizes.txt"), root)
+    names = [c for c, _ in CHROMS]
+    for track, kind in (("dense_track", "dense"), ("sparse_track", "sparse")):
+        src = os.path.join(TESTDB, "tracks", track + ".track")
+        blobs = {cid: open(os.path.join(src, c), "rb").read() for cid, c in enumerate(names)}
+        formats.write_indexed_track(os.path.join(root, "tracks", track + ".track"), kind, blobs)
+    formats.write_indexed_genome(os.path.join(root, "seq"), [(cid, c, read_seq(c)) for cid, c in enumerate(names)])
+    d2 = api.gdb_init(root)
+    try:
+        assert d2._track_type("dense_track") == "dense" and d2._track_type("sparse_track") == "sparse"
+        iv = db.gintervals_all()
+        for d in (db, d2):
+            d.gvtrack_create("q", "dense_track", "quantile", 0.5)
+            d.gvtrack_iterator("q", sshift=-300, eshift=300)
+            d.gvtrack_create("near", "sparse_track", "nearest")
+            d.gvtrack_create("k", None, "kmer.count", {"kmer": "ACG", "strand": 0})
+        a = db.gextract("dense_track", "q", "near", "k", intervals=iv, iterator=500)
+        b = d2.gextract("dense_track", "q", "near", "k", intervals=d2.gintervals_all(), iterator=500)
+        for col in ("start", "end", "dense_track", "q", "near", "k", "intervalID"):
+            assert_same(np.asarray(b[col], dtype=np.float64), np.asarray(a[col], dtype=np.float64), "indexed layout: " + col)
+        assert np.array_equal(d2.gsummary("dense_track"), db.gsummary("dense_track"), equal_nan=True)
+    finally:
+        d2.close()

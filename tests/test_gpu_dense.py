@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import CHROMS, assert_close, assert_same, read_dense
+from misha_b200 import gpu
 from oracle import port
 
 pytestmark = pytest.mark.gpu
