@@ -189,6 +189,14 @@ int mg_coverage(mg_ctx *ctx, const mg_ivset *s, const mg_rows *rows, int64_t fir
 /* h_logp: L x 4 float log-probabilities (A,C,G,T) after normalisation and prior (mg_pssm_logp). strand: 1 / -1. */
 int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
 		   const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream);
+/* The same under spatial weights (gvtrack.create(..., "pwm*", list(spat_factor = , spat_bin = )); PWMParams, src/TrackExpressionParams.h,  */
+/* PWMScorer's spat_factor / spat_bin, src/PWMScorer.cpp:112-165): factor k weighs the anchors whose index in the scored target lies in    */
+/* [k spat_bin, (k + 1) spat_bin), the last factor everything beyond; log(max(1e-30f, factor)) is added to each strand's log-likelihood   */
+/* (pwm, pwm.max) or to the strands' union before the threshold (pwm.count, which -- like the reference's scorer -- does not count anchors */
+/* past the last bin). Fresh-window semantics. MG_PWM_MAX_POS is refused with weights. nspat = 0: mg_pwm.                                 */
+int mg_pwm_spatial(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand, float score_thresh,
+				   const float *h_spat_factor, int nspat, int spat_bin, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift,
+				   int64_t eshift, double *d_out, void *stream);
 /* kmer.count / kmer.frac vtracks (KmerCounter::score_interval, src/KmerCounter.cpp:38-176; SequenceVarProcessor calls it per  */
 /* row like score_interval of the PWM scorer): occurrences of `kmer` (case folded; A, C, G, T only, at most 32 bases) starting   */
 /* inside the window, on the forward strand (strand 1), as its reverse complement (strand -1) or both (strand 0); `extend`       */

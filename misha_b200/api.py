@@ -204,6 +204,10 @@ def r_eval(py, variables):
     return eval(py, {"__builtins__": {}}, {**R_FUNCS, **env})  # noqa: S307 - the expression language of the host
 
 
+def rows_is_fixedbin(rows):
+    return getattr(rows, "binsize", None) is not None
+
+
 class Intervals(dict):
     """A 1-D intervals set: columns chrom (names), start, end (+ anything else). Mirrors the R data frame."""
 
@@ -583,6 +587,57 @@ class MishaDB:
         return out
 
     # ---- entry points -------------------------------------------------------------------------------------
+    def gtrack_create(self, track, expr, iterator=None, indexed=None):
+        """gtrack.create(track, description, expr, iterator) -- src/GenomeTrackCreate.cpp:35-215: the expression evaluated over the
+        whole genome; a fixed-bin iterator yields a dense track (uint32 bin size + one float32 per bin and chromosome, every
+        chromosome written), an intervals iterator a sparse one (every iterator interval with its value, chromosomes without rows get
+        a header-only file). The value is the expression's double narrowed to float, as write_next_bin / pack_record store it.
+        indexed: write track.idx + track.dat (the reference does when the database is indexed; default: as the sequence is stored)."""
+        if not re.match(r"^[A-Za-z][A-Za-z0-9_.]*$", track):
+            raise MishaError("Invalid track name %s" % track)
+        d = self._track_dir(track)
+        if os.path.exists(d):
+            raise MishaError("Track %s already exists" % track)
+        scope = self.gintervals_all()
+        rows, _ = self._rows([expr], scope, iterator, unify_scope=False)
+        vals = np.asarray(self._eval(expr, rows, {}), dtype=np.float64).astype(np.float32)
+        c, s, e, _ = rows.coords()
+        kind = "dense" if isinstance(iterator, (int, np.integer)) or (iterator is None and rows_is_fixedbin(rows)) else "sparse"
+        blobs = {}
+        for cid in range(len(self.chrom_names)):
+            m = c == cid
+            if kind == "dense":
+                bin_size = int(iterator) if iterator is not None else int(rows.binsize)
+                if not m.any():
+                    continue
+                blobs[cid] = formats.dense_blob(vals[m], bin_size)
+            else:
+                blobs[cid] = formats.sparse_blob(s[m], e[m], vals[m])
+        if indexed is None:
+            indexed = os.path.exists(os.path.join(self.groot, "seq", "genome.idx"))
+        if indexed:
+            formats.write_indexed_track(d, kind, {cid: blobs.get(cid, b"") for cid in range(len(self.chrom_names))})
+        else:
+            os.makedirs(d)
+            for cid, b in blobs.items():
+                with open(os.path.join(d, self.chrom_names[cid]), "wb") as f:
+                    f.write(b)
+        self._track_idx.pop(track, None)
+        return track
+
+    def gtrack_rm(self, track):
+        """gtrack.rm: the track's directory and whatever of it is staged."""
+        import shutil
+        d = self._track_dir(track)
+        if not os.path.isdir(d):
+            raise MishaError("Track %s does not exist" % track)
+        for cache in (self._dense, self._sparse):
+            t = cache.pop(track, None)
+            if t is not None:
+                t.free()
+        self._track_idx.pop(track, None)
+        shutil.rmtree(d)
+
     def gextract(self, *exprs, intervals=None, iterator=None, colnames=None):
         """R/compute-core.R:77. Returns a dict of columns: chrom, start, end, one per expression, intervalID."""
         if not exprs:

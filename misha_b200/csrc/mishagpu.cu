@@ -1940,10 +1940,24 @@ extern "C" int mg_masked(mg_ctx *ctx, const mg_seq *s, int mode, const mg_rows *
 	return 0;
 }
 
+extern "C" int mg_pwm_spatial(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand,
+							  float score_thresh, const float *h_spat_factor, int nspat, int spat_bin, const mg_rows *rows, int64_t first,
+							  int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream);
 extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand,
 					  float score_thresh, const mg_rows *rows, int64_t first, int64_t count, int64_t sshift, int64_t eshift, double *d_out,
 					  void *stream)
 {
+	return mg_pwm_spatial(ctx, s, h_logp, L, bidirect, extend, mode, strand, score_thresh, nullptr, 0, 1, rows, first, count, sshift, eshift, d_out,
+						  stream);
+}
+
+extern "C" int mg_pwm_spatial(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, int bidirect, int extend, int mode, int strand,
+							  float score_thresh, const float *h_spat_factor, int nspat, int spat_bin, const mg_rows *rows, int64_t first,
+							  int64_t count, int64_t sshift, int64_t eshift, double *d_out, void *stream)
+{
+	MG_REQUIRE(ctx, nspat >= 0 && nspat <= MG_PWM_MAXSPAT && (nspat == 0 || h_spat_factor), "spatial weights: 0..%d factors", MG_PWM_MAXSPAT);
+	MG_REQUIRE(ctx, nspat == 0 || mode != MG_PWM_MAX_POS, "pwm.max.pos under spatial weights is not offered (the reference's fresh and sliding "
+			   "evaluations disagree on it)");
 	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
 	MG_REQUIRE(ctx, L >= 1 && L <= MG_PWM_MAXL, "PSSM length %d not in [1, %d]", L, MG_PWM_MAXL);
 	MG_REQUIRE(ctx, mode == MG_PWM_TOTAL || mode == MG_PWM_MAX || mode == MG_PWM_COUNT || mode == MG_PWM_MAX_POS, "unsupported pwm mode %d", mode);
@@ -1984,6 +1998,19 @@ extern "C" int mg_pwm(mg_ctx *ctx, const mg_seq *s, const float *h_logp, int L, 
 	q.strand = strand;
 	q.thresh = score_thresh;
 	q.out = d_out;
+	q.spat_log = nullptr;
+	q.nspat = nspat;
+	q.spat_bin = spat_bin < 1 ? 1 : spat_bin; // std::max(1, spat_bin_size), src/PWMScorer.cpp:118
+	if (nspat) {
+		std::vector<float> sl((size_t)nspat);
+		for (int k = 0; k < nspat; ++k) // src/PWMScorer.cpp:121-124, in float on the host like the reference
+			sl[k] = std::log(std::max(1e-30f, h_spat_factor[k]));
+		float *d_sl = nullptr;
+		MG_CUDA(ctx, mg_scratch.alloc(&d_sl, sizeof(float) * (size_t)nspat));
+		MG_CUDA(ctx, cudaMemcpyAsync(d_sl, sl.data(), sizeof(float) * (size_t)nspat, cudaMemcpyHostToDevice, st));
+		MG_CUDA(ctx, cudaStreamSynchronize(st));
+		q.spat_log = d_sl;
+	}
 	const int64_t blocks_needed = mg_div_up(count, MG_PWM_WARPS);
 	const int64_t cap = (int64_t)ctx->sm_count * 16;
 	const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);

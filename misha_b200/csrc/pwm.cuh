@@ -84,7 +84,12 @@ struct PwmQuery {
 	int bidirect, extend, mode, strand;
 	float thresh;
 	double *out;
+	// spatial weights (PWMParams spat_factor / spat_bin, src/PWMScorer.cpp:112-165): log(max(1e-30f, factor)) per bin of spat_bin TARGET
+	// positions, the last bin extended over whatever follows; nspat = 0: none
+	const float *spat_log;
+	int nspat, spat_bin;
 };
+#define MG_PWM_MAXSPAT 2048
 
 // src/util.h:16-28. STRICT: expf / logf taken as the correctly rounded values (double evaluation rounded to float; glibc's
 // are correctly rounded in all but rare cases) -- two double-precision transcendentals per anchor, which is what bounds the
@@ -130,12 +135,16 @@ template <bool BID, int MODE, bool STRICT>
 __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(const PwmQuery q)
 {
 	__shared__ float2 stab[MG_PWM_MAXL * 5];
+	__shared__ float sspat[MODE == MG_PWM_MAX_POS ? 1 : MG_PWM_MAXSPAT];
 	__shared__ __align__(16) uint8_t stile[MG_PWM_WARPS][MG_PWM_TILE + 16];
 	__shared__ uint32_t spk[MG_PWM_WARPS][3 * ((MG_PWM_TILE + 16 + 31) / 32 + 2)]; // {inval, codes lo, codes hi} per 32 bases
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int L = q.L, Lpad = (L + 3) & ~3; // motif rows padded to a multiple of 4 with zeros: adding 0.f changes nothing
 	for (int t = threadIdx.x; t < Lpad * 5; t += blockDim.x)
 		stab[t] = t < L * 5 ? q.tab[t] : make_float2(0.f, 0.f);
+	if (MODE != MG_PWM_MAX_POS)
+		for (int t = threadIdx.x; t < q.nspat; t += blockDim.x)
+			sspat[t] = q.spat_log[t];
 	__syncthreads();
 	const uint32_t stab_s = (uint32_t)__cvta_generic_to_shared(stab);
 	uint8_t *tile = stile[warp];
@@ -273,7 +282,21 @@ __global__ void __launch_bounds__(MG_PWM_WARPS * 32, MG_PWM_MINBLOCKS) k_pwm(con
 						}
 						continue;
 					}
-					if (BID)
+					if (MODE != MG_PWM_MAX_POS && q.nspat) {
+						// the anchor's spatial bin by its TARGET index (integrate_energy_logspat / _max_logspat, src/DnaPSSM.cpp:933-1075:
+						// each strand weighted, then united; count_motif_hits_with_spatial, src/PWMScorer.cpp:219-249: united, then weighted)
+						const int ti = rev ? (int)(na - 1 - a) : (int)a, b = ti / q.spat_bin;
+						const float sl = sspat[b < q.nspat ? b : q.nspat - 1];
+						if (BID) {
+							v = MODE == MG_PWM_COUNT ? __fadd_rn(mg_log_sum_log<STRICT>(f[u], r[u]), sl)
+													 : mg_log_sum_log<STRICT>(__fadd_rn(f[u], sl), __fadd_rn(r[u], sl));
+						} else
+							v = __fadd_rn(rev ? r[u] : f[u], sl);
+						// pwm.count: the reference's scorer answers from spat_seed, whose hit counts stop at the end of the last spatial bin
+						// (src/PWMScorer.cpp:1098-1111) although pwm / pwm.max extend that bin over the rest (:934-937)
+						if (MODE == MG_PWM_COUNT && b >= q.nspat)
+							v = NEG_INF;
+					} else if (BID)
 						v = mg_log_sum_log<STRICT>(f[u], r[u]);
 					else
 						v = rev ? r[u] : f[u];

@@ -207,7 +207,7 @@ def write_indexed_genome(seq_dir, contigs):
     off, body, chunks = 0, [], []
     with open(os.path.join(seq_dir, "genome.seq"), "wb") as f:
         for chromid, name, bases in contigs:
-            b = np.ascontiguousarray(bases, dtype=np.uint8)
+            b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.ascontiguousarray(bases, dtype=np.uint8)
             f.write(b.tobytes())
             nm = name.encode()
             body.append(struct.pack("<IH", chromid, len(nm)) + nm + struct.pack("<QQQ", off, len(b), 0))

@@ -140,7 +140,9 @@ class Context:
         schrom, sstart, send = _arr(schrom, np.int32), _arr(sstart, np.int64), _arr(send, np.int64)
         h = c_vp()
         self._check(self.lib.mg_rows_fixedbin(self.h, c_i64(binsize), c_i64(len(schrom)), _p(schrom), _p(sstart), _p(send), ctypes.byref(h)))
-        return Rows(self, h)
+        r = Rows(self, h)
+        r.binsize = int(binsize)  # the fixed-bin iterator's bin (None for explicit rows)
+        return r
 
     def rows_intervals(self, ichrom, istart, iend, schrom, sstart, send, stream=None):
         a = [_arr(ichrom, np.int32), _arr(istart, np.int64), _arr(iend, np.int64), _arr(schrom, np.int32), _arr(sstart, np.int64),
@@ -155,6 +157,7 @@ class Rows:
     def __init__(self, ctx, h):
         self.ctx, self.h = ctx, h
         self.n = int(ctx.lib.mg_rows_count(h))
+        self.binsize = None
 
     def coords(self, first=0, count=None, stream=None):
         """(chrom int32, start int64, end int64, scope_idx int64) of rows [first, first+count) on the host."""
@@ -353,14 +356,16 @@ class Sequence:
         self.ctx._check(self.ctx.lib.mg_seq_stage(self.ctx.h, self.h, c_int(chromid), _p(a), c_i64(len(a))))
 
     def pwm_dev(self, rows, logp, bidirect=True, extend=True, mode="pwm", strand=1, score_thresh=0.0, sshift=0, eshift=0, first=0,
-                count=None, out=None, stream=None):
+                count=None, out=None, stream=None, spat_factor=None, spat_bin=1):
+        """spat_factor / spat_bin: spatial weights (mg_pwm_spatial); None: mg_pwm."""
         count = rows.n - first if count is None else count
         lp = _arr(logp, np.float32)
         out = out or self.ctx.alloc(count, np.float64)
         c = self.ctx
-        c._check(c.lib.mg_pwm(c.h, self.h, _p(lp), c_int(lp.shape[0]), c_int(int(bidirect)), c_int(int(extend)), c_int(PWM_MODES[mode]),
-                              c_int(strand), ctypes.c_float(score_thresh), rows.h, c_i64(first), c_i64(count), c_i64(sshift),
-                              c_i64(eshift), c_vp(out.ptr), c_vp(stream)))
+        sp = _arr(spat_factor, np.float32) if spat_factor is not None else np.zeros(0, np.float32)
+        c._check(c.lib.mg_pwm_spatial(c.h, self.h, _p(lp), c_int(lp.shape[0]), c_int(int(bidirect)), c_int(int(extend)), c_int(PWM_MODES[mode]),
+                                      c_int(strand), ctypes.c_float(score_thresh), _p(sp) if len(sp) else None, c_int(len(sp)), c_int(int(spat_bin)),
+                                      rows.h, c_i64(first), c_i64(count), c_i64(sshift), c_i64(eshift), c_vp(out.ptr), c_vp(stream)))
         return out
 
     def pwm(self, rows, logp, **kw):

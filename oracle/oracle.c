@@ -791,9 +791,31 @@ static float orc_match_rc(const float *logp, int L, const char *s, int rev_order
 /* mode: 0 = pwm (log-sum-exp over anchors, src/utils/RunningLogSumExp.h:32-45,175-178), 1 = pwm.max,         */
 /* 2 = pwm.max.pos, 3 = pwm.count (src/PWMScorer.cpp:660-690). strand: 1 / -1 (used when !bidirect and for the add order).     */
 /* score_interval: src/PWMScorer.cpp:742-861; expansion src/GenomeSeqScorer.cpp:16-38.                        */
+/* Spatial weights (PWMParams spat_factor / spat_bin, src/PWMScorer.cpp:112-165, src/DnaPSSM.cpp:933-1075): the anchor at TARGET   */
+/* index t (the reverse complement's index for strand -1) gets log(max(1e-30f, spat[min(t / spat_bin, nspat - 1)])) added to each  */
+/* strand's log-likelihood before the strands are united (pwm, pwm.max: integrate_energy_logspat / integrate_energy_max_logspat)   */
+/* or to the united value before the threshold (pwm.count: count_motif_hits_with_spatial, :219-249). nspat = 0: no weights.        */
+/* pwm.max.pos under spatial weights is not restated (the reference's fresh-window and sliding versions disagree on strand -1).    */
+void orc_pwm_spat(const char *seq, int64_t chromsize, const float *logp, int L, int bidirect, int extend, int mode, int strand,
+				  float score_thresh, const float *spat, int nspat, int spat_bin, int64_t n, const int64_t *start, const int64_t *end,
+				  int64_t sshift, int64_t eshift, double *out);
 void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int bidirect, int extend, int mode, int strand,
 			 float score_thresh, int64_t n, const int64_t *start, const int64_t *end, int64_t sshift, int64_t eshift, double *out)
 {
+	orc_pwm_spat(seq, chromsize, logp, L, bidirect, extend, mode, strand, score_thresh, NULL, 0, 1, n, start, end, sshift, eshift, out);
+}
+void orc_pwm_spat(const char *seq, int64_t chromsize, const float *logp, int L, int bidirect, int extend, int mode, int strand,
+				  float score_thresh, const float *spat, int nspat, int spat_bin, int64_t n, const int64_t *start, const int64_t *end,
+				  int64_t sshift, int64_t eshift, double *out)
+{
+	float *slog = NULL;
+	if (nspat > 0) {
+		slog = (float *)malloc((size_t)nspat * sizeof(float));
+		for (int k = 0; k < nspat; ++k)
+			slog[k] = logf(spat[k] > 1e-30f ? spat[k] : 1e-30f);
+		if (spat_bin < 1)
+			spat_bin = 1;
+	}
 	float *vals = NULL;
 	int64_t cap = 0;
 	for (int64_t i = 0; i < n; ++i) {
@@ -826,6 +848,8 @@ void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int b
 		/* strand -1 scores the reverse complement of [ws, xe): target index t <-> genomic anchor (tlen - L) - t, */
 		/* so the first na target anchors are the last na genomic ones */
 		int64_t a_base = strand == -1 ? (tlen - L + 1) - na : 0;
+		if (mode == 2 && nspat > 0)
+			continue; /* not restated: NaN */
 		if (mode == 2) {
 			/* pwm.max.pos: src/PWMScorer.cpp:325-337 -> max_like_match(combine_strands = false) over the target, */
 			/* then compute_position_result (:168-182), all in float */
@@ -867,15 +891,31 @@ void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int b
 		int rev = strand == -1;
 		for (int64_t a = 0; a < na; ++a) {
 			const char *s = seq + ws + a_base + a;
-			float v;
+			float v, sl = 0.f;
+			if (nspat > 0) { /* target index of this anchor, its spatial bin */
+				int64_t t = rev ? na - 1 - a : a, b = t / spat_bin;
+				sl = slog[b < nspat ? b : nspat - 1];
+			}
 			if (bidirect) {
 				float f = orc_like_fwd(logp, L, s, rev), r = orc_like_rc(logp, L, s, rev);
+				if (nspat > 0 && mode != 3) { /* each strand weighted, then united */
+					f += sl;
+					r += sl;
+				}
 				v = f;
 				orc_log_sum_log(&v, r);
-			} else if (strand == -1)
-				v = orc_like_rc(logp, L, s, rev);
-			else
-				v = orc_like_fwd(logp, L, s, 0);
+				if (nspat > 0 && mode == 3) /* pwm.count: the union, then the weight */
+					v += sl;
+			} else {
+				v = strand == -1 ? orc_like_rc(logp, L, s, rev) : orc_like_fwd(logp, L, s, 0);
+				if (nspat > 0)
+					v += sl;
+			}
+			/* pwm.count under spatial weights: every scorer answers its first interval from spat_seed, whose per-bin hit counts stop at  */
+			/* the end of the LAST spatial bin (j_end = min(W, (b + 1) B) for b < bins, src/PWMScorer.cpp:1098-1111) -- anchors past    */
+			/* nspat * spat_bin are not counted, although pwm / pwm.max extend the last bin over them (bin_total_recompute, :934-937)   */
+			if (nspat > 0 && mode == 3 && (rev ? na - 1 - a : a) >= (int64_t)nspat * spat_bin)
+				v = -INFINITY;
 			vals[a] = v;
 		}
 		if (mode == 0) {
@@ -910,6 +950,7 @@ void orc_pwm(const char *seq, int64_t chromsize, const float *logp, int L, int b
 		}
 	}
 	free(vals);
+	free(slog);
 }
 
 /* ------------------------------------------------------------------------------------------------------ */

@@ -247,6 +247,19 @@ def pwm(seq, logp, start, end, bidirect=True, extend=True, mode="pwm", strand=1,
     return out
 
 
+def pwm_spat(seq, logp, start, end, spat, spat_bin, bidirect=True, extend=True, mode="pwm", strand=1, score_thresh=0.0, sshift=0, eshift=0):
+    """pwm / pwm.max / pwm.count under spatial weights (spat = factors per bin of spat_bin target positions). float64[n]."""
+    s = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+    lp = np.ascontiguousarray(logp, dtype=np.float32)
+    sp = np.ascontiguousarray(spat, dtype=np.float32)
+    start, end = _i64(start), _i64(end)
+    out = np.empty(len(start), dtype=np.float64)
+    lib().orc_pwm_spat(_p(s), c_i64(len(s)), _p(lp), ctypes.c_int(lp.shape[0]), ctypes.c_int(int(bidirect)), ctypes.c_int(int(extend)),
+                       ctypes.c_int(PWM_MODES[mode]), ctypes.c_int(strand), ctypes.c_float(score_thresh), _p(sp), ctypes.c_int(len(sp)),
+                       ctypes.c_int(int(spat_bin)), c_i64(len(start)), _p(start), _p(end), c_i64(sshift), c_i64(eshift), _p(out))
+    return out
+
+
 def kmer(seq, kmer, start, end, mode="kmer.count", extend=True, strand=0, sshift=0, eshift=0):
     """kmer.count / kmer.frac of one chromosome's bytes per interval (KmerCounter restatement). Returns float64[n]."""
     s = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)

@@ -166,6 +166,23 @@ def pwm_eval(groot, chrom_names, chrom_sizes, pssm, chromid, start, end, bidirec
     return out.astype(np.float64)
 
 
+def pwm_eval_spat(groot, chrom_names, chrom_sizes, pssm, chromid, start, end, spat, spat_bin, bidirect=True, prior=0.01, extend=True, mode="pwm",
+                  strand=1, score_thresh=0.0, fresh=True):
+    """PWMScorer::score_interval with spatial weights; fresh: a new scorer per interval (no sliding-window history)."""
+    p = np.ascontiguousarray(pssm, dtype=np.float64)
+    sizes = np.ascontiguousarray(chrom_sizes, dtype=np.int64)
+    chromid = np.ascontiguousarray(chromid, dtype=np.int32)
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    sp = np.ascontiguousarray(spat, dtype=np.float32)
+    out = np.empty(len(start), dtype=np.float32)
+    _check(lib().ref_pwm_eval_spat(groot.encode(), ctypes.c_int(len(chrom_names)), _names(chrom_names), _p(sizes), _p(p), ctypes.c_int(p.shape[0]),
+                                   ctypes.c_int(int(bidirect)), ctypes.c_double(prior), ctypes.c_int(int(extend)), ctypes.c_int(PWM_MODES[mode]),
+                                   ctypes.c_int(strand), ctypes.c_float(score_thresh), _p(sp), ctypes.c_int(len(sp)), ctypes.c_int(int(spat_bin)),
+                                   ctypes.c_int(int(fresh)), c_i64(len(start)), _p(chromid), _p(start), _p(end), _p(out)))
+    return out.astype(np.float64)
+
+
 def kmer_eval(groot, chrom_names, chrom_sizes, kmer, chromid, start, end, mode="kmer.count", extend=True, strand=0):
     """KmerCounter::score_interval (src/KmerCounter.cpp:38-101) per interval."""
     sizes = np.ascontiguousarray(chrom_sizes, dtype=np.int64)

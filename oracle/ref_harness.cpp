@@ -16,6 +16,7 @@
 //   TrackExpressionFixedBinIterator           src/TrackExpressionFixedBinIterator.cpp:29-62
 //   TrackExpressionIntervals1DIterator        src/TrackExpressionIntervals1DIterator.cpp:21-85
 //   GIntervals::sort / unify_overlaps         src/GIntervals.cpp:59-74
+#include <memory>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -260,6 +261,36 @@ extern "C" int ref_pwm_eval(const char *groot, int nchroms, const char *const *n
 	for (int64_t i = 0; i < n; ++i) {
 		GInterval iv(chromid[i], start[i], end[i], 0);
 		out[i] = scorer.score_interval(iv, ck);
+	}
+	return 0;
+	REF_CATCH
+}
+
+// The same with spatial weights (PWMParams spat_factor / spat_bin). fresh != 0: a new PWMScorer per interval, i.e. no sliding-window
+// state carried from one interval to the next.
+extern "C" int ref_pwm_eval_spat(const char *groot, int nchroms, const char *const *names, const int64_t *sizes, const double *pssm, int L,
+								 int bidirect, double prior, int extend, int mode, int strand, float score_thresh, const float *spat, int nspat,
+								 int spat_bin, int fresh, int64_t n, const int32_t *chromid, const int64_t *start, const int64_t *end, float *out)
+{
+	REF_TRY
+	GenomeChromKey ck;
+	make_chromkey(ck, nchroms, names, sizes);
+	DnaPSSM p;
+	p.resize(L);
+	for (int i = 0; i < L; ++i) {
+		float pa = pssm[i * 4 + 0], pc = pssm[i * 4 + 1], pg = pssm[i * 4 + 2], pt = pssm[i * 4 + 3];
+		p[i] = DnaProbVec(pa, pc, pg, pt);
+	}
+	p.set_bidirect(bidirect != 0);
+	if (prior > 0)
+		p.add_dirichlet_prior((float)prior);
+	std::vector<float> sp(spat, spat + nspat);
+	std::unique_ptr<PWMScorer> scorer;
+	for (int64_t i = 0; i < n; ++i) {
+		if (!scorer || fresh)
+			scorer.reset(new PWMScorer(p, std::string(groot), extend != 0, (PWMScorer::ScoringMode)mode, (char)strand, sp, spat_bin, score_thresh));
+		GInterval iv(chromid[i], start[i], end[i], 0);
+		out[i] = scorer->score_interval(iv, ck);
 	}
 	return 0;
 	REF_CATCH

@@ -350,6 +350,44 @@ def test_indexed_database_layout(db, tmp_path):
         b = d2.gextract("dense_track", "q", "near", "k", intervals=d2.gintervals_all(), iterator=500)
         for col in ("start", "end", "dense_track", "q", "near", "k", "intervalID"):
             assert_same(np.asarray(b[col], dtype=np.float64), np.asarray(a[col], dtype=np.float64), "indexed layout: " + col)
-        assert np.array_equal(d2.gsummary("dense_track"), db.gsummary("dense_track"), equal_nan=True)
+        sa, sb = db.gsummary("dense_track"), d2.gsummary("dense_track")
+        assert list(sa) == list(sb) and np.array_equal(list(sa.values()), list(sb.values()), equal_nan=True)
     finally:
         d2.close()
+
+
+def test_gtrack_create_from_an_expression(db, tmp_path):
+    """gtrack.create (src/GenomeTrackCreate.cpp:35-215): a dense track from an expression over a fixed-bin iterator, a sparse one over
+    an intervals iterator, per-chromosome and indexed; what is written reads back as the expression's float values."""
+    import os
+    import shutil
+    root = str(tmp_path / "db")
+    shutil.copytree(TESTDB, root)
+    d = api.gdb_init(root)
+    try:
+        d.gvtrack_create("mx", "dense_track", "max")
+        d.gvtrack_iterator("mx", sshift=-100, eshift=100)
+        src = d.gextract("mx * 2 + 1", intervals=d.gintervals_all(), iterator=100)
+        for name, indexed in (("created.pc", False), ("created.ix", True)):
+            d.gtrack_create(name, "mx * 2 + 1", iterator=100, indexed=indexed)
+            assert d.gtrack_exists(name) and d._track_type(name) == "dense"
+            files = sorted(os.listdir(d._track_dir(name)))
+            assert files == (["track.dat", "track.idx"] if indexed else ["chr1", "chr2", "chrX"])
+            back = d.gextract(name, intervals=d.gintervals_all())  # implicit iterator = the new track's bin size
+            assert np.array_equal(back["start"], src["start"])
+            assert_same(back[name], src["mx * 2 + 1"].astype(np.float32).astype(np.float64), "dense track created from an expression (%s)" % name)
+        with pytest.raises(api.MishaError, match="already exists"):
+            d.gtrack_create("created.pc", "dense_track", iterator=100)
+        d.gtrack_rm("created.pc")
+        assert not d.gtrack_exists("created.pc")
+        # sparse: one record per iterator interval
+        iv = d.gintervals([1, 1, 2], [100, 5000, 777], [900, 5200, 1500])
+        d.gtrack_create("created.sp", "dense_track", iterator=iv)
+        assert d._track_type("created.sp") == "sparse"
+        want = d.gextract("dense_track", intervals=iv, iterator=iv)
+        rs, re_, rv = d._sparse_records("created.sp", 0)
+        assert rs.tolist() == [100, 5000] and re_.tolist() == [900, 5200]
+        assert_same(rv.astype(np.float64), want["dense_track"][:2].astype(np.float32).astype(np.float64), "sparse track values")
+        assert len(d._sparse_records("created.sp", 2)[0]) == 0 and os.path.exists(os.path.join(d._track_dir("created.sp"), "chrX"))
+    finally:
+        d.close()

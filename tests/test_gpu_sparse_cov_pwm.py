@@ -610,3 +610,37 @@ def test_masked_golden_and_oracle(gpu_ctx, seq_testdb):
             for sshift, eshift in ((-3000, 4000), (7, -3), (0, 31)):
                 got = seq_testdb.masked_dev(rows, mode=mode, sshift=sshift, eshift=eshift).to_host()
                 assert_same(got, port.masked(seq, s, e, mode, sshift, eshift), f"{c} {mode} shift {sshift} {eshift}")
+
+
+def test_pwm_spatial_weights(gpu_ctx, seq_testdb):
+    """pwm / pwm.max / pwm.count under spatial weights (mg_pwm_spatial) against the compiled reference's PWMScorer with spat_factor set
+    (tests/golden/pwm_spat_vectors.npz) and the restatement under shifts."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "pwm_spat_vectors.npz"))
+    logp = gpu.pssm_logp(g["pssm"], float(g["prior"]))
+    spat, sbin, th = g["spat"], int(g["spat_bin"]), float(g["thresh"])
+    for cid, (c, size) in enumerate(CHROMS):
+        if c + "_start" not in g:
+            continue
+        s, e = g[c + "_start"], g[c + "_end"]
+        rows = gpu_ctx.rows_upload(np.full(len(s), cid, np.int32), s, e)
+        for bid in (1, 0):
+            for strand in (1, -1):
+                for ext in (1, 0):
+                    for mode in ("pwm", "pwm.max", "pwm.count"):
+                        got = seq_testdb.pwm(rows, logp, bidirect=bool(bid), extend=bool(ext), mode=mode, strand=strand, score_thresh=th, spat_factor=spat,
+                                             spat_bin=sbin)
+                        exp = g["%s_%s_b%d_s%d_e%d" % (c, mode, bid, strand, ext)]
+                        if mode == "pwm.count":
+                            assert_same(got, exp, "%s %s b%d s%d e%d" % (c, mode, bid, strand, ext))
+                        else:
+                            assert_close(got, exp, RTOL, "%s %s b%d s%d e%d" % (c, mode, bid, strand, ext))
+        seq = read_seq(c)
+        for ss, es in ((-50, 80), (30, 10)):
+            got = seq_testdb.pwm(rows, logp, mode="pwm", sshift=ss, eshift=es, spat_factor=spat, spat_bin=sbin)
+            assert_close(got, port.pwm_spat(seq, logp, s, e, spat, sbin, mode="pwm", sshift=ss, eshift=es), RTOL, "%s spatial pwm, shifts" % c)
+    with pytest.raises(gpu.MishaGpuError):
+        seq_testdb.pwm(rows, logp, mode="pwm.max.pos", spat_factor=spat, spat_bin=sbin)
+    # no weights given: the plain scorer, bit for bit
+    assert_same(seq_testdb.pwm(rows, logp, spat_factor=None), seq_testdb.pwm(rows, logp), "no weights == mg_pwm")

@@ -290,3 +290,24 @@ def test_path_dependent_counts_and_lse_against_the_compiled_reference():
         lse = port.dense_window_ext(bins, bs, size, s, e, lse_mode=int(generic))["lse"]
         np.testing.assert_allclose(lse, g[name + "_lse"], rtol=1e-6, atol=1e-6, equal_nan=True)
     assert np.sum(g["reducer_size"] != g["generic_size"]) > 100, "the fixture holds windows on which the two paths disagree"
+
+
+def test_pwm_spatial_weights_against_the_compiled_reference():
+    """pwm / pwm.max / pwm.count under spatial weights: the restatement against PWMScorer with spat_factor set (pwm_spat_vectors.npz)."""
+    g = np.load(os.path.join(GOLDEN, "pwm_spat_vectors.npz"))
+    logp = port.pssm_logp(g["pssm"], float(g["prior"]))
+    for c, _ in CHROMS:
+        if c + "_start" not in g:
+            continue
+        seq, s, e = read_seq(c), g[c + "_start"], g[c + "_end"]
+        for bid in (1, 0):
+            for strand in (1, -1):
+                for ext in (1, 0):
+                    for mode in ("pwm", "pwm.max", "pwm.count"):
+                        exp = g["%s_%s_b%d_s%d_e%d" % (c, mode, bid, strand, ext)]
+                        got = port.pwm_spat(seq, logp, s, e, g["spat"], int(g["spat_bin"]), bidirect=bool(bid), extend=bool(ext), mode=mode, strand=strand,
+                                            score_thresh=float(g["thresh"]))
+                        if mode == "pwm.count":
+                            assert_same(got, exp, "%s %s" % (c, mode))
+                        else:
+                            np.testing.assert_allclose(got, exp, rtol=1e-6, atol=1e-6, equal_nan=True)
