@@ -204,6 +204,16 @@ def r_eval(py, variables):
     return eval(py, {"__builtins__": {}}, {**R_FUNCS, **env})  # noqa: S307 - the expression language of the host
 
 
+def _value_column(iv):
+    """Name of the first numeric column of an intervals set that is not a coordinate column, or None."""
+    for k, v in iv.items():
+        if k in ("chrom", "start", "end", "strand", "intervalID"):
+            continue
+        if np.issubdtype(np.asarray(v).dtype, np.number):
+            return k
+    return None
+
+
 def rows_is_fixedbin(rows):
     return getattr(rows, "binsize", None) is not None
 
@@ -395,6 +405,21 @@ class MishaDB:
             self._ivsets[vt.name] = s
         return self._ivsets[vt.name]
 
+    def _value_track(self, vt):
+        """The value-based source of a vtrack staged like a sparse track: sorted records, values narrowed to float (NA -> NaN)."""
+        key = "\0value:" + vt.name
+        if key not in self._sparse:
+            iv = vt.src
+            cid = self._cids(iv)
+            vals = np.asarray(iv[_value_column(iv)], dtype=np.float64).astype(np.float32)
+            t = gpu.SparseTrack(self.ctx)
+            for c in range(len(self.chroms)):
+                m = np.flatnonzero(cid == c)
+                m = m[np.argsort(iv["start"][m], kind="stable")]
+                t.stage(c, iv["start"][m], iv["end"][m], vals[m])
+            self._sparse[key] = t
+        return self._sparse[key]
+
     # ---- virtual tracks -----------------------------------------------------------------------------------
     def gvtrack_create(self, vtrack, src=None, func=None, params=None):
         """R/vtrack.R:1204. src: track name, Intervals (for 'coverage'), or None for sequence functions (pwm*)."""
@@ -409,6 +434,21 @@ class MishaDB:
             if func == "quantile":
                 if params is None or not (0 <= float(params) <= 1):
                     raise MishaError("Virtual track %s: function quantile requires a percentile in [0, 1]" % vtrack)
+        elif isinstance(src, Intervals) and _value_column(src) is not None and (func or "avg") not in ("coverage", "distance", "distance.center", "neighbor.count"):
+            # a VALUE-BASED track: intervals with one numeric value column act as an in-memory sparse track (GenomeTrackInMemory,
+            # src/GenomeTrackInMemory.cpp:36-270 = GenomeTrackSparse's count-based arithmetic; detection as in
+            # src/TrackExpressionVars.cpp:906-976: the first numeric column that is not chrom / start / end / strand / intervalID)
+            func = func or "avg"
+            if func not in TRACK_FUNCS:
+                raise MishaError("Virtual track %s: invalid function %s used with value-based intervals" % (vtrack, func))
+            if func == "quantile" and (params is None or not (0 <= float(params) <= 1)):
+                raise MishaError("Virtual track %s: function quantile requires a percentile in [0, 1]" % vtrack)
+            self._validate(src)
+            cid = self._cids(src)
+            order = np.lexsort((src["start"], cid))
+            c, st, en = cid[order], src["start"][order], src["end"][order]
+            if np.any((c[1:] == c[:-1]) & (st[1:] < en[:-1])):
+                raise MishaError("Virtual track %s: value-based intervals must not overlap" % vtrack)
         elif isinstance(src, Intervals):
             func = func or "coverage"
             if func != "coverage":
@@ -435,8 +475,21 @@ class MishaDB:
             prior = float(p.get("prior", 0.01))  # defaults: R/vtrack.R:179-290
             if not (0 <= prior <= 1):
                 raise MishaError("Virtual track %s: prior must be between 0 and 1" % vtrack)
+            spat, spat_bin = p.get("spat_factor"), p.get("spat_bin")
+            if spat is not None:  # R/vtrack.R:249-262
+                spat = np.atleast_1d(np.asarray(spat, dtype=np.float64))
+                if np.any(~(spat > 0)):
+                    raise MishaError("spat_factor must be a numeric vector with all positive values")
+                spat_bin = 1 if spat_bin is None else spat_bin
+                if not spat_bin > 0:
+                    raise MishaError("spat_bin must be a positive integer")
+                if func == "pwm.max.pos":
+                    raise MishaError("Virtual track %s: pwm.max.pos under spatial weights is not supported by this build" % vtrack)
+                if p.get("spat_min") is not None or p.get("spat_max") is not None:
+                    raise MishaError("Virtual track %s: spat_min / spat_max are not supported by this build" % vtrack)
             params = dict(pssm=pssm, bidirect=bool(p.get("bidirect", True)), prior=prior, extend=bool(p.get("extend", True)),
-                          strand=int(p.get("strand", 1)), score_thresh=float(p.get("score.thresh", p.get("score_thresh", 0.0))))
+                          strand=int(p.get("strand", 1)), score_thresh=float(p.get("score.thresh", p.get("score_thresh", 0.0))),
+                          spat_factor=None if spat is None else spat.astype(np.float32), spat_bin=int(spat_bin or 1))
         else:
             raise MishaError("Virtual track %s: unsupported source" % vtrack)
         self.vtracks[vtrack] = _VTrack(vtrack, src, func, params)
@@ -539,6 +592,8 @@ class MishaDB:
             kind = self._track_type(vt.src)
             t = self._dense_track(vt.src) if kind == "dense" else self._sparse_track(vt.src)
             return t.window_dev(rows, [f], vt.sshift, vt.eshift)[0]
+        if isinstance(vt.src, Intervals) and vt.func != "coverage":  # value-based: the in-memory sparse track
+            return self._value_track(vt).window_dev(rows, [_gpu_func(vt)], vt.sshift, vt.eshift)[0]
         if isinstance(vt.src, Intervals):
             return self._ivset(vt).coverage_dev(rows, vt.sshift, vt.eshift)
         p = vt.params
@@ -548,7 +603,8 @@ class MishaDB:
             return self._sequence().kmer_dev(rows, p["kmer"], mode=vt.func, extend=p["extend"], strand=p["strand"], sshift=vt.sshift, eshift=vt.eshift)
         logp = gpu.pssm_logp(p["pssm"], p["prior"])
         return self._sequence().pwm_dev(rows, logp, bidirect=p["bidirect"], extend=p["extend"], mode=vt.func, strand=p["strand"],
-                                        score_thresh=p["score_thresh"], sshift=vt.sshift, eshift=vt.eshift)
+                                        score_thresh=p["score_thresh"], sshift=vt.sshift, eshift=vt.eshift, spat_factor=p.get("spat_factor"),
+                                        spat_bin=p.get("spat_bin", 1))
 
     def _eval(self, expr, rows, cache, logical=False):
         """Host value vector of a track expression over the rows. logical: a logical result is returned as RLogical (R's three-valued

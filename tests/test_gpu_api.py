@@ -391,3 +391,35 @@ def test_gtrack_create_from_an_expression(db, tmp_path):
         assert len(d._sparse_records("created.sp", 2)[0]) == 0 and os.path.exists(os.path.join(d._track_dir("created.sp"), "chrX"))
     finally:
         d.close()
+
+
+def test_value_based_vtracks(db):
+    """gvtrack.create(src = data frame with a value column): an in-memory sparse track (GenomeTrackInMemory,
+    src/GenomeTrackInMemory.cpp:36-270, "count-based statistics matching GenomeTrackSparse"): the same answers as the sparse reader's
+    restatement over those records."""
+    rs, re_, rv = read_sparse("sparse_track", "chr1")
+    pick = np.arange(0, len(rs), 3)
+    src = api.Intervals(["chr1"] * len(pick), rs[pick], re_[pick], score=rv[pick].astype(np.float64))
+    iv = db.gintervals([1] * 5, [0, 1000, 40000, 100000, 499000], [600, 9000, 41000, 230000, 500000])
+    names = ("avg", "sum", "min", "max", "nearest", "size", "stddev")
+    for f in names:
+        db.gvtrack_create("vb_" + f, src, f)
+    db.gvtrack_create("vb_q", src, "quantile", 0.3)
+    db.gvtrack_iterator("vb_max", sshift=-500, eshift=500)
+    got = db.gextract(*["vb_" + f for f in names], "vb_q", intervals=iv, iterator=iv)
+    exp = port.sparse_window(rs[pick], re_[pick], rv[pick], 500000, iv["start"], iv["end"], 0, 0, 0.3, funcs=names + ("quantile",))
+    for f in names:
+        if f == "max":
+            continue
+        assert_same(got["vb_" + f], exp[f], "value-based " + f)
+    assert_same(got["vb_q"], exp["quantile"], "value-based quantile")
+    exps = port.sparse_window(rs[pick], re_[pick], rv[pick], 500000, iv["start"], iv["end"], -500, 500, 0.5, funcs=("max",))
+    assert_same(got["vb_max"], exps["max"], "value-based max under shifts")
+    # interval functions over the same data frame keep their meaning; overlapping value-based intervals are refused
+    db.gvtrack_create("vb_cov", src, "coverage")
+    assert np.all((db.gextract("vb_cov", intervals=iv, iterator=iv)["vb_cov"] >= 0))
+    bad = api.Intervals(["chr1", "chr1"], [100, 150], [200, 300], v=[1.0, 2.0])
+    with pytest.raises(api.MishaError, match="overlap"):
+        db.gvtrack_create("vb_bad", bad, "avg")
+    for f in names + ("q", "cov"):
+        db.gvtrack_rm("vb_" + f)
