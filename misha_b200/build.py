@@ -54,8 +54,17 @@ def build_host(force=False):
         raise RuntimeError("%s not found and no prebuilt host layer" % CXX)
     common = [CXX, "-std=c++17", "-O2", "-Wall"]
     link = ["-L" + HERE, "-lmishagpu", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(common + ["-fPIC", "-shared", "-o", HOST_SO, os.path.join(HOST, "GpuTrackExprScanner.cpp")] + link)
-    subprocess.check_call(common + ["-o", HOST_DEMO, os.path.join(HOST, "mg_host_demo.cpp"), "-L" + HERE, "-lmishahost"] + link[1:])
+    with _BuildLock():
+        tmp_so, tmp_demo = HOST_SO + ".tmp.%d" % os.getpid(), HOST_DEMO + ".tmp.%d" % os.getpid()
+        try:
+            subprocess.check_call(common + ["-fPIC", "-shared", "-o", tmp_so, os.path.join(HOST, "GpuTrackExprScanner.cpp")] + link)
+            os.replace(tmp_so, HOST_SO)
+            subprocess.check_call(common + ["-o", tmp_demo, os.path.join(HOST, "mg_host_demo.cpp"), "-L" + HERE, "-lmishahost"] + link[1:])
+            os.replace(tmp_demo, HOST_DEMO)
+        finally:
+            for t in (tmp_so, tmp_demo):
+                if os.path.exists(t):
+                    os.remove(t)
     return HOST_SO
 
 
@@ -66,6 +75,23 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps())
 
 
+class _BuildLock:
+    """One builder at a time per checkout: N ranks of a torchrun job import the package at the same moment, and a library that is being
+    written must never be the one another process loads. The lock file lives next to the library; whoever gets it re-checks the
+    timestamps (the previous holder may have built already)."""
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(os.path.join(HERE, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return SO
@@ -73,10 +99,19 @@ def build(force=False, verbose=False):
         if os.path.exists(SO):
             return SO  # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
         raise RuntimeError("nvcc not found at %s and no prebuilt %s" % (NVCC, SO))
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    with _BuildLock():
+        if not force and up_to_date():
+            return SO
+        tmp = SO + ".tmp.%d" % os.getpid()  # written aside, renamed into place: a reader sees the old library or the new one, never half of one
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+        if verbose:
+            print(" ".join(cmd))
+        try:
+            subprocess.check_call(cmd)
+            os.replace(tmp, SO)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
     return SO
 
 

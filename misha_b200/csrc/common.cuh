@@ -47,6 +47,7 @@ struct mg_ctx {
 	int64_t hbm_budget = 0;  // bytes the dense tracks' index structures + cores may hold on this device (0: 85 % of the device's memory)
 	int64_t use_tick = 0;    // advances with every query: least-recently-used index groups go first when the budget is short
 	std::vector<struct mg_dense *> dense_tracks; // every live dense track of this context (budget accounting)
+	bool inline_table = true; // the chromosome table travels in the kernel parameters of the dense tile kernels (dense.cuh: DenseQuery::inl_*)
 	uint32_t pipe_attr = 0;  // k_dense_pipe instantiations whose shared-memory attributes have been set
 	uint32_t tile_attr = 0;  // k_dense_tile instantiations whose dynamic shared-memory limit has been raised on this device
 	bool force_sweep = false; // tests / ablation: route min/max/quantile through the warp-per-row sweep kernel
@@ -61,6 +62,7 @@ struct mg_ctx {
 	void *pipe_dev[3] = {nullptr, nullptr, nullptr};
 	int64_t pipe_dev_bytes[3] = {0, 0, 0};
 	unsigned long long *d_first_bad = nullptr; // first row of a host batch whose chromosome id was out of range (k_rows_sanitize); ~0: none
+	uint8_t *d_served = nullptr; // member of a group: served[chromid] != 0 for the chromosomes this device owns (null: every chromosome)
 	int64_t pipe_next = 0; // chunks enqueued so far: the slot of the next one is pipe_next % 3
 };
 

@@ -75,6 +75,7 @@ struct mg_dense {
 };
 
 #define MG_MAX_Q 8
+#define MG_INL_CHROMS 32
 
 struct DenseQuery {
 	RowSrc rows;
@@ -94,6 +95,14 @@ struct DenseQuery {
 	int stage;  // k_dense_rowquery stages the block records its rows need in shared memory (0: walk them through L1; ablation)
 	double q_pct[MG_MAX_Q];
 	double *q_out[MG_MAX_Q];
+	// The chromosome table in the kernel parameters (genomes of <= MG_INL_CHROMS chromosomes shorter than 2^31 bp): sizes, bin counts and the
+	// array bases a tile's thread block needs BEFORE it can issue its bulk copies come from the constant bank instead of two dependent global
+	// round trips (chrom_sizes[chrom], then table[chrom]) in every thread block's life. inl_n = 0: not filled, the kernels load the tables.
+	int inl_n;
+	uint32_t inl_csize[MG_INL_CHROMS], inl_nbins[MG_INL_CHROMS];
+	const float *inl_vals[MG_INL_CHROMS];
+	const Pref *inl_p8[MG_INL_CHROMS];
+	const uint8_t *inl_bw[MG_INL_CHROMS];
 };
 
 // ------------------------------------------------------------------------------------------------------------

@@ -207,7 +207,8 @@ __device__ __forceinline__ void mg_tile_row(const DenseQuery &q, int64_t row, bo
 	int chrom;
 	int64_t s, e, scope;
 	mg_get_row(q.rows, row, chrom, s, e, scope);
-	const int64_t csize = __ldg(q.chrom_sizes + chrom);
+	const bool inl = q.inl_n > 0; // sizes and bin counts from the kernel parameters (see DenseQuery)
+	const int64_t csize = inl ? (int64_t)q.inl_csize[chrom] : __ldg(q.chrom_sizes + chrom);
 	int64_t ws = s + q.sshift, we = e + q.eshift;
 	ws = ws < 0 ? 0 : ws;
 	we = we > csize ? csize : we;
@@ -215,7 +216,7 @@ __device__ __forceinline__ void mg_tile_row(const DenseQuery &q, int64_t row, bo
 	if (!r.ok)
 		return;
 	if ((uint64_t)csize <= 0x7fffffffull - q.bin_size && q.bin_magic) { // every coordinate and bin of this chromosome fits 31 bits
-		const uint32_t nbins = (uint32_t)q.table[chrom].nbins;
+		const uint32_t nbins = inl ? q.inl_nbins[chrom] : (uint32_t)q.table[chrom].nbins;
 		const uint32_t a = (uint32_t)ws, b = (uint32_t)we + q.bin_size - 1u;
 		const uint32_t sb = (uint32_t)__umul64hi((uint64_t)a, q.bin_magic); // src/GenomeTrackFixedBin.cpp:675
 		uint32_t eb = (uint32_t)__umul64hi((uint64_t)b, q.bin_magic);       // :676
@@ -611,6 +612,9 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	const uint32_t span8 = anyreg ? ((bmax - b0 + 7u) & ~7u) : 0u; // staged bins: whole groups of 8 (the track is padded with NaN)
 	const uint32_t blk0 = bmin / MG_BW_STRIDE, nrec = anyreg ? (bmax - 1u) / MG_BW_STRIDE - blk0 + 1u : 0u;
 	const DenseChrom *ch = q.table + cmin;
+	const bool inl = q.inl_n > 0 && anyreg;
+	const uint8_t *bw_base = Q ? (inl ? q.inl_bw[cmin] : (anyreg ? ch->bw : nullptr)) : nullptr;
+	const Pref *p8_base = inl ? q.inl_p8[cmin] : (anyreg ? ch->p8 : nullptr);
 	bool fast = anyreg && !anybad && cmin == cmax && span8 <= MG_TL_CAP;
 	if (Q)
 		fast = fast && q.use_bw && nrec <= MG_TL_SLOTS;
@@ -624,12 +628,12 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	float *s_vals = reinterpret_cast<float *>(smem);
 	uint8_t *s_lv = smem + MG_TH_SZ_VALS;
 	if (t == 0) {
-		const float *vsrc = ch->vals;
+		const float *vsrc = inl ? q.inl_vals[cmin] : ch->vals;
 		const uint32_t vbytes = span8 * 4u;
 		mg_mbar_expect_tx(&s_bar, vbytes + (Q ? nrec * MG_BW_STAGE_BYTES : 0u));
 		mg_bulk_g2s(s_vals, vsrc + b0, vbytes, &s_bar);
 		if (Q) {
-			const uint8_t *src = ch->bw + (size_t)blk0 * MG_BW_RECORD_BYTES;
+			const uint8_t *src = bw_base + (size_t)blk0 * MG_BW_RECORD_BYTES;
 			for (uint32_t sl = 0; sl < nrec; ++sl)
 				mg_bulk_g2s(s_lv + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar);
 		}
@@ -642,8 +646,8 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	pa.cnt = pb.cnt = 0;
 	float tmx = __int_as_float(0xff800000), tmn = __int_as_float(0x7f800000);
 	if (multi) {
-		pa = mg_ld_pref(ch->p8 + g0 + 1);
-		pb = mg_ld_pref(ch->p8 + g1);
+		pa = mg_ld_pref(p8_base + g0 + 1);
+		pb = mg_ld_pref(p8_base + g1);
 		const uint32_t gs = g0 + 1, len = g1 - gs;
 		if (MM && len > 0) { // len < 2^MG_ST_LEVELS: the tile holds MG_TL_CAP bins
 			const int j = 31 - __clz((int)len);
@@ -653,6 +657,7 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 				tmn = fminf(__ldg(ch->smin[j] + gs), __ldg(ch->smin[j] + g1 - (1u << j)));
 		}
 	}
+	const double abs_sum = SUM && multi ? ch->abs_sum : 0.; // scale of the cancellation guard below: loaded with the rest, before the wait
 	// one warp watches the barrier, the others park at the thread-block barrier (no issue slots spent on polling)
 	if (warp == 0)
 		mg_mbar_wait(&s_bar, 0);
@@ -683,7 +688,7 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 			S = (S + (pb.sum - pa.sum)) + St;
 			n = (uint32_t)nh + (uint32_t)(pb.cnt - pa.cnt) + (uint32_t)nt;
 			// the prefix difference has lost too many digits against the chromosome's running sum: the bins in order, from the staged copy
-			if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < ch->abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
+			if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
 				S = 0;
 				for (uint32_t b = sb - b0; b < eb - b0; ++b) {
 					const float v = s_vals[b];
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	if (Q) {
 		const uint32_t blk = sb / MG_BW_STRIDE, l = sb - blk * MG_BW_STRIDE;
 		const uint8_t *lv = s_lv + (size_t)(blk - blk0) * MG_BW_STAGE_BYTES;
-		const uint16_t *pos = reinterpret_cast<const uint16_t *>(ch->bw + (size_t)blk * MG_BW_RECORD_BYTES + MG_BW_POS_OFFSET);
+		const uint16_t *pos = reinterpret_cast<const uint16_t *>(bw_base + (size_t)blk * MG_BW_RECORD_BYTES + MG_BW_POS_OFFSET);
 		const float *vblk = s_vals + ((int)(blk * MG_BW_STRIDE) - (int)b0); // block-local position -> staged bin
 		for (int k = 0; k < q.nq; ++k) {
 			double qv = mg_nan();

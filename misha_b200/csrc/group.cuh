@@ -131,6 +131,18 @@ extern "C" int mg_group_init(int ndev, const int *dev_ids, int nchroms, const in
 		g->owner[i] = best;
 		load[best] += chrom_sizes[i];
 	}
+	if (ndev > 1)
+		for (int k = 0; k < ndev; ++k) { // what each member serves, for the device-side check of routed rows (k_rows_sanitize)
+			std::vector<uint8_t> served((size_t)nchroms);
+			for (int i = 0; i < nchroms; ++i)
+				served[i] = g->owner[i] == k;
+			mg_ctx *c = g->ctx[k];
+			if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&c->d_served, (size_t)nchroms) != cudaSuccess ||
+				cudaMemcpy(c->d_served, served.data(), (size_t)nchroms, cudaMemcpyHostToDevice) != cudaSuccess) {
+				mg_group_shutdown(g);
+				return mg_gfail(nullptr, "mg_group_init: device %d: %s", dev_ids[k], cudaGetErrorString(cudaGetLastError()));
+			}
+		}
 	*out = g;
 	return 0;
 }
@@ -248,6 +260,37 @@ static bool mg_group_runs(mg_group *g, int64_t n, const int32_t *h_chrom, std::v
 	return true;
 }
 
+// The same for rows that come chromosome by chromosome in ascending id order (what every scanner of the reference produces from a sorted
+// scope): the end of a run is found by bisection, O(chromosomes x log rows) instead of a pass over every id. Nothing here verifies the order --
+// the members do, on the device: a row that reaches a member which does not own its chromosome is recorded (k_rows_sanitize) and the caller
+// routes the batch again with the exact pass.
+static bool mg_group_runs_sorted(mg_group *g, int64_t n, const int32_t *h_chrom, std::vector<GroupRun> &runs)
+{
+	runs.clear();
+	const int nch = (int)g->owner.size();
+	int64_t i = 0;
+	while (i < n) {
+		const int32_t c = h_chrom[i];
+		if (c < 0 || c >= nch)
+			return false;
+		int64_t lo = i, hi = n; // first index > i whose id exceeds c, were the ids ascending
+		while (hi - lo > 1) {
+			const int64_t mid = lo + (hi - lo) / 2;
+			if (h_chrom[mid] <= c)
+				lo = mid;
+			else
+				hi = mid;
+		}
+		const int m = g->owner[c];
+		if (!runs.empty() && runs.back().member == m)
+			runs.back().count += hi - i;
+		else
+			runs.push_back(GroupRun{m, i, hi - i});
+		i = hi;
+	}
+	return true;
+}
+
 // gextract: host rows in, host columns out (the group's mg_h_dense_window)
 extern "C" int mg_group_h_dense_window(mg_group *g, const mg_gdense *t, int64_t n, const int32_t *h_chrom, const int64_t *h_start, const int64_t *h_end,
 									   int64_t sshift, int64_t eshift, int nfuncs, const int *funcs, const double *params, double *const *h_out)
@@ -257,13 +300,79 @@ extern "C" int mg_group_h_dense_window(mg_group *g, const mg_gdense *t, int64_t 
 	const int nm = (int)g->ctx.size();
 	const int64_t MAX_RUNS = 4096;
 	std::vector<GroupRun> runs;
-	if (!mg_group_runs(g, n, h_chrom, runs, MAX_RUNS))
-		return 1;
-	// rows in no useful order: one gathered batch per member
+	// gathered batches (rows in no useful order): one per member
 	std::vector<std::vector<int64_t>> idx;
 	std::vector<std::vector<int32_t>> gc(nm);
 	std::vector<std::vector<int64_t>> gs(nm), ge(nm);
 	std::vector<std::vector<double>> gout;
+	std::vector<char> used(nm, 0);
+
+	// enqueue every run, then drain: no member is waited for before the others have their work. misrouted: a member met a row of a
+	// chromosome it does not own, or an id out of range (only the trusting routing below can cause the former)
+	auto execute = [&](bool gather, bool &misrouted) -> int {
+		int rc = 0;
+		std::fill(used.begin(), used.end(), 0);
+		for (const GroupRun &r : runs) {
+			mg_ctx *ctx = g->ctx[r.member];
+			const mg_dense *tt = t->t[r.member];
+			double *outp[32];
+			const int32_t *pc;
+			const int64_t *ps, *pe;
+			if (gather) {
+				pc = gc[r.member].data(); ps = gs[r.member].data(); pe = ge[r.member].data();
+				for (int f = 0; f < nfuncs; ++f)
+					outp[f] = gout[(size_t)r.member * nfuncs + f].data();
+			} else {
+				pc = h_chrom + r.first; ps = h_start + r.first; pe = h_end + r.first;
+				for (int f = 0; f < nfuncs; ++f)
+					outp[f] = h_out[f] + r.first;
+			}
+			used[r.member] = 1;
+			if (cudaSetDevice(ctx->device) != cudaSuccess || mg_pipe_prepare(ctx, mg_pipe_slot_bytes(ctx, nfuncs)) ||
+				mg_h_pipeline_run(ctx, r.count, pc, ps, pe, nfuncs, outp, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
+					DenseQuery q;
+					bool need_sweep;
+					return mg_fill_dense_query(ctx, tt, &rows, 0, m, sshift, eshift, nfuncs, funcs, params, d_cols, q, need_sweep) ||
+						   mg_launch_dense(ctx, q, need_sweep, st);
+				})) {
+				rc = mg_gfail(g, "device %d: %s", ctx->device, ctx->err.empty() ? "cudaSetDevice failed" : ctx->err.c_str());
+				break;
+			}
+		}
+		misrouted = false;
+		for (int k = 0; k < nm; ++k) { // whatever happened, nothing stays in flight into the caller's buffers
+			if (!used[k])
+				continue;
+			mg_ctx *ctx = g->ctx[k];
+			cudaSetDevice(ctx->device);
+			for (int i = 0; i < 3; ++i)
+				if (ctx->pipe_stream[i]) {
+					const cudaError_t e = cudaStreamSynchronize(ctx->pipe_stream[i]);
+					if (e != cudaSuccess && !rc)
+						rc = mg_gfail(g, "device %d: %s", ctx->device, cudaGetErrorString(e));
+				}
+			if (ctx->d_first_bad) { // the members' records of rows they should not have got (reset either way)
+				unsigned long long bad = ~0ull;
+				if (cudaMemcpy(&bad, ctx->d_first_bad, 8, cudaMemcpyDeviceToHost) == cudaSuccess && bad != ~0ull) {
+					misrouted = true;
+					cudaMemset(ctx->d_first_bad, 0xff, 8);
+				}
+			}
+		}
+		return rc;
+	};
+
+	// 1. trust the order (chromosome-major, ascending ids: what a sorted scope yields): routing by bisection, verified on the devices
+	bool misrouted = false;
+	if (mg_group_runs_sorted(g, n, h_chrom, runs) && (int64_t)runs.size() <= MAX_RUNS) {
+		if (execute(false, misrouted))
+			return 1;
+		if (!misrouted)
+			return 0;
+	}
+	// 2. any other order (or a bad id): the exact pass over every row's id; more owner changes than MAX_RUNS -> gather / scatter
+	if (!mg_group_runs(g, n, h_chrom, runs, MAX_RUNS))
+		return 1;
 	const bool gather = (int64_t)runs.size() > MAX_RUNS;
 	if (gather) {
 		idx.assign(nm, {});
@@ -289,49 +398,9 @@ extern "C" int mg_group_h_dense_window(mg_group *g, const mg_gdense *t, int64_t 
 				runs.push_back(GroupRun{k, 0, (int64_t)m});
 		}
 	}
-	// enqueue everything, then drain: no member is waited for before the others have their work
-	int rc = 0;
-	std::vector<char> used(nm, 0);
-	for (const GroupRun &r : runs) {
-		mg_ctx *ctx = g->ctx[r.member];
-		const mg_dense *tt = t->t[r.member];
-		double *outp[32];
-		const int32_t *pc;
-		const int64_t *ps, *pe;
-		if (gather) {
-			pc = gc[r.member].data(); ps = gs[r.member].data(); pe = ge[r.member].data();
-			for (int f = 0; f < nfuncs; ++f)
-				outp[f] = gout[(size_t)r.member * nfuncs + f].data();
-		} else {
-			pc = h_chrom + r.first; ps = h_start + r.first; pe = h_end + r.first;
-			for (int f = 0; f < nfuncs; ++f)
-				outp[f] = h_out[f] + r.first;
-		}
-		used[r.member] = 1;
-		if (cudaSetDevice(ctx->device) != cudaSuccess || mg_pipe_prepare(ctx, mg_pipe_slot_bytes(ctx, nfuncs)) ||
-			mg_h_pipeline_run(ctx, r.count, pc, ps, pe, nfuncs, outp, [&](const mg_rows &rows, int64_t m, double *const *d_cols, cudaStream_t st) {
-				DenseQuery q;
-				bool need_sweep;
-				return mg_fill_dense_query(ctx, tt, &rows, 0, m, sshift, eshift, nfuncs, funcs, params, d_cols, q, need_sweep) ||
-					   mg_launch_dense(ctx, q, need_sweep, st);
-			})) {
-			rc = mg_gfail(g, "device %d: %s", ctx->device, ctx->err.empty() ? "cudaSetDevice failed" : ctx->err.c_str());
-			break;
-		}
-	}
-	for (int k = 0; k < nm; ++k) { // whatever happened, nothing stays in flight into the caller's buffers
-		if (!used[k])
-			continue;
-		cudaSetDevice(g->ctx[k]->device);
-		for (int i = 0; i < 3; ++i)
-			if (g->ctx[k]->pipe_stream[i]) {
-				const cudaError_t e = cudaStreamSynchronize(g->ctx[k]->pipe_stream[i]);
-				if (e != cudaSuccess && !rc)
-					rc = mg_gfail(g, "device %d: %s", g->ctx[k]->device, cudaGetErrorString(e));
-			}
-	}
-	if (rc)
-		return rc;
+	if (execute(gather, misrouted))
+		return 1;
+	MG_GREQUIRE(g, !misrouted, "mg_group_h_dense_window: a member was handed rows of a chromosome it does not own (internal routing error)");
 	if (gather)
 		for (int k = 0; k < nm; ++k)
 			for (int f = 0; f < nfuncs; ++f) {

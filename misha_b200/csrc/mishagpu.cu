@@ -71,6 +71,8 @@ extern "C" void mg_shutdown(mg_ctx *ctx)
 	}
 	if (ctx->d_first_bad)
 		cudaFree(ctx->d_first_bad);
+	if (ctx->d_served)
+		cudaFree(ctx->d_served);
 	for (auto &kv : ctx->stream_scratch)
 		cudaFree(kv.second);
 	cudaFree(ctx->d_chrom_sizes);
@@ -117,6 +119,10 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 	}
 	if (name && !strcmp(name, "hbm_budget_mb")) { // what the dense tracks may hold on this device; least-recently-used index groups are dropped beyond it
 		ctx->hbm_budget = value > 0 ? value << 20 : 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "inline_table")) { // 0: the tile kernels load chromosome sizes / array bases from the tables in HBM (ablation)
+		ctx->inline_table = value != 0;
 		return 0;
 	}
 	if (name && !strcmp(name, "tile_kernel")) {
@@ -915,6 +921,21 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 		if (groups && mg_dense_ensure(ctx, const_cast<mg_dense *>(t), groups))
 			return 1;
 	}
+	if (ctx->nchroms <= MG_INL_CHROMS && ctx->inline_table) { // after mg_dense_ensure: the group pointers are the current ones
+		bool fits = true;
+		for (int c = 0; c < ctx->nchroms; ++c)
+			fits = fits && ctx->chrom_sizes[c] < (int64_t)0x7fffffff - (int64_t)t->bin_size && t->h_table[c].nbins < (int64_t)0x7fffffff;
+		if (fits) {
+			q.inl_n = ctx->nchroms;
+			for (int c = 0; c < ctx->nchroms; ++c) {
+				q.inl_csize[c] = (uint32_t)ctx->chrom_sizes[c];
+				q.inl_nbins[c] = (uint32_t)t->h_table[c].nbins;
+				q.inl_vals[c] = t->h_table[c].vals;
+				q.inl_p8[c] = t->h_table[c].p8;
+				q.inl_bw[c] = t->h_table[c].bw;
+			}
+		}
+	}
 	for (int k = 0; k < nfuncs; ++k) {
 		const int f = funcs[k] & ~MG_FUNC_GENERIC;
 		MG_REQUIRE(ctx, f >= 0 && f < MG_NUM_FUNCS, "unknown function id %d", f);
@@ -1165,14 +1186,18 @@ static int mg_check_rows(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 // Chromosome ids of a chunk already on the device: an id out of range is replaced by 0 -- the kernels index per-chromosome tables with
 // it -- and the first offending row is recorded; the host looks at the record once, after the drain. (A pass over the ids on the
 // host, even a branch-free one per chunk, cost more than a millisecond of the 5 ms a 10 M-row batch takes end to end.)
-__global__ void __launch_bounds__(256) k_rows_sanitize(int32_t *chrom, int64_t m, int nchroms, int64_t base_row, unsigned long long *first_bad)
+// served: when not null, served[id] != 0 marks the chromosomes this device holds (a member of a group is handed the rows of its own
+// chromosomes by a routing that trusts the rows' order; a row of somebody else's chromosome is recorded the same way and the host re-routes).
+__global__ void __launch_bounds__(256) k_rows_sanitize(int32_t *chrom, int64_t m, int nchroms, int64_t base_row, unsigned long long *first_bad,
+													 const uint8_t *__restrict__ served)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m)
 		return;
-	if ((uint32_t)chrom[i] >= (uint32_t)nchroms) {
+	const uint32_t c = (uint32_t)chrom[i];
+	if (c >= (uint32_t)nchroms || (served && !served[c])) {
 		atomicMin(first_bad, (unsigned long long)(base_row + i));
-		chrom[i] = 0;
+		chrom[i] = c < (uint32_t)nchroms ? (int32_t)c : 0; // a valid id of another member: tables exist (empty there), nothing is out of bounds
 	}
 }
 
@@ -1204,7 +1229,7 @@ static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, con
 		MG_CUDA(ctx, cudaMemcpyAsync(d_start, h_start + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
 		MG_CUDA(ctx, cudaMemcpyAsync(d_end, h_end + done, (size_t)m * 8, cudaMemcpyHostToDevice, st));
 		MG_CUDA(ctx, cudaMemcpyAsync(d_chrom, h_chrom + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-		k_rows_sanitize<<<(unsigned)mg_div_up(m, 256), 256, 0, st>>>(d_chrom, m, ctx->nchroms, row_base + done, ctx->d_first_bad);
+		k_rows_sanitize<<<(unsigned)mg_div_up(m, 256), 256, 0, st>>>(d_chrom, m, ctx->nchroms, row_base + done, ctx->d_first_bad, ctx->d_served);
 		MG_LAUNCH_CHECK(ctx);
 		mg_rows rows;
 		rows.src.kind = 0;
