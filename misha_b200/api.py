@@ -234,6 +234,7 @@ class _VTrack:
     def __init__(self, name, src, func, params):
         self.name, self.src, self.func, self.params = name, src, func, params
         self.sshift = self.eshift = 0
+        self.slice, self.slice_func, self.slice_percentile = None, "avg", 0.5  # gvtrack.array.slice (array tracks only)
 
 
 class MishaDB:
@@ -404,6 +405,40 @@ class MishaDB:
                 s.stage(c, np.array(us, np.int64), np.array(ue, np.int64))
             self._ivsets[vt.name] = s
         return self._ivsets[vt.name]
+
+    def _array_track(self, track, slice_cols, slice_func, slice_percentile):
+        """An array track under a slice (gvtrack.array.slice: columns + the function that folds them, R/vtrack.R; src/GenomeTrackArrays.cpp):
+        every record presents ONE value -- get_sliced_val over its stored (value, column) pairs -- and from there on the track is a sparse
+        track (calc_vals, src/GenomeTrackArrays.h:131-196, is GenomeTrackSparse's arithmetic). The fold runs on the host at staging time."""
+        key = "\0array:%s:%s:%s:%r" % (track, ",".join(map(str, slice_cols)) if slice_cols is not None else "*", slice_func, slice_percentile)
+        if key not in self._sparse:
+            d, idx = self._track_dir(track), self._track_index(track)
+            t = gpu.SparseTrack(self.ctx)
+            try:
+                for cid, c in enumerate(self.chrom_names):
+                    st, en, rf, v, cols = formats.read_array_chrom(d, c, cid, idx)
+                    t.stage(cid, st, en, formats.array_slice_values(rf, v, cols, slice_cols, slice_func, slice_percentile))
+            except formats.FormatError as e:
+                raise MishaError("Track %s: %s" % (track, e))
+            self._sparse[key] = t
+        return self._sparse[key]
+
+    def gvtrack_array_slice(self, vtrack, slice=None, func="avg", params=None):
+        """gvtrack.array.slice(vtrack, slice, func, params), R/vtrack.R: which columns (0-based indices) of the array track a virtual track
+        reads and how they are folded into one value per record: avg / min / max / stddev / sum / quantile (params = percentile)."""
+        if vtrack not in self.vtracks:
+            raise MishaError("Virtual track %s does not exist" % vtrack)
+        vt = self.vtracks[vtrack]
+        if not isinstance(vt.src, str) or self._track_type(vt.src) != "array":
+            raise MishaError("Virtual track %s: slices apply to array tracks only" % vtrack)
+        if func not in formats.SLICE_FUNCS:
+            raise MishaError("Virtual track %s: invalid slice function %s" % (vtrack, func))
+        if func == "quantile" and (params is None or not (0 <= float(params) <= 1)):
+            raise MishaError("Virtual track %s: slice function quantile requires a percentile in [0, 1]" % vtrack)
+        vt.slice = None if slice is None else sorted({int(x) for x in np.atleast_1d(slice)})
+        if vt.slice is not None and (not vt.slice or vt.slice[0] < 0):
+            raise MishaError("Virtual track %s: invalid slice" % vtrack)
+        vt.slice_func, vt.slice_percentile = func, float(params) if params is not None else 0.5
 
     def _value_track(self, vt):
         """The value-based source of a vtrack staged like a sparse track: sorted records, values narrowed to float (NA -> NaN)."""
@@ -590,7 +625,10 @@ class MishaDB:
         if isinstance(vt.src, str):
             f = _gpu_func(vt)
             kind = self._track_type(vt.src)
-            t = self._dense_track(vt.src) if kind == "dense" else self._sparse_track(vt.src)
+            if kind == "array":
+                t = self._array_track(vt.src, vt.slice, vt.slice_func, vt.slice_percentile)
+            else:
+                t = self._dense_track(vt.src) if kind == "dense" else self._sparse_track(vt.src)
             return t.window_dev(rows, [f], vt.sshift, vt.eshift)[0]
         if isinstance(vt.src, Intervals) and vt.func != "coverage":  # value-based: the in-memory sparse track
             return self._value_track(vt).window_dev(rows, [_gpu_func(vt)], vt.sshift, vt.eshift)[0]

@@ -123,8 +123,6 @@ def track_type(track_dir, chrom_names):
     """"dense" / "sparse" (src/GenomeTrack.cpp:227-250: the first int32 of a chromosome's data; the index says it for indexed tracks)."""
     index = read_track_index(track_dir)
     if index is not None:
-        if index[1] == "array":
-            raise FormatError("array tracks are not supported by this build")
         return index[1]
     for c in chrom_names:
         f = os.path.join(track_dir, c)
@@ -134,6 +132,8 @@ def track_type(track_dir, chrom_names):
                 return "dense"
             if sig == -1:
                 return "sparse"
+            if sig == ARRAY_SIGNATURE:
+                return "array"
             raise FormatError("unsupported track type (signature %d)" % sig)
     return None
 
@@ -154,6 +154,108 @@ def read_sparse_chrom(track_dir, chrom_name, chromid, index=None):
     n = (len(raw) - 4) // SPARSE_REC.itemsize
     rec = raw[4:4 + n * SPARSE_REC.itemsize].view(SPARSE_REC)
     return rec["s"].copy(), rec["e"].copy(), rec["v"].copy()
+
+
+# ---- array tracks (src/GenomeTrackArrays.cpp) -----------------------------------------------------------------------------------
+ARRAY_SIGNATURE = -8  # GenomeTrack::FORMAT_SIGNATURES[ARRAYS], src/GenomeTrack.cpp:23
+SLICE_FUNCS = ("avg", "min", "max", "stddev", "sum", "quantile")  # GenomeTrackArrays::SLICE_FUNCTION_NAMES
+
+
+def read_array_chrom(track_dir, chrom_name, chromid, index=None):
+    """One chromosome of an array track: (start int64[n], end int64[n], rec_first int64[n + 1], vals float32[m], cols uint32[m]) -- every
+    record's stored (value, column) pairs back to back (NaN values are never stored, src/GenomeTrackArrays.cpp:281-298). Layout: int32
+    signature, int64 position of the interval table, the records' {uint32 count, count x {float32, uint32}} blocks, then the table
+    {uint64 n, n x {int64 start, int64 end, int64 position of the record's block}}; positions are relative to the chromosome's data
+    (:141-200)."""
+    raw = _chrom_blob(track_dir, chrom_name, chromid, index)
+    empty = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.float32), np.zeros(0, np.uint32))
+    if raw is None or len(raw) < 12:
+        return empty
+    if int(raw[:4].view(np.int32)[0]) != ARRAY_SIGNATURE:
+        raise FormatError("Invalid arrays track header in %s" % os.path.join(track_dir, chrom_name))
+    ipos = int(raw[4:12].view(np.int64)[0])
+    n = int(raw[ipos:ipos + 8].view(np.uint64)[0])
+    tab = raw[ipos + 8:ipos + 8 + 24 * n].view(np.int64).reshape(n, 3)
+    start, end, vpos = tab[:, 0].copy(), tab[:, 1].copy(), tab[:, 2]
+    if n and (np.any(start < 0) or np.any(start >= end) or np.any(start[1:] < end[:-1]) or np.any(vpos < 0) or np.any(vpos >= len(raw)) or np.any(np.diff(vpos) <= 0)):
+        raise FormatError("Invalid format of arrays track file %s" % os.path.join(track_dir, chrom_name))
+    counts = np.array([int(raw[p:p + 4].view(np.uint32)[0]) for p in vpos], dtype=np.int64)
+    rec_first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    vals, cols = np.empty(rec_first[-1], np.float32), np.empty(rec_first[-1], np.uint32)
+    for r, p in enumerate(vpos):
+        blk = raw[p + 4:p + 4 + 8 * counts[r]]
+        pair = blk.view(np.dtype([("v", "<f4"), ("i", "<u4")]))
+        vals[rec_first[r]:rec_first[r + 1]], cols[rec_first[r]:rec_first[r + 1]] = pair["v"], pair["i"]
+    return start, end, rec_first, vals, cols
+
+
+def array_slice_values(rec_first, vals, cols, slice_cols=None, func="avg", percentile=0.5):
+    """The value every record of an array track presents under gvtrack.array.slice(slice, func): GenomeTrackArrays::get_sliced_val
+    (src/GenomeTrackArrays.cpp:372-556), narrowed to float as its return type does. slice_cols None / empty = every stored value.
+    Accumulations run in double in column order; squares of the stddev are float products as in the reference (v * v on floats)."""
+    n = len(rec_first) - 1
+    out = np.full(n, np.nan, dtype=np.float32)
+    sl = None if slice_cols is None or len(slice_cols) == 0 else np.unique(np.asarray(slice_cols, dtype=np.uint32))
+    for r in range(n):
+        v, c = vals[rec_first[r]:rec_first[r + 1]], cols[rec_first[r]:rec_first[r + 1]]
+        if sl is not None:
+            keep = np.isin(c, sl)
+            order = np.argsort(c[keep], kind="stable")
+            v = v[keep][order]
+            v = v[~np.isnan(v)]
+            if func in ("avg", "sum", "min", "max", "quantile") and len(v) == 0:
+                continue
+        N = len(v)
+        with np.errstate(all="ignore"):
+            if func == "avg":
+                out[r] = np.float32(_seq_sum(v) / N) if N else np.float32(np.nan)
+            elif func == "sum":
+                out[r] = np.float32(_seq_sum(v))
+            elif func == "min":
+                out[r] = v.min() if N else np.float32(np.finfo(np.float32).max)
+            elif func == "max":
+                out[r] = v.max() if N else np.float32(-np.finfo(np.float32).max)
+            elif func == "stddev":
+                if sl is not None and N <= 1:
+                    continue
+                s, msq = _seq_sum(v), _seq_sum((v * v).astype(np.float32))
+                avg = s / N if N else np.nan
+                out[r] = np.float32(np.sqrt(msq / (N - 1) - (avg * avg) * (N / (N - 1)))) if N != 1 else np.float32(np.nan)
+            elif func == "quantile":
+                srt = np.sort(v)
+                idx = (N - 1) * min(max(percentile, 0.0), 1.0)  # StreamPercentiler exact regime, src/StreamPercentiler.h:191-217
+                i1, i2 = int(np.floor(idx)), int(np.ceil(idx))
+                w = idx - i1
+                out[r] = np.float32(float(srt[i1]) * (1.0 - w) + float(srt[i2]) * w)
+            else:
+                raise FormatError("Unrecognized slice function %s" % func)
+    return out
+
+
+def _seq_sum(v):
+    s = 0.0
+    for x in v:
+        s += float(x)
+    return s
+
+
+def array_blob(start, end, rec_first, vals, cols):
+    """The bytes of one array-track chromosome (tests / synthetic databases); NaN values are dropped, records without values skipped."""
+    body, table = [], []
+    pos = 12
+    for r in range(len(start)):
+        v, c = np.asarray(vals[rec_first[r]:rec_first[r + 1]], np.float32), np.asarray(cols[rec_first[r]:rec_first[r + 1]], np.uint32)
+        keep = ~np.isnan(v)
+        if not keep.any():
+            continue
+        pair = np.empty(int(keep.sum()), dtype=np.dtype([("v", "<f4"), ("i", "<u4")]))
+        pair["v"], pair["i"] = v[keep], c[keep]
+        blk = np.uint32(len(pair)).tobytes() + pair.tobytes()
+        table.append((int(start[r]), int(end[r]), pos))
+        body.append(blk)
+        pos += len(blk)
+    tab = np.array(table, dtype=np.int64).reshape(-1, 3)
+    return np.int32(ARRAY_SIGNATURE).tobytes() + np.int64(pos).tobytes() + b"".join(body) + np.uint64(len(table)).tobytes() + tab.tobytes()
 
 
 def dense_blob(bins, bin_size):

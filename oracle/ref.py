@@ -119,6 +119,28 @@ def sparse_eval_ext(chrom_file, chromid, start, end, funcs=EXT_COLS, extra_funcs
     return _eval_ext(lib().ref_sparse_eval_ext, chrom_file, chromid, start, end, funcs, extra_funcs)
 
 
+SLICE_FUNCS = {"avg": 0, "min": 1, "max": 2, "stddev": 3, "sum": 4, "quantile": 5}
+
+
+def array_write(chrom_file, chromid, start, end, rec_first, vals, idx):
+    """An array-track chromosome file through the reference's own writer (GenomeTrackArrays::write_next_interval)."""
+    start, end = np.ascontiguousarray(start, dtype=np.int64), np.ascontiguousarray(end, dtype=np.int64)
+    rf = np.ascontiguousarray(rec_first, dtype=np.int64)
+    v, ix = np.ascontiguousarray(vals, dtype=np.float32), np.ascontiguousarray(idx, dtype=np.uint32)
+    _check(lib().ref_array_write(chrom_file.encode(), ctypes.c_int(chromid), c_i64(len(start)), _p(start), _p(end), _p(rf), _p(v), _p(ix)))
+
+
+def array_eval(chrom_file, chromid, start, end, slice_cols, slice_func="avg", slice_percentile=0.5, funcs=("avg",), percentile=0.5):
+    """GenomeTrackArrays::read_interval with a slice / slice function set (gvtrack.array.slice)."""
+    start, end = np.ascontiguousarray(start, dtype=np.int64), np.ascontiguousarray(end, dtype=np.int64)
+    sl = np.ascontiguousarray(slice_cols, dtype=np.uint32)
+    out = np.empty((len(start), len(COLS)), dtype=np.float32)
+    _check(lib().ref_array_eval(chrom_file.encode(), ctypes.c_int(chromid), ctypes.c_int(len(sl)), _p(sl), ctypes.c_int(SLICE_FUNCS[slice_func]),
+                                ctypes.c_double(slice_percentile), ctypes.c_uint32(_mask(funcs)), ctypes.c_int(int("quantile" in funcs)),
+                                ctypes.c_double(percentile), c_i64(len(start)), _p(start), _p(end), _p(out)))
+    return {f: out[:, COLS.index(f)].astype(np.float64) for f in funcs}
+
+
 def gquantiles(vals, percentiles):
     v = np.ascontiguousarray(vals, dtype=np.float64)
     p = np.ascontiguousarray(percentiles, dtype=np.float64)

@@ -26,6 +26,7 @@
 
 #include "GenomeTrackFixedBin.h"
 #include "GenomeTrackSparse.h"
+#include "GenomeTrackArrays.h"
 #include "StreamPercentiler.h"
 #include "BinFinder.h"
 #include "GenomeChromKey.h"
@@ -158,6 +159,46 @@ extern "C" int ref_sparse_eval_ext(const char *chrom_file, int chromid, uint32_t
 	t.init_read(chrom_file, chromid);
 	register_funcs(t, func_mask, 0, 0);
 	eval_ext(t, chromid, func_mask, n, start, end, out);
+	return 0;
+	REF_CATCH
+}
+
+// Array tracks (src/GenomeTrackArrays.{h,cpp}): written by the reference's own writer, read back through its own reader with a slice and a
+// slice function set (gvtrack.array.slice). vals / idx = the records' (value, column) pairs back to back, rec_first[nrec + 1] their offsets.
+extern "C" int ref_array_write(const char *chrom_file, int chromid, int64_t nrec, const int64_t *start, const int64_t *end, const int64_t *rec_first,
+							   const float *vals, const uint32_t *idx)
+{
+	REF_TRY
+	GenomeTrackArrays t;
+	t.init_write(chrom_file, chromid);
+	for (int64_t r = 0; r < nrec; ++r) {
+		GenomeTrackArrays::ArrayVals av;
+		for (int64_t k = rec_first[r]; k < rec_first[r + 1]; ++k)
+			av.push_back(GenomeTrackArrays::ArrayVal(vals[k], idx[k]));
+		t.write_next_interval(GInterval(chromid, start[r], end[r], 0), av.begin(), av.end());
+	}
+	return 0;
+	REF_CATCH
+}
+
+// slice_func: GenomeTrackArrays::SliceFunctions (0 avg, 1 min, 2 max, 3 stddev, 4 sum, 5 quantile); out as ref_dense_eval (n x NUM_COLS)
+extern "C" int ref_array_eval(const char *chrom_file, int chromid, int nslice, const uint32_t *slice, int slice_func, double slice_percentile,
+							  uint32_t func_mask, int use_quantile, double percentile, int64_t n, const int64_t *start, const int64_t *end, float *out)
+{
+	REF_TRY
+	GenomeTrackArrays t;
+	t.init_read(chrom_file, chromid);
+	std::vector<unsigned> sl(slice, slice + nslice);
+	if (slice_func == GenomeTrackArrays::S_QUANTILE)
+		t.set_slice_quantile(slice_percentile, 1000000, 100000, 100000, sl);
+	else
+		t.set_slice_function((GenomeTrackArrays::SliceFunctions)slice_func, sl);
+	register_funcs(t, func_mask, use_quantile, 1000000);
+	for (int64_t i = 0; i < n; ++i) {
+		GInterval iv(chromid, start[i], end[i], 0);
+		t.read_interval(iv);
+		collect(t, func_mask, use_quantile, percentile, out + i * NUM_COLS);
+	}
 	return 0;
 	REF_CATCH
 }

@@ -92,3 +92,37 @@ def test_the_reference_reads_what_we_write(db):
     gidx = formats.read_genome_index(os.path.join(db["root"], "seq"))
     assert gidx[2][0] == "chrX" and gidx[2][2] == SIZES[2]
     assert np.array_equal(formats.read_seq_chrom(os.path.join(db["root"], "seq"), "chrX", 2, gidx), db["seq"][2])
+
+
+def test_array_tracks_against_the_reference(tmp_path):
+    """Array tracks (src/GenomeTrackArrays.cpp): files written by the reference's own writer are parsed by formats.read_array_chrom, and
+    the per-record value under a slice / slice function (array_slice_values) followed by the sparse-track arithmetic reproduces what the
+    reference's reader returns for avg / min / max / sum / nearest / stddev of windows; our writer's bytes equal the reference's."""
+    if not ref.available():
+        pytest.skip("compiled reference not present")
+    rng = np.random.default_rng(21)
+    size, nrec, ncol = 200_000, 400, 12
+    start = np.sort(rng.choice(size // 50 - 2, nrec, replace=False)).astype(np.int64) * 50
+    end = start + rng.integers(1, 50, nrec)
+    counts = rng.integers(1, ncol + 1, nrec)
+    rec_first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    cols = np.concatenate([np.sort(rng.choice(ncol, k, replace=False)) for k in counts]).astype(np.uint32)
+    vals = rng.normal(size=len(cols)).astype(np.float32)
+    d = tmp_path / "arr.track"
+    os.makedirs(d)
+    path = str(d / "chr1")
+    ref.array_write(path, 0, start, end, rec_first, vals, cols)
+    assert open(path, "rb").read() == formats.array_blob(start, end, rec_first, vals, cols), "our writer == the reference's bytes"
+    assert formats.track_type(str(d), ["chr1"]) == "array"
+    s2, e2, rf2, v2, c2 = formats.read_array_chrom(str(d), "chr1", 0)
+    assert np.array_equal(s2, start) and np.array_equal(e2, end) and np.array_equal(rf2, rec_first) and np.array_equal(v2, vals) and np.array_equal(c2, cols)
+    ws = np.sort(rng.integers(0, size - 3000, 500)).astype(np.int64)
+    we = ws + rng.integers(1, 3000, 500)
+    for slice_cols in ([], [0, 3, 4, 9], [11], [2, 5]):
+        for sfunc, sp in (("avg", 0.5), ("min", 0.5), ("max", 0.5), ("sum", 0.5), ("stddev", 0.5), ("quantile", 0.3)):
+            rec_val = formats.array_slice_values(rec_first, vals, cols, slice_cols, sfunc, sp)
+            names = ("avg", "min", "max", "sum", "nearest", "stddev")
+            exp = ref.array_eval(path, 0, ws, we, slice_cols, sfunc, sp, funcs=names)
+            got = port.sparse_window(start, end, rec_val, size, ws, we, 0, 0, 0.5, funcs=names)
+            for f in names:
+                np.testing.assert_allclose(got[f], exp[f], rtol=2e-6, atol=1e-6, equal_nan=True, err_msg="slice %s %s -> %s" % (slice_cols, sfunc, f))

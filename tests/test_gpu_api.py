@@ -423,3 +423,56 @@ def test_value_based_vtracks(db):
         db.gvtrack_create("vb_bad", bad, "avg")
     for f in names + ("q", "cov"):
         db.gvtrack_rm("vb_" + f)
+
+
+def test_array_track_slices(tmp_path):
+    """An array track (src/GenomeTrackArrays.cpp) under gvtrack.array.slice: the per-record fold on the host, the window functions on the
+    device; expected values from the sparse restatement over the folded records (tests/test_formats.py pins the fold and the file format
+    to the reference's own reader / writer)."""
+    import os
+    import shutil
+    from misha_b200 import formats
+    root = str(tmp_path / "db")
+    shutil.copytree(TESTDB, root)
+    rng = np.random.default_rng(31)
+    ncol = 8
+    recs = {}
+    for cid, (c, size) in enumerate(CHROMS):
+        n = 300
+        st = np.sort(rng.choice(size // 100 - 2, n, replace=False)).astype(np.int64) * 100
+        en = st + rng.integers(1, 100, n)
+        counts = rng.integers(1, ncol + 1, n)
+        rf = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        cols = np.concatenate([np.sort(rng.choice(ncol, k, replace=False)) for k in counts]).astype(np.uint32)
+        vals = rng.normal(size=len(cols)).astype(np.float32)
+        recs[cid] = (st, en, rf, vals, cols)
+    d = os.path.join(root, "tracks", "arr.track")
+    formats.write_indexed_track(d, "array", {cid: formats.array_blob(*recs[cid]) for cid in recs})  # the indexed layout of an array track
+    db2 = api.gdb_init(root)
+    try:
+        assert db2._track_type("arr") == "array"
+        db2.gvtrack_create("a_all", "arr", "avg")
+        db2.gvtrack_create("a_max", "arr", "max")
+        db2.gvtrack_array_slice("a_max", [1, 4, 6], "sum")
+        db2.gvtrack_create("a_q", "arr", "nearest")
+        db2.gvtrack_array_slice("a_q", [0, 2, 3, 7], "quantile", 0.25)
+        db2.gvtrack_iterator("a_q", sshift=-2000, eshift=2000)
+        iv = db2.gintervals_all()
+        got = db2.gextract("a_all", "a_max", "a_q", intervals=iv, iterator=5000)
+        off = 0
+        for cid, (c, size) in enumerate(CHROMS):
+            st, en, rf, vals, cols = recs[cid]
+            s = np.arange(0, size, 5000, dtype=np.int64)
+            e = np.minimum(s + 5000, size)
+            n = len(s)
+            for name, sl, sf, sp, f, ss, es in (("a_all", None, "avg", 0.5, "avg", 0, 0), ("a_max", [1, 4, 6], "sum", 0.5, "max", 0, 0),
+                                                ("a_q", [0, 2, 3, 7], "quantile", 0.25, "nearest", -2000, 2000)):
+                rv = formats.array_slice_values(rf, vals, cols, sl, sf, sp)
+                exp = port.sparse_window(st, en, rv, size, s, e, ss, es, 0.5, funcs=(f,))[f]
+                assert_same(got[name][off:off + n], exp, "%s %s" % (c, name))
+            off += n
+        with pytest.raises(api.MishaError, match="array tracks only"):
+            db2.gvtrack_create("d", "dense_track", "avg")
+            db2.gvtrack_array_slice("d", [0])
+    finally:
+        db2.close()
