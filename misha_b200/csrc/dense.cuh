@@ -33,6 +33,7 @@ struct DenseChrom {
 	// fewer than 2^MG_ST_LEVELS full groups is two lookups
 	const float *smax[MG_ST_LEVELS];
 	const float *smin[MG_ST_LEVELS];
+	int64_t st_pitch; // smax[j] = smax[0] + j * st_pitch for every level that exists (one slab per extremum)
 	int64_t ngroups;
 	const uint2 *wm;          // wavelet matrix over RANK keys, wm_levels x wm_blocks units {ones before, 32 bits}
 	const uint32_t *wm_zeros; // zeros per level
@@ -86,6 +87,7 @@ struct DenseQuery {
 	uint32_t bin_size;
 	double *out[MG_NUM_FUNCS]; // one column per function (null = not requested); MG_QUANTILE unused here
 	uint64_t bin_magic; // ceil(2^64 / bin_size): floor(x / bin_size) == umul64hi(x, bin_magic) for x < 2^32 (0 when bin_size == 1)
+	uint32_t bin_magic32, bin_shift32; // floor(x / bin_size) == __umulhi(x, bin_magic32) >> bin_shift32 for x < 2^31 (bin_size > 1)
 	uint32_t pos_rel; // bit f set: position function f is reported relative to the window start
 	uint32_t out_mask; // bit f set: out[f] is requested
 	uint32_t generic_mask; // bit f set: function f follows the reference's generic read_interval path (MG_FUNC_GENERIC)
@@ -103,7 +105,10 @@ struct DenseQuery {
 	const float *inl_vals[MG_INL_CHROMS];
 	const Pref *inl_p8[MG_INL_CHROMS];
 	const uint8_t *inl_bw[MG_INL_CHROMS];
+	const float *inl_smax[MG_INL_CHROMS], *inl_smin[MG_INL_CHROMS]; // sparse-table slabs (null until the min / max group exists)
+	uint32_t inl_stpitch[MG_INL_CHROMS];
 };
+static_assert(sizeof(DenseQuery) <= 4096, "kernel parameters");
 
 // ------------------------------------------------------------------------------------------------------------
 // Staging. Tile = 256 threads x 8 bins.
@@ -303,12 +308,28 @@ __device__ __forceinline__ bool mg_dense_win(const DenseQuery &q, int64_t row, D
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// p8 entries from the per-bin prefix the staging pass produces (which is then released)
-__global__ void __launch_bounds__(256) k_p8_build(const Pref *__restrict__ pref, int64_t nbins, Pref *__restrict__ p8, int64_t nentries)
+// p8 entries from the per-bin prefix the staging pass produces (which is then released). The count word's top 16 bits say which bins
+// hold no value in the entry's own group of 8 (bits 48-55: bin 8 g + j -> bit j) and in the group before it (bits 56-63): a window's two
+// partial groups are counted from the two entries it loads anyway, before any bin has arrived.
+// (Measured and dropped: entries per 16 bins for k_dense_thin -- half the prefix bytes, 0.155 GB of the C3 step's 1.97, but 16-bin partial
+// groups: 0.386 -> 0.409 ms. The step pays for instructions as it pays for bytes.)
+#define MG_P8_CNT_BITS 48
+__device__ __forceinline__ uint32_t mg_nan_bits8(const float *__restrict__ v)
+{
+	const float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
+	return (a.x != a.x ? 1u : 0u) | (a.y != a.y ? 2u : 0u) | (a.z != a.z ? 4u : 0u) | (a.w != a.w ? 8u : 0u) | (b.x != b.x ? 16u : 0u) |
+		   (b.y != b.y ? 32u : 0u) | (b.z != b.z ? 64u : 0u) | (b.w != b.w ? 128u : 0u);
+}
+__global__ void __launch_bounds__(256) k_p8_build(const Pref *__restrict__ pref, const float *__restrict__ vals /* padded with a NaN group */, int64_t nbins,
+												  Pref *__restrict__ p8, int64_t nentries)
 {
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (g < nentries)
-		p8[g] = pref[min(g * 8, nbins)];
+	if (g < nentries) {
+		Pref p = pref[min(g * 8, nbins)];
+		const unsigned long long cur = mg_nan_bits8(vals + 8 * g), prev = g > 0 ? mg_nan_bits8(vals + 8 * (g - 1)) : 0xffull;
+		p.cnt = (long long)((unsigned long long)p.cnt | (cur << MG_P8_CNT_BITS) | (prev << (MG_P8_CNT_BITS + 8)));
+		p8[g] = p;
+	}
 }
 
 #define MG_PREFIX_DIRECT_BINS 4
@@ -318,10 +339,9 @@ __device__ __forceinline__ Pref mg_ld_pref(const Pref *p)
 	const int4 r = __ldg(reinterpret_cast<const int4 *>(p)); // one 16-byte read-only load
 	Pref o;
 	o.sum = __hiloint2double(r.y, r.x);
-	o.cnt = (long long)(((unsigned long long)(unsigned)r.w << 32) | (unsigned)r.z);
+	o.cnt = (long long)(((unsigned long long)((unsigned)r.w & 0xffffu) << 32) | (unsigned)r.z);
 	return o;
 }
-
 // bins [lo, hi) of the aligned group of 8 starting at bin 8 g: one 32-byte sector. Sum in bin order (exact for the few
 // floats involved), non-NaN count, extrema.
 // x when it is a number and bit J of sel is set, else 0; counts it in n. Inline PTX: left to the compiler, the select moves behind

@@ -245,13 +245,29 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, con
 		}
 	}
 	m = __byte_perm(m, 0, 0x3120); // bytes (ranks 0-7, 16-23, 8-15, 24-31) -> rank order
-	for (uint32_t j = 0; j < k; ++j) // drop the k members below
-		m &= m - 1u;
-	const uint32_t j1 = __ffs(m) - 1;
+	// the (k + 1)-th member (k < 16, among the bucket's own 16 ranks): a bisection over the mask's low half by population counts -- the
+	// same four steps in every lane, where clearing k bits one by one runs as long as the warp's largest k
+	uint32_t j1 = 0, kk = k;
+	{
+		uint32_t c = __popc(m & 0xffu);
+		bool up = kk >= c;
+		kk = up ? kk - c : kk;
+		j1 = up ? 8u : 0u;
+		c = __popc((m >> j1) & 0xfu);
+		up = kk >= c;
+		kk = up ? kk - c : kk;
+		j1 = up ? j1 + 4u : j1;
+		c = __popc((m >> j1) & 0x3u);
+		up = kk >= c;
+		kk = up ? kk - c : kk;
+		j1 = up ? j1 + 2u : j1;
+		c = (m >> j1) & 1u;
+		j1 = kk >= c ? j1 + 1u : j1;
+	}
 	x1 = mg_bw_ld<GV>(vals_block + __ldg(pos + mg_bw_pos_slot(rank0 + j1)));
 	x2 = x1;
 	if (want2) {
-		m &= m - 1u;
+		m &= 0xfffffffeu << j1; // the members above
 		uint32_t rk = rank0 + (uint32_t)__ffs(m) - 1u;
 		if (!m) { // no member among the 31 ranks that follow: walk on (exists because k + 1 < n)
 			rk = rank0 + 2 * MG_BW_BUCKET;

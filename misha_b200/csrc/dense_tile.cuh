@@ -218,8 +218,8 @@ __device__ __forceinline__ void mg_tile_row(const DenseQuery &q, int64_t row, bo
 	if ((uint64_t)csize <= 0x7fffffffull - q.bin_size && q.bin_magic) { // every coordinate and bin of this chromosome fits 31 bits
 		const uint32_t nbins = inl ? q.inl_nbins[chrom] : (uint32_t)q.table[chrom].nbins;
 		const uint32_t a = (uint32_t)ws, b = (uint32_t)we + q.bin_size - 1u;
-		const uint32_t sb = (uint32_t)__umul64hi((uint64_t)a, q.bin_magic); // src/GenomeTrackFixedBin.cpp:675
-		uint32_t eb = (uint32_t)__umul64hi((uint64_t)b, q.bin_magic);       // :676
+		const uint32_t sb = __umulhi(a, q.bin_magic32) >> q.bin_shift32; // src/GenomeTrackFixedBin.cpp:675 (a, b < 2^31)
+		uint32_t eb = __umulhi(b, q.bin_magic32) >> q.bin_shift32;       // :676
 		eb = eb < nbins ? eb : nbins;                                      // read_bins_bulk clamp :1036-1041
 		r.sb = sb;
 		r.eb = eb;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(MG_TL_THREADS, (Q && WMAX && WMIN) ? 2 : 3) k_
 		s_abs = 0.f;
 	}
 	if (t < 8)
-		s_acc[t] = (t == 0 || t == 2) ? 0xffffffffu : 0u;
+		s_acc[t] = (t == 0 || t == 2 || t == 4) ? 0xffffffffu : 0u;
 
 	// ---- 1. the rows' windows; the tile's bin range, chromosome and record range ----
 	TileRow r;
@@ -570,6 +570,40 @@ __device__ __forceinline__ void mg_part8_smem(const float *__restrict__ svals /*
 	}
 }
 
+// the same with the selection already made: bit j of m = bin j of the group is inside the window and holds a value.
+// Inline PTX for the reason mg_take gives: a predicate from the mask bit and selects on the FLOAT, before the conversion to double.
+template <uint32_t J>
+__device__ __forceinline__ void mg_pick(float x, uint32_t m, float &zero_or_x, float &ninf_or_x, float &pinf_or_x)
+{
+	asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tand.b32 t, %4, %5;\n\tsetp.ne.u32 p, t, 0;\n\tselp.f32 %0, %3, 0f00000000, p;\n\t"
+		"selp.f32 %1, %3, 0fFF800000, p;\n\tselp.f32 %2, %3, 0f7F800000, p;\n\t}"
+		: "=f"(zero_or_x), "=f"(ninf_or_x), "=f"(pinf_or_x)
+		: "f"(x), "r"(m), "n"(1u << J));
+}
+template <bool SUM, bool MM>
+__device__ __forceinline__ void mg_part8_mask(const float *__restrict__ svals, uint32_t m, double &S, float &mx, float &mn)
+{
+	const float4 a = reinterpret_cast<const float4 *>(svals)[0], b = reinterpret_cast<const float4 *>(svals)[1];
+	float c[8], h[8], l[8];
+	mg_pick<0>(a.x, m, c[0], h[0], l[0]);
+	mg_pick<1>(a.y, m, c[1], h[1], l[1]);
+	mg_pick<2>(a.z, m, c[2], h[2], l[2]);
+	mg_pick<3>(a.w, m, c[3], h[3], l[3]);
+	mg_pick<4>(b.x, m, c[4], h[4], l[4]);
+	mg_pick<5>(b.y, m, c[5], h[5], l[5]);
+	mg_pick<6>(b.z, m, c[6], h[6], l[6]);
+	mg_pick<7>(b.w, m, c[7], h[7], l[7]);
+	if (SUM) // bin order
+		S = (((((((S + (double)c[0]) + (double)c[1]) + (double)c[2]) + (double)c[3]) + (double)c[4]) + (double)c[5]) + (double)c[6]) + (double)c[7];
+	if (MM) {
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			mx = fmaxf(mx, h[j]);
+			mn = fminf(mn, l[j]);
+		}
+	}
+}
+
 template <bool SUM, bool WMAX, bool WMIN, bool Q>
 __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __grid_constant__ DenseQuery q)
 {
@@ -583,30 +617,36 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	if (t == 0)
 		mg_mbar_init(&s_bar, 1);
 	if (t < 8)
-		s_acc[t] = (t == 0 || t == 2) ? 0xffffffffu : 0u;
+		s_acc[t] = (t == 0 || t == 2 || t == 4) ? 0xffffffffu : 0u;
 
 	// ---- 1. the rows' windows; the tile's bin range, chromosome and record range ----
 	TileRow r;
 	mg_tile_row(q, q.first + i, live, r);
 	const uint32_t sb = r.sb, eb = r.eb, nb = eb - sb;
 	const bool ok = r.ok, reg = r.reg;
+	const uint32_t g0 = sb >> 3, g1 = reg ? (eb - 1u) >> 3 : 0u;
+	const bool multi = reg && g0 != g1;
+	const uint32_t gs = g0 + 1, len = multi ? g1 - gs : 0u; // the whole groups of 8 inside the window: [gs, g1)
 	__syncthreads(); // the accumulators are initialised
 	{
 		const uint32_t r_cmin = __reduce_min_sync(0xffffffffu, reg ? r.chrom : 0xffffffffu), r_cmax = __reduce_max_sync(0xffffffffu, r.chrom);
 		const uint32_t r_bmin = __reduce_min_sync(0xffffffffu, reg ? sb : 0xffffffffu), r_bmax = __reduce_max_sync(0xffffffffu, eb);
+		const uint32_t r_lmin = MM ? __reduce_min_sync(0xffffffffu, len > 0 ? len : 0xffffffffu) : 0u;
 		const bool r_bad = __any_sync(0xffffffffu, r.bad || (Q && nb > MG_BW_S));
 		if (lane == 0) {
 			atomicMin(&s_acc[0], r_cmin);
 			atomicMax(&s_acc[1], r_cmax);
 			atomicMin(&s_acc[2], r_bmin);
 			atomicMax(&s_acc[3], r_bmax);
+			if (MM)
+				atomicMin(&s_acc[4], r_lmin);
 			if (r_bad)
 				s_acc[6] = 1u;
 		}
 	}
 	__syncthreads();
 	const uint4 acc0 = *reinterpret_cast<const uint4 *>(s_acc);
-	const uint32_t cmin = acc0.x, cmax = acc0.y, bmin = acc0.z, bmax = acc0.w, anybad = s_acc[6];
+	const uint32_t cmin = acc0.x, cmax = acc0.y, bmin = acc0.z, bmax = acc0.w, lmin = s_acc[4], anybad = s_acc[6];
 	const bool anyreg = cmin != 0xffffffffu;
 	const uint32_t b0 = bmin & ~7u;                                // group-aligned start of the staged bins
 	const uint32_t span8 = anyreg ? ((bmax - b0 + 7u) & ~7u) : 0u; // staged bins: whole groups of 8 (the track is padded with NaN)
@@ -638,26 +678,50 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 				mg_bulk_g2s(s_lv + sl * MG_BW_STAGE_BYTES, src + (size_t)sl * MG_BW_RECORD_BYTES, MG_BW_STAGE_BYTES, &s_bar);
 		}
 	}
-	// ---- 3. what the whole groups of the window contribute, from the chromosome's structures: loads that fly with the copies ----
-	const uint32_t g0 = sb >> 3, g1 = reg ? (eb - 1u) >> 3 : 0u;
-	const bool multi = reg && g0 != g1;
-	Pref pa, pb;
-	pa.sum = pb.sum = 0;
-	pa.cnt = pb.cnt = 0;
-	float tmx = __int_as_float(0xff800000), tmn = __int_as_float(0x7f800000);
-	if (multi) {
-		pa = mg_ld_pref(p8_base + g0 + 1);
-		pb = mg_ld_pref(p8_base + g1);
-		const uint32_t gs = g0 + 1, len = g1 - gs;
-		if (MM && len > 0) { // len < 2^MG_ST_LEVELS: the tile holds MG_TL_CAP bins
-			const int j = 31 - __clz((int)len);
-			if (WMAX)
-				tmx = fmaxf(__ldg(ch->smax[j] + gs), __ldg(ch->smax[j] + g1 - (1u << j)));
-			if (WMIN)
-				tmn = fminf(__ldg(ch->smin[j] + gs), __ldg(ch->smin[j] + g1 - (1u << j)));
+	// what the whole groups of the window contribute, from the chromosome's structures: loads that fly with the copies (their values are
+	// looked at after the wait). Sums and counts: two p8 entries. Extrema: the sparse table, at ONE level for the whole tile -- the level of
+	// the tile's shortest run, 2 to 4 lookups a row: rows whose runs straddle a power of two (C3: 63 - 65 groups) would otherwise stream
+	// two levels of the table through the device.
+	int4 pa_raw = make_int4(0, 0, 0, (int)0xffff0000u), pb_raw = pa_raw; // entry g0 + 1 also says which bins of group g0 hold no value
+	float mx0 = __int_as_float(0xff800000), mx1 = mx0, mx2 = mx0, mx3 = mx0;
+	float mn0 = __int_as_float(0x7f800000), mn1 = mn0, mn2 = mn0, mn3 = mn0;
+	double abs_sum = 0; // scale of the cancellation guard below
+	if (reg) {
+		pa_raw = __ldg(reinterpret_cast<const int4 *>(p8_base + g0 + 1));
+		if (multi) {
+			pb_raw = __ldg(reinterpret_cast<const int4 *>(p8_base + g1));
+			if (MM && len > 0) { // lmin <= len < 2^MG_ST_LEVELS: the tile holds MG_TL_CAP bins
+				int j = 31 - __clz((int)lmin);
+				uint32_t nl = (len + (1u << j) - 1u) >> j;
+				if (nl > 4u) { // far longer than the tile's shortest: the row's own level
+					j = 31 - __clz((int)len);
+					nl = 2u;
+				}
+				const uint32_t w = 1u << j;
+				// the level's address from the kernel parameters when they hold the table: no pointer load ahead of the entries
+				if (WMAX) {
+					const float *lvl = inl ? q.inl_smax[cmin] + (size_t)j * q.inl_stpitch[cmin] : ch->smax[j];
+					mx0 = __ldg(lvl + gs);
+					mx1 = __ldg(lvl + g1 - w);
+					if (nl > 2u)
+						mx2 = __ldg(lvl + gs + w);
+					if (nl > 3u)
+						mx3 = __ldg(lvl + gs + 2u * w);
+				}
+				if (WMIN) {
+					const float *lvl = inl ? q.inl_smin[cmin] + (size_t)j * q.inl_stpitch[cmin] : ch->smin[j];
+					mn0 = __ldg(lvl + gs);
+					mn1 = __ldg(lvl + g1 - w);
+					if (nl > 2u)
+						mn2 = __ldg(lvl + gs + w);
+					if (nl > 3u)
+						mn3 = __ldg(lvl + gs + 2u * w);
+				}
+			}
+			if (SUM)
+				abs_sum = ch->abs_sum;
 		}
 	}
-	const double abs_sum = SUM && multi ? ch->abs_sum : 0.; // scale of the cancellation guard below: loaded with the rest, before the wait
 	// one warp watches the barrier, the others park at the thread-block barrier (no issue slots spent on polling)
 	if (warp == 0)
 		mg_mbar_wait(&s_bar, 0);
@@ -665,28 +729,27 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	if (!live)
 		return;
 
-	// ---- 4. the row ----
+	// ---- 3. the row ----
+	// the window's values are counted from the two entries: their difference and the no-value masks of the two partial groups
+	const double pa_sum = __hiloint2double(pa_raw.y, pa_raw.x), pb_sum = __hiloint2double(pb_raw.y, pb_raw.x);
+	const uint32_t sel_h = reg ? (((1u << (multi ? 8u : eb - 8u * g0)) - 1u) & ~((1u << (sb & 7u)) - 1u)) : 0u; // bins of group g0 inside the window
+	const uint32_t sel_t = multi ? (1u << (eb - 8u * g1)) - 1u : 0u;                                            // bins of group g1
+	const uint32_t mh = sel_h & ~((uint32_t)pa_raw.w >> 24), mt = sel_t & ~((uint32_t)pb_raw.w >> 16); // ... that hold a value
+	const uint32_t n = __popc(mh) + __popc(mt) + (multi ? (uint32_t)pb_raw.z - (uint32_t)pa_raw.z : 0u);
 	const uint32_t om = q.out_mask; // bit f: column f is requested
 	double avg = mg_nan(), sum = mg_nan(), size = mg_nan(), exists = mg_nan(), mn = mg_nan(), mx = mg_nan();
-	uint32_t n = 0;
 	if (ok) {
 		size = 0;
 		exists = 0;
 	}
-	if (reg) {
+	if (reg && (SUM || MM)) {
 		double S = 0;
-		int nh = 0, nt = 0;
-		float pmx = tmx, pmn = tmn;
-		const float *gh = s_vals + (8u * g0 - b0);
-		if (!multi) {
-			mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), (int)(eb - 8u * g0), S, nh, pmx, pmn);
-			n = (uint32_t)nh;
-		} else {
+		float pmx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), pmn = fminf(fminf(mn0, mn1), fminf(mn2, mn3));
+		mg_part8_mask<SUM, MM>(s_vals + (8u * g0 - b0), mh, S, pmx, pmn);
+		if (multi) {
 			double St = 0;
-			mg_part8_smem<SUM, MM>(gh, (int)(sb & 7u), 8, S, nh, pmx, pmn);
-			mg_part8_smem<SUM, MM>(s_vals + (8u * g1 - b0), 0, (int)(eb - 8u * g1), St, nt, pmx, pmn);
-			S = (S + (pb.sum - pa.sum)) + St;
-			n = (uint32_t)nh + (uint32_t)(pb.cnt - pa.cnt) + (uint32_t)nt;
+			mg_part8_mask<SUM, MM>(s_vals + (8u * g1 - b0), mt, St, pmx, pmn);
+			S = (S + (pb_sum - pa_sum)) + St;
 			// the prefix difference has lost too many digits against the chromosome's running sum: the bins in order, from the staged copy
 			if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
 				S = 0;

@@ -370,27 +370,37 @@ static int mg_build_ext(mg_ctx *ctx, mg_dense *t, DenseChrom &dc, MgArena &arena
 	StagePhase ph("sparse tables");
 	const int64_t ng = mg_div_up(nbins > 0 ? nbins : 1, 8);
 	dc.ngroups = ng;
+	// every level in ONE slab per extremum, pitch entries apart (level 0 is a copy of pyramid level 0): a kernel that holds the slab's base and
+	// the pitch in its parameters (DenseQuery::inl_smax) reaches smax[j][g] without first loading the level's pointer from the table
+	int nlev = 1;
+	while (nlev < MG_ST_LEVELS && (1ll << nlev) <= ng)
+		++nlev;
+	const int64_t pitch = (ng + 31) / 32 * 32;
+	float *slab_max = nullptr, *slab_min = nullptr;
+	if (mg_group_alloc(ctx, t, MG_G_EXT, pitch * nlev, &slab_max, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, pitch * nlev, &slab_min, &arena))
+		return 1;
 	if (!dc.pmax[0]) { // chromosomes of <= 8 bins have no pyramid level: build the single group entry
 		float *pmax = nullptr, *pmin = nullptr;
 		if (mg_group_alloc(ctx, t, MG_G_EXT, 16, &pmax, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, 16, &pmin, &arena))
 			return 1;
 		k_pyr_build<<<1, 256>>>(dc.vals, dc.vals, nbins, pmax, pmin, 16);
 		MG_LAUNCH_CHECK(ctx);
-		dc.smax[0] = pmax;
-		dc.smin[0] = pmin;
+		MG_CUDA(ctx, cudaMemcpyAsync(slab_max, pmax, sizeof(float) * ng, cudaMemcpyDeviceToDevice));
+		MG_CUDA(ctx, cudaMemcpyAsync(slab_min, pmin, sizeof(float) * ng, cudaMemcpyDeviceToDevice));
 	} else {
-		dc.smax[0] = dc.pmax[0];
-		dc.smin[0] = dc.pmin[0];
+		MG_CUDA(ctx, cudaMemcpyAsync(slab_max, dc.pmax[0], sizeof(float) * ng, cudaMemcpyDeviceToDevice));
+		MG_CUDA(ctx, cudaMemcpyAsync(slab_min, dc.pmin[0], sizeof(float) * ng, cudaMemcpyDeviceToDevice));
 	}
+	dc.smax[0] = slab_max;
+	dc.smin[0] = slab_min;
+	dc.st_pitch = pitch;
 	for (int j = 1; j < MG_ST_LEVELS; ++j) {
-		if ((1ll << j) > ng) { // never selected: a run of len groups uses level floor(log2 len)
+		if (j >= nlev) { // never selected: a run of len groups uses level floor(log2 len)
 			dc.smax[j] = dc.smax[j - 1];
 			dc.smin[j] = dc.smin[j - 1];
 			continue;
 		}
-		float *smax = nullptr, *smin = nullptr;
-		if (mg_group_alloc(ctx, t, MG_G_EXT, ng, &smax, &arena) || mg_group_alloc(ctx, t, MG_G_EXT, ng, &smin, &arena))
-			return 1;
+		float *smax = slab_max + pitch * j, *smin = slab_min + pitch * j;
 		k_st_build<<<(unsigned)mg_div_up(ng, 256), 256>>>(dc.smax[j - 1], dc.smin[j - 1], ng, 1ll << (j - 1), smax, smin);
 		MG_LAUNCH_CHECK(ctx);
 		dc.smax[j] = smax;
@@ -670,7 +680,7 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 	arena.chunk = (size_t)6 * (size_t)nbins + ((size_t)1 << 20);
 	float *vals = nullptr;
 	Pref *pref = nullptr;
-	const int64_t padded = (nbins + 7) / 8 * 8 + 8; // group-of-8 / float4-safe tail, NaN filled
+	const int64_t padded = (nbins + 15) / 16 * 16 + 16; // group-of-16 / float4-safe tail, NaN filled
 	if (mg_alloc_tracked(ctx, t->allocs, t->bytes, padded, &vals, &arena))
 		return 1;
 	MgScratch tmp(nullptr);
@@ -689,7 +699,7 @@ extern "C" int mg_dense_stage(mg_ctx *ctx, mg_dense *t, int chromid, const float
 		Pref *p8 = nullptr;
 		if (mg_alloc_tracked(ctx, t->allocs, t->bytes, nent, &p8, &arena))
 			return 1;
-		k_p8_build<<<(unsigned)mg_div_up(nent, 256), 256>>>(pref, nbins, p8, nent);
+		k_p8_build<<<(unsigned)mg_div_up(nent, 256), 256>>>(pref, vals, nbins, p8, nent);
 		MG_LAUNCH_CHECK(ctx);
 		dc.p8 = p8;
 	}
@@ -893,6 +903,13 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 	q.chrom_sizes = ctx->d_chrom_sizes;
 	q.bin_size = t->bin_size;
 	q.bin_magic = t->bin_size > 1 ? ~0ull / t->bin_size + 1 : 0;
+	if (t->bin_size > 1) { // 2^(s-1) < d <= 2^s, m = floor(2^(31+s) / d) + 1 (< 2^32): floor(x / d) == (x m) >> (31 + s) for every x < 2^31
+		uint32_t sft = 1;
+		while ((1ull << sft) < t->bin_size)
+			++sft;
+		q.bin_magic32 = (uint32_t)(((1ull << (31 + sft)) / t->bin_size) + 1ull);
+		q.bin_shift32 = sft - 1;
+	}
 	q.use_bw = ctx->block_wm ? 1 : 0;
 	q.stage = ctx->stage_records ? 1 : 0;
 	q.prefetch = ctx->prefetch ? 1 : 0;
@@ -933,6 +950,9 @@ static int mg_fill_dense_query(mg_ctx *ctx, const mg_dense *t, const mg_rows *ro
 				q.inl_vals[c] = t->h_table[c].vals;
 				q.inl_p8[c] = t->h_table[c].p8;
 				q.inl_bw[c] = t->h_table[c].bw;
+				q.inl_smax[c] = t->h_table[c].smax[0];
+				q.inl_smin[c] = t->h_table[c].smin[0];
+				q.inl_stpitch[c] = (uint32_t)t->h_table[c].st_pitch;
 			}
 		}
 	}
