@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--intervals", type=int, default=N_INTERVALS, help=argparse.SUPPRESS)  # smaller = NOT the named config
     ap.add_argument("--scale", type=float, default=1.0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    # development aid: one process on one GPU takes the rows rank R of W would take (where does a rank's time go?); NOT a bench line
+    ap.add_argument("--emulate-slice", default="", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -194,7 +196,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     numa = bind_to_gpu_cpus(local)
-    chroms, counts, mine = build_workload(args, rank, world)
+    if args.emulate_slice:
+        if args.emulate_slice.startswith("c:"):  # one whole chromosome
+            chroms, counts, _ = build_workload(args, 0, 1)
+            ci = int(args.emulate_slice[2:])
+            mine = [(ci, 0, int(counts[ci]))]
+        else:
+            er, ew = (int(x) for x in args.emulate_slice.split("/"))
+            chroms, counts, mine = build_workload(args, er, ew)
+    else:
+        chroms, counts, mine = build_workload(args, rank, world)
     sizes = [s for _, s in chroms]
     ctx = gpu.Context(sizes, device=local)
     stream = torch.cuda.current_stream().cuda_stream

@@ -204,15 +204,11 @@ __device__ __forceinline__ uint32_t mg_bw_count(const uint8_t *__restrict__ rec,
 	return (r - l) - (mg_bw_rank<true>(lv, r) - mg_bw_rank<true>(lv, l));
 }
 
-// k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l <= S; with want2 (k + 1 < n) also the
-// (k+1)-th. lv = the record's walked levels (global or staged), pos = the record's pos_of_rank in global memory, vals_block =
-// the track (or its staged copy) at the block's first bin.
-// G: where the levels live (true: global memory), GV: where the bins live
-template <bool G, bool GV = G>
-__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint16_t *__restrict__ pos, const float *__restrict__ vals_block, uint32_t l,
-											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
+// the walk: the bucket of MG_BW_BUCKET consecutive ranks that holds the k-th smallest rank of the window (returned: its first rank) and how
+// many of the window's members in that bucket lie below it (k on return)
+template <bool G>
+__device__ __forceinline__ uint32_t mg_bw_walk(const uint8_t *__restrict__ lv, uint32_t l, uint32_t r, uint32_t &k)
 {
-	const uint32_t l0 = l, len = r - l;
 	uint32_t bucket = 0;
 #pragma unroll
 	for (int level = 0; level < MG_BW_WL; ++level, lv += MG_BW_LEVEL_BYTES) {
@@ -224,11 +220,14 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, con
 		k = one ? k - nz : k;
 		bucket = (bucket << 1) | (one ? 1u : 0u);
 	}
-	// the bucket's 16 ranks hold r - l >= k + 1 window members; the k-th smallest is the (k+1)-th of them in rank order, its
-	// successor the next member, here or in the ranks that follow. Membership of two positions at once: with p < B <= 2^14 in either
-	// half of a word, p + (2^15 - l0) has bit 15 set iff p >= l0 and p + (2^15 - l0 - len) has it clear iff p < l0 + len, neither
-	// addition carries into the other half.
-	const uint32_t rank0 = bucket << MG_BW_BUCKET_BITS;
+	return bucket << MG_BW_BUCKET_BITS;
+}
+
+// which of the 32 ranks rank0 .. rank0 + 31 sit at positions inside the window [l0, l0 + len): bit j = rank rank0 + j. Membership of two
+// positions at once: with p < B <= 2^14 in either half of a word, p + (2^15 - l0) has bit 15 set iff p >= l0 and p + (2^15 - l0 - len)
+// has it clear iff p < l0 + len, neither addition carries into the other half.
+__device__ __forceinline__ uint32_t mg_bw_members(const uint16_t *__restrict__ pos, uint32_t rank0, uint32_t l0, uint32_t len)
+{
 	const uint4 *p4 = reinterpret_cast<const uint4 *>(pos + rank0);
 	const uint32_t addlo = (0x8000u - l0) * 0x10001u, addhi = (0x8000u - l0 - len) * 0x10001u;
 	uint32_t m = 0;
@@ -244,36 +243,60 @@ __device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, con
 			m |= g < 2 ? in >> (15 - j) : in >> (7 - j);
 		}
 	}
-	m = __byte_perm(m, 0, 0x3120); // bytes (ranks 0-7, 16-23, 8-15, 24-31) -> rank order
-	// the (k + 1)-th member (k < 16, among the bucket's own 16 ranks): a bisection over the mask's low half by population counts -- the
-	// same four steps in every lane, where clearing k bits one by one runs as long as the warp's largest k
-	uint32_t j1 = 0, kk = k;
-	{
-		uint32_t c = __popc(m & 0xffu);
-		bool up = kk >= c;
-		kk = up ? kk - c : kk;
-		j1 = up ? 8u : 0u;
-		c = __popc((m >> j1) & 0xfu);
-		up = kk >= c;
-		kk = up ? kk - c : kk;
-		j1 = up ? j1 + 4u : j1;
-		c = __popc((m >> j1) & 0x3u);
-		up = kk >= c;
-		kk = up ? kk - c : kk;
-		j1 = up ? j1 + 2u : j1;
-		c = (m >> j1) & 1u;
-		j1 = kk >= c ? j1 + 1u : j1;
-	}
+	return __byte_perm(m, 0, 0x3120); // bytes (ranks 0-7, 16-23, 8-15, 24-31) -> rank order
+}
+
+// the (k + 1)-th set bit among the low 16 of m (k < 16; it exists): a bisection by population counts -- the same four steps in every
+// lane, where clearing k bits one by one runs as long as the warp's largest k
+__device__ __forceinline__ uint32_t mg_bw_pick16(uint32_t m, uint32_t k)
+{
+	uint32_t c = __popc(m & 0xffu);
+	bool up = k >= c;
+	k = up ? k - c : k;
+	uint32_t j = up ? 8u : 0u;
+	c = __popc((m >> j) & 0xfu);
+	up = k >= c;
+	k = up ? k - c : k;
+	j = up ? j + 4u : j;
+	c = __popc((m >> j) & 0x3u);
+	up = k >= c;
+	k = up ? k - c : k;
+	j = up ? j + 2u : j;
+	c = (m >> j) & 1u;
+	return k >= c ? j + 1u : j;
+}
+
+// rank of the k-th smallest of the window by a walk of its own: what the successor search falls back to when the next member is not
+// among the 31 ranks behind the k-th -- windows with a handful of values in a block full of other values (a long run of NaN under the
+// window) have their members hundreds of ranks apart, and looking at pos_of_rank entry by entry is one dependent load per rank
+template <bool G>
+__device__ __noinline__ uint32_t mg_bw_rank_of_kth(const uint8_t *lv, const uint16_t *pos, uint32_t l, uint32_t r, uint32_t k)
+{
+	const uint32_t rank0 = mg_bw_walk<G>(lv, l, r, k);
+	return rank0 + mg_bw_pick16(mg_bw_members(pos, rank0, l, r - l), k);
+}
+
+// k-th smallest (0-based) non-NaN value of the block-local window [l, r), k < n <= r - l <= S; with want2 (k + 1 < n) also the
+// (k+1)-th. lv = the record's walked levels (global or staged), pos = the record's pos_of_rank in global memory, vals_block =
+// the track (or its staged copy) at the block's first bin.
+// G: where the levels live (true: global memory), GV: where the bins live
+template <bool G, bool GV = G>
+__device__ __forceinline__ void mg_bw_select(const uint8_t *__restrict__ lv, const uint16_t *__restrict__ pos, const float *__restrict__ vals_block, uint32_t l,
+											 uint32_t r, uint32_t k, bool want2, float &x1, float &x2)
+{
+	// the bucket's 16 ranks hold >= kb + 1 window members; the k-th smallest is the (kb + 1)-th of them in rank order, its successor the
+	// next member, here or in the ranks that follow
+	uint32_t kb = k;
+	const uint32_t rank0 = mg_bw_walk<G>(lv, l, r, kb);
+	uint32_t m = mg_bw_members(pos, rank0, l, r - l);
+	const uint32_t j1 = mg_bw_pick16(m, kb);
 	x1 = mg_bw_ld<GV>(vals_block + __ldg(pos + mg_bw_pos_slot(rank0 + j1)));
 	x2 = x1;
 	if (want2) {
 		m &= 0xfffffffeu << j1; // the members above
 		uint32_t rk = rank0 + (uint32_t)__ffs(m) - 1u;
-		if (!m) { // no member among the 31 ranks that follow: walk on (exists because k + 1 < n)
-			rk = rank0 + 2 * MG_BW_BUCKET;
-			while (rk < MG_BW_B - 1 && (uint32_t)__ldg(pos + mg_bw_pos_slot(rk)) - l0 >= len)
-				++rk;
-		}
+		if (!m) // none among the 31 ranks that follow (it exists: k + 1 < n)
+			rk = mg_bw_rank_of_kth<G>(lv, pos, l, r, k + 1u);
 		x2 = mg_bw_ld<GV>(vals_block + __ldg(pos + mg_bw_pos_slot(rk)));
 	}
 }

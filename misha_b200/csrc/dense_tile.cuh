@@ -604,13 +604,31 @@ __device__ __forceinline__ void mg_part8_mask(const float *__restrict__ svals, u
 	}
 }
 
+#ifdef MG_DBG_BLOCKTIME
+// development build only (tools/dbg_slow_blocks.py): the longest thread lifetime (ns) of every thread block of the last k_dense_thin launch
+__device__ unsigned long long g_dbg_blocktime[1 << 16];
+struct MgDbgTimer {
+	unsigned long long t0;
+	__device__ MgDbgTimer() { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
+	__device__ ~MgDbgTimer()
+	{
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (blockIdx.x < (1u << 16))
+			atomicMax(&g_dbg_blocktime[blockIdx.x], t1 - t0);
+	}
+};
+#endif
 template <bool SUM, bool WMAX, bool WMIN, bool Q>
 __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __grid_constant__ DenseQuery q)
 {
 	constexpr bool MM = WMAX || WMIN;
+#ifdef MG_DBG_BLOCKTIME
+	MgDbgTimer dbg_timer;
+#endif
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint64_t s_bar;
-	__shared__ __align__(16) uint32_t s_acc[8]; // chrom min, chrom max, min sbin, max ebin, -, -, any bad row, -
+	__shared__ __align__(16) uint32_t s_acc[8]; // chrom min, chrom max, min sbin, max ebin, shortest run of whole groups, -, any bad row, -
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	const int64_t i = (int64_t)blockIdx.x * MG_TL_THREADS + t;
 	const bool live = i < q.count;
@@ -753,6 +771,7 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 			// the prefix difference has lost too many digits against the chromosome's running sum: the bins in order, from the staged copy
 			if (SUM && g0 + 1 < g1 && n > 0 && fabs(S) < abs_sum * 1.4901161193847656e-08 /* 2^-26 */) {
 				S = 0;
+#pragma unroll 8
 				for (uint32_t b = sb - b0; b < eb - b0; ++b) {
 					const float v = s_vals[b];
 					if (v == v)

@@ -3001,3 +3001,17 @@ extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, 
 
 // ---- several devices behind one host thread ------------------------------------------------------------------------------
 #include "group.cuh"
+
+#ifdef MG_DBG_BLOCKTIME
+extern "C" int mg_dbg_blocktimes(unsigned long long *h_out, int n, int reset)
+{
+	if (h_out && cudaMemcpyFromSymbol(h_out, g_dbg_blocktime, sizeof(unsigned long long) * (size_t)n) != cudaSuccess)
+		return 1;
+	if (reset) {
+		void *p = nullptr;
+		if (cudaGetSymbolAddress(&p, g_dbg_blocktime) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned long long) << 16) != cudaSuccess)
+			return 1;
+	}
+	return 0;
+}
+#endif

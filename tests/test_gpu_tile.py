@@ -189,6 +189,35 @@ def test_unsorted_and_mixed_chromosomes(track):
     check(track, chrom[o], s[o], e[o], -5000, 5000, "sorted, seams")
 
 
+def test_windows_with_a_handful_of_values():
+    """A long run of NaN under the windows, every other bin of the block a number: a window's few values are hundreds of local ranks
+    apart, so the (k+1)-th smallest is found by a walk of its own (mg_bw_rank_of_kth), not behind the k-th in pos_of_rank."""
+    size = 600_000
+    n = -(-size // BIN)
+    rng = np.random.default_rng(77)
+    v = np.exp(rng.standard_normal(n)).astype(np.float32)
+    v[5000:5700] = np.nan   # longer than a +-5 kb window
+    v[12000:12490] = np.nan  # a little shorter: windows keep ~ 20 values from either side
+    ctx = gpu.Context([size])
+    try:
+        t = gpu.DenseTrack(ctx, BIN)
+        t.stage(0, v)
+        s = np.arange(4400 * BIN, 13200 * BIN, 7, dtype=np.int64)  # several rows per bin: sorted, every tile on the shared-memory path
+        e = s + 150
+        rows = ctx.rows_upload(np.zeros(len(s), np.int32), s, e)
+        for q in (0.0, 0.3, 0.5, 0.9, 1.0):
+            exp = port.dense_window(v, BIN, size, s, e, -5000, 5000, q, ("quantile", "size"))
+            for tk in (3, 1, 0):
+                ctx.set_option("tile_kernel", tk)
+                got = t.window(rows, [("quantile", q), "size"], -5000, 5000)
+                assert_same(got[0], exp["quantile"], "quantile %.1f, tile_kernel %d" % (q, tk))
+                assert_same(got[1], exp["size"], "size, tile_kernel %d" % tk)
+            few = (exp["size"] > 0) & (exp["size"] < 12)
+            assert few.sum() > 40  # the case is there
+    finally:
+        ctx.close()
+
+
 def test_edges(track):
     """Windows clamped at either chromosome end, rows without any bin (shifted out of range), one-bin windows."""
     size = SIZES[1]
