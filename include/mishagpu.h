@@ -279,6 +279,12 @@ int mg_percentile_lookup(mg_ctx *ctx, double *d_col, int64_t n, const double *h_
 /* device arrays with room for `count` entries; *h_nout receives the number produced (the call synchronises).     */
 int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
 					int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream);
+/* The same with the intervals in HOST arrays of `capacity` entries (pinned memory makes the copies run at the link's speed): the */
+/* TRUE runs are counted first, the device side of the result is allocated at its size. *h_nout receives the number of intervals;  */
+/* when it exceeds `capacity` nothing is copied and the caller calls again with larger arrays (what C_gscreen's growing vector of   */
+/* intervals does, src/GenomeTrackScreener.cpp:195-220). Synchronises the stream.                                                  */
+int mg_h_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *h_chrom,
+					  int64_t *h_start, int64_t *h_end, int64_t capacity, int64_t *h_nout, void *stream);
 
 /* gscreen predicates that are comparisons of value columns against constants, all joined by `&` or all by `|` (e.g.   */
 /* "near > 0.5 & cov > 0.25"): d_flag[i] = 1 where R's result is TRUE, else 0. A comparison with NaN is NA in R, and  */

@@ -2973,6 +2973,31 @@ extern "C" int mg_screen_compare(mg_ctx *ctx, int nterms, const double *const *d
 	return 0;
 }
 
+// the fixed-bin iterator's implicit rows take the 16-rows-per-thread kernels (the flags are then read 16 bytes at a time: the array must
+// be 16-byte aligned and readable up to the next multiple of 16, which every allocation of this library is)
+static bool mg_screen_fb(const mg_rows *rows, const int8_t *d_flag) { return rows->src.kind == 1 && ((uintptr_t)d_flag & 15u) == 0; }
+static int64_t mg_screen_nblocks(const mg_rows *rows, const int8_t *d_flag, int64_t count)
+{
+	return mg_screen_fb(rows, d_flag) ? mg_div_up(count, (int64_t)MG_SCB_THREADS * MG_SCB_ROWS) : mg_div_up(count, MG_SCR_THREADS);
+}
+static void mg_screen_launch_count(const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int64_t nblocks, long long *heads, long long *tails,
+								   long long *total, cudaStream_t st)
+{
+	if (mg_screen_fb(rows, d_flag))
+		k_screen_count_fb<<<(unsigned)nblocks, MG_SCB_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails);
+	else
+		k_screen_count<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails);
+	k_screen_scan<<<1, 1024, 0, st>>>(heads, tails, nblocks, total);
+}
+static void mg_screen_launch_write(const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int64_t nblocks, const long long *heads,
+								   const long long *tails, int32_t *d_chrom, int64_t *d_start, int64_t *d_end, cudaStream_t st)
+{
+	if (mg_screen_fb(rows, d_flag))
+		k_screen_write_fb<<<(unsigned)nblocks, MG_SCB_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails, d_chrom, d_start, d_end);
+	else
+		k_screen_write<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails, d_chrom, d_start, d_end);
+}
+
 extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *d_chrom,
 							   int64_t *d_start, int64_t *d_end, int64_t *h_nout, void *stream)
 {
@@ -2982,20 +3007,56 @@ extern "C" int mg_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, 
 		return 0;
 	cudaStream_t st = mg_stream(stream);
 	MgScratch mg_scratch(st);
-	const int64_t nblocks = mg_div_up(count, MG_SCR_THREADS);
+	const int64_t nblocks = mg_screen_nblocks(rows, d_flag, count);
 	long long *blk = nullptr;
 	MG_CUDA(ctx, mg_scratch.alloc(&blk, sizeof(long long) * (2 * nblocks + 1)));
 	long long *heads = blk, *tails = blk + nblocks, *total = blk + 2 * nblocks;
-	k_screen_count<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails);
+	mg_screen_launch_count(rows, first, count, d_flag, nblocks, heads, tails, total, st);
 	MG_LAUNCH_CHECK(ctx);
-	k_screen_scan<<<1, 1024, 0, st>>>(heads, tails, nblocks, total);
-	MG_LAUNCH_CHECK(ctx);
-	k_screen_write<<<(unsigned)nblocks, MG_SCR_THREADS, 0, st>>>(rows->src, first, count, d_flag, heads, tails, d_chrom, d_start, d_end);
+	mg_screen_launch_write(rows, first, count, d_flag, nblocks, heads, tails, d_chrom, d_start, d_end, st);
 	MG_LAUNCH_CHECK(ctx);
 	long long n = 0;
 	MG_CUDA(ctx, cudaMemcpyAsync(&n, total, sizeof(long long), cudaMemcpyDeviceToHost, st));
 	MG_CUDA(ctx, cudaStreamSynchronize(st));
 	*h_nout = n;
+	return 0;
+}
+
+// The same with the intervals delivered to the host: the runs are counted first, so the device side of the result is allocated at its
+// size (a 20 bp iterator over hg38 has 154 M rows and a few million runs), written, and copied into the caller's arrays.
+extern "C" int mg_h_screen_merge(mg_ctx *ctx, const mg_rows *rows, int64_t first, int64_t count, const int8_t *d_flag, int32_t *h_chrom,
+								 int64_t *h_start, int64_t *h_end, int64_t capacity, int64_t *h_nout, void *stream)
+{
+	MG_REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= rows->src.n, "row range out of bounds");
+	MG_REQUIRE(ctx, capacity >= 0, "mg_h_screen_merge: negative capacity");
+	*h_nout = 0;
+	if (!count)
+		return 0;
+	cudaStream_t st = mg_stream(stream);
+	MgScratch mg_scratch(st);
+	const int64_t nblocks = mg_screen_nblocks(rows, d_flag, count);
+	long long *blk = nullptr;
+	MG_CUDA(ctx, mg_scratch.alloc(&blk, sizeof(long long) * (2 * nblocks + 1)));
+	long long *heads = blk, *tails = blk + nblocks, *total = blk + 2 * nblocks;
+	mg_screen_launch_count(rows, first, count, d_flag, nblocks, heads, tails, total, st);
+	MG_LAUNCH_CHECK(ctx);
+	long long n = 0;
+	MG_CUDA(ctx, cudaMemcpyAsync(&n, total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
+	*h_nout = n;
+	if (n == 0 || n > capacity) // too many for the caller's arrays: the count is the answer, nothing is copied
+		return 0;
+	int32_t *d_chrom = nullptr;
+	int64_t *d_start = nullptr, *d_end = nullptr;
+	MG_CUDA(ctx, mg_scratch.alloc(&d_chrom, sizeof(int32_t) * (size_t)n));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_start, sizeof(int64_t) * (size_t)n));
+	MG_CUDA(ctx, mg_scratch.alloc(&d_end, sizeof(int64_t) * (size_t)n));
+	mg_screen_launch_write(rows, first, count, d_flag, nblocks, heads, tails, d_chrom, d_start, d_end, st);
+	MG_LAUNCH_CHECK(ctx);
+	MG_CUDA(ctx, cudaMemcpyAsync(h_chrom, d_chrom, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(h_start, d_start, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaMemcpyAsync(h_end, d_end, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	MG_CUDA(ctx, cudaStreamSynchronize(st));
 	return 0;
 }
 

@@ -1432,6 +1432,103 @@ __global__ void __launch_bounds__(MG_SCR_THREADS) k_screen_count(const RowSrc rs
 	}
 }
 
+// ---- the fixed-bin iterator's implicit rows: 16 rows per thread, heads and tails as bit masks -----------------------------------
+// Consecutive implicit rows of one scope interval always touch (row r ends where row r + 1 starts), so inside a scope interval a
+// head is a TRUE row after a row that is not TRUE and a tail a TRUE row before one that is not: two shifts and an AND over 16 flags
+// loaded at once. Only the few 16-row chunks that hold a scope interval's first row look at coordinates (two scope intervals may
+// touch, then the run goes on: src/GenomeTrackScreener.cpp:203-211 compares chromosome and coordinates, nothing else).
+#define MG_SCB_ROWS 16
+#define MG_SCB_THREADS 256
+
+__device__ __forceinline__ uint32_t mg_true_bits4(uint32_t w) // bit j = byte j of w equals 1
+{
+	const uint32_t m = __vcmpeq4(w, 0x01010101u) & 0x01010101u;
+	return (m * 0x01020408u) >> 24;
+}
+
+// heads / tails (bit j = row i0 + j) of the 16 rows from i0 (a multiple of 16); rc: the scope interval of row i0
+__device__ __forceinline__ void mg_screen_bits(const RowSrc &rs, int64_t first, int64_t count, const int8_t *__restrict__ flag, int64_t i0, uint32_t &heads,
+											   uint32_t &tails, RowCache &rc)
+{
+	const int64_t left = count - i0;
+	uint32_t bits = 0;
+	if (left >= 16) {
+		const uint4 f = __ldg(reinterpret_cast<const uint4 *>(flag + i0));
+		bits = mg_true_bits4(f.x) | (mg_true_bits4(f.y) << 4) | (mg_true_bits4(f.z) << 8) | (mg_true_bits4(f.w) << 12);
+	} else { // the last rows: nothing is read past the array
+		for (int j = 0; j < (int)left; ++j)
+			bits |= (flag[i0 + j] == 1 ? 1u : 0u) << j;
+	}
+	const uint32_t prev = i0 > 0 && flag[i0 - 1] == 1 ? 1u : 0u, next = left > 16 && flag[i0 + 16] == 1 ? 1u : 0u;
+	const uint32_t w = prev | (bits << 1) | (next << 17); // bit j + 1 = row i0 + j
+	uint32_t brk = 0;                                      // bit j: rows i0 + j - 1 and i0 + j do not touch (j = 0 .. 16)
+	if (bits) {
+		const int64_t r0 = first + i0;
+		mg_rowcache_load(rs, r0, rc);
+		if (r0 == rc.row0 || r0 + 16 >= rc.row1) { // a scope interval starts inside rows i0 .. i0 + 16: look at the coordinates there
+			RowCache c2;
+			for (int j = 0; j <= 16; ++j) {
+				const int64_t r = r0 + j;
+				if (r < 1 || r >= rs.n || i0 + j < 1 || i0 + j >= count)
+					continue;
+				int ca, cb;
+				int64_t sa, ea, sb, eb, k;
+				mg_get_row_cached(rs, r - 1, c2, ca, sa, ea, k);
+				mg_get_row_cached(rs, r, c2, cb, sb, eb, k);
+				if (!(ca == cb && ea == sb))
+					brk |= 1u << j;
+			}
+		}
+	}
+	heads = (w >> 1) & (~w | brk) & 0xffffu;
+	tails = (w >> 1) & (~(w >> 2) | (brk >> 1)) & 0xffffu;
+}
+
+__global__ void __launch_bounds__(MG_SCB_THREADS) k_screen_count_fb(const RowSrc rs, int64_t first, int64_t count, const int8_t *flag, long long *block_heads,
+																	 long long *block_tails)
+{
+	__shared__ int sc[33];
+	const int64_t i0 = ((int64_t)blockIdx.x * MG_SCB_THREADS + threadIdx.x) * MG_SCB_ROWS;
+	uint32_t heads = 0, tails = 0;
+	RowCache rc;
+	if (i0 < count)
+		mg_screen_bits(rs, first, count, flag, i0, heads, tails, rc);
+	int th;
+	mg_block_excl_scan<int>(__popc(heads) | (__popc(tails) << 16), sc, th); // both counts in one scan: a block holds 4096 rows
+	if (threadIdx.x == 0) {
+		block_heads[blockIdx.x] = th & 0xffff;
+		block_tails[blockIdx.x] = th >> 16;
+	}
+}
+
+__global__ void __launch_bounds__(MG_SCB_THREADS) k_screen_write_fb(const RowSrc rs, int64_t first, int64_t count, const int8_t *flag,
+																	 const long long *block_heads, const long long *block_tails, int32_t *ochrom,
+																	 int64_t *ostart, int64_t *oend)
+{
+	__shared__ int sc[33];
+	const int64_t i0 = ((int64_t)blockIdx.x * MG_SCB_THREADS + threadIdx.x) * MG_SCB_ROWS;
+	uint32_t heads = 0, tails = 0;
+	RowCache rc;
+	if (i0 < count)
+		mg_screen_bits(rs, first, count, flag, i0, heads, tails, rc);
+	int tot;
+	const int off = mg_block_excl_scan<int>(__popc(heads) | (__popc(tails) << 16), sc, tot);
+	long long hoff = block_heads[blockIdx.x] + (off & 0xffff), toff = block_tails[blockIdx.x] + (off >> 16);
+	for (uint32_t m = heads | tails; m; m &= m - 1u) {
+		const int j = __ffs(m) - 1;
+		int c;
+		int64_t s, e, k;
+		mg_get_row_cached(rs, first + i0 + j, rc, c, s, e, k);
+		if ((heads >> j) & 1u) {
+			ochrom[hoff] = c;
+			ostart[hoff] = s;
+			++hoff;
+		}
+		if ((tails >> j) & 1u)
+			oend[toff++] = e;
+	}
+}
+
 __global__ void __launch_bounds__(1024) k_screen_scan(long long *block_heads, long long *block_tails, int64_t nblocks, long long *total_out)
 {
 	__shared__ long long sc[33];

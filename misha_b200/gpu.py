@@ -545,6 +545,20 @@ def screen_merge(ctx, rows, dflag, first=0, count=None, stream=None, scratch=Non
     return dc.to_host(stream, m), ds.to_host(stream, m), de.to_host(stream, m)
 
 
+def screen_merge_host(ctx, rows, dflag, host_out, first=0, count=None, stream=None):
+    """The merged TRUE runs in the caller's host arrays host_out = (int32 chrom, int64 start, int64 end), e.g. Context.pinned buffers kept
+    across calls: returns views of their first m entries, or None when the arrays are too short for the m runs found (m is then
+    in screen_merge_host.last_count)."""
+    count = rows.n - first if count is None else count
+    hc, hs, he = host_out
+    cap = min(len(hc), len(hs), len(he))
+    nout = c_i64()
+    ctx._check(ctx.lib.mg_h_screen_merge(ctx.h, rows.h, c_i64(first), c_i64(count), c_vp(dflag.ptr), _p(hc), _p(hs), _p(he), c_i64(cap),
+                                         ctypes.byref(nout), c_vp(stream)))
+    screen_merge_host.last_count = m = nout.value
+    return None if m > cap else (hc[:m], hs[:m], he[:m])
+
+
 # ---- several GPUs behind one host thread (mg_group_*) -------------------------------------------------------------------------
 class Group:
     """One mg_ctx per device, driven from this thread: chromosomes staged on their owners, rows routed to them, the small

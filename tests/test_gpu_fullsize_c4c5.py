@@ -91,6 +91,9 @@ def test_c4_gscreen_intervals(c4):
     flag = gpu.screen_compare(ctx, [near, cov], [">", ">"], [0.5, 0.25], False, rows.n)
     gc, gs, ge = gpu.screen_merge(ctx, rows, flag)
     assert len(gc) > 100_000 and np.all(ge > gs)
+    host = (ctx.pinned(len(gc), np.int32), ctx.pinned(len(gc), np.int64), ctx.pinned(len(gc), np.int64))
+    hc, hs, he = gpu.screen_merge_host(ctx, rows, flag, host)  # device side allocated at the size of the result
+    assert np.array_equal(hc, gc) and np.array_equal(hs, gs) and np.array_equal(he, ge)
     order_ok = (gc[1:] > gc[:-1]) | ((gc[1:] == gc[:-1]) & (gs[1:] > ge[:-1]))  # sorted, runs separated by at least one FALSE row
     assert np.all(order_ok)
     for cid, (rs, re, rv) in c4["recs"].items():

@@ -155,6 +155,25 @@ def test_screen_merge(gpu_ctx):
         gc, gs, ge = gpu.screen_merge(gpu_ctx, rows, dflag)
         ec, es, ee = port.screen_merge(c, s, e, flag)
         assert np.array_equal(gc, ec) and np.array_equal(gs, es) and np.array_equal(ge, ee), f"p={p}"
+        # the host-array entry point (mg_h_screen_merge): the same intervals; arrays one entry short get the count and nothing else
+        host = (gpu_ctx.pinned(len(ec) + 3, np.int32), gpu_ctx.pinned(len(ec) + 3, np.int64), gpu_ctx.pinned(len(ec) + 3, np.int64))
+        hc, hs, he = gpu.screen_merge_host(gpu_ctx, rows, dflag, host)
+        assert np.array_equal(hc, ec) and np.array_equal(hs, es) and np.array_equal(he, ee), f"host arrays, p={p}"
+        if len(ec):
+            short = tuple(h[:len(ec) - 1] for h in host)
+            assert gpu.screen_merge_host(gpu_ctx, rows, dflag, short) is None and gpu.screen_merge_host.last_count == len(ec)
+    # scope intervals that touch (the run goes on across them), leave a gap, or change chromosome; sub-ranges that begin and end anywhere
+    # in a 16-row chunk (the fixed-bin kernels read 16 flags per thread)
+    rows = gpu_ctx.rows_fixedbin(20, np.array([0, 0, 0, 1, 1], np.int32), np.array([0, 1000, 5000, 40, 1040]), np.array([1000, 3010, 9000, 1040, 2000]))
+    c, s, e, _ = rows.coords()
+    for p in (1.0, 0.9, 0.5, 0.1):
+        flag = (rng.random(rows.n) < p).astype(np.int8)
+        for first, count in ((0, rows.n), (7, rows.n - 20), (33, 100), (48, 17), (0, 1), (rows.n - 1, 1), (49, 150)):
+            sub = np.ascontiguousarray(flag[first:first + count])
+            dflag = gpu_ctx.alloc(count, np.int8).from_host(sub)
+            gc, gs, ge = gpu.screen_merge(gpu_ctx, rows, dflag, first, count)
+            ec, es, ee = port.screen_merge(c[first:first + count], s[first:first + count], e[first:first + count], sub)
+            assert np.array_equal(gc, ec) and np.array_equal(gs, es) and np.array_equal(ge, ee), f"scope seams p={p} first={first} count={count}"
     # explicit rows with gaps: touching rows merge, gapped rows do not, chromosome change splits
     ch = np.array([0, 0, 0, 0, 1, 1]); st = np.array([0, 10, 30, 40, 40, 50]); en = np.array([10, 20, 40, 50, 50, 60])
     rows = gpu_ctx.rows_upload(ch, st, en)

@@ -266,7 +266,8 @@ def run_c4(args):
     rows_total = int(env.sum_over_ranks(float(rows.n)))
     near, cov = ctx.alloc(rows.n, np.float64), ctx.alloc(rows.n, np.float64)
     flag = ctx.alloc(rows.n, np.int8)
-    scratch = (ctx.alloc(rows.n, np.int32), ctx.alloc(rows.n, np.int64), ctx.alloc(rows.n, np.int64))
+    cap = 16_000_000  # intervals the pinned host arrays can take (the step produces ~ 2 M)
+    host_iv = (ctx.pinned(cap, np.int32), ctx.pinned(cap, np.int64), ctx.pinned(cap, np.int64))
     out = {}
 
     def cols():
@@ -279,14 +280,14 @@ def run_c4(args):
 
     def step_e2e():  # gscreen as the caller sees it: the merged intervals on the host
         step_dev()
-        out["iv"] = gpu.screen_merge(ctx, rows, flag, stream=env.stream, scratch=scratch)
+        out["iv"] = gpu.screen_merge_host(ctx, rows, flag, host_iv, stream=env.stream)
 
     ms_step = env.timed(step_dev, args.steps)
     ms_e2e = env.timed(step_e2e, args.steps, events=False)
     ms_near = env.timed(lambda: sp.window_dev(rows, ["nearest"], out=[near], stream=env.stream), args.steps)
     ms_cov = env.timed(lambda: iv.coverage_dev(rows, out=cov, stream=env.stream), args.steps)
     ms_cmp = env.timed(lambda: gpu.screen_compare(ctx, [near, cov], [">", ">"], [0.5, 0.25], False, rows.n, dflag=flag, stream=env.stream), args.steps)
-    ms_merge = env.timed(lambda: gpu.screen_merge(ctx, rows, flag, stream=env.stream, scratch=scratch), args.steps, events=False)
+    ms_merge = env.timed(lambda: gpu.screen_merge_host(ctx, rows, flag, host_iv, stream=env.stream), args.steps, events=False)
     n_out = len(out["iv"][0])
     alg_near, alg_cov = 20 * nrec + 8 * rows.n, 16 * nrec + 8 * rows.n
     line = base_line(env, "C4", rows_total, ms_step, "C4: nearest (5 M-record sparse track) + coverage (the same intervals) vtracks and the gscreen predicate "
@@ -294,7 +295,7 @@ def run_c4(args):
                      {"rows": rows_total, "records": int(sum(cnt)), "iterator": 20})
     line["dtype"] = "f32 values / f64 accumulate, i64 coordinates"
     line["e2e"] = {"value": rows_total / (ms_e2e / 1e3), "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_out * 20),
-                   "ms_per_step": ms_e2e, "api": "mg_sparse_window + mg_coverage + mg_screen_compare + mg_screen_merge (intervals to the host); the iterator's rows "
+                   "ms_per_step": ms_e2e, "api": "mg_sparse_window + mg_coverage + mg_screen_compare + mg_h_screen_merge (intervals into pinned host arrays); the iterator's rows "
                    "are implicit: no per-step host input", "intervals_out_rank0": int(n_out),
                    "attribution_ms": {"nearest": round(ms_near, 4), "coverage": round(ms_cov, 4), "predicate": round(ms_cmp, 4),
                                       "run merge + compaction + D2H of the intervals (host clock, synchronises)": round(ms_merge, 4)}}
