@@ -19,6 +19,7 @@
 
 #define MG_SM_COUNT_B200 148
 
+#define MG_PIPE_MAX_SLOTS 8
 struct mg_ctx {
 	int device = 0;
 	int sm_count = MG_SM_COUNT_B200;
@@ -28,7 +29,7 @@ struct mg_ctx {
 	std::vector<int64_t> chrom_sizes;
 	int64_t *d_chrom_sizes = nullptr;
 	int64_t launches = 0;
-	int64_t pipe_chunk_rows = 1 << 19; // rows per slot of the host-buffer pipeline (measured best of 2^17..2^22 on B200 / PCIe Gen5)
+	int64_t pipe_chunk_rows = 3 << 17; // rows per slot of the host-buffer pipeline (C3 end to end on four B200 boxes: 5.3 - 6.5 ms at 2^19, 5.5 - 5.7 at 3 * 2^17, 5.6 - 5.8 at 2^18, 5.7 at 2^20, 7.6 at 2^17; the copies alone 4.7 - 4.8)
 	bool zero_copy = false; // host-buffer entry points: kernels read rows / write columns straight in pinned host memory.
 	                        // Measured SLOWER than the 3-slot DMA pipeline on B200 (5.9 vs 5.3 ms for C3), hence off by default.
 	bool pwm_strict = false; // PWM strand / anchor log-sum-exp with double-precision exp / log (correctly rounded float results)
@@ -58,12 +59,13 @@ struct mg_ctx {
 	int thr_include_lowest = -1;
 	std::map<void *, void *> stream_scratch; // per-stream reduction scratch (mishagpu.cu: mg_stream_scratch)
 	// internal streams + staging buffers of the host-buffer entry points (lazily created)
-	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
-	void *pipe_dev[3] = {nullptr, nullptr, nullptr};
-	int64_t pipe_dev_bytes[3] = {0, 0, 0};
+	cudaStream_t pipe_stream[MG_PIPE_MAX_SLOTS] = {};
+	void *pipe_dev[MG_PIPE_MAX_SLOTS] = {};
+	int64_t pipe_dev_bytes[MG_PIPE_MAX_SLOTS] = {};
+	int pipe_slots = 3; // device slots (one stream each) the chunks of a host batch rotate through (option pipe_slots)
 	unsigned long long *d_first_bad = nullptr; // first row of a host batch whose chromosome id was out of range (k_rows_sanitize); ~0: none
 	uint8_t *d_served = nullptr; // member of a group: served[chromid] != 0 for the chromosomes this device owns (null: every chromosome)
-	int64_t pipe_next = 0; // chunks enqueued so far: the slot of the next one is pipe_next % 3
+	int64_t pipe_next = 0; // chunks enqueued so far: the slot of the next one is pipe_next % pipe_slots
 };
 
 extern thread_local std::string g_mg_init_err;

@@ -345,7 +345,7 @@ extern "C" int mg_group_h_dense_window(mg_group *g, const mg_gdense *t, int64_t 
 				continue;
 			mg_ctx *ctx = g->ctx[k];
 			cudaSetDevice(ctx->device);
-			for (int i = 0; i < 3; ++i)
+			for (int i = 0; i < MG_PIPE_MAX_SLOTS; ++i)
 				if (ctx->pipe_stream[i]) {
 					const cudaError_t e = cudaStreamSynchronize(ctx->pipe_stream[i]);
 					if (e != cudaSuccess && !rc)

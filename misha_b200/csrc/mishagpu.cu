@@ -63,7 +63,7 @@ extern "C" void mg_shutdown(mg_ctx *ctx)
 	if (!ctx)
 		return;
 	cudaSetDevice(ctx->device);
-	for (int i = 0; i < 3; ++i) {
+	for (int i = 0; i < MG_PIPE_MAX_SLOTS; ++i) {
 		if (ctx->pipe_dev[i])
 			cudaFree(ctx->pipe_dev[i]);
 		if (ctx->pipe_stream[i])
@@ -139,6 +139,12 @@ extern "C" int mg_set_option(mg_ctx *ctx, const char *name, int64_t value)
 	}
 	if (name && !strcmp(name, "zero_copy")) {
 		ctx->zero_copy = value != 0;
+		return 0;
+	}
+	if (name && !strcmp(name, "pipe_slots")) {
+		if (value < 2 || value > MG_PIPE_MAX_SLOTS)
+			return mg_fail(ctx, "mg_set_option: pipe_slots must be 2 .. %d", MG_PIPE_MAX_SLOTS);
+		ctx->pipe_slots = (int)value;
 		return 0;
 	}
 	if (name && !strcmp(name, "pipe_chunk_rows")) {
@@ -1165,7 +1171,7 @@ static int mg_pipe_prepare(mg_ctx *ctx, int64_t bytes_per_slot)
 		MG_CUDA(ctx, cudaMalloc(&ctx->d_first_bad, 8));
 		MG_CUDA(ctx, cudaMemset(ctx->d_first_bad, 0xff, 8)); // "no bad row"
 	}
-	for (int i = 0; i < 3; ++i) {
+	for (int i = 0; i < ctx->pipe_slots; ++i) {
 		if (!ctx->pipe_stream[i])
 			MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
 		if (ctx->pipe_dev_bytes[i] < bytes_per_slot) {
@@ -1238,7 +1244,7 @@ static int mg_h_pipeline_run(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, con
 	step = step > CHUNK ? CHUNK : step;
 	for (int64_t done = 0; done < n; done += step) {
 		const int64_t m = n - done < step ? n - done : step;
-		const int slot = (int)(ctx->pipe_next++ % 3);
+		const int slot = (int)(ctx->pipe_next++ % ctx->pipe_slots);
 		cudaStream_t st = ctx->pipe_stream[slot];
 		char *base = (char *)ctx->pipe_dev[slot];
 		int64_t *d_start = (int64_t *)base, *d_end = (int64_t *)(base + CHUNK * 8);
@@ -1291,7 +1297,9 @@ static int mg_h_pipeline(mg_ctx *ctx, int64_t n, const int32_t *h_chrom, const i
 		return 1;
 	int rc = mg_h_pipeline_run(ctx, n, h_chrom, h_start, h_end, ncols, h_out, launch);
 	const std::string first_err = rc ? ctx->err : std::string();
-	for (int i = 0; i < 3; ++i) {
+	for (int i = 0; i < MG_PIPE_MAX_SLOTS; ++i) {
+		if (!ctx->pipe_stream[i])
+			continue;
 		const cudaError_t e = cudaStreamSynchronize(ctx->pipe_stream[i]);
 		if (e != cudaSuccess && !rc)
 			rc = mg_fail(ctx, "host pipeline: %s", cudaGetErrorString(e));
