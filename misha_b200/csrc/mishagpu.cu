@@ -2137,7 +2137,7 @@ static int mg_summary_blocks(mg_ctx *ctx, int64_t n)
 	return (int)(b < 1 ? 1 : b);
 }
 
-extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *d_partial, void *stream)
+static int mg_summary_impl(mg_ctx *ctx, const double *d_vals, int64_t n, double *d_partial, void *stream, bool narrow)
 {
 	if (n <= 0)
 		return 0;
@@ -2146,11 +2146,19 @@ extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *
 	const int nb = mg_summary_blocks(ctx, n);
 	Moments *scratch = nullptr;
 	MG_CUDA(ctx, mg_scratch.alloc(&scratch, sizeof(Moments) * nb));
-	k_summary_values<<<nb, MG_SUM_THREADS, 0, st>>>(d_vals, n, scratch);
+	if (narrow)
+		k_summary_values<true><<<nb, MG_SUM_THREADS, 0, st>>>(d_vals, n, scratch);
+	else
+		k_summary_values<false><<<nb, MG_SUM_THREADS, 0, st>>>(d_vals, n, scratch);
 	MG_LAUNCH_CHECK(ctx);
 	k_summary_final<<<1, MG_SUM_THREADS, 0, st>>>(scratch, nb, d_partial);
 	MG_LAUNCH_CHECK(ctx);
 	return 0;
+}
+
+extern "C" int mg_summary(mg_ctx *ctx, const double *d_vals, int64_t n, double *d_partial, void *stream)
+{
+	return mg_summary_impl(ctx, d_vals, n, d_partial, stream, false);
 }
 
 // Per-stream device scratch (a zeroed 256-byte header + MG_SUM_MAX_BLOCKS block partials), allocated on first use and kept:
@@ -2828,7 +2836,7 @@ extern "C" int mg_summary_segmented(mg_ctx *ctx, const double *d_vals, int64_t n
 	MG_LAUNCH_CHECK(ctx);
 	for (int64_t s = 0; s < nseg; ++s) {
 		const int64_t c = h_seg_first[s + 1] - h_seg_first[s];
-		if (c > big && mg_summary(ctx, d_vals + h_seg_first[s], c, d_part + 6 * s, stream))
+		if (c > big && mg_summary_impl(ctx, d_vals + h_seg_first[s], c, d_part + 6 * s, stream, true)) // narrowed to float like the segments k_summary_segs takes
 			return 1;
 	}
 	MG_CUDA(ctx, cudaMemcpyAsync(h_partials, d_part, (size_t)nseg * 48, cudaMemcpyDeviceToHost, st));

@@ -79,6 +79,9 @@ __device__ __forceinline__ void mom_block_reduce(Moments &m, Moments *smem /* >=
 	}
 }
 
+// NARROW: every value goes through float first, as the reference's per-interval summary reads it (`float val`,
+// src/GenomeTrackSummary.cpp:314) -- what k_summary_segs does for the segments it handles itself
+template <bool NARROW>
 __global__ void __launch_bounds__(MG_SUM_THREADS) k_summary_values(const double *__restrict__ vals, int64_t n, Moments *block_out)
 {
 	__shared__ Moments sm[MG_SUM_THREADS / 32];
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(MG_SUM_THREADS) k_summary_values(const double 
 	mom_init(m);
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		mom_add(m, __ldcs(vals + i));
+		mom_add(m, NARROW ? (double)(float)__ldcs(vals + i) : __ldcs(vals + i));
 	mom_block_reduce(m, sm);
 	if (threadIdx.x == 0)
 		block_out[blockIdx.x] = m;

@@ -331,7 +331,9 @@ def test_summary_segmented(gpu_ctx):
     sizes = [0, 1, 2, 33, 0, 1000, 7, 300000, 5] + list(rng.integers(0, 200, 500))
     sf = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n = int(sf[-1])
-    col = np.where(rng.random(n) < 0.1, np.nan, rng.lognormal(size=n)).astype(np.float32).astype(np.float64)
+    # doubles that are not floats (a host expression like track * 0.1): every segment, the 300000-row one that goes through the whole-device
+    # kernels included, reads its values through float as the reference does (src/GenomeTrackSummary.cpp:314)
+    col = np.where(rng.random(n) < 0.1, np.nan, rng.lognormal(size=n) * 0.1)
     col[sf[6]:sf[7]] = np.nan
     d = gpu_ctx.alloc(n, np.float64).from_host(col)
     got = gpu.summary_segmented(gpu_ctx, d, sf)
