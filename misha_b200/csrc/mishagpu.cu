@@ -2484,6 +2484,18 @@ extern "C" int mg_dense_hist(mg_ctx *ctx, const mg_dense *t, const mg_rows *rows
 		ft.uniform = hs.binsize[0] != 0.;
 		ft.b0 = (float)h_breaks[0];
 		ft.inv_binsize = ft.uniform ? (float)(1. / hs.binsize[0]) : 0.f;
+		ft.near = 2.f; // no value is "far from every break": the kernel always looks at the thresholds
+		if (ft.uniform) {
+			// how far (in bins) the kernel's float position t = (v - b0) * inv + 1 can lie from the value's true position among THESE breaks:
+			// the roundings of b0 and inv, the breaks' own deviation from b0 + j * binsize, three float roundings of at most 2^-24 relative
+			const double bs = hs.binsize[0], tmax = nb + 2.;
+			double err = fabs(h_breaks[0] - (double)ft.b0) / bs + tmax * (fabs(1. / bs - (double)ft.inv_binsize) * bs + 3. * 5.960464477539063e-08);
+			for (int j = 0; j < nbreaks; ++j)
+				err = std::max(err, fabs(h_breaks[j] - (h_breaks[0] + j * bs)) / bs + tmax * 3. * 5.960464477539063e-08);
+			const double near = 4. * err + 9.5367431640625e-07;
+			if (near < 0.25)
+				ft.near = (float)near;
+		}
 		memcpy(ft.thr, thr.data(), sizeof(float) * thr.size());
 		SegTable tab;
 		mg_make_segtable(segs, tab);

@@ -444,6 +444,7 @@ struct FloatThr {
 	int nb;
 	int uniform;
 	float b0, inv_binsize;
+	float near; // a position whose fraction keeps this far from 0 and 1 has the count floor(position): see k_segs_hist (>= 1: never)
 	float thr[MG_HIST_PRIVATE_MAX + 1];
 };
 
@@ -513,16 +514,25 @@ __global__ void __launch_bounds__(MG_HIST_THREADS) k_segs_hist(const SegTable st
 	};
 	if (ft.uniform) {
 		const float b0 = ft.b0, inv = ft.inv_binsize, top = (float)(nb + 1);
+		// t = the value's position in units of bins (+ 1). The host bounds its distance from the true position among these breaks (ft.near
+		// is four times that bound): a t whose fraction keeps that far from both ends has the count floor(t) without a look at the
+		// thresholds; the few values near a break -- and everything negative, huge or NaN -- take the exact path
+		const float NEAR = ft.near;
 		mg_stream_segtable(st, [&](float v) {
-			if (v != v)
-				return;
-			int c = (int)fminf(fmaxf((v - b0) * inv + 1.f, 0.f), top);
-			const float t0 = mg_lds_f(pbase + 4u * c), t1 = mg_lds_f(pbase + 4u * c + 4u);
-			if (!(t0 < v) || t1 < v) { // the float guess missed: walk to the right count (sentinels bound both walks)
-				while (mg_lds_f(pbase + 4u * c + 4u) < v)
-					++c;
-				while (!(mg_lds_f(pbase + 4u * c) < v))
-					--c;
+			const float t = (v - b0) * inv + 1.f;
+			int c = __float2int_rz(t);
+			const float fr = t - (float)c;
+			if (!(fr >= NEAR && fr <= 1.f - NEAR)) {
+				if (v != v)
+					return;
+				c = (int)fminf(fmaxf(t, 0.f), top);
+				const float t0 = mg_lds_f(pbase + 4u * c), t1 = mg_lds_f(pbase + 4u * c + 4u);
+				if (!(t0 < v) || t1 < v) { // the float guess missed: walk to the right count (sentinels bound both walks)
+					while (mg_lds_f(pbase + 4u * c + 4u) < v)
+						++c;
+					while (!(mg_lds_f(pbase + 4u * c) < v))
+						--c;
+				}
 			}
 			if ((unsigned)(c - 1) < (unsigned)nb)
 				count_bin(hbase + COL * c);
