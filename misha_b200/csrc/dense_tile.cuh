@@ -647,20 +647,16 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 	const uint32_t gs = g0 + 1, len = multi ? g1 - gs : 0u; // the whole groups of 8 inside the window: [gs, g1)
 	__syncthreads(); // the accumulators are initialised
 	{
-		const uint32_t r_cmin = __reduce_min_sync(0xffffffffu, reg ? r.chrom : 0xffffffffu), r_cmax = __reduce_max_sync(0xffffffffu, r.chrom);
-		const uint32_t r_bmin = __reduce_min_sync(0xffffffffu, reg ? sb : 0xffffffffu), r_bmax = __reduce_max_sync(0xffffffffu, eb);
-		const uint32_t r_lmin = MM ? __reduce_min_sync(0xffffffffu, len > 0 ? len : 0xffffffffu) : 0u;
-		const bool r_bad = __any_sync(0xffffffffu, r.bad || (Q && nb > MG_BW_S));
-		if (lane == 0) {
-			atomicMin(&s_acc[0], r_cmin);
-			atomicMax(&s_acc[1], r_cmax);
-			atomicMin(&s_acc[2], r_bmin);
-			atomicMax(&s_acc[3], r_bmax);
-			if (MM)
-				atomicMin(&s_acc[4], r_lmin);
-			if (r_bad)
-				s_acc[6] = 1u;
-		}
+		// every thread hands its values to the shared-memory reductions: the compiler folds a warp's 32 into one (CREDUX + one elected
+		// lane's ATOMS) -- a reduction written out here ahead of a single lane's atomic would be folded a second time
+		atomicMin(&s_acc[0], reg ? r.chrom : 0xffffffffu);
+		atomicMax(&s_acc[1], r.chrom);
+		atomicMin(&s_acc[2], reg ? sb : 0xffffffffu);
+		atomicMax(&s_acc[3], eb);
+		if (MM)
+			atomicMin(&s_acc[4], len > 0 ? len : 0xffffffffu);
+		if (r.bad || (Q && nb > MG_BW_S))
+			s_acc[6] = 1u;
 	}
 	__syncthreads();
 	const uint4 acc0 = *reinterpret_cast<const uint4 *>(s_acc);
