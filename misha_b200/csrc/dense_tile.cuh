@@ -789,11 +789,16 @@ __global__ void __launch_bounds__(MG_TL_THREADS, MG_TH_MB) k_dense_thin(const __
 		}
 	}
 	if (SUM) {
-		if (om & (1u << MG_AVG)) mg_st_stream(q.out[MG_AVG] + i, avg);
-		if (om & (1u << MG_NEAREST)) mg_st_stream(q.out[MG_NEAREST] + i, avg);
-		if (om & (1u << MG_SUM)) mg_st_stream(q.out[MG_SUM] + i, sum);
-		if (om & (1u << MG_SIZE)) mg_st_stream(q.out[MG_SIZE] + i, size);
-		if (om & (1u << MG_EXISTS)) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+		constexpr uint32_t GROUP = (1u << MG_AVG) | (1u << MG_NEAREST) | (1u << MG_SUM) | (1u << MG_SIZE) | (1u << MG_EXISTS);
+		if ((om & GROUP) == (1u << MG_AVG)) // the usual request, without the other four columns' tests and addresses in its way
+			mg_st_stream(q.out[MG_AVG] + i, avg);
+		else {
+			if (om & (1u << MG_AVG)) mg_st_stream(q.out[MG_AVG] + i, avg);
+			if (om & (1u << MG_NEAREST)) mg_st_stream(q.out[MG_NEAREST] + i, avg);
+			if (om & (1u << MG_SUM)) mg_st_stream(q.out[MG_SUM] + i, sum);
+			if (om & (1u << MG_SIZE)) mg_st_stream(q.out[MG_SIZE] + i, size);
+			if (om & (1u << MG_EXISTS)) mg_st_stream(q.out[MG_EXISTS] + i, exists);
+		}
 	}
 	if (WMIN) mg_st_stream(q.out[MG_MIN] + i, mn);
 	if (WMAX) mg_st_stream(q.out[MG_MAX] + i, mx);
