@@ -117,7 +117,13 @@ int mg_sync(mg_ctx *ctx, void *stream);
  *   "hist_red" = 0       gdist over a dense track counts with a 16-bit load / add / store instead of one red.shared.add
  *   "prefetch" = 0       no L1 prefetch of block records / window lines in the row-query kernels
  *   "pwm_strict" = 1     PWM log-sum-exp with double-precision exp / log rounded to float (default: float expf / logf)
- *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 2^19)
+ *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 3 * 2^17)
+ *   "pipe_slots" = n     device slots (one stream each) the chunks of a host batch rotate through (default 3, 2 .. 8)
+ *   "tile_kernel" = n    which dense window kernel runs: 3 (default) k_dense_thin when two or more function groups (sums,
+ *                        extrema, quantiles) share a scan, the per-row kernels for a single group; 4 k_dense_thin always; 1 / 2
+ *                        k_dense_tile (sums to the reference's bits); 5 / 6 k_dense_pipe; 0 the per-row kernels
+ *   "inline_table" = 0   the tile kernels load chromosome sizes / array bases from the tables in HBM instead of their parameters
+ *   "hbm_budget_mb" = n  what the dense tracks of this ctx may hold; least-recently-used index groups are dropped beyond it
  *   "zero_copy" = 1      mg_h_* kernels read / write pinned host buffers directly instead of the DMA pipeline (default 0:
  *                        measured slower on B200)
  *   "l2_fetch_granularity" = 32 / 64 / 128   cudaLimitMaxL2FetchGranularity */
