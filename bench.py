@@ -323,7 +323,7 @@ def run_ours(args):
 
     # ---- per-kernel timing for the roofline (each function group alone, same stream, CUDA events) ----
     kernels = []
-    for name, funcs in (("k_dense_prefix[avg]", ["avg"]), ("k_dense_rowquery[max]", ["max"]), ("k_dense_rowquery[quantile(0.9)]", [("quantile", 0.9)]),
+    for name, funcs in (("k_dense_prefix[avg]", ["avg"]), ("k_dense_rowquery[max]", ["max"]), ("k_dense_thin[quantile(0.9)]", [("quantile", 0.9)]),
                         ("k_dense_thin[avg+max+quantile(0.9)]", FUNCS)):
         outs = d_out[:len(funcs)]
         for _ in range(3):

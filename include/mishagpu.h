@@ -120,7 +120,7 @@ int mg_sync(mg_ctx *ctx, void *stream);
  *   "pipe_chunk_rows"    rows per slot of the host-buffer pipeline (default 3 * 2^17)
  *   "pipe_slots" = n     device slots (one stream each) the chunks of a host batch rotate through (default 3, 2 .. 8)
  *   "tile_kernel" = n    which dense window kernel runs: 3 (default) k_dense_thin when two or more function groups (sums,
- *                        extrema, quantiles) share a scan, the per-row kernels for a single group; 4 k_dense_thin always; 1 / 2
+ *                        extrema, quantiles) share a scan or a quantile is asked for, the per-row kernels otherwise; 4 k_dense_thin always; 1 / 2
  *                        k_dense_tile (sums to the reference's bits); 5 / 6 k_dense_pipe; 0 the per-row kernels
  *   "inline_table" = 0   the tile kernels load chromosome sizes / array bases from the tables in HBM instead of their parameters
  *   "hbm_budget_mb" = n  what the dense tracks of this ctx may hold; least-recently-used index groups are dropped beyond it

@@ -1038,7 +1038,7 @@ static int mg_launch_dense(mg_ctx *ctx, const DenseQuery &q, bool need_sweep, cu
 	}
 	const int ngroups = (want_sum ? 1 : 0) + (want_mm ? 1 : 0) + (q.nq > 0 ? 1 : 0);
 	const bool tile_ok = ctx->tile_kernel && !ctx->force_sweep && !q.out[MG_STDDEV] && (q.nq == 0 || q.use_bw) &&
-						 (ctx->tile_kernel == 3 ? ngroups >= 2 : (need_sweep || ctx->tile_kernel == 2 || ctx->tile_kernel >= 4));
+						 (ctx->tile_kernel == 3 ? (ngroups >= 2 || q.nq > 0) : (need_sweep || ctx->tile_kernel == 2 || ctx->tile_kernel >= 4));
 	if (tile_ok) {
 		// a thread block per tile of rows, everything from shared memory (dense_tile.cuh)
 		const unsigned grid = (unsigned)mg_div_up(q.count, MG_TL_THREADS);
