@@ -176,6 +176,39 @@ def copy_bound(torch, ctx, h_in, h_out, barrier, steps):
     return dt * 1e3
 
 
+def copy_bound_chunked(torch, ctx, h_in, h_out, barrier, steps, chunk_rows=3 << 17, slots=3):
+    """The same bytes the way a pipeline has to move them: in chunks of the library's default size, a chunk's three uploads and then its three
+    downloads on the chunk's slot stream (three slots in turn) -- mg_h_pipeline's copies without its kernels. ms per step on this rank."""
+    streams = [torch.cuda.Stream() for _ in range(slots)]
+    d_in = [ctx.alloc(a.size, a.dtype) for a in h_in]
+    d_out = [ctx.alloc(a.size, a.dtype) for a in h_out]
+    n = h_in[0].size
+    vp, i64 = ctypes.c_void_p, ctypes.c_int64
+
+    def once():
+        k = 0
+        for a0 in range(0, n, chunk_rows):
+            m = min(chunk_rows, n - a0)
+            st = vp(streams[k % slots].cuda_stream)
+            k += 1
+            for d, a in zip(d_in, h_in):
+                ctx._check(ctx.lib.mg_copy_h2d(ctx.h, vp(d.ptr + a0 * a.itemsize), vp(a.ctypes.data + a0 * a.itemsize), i64(m * a.itemsize), st))
+            for d, a in zip(d_out, h_out):
+                ctx._check(ctx.lib.mg_copy_d2h(ctx.h, vp(a.ctypes.data + a0 * a.itemsize), vp(d.ptr + a0 * a.itemsize), i64(m * a.itemsize), st))
+    once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    for st in streams:
+        st.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    barrier()
+    for d in d_in + d_out:
+        d.free()
+    return dt * 1e3
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -306,6 +339,7 @@ def run_ours(args):
 
     # ---- the host link's bound for the end-to-end step (before it: the copies overwrite the result buffers) ----
     bound_ms = max_over_ranks(copy_bound(torch, ctx, [h_chrom, h_start, h_end], h_out, barrier, args.steps))
+    bound_chunked_ms = max_over_ranks(copy_bound_chunked(torch, ctx, [h_chrom, h_start, h_end], h_out, barrier, args.steps))
     # ---- end to end through the host-buffer C-ABI call: pinned host arrays in, host columns out ----
     for _ in range(2):
         dense.window_host(h_chrom, h_start, h_end, FUNCS, SSHIFT, ESHIFT, out=h_out)
@@ -390,7 +424,9 @@ def run_ours(args):
         "e2e": {"value": n_total / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n_mine * 20), "d2h_bytes_per_step": int(n_mine * 8 * len(FUNCS)),
                 "ms_per_step": e2e_s * 1e3, "api": "mg_h_dense_window (pinned host arrays in, host columns out)",
                 "copy_bound_ms": bound_ms, "copy_bound": "the step's H2D + D2H bytes alone, plain cudaMemcpyAsync on two streams from / into the "
-                "same pinned buffers, all ranks at once (max over ranks): what the host link allows", "host_numa": numa},
+                "same pinned buffers, all ranks at once (max over ranks): what the host link allows",
+                "copy_bound_chunked_ms": bound_chunked_ms, "copy_bound_chunked": "the same bytes as a pipeline has to move them: chunks of 3 * 2^17 rows, a chunk's "
+                "three uploads then its three downloads on one of three streams in turn -- the library's copies without its kernels", "host_numa": numa},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
     if cpu:
