@@ -431,6 +431,9 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if args.emulate_slice:  # development aid: the rows one rank of a larger job would take -- NOT the named workload
+        line["config"]["emulated_slice"] = args.emulate_slice
+        line["config"]["workload"] = "NOT THE NAMED WORKLOAD (--emulate-slice %s of): " % args.emulate_slice + line["config"]["workload"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
